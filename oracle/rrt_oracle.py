@@ -1,0 +1,304 @@
+"""CPU restatement of DearCaat/RRT-MIL's ``RRTEncoder.forward`` (eval mode, one bag).
+
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  The product never imports this.
+
+Parity status: the reference repository holds no tests, golden vectors or known-answer
+fixtures for this path.  The oracle is therefore pinned against
+OUTPUTS OF THE REFERENCE ITSELF, imported read-only in the build container
+(``oracle/_reference_shim.py``): ``oracle/make_golden.py`` runs the real
+``modules.rrt.RRTEncoder`` in float64 on seeded inputs and commits the results under
+``tests/golden/``; ``tests/test_oracle_golden.py`` checks both restatements below against
+those fixtures (and, when ``/root/reference`` is present, against the live reference).
+
+Two restatements of the same math, both plain PyTorch on CPU, any float dtype:
+
+* ``order="reference"`` follows the reference's operator sequence one-for-one (pad with
+  zeros after LayerNorm, gather into regions, materialise the ``[R,h,P,P]`` logit map,
+  depthwise ``Conv2d`` (k,1) on that map, the ``[R,k,P,D]`` CR-MSA tensors ...).  This is
+  what the CPU baseline in ``bench.py`` times: it issues the same ATen work as the
+  reference's own forward.
+* ``order="spec"`` is the algebraically reduced form the CUDA kernels implement (EPEG as a
+  depthwise 1-D conv on the scaled Q, CR-MSA as two rank-k products).
+
+Weights travel as a flat ``dict`` keyed by the reference's ``state_dict`` names.
+
+Reference lines followed (``/root/reference``):
+  modules/rrt.py:108-131   TransLayer.forward_trans      -> ``_residual_block``
+  modules/rrt.py:165-202   RRTEncoder.forward            -> ``encoder_forward``
+  modules/rmsa.py:28-54    region_partition / reverse    -> ``region_slot_map``
+  modules/rmsa.py:91-134   InnerAttention.forward        -> ``inner_attention``
+  modules/rmsa.py:175-230  RegionAttntion.padding/forward-> ``grid_geometry``, ``rmsa_block``
+  modules/rmsa.py:261-337  CrossRegionAttntion           -> ``crmsa_block``
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, asdict
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+LN_EPS = 1e-5  # nn.LayerNorm default, modules/rrt.py:47,139
+
+
+@dataclass
+class EncoderConfig:
+    """Constructor options of ``RRTEncoder`` that reach the hot path (modules/rrt.py:134)."""
+
+    mlp_dim: int = 512
+    region_num: int = 8
+    n_layers: int = 2
+    n_heads: int = 8
+    epeg: bool = True
+    epeg_k: int = 15
+    region_size: int = 0
+    min_region_num: int = 0
+    min_region_ratio: float = 0.0
+    qkv_bias: bool = True
+    epeg_bias: bool = True
+    cr_msa: bool = True
+    crmsa_k: int = 3
+    all_shortcut: bool = False
+    crmsa_mlp: bool = False
+    crmsa_heads: int = 8
+
+    def to_dict(self):
+        return asdict(self)
+
+
+# ----------------------------------------------------------------------------------------
+# geometry
+# ----------------------------------------------------------------------------------------
+def _ceil_sqrt(n: int) -> int:
+    return 0 if n <= 0 else math.isqrt(n - 1) + 1
+
+
+def grid_geometry(L: int, region_num: int, region_size: int = 0, min_region_num: int = 0,
+                  min_region_ratio: float = 0.0) -> Tuple[int, int, int]:
+    """(H, rs, add_length): side of the padded square grid, side of one region, pad tokens.
+
+    modules/rmsa.py:175-198 (identical code at :261-284 for CR-MSA).
+    """
+    H = _ceil_sqrt(L)
+    if region_size and region_size > 0:
+        H += (-H) % region_size
+        rs = region_size
+    else:
+        H += (-H) % region_num
+        rs = H // region_num
+    add = H * H - L
+    # "if padding much, give up region attention" escape (never fires with the 0/0 defaults)
+    if add > L / (min_region_ratio + 1e-8) or L < min_region_num:
+        H = _ceil_sqrt(L)
+        H += (-H) % 2
+        add = H * H - L
+        rs = H
+    return H, rs, add
+
+
+def region_slot_map(H: int, rs: int) -> torch.Tensor:
+    """slot -> padded token index.  Slot ``rho*P + p`` (region-major) holds grid cell
+    ``(row, col)`` with ``rho = (row//rs)*(H//rs) + col//rs`` and ``p = (row%rs)*rs + col%rs``
+    (modules/rmsa.py:37-38)."""
+    g = H // rs
+    slot = torch.arange(H * H)
+    rho, p = slot // (rs * rs), slot % (rs * rs)
+    row = (rho // g) * rs + p // rs
+    col = (rho % g) * rs + p % rs
+    return row * H + col
+
+
+# ----------------------------------------------------------------------------------------
+# building blocks
+# ----------------------------------------------------------------------------------------
+def layer_norm(x, w, b):
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + LN_EPS) * w + b
+
+
+def _to_regions(z: torch.Tensor, L: int, H: int, rs: int) -> torch.Tensor:
+    """[L,D] -> zero-pad to H*H tokens -> [R,P,D] (modules/rmsa.py:199-215)."""
+    D = z.shape[-1]
+    zp = torch.zeros(H * H, D, dtype=z.dtype)
+    zp[:L] = z
+    return zp[region_slot_map(H, rs)].view(-1, rs * rs, D)
+
+
+def _from_regions(y: torch.Tensor, L: int, H: int, rs: int) -> torch.Tensor:
+    """inverse of ``_to_regions`` followed by dropping the pad tail (modules/rmsa.py:221-228)."""
+    D = y.shape[-1]
+    out = torch.empty(H * H, D, dtype=y.dtype)
+    out[region_slot_map(H, rs)] = y.reshape(-1, D)
+    return out[:L]
+
+
+def inner_attention(xr: torch.Tensor, w: Dict[str, torch.Tensor], prefix: str, heads: int,
+                    order: str) -> torch.Tensor:
+    """Multi-head attention over each row-block of ``xr`` [B_,S,D] (modules/rmsa.py:91-134).
+
+    ``prefix`` points at the InnerAttention (``...attn.attn.``).  EPEG is applied when
+    ``prefix + 'pe.weight'`` exists.  Eval mode: both dropouts are identities.
+    """
+    B_, S, D = xr.shape
+    d = D // heads
+    qkv = xr @ w[prefix + "qkv.weight"].T
+    if prefix + "qkv.bias" in w:
+        qkv = qkv + w[prefix + "qkv.bias"]
+    qkv = qkv.view(B_, S, 3, heads, d).permute(2, 0, 3, 1, 4)  # [3,B_,h,S,d]
+    q, k, v = qkv[0] * d ** -0.5, qkv[1], qkv[2]
+    pe_w = w.get(prefix + "pe.weight")
+    if order == "reference":
+        logits = q @ k.transpose(-1, -2)  # [B_,h,S,S]
+        if pe_w is not None:
+            kk = pe_w.shape[2]
+            logits = logits + F.conv2d(logits, pe_w, w.get(prefix + "pe.bias"),
+                                       padding=(kk // 2, 0), groups=heads)
+    else:
+        if pe_w is not None:
+            kk = pe_w.shape[2]
+            # depthwise conv along the token axis of q, one tap vector per head; the conv
+            # bias is constant along the key axis and vanishes in the softmax.
+            taps = pe_w.view(heads, 1, kk).repeat_interleave(d, 0)  # [h*d,1,kk]
+            qc = q.permute(0, 1, 3, 2).reshape(B_, heads * d, S)
+            qc = F.conv1d(qc, taps, padding=kk // 2, groups=heads * d)
+            q = q + qc.view(B_, heads, d, S).permute(0, 1, 3, 2)
+        logits = q @ k.transpose(-1, -2)
+    o = torch.softmax(logits, -1) @ v  # [B_,h,S,d]
+    o = o.transpose(1, 2).reshape(B_, S, D)
+    return o @ w[prefix + "proj.weight"].T + w[prefix + "proj.bias"]
+
+
+def rmsa_block(z, w, prefix, cfg: EncoderConfig, order):
+    """RegionAttntion.forward on an already-normalised [L,D] (modules/rmsa.py:204-230)."""
+    L = z.shape[0]
+    H, rs, _ = grid_geometry(L, cfg.region_num, cfg.region_size, cfg.min_region_num,
+                             cfg.min_region_ratio)
+    y = inner_attention(_to_regions(z, L, H, rs), w, prefix + "attn.", cfg.n_heads, order)
+    return _from_regions(y, L, H, rs)
+
+
+def crmsa_block(z, w, prefix, cfg: EncoderConfig, order):
+    """CrossRegionAttntion.forward on an already-normalised [L,D] (modules/rmsa.py:290-337).
+
+    The CR-MSA TransLayer is built without ``n_region`` / ``region_size`` / ``min_region_*``
+    (modules/rrt.py:148), so it always partitions with the TransLayer defaults
+    (``n_region=8, region_size=0, min_region_num=0, min_region_ratio=0``; modules/rrt.py:44).
+    """
+    L, D = z.shape
+    H, rs, _ = grid_geometry(L, 8, 0, 0, 0.0)
+    xr = _to_regions(z, L, H, rs)  # [R,P,D]
+    if cfg.crmsa_mlp:
+        hid = torch.tanh(xr @ w[prefix + "phi.0.weight"].T)
+        logits = (hid @ w[prefix + "phi.2.weight"].T).transpose(1, 2)  # [R,k,P]
+    else:
+        logits = (xr @ w[prefix + "phi"]).transpose(1, 2)  # [R,k,P]
+    combine = logits.softmax(-1)
+    dispatch = logits.softmax(1)
+    lo = logits.min(-1, keepdim=True).values
+    hi = logits.max(-1, keepdim=True).values
+    dispatch_mm = (logits - lo) / (hi - lo + 1e-8)
+    if order == "reference":
+        lm = (xr.unsqueeze(1) * combine.unsqueeze(-1)).sum(-2)  # [R,k,P,D] -> [R,k,D]
+    else:
+        lm = combine @ xr  # [R,k,D]
+    lm = inner_attention(lm.transpose(0, 1), w, prefix + "attn.", cfg.crmsa_heads, order)
+    lm = lm.transpose(0, 1)  # [R,k,D]
+    if order == "reference":
+        y = lm.unsqueeze(2) * dispatch_mm.unsqueeze(-1)  # [R,k,P,D]
+        y = (y * dispatch.unsqueeze(-1)).sum(1)
+    else:
+        y = (dispatch_mm * dispatch).transpose(1, 2) @ lm  # [R,P,D]
+    return _from_regions(y, L, H, rs)
+
+
+def encoder_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfig,
+                    order: str = "reference") -> torch.Tensor:
+    """``RRTEncoder.forward`` for one bag ``x`` [L,D] -> [L,D] (modules/rrt.py:165-202)."""
+    assert order in ("reference", "spec")
+    assert x.dim() == 2 and x.shape[1] == cfg.mlp_dim
+    h = x
+    for i in range(cfg.n_layers - 1):
+        p = f"layers.{i}."
+        h = h + rmsa_block(layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w,
+                           p + "attn.", cfg, order)
+    if cfg.cr_msa:
+        p = "cr_msa."
+        h = h + crmsa_block(layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w,
+                            p + "attn.", cfg, order)
+    if cfg.all_shortcut:
+        h = h + x
+    return layer_norm(h, w["norm.weight"], w["norm.bias"])
+
+
+# ----------------------------------------------------------------------------------------
+# seeded synthetic weights / inputs (platform-stable: numpy legacy RandomState streams)
+# ----------------------------------------------------------------------------------------
+def weight_shapes(cfg: EncoderConfig) -> Dict[str, Tuple[int, ...]]:
+    D = cfg.mlp_dim
+    shp: Dict[str, Tuple[int, ...]] = {"norm.weight": (D,), "norm.bias": (D,)}
+
+    def attn(prefix, epeg):
+        shp[prefix + "qkv.weight"] = (3 * D, D)
+        if cfg.qkv_bias:
+            shp[prefix + "qkv.bias"] = (3 * D,)
+        shp[prefix + "proj.weight"] = (D, D)
+        shp[prefix + "proj.bias"] = (D,)
+        if epeg:
+            shp[prefix + "pe.weight"] = (cfg.n_heads, 1, cfg.epeg_k, 1)
+            if cfg.epeg_bias:
+                shp[prefix + "pe.bias"] = (cfg.n_heads,)
+
+    for i in range(cfg.n_layers - 1):
+        shp[f"layers.{i}.norm.weight"] = (D,)
+        shp[f"layers.{i}.norm.bias"] = (D,)
+        attn(f"layers.{i}.attn.attn.", cfg.epeg)
+    if cfg.cr_msa:
+        shp["cr_msa.norm.weight"] = (D,)
+        shp["cr_msa.norm.bias"] = (D,)
+        if cfg.crmsa_mlp:
+            shp["cr_msa.attn.phi.0.weight"] = (D // 4, D)
+            shp["cr_msa.attn.phi.2.weight"] = (cfg.crmsa_k, D // 4)
+        else:
+            shp["cr_msa.attn.phi"] = (D, cfg.crmsa_k)
+        attn("cr_msa.attn.attn.", False)
+    return shp
+
+
+def make_weights(cfg: EncoderConfig, seed: int, dtype=torch.float64,
+                 randomize_bias: bool = True) -> Dict[str, torch.Tensor]:
+    """Xavier-normal matrices as ``initialize_weights`` draws them (modules/rrt.py:9-23); biases
+    and LayerNorm affines are re-drawn N(0,0.1^2) / 1+N(0,0.1^2) so that bias paths are
+    exercised (the reference's zero-initialised biases would hide bias bugs)."""
+    rs = np.random.RandomState(seed)
+    out = {}
+    for name, shape in weight_shapes(cfg).items():
+        if name.endswith("norm.weight"):
+            a = 1.0 + 0.1 * rs.standard_normal(shape) if randomize_bias else np.ones(shape)
+        elif name.endswith("bias"):
+            a = 0.1 * rs.standard_normal(shape) if randomize_bias else np.zeros(shape)
+        elif name.endswith("pe.weight"):
+            fan = shape[2]  # Conv2d(h,h,(k,1),groups=h): fan_in = fan_out = k per group
+            a = rs.standard_normal(shape) * math.sqrt(2.0 / (fan + fan))
+        elif name.endswith("phi"):
+            bound = 1.0 / math.sqrt(shape[1])  # kaiming_uniform(a=sqrt5) on [D,k]: fan_in=k
+            a = rs.uniform(-bound, bound, shape)
+        else:
+            a = rs.standard_normal(shape) * math.sqrt(2.0 / (shape[0] + shape[1]))
+        out[name] = torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+    return out
+
+
+def make_bag(L: int, D: int, seed: int, dtype=torch.float64, kind: str = "randn") -> torch.Tensor:
+    rs = np.random.RandomState(seed)
+    a = rs.standard_normal((L, D))
+    if kind == "relu":  # look-alike of Linear+ReLU+Dropout(0.25) output, modules/rrt.py:208-217
+        a = np.maximum(a, 0.0) * (rs.uniform(size=(L, D)) > 0.25) / 0.75
+    return torch.from_numpy(a).to(dtype)
+
+
+def rel_err(y: torch.Tensor, ref: torch.Tensor) -> float:
+    y, ref = y.double(), ref.double()
+    return float((y - ref).norm() / ref.norm().clamp_min(1e-300))
