@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the RRTEncoder hot path: patches/sec through RRTEncoder at N=9000, D=512
+(BASELINE.json metric; workload = configs[1]'s shape, forward, eval mode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the encoder over a batch of ``--bags`` distinct synthetic bags
+(16 x 9000 x 512 fp32 = 295 MB of inputs and as much output, > the 126 MB L2, so consecutive
+iterations never find their inputs in L2).  Each rank (one process per GPU) owns its own bags;
+bags are independent, so there is no data-path collective and scaling is weak.
+
+Printed JSON (rank 0, one line): the base contract's keys plus ``roofline`` (dominant kernel,
+timed with CUDA events inside the library on the launching stream), ``cpu_baseline`` (the CPU
+oracle port timed on this box's host cores), ``e2e`` (host buffers in, host buffers out, copies
+inside the timed region), ``clocks``, ``gpu_launches`` and a per-stage breakdown.
+
+``--impl reference`` times the reference's CPU algorithm (the oracle's reference-order port --
+the reference itself is Python and /root/reference does not exist on the GPU box) on all host
+threads, one bag per step, and prints the same line with ``"impl": "reference"``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "patches/sec through RRTEncoder at N=9000 D=512"
+UNIT = "patches/s"
+N_TOKENS, DIM = 9000, 512
+ENC_KW = dict(mlp_dim=DIM, region_num=8, epeg_k=15, crmsa_k=3, n_layers=2, n_heads=8, crmsa_heads=8)
+
+
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0,
+                source="fallback (B200_PROFILING.md)")
+
+
+def encoder_flops(L):
+    """Algorithmic forward FLOPs of one bag."""
+    import math
+    D, ke, kc, g = DIM, ENC_KW["epeg_k"], ENC_KW["crmsa_k"], ENC_KW["region_num"]
+    H = math.isqrt(L - 1) + 1
+    Hr = H + (-H) % g
+    Hc = H + (-H) % 8
+    np_r, p_r, np_c = Hr * Hr, (Hr // g) ** 2, Hc * Hc
+    T = kc * 64
+    return np_r * (8 * D * D + 4 * p_r * D + 2 * ke * D) + T * (8 * D * D + 4 * 64 * D) + 6 * np_c * D * kc
+
+
+def stage_algorithmic(stage, L):
+    """(bound, algorithmic flops, algorithmic bytes) of one launch of a stage at N=9000/D=512."""
+    import math
+    D, kc = DIM, ENC_KW["crmsa_k"]
+    H = math.isqrt(L - 1) + 1
+    Hr = H + (-H) % ENC_KW["region_num"]
+    np_r, p_r = Hr * Hr, (Hr // ENC_KW["region_num"]) ** 2
+    if stage == "qkv_gemm":
+        return "tensor", 2.0 * np_r * 3 * D * D, 4.0 * (np_r * D + 3 * D * D + np_r * 3 * D)
+    if stage == "proj_gemm_residual":
+        return "tensor", 2.0 * np_r * D * D, 4.0 * (np_r * D + D * D + 2 * L * D)
+    if stage == "rmsa_attention":
+        return "tensor", 4.0 * np_r * p_r * D, 4.0 * (np_r * 3 * D + np_r * D)
+    if stage == "ln_partition":
+        return "hbm", 0.0, 4.0 * (L * D + np_r * D)
+    if stage == "crmsa_stats_logits":
+        return "hbm", 0.0, 4.0 * L * D
+    if stage == "crmsa_combine":
+        return "hbm", 0.0, 4.0 * L * D
+    if stage == "crmsa_dispatch_final_ln":
+        return "hbm", 0.0, 4.0 * 2 * L * D
+    return "latency", 0.0, 0.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_forward_factory(threads):
+    """The reference's CPU algorithm (oracle, reference operator order, fp32)."""
+    from oracle import rrt_oracle as O  # CPU baseline leg: the one place bench.py executes oracle/
+    torch.set_num_threads(threads)
+    cfg = O.EncoderConfig(**{k: v for k, v in ENC_KW.items()})
+    w = O.make_weights(cfg, 2021, dtype=torch.float32, randomize_bias=False)
+    x = O.make_bag(N_TOKENS, DIM, 7, dtype=torch.float32)
+
+    def run():
+        with torch.no_grad():
+            return O.encoder_forward(x, w, cfg, "reference")
+    return run
+
+
+def time_cpu_baseline(budget_s=12.0, min_bags=5):
+    threads = os.cpu_count() or 1
+    run = cpu_reference_forward_factory(threads)
+    for _ in range(2):
+        run()
+    times, t_end = [], time.perf_counter() + budget_s
+    while len(times) < min_bags or time.perf_counter() < t_end:
+        t0 = time.perf_counter(); run(); times.append(time.perf_counter() - t0)
+        if len(times) >= 200:
+            break
+    med = statistics.median(times)
+    return {"value": N_TOKENS / med, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{len(times)} forwards of one N={N_TOKENS} D={DIM} bag, fp32, eval, median "
+                      f"{med * 1e3:.1f} ms/bag (oracle/rrt_oracle.py reference operator order)"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    run = cpu_reference_forward_factory(threads)
+    for _ in range(max(args.warmup, 1)):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    val = N_TOKENS * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"RRTEncoder forward, one bag N={N_TOKENS} D={DIM} region_num=8 "
+                               "epeg_k=15 crmsa_k=3 per step, CPU", "bags_per_step": 1},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x 1 bag of N={N_TOKENS}"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch.distributed as dist
+    from rrt_mil_b200 import RRTEncoder, cabi
+    from rrt_mil_b200.pipeline import HostPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path for the product arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    torch.manual_seed(2021)  # reference default seed (main.py:645)
+    enc = RRTEncoder(need_init=True, **ENC_KW).to(dev).eval()
+    B = args.bags
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    bags = [torch.randn(N_TOKENS, DIM, device=dev, generator=gen) for _ in range(B)]
+    outs = [torch.empty_like(b) for b in bags]
+    patches_per_step = B * N_TOKENS
+
+    def step():
+        with torch.no_grad():
+            enc.forward_bags(bags, outs)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: device-resident inputs -------------------------------------------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = cabi.launch_count()
+    barrier(); torch.cuda.synchronize()
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    barrier()
+    launches = cabi.launch_count() - n0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * patches_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- per-stage CUDA-event timing inside the library (same stream, same workload) ----------
+    cabi.stage_timing(True)
+    for _ in range(min(args.steps, 5)):
+        step()
+    torch.cuda.synchronize()
+    stages = cabi.read_stage_timing()
+    cabi.stage_timing(False)
+    stage_avg_us = {k: v[0] / v[1] * 1e3 for k, v in stages.items()}
+    tot = sum(v[0] for v in stages.values()) or 1.0
+    stage_share = {k: v[0] / tot for k, v in stages.items()}
+    dom = max(stages, key=lambda k: stages[k][0])
+    peaks = measured_peaks()
+    bound, fl, by = stage_algorithmic(dom, N_TOKENS)
+    dur_s = stage_avg_us[dom] * 1e-6
+    if bound == "tensor":
+        peak = peaks["bf16_tflops"] / 2.0  # tf32 dense rate is half the bf16 rate
+        achieved = fl / dur_s / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": peaks["source"] + "; bf16 burst / 2 for tf32 operands",
+                "flops_per_launch": fl, "avg_launch_us": stage_avg_us[dom]}
+    else:
+        peak = peaks["hbm_gbs"]
+        achieved = by / dur_s / 1e9 if by else 0.0
+        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None, "traffic": None,
+                "peak_source": peaks["source"], "bytes_per_launch": by,
+                "avg_launch_us": stage_avg_us[dom]}
+    tr_file = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes/launch from ncu --set full
+    if os.path.isfile(tr_file):
+        roof["traffic"] = json.load(open(tr_file)).get(dom)
+
+    # ---- e2e: pinned host bags in, pinned host results out, copies inside the timed region ------
+    pipe = HostPipeline(enc, n_streams=args.e2e_streams, device=dev)
+    hx = [torch.randn(N_TOKENS, DIM).pin_memory() for _ in range(B)]
+    hy = [torch.empty(N_TOKENS, DIM).pin_memory() for _ in range(B)]
+    for _ in range(2):
+        pipe.run(hx, hy)
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        pipe.run(hx, hy)  # returns after the last device->host copy has landed
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = world * patches_per_step * e2e_steps / float(t_e2e.item())
+    bytes_step = B * N_TOKENS * DIM * 4
+
+    line = None
+    if rank == 0:
+        fl_bag = encoder_flops(N_TOKENS)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": f"RRTEncoder forward (eval), bags of N={N_TOKENS} D={DIM}, region_num=8 "
+                                   "epeg_k=15 crmsa_k=3 n_layers=2 (BASELINE configs[1] shape), fp32 I/O, "
+                                   "tf32 tensor-core operands, fp32 accumulate",
+                       "bags_per_step_per_gpu": B, "l2_policy": f"inputs larger than L2: {B} distinct bags "
+                       f"({bytes_step / 1e6:.0f} MB in, same out) per step",
+                       "parallelism": f"bag-parallel x{world}, no data-path collective"},
+            "us_per_bag": ms_total / args.steps / B * 1e3,
+            "encoder_tflops": fl_bag * B * args.steps / (ms_total * 1e-3) / 1e12,
+            "roofline": roof,
+            "stages_us_per_launch": {k: round(v, 2) for k, v in stage_avg_us.items()},
+            "stages_share": {k: round(v, 4) for k, v in stage_share.items()},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": bytes_step,
+                    "d2h_bytes_per_step": bytes_step, "steps": e2e_steps,
+                    "how": f"HostPipeline.run over pinned host bags, {args.e2e_streams} streams, wall clock"},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = time_cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bags", type=int, default=16, help="distinct bags per step per GPU")
+    ap.add_argument("--e2e-streams", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,175 @@
+/*
+ * rrt_b200.h -- C ABI of the B200-native RRTEncoder hot path (librrt_b200.so).
+ *
+ * The reference (DearCaat/RRT-MIL) is pure Python/PyTorch and has no FFI of its own; the
+ * boundary it offers is the nn.Module call  RRTEncoder(...).forward(x:[1,N,D]) -> [1,N,D]
+ * (/root/reference/modules/rrt.py:133-202).  This header is what a binding for that call
+ * binds instead of the ATen operator sequence underneath it: plain pointers and sizes, no
+ * torch types.  rrt_mil_b200/cabi.py is the ctypes binding; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer named *_dev / x / out / weights is a DEVICE pointer (fp32, row-major,
+ *     channel fastest) unless the name says host; `stream` is a cudaStream_t passed as void*;
+ *   - calls only enqueue work on `stream`; they never synchronise the device (the *_host entry
+ *     point synchronises `stream` once, at the end, because its result lives in host memory);
+ *   - the caller owns every buffer, including the workspace (size from rrt_workspace_bytes);
+ *   - return value 0 = ok, negative = error (RRT_E_*), text from rrt_last_error();
+ *   - there is no CPU fallback: without a CUDA device every compute entry returns RRT_E_CUDA.
+ */
+#ifndef RRT_B200_H_
+#define RRT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define RRT_API
+#else
+#define RRT_API __attribute__((visibility("default")))
+#endif
+
+#define RRT_ABI_VERSION 1
+#define RRT_MAX_RMSA_LAYERS 8 /* n_layers-1 R-MSA TransLayers (modules/rrt.py:143) */
+#define RRT_MAX_CRMSA_K 16    /* crmsa_k landmarks per region                         */
+#define RRT_MAX_EPEG_K 63     /* odd EPEG kernel length                               */
+
+enum {
+  RRT_OK = 0,
+  RRT_E_INVALID = -1,     /* bad argument / unsupported configuration */
+  RRT_E_WORKSPACE = -2,   /* workspace too small                      */
+  RRT_E_CUDA = -3         /* CUDA runtime error (text in rrt_last_error) */
+};
+
+/* math_mode: what the tensor-core contractions compute in.  I/O is always fp32. */
+enum {
+  RRT_MATH_TF32 = 0 /* tf32 operands, fp32 accumulate: meets the 1e-3 rel "fp32" bar */
+};
+
+/* Constructor options of RRTEncoder that reach the hot path
+ * (modules/rrt.py:134; same names, same defaults on the Python side). */
+typedef struct rrt_config {
+  int32_t dim;              /* mlp_dim; multiple of 128, <= 1024                       */
+  int32_t n_rmsa_layers;    /* n_layers - 1                                            */
+  int32_t n_heads;          /* heads of the R-MSA layers                               */
+  int32_t region_num;       /* regions per side of the R-MSA grid                      */
+  int32_t region_size;      /* >0: fixed region side instead (modules/rmsa.py:177-182) */
+  int32_t min_region_num;   /* "give up region attention" escape, modules/rmsa.py:193  */
+  double min_region_ratio;  /*   "                                                     */
+  int32_t epeg;             /* EPEG conv on the logit map on/off                       */
+  int32_t epeg_k;           /* odd kernel length                                       */
+  int32_t qkv_bias;
+  int32_t cr_msa;           /* CR-MSA layer on/off                                     */
+  int32_t crmsa_k;
+  int32_t crmsa_heads;
+  int32_t crmsa_mlp;        /* phi = Linear-tanh-Linear instead of a [D,k] matrix      */
+  int32_t all_shortcut;
+  int32_t math_mode;        /* RRT_MATH_*                                              */
+} rrt_config;
+
+/* One InnerAttention (modules/rmsa.py:56-89).  qkv_b may be NULL (qkv_bias=False);
+ * pe_w is the depthwise EPEG taps [heads, epeg_k] (= pe.weight[h,0,:,0]) or NULL.
+ * pe.bias is not needed: it is constant along the softmax axis. */
+typedef struct rrt_attn_weights {
+  const float* qkv_w;  /* [3D, D] */
+  const float* qkv_b;  /* [3D] or NULL */
+  const float* proj_w; /* [D, D] */
+  const float* proj_b; /* [D] */
+  const float* pe_w;   /* [heads, epeg_k] or NULL */
+} rrt_attn_weights;
+
+/* state_dict of one RRTEncoder, by reference name. */
+typedef struct rrt_weights {
+  const float* norm_w; /* norm.weight [D] (final LayerNorm) */
+  const float* norm_b;
+  const float* layer_norm_w[RRT_MAX_RMSA_LAYERS]; /* layers.i.norm.weight */
+  const float* layer_norm_b[RRT_MAX_RMSA_LAYERS];
+  rrt_attn_weights layer_attn[RRT_MAX_RMSA_LAYERS]; /* layers.i.attn.attn.* */
+  const float* cr_norm_w; /* cr_msa.norm.* */
+  const float* cr_norm_b;
+  const float* cr_phi;    /* cr_msa.attn.phi [D, k]           (crmsa_mlp = 0) */
+  const float* cr_phi_w1; /* cr_msa.attn.phi.0.weight [D/4,D] (crmsa_mlp = 1) */
+  const float* cr_phi_w2; /* cr_msa.attn.phi.2.weight [k,D/4] (crmsa_mlp = 1) */
+  rrt_attn_weights cr_attn; /* cr_msa.attn.attn.* (pe_w NULL) */
+} rrt_weights;
+
+/* ---- housekeeping ------------------------------------------------------------------- */
+RRT_API int rrt_abi_version(void);
+RRT_API const char* rrt_last_error(void);
+
+/* Padded square grid of a bag of L tokens: H = side, rs = region side
+ * (modules/rmsa.py:175-198).  Pure host arithmetic. */
+RRT_API int rrt_grid_geometry(int64_t L, int32_t region_num, int32_t region_size,
+                              int32_t min_region_num, double min_region_ratio, int32_t* H,
+                              int32_t* rs);
+
+/* Bytes of device workspace rrt_encoder_forward needs for a bag of L tokens. */
+RRT_API int rrt_workspace_bytes(const rrt_config* cfg, int64_t L, size_t* bytes);
+
+/* ---- the hot path ------------------------------------------------------------------- */
+/* RRTEncoder.forward for one bag, eval mode: x [L, D] -> out [L, D]
+ * (modules/rrt.py:165-202).  x and out may not alias. */
+RRT_API int rrt_encoder_forward(const rrt_config* cfg, const rrt_weights* w, const float* x,
+                                float* out, int64_t L, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
+/* n_bags independent bags back to back on `stream` (one bag per forward, exactly as n_bags calls
+ * of rrt_encoder_forward; the workspace is reused and must fit the longest bag).  xs / outs / Ls
+ * are HOST arrays of device pointers / lengths. */
+RRT_API int rrt_encoder_forward_batch(const rrt_config* cfg, const rrt_weights* w,
+                                      const float* const* xs, float* const* outs,
+                                      const int64_t* Ls, int32_t n_bags, void* workspace,
+                                      size_t workspace_bytes, void* stream);
+
+/* Same call with HOST bags (pinned or pageable): copies x_host to x_dev, runs the forward,
+ * copies the result back to out_host, all on `stream`, then synchronises `stream`.
+ * x_dev / out_dev are caller-owned device staging buffers of L*D floats each. */
+RRT_API int rrt_encoder_forward_host(const rrt_config* cfg, const rrt_weights* w,
+                                     const float* x_host, float* out_host, float* x_dev,
+                                     float* out_dev, int64_t L, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+
+/* ---- the blocks of the path, exported so each can be checked against the oracle -------- */
+/* x1 = x + RegionAttntion(LayerNorm(x))   (modules/rrt.py:123-125, modules/rmsa.py:204-230) */
+RRT_API int rrt_rmsa_block_forward(const rrt_config* cfg, const float* norm_w,
+                                   const float* norm_b, const rrt_attn_weights* attn,
+                                   const float* x, float* x1, int64_t L, void* workspace,
+                                   size_t workspace_bytes, void* stream);
+
+/* y = x1 + CrossRegionAttntion(LayerNorm(x1)) (+ x0 if cfg->all_shortcut and x0 != NULL);
+ * out = LayerNorm(y; final_norm) if final_norm_w != NULL else y
+ * (modules/rrt.py:190-195, modules/rmsa.py:290-337). */
+RRT_API int rrt_crmsa_block_forward(const rrt_config* cfg, const rrt_weights* w,
+                                    const float* x1, const float* x0, float* out, int64_t L,
+                                    int32_t apply_final_norm, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
+/* c[M,N] = a[M,K] @ w[N,K]^T + bias[N]   (nn.Linear; bias may be NULL).  K % 32 == 0. */
+RRT_API int rrt_linear_forward(const float* a, const float* w, const float* bias, float* c,
+                               int64_t M, int32_t N, int32_t K, void* stream);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------- */
+/* Kernel launches issued by this library in this process so far. */
+RRT_API int64_t rrt_launch_count(void);
+
+/* Stage timing: when enabled, every kernel of rrt_encoder_forward (and of the block entry points)
+ * is bracketed by CUDA events on the launching stream.  rrt_stage_timing_read sums the finished
+ * intervals per stage since the last enable; the caller synchronises the stream first.  Stages
+ * are numbered 0 .. rrt_stage_count()-1 in pipeline order; rrt_stage_name gives the kernel role. */
+RRT_API int rrt_stage_timing_enable(int32_t on);
+RRT_API int32_t rrt_stage_count(void);
+RRT_API const char* rrt_stage_name(int32_t stage);
+RRT_API int rrt_stage_timing_read(int32_t stage, double* total_ms, int64_t* launches);
+
+/* out[L,D] = LayerNorm(x[L,D]) (eps 1e-5). */
+RRT_API int rrt_layernorm_forward(const float* x, const float* gamma, const float* beta,
+                                  float* out, int64_t L, int32_t D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRT_B200_H_ */

@@ -114,25 +114,23 @@ def region_slot_map(H: int, rs: int) -> torch.Tensor:
 # building blocks
 # ----------------------------------------------------------------------------------------
 def layer_norm(x, w, b):
-    mu = x.mean(-1, keepdim=True)
-    var = ((x - mu) ** 2).mean(-1, keepdim=True)
-    return (x - mu) / torch.sqrt(var + LN_EPS) * w + b
+    # the same ATen operator nn.LayerNorm dispatches to (biased variance, eps inside the sqrt)
+    return F.layer_norm(x, (x.shape[-1],), w, b, LN_EPS)
 
 
 def _to_regions(z: torch.Tensor, L: int, H: int, rs: int) -> torch.Tensor:
     """[L,D] -> zero-pad to H*H tokens -> [R,P,D] (modules/rmsa.py:199-215)."""
-    D = z.shape[-1]
-    zp = torch.zeros(H * H, D, dtype=z.dtype)
-    zp[:L] = z
-    return zp[region_slot_map(H, rs)].view(-1, rs * rs, D)
+    D, g = z.shape[-1], H // rs
+    zp = torch.cat([z, torch.zeros(H * H - L, D, dtype=z.dtype)]) if H * H > L else z
+    # grid (row, col) -> (region row, row in region, region col, col in region); the slot order of
+    # ``region_slot_map`` is exactly this axis swap
+    return zp.view(g, rs, g, rs, D).transpose(1, 2).reshape(g * g, rs * rs, D)
 
 
 def _from_regions(y: torch.Tensor, L: int, H: int, rs: int) -> torch.Tensor:
     """inverse of ``_to_regions`` followed by dropping the pad tail (modules/rmsa.py:221-228)."""
-    D = y.shape[-1]
-    out = torch.empty(H * H, D, dtype=y.dtype)
-    out[region_slot_map(H, rs)] = y.reshape(-1, D)
-    return out[:L]
+    D, g = y.shape[-1], H // rs
+    return y.reshape(g, g, rs, rs, D).transpose(1, 2).reshape(H * H, D)[:L]
 
 
 def inner_attention(xr: torch.Tensor, w: Dict[str, torch.Tensor], prefix: str, heads: int,
@@ -144,9 +142,7 @@ def inner_attention(xr: torch.Tensor, w: Dict[str, torch.Tensor], prefix: str, h
     """
     B_, S, D = xr.shape
     d = D // heads
-    qkv = xr @ w[prefix + "qkv.weight"].T
-    if prefix + "qkv.bias" in w:
-        qkv = qkv + w[prefix + "qkv.bias"]
+    qkv = F.linear(xr, w[prefix + "qkv.weight"], w.get(prefix + "qkv.bias"))
     qkv = qkv.view(B_, S, 3, heads, d).permute(2, 0, 3, 1, 4)  # [3,B_,h,S,d]
     q, k, v = qkv[0] * d ** -0.5, qkv[1], qkv[2]
     pe_w = w.get(prefix + "pe.weight")
@@ -168,7 +164,7 @@ def inner_attention(xr: torch.Tensor, w: Dict[str, torch.Tensor], prefix: str, h
         logits = q @ k.transpose(-1, -2)
     o = torch.softmax(logits, -1) @ v  # [B_,h,S,d]
     o = o.transpose(1, 2).reshape(B_, S, D)
-    return o @ w[prefix + "proj.weight"].T + w[prefix + "proj.bias"]
+    return F.linear(o, w[prefix + "proj.weight"], w[prefix + "proj.bias"])
 
 
 def rmsa_block(z, w, prefix, cfg: EncoderConfig, order):

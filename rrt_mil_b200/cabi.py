@@ -1,0 +1,148 @@
+"""ctypes binding of librrt_b200.so -- one-to-one with include/rrt_b200.h.
+
+The library is the product's only compute path.  It is loaded lazily on first use and there is no
+fallback: a missing or stale library raises ``RuntimeError`` telling the user to build it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librrt_b200.so")
+
+RRT_ABI_VERSION = 1
+RRT_MAX_RMSA_LAYERS = 8
+RRT_MAX_CRMSA_K = 16
+RRT_MAX_EPEG_K = 63
+RRT_OK, RRT_E_INVALID, RRT_E_WORKSPACE, RRT_E_CUDA = 0, -1, -2, -3
+RRT_MATH_TF32 = 0
+
+c_float_p = C.c_void_p  # device pointers travel as integers
+
+
+class RrtConfig(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("n_rmsa_layers", C.c_int32), ("n_heads", C.c_int32),
+        ("region_num", C.c_int32), ("region_size", C.c_int32), ("min_region_num", C.c_int32),
+        ("min_region_ratio", C.c_double), ("epeg", C.c_int32), ("epeg_k", C.c_int32),
+        ("qkv_bias", C.c_int32), ("cr_msa", C.c_int32), ("crmsa_k", C.c_int32),
+        ("crmsa_heads", C.c_int32), ("crmsa_mlp", C.c_int32), ("all_shortcut", C.c_int32),
+        ("math_mode", C.c_int32),
+    ]
+
+
+class RrtAttnWeights(C.Structure):
+    _fields_ = [("qkv_w", c_float_p), ("qkv_b", c_float_p), ("proj_w", c_float_p),
+                ("proj_b", c_float_p), ("pe_w", c_float_p)]
+
+
+class RrtWeights(C.Structure):
+    _fields_ = [
+        ("norm_w", c_float_p), ("norm_b", c_float_p),
+        ("layer_norm_w", c_float_p * RRT_MAX_RMSA_LAYERS),
+        ("layer_norm_b", c_float_p * RRT_MAX_RMSA_LAYERS),
+        ("layer_attn", RrtAttnWeights * RRT_MAX_RMSA_LAYERS),
+        ("cr_norm_w", c_float_p), ("cr_norm_b", c_float_p), ("cr_phi", c_float_p),
+        ("cr_phi_w1", c_float_p), ("cr_phi_w2", c_float_p), ("cr_attn", RrtAttnWeights),
+    ]
+
+
+# name -> (restype, argtypes); must list every RRT_API symbol of include/rrt_b200.h
+_P = C.c_void_p
+SIGNATURES = {
+    "rrt_abi_version": (C.c_int, []),
+    "rrt_last_error": (C.c_char_p, []),
+    "rrt_grid_geometry": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "rrt_workspace_bytes": (C.c_int, [C.POINTER(RrtConfig), C.c_int64, C.POINTER(C.c_size_t)]),
+    "rrt_encoder_forward": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P,
+                                      C.c_int64, _P, C.c_size_t, _P]),
+    "rrt_encoder_forward_batch": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights),
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_int64), C.c_int32, _P, C.c_size_t, _P]),
+    "rrt_encoder_forward_host": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P, _P,
+                                           _P, C.c_int64, _P, C.c_size_t, _P]),
+    "rrt_rmsa_block_forward": (C.c_int, [C.POINTER(RrtConfig), _P, _P, C.POINTER(RrtAttnWeights),
+                                         _P, _P, C.c_int64, _P, C.c_size_t, _P]),
+    "rrt_crmsa_block_forward": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P, _P,
+                                          C.c_int64, C.c_int32, _P, C.c_size_t, _P]),
+    "rrt_launch_count": (C.c_int64, []),
+    "rrt_stage_timing_enable": (C.c_int, [C.c_int32]),
+    "rrt_stage_count": (C.c_int32, []),
+    "rrt_stage_name": (C.c_char_p, [C.c_int32]),
+    "rrt_stage_timing_read": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "rrt_linear_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "rrt_layernorm_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class RrtError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the C-ABI library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python -m rrt_mil_b200.build` "
+                    "(there is no CPU or PyTorch fallback for the RRTEncoder hot path)")
+            handle = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(handle, name)  # AttributeError if the .so is stale
+                fn.restype, fn.argtypes = res, args
+            if handle.rrt_abi_version() != RRT_ABI_VERSION:
+                raise RuntimeError("librrt_b200.so ABI version mismatch: rebuild it")
+            _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != RRT_OK:
+        msg = lib().rrt_last_error().decode("utf-8", "replace")
+        exc = {RRT_E_INVALID: ValueError, RRT_E_WORKSPACE: RrtError, RRT_E_CUDA: RrtError}.get(rc, RrtError)
+        raise exc(f"{what or 'librrt_b200'} failed ({rc}): {msg}")
+
+
+def grid_geometry(L: int, region_num: int, region_size: int = 0, min_region_num: int = 0,
+                  min_region_ratio: float = 0.0):
+    H, rs = C.c_int32(), C.c_int32()
+    check(lib().rrt_grid_geometry(L, region_num, region_size, min_region_num, min_region_ratio,
+                                  C.byref(H), C.byref(rs)), "rrt_grid_geometry")
+    return H.value, rs.value
+
+
+def workspace_bytes(cfg: RrtConfig, L: int) -> int:
+    n = C.c_size_t()
+    check(lib().rrt_workspace_bytes(C.byref(cfg), L, C.byref(n)), "rrt_workspace_bytes")
+    return n.value
+
+
+def stage_timing(enable: bool) -> None:
+    check(lib().rrt_stage_timing_enable(int(enable)), "rrt_stage_timing_enable")
+
+
+def read_stage_timing() -> dict:
+    """{stage name: (total ms, intervals)} accumulated since ``stage_timing(True)``; synchronise the
+    stream(s) first."""
+    out = {}
+    L = lib()
+    for i in range(L.rrt_stage_count()):
+        ms, n = C.c_double(), C.c_int64()
+        check(L.rrt_stage_timing_read(i, C.byref(ms), C.byref(n)), "rrt_stage_timing_read")
+        if n.value:
+            out[L.rrt_stage_name(i).decode()] = (ms.value, n.value)
+    return out
+
+
+def launch_count() -> int:
+    return int(lib().rrt_launch_count())

@@ -1,0 +1,464 @@
+// C ABI of librrt_b200.so (include/rrt_b200.h): argument checking, workspace carving and the
+// kernel sequence of RRTEncoder.forward.  No torch types, no host synchronisation (except the
+// *_host entry, whose result lives in host memory).
+#include "../../include/rrt_b200.h"
+#include "kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+int fail_cuda(cudaError_t e, const char* where) {
+  return fail(RRT_E_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define RRT_CUDA(call, where)                          \
+  do {                                                 \
+    cudaError_t e__ = (call);                          \
+    if (e__ != cudaSuccess) return fail_cuda(e__, where); \
+  } while (0)
+
+// ---- measurement hooks ---------------------------------------------------------------------
+enum Stage {
+  kStLnPartition = 0, kStQkvGemm, kStRmsaAttn, kStProjGemm, kStCrLogits, kStCrMlp, kStCrCombine,
+  kStLmQkv, kStLmAttn, kStLmProj, kStCrDispatch, kStFinalLn, kStOther, kStCount
+};
+const char* const kStageNames[kStCount] = {
+    "ln_partition", "qkv_gemm", "rmsa_attention", "proj_gemm_residual", "crmsa_stats_logits",
+    "crmsa_mlp_phi", "crmsa_combine", "landmark_qkv_gemm", "landmark_attention",
+    "landmark_proj_gemm", "crmsa_dispatch_final_ln", "final_layernorm", "other"};
+
+std::atomic<int64_t> g_launches{0};
+std::atomic<bool> g_timing{false};
+std::mutex g_timing_mu;
+struct Interval { int stage; cudaEvent_t a, b; };
+std::vector<Interval> g_pending;
+std::vector<cudaEvent_t> g_event_pool;
+double g_stage_ms[kStCount];
+int64_t g_stage_n[kStCount];
+
+cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct StageScope {
+  int stage; cudaStream_t st; cudaEvent_t a = nullptr; bool on;
+  StageScope(int stage_, cudaStream_t st_, int n_launches = 1) : stage(stage_), st(st_) {
+    g_launches.fetch_add(n_launches, std::memory_order_relaxed);
+    on = g_timing.load(std::memory_order_relaxed);
+    if (on) { std::lock_guard<std::mutex> l(g_timing_mu); a = take_event(); cudaEventRecord(a, st); }
+  }
+  ~StageScope() {
+    if (!on) return;
+    std::lock_guard<std::mutex> l(g_timing_mu);
+    cudaEvent_t b = take_event();
+    cudaEventRecord(b, st);
+    g_pending.push_back({stage, a, b});
+  }
+};
+
+void drain_pending() {  // caller holds g_timing_mu
+  std::vector<Interval> keep;
+  for (auto& iv : g_pending) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventElapsedTime(&ms, iv.a, iv.b);
+    if (e == cudaErrorNotReady) { keep.push_back(iv); continue; }
+    if (e == cudaSuccess) { g_stage_ms[iv.stage] += ms; g_stage_n[iv.stage] += 1; }
+    else cudaGetLastError();
+    g_event_pool.push_back(iv.a);
+    g_event_pool.push_back(iv.b);
+  }
+  g_pending.swap(keep);
+}
+
+int ceil_sqrt(int64_t n) {
+  if (n <= 0) return 0;
+  int64_t r = (int64_t)std::floor(std::sqrt((double)(n - 1)));
+  while (r * r > n - 1) --r;
+  while ((r + 1) * (r + 1) <= n - 1) ++r;
+  return (int)r + 1;  // isqrt(n-1) + 1 == ceil(sqrt(n))
+}
+
+// modules/rmsa.py:175-198
+bool make_grid(int64_t L, int region_num, int region_size, int min_region_num,
+               double min_region_ratio, rrt::Grid* out) {
+  if (L < 1 || L > (1 << 28)) return false;
+  int H = ceil_sqrt(L), rs;
+  if (region_size > 0) {
+    H += ((-H) % region_size + region_size) % region_size;
+    rs = region_size;
+  } else {
+    if (region_num < 1) return false;
+    H += ((-H) % region_num + region_num) % region_num;
+    rs = H / region_num;
+  }
+  int64_t add = (int64_t)H * H - L;
+  if ((double)add > (double)L / (min_region_ratio + 1e-8) || L < min_region_num) {
+    H = ceil_sqrt(L);
+    H += H % 2;
+    rs = H;
+  }
+  if (rs < 1 || (int64_t)H * H > (1LL << 30)) return false;
+  out->L = (int)L;
+  out->H = H;
+  out->rs = rs;
+  out->g = H / rs;
+  out->P = rs * rs;
+  out->R = out->g * out->g;
+  out->Np = H * H;
+  return true;
+}
+
+bool crmsa_grid(int64_t L, rrt::Grid* out) {
+  // the CR-MSA TransLayer is always built with the defaults n_region=8, region_size=0,
+  // min_region_num=0, min_region_ratio=0 (modules/rrt.py:148 vs :44)
+  return make_grid(L, 8, 0, 0, 0.0, out);
+}
+
+int check_config(const rrt_config* c) {
+  if (!c) return fail(RRT_E_INVALID, "cfg is NULL");
+  if (c->dim < 128 || c->dim > 1024 || c->dim % 128)
+    return fail(RRT_E_INVALID, "dim must be a multiple of 128 in [128,1024]");
+  if (c->n_rmsa_layers < 0 || c->n_rmsa_layers > RRT_MAX_RMSA_LAYERS)
+    return fail(RRT_E_INVALID, "n_rmsa_layers out of range");
+  if (c->n_rmsa_layers > 0) {
+    if (c->n_heads < 1 || c->dim % c->n_heads) return fail(RRT_E_INVALID, "dim % n_heads != 0");
+    int hd = c->dim / c->n_heads;
+    if (hd != 32 && hd != 64 && hd != 128)
+      return fail(RRT_E_INVALID, "R-MSA head_dim must be 32, 64 or 128");
+    if (c->epeg && (c->epeg_k < 1 || c->epeg_k > RRT_MAX_EPEG_K || c->epeg_k % 2 == 0))
+      return fail(RRT_E_INVALID, "epeg_k must be odd and <= 63 (the reference fails on even k)");
+    if (c->region_size <= 0 && c->region_num < 1) return fail(RRT_E_INVALID, "region_num < 1");
+  }
+  if (c->cr_msa) {
+    if (c->crmsa_k < 1 || c->crmsa_k > RRT_MAX_CRMSA_K)
+      return fail(RRT_E_INVALID, "crmsa_k out of range");
+    if (c->crmsa_heads < 1 || c->dim % c->crmsa_heads || (c->dim / c->crmsa_heads) % 32)
+      return fail(RRT_E_INVALID, "CR-MSA head_dim must be a multiple of 32");
+  }
+  if (c->math_mode != RRT_MATH_TF32) return fail(RRT_E_INVALID, "unknown math_mode");
+  return RRT_OK;
+}
+
+// ---- workspace ----------------------------------------------------------------------------
+struct Workspace {
+  float* z;        // [Np_r, D]   LN'd, padded, region-ordered tokens (also z2 for crmsa_mlp)
+  float* qkv;      // [Np_r, 3D]
+  float* o;        // [Np_r, D]
+  float* xa;       // [L, D] residual stream ping
+  float* xb;       // [L, D] residual stream pong
+  float2* stats;   // [Np_c]
+  float* logits;   // [Np_c, k]
+  float2* rstat;   // [R_c, k]
+  float* lm;       // [k*R_c, D]
+  float* lqkv;     // [k*R_c, 3D]
+  float* lo;       // [k*R_c, D]
+  float* lout;     // [k*R_c, D]
+  float* hidden;   // [Np_c, D/4] (crmsa_mlp)
+  size_t bytes;
+};
+
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+bool carve(const rrt_config* c, int64_t L, void* base, Workspace* ws) {
+  rrt::Grid gr{}, gc{};
+  size_t np_r = 0;
+  if (c->n_rmsa_layers > 0) {
+    if (!make_grid(L, c->region_num, c->region_size, c->min_region_num, c->min_region_ratio, &gr))
+      return false;
+    np_r = gr.Np;
+  }
+  size_t np_c = 0;
+  if (c->cr_msa) {
+    if (!crmsa_grid(L, &gc)) return false;
+    np_c = gc.Np;
+  }
+  const size_t D = c->dim, k = c->cr_msa ? c->crmsa_k : 0, T = k * 64;
+  size_t np_z = np_r;
+  if (c->cr_msa && c->crmsa_mlp && np_c > np_z) np_z = np_c;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t nbytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(nbytes);
+    return r;
+  };
+  ws->z = (float*)take(np_z * D * 4);
+  ws->qkv = (float*)take(np_r * 3 * D * 4);
+  ws->o = (float*)take(np_r * D * 4);
+  ws->xa = (float*)take((size_t)L * D * 4);
+  ws->xb = (float*)take((size_t)L * D * 4);
+  ws->stats = (float2*)take(np_c * 8);
+  ws->logits = (float*)take(np_c * k * 4);
+  ws->rstat = (float2*)take(64 * k * 8);
+  ws->lm = (float*)take(T * D * 4);
+  ws->lqkv = (float*)take(T * 3 * D * 4);
+  ws->lo = (float*)take(T * D * 4);
+  ws->lout = (float*)take(T * D * 4);
+  ws->hidden = (float*)take((c->cr_msa && c->crmsa_mlp) ? np_c * (D / 4) * 4 : 0);
+  ws->bytes = off + 256;
+  return true;
+}
+
+int check_ws(const rrt_config* cfg, int64_t L, void* workspace, size_t workspace_bytes,
+             Workspace* ws) {
+  if (!carve(cfg, L, workspace, ws)) return fail(RRT_E_INVALID, "bad bag length / geometry");
+  if (!workspace || workspace_bytes < ws->bytes) return fail(RRT_E_WORKSPACE, "workspace too small");
+  if (((uintptr_t)workspace) & 255) return fail(RRT_E_INVALID, "workspace must be 256-byte aligned");
+  return RRT_OK;
+}
+
+// ---- blocks -------------------------------------------------------------------------------
+int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
+               const rrt_attn_weights* a, const float* x, float* x1, int64_t L, Workspace& ws,
+               cudaStream_t st) {
+  rrt::Grid g{};
+  if (!make_grid(L, c->region_num, c->region_size, c->min_region_num, c->min_region_ratio, &g))
+    return fail(RRT_E_INVALID, "bad geometry");
+  const int D = c->dim;
+  { StageScope s_(kStLnPartition, st); RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws.z, g, D, false, st), "ln_partition"); }
+  rrt::GemmEpilogue e1;
+  e1.bias = c->qkv_bias ? a->qkv_b : nullptr;
+  { StageScope s_(kStQkvGemm, st); RRT_CUDA(rrt::launch_gemm_mma(ws.z, a->qkv_w, ws.qkv, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
+  { StageScope s_(kStRmsaAttn, st);
+    RRT_CUDA(rrt::launch_rmsa_attention(ws.qkv, c->epeg ? a->pe_w : nullptr, ws.o, g, D, c->n_heads,
+                                        c->epeg_k, st), "rmsa attention"); }
+  rrt::GemmEpilogue e2;
+  e2.mode = rrt::kEpiResidualUnpart;
+  e2.bias = a->proj_b;
+  e2.resid = x;
+  e2.grid = g;
+  { StageScope s_(kStProjGemm, st); RRT_CUDA(rrt::launch_gemm_mma(ws.o, a->proj_w, x1, g.Np, D, D, e2, st), "proj gemm"); }
+  return RRT_OK;
+}
+
+int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, const float* x0,
+                float* out, int64_t L, bool final_norm, Workspace& ws, cudaStream_t st) {
+  rrt::Grid g{};
+  if (!crmsa_grid(L, &g)) return fail(RRT_E_INVALID, "bad geometry");
+  const int D = c->dim, k = c->crmsa_k, T = k * g.R;
+  if (c->crmsa_mlp) {
+    if (!w->cr_phi_w1 || !w->cr_phi_w2) return fail(RRT_E_INVALID, "crmsa_mlp weights missing");
+    { StageScope s_(kStCrLogits, st);
+      RRT_CUDA(rrt::launch_crmsa_stats_logits(x1, w->cr_norm_w, w->cr_norm_b, nullptr, ws.stats,
+                                              nullptr, g, D, k, st), "crmsa stats"); }
+    StageScope s_mlp(kStCrMlp, st, 3);
+    RRT_CUDA(rrt::launch_ln_partition(x1, w->cr_norm_w, w->cr_norm_b, ws.z, g, D, false, st),
+             "crmsa ln_partition");
+    rrt::GemmEpilogue eh;
+    eh.mode = rrt::kEpiTanh;
+    RRT_CUDA(rrt::launch_gemm_mma(ws.z, w->cr_phi_w1, ws.hidden, g.Np, D / 4, D, eh, st), "phi.0");
+    RRT_CUDA(rrt::launch_crmsa_mlp_logits(ws.hidden, w->cr_phi_w2, ws.logits, g.Np, D / 4, k, st),
+             "phi.2");
+  } else {
+    if (!w->cr_phi) return fail(RRT_E_INVALID, "cr_phi missing");
+    StageScope s_(kStCrLogits, st);
+    RRT_CUDA(rrt::launch_crmsa_stats_logits(x1, w->cr_norm_w, w->cr_norm_b, w->cr_phi, ws.stats,
+                                            ws.logits, g, D, k, st), "crmsa logits");
+  }
+  { StageScope s_(kStCrCombine, st);
+    RRT_CUDA(rrt::launch_crmsa_combine(x1, w->cr_norm_w, w->cr_norm_b, ws.stats, ws.logits, ws.lm,
+                                       ws.rstat, g, D, k, st), "crmsa combine"); }
+  rrt::GemmEpilogue e1;
+  e1.bias = c->qkv_bias ? w->cr_attn.qkv_b : nullptr;
+  { StageScope s_(kStLmQkv, st);
+    RRT_CUDA(rrt::launch_gemm_mma(ws.lm, w->cr_attn.qkv_w, ws.lqkv, T, 3 * D, D, e1, st), "landmark qkv"); }
+  { StageScope s_(kStLmAttn, st);
+    RRT_CUDA(rrt::launch_landmark_attention(ws.lqkv, ws.lo, k, g.R, D, c->crmsa_heads, st),
+             "landmark attention"); }
+  rrt::GemmEpilogue e2;
+  e2.bias = w->cr_attn.proj_b;
+  { StageScope s_(kStLmProj, st);
+    RRT_CUDA(rrt::launch_gemm_mma(ws.lo, w->cr_attn.proj_w, ws.lout, T, D, D, e2, st), "landmark proj"); }
+  { StageScope s_(kStCrDispatch, st);
+    RRT_CUDA(rrt::launch_crmsa_dispatch(x1, x0, ws.logits, ws.rstat, ws.lout,
+                                        final_norm ? w->norm_w : nullptr,
+                                        final_norm ? w->norm_b : nullptr, out, g, D, k, st),
+             "crmsa dispatch"); }
+  return RRT_OK;
+}
+
+int encoder_forward(const rrt_config* cfg, const rrt_weights* w, const float* x, float* out,
+                    int64_t L, Workspace& ws, cudaStream_t st) {
+  const int D = cfg->dim;
+  const float* cur = x;
+  for (int i = 0; i < cfg->n_rmsa_layers; ++i) {
+    float* nxt = (cur == ws.xa) ? ws.xb : ws.xa;
+    int rc = rmsa_block(cfg, w->layer_norm_w[i], w->layer_norm_b[i], &w->layer_attn[i], cur, nxt, L,
+                        ws, st);
+    if (rc) return rc;
+    cur = nxt;
+  }
+  const float* x0 = cfg->all_shortcut ? x : nullptr;
+  if (cfg->cr_msa) return crmsa_block(cfg, w, cur, x0, out, L, true, ws, st);
+  { StageScope s_(kStFinalLn, st); RRT_CUDA(rrt::launch_add_layernorm(cur, x0, w->norm_w, w->norm_b, out, (int)L, D, st), "final norm"); }
+  return RRT_OK;
+}
+
+}  // namespace
+
+// ===============================================================================================
+extern "C" {
+
+RRT_API int rrt_abi_version(void) { return RRT_ABI_VERSION; }
+RRT_API const char* rrt_last_error(void) { return g_last_error.c_str(); }
+
+RRT_API int rrt_grid_geometry(int64_t L, int32_t region_num, int32_t region_size,
+                              int32_t min_region_num, double min_region_ratio, int32_t* H,
+                              int32_t* rs) {
+  rrt::Grid g{};
+  if (!H || !rs) return fail(RRT_E_INVALID, "NULL output");
+  if (!make_grid(L, region_num, region_size, min_region_num, min_region_ratio, &g))
+    return fail(RRT_E_INVALID, "bad bag length / geometry");
+  *H = g.H;
+  *rs = g.rs;
+  return RRT_OK;
+}
+
+RRT_API int rrt_workspace_bytes(const rrt_config* cfg, int64_t L, size_t* bytes) {
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (!bytes) return fail(RRT_E_INVALID, "NULL output");
+  Workspace ws{};
+  if (!carve(cfg, L, nullptr, &ws)) return fail(RRT_E_INVALID, "bad bag length / geometry");
+  *bytes = ws.bytes;
+  return RRT_OK;
+}
+
+RRT_API int rrt_encoder_forward(const rrt_config* cfg, const rrt_weights* w, const float* x,
+                                float* out, int64_t L, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (!w || !x || !out) return fail(RRT_E_INVALID, "NULL pointer");
+  if (x == out) return fail(RRT_E_INVALID, "x and out may not alias");
+  Workspace ws{};
+  rc = check_ws(cfg, L, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  return encoder_forward(cfg, w, x, out, L, ws, (cudaStream_t)stream);
+}
+
+RRT_API int rrt_encoder_forward_batch(const rrt_config* cfg, const rrt_weights* w,
+                                      const float* const* xs, float* const* outs,
+                                      const int64_t* Ls, int32_t n_bags, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (!w || !xs || !outs || !Ls || n_bags < 0) return fail(RRT_E_INVALID, "bad argument");
+  for (int i = 0; i < n_bags; ++i) {
+    if (!xs[i] || !outs[i] || xs[i] == outs[i]) return fail(RRT_E_INVALID, "bad bag pointer");
+    Workspace ws{};
+    rc = check_ws(cfg, Ls[i], workspace, workspace_bytes, &ws);
+    if (rc) return rc;
+    rc = encoder_forward(cfg, w, xs[i], outs[i], Ls[i], ws, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return RRT_OK;
+}
+
+RRT_API int rrt_encoder_forward_host(const rrt_config* cfg, const rrt_weights* w,
+                                     const float* x_host, float* out_host, float* x_dev,
+                                     float* out_dev, int64_t L, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (!w || !x_host || !out_host || !x_dev || !out_dev) return fail(RRT_E_INVALID, "NULL pointer");
+  Workspace ws{};
+  rc = check_ws(cfg, L, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t nbytes = (size_t)L * cfg->dim * sizeof(float);
+  RRT_CUDA(cudaMemcpyAsync(x_dev, x_host, nbytes, cudaMemcpyHostToDevice, st), "h2d");
+  rc = encoder_forward(cfg, w, x_dev, out_dev, L, ws, st);
+  if (rc) return rc;
+  RRT_CUDA(cudaMemcpyAsync(out_host, out_dev, nbytes, cudaMemcpyDeviceToHost, st), "d2h");
+  RRT_CUDA(cudaStreamSynchronize(st), "stream sync");
+  return RRT_OK;
+}
+
+RRT_API int rrt_rmsa_block_forward(const rrt_config* cfg, const float* norm_w,
+                                   const float* norm_b, const rrt_attn_weights* attn,
+                                   const float* x, float* x1, int64_t L, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (cfg->n_rmsa_layers < 1) return fail(RRT_E_INVALID, "cfg has no R-MSA layer");
+  if (!norm_w || !norm_b || !attn || !x || !x1 || x == x1) return fail(RRT_E_INVALID, "bad pointer");
+  Workspace ws{};
+  rc = check_ws(cfg, L, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  return rmsa_block(cfg, norm_w, norm_b, attn, x, x1, L, ws, (cudaStream_t)stream);
+}
+
+RRT_API int rrt_crmsa_block_forward(const rrt_config* cfg, const rrt_weights* w,
+                                    const float* x1, const float* x0, float* out, int64_t L,
+                                    int32_t apply_final_norm, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (!cfg->cr_msa) return fail(RRT_E_INVALID, "cfg has cr_msa off");
+  if (!w || !x1 || !out || x1 == out) return fail(RRT_E_INVALID, "bad pointer");
+  Workspace ws{};
+  rc = check_ws(cfg, L, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  return crmsa_block(cfg, w, x1, cfg->all_shortcut ? x0 : nullptr, out, L, apply_final_norm != 0,
+                     ws, (cudaStream_t)stream);
+}
+
+RRT_API int64_t rrt_launch_count(void) { return g_launches.load(); }
+
+RRT_API int rrt_stage_timing_enable(int32_t on) {
+  std::lock_guard<std::mutex> l(g_timing_mu);
+  drain_pending();
+  for (auto& iv : g_pending) { g_event_pool.push_back(iv.a); g_event_pool.push_back(iv.b); }
+  g_pending.clear();
+  for (int i = 0; i < kStCount; ++i) { g_stage_ms[i] = 0.0; g_stage_n[i] = 0; }
+  g_timing.store(on != 0);
+  return RRT_OK;
+}
+RRT_API int32_t rrt_stage_count(void) { return kStCount; }
+RRT_API const char* rrt_stage_name(int32_t stage) {
+  return (stage >= 0 && stage < kStCount) ? kStageNames[stage] : "";
+}
+RRT_API int rrt_stage_timing_read(int32_t stage, double* total_ms, int64_t* launches) {
+  if (stage < 0 || stage >= kStCount || !total_ms || !launches) return fail(RRT_E_INVALID, "bad stage");
+  std::lock_guard<std::mutex> l(g_timing_mu);
+  drain_pending();
+  *total_ms = g_stage_ms[stage];
+  *launches = g_stage_n[stage];
+  return RRT_OK;
+}
+
+RRT_API int rrt_linear_forward(const float* a, const float* w, const float* bias, float* c,
+                               int64_t M, int32_t N, int32_t K, void* stream) {
+  if (!a || !w || !c || M < 0 || M > (1 << 30)) return fail(RRT_E_INVALID, "bad argument");
+  rrt::GemmEpilogue e;
+  e.bias = bias;
+  StageScope s_(kStOther, (cudaStream_t)stream);
+  RRT_CUDA(rrt::launch_gemm_mma(a, w, c, (int)M, N, K, e, (cudaStream_t)stream), "linear");
+  return RRT_OK;
+}
+
+RRT_API int rrt_layernorm_forward(const float* x, const float* gamma, const float* beta,
+                                  float* out, int64_t L, int32_t D, void* stream) {
+  if (!x || !gamma || !beta || !out) return fail(RRT_E_INVALID, "NULL pointer");
+  StageScope s_(kStOther, (cudaStream_t)stream);
+  RRT_CUDA(rrt::launch_layernorm(x, gamma, beta, out, (int)L, D, (cudaStream_t)stream), "layernorm");
+  return RRT_OK;
+}
+
+}  // extern "C"

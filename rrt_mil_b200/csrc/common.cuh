@@ -1,0 +1,86 @@
+// Shared device/host helpers for the RRTEncoder kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace rrt {
+
+constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default (modules/rrt.py:47,139)
+#define RRT_MAX_K_DEV 16  // == RRT_MAX_CRMSA_K in include/rrt_b200.h
+
+// Padded square grid of one bag (modules/rmsa.py:175-198).  Slot s = rho*P + p is the
+// region-major position of grid cell (row, col); token t = row*H + col; t >= L is padding.
+struct Grid {
+  int L;   // real tokens
+  int H;   // grid side
+  int rs;  // region side
+  int g;   // regions per side = H / rs
+  int P;   // tokens per region = rs*rs
+  int R;   // regions = g*g
+  int Np;  // padded tokens = H*H
+
+  __host__ __device__ __forceinline__ int slot_to_token(int s) const {
+    int rho = s / P, p = s - rho * P;
+    int rr = rho / g, rc = rho - rr * g;
+    int pr = p / rs, pc = p - pr * rs;
+    return (rr * rs + pr) * H + rc * rs + pc;
+  }
+  __host__ __device__ __forceinline__ int token_to_slot(int t) const {
+    int row = t / H, col = t - row * H;
+    int rr = row / rs, pr = row - rr * rs;
+    int rc = col / rs, pc = col - rc * rs;
+    return (rr * g + rc) * P + pr * rs + pc;
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// round-to-nearest fp32 -> tf32 (kept in an fp32 container)
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ uint32_t tf32_bits(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// D(16x8,f32) += A(16x8,tf32,row) * B(8x8,tf32,col)
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4],
+                                                const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      "{%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+}  // namespace rrt

@@ -1,0 +1,408 @@
+// CR-MSA (modules/rmsa.py:290-337) without the [R,k,P,D] tensors the reference materialises:
+//   stats/logits  : per slot LayerNorm statistics + logits = LN(x1) . phi          (streaming)
+//   combine       : per region softmax_P / min / max of the logits, landmarks = cw . LN(x1)
+//   landmark attn : MHA core over the 64 regions' landmarks (batch = k)
+//   dispatch      : out = LN_final(x1 + (dmm*dw)^T . landmarks' (+ x0))             (streaming)
+// The streaming kernels are HBM/L2-bound: one warp per token row, float4 accesses.
+#include "kernels.cuh"
+
+namespace rrt {
+namespace {
+
+// ------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) crmsa_stats_logits_kernel(
+    const float* __restrict__ x1, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ phi, float2* __restrict__ stats, float* __restrict__ logits,
+    Grid grid, int k) {
+  constexpr int D = 128 * V;
+  int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (slot >= grid.Np) return;
+  int tok = grid.slot_to_token(slot);
+  if (tok >= grid.L) {  // zero pad token: LN output forced to 0 -> logits 0
+    if (lane == 0) stats[slot] = make_float2(0.f, 0.f);
+    if (phi && lane < k) logits[(size_t)slot * k + lane] = 0.f;
+    return;
+  }
+  const float* xrow = x1 + (size_t)tok * D;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = __ldg(reinterpret_cast<const float4*>(xrow) + lane + 32 * i);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  float rstd = rsqrtf(warp_sum(q) * (1.f / D) + kLnEps);
+  if (lane == 0) stats[slot] = make_float2(mean, rstd);
+  if (!phi) return;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    v[i].x = (v[i].x - mean) * rstd * gm.x + bt.x;
+    v[i].y = (v[i].y - mean) * rstd * gm.y + bt.y;
+    v[i].z = (v[i].z - mean) * rstd * gm.z + bt.z;
+    v[i].w = (v[i].w - mean) * rstd * gm.w + bt.w;
+  }
+  for (int n = 0; n < k; ++n) {
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      int c = 4 * (lane + 32 * i);
+      d = fmaf(v[i].x, __ldg(phi + (size_t)(c + 0) * k + n), d);
+      d = fmaf(v[i].y, __ldg(phi + (size_t)(c + 1) * k + n), d);
+      d = fmaf(v[i].z, __ldg(phi + (size_t)(c + 2) * k + n), d);
+      d = fmaf(v[i].w, __ldg(phi + (size_t)(c + 3) * k + n), d);
+    }
+    d = warp_sum(d);
+    if (lane == 0) logits[(size_t)slot * k + n] = d;
+  }
+}
+
+__global__ void __launch_bounds__(256) crmsa_mlp_logits_kernel(const float* __restrict__ hidden,
+                                                               const float* __restrict__ w2,
+                                                               float* __restrict__ logits, int Np,
+                                                               int Dh, int k) {
+  int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (slot >= Np) return;
+  const float* hrow = hidden + (size_t)slot * Dh;
+  for (int n = 0; n < k; ++n) {
+    float d = 0.f;
+    for (int c = lane; c < Dh; c += 32) d = fmaf(__ldg(hrow + c), __ldg(w2 + (size_t)n * Dh + c), d);
+    d = warp_sum(d);
+    if (lane == 0) logits[(size_t)slot * k + n] = d;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// grid (D/128, R), 256 threads.  smem: cw[P*k] | part[8][k][128]
+template <int KMAX>
+__global__ void __launch_bounds__(256) crmsa_combine_kernel(
+    const float* __restrict__ x1, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float2* __restrict__ stats, const float* __restrict__ logits,
+    float* __restrict__ landmarks, float2* __restrict__ rstat, Grid grid, int D, int k) {
+  extern __shared__ __align__(16) float smem[];
+  const int P = grid.P, rho = blockIdx.y, chunk = blockIdx.x;
+  float* cw = smem;                                   // [P][k]
+  float* part = smem + (((size_t)P * k + 3) & ~(size_t)3);  // [8][k][128]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const float* lg = logits + (size_t)rho * P * k;
+  for (int i = tid; i < P * k; i += blockDim.x) cw[i] = __ldg(lg + i);
+  __syncthreads();
+  // per landmark n: min / max / sum of exp over the P tokens of the region, then normalise
+  for (int n = warp; n < k; n += 8) {
+    float mx = -INFINITY, mn = INFINITY;
+    for (int p = lane; p < P; p += 32) {
+      float v = cw[p * k + n];
+      mx = fmaxf(mx, v);
+      mn = fminf(mn, v);
+    }
+    mx = warp_max(mx);
+    mn = warp_min(mn);
+    float sum = 0.f;
+    for (int p = lane; p < P; p += 32) sum += __expf(cw[p * k + n] - mx);
+    sum = warp_sum(sum);
+    float inv = 1.f / sum;
+    for (int p = lane; p < P; p += 32) cw[p * k + n] = __expf(cw[p * k + n] - mx) * inv;
+    if (chunk == 0 && lane == 0) rstat[(size_t)rho * k + n] = make_float2(mn, mx);
+  }
+  __syncthreads();
+
+  const int c0 = chunk * 128 + lane * 4;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+  const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c0));
+  float4 acc[KMAX];
+#pragma unroll
+  for (int n = 0; n < KMAX; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  constexpr int U = 4;  // rows in flight per warp
+  for (int p0 = warp; p0 < P; p0 += 8 * U) {
+    float4 xv[U];
+    float2 st[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int p = p0 + 8 * u;
+      st[u] = make_float2(0.f, 0.f);
+      xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < P) {
+        int slot = rho * P + p;
+        st[u] = __ldg(stats + slot);
+        if (st[u].y != 0.f) {
+          int tok = grid.slot_to_token(slot);
+          xv[u] = __ldg(reinterpret_cast<const float4*>(x1 + (size_t)tok * D + c0));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int p = p0 + 8 * u;
+      if (p >= P || st[u].y == 0.f) continue;  // pad rows are exact zeros after the norm
+      float4 z;
+      z.x = (xv[u].x - st[u].x) * st[u].y * gm.x + bt.x;
+      z.y = (xv[u].y - st[u].x) * st[u].y * gm.y + bt.y;
+      z.z = (xv[u].z - st[u].x) * st[u].y * gm.z + bt.z;
+      z.w = (xv[u].w - st[u].x) * st[u].y * gm.w + bt.w;
+#pragma unroll
+      for (int n = 0; n < KMAX; ++n) {
+        if (n < k) {
+          float wgt = cw[p * k + n];
+          acc[n].x = fmaf(wgt, z.x, acc[n].x);
+          acc[n].y = fmaf(wgt, z.y, acc[n].y);
+          acc[n].z = fmaf(wgt, z.z, acc[n].z);
+          acc[n].w = fmaf(wgt, z.w, acc[n].w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < KMAX; ++n)
+    if (n < k) *reinterpret_cast<float4*>(part + ((size_t)(warp * k + n)) * 128 + lane * 4) = acc[n];
+  __syncthreads();
+  for (int i = tid; i < k * 128; i += blockDim.x) {
+    int n = i >> 7, c = i & 127;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[((size_t)(w * k + n)) * 128 + c];
+    landmarks[((size_t)n * grid.R + rho) * D + chunk * 128 + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// grid (heads, k), 256 threads; sequence length R = 64 (the CR-MSA grid is always 8x8 regions).
+__global__ void __launch_bounds__(256) landmark_attn_kernel(const float* __restrict__ lqkv,
+                                                            float* __restrict__ lo, int D,
+                                                            int heads, float scale) {
+  constexpr int R = 64, CH = 32;
+  __shared__ float qs[R][CH + 1];
+  __shared__ float ks[R][CH + 1];
+  __shared__ float ps[R][R + 1];
+  const int h = blockIdx.x, n = blockIdx.y, dh = D / heads;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const size_t ld = 3 * (size_t)D;
+  const float* base = lqkv + (size_t)n * R * ld + h * dh;
+
+  float s[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+  for (int c0 = 0; c0 < dh; c0 += CH) {
+    __syncthreads();
+    for (int i = tid; i < R * CH; i += 256) {
+      int r = i / CH, c = i - r * CH;
+      qs[r][c] = __ldg(base + (size_t)r * ld + c0 + c);
+      ks[r][c] = __ldg(base + (size_t)r * ld + D + c0 + c);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < CH; ++c) {
+      float qv[4], kv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { qv[i] = qs[ty * 4 + i][c]; kv[i] = ks[tx * 4 + i][c]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = fmaf(qv[i], kv[j], s[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ps[ty * 4 + i][tx * 4 + j] = s[i][j] * scale;
+  __syncthreads();
+  {  // row softmax: warp w owns rows 8w..8w+7
+    int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+      float a = ps[r][lane], b = ps[r][lane + 32];
+      float mx = warp_max(fmaxf(a, b));
+      a = __expf(a - mx);
+      b = __expf(b - mx);
+      float inv = 1.f / warp_sum(a + b);
+      ps[r][lane] = a * inv;
+      ps[r][lane + 32] = b * inv;
+    }
+  }
+  // O[:, c0:c0+32] = P @ V[:, c0:c0+32]; V chunk staged in qs
+  for (int c0 = 0; c0 < dh; c0 += CH) {
+    __syncthreads();
+    for (int i = tid; i < R * CH; i += 256) {
+      int r = i / CH, c = i - r * CH;
+      qs[r][c] = __ldg(base + (size_t)r * ld + 2 * D + c0 + c);
+    }
+    __syncthreads();
+    float o[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < R; ++j) {
+      float v0 = qs[j][tx * 2], v1 = qs[j][tx * 2 + 1];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float p = ps[ty * 4 + i][j];
+        o[i][0] = fmaf(p, v0, o[i][0]);
+        o[i][1] = fmaf(p, v1, o[i][1]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float2*>(lo + ((size_t)n * R + ty * 4 + i) * D + h * dh + c0 + tx * 2) =
+          make_float2(o[i][0], o[i][1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) crmsa_dispatch_kernel(
+    const float* __restrict__ x1, const float* __restrict__ x0, const float* __restrict__ logits,
+    const float2* __restrict__ rstat, const float* __restrict__ lm, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* __restrict__ out, Grid grid, int k) {
+  constexpr int D = 128 * V;
+  int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (tok >= grid.L) return;
+  int slot = grid.token_to_slot(tok);
+  int rho = slot / grid.P;
+  // dispatch weight of landmark n for this token: softmax over the k logits x min-max over the region
+  float wgt[RRT_MAX_K_DEV];
+  {
+    float mx = -INFINITY;
+    for (int n = 0; n < k; ++n) {
+      wgt[n] = __ldg(logits + (size_t)slot * k + n);
+      mx = fmaxf(mx, wgt[n]);
+    }
+    float sum = 0.f;
+    for (int n = 0; n < k; ++n) sum += __expf(wgt[n] - mx);
+    float inv = 1.f / sum;
+    for (int n = 0; n < k; ++n) {
+      float2 mm = __ldg(rstat + (size_t)rho * k + n);
+      float l = wgt[n];
+      wgt[n] = __expf(l - mx) * inv * ((l - mm.x) / (mm.y - mm.x + 1e-8f));
+    }
+  }
+  float4 v[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = __ldg(reinterpret_cast<const float4*>(x1 + (size_t)tok * D) + lane + 32 * i);
+    if (x0) {
+      float4 u = __ldg(reinterpret_cast<const float4*>(x0 + (size_t)tok * D) + lane + 32 * i);
+      v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+    }
+  }
+  for (int n = 0; n < k; ++n) {
+    const float4* lrow = reinterpret_cast<const float4*>(lm + ((size_t)n * grid.R + rho) * D);
+    float w = wgt[n];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 u = __ldg(lrow + lane + 32 * i);
+      v[i].x = fmaf(w, u.x, v[i].x); v[i].y = fmaf(w, u.y, v[i].y);
+      v[i].z = fmaf(w, u.z, v[i].z); v[i].w = fmaf(w, u.w, v[i].w);
+    }
+  }
+  float* orow = out + (size_t)tok * D;
+  if (!gamma) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) reinterpret_cast<float4*>(orow)[lane + 32 * i] = v[i];
+    return;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  float rstd = rsqrtf(warp_sum(q) * (1.f / D) + kLnEps);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * gm.x + bt.x;
+    o.y = (v[i].y - mean) * rstd * gm.y + bt.y;
+    o.z = (v[i].z - mean) * rstd * gm.z + bt.z;
+    o.w = (v[i].w - mean) * rstd * gm.w + bt.w;
+    reinterpret_cast<float4*>(orow)[lane + 32 * i] = o;
+  }
+}
+
+#define RRT_DISPATCH_V(D, ...)                           \
+  switch ((D) / 128) {                                   \
+    case 1: { constexpr int V = 1; __VA_ARGS__; break; } \
+    case 2: { constexpr int V = 2; __VA_ARGS__; break; } \
+    case 3: { constexpr int V = 3; __VA_ARGS__; break; } \
+    case 4: { constexpr int V = 4; __VA_ARGS__; break; } \
+    case 6: { constexpr int V = 6; __VA_ARGS__; break; } \
+    case 8: { constexpr int V = 8; __VA_ARGS__; break; } \
+    default: return cudaErrorInvalidValue;               \
+  }
+}  // namespace
+
+cudaError_t launch_crmsa_stats_logits(const float* x1, const float* gamma, const float* beta,
+                                      const float* phi, float2* stats, float* logits,
+                                      const Grid& grid, int D, int k, cudaStream_t stream) {
+  if (D % 128 || k > 32) return cudaErrorInvalidValue;
+  int blocks = (grid.Np + 7) / 8;
+  RRT_DISPATCH_V(D, crmsa_stats_logits_kernel<V><<<blocks, 256, 0, stream>>>(x1, gamma, beta, phi, stats, logits, grid, k));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_crmsa_mlp_logits(const float* hidden, const float* w2, float* logits, int Np,
+                                    int Dh, int k, cudaStream_t stream) {
+  crmsa_mlp_logits_kernel<<<(Np + 7) / 8, 256, 0, stream>>>(hidden, w2, logits, Np, Dh, k);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_crmsa_combine(const float* x1, const float* gamma, const float* beta,
+                                 const float2* stats, const float* logits, float* landmarks,
+                                 float2* rstat, const Grid& grid, int D, int k,
+                                 cudaStream_t stream) {
+  if (D % 128 || k < 1 || k > 16) return cudaErrorInvalidValue;
+  size_t smem = ((((size_t)grid.P * k + 3) & ~(size_t)3) + (size_t)8 * k * 128) * sizeof(float);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  dim3 g(D / 128, grid.R);
+#define RRT_COMBINE(KM)                                                                          \
+  {                                                                                              \
+    cudaError_t e = cudaFuncSetAttribute(crmsa_combine_kernel<KM>,                               \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+    if (e != cudaSuccess) return e;                                                              \
+    crmsa_combine_kernel<KM><<<g, 256, smem, stream>>>(x1, gamma, beta, stats, logits, landmarks, \
+                                                       rstat, grid, D, k);                       \
+  }
+  if (k <= 4) RRT_COMBINE(4) else if (k <= 8) RRT_COMBINE(8) else RRT_COMBINE(16)
+#undef RRT_COMBINE
+  return cudaGetLastError();
+}
+
+cudaError_t launch_landmark_attention(const float* lqkv, float* lo, int k, int R, int D, int heads,
+                                      cudaStream_t stream) {
+  if (R != 64 || heads <= 0 || D % heads || (D / heads) % 32) return cudaErrorInvalidValue;
+  float scale = 1.f / sqrtf((float)(D / heads));
+  landmark_attn_kernel<<<dim3(heads, k), 256, 0, stream>>>(lqkv, lo, D, heads, scale);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_crmsa_dispatch(const float* x1, const float* x0, const float* logits,
+                                  const float2* rstat, const float* lm, const float* gamma,
+                                  const float* beta, float* out, const Grid& grid, int D, int k,
+                                  cudaStream_t stream) {
+  if (D % 128 || k < 1 || k > RRT_MAX_K_DEV) return cudaErrorInvalidValue;
+  if (grid.L == 0) return cudaSuccess;
+  int blocks = (grid.L + 7) / 8;
+  RRT_DISPATCH_V(D, crmsa_dispatch_kernel<V><<<blocks, 256, 0, stream>>>(x1, x0, logits, rstat, lm, gamma, beta, out, grid, k));
+  return cudaGetLastError();
+}
+
+}  // namespace rrt

@@ -1,0 +1,116 @@
+// LayerNorm (+ zero padding + region partition) streaming kernels.  HBM-bound: one warp per
+// token row, float4 loads/stores, two-pass statistics held in registers.
+#include "kernels.cuh"
+
+namespace rrt {
+
+template <int V>  // D = 128 * V
+__device__ __forceinline__ void ln_row(const float* __restrict__ xrow, const float* __restrict__ x0row,
+                                       const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float* __restrict__ orow,
+                                       int lane, bool round_tf32) {
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = __ldg(reinterpret_cast<const float4*>(xrow) + lane + 32 * i);
+    if (x0row != nullptr) {
+      float4 u = __ldg(reinterpret_cast<const float4*>(x0row) + lane + 32 * i);
+      v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+    }
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float inv_d = 1.f / (128.f * V);
+  float mean = warp_sum(s) * inv_d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  float rstd = rsqrtf(warp_sum(q) * inv_d + kLnEps);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * gm.x + bt.x;
+    o.y = (v[i].y - mean) * rstd * gm.y + bt.y;
+    o.z = (v[i].z - mean) * rstd * gm.z + bt.z;
+    o.w = (v[i].w - mean) * rstd * gm.w + bt.w;
+    if (round_tf32) { o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w); }
+    reinterpret_cast<float4*>(orow)[lane + 32 * i] = o;
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) ln_partition_kernel(const float* __restrict__ x,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta,
+                                                           float* __restrict__ z, Grid grid,
+                                                           bool round_tf32) {
+  const int D = 128 * V;
+  int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (slot >= grid.Np) return;
+  int t = grid.slot_to_token(slot);
+  float* zrow = z + (size_t)slot * D;
+  if (t >= grid.L) {  // pad token: exact zeros AFTER the norm (modules/rmsa.py:200)
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      reinterpret_cast<float4*>(zrow)[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  ln_row<V>(x + (size_t)t * D, nullptr, gamma, beta, zrow, lane, round_tf32);
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ x1,
+                                                            const float* __restrict__ x0,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            float* __restrict__ out, int L) {
+  const int D = 128 * V;
+  int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= L) return;
+  ln_row<V>(x1 + (size_t)t * D, x0 ? x0 + (size_t)t * D : nullptr, gamma, beta,
+            out + (size_t)t * D, threadIdx.x & 31, false);
+}
+
+#define RRT_DISPATCH_V(D, ...)                         \
+  switch ((D) / 128) {                                 \
+    case 1: { constexpr int V = 1; __VA_ARGS__; break; } \
+    case 2: { constexpr int V = 2; __VA_ARGS__; break; } \
+    case 3: { constexpr int V = 3; __VA_ARGS__; break; } \
+    case 4: { constexpr int V = 4; __VA_ARGS__; break; } \
+    case 6: { constexpr int V = 6; __VA_ARGS__; break; } \
+    case 8: { constexpr int V = 8; __VA_ARGS__; break; } \
+    default: return cudaErrorInvalidValue;             \
+  }
+
+cudaError_t launch_ln_partition(const float* x, const float* gamma, const float* beta, float* z,
+                                const Grid& grid, int D, bool round_tf32, cudaStream_t stream) {
+  if (D % 128) return cudaErrorInvalidValue;
+  const int wpb = 8;
+  int blocks = (grid.Np + wpb - 1) / wpb;
+  RRT_DISPATCH_V(D, ln_partition_kernel<V><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, z, grid, round_tf32));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_add_layernorm(const float* x1, const float* x0, const float* gamma,
+                                 const float* beta, float* out, int L, int D,
+                                 cudaStream_t stream) {
+  if (D % 128) return cudaErrorInvalidValue;
+  if (L == 0) return cudaSuccess;
+  const int wpb = 8;
+  int blocks = (L + wpb - 1) / wpb;
+  RRT_DISPATCH_V(D, add_layernorm_kernel<V><<<blocks, wpb * 32, 0, stream>>>(x1, x0, gamma, beta, out, L));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* out,
+                             int L, int D, cudaStream_t stream) {
+  return launch_add_layernorm(x, nullptr, gamma, beta, out, L, D, stream);
+}
+
+}  // namespace rrt

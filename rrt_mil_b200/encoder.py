@@ -1,0 +1,269 @@
+"""``RRTEncoder`` -- the reference's plug-in surface over the B200 C-ABI library.
+
+Mirrors ``/root/reference/modules/rrt.py:133-202`` (constructor keywords and defaults, sub-module
+tree, ``state_dict`` keys, ``final_dim``, 2-D / 3-D / 4-D input handling) so that it drops into the
+reference's MIL aggregators (``rrt=<module>``) and loads reference checkpoints with ``strict=True``.
+The sub-modules below only OWN parameters (real ``nn.Linear`` / ``nn.Conv2d`` / ``nn.LayerNorm``
+objects, so host-side ``initialize_weights`` passes keep working); all arithmetic of the forward
+happens in ``librrt_b200.so`` (hand-written sm_100a CUDA) in one C call per bag.
+
+No fallback: CPU tensors, missing library, or options the kernels do not cover raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+from torch import nn
+
+from . import cabi
+
+
+def initialize_weights(module: nn.Module) -> None:
+    """Same initialisation the reference applies with ``need_init=True`` (modules/rrt.py:9-23):
+    Xavier-normal Linear/Conv2d weights, zero biases, LayerNorm (1, 0)."""
+    for m in module.modules():
+        if isinstance(m, (nn.Conv2d, nn.Linear)):
+            nn.init.xavier_normal_(m.weight)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+
+
+class _ParamHolder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover - guard
+        raise RuntimeError(f"{type(self).__name__} only owns parameters; call RRTEncoder.forward")
+
+
+class InnerAttention(_ParamHolder):
+    """Parameters of modules/rmsa.py:56-89: ``qkv``, ``proj`` and the EPEG conv ``pe``."""
+
+    def __init__(self, dim, num_heads, qkv_bias, epeg, epeg_k, epeg_bias):
+        super().__init__()
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        if epeg:
+            self.pe = nn.Conv2d(num_heads, num_heads, (epeg_k, 1), padding=(epeg_k // 2, 0),
+                                groups=num_heads, bias=epeg_bias)
+        else:
+            self.pe = None
+
+
+class RegionAttention(_ParamHolder):
+    """modules/rmsa.py:152-173 (``RegionAttntion``)."""
+
+    def __init__(self, dim, num_heads, qkv_bias, epeg, epeg_k, epeg_bias):
+        super().__init__()
+        self.attn = InnerAttention(dim, num_heads, qkv_bias, epeg, epeg_k, epeg_bias)
+
+
+class CrossRegionAttention(_ParamHolder):
+    """modules/rmsa.py:232-259 (``CrossRegionAttntion``): ``phi`` + an InnerAttention without EPEG."""
+
+    def __init__(self, dim, num_heads, qkv_bias, crmsa_k, crmsa_mlp):
+        super().__init__()
+        self.attn = InnerAttention(dim, num_heads, qkv_bias, False, 0, False)
+        if crmsa_mlp:
+            self.phi = nn.Sequential(nn.Linear(dim, dim // 4, bias=False), nn.Tanh(),
+                                     nn.Linear(dim // 4, crmsa_k, bias=False))
+        else:
+            self.phi = nn.Parameter(torch.empty(dim, crmsa_k))
+            nn.init.kaiming_uniform_(self.phi, a=math.sqrt(5))
+
+
+class TransLayer(_ParamHolder):
+    """modules/rrt.py:43-106: pre-LayerNorm + attention (+ residual, done in the kernels)."""
+
+    def __init__(self, dim, attn_module):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.attn = attn_module
+
+
+class RRTEncoder(nn.Module):
+    def __init__(self, mlp_dim=512, pos_pos=0, pos='none', peg_k=7, attn='rmsa', region_num=8,
+                 drop_out=0.1, n_layers=2, n_heads=8, drop_path=0., ffn=False, ffn_act='gelu',
+                 mlp_ratio=4., trans_dim=64, epeg=True, epeg_k=15, region_size=0, min_region_num=0,
+                 min_region_ratio=0, qkv_bias=True, peg_bias=True, peg_1d=False, cr_msa=True,
+                 crmsa_k=3, all_shortcut=False, crmsa_mlp=False, crmsa_heads=8, need_init=False,
+                 **kwargs):
+        super().__init__()
+        # ---- options the kernels do not cover raise instead of silently computing something else
+        if attn != 'rmsa':
+            raise NotImplementedError(f"attn={attn!r}: only 'rmsa' is built (the reference also "
+                                      "raises for unknown values, modules/rrt.py:89-90)")
+        if pos not in ('none', None):
+            raise NotImplementedError(f"pos={pos!r}: ablation positional encodings are not built")
+        if ffn:
+            raise NotImplementedError("ffn=True (ablation MLP) is not built")
+        epeg_2d = kwargs.pop('epeg_2d', False)
+        epeg_type = kwargs.pop('epeg_type', 'attn')
+        epeg_bias = kwargs.pop('epeg_bias', True)
+        region_attn = kwargs.pop('region_attn', 'native')
+        if epeg and (epeg_2d or epeg_type != 'attn'):
+            raise NotImplementedError("epeg_2d / epeg_type != 'attn' (ablations) are not built")
+        if region_attn != 'native':
+            raise NotImplementedError("region_attn != 'native' (ablation) is not built")
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
+        if n_layers < 1 or n_layers - 1 > cabi.RRT_MAX_RMSA_LAYERS:
+            raise ValueError("n_layers out of range")
+        if epeg and n_layers > 1 and (epeg_k % 2 == 0 or epeg_k > cabi.RRT_MAX_EPEG_K):
+            raise ValueError("epeg_k must be odd (the reference's forward fails on even kernels: "
+                             "Conv2d padding k//2 yields P+1 rows, modules/rmsa.py:83,108) and <= 63")
+
+        self.final_dim = mlp_dim
+        self.all_shortcut = all_shortcut
+        self.drop_out = float(drop_out)
+        self.drop_path_rate = float(drop_path)
+        self.pos_pos = pos_pos
+        self.norm = nn.LayerNorm(mlp_dim)
+        self.layers = nn.Sequential(*[
+            TransLayer(mlp_dim, RegionAttention(mlp_dim, n_heads, qkv_bias, epeg, epeg_k, epeg_bias))
+            for _ in range(n_layers - 1)])
+        self.cr_msa = (TransLayer(mlp_dim, CrossRegionAttention(mlp_dim, crmsa_heads, qkv_bias,
+                                                                crmsa_k, crmsa_mlp))
+                       if cr_msa else nn.Identity())
+        self.pos_embedding = nn.Identity()
+
+        cfg = cabi.RrtConfig()
+        cfg.dim, cfg.n_rmsa_layers, cfg.n_heads = mlp_dim, n_layers - 1, n_heads
+        cfg.region_num, cfg.region_size = region_num, int(region_size or 0)
+        cfg.min_region_num, cfg.min_region_ratio = int(min_region_num), float(min_region_ratio)
+        cfg.epeg, cfg.epeg_k, cfg.qkv_bias = int(bool(epeg)), int(epeg_k), int(bool(qkv_bias))
+        cfg.cr_msa, cfg.crmsa_k, cfg.crmsa_heads = int(bool(cr_msa)), int(crmsa_k), int(crmsa_heads)
+        cfg.crmsa_mlp, cfg.all_shortcut = int(bool(crmsa_mlp)), int(bool(all_shortcut))
+        cfg.math_mode = cabi.RRT_MATH_TF32
+        self._cfg = cfg
+        self._crmsa_mlp = bool(crmsa_mlp)
+
+        if need_init:
+            self.apply(initialize_weights)
+
+    # ------------------------------------------------------------------------------------------
+    def extra_repr(self) -> str:
+        c = self._cfg
+        return (f"dim={c.dim}, n_layers={c.n_rmsa_layers + 1}, region_num={c.region_num}, "
+                f"epeg_k={c.epeg_k if c.epeg else None}, crmsa_k={c.crmsa_k if c.cr_msa else None}, "
+                f"all_shortcut={bool(c.all_shortcut)}")
+
+    @staticmethod
+    def _ptr(t, device):
+        if t is None:
+            return None
+        if t.device != device or t.dtype != torch.float32:
+            raise RuntimeError("all RRTEncoder parameters must be float32 on the input's device")
+        if not t.is_contiguous():
+            raise RuntimeError("RRTEncoder parameters must be contiguous")
+        return t.data_ptr()
+
+    def _attn_weights(self, inner: InnerAttention, dst: cabi.RrtAttnWeights, device):
+        p = self._ptr
+        dst.qkv_w, dst.qkv_b = p(inner.qkv.weight, device), p(inner.qkv.bias, device)
+        dst.proj_w, dst.proj_b = p(inner.proj.weight, device), p(inner.proj.bias, device)
+        dst.pe_w = p(inner.pe.weight, device) if inner.pe is not None else None
+
+    def _weights(self, device) -> cabi.RrtWeights:
+        w, p = cabi.RrtWeights(), self._ptr
+        w.norm_w, w.norm_b = p(self.norm.weight, device), p(self.norm.bias, device)
+        for i, layer in enumerate(self.layers):
+            w.layer_norm_w[i], w.layer_norm_b[i] = p(layer.norm.weight, device), p(layer.norm.bias, device)
+            self._attn_weights(layer.attn.attn, w.layer_attn[i], device)
+        if self._cfg.cr_msa:
+            cr = self.cr_msa
+            w.cr_norm_w, w.cr_norm_b = p(cr.norm.weight, device), p(cr.norm.bias, device)
+            if self._crmsa_mlp:
+                w.cr_phi_w1, w.cr_phi_w2 = p(cr.attn.phi[0].weight, device), p(cr.attn.phi[2].weight, device)
+            else:
+                w.cr_phi = p(cr.attn.phi, device)
+            self._attn_weights(cr.attn.attn, w.cr_attn, device)
+        return w
+
+    def _check_mode(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("RRTEncoder (rrt_mil_b200) runs on CUDA only; there is no CPU fallback")
+        if x.dtype != torch.float32:
+            raise NotImplementedError(f"input dtype {x.dtype}: only float32 bags are supported")
+        needs_grad = torch.is_grad_enabled() and (
+            x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            raise NotImplementedError(
+                "backward kernels are not built yet: call under torch.no_grad() / inference_mode()")
+        if self.training and (self.drop_out > 0 or self.drop_path_rate > 0):
+            raise NotImplementedError("training-mode dropout / drop_path is not built: use .eval() "
+                                      "or drop_out=0")
+
+    def forward_bag(self, x: torch.Tensor) -> torch.Tensor:
+        """One bag ``[N, D]`` float32 CUDA -> ``[N, D]``; enqueues on the current stream."""
+        self._check_mode(x)
+        if x.dim() != 2 or x.shape[1] != self.final_dim:
+            raise ValueError(f"expected a [N, {self.final_dim}] bag, got {tuple(x.shape)}")
+        N = x.shape[0]
+        if N < 1:
+            raise ValueError("empty bag")
+        x = x.contiguous()
+        lib, cfg = cabi.lib(), self._cfg
+        with torch.cuda.device(x.device):
+            nbytes = cabi.workspace_bytes(cfg, N)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            out = torch.empty_like(x)
+            w = self._weights(x.device)
+            rc = lib.rrt_encoder_forward(C.byref(cfg), C.byref(w), x.data_ptr(), out.data_ptr(), N,
+                                         ws.data_ptr(), nbytes,
+                                         torch.cuda.current_stream(x.device).cuda_stream)
+        cabi.check(rc, "rrt_encoder_forward")
+        return out
+
+    def forward_bags(self, bags, outs=None):
+        """Independent bags ``[N_i, D]`` back to back on the current stream with ONE C call
+        (amortises the host-side cost of a call; results equal per-bag ``forward``)."""
+        if not bags:
+            return []
+        for x in bags:
+            self._check_mode(x)
+            if x.dim() != 2 or x.shape[1] != self.final_dim or x.shape[0] < 1 or not x.is_contiguous():
+                raise ValueError(f"expected contiguous [N, {self.final_dim}] bags")
+            if x.device != bags[0].device:
+                raise ValueError("all bags of one call must live on the same device")
+        device = bags[0].device
+        if outs is None:
+            outs = [torch.empty_like(x) for x in bags]
+        n = len(bags)
+        lib, cfg = cabi.lib(), self._cfg
+        with torch.cuda.device(device):
+            nbytes = cabi.workspace_bytes(cfg, max(x.shape[0] for x in bags))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            w = self._weights(device)
+            xs = (C.c_void_p * n)(*[x.data_ptr() for x in bags])
+            os_ = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+            ls = (C.c_int64 * n)(*[x.shape[0] for x in bags])
+            rc = lib.rrt_encoder_forward_batch(C.byref(cfg), C.byref(w), xs, os_, ls, n, ws.data_ptr(),
+                                               nbytes, torch.cuda.current_stream(device).cuda_stream)
+        cabi.check(rc, "rrt_encoder_forward_batch")
+        return outs
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        shape_len = x.dim()
+        if shape_len == 2:          # [N, C]  (clam / dsmil hosts)
+            x3 = x.unsqueeze(0)
+        elif shape_len == 4:        # [B, C, H, W]
+            x3 = x.reshape(x.size(0), x.size(1), -1).transpose(1, 2)
+        elif shape_len == 3:
+            x3 = x
+        else:
+            raise ValueError(f"expected a 2-D, 3-D or 4-D input, got {tuple(x.shape)}")
+        batch, num_patches, channels = x3.shape
+        if batch != 1:
+            # the reference silently mixes the bags of a batch inside CR-MSA;
+            # every host calls with one bag, which is the contract kept here
+            raise ValueError("RRTEncoder processes one bag per call (batch dimension must be 1)")
+        y = self.forward_bag(x3[0]).unsqueeze(0)
+        if shape_len == 2:
+            y = y.squeeze(0)
+        elif shape_len == 4:
+            side = int(num_patches ** 0.5)
+            y = y.transpose(1, 2).reshape(batch, channels, side, side)
+        return y

@@ -1,0 +1,80 @@
+"""The C-ABI library loads without a GPU and exports exactly what include/rrt_b200.h declares.
+No compute entry is called here (CPU box)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from rrt_mil_b200 import cabi, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rrt_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()  # no-op when the in-tree .so is current
+    return cabi.lib()
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"RRT_API\s+[\w\s\*]+?\b(rrt_\w+)\s*\(", text)))
+
+
+def test_header_declares_what_the_binding_binds():
+    assert declared_symbols() == sorted(cabi.SIGNATURES)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+
+
+def test_abi_version_and_constants(lib):
+    assert lib.rrt_abi_version() == cabi.RRT_ABI_VERSION
+    text = open(HEADER).read()
+    for macro, val in [("RRT_ABI_VERSION", cabi.RRT_ABI_VERSION),
+                       ("RRT_MAX_RMSA_LAYERS", cabi.RRT_MAX_RMSA_LAYERS),
+                       ("RRT_MAX_CRMSA_K", cabi.RRT_MAX_CRMSA_K),
+                       ("RRT_MAX_EPEG_K", cabi.RRT_MAX_EPEG_K)]:
+        assert int(re.search(rf"#define {macro} (\d+)", text).group(1)) == val
+
+
+def test_grid_geometry_matches_oracle(lib):
+    from oracle import rrt_oracle as O
+    cases = [(L, g, rs, mn, mr) for L in (1, 2, 50, 63, 64, 65, 512, 576, 577, 9000, 9216, 50000, 123457)
+             for (g, rs, mn, mr) in ((8, 0, 0, 0.0), (16, 0, 0, 0.0), (4, 0, 0, 0.0), (8, 5, 0, 0.0),
+                                     (8, 0, 700, 0.0), (16, 0, 0, 5.0), (8, 0, 0, 0.5))]
+    for L, g, rs, mn, mr in cases:
+        H, r, _ = O.grid_geometry(L, g, rs, mn, mr)
+        assert cabi.grid_geometry(L, g, rs, mn, mr) == (H, r), (L, g, rs, mn, mr)
+
+
+def test_workspace_bytes_and_config_validation(lib):
+    from rrt_mil_b200 import RRTEncoder
+    cfg = RRTEncoder()._cfg
+    n9000 = cabi.workspace_bytes(cfg, 9000)
+    # z + qkv + o over 9216 padded tokens, two residual buffers over 9000: ~130 MB at D=512
+    assert 120e6 < n9000 < 160e6
+    assert cabi.workspace_bytes(cfg, 512) < n9000
+    bad = cabi.RrtConfig.from_buffer_copy(cfg)
+    bad.dim = 100
+    with pytest.raises(ValueError):
+        cabi.workspace_bytes(bad, 512)
+    bad = cabi.RrtConfig.from_buffer_copy(cfg)
+    bad.epeg_k = 4
+    with pytest.raises(ValueError):
+        cabi.workspace_bytes(bad, 512)
+    with pytest.raises(ValueError):
+        cabi.workspace_bytes(cfg, 0)
+    assert b"geometry" in lib.rrt_last_error() or b"bag" in lib.rrt_last_error()
+
+
+def test_struct_layout_matches_header_sizes():
+    # 64-bit ABI: config = 6 int32 + double + 9 int32 (padded to 8) ; weights = pointer table
+    assert C.sizeof(cabi.RrtConfig) == 72
+    assert C.sizeof(cabi.RrtAttnWeights) == 5 * 8
+    assert C.sizeof(cabi.RrtWeights) == 8 * (2 + 2 * 8 + 5 * 8 + 5 + 5)
