@@ -33,7 +33,7 @@ extern "C" {
 #define RRT_API __attribute__((visibility("default")))
 #endif
 
-#define RRT_ABI_VERSION 1
+#define RRT_ABI_VERSION 2
 #define RRT_MAX_RMSA_LAYERS 8 /* n_layers-1 R-MSA TransLayers (modules/rrt.py:143) */
 #define RRT_MAX_CRMSA_K 16    /* crmsa_k landmarks per region                         */
 #define RRT_MAX_EPEG_K 63     /* odd EPEG kernel length                               */
@@ -80,6 +80,11 @@ typedef struct rrt_attn_weights {
   const float* proj_w; /* [D, D] */
   const float* proj_b; /* [D] */
   const float* pe_w;   /* [heads, epeg_k] or NULL */
+  /* Optional tf32-rounded shadows of qkv_w / proj_w (rrt_round_tf32), the form the tcgen05 GEMMs
+   * consume.  NULL: the library rounds into its workspace on every call (correct, ~2 us slower).
+   * The Python binding keeps shadows and refreshes them when a parameter changes. */
+  const float* qkv_w_tf32;
+  const float* proj_w_tf32;
 } rrt_attn_weights;
 
 /* state_dict of one RRTEncoder, by reference name. */
@@ -147,6 +152,15 @@ RRT_API int rrt_crmsa_block_forward(const rrt_config* cfg, const rrt_weights* w,
                                     const float* x1, const float* x0, float* out, int64_t L,
                                     int32_t apply_final_norm, void* workspace,
                                     size_t workspace_bytes, void* stream);
+
+/* dst[i] = src[i] rounded to nearest tf32 (10-bit mantissa), kept as fp32.  n % 4 == 0. */
+RRT_API int rrt_round_tf32(const float* src, float* dst, int64_t n, void* stream);
+
+/* The tcgen05/TMA/TMEM GEMM the bag-sized layers run on, exposed for parity tests:
+ * c[M,N] = a[M,K] @ w[N,K]^T + bias[N].  a and w must be tf32-representable (rrt_round_tf32),
+ * 16-byte aligned; K % 32 == 0, N % 4 == 0. */
+RRT_API int rrt_linear_tf32_forward(const float* a, const float* w, const float* bias, float* c,
+                                    int64_t M, int32_t N, int32_t K, void* stream);
 
 /* c[M,N] = a[M,K] @ w[N,K]^T + bias[N]   (nn.Linear; bias may be NULL).  K % 32 == 0. */
 RRT_API int rrt_linear_forward(const float* a, const float* w, const float* bias, float* c,

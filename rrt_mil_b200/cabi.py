@@ -12,7 +12,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librrt_b200.so")
 
-RRT_ABI_VERSION = 1
+RRT_ABI_VERSION = 2
 RRT_MAX_RMSA_LAYERS = 8
 RRT_MAX_CRMSA_K = 16
 RRT_MAX_EPEG_K = 63
@@ -35,7 +35,8 @@ class RrtConfig(C.Structure):
 
 class RrtAttnWeights(C.Structure):
     _fields_ = [("qkv_w", c_float_p), ("qkv_b", c_float_p), ("proj_w", c_float_p),
-                ("proj_b", c_float_p), ("pe_w", c_float_p)]
+                ("proj_b", c_float_p), ("pe_w", c_float_p), ("qkv_w_tf32", c_float_p),
+                ("proj_w_tf32", c_float_p)]
 
 
 class RrtWeights(C.Structure):
@@ -73,6 +74,8 @@ SIGNATURES = {
     "rrt_stage_count": (C.c_int32, []),
     "rrt_stage_name": (C.c_char_p, [C.c_int32]),
     "rrt_stage_timing_read": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "rrt_round_tf32": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "rrt_linear_tf32_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "rrt_linear_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "rrt_layernorm_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
 }

@@ -169,6 +169,7 @@ struct Workspace {
   float* lo;       // [k*R_c, D]
   float* lout;     // [k*R_c, D]
   float* hidden;   // [Np_c, D/4] (crmsa_mlp)
+  float* wround;   // [3D*D + D*D] tf32-rounded weights when the caller passes no shadow
   size_t bytes;
 };
 
@@ -210,6 +211,7 @@ bool carve(const rrt_config* c, int64_t L, void* base, Workspace* ws) {
   ws->lo = (float*)take(T * D * 4);
   ws->lout = (float*)take(T * D * 4);
   ws->hidden = (float*)take((c->cr_msa && c->crmsa_mlp) ? np_c * (D / 4) * 4 : 0);
+  ws->wround = (float*)take(4 * D * D * 4);
   ws->bytes = off + 256;
   return true;
 }
@@ -230,19 +232,48 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
   if (!make_grid(L, c->region_num, c->region_size, c->min_region_num, c->min_region_ratio, &g))
     return fail(RRT_E_INVALID, "bad geometry");
   const int D = c->dim;
-  { StageScope s_(kStLnPartition, st); RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws.z, g, D, false, st), "ln_partition"); }
+  // bag-sized GEMMs run on tcgen05 (tf32 operands pre-rounded by the producing kernels)
+  const bool tc = rrt::gemm_tcgen05_supported(g.Np, 3 * D, D);
+  const float* wq = a->qkv_w;
+  const float* wp = a->proj_w;
+  if (tc) {
+    wq = a->qkv_w_tf32;
+    wp = a->proj_w_tf32;
+    if (!wq || !wp) {
+      StageScope s_(kStOther, st, 2);
+      if (!wq) {
+        RRT_CUDA(rrt::launch_round_tf32(a->qkv_w, ws.wround, (size_t)3 * D * D, st), "round qkv_w");
+        wq = ws.wround;
+      }
+      if (!wp) {
+        RRT_CUDA(rrt::launch_round_tf32(a->proj_w, ws.wround + (size_t)3 * D * D, (size_t)D * D, st),
+                 "round proj_w");
+        wp = ws.wround + (size_t)3 * D * D;
+      }
+    }
+  }
+  { StageScope s_(kStLnPartition, st); RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws.z, g, D, tc, st), "ln_partition"); }
   rrt::GemmEpilogue e1;
   e1.bias = c->qkv_bias ? a->qkv_b : nullptr;
-  { StageScope s_(kStQkvGemm, st); RRT_CUDA(rrt::launch_gemm_mma(ws.z, a->qkv_w, ws.qkv, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
+  { StageScope s_(kStQkvGemm, st);
+    if (tc) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.z, wq, ws.qkv, g.Np, 3 * D, D, e1, st), "qkv gemm (tcgen05)");
+    else RRT_CUDA(rrt::launch_gemm_mma(ws.z, wq, ws.qkv, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
   { StageScope s_(kStRmsaAttn, st);
-    RRT_CUDA(rrt::launch_rmsa_attention(ws.qkv, c->epeg ? a->pe_w : nullptr, ws.o, g, D, c->n_heads,
-                                        c->epeg_k, st), "rmsa attention"); }
+    const float* taps = c->epeg ? a->pe_w : nullptr;
+    if (rrt::rmsa_attention_f16_supported(g, D, c->n_heads))
+      RRT_CUDA(rrt::launch_rmsa_attention_f16(ws.qkv, taps, ws.o, g, D, c->n_heads, c->epeg_k, tc, st),
+               "rmsa attention (region-resident)");
+    else
+      RRT_CUDA(rrt::launch_rmsa_attention(ws.qkv, taps, ws.o, g, D, c->n_heads, c->epeg_k, tc, st),
+               "rmsa attention (flash)"); }
   rrt::GemmEpilogue e2;
   e2.mode = rrt::kEpiResidualUnpart;
   e2.bias = a->proj_b;
   e2.resid = x;
   e2.grid = g;
-  { StageScope s_(kStProjGemm, st); RRT_CUDA(rrt::launch_gemm_mma(ws.o, a->proj_w, x1, g.Np, D, D, e2, st), "proj gemm"); }
+  { StageScope s_(kStProjGemm, st);
+    if (tc) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.o, wp, x1, g.Np, D, D, e2, st), "proj gemm (tcgen05)");
+    else RRT_CUDA(rrt::launch_gemm_mma(ws.o, wp, x1, g.Np, D, D, e2, st), "proj gemm"); }
   return RRT_OK;
 }
 
@@ -270,20 +301,43 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
     RRT_CUDA(rrt::launch_crmsa_stats_logits(x1, w->cr_norm_w, w->cr_norm_b, w->cr_phi, ws.stats,
                                             ws.logits, g, D, k, st), "crmsa logits");
   }
+  // landmark GEMMs (M = k*64 rows) on the narrow-tile tcgen05 kernel; operands rounded by producers
+  const bool tc = rrt::gemm_tcgen05_supported(T, 3 * D, D);
+  const float* wq = w->cr_attn.qkv_w;
+  const float* wp = w->cr_attn.proj_w;
+  if (tc) {
+    wq = w->cr_attn.qkv_w_tf32;
+    wp = w->cr_attn.proj_w_tf32;
+    if (!wq || !wp) {
+      if (!ws.wround) return fail(RRT_E_WORKSPACE, "no room for rounded landmark weights");
+      StageScope s_(kStOther, st, 2);
+      if (!wq) {
+        RRT_CUDA(rrt::launch_round_tf32(w->cr_attn.qkv_w, ws.wround, (size_t)3 * D * D, st), "round");
+        wq = ws.wround;
+      }
+      if (!wp) {
+        RRT_CUDA(rrt::launch_round_tf32(w->cr_attn.proj_w, ws.wround + (size_t)3 * D * D,
+                                        (size_t)D * D, st), "round");
+        wp = ws.wround + (size_t)3 * D * D;
+      }
+    }
+  }
   { StageScope s_(kStCrCombine, st);
     RRT_CUDA(rrt::launch_crmsa_combine(x1, w->cr_norm_w, w->cr_norm_b, ws.stats, ws.logits, ws.lm,
-                                       ws.rstat, g, D, k, st), "crmsa combine"); }
+                                       ws.rstat, g, D, k, tc, st), "crmsa combine"); }
   rrt::GemmEpilogue e1;
   e1.bias = c->qkv_bias ? w->cr_attn.qkv_b : nullptr;
   { StageScope s_(kStLmQkv, st);
-    RRT_CUDA(rrt::launch_gemm_mma(ws.lm, w->cr_attn.qkv_w, ws.lqkv, T, 3 * D, D, e1, st), "landmark qkv"); }
+    if (tc) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lm, wq, ws.lqkv, T, 3 * D, D, e1, st), "landmark qkv");
+    else RRT_CUDA(rrt::launch_gemm_mma(ws.lm, wq, ws.lqkv, T, 3 * D, D, e1, st), "landmark qkv"); }
   { StageScope s_(kStLmAttn, st);
-    RRT_CUDA(rrt::launch_landmark_attention(ws.lqkv, ws.lo, k, g.R, D, c->crmsa_heads, st),
+    RRT_CUDA(rrt::launch_landmark_attention(ws.lqkv, ws.lo, k, g.R, D, c->crmsa_heads, tc, st),
              "landmark attention"); }
   rrt::GemmEpilogue e2;
   e2.bias = w->cr_attn.proj_b;
   { StageScope s_(kStLmProj, st);
-    RRT_CUDA(rrt::launch_gemm_mma(ws.lo, w->cr_attn.proj_w, ws.lout, T, D, D, e2, st), "landmark proj"); }
+    if (tc) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lo, wp, ws.lout, T, D, D, e2, st), "landmark proj");
+    else RRT_CUDA(rrt::launch_gemm_mma(ws.lo, wp, ws.lout, T, D, D, e2, st), "landmark proj"); }
   { StageScope s_(kStCrDispatch, st);
     RRT_CUDA(rrt::launch_crmsa_dispatch(x1, x0, ws.logits, ws.rstat, ws.lout,
                                         final_norm ? w->norm_w : nullptr,
@@ -450,6 +504,24 @@ RRT_API int rrt_linear_forward(const float* a, const float* w, const float* bias
   e.bias = bias;
   StageScope s_(kStOther, (cudaStream_t)stream);
   RRT_CUDA(rrt::launch_gemm_mma(a, w, c, (int)M, N, K, e, (cudaStream_t)stream), "linear");
+  return RRT_OK;
+}
+
+RRT_API int rrt_round_tf32(const float* src, float* dst, int64_t n, void* stream) {
+  if (!src || !dst || n < 0 || n % 4) return fail(RRT_E_INVALID, "bad argument");
+  StageScope s_(kStOther, (cudaStream_t)stream);
+  RRT_CUDA(rrt::launch_round_tf32(src, dst, (size_t)n, (cudaStream_t)stream), "round_tf32");
+  return RRT_OK;
+}
+
+RRT_API int rrt_linear_tf32_forward(const float* a, const float* w, const float* bias, float* c,
+                                    int64_t M, int32_t N, int32_t K, void* stream) {
+  if (!a || !w || !c || M < 1 || M > (1 << 30)) return fail(RRT_E_INVALID, "bad argument");
+  if (!rrt::gemm_tcgen05_supported((int)M, N, K)) return fail(RRT_E_INVALID, "shape not supported");
+  rrt::GemmEpilogue e;
+  e.bias = bias;
+  StageScope s_(kStOther, (cudaStream_t)stream);
+  RRT_CUDA(rrt::launch_gemm_tcgen05(a, w, c, (int)M, N, K, e, (cudaStream_t)stream), "linear (tcgen05)");
   return RRT_OK;
 }
 

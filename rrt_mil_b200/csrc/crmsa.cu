@@ -16,54 +16,69 @@ __global__ void __launch_bounds__(256) crmsa_stats_logits_kernel(
     const float* __restrict__ phi, float2* __restrict__ stats, float* __restrict__ logits,
     Grid grid, int k) {
   constexpr int D = 128 * V;
-  int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  int lane = threadIdx.x & 31;
-  if (slot >= grid.Np) return;
-  int tok = grid.slot_to_token(slot);
-  if (tok >= grid.L) {  // zero pad token: LN output forced to 0 -> logits 0
-    if (lane == 0) stats[slot] = make_float2(0.f, 0.f);
-    if (phi && lane < k) logits[(size_t)slot * k + lane] = 0.f;
-    return;
+  extern __shared__ __align__(16) float phi_t[];  // [k][D]: phi transposed so lanes read float4 runs
+  if (phi) {
+    for (int i = threadIdx.x; i < D * k; i += blockDim.x) {
+      int c = i / k, n = i - c * k;
+      phi_t[n * D + c] = __ldg(phi + i);
+    }
+    __syncthreads();
   }
-  const float* xrow = x1 + (size_t)tok * D;
-  float4 v[V];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    v[i] = __ldg(reinterpret_cast<const float4*>(xrow) + lane + 32 * i);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  float mean = warp_sum(s) * (1.f / D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
-  }
-  float rstd = rsqrtf(warp_sum(q) * (1.f / D) + kLnEps);
-  if (lane == 0) stats[slot] = make_float2(mean, rstd);
-  if (!phi) return;
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
-    float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
-    v[i].x = (v[i].x - mean) * rstd * gm.x + bt.x;
-    v[i].y = (v[i].y - mean) * rstd * gm.y + bt.y;
-    v[i].z = (v[i].z - mean) * rstd * gm.z + bt.z;
-    v[i].w = (v[i].w - mean) * rstd * gm.w + bt.w;
-  }
-  for (int n = 0; n < k; ++n) {
-    float d = 0.f;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  float4 gm[V], bt[V];
+  if (phi) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      int c = 4 * (lane + 32 * i);
-      d = fmaf(v[i].x, __ldg(phi + (size_t)(c + 0) * k + n), d);
-      d = fmaf(v[i].y, __ldg(phi + (size_t)(c + 1) * k + n), d);
-      d = fmaf(v[i].z, __ldg(phi + (size_t)(c + 2) * k + n), d);
-      d = fmaf(v[i].w, __ldg(phi + (size_t)(c + 3) * k + n), d);
+      gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+      bt[i] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
     }
-    d = warp_sum(d);
-    if (lane == 0) logits[(size_t)slot * k + n] = d;
+  }
+  for (int slot = blockIdx.x * wpb + (threadIdx.x >> 5); slot < grid.Np; slot += gridDim.x * wpb) {
+    int tok = grid.slot_to_token(slot);
+    if (tok >= grid.L) {  // zero pad token: LN output forced to 0 -> logits 0
+      if (lane == 0) stats[slot] = make_float2(0.f, 0.f);
+      if (phi && lane < k) logits[(size_t)slot * k + lane] = 0.f;
+      continue;
+    }
+    const float* xrow = x1 + (size_t)tok * D;
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i] = __ldg(reinterpret_cast<const float4*>(xrow) + lane + 32 * i);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    float mean = warp_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    float rstd = rsqrtf(warp_sum(q) * (1.f / D) + kLnEps);
+    if (lane == 0) stats[slot] = make_float2(mean, rstd);
+    if (!phi) continue;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i].x = (v[i].x - mean) * rstd * gm[i].x + bt[i].x;
+      v[i].y = (v[i].y - mean) * rstd * gm[i].y + bt[i].y;
+      v[i].z = (v[i].z - mean) * rstd * gm[i].z + bt[i].z;
+      v[i].w = (v[i].w - mean) * rstd * gm[i].w + bt[i].w;
+    }
+    float mine = 0.f;  // lane n keeps logit n
+    for (int n = 0; n < k; ++n) {
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float4 ph = *reinterpret_cast<const float4*>(phi_t + n * D + 4 * (lane + 32 * i));
+        d = fmaf(v[i].x, ph.x, d); d = fmaf(v[i].y, ph.y, d);
+        d = fmaf(v[i].z, ph.z, d); d = fmaf(v[i].w, ph.w, d);
+      }
+      d = warp_sum(d);
+      if (lane == n) mine = d;
+    }
+    if (lane < k) logits[(size_t)slot * k + lane] = mine;
   }
 }
 
@@ -89,7 +104,8 @@ template <int KMAX>
 __global__ void __launch_bounds__(256) crmsa_combine_kernel(
     const float* __restrict__ x1, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float2* __restrict__ stats, const float* __restrict__ logits,
-    float* __restrict__ landmarks, float2* __restrict__ rstat, Grid grid, int D, int k) {
+    float* __restrict__ landmarks, float2* __restrict__ rstat, Grid grid, int D, int k,
+    bool round_out) {
   extern __shared__ __align__(16) float smem[];
   const int P = grid.P, rho = blockIdx.y, chunk = blockIdx.x;
   float* cw = smem;                                   // [P][k]
@@ -125,7 +141,7 @@ __global__ void __launch_bounds__(256) crmsa_combine_kernel(
 #pragma unroll
   for (int n = 0; n < KMAX; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  constexpr int U = 4;  // rows in flight per warp
+  constexpr int U = KMAX <= 4 ? 8 : 4;  // rows in flight per warp
   for (int p0 = warp; p0 < P; p0 += 8 * U) {
     float4 xv[U];
     float2 st[U];
@@ -173,7 +189,7 @@ __global__ void __launch_bounds__(256) crmsa_combine_kernel(
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += part[((size_t)(w * k + n)) * 128 + c];
-    landmarks[((size_t)n * grid.R + rho) * D + chunk * 128 + c] = s;
+    landmarks[((size_t)n * grid.R + rho) * D + chunk * 128 + c] = round_out ? to_tf32(s) : s;
   }
 }
 
@@ -181,7 +197,7 @@ __global__ void __launch_bounds__(256) crmsa_combine_kernel(
 // grid (heads, k), 256 threads; sequence length R = 64 (the CR-MSA grid is always 8x8 regions).
 __global__ void __launch_bounds__(256) landmark_attn_kernel(const float* __restrict__ lqkv,
                                                             float* __restrict__ lo, int D,
-                                                            int heads, float scale) {
+                                                            int heads, float scale, bool round_out) {
   constexpr int R = 64, CH = 32;
   __shared__ float qs[R][CH + 1];
   __shared__ float ks[R][CH + 1];
@@ -254,9 +270,11 @@ __global__ void __launch_bounds__(256) landmark_attn_kernel(const float* __restr
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
+      if (round_out) { o[i][0] = to_tf32(o[i][0]); o[i][1] = to_tf32(o[i][1]); }
       *reinterpret_cast<float2*>(lo + ((size_t)n * R + ty * 4 + i) * D + h * dh + c0 + tx * 2) =
           make_float2(o[i][0], o[i][1]);
+    }
   }
 }
 
@@ -272,35 +290,34 @@ __global__ void __launch_bounds__(256) crmsa_dispatch_kernel(
   if (tok >= grid.L) return;
   int slot = grid.token_to_slot(tok);
   int rho = slot / grid.P;
-  // dispatch weight of landmark n for this token: softmax over the k logits x min-max over the region
-  float wgt[RRT_MAX_K_DEV];
-  {
-    float mx = -INFINITY;
-    for (int n = 0; n < k; ++n) {
-      wgt[n] = __ldg(logits + (size_t)slot * k + n);
-      mx = fmaxf(mx, wgt[n]);
-    }
-    float sum = 0.f;
-    for (int n = 0; n < k; ++n) sum += __expf(wgt[n] - mx);
-    float inv = 1.f / sum;
-    for (int n = 0; n < k; ++n) {
-      float2 mm = __ldg(rstat + (size_t)rho * k + n);
-      float l = wgt[n];
-      wgt[n] = __expf(l - mx) * inv * ((l - mm.x) / (mm.y - mm.x + 1e-8f));
-    }
-  }
+  // the long-latency row loads go first; the (dependent, L2-resident) weight chain overlaps them
   float4 v[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
+  for (int i = 0; i < V; ++i)
     v[i] = __ldg(reinterpret_cast<const float4*>(x1 + (size_t)tok * D) + lane + 32 * i);
-    if (x0) {
-      float4 u = __ldg(reinterpret_cast<const float4*>(x0 + (size_t)tok * D) + lane + 32 * i);
-      v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+  float4 u0[V];
+  if (x0) {
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      u0[i] = __ldg(reinterpret_cast<const float4*>(x0 + (size_t)tok * D) + lane + 32 * i);
+  }
+  // dispatch weight of landmark n for this token: softmax over the k logits x min-max over the
+  // region.  Lane n (< k) owns landmark n; the weight is broadcast with a shuffle when used.
+  float lg = lane < k ? __ldg(logits + (size_t)slot * k + lane) : -INFINITY;
+  float2 mm = lane < k ? __ldg(rstat + (size_t)rho * k + lane) : make_float2(0.f, 1.f);
+  float mx = warp_max(lg);
+  float ex = lane < k ? __expf(lg - mx) : 0.f;
+  float inv = 1.f / warp_sum(ex);
+  float my_w = lane < k ? ex * inv * ((lg - mm.x) / (mm.y - mm.x + 1e-8f)) : 0.f;
+  if (x0) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i].x += u0[i].x; v[i].y += u0[i].y; v[i].z += u0[i].z; v[i].w += u0[i].w;
     }
   }
   for (int n = 0; n < k; ++n) {
     const float4* lrow = reinterpret_cast<const float4*>(lm + ((size_t)n * grid.R + rho) * D);
-    float w = wgt[n];
+    float w = __shfl_sync(0xffffffffu, my_w, n);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       float4 u = __ldg(lrow + lane + 32 * i);
@@ -355,7 +372,16 @@ cudaError_t launch_crmsa_stats_logits(const float* x1, const float* gamma, const
                                       const Grid& grid, int D, int k, cudaStream_t stream) {
   if (D % 128 || k > 32) return cudaErrorInvalidValue;
   int blocks = (grid.Np + 7) / 8;
-  RRT_DISPATCH_V(D, crmsa_stats_logits_kernel<V><<<blocks, 256, 0, stream>>>(x1, gamma, beta, phi, stats, logits, grid, k));
+  if (blocks > 148 * 4) blocks = 148 * 4;  // grid-stride over rows: phi is staged once per block
+  size_t smem = phi ? (size_t)D * k * sizeof(float) : 0;
+  RRT_DISPATCH_V(D, {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(crmsa_stats_logits_kernel<V>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    crmsa_stats_logits_kernel<V><<<blocks, 256, smem, stream>>>(x1, gamma, beta, phi, stats, logits, grid, k);
+  });
   return cudaGetLastError();
 }
 
@@ -367,7 +393,7 @@ cudaError_t launch_crmsa_mlp_logits(const float* hidden, const float* w2, float*
 
 cudaError_t launch_crmsa_combine(const float* x1, const float* gamma, const float* beta,
                                  const float2* stats, const float* logits, float* landmarks,
-                                 float2* rstat, const Grid& grid, int D, int k,
+                                 float2* rstat, const Grid& grid, int D, int k, bool round_out,
                                  cudaStream_t stream) {
   if (D % 128 || k < 1 || k > 16) return cudaErrorInvalidValue;
   size_t smem = ((((size_t)grid.P * k + 3) & ~(size_t)3) + (size_t)8 * k * 128) * sizeof(float);
@@ -379,7 +405,7 @@ cudaError_t launch_crmsa_combine(const float* x1, const float* gamma, const floa
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
     if (e != cudaSuccess) return e;                                                              \
     crmsa_combine_kernel<KM><<<g, 256, smem, stream>>>(x1, gamma, beta, stats, logits, landmarks, \
-                                                       rstat, grid, D, k);                       \
+                                                       rstat, grid, D, k, round_out);            \
   }
   if (k <= 4) RRT_COMBINE(4) else if (k <= 8) RRT_COMBINE(8) else RRT_COMBINE(16)
 #undef RRT_COMBINE
@@ -387,10 +413,10 @@ cudaError_t launch_crmsa_combine(const float* x1, const float* gamma, const floa
 }
 
 cudaError_t launch_landmark_attention(const float* lqkv, float* lo, int k, int R, int D, int heads,
-                                      cudaStream_t stream) {
+                                      bool round_out, cudaStream_t stream) {
   if (R != 64 || heads <= 0 || D % heads || (D / heads) % 32) return cudaErrorInvalidValue;
   float scale = 1.f / sqrtf((float)(D / heads));
-  landmark_attn_kernel<<<dim3(heads, k), 256, 0, stream>>>(lqkv, lo, D, heads, scale);
+  landmark_attn_kernel<<<dim3(heads, k), 256, 0, stream>>>(lqkv, lo, D, heads, scale, round_out);
   return cudaGetLastError();
 }
 

@@ -15,7 +15,7 @@ template <int HD>
 __global__ void __launch_bounds__(256) rmsa_attn_kernel(const float* __restrict__ qkv,
                                                         const float* __restrict__ taps,
                                                         float* __restrict__ o, Grid grid, int D,
-                                                        int epeg_k, float qscale) {
+                                                        int epeg_k, float qscale, bool round_out) {
   constexpr int LDS = HD + 4;
   constexpr int KS = HD / 8;  // k-steps over head_dim; also n-tiles of the output
   extern __shared__ __align__(16) float smem[];
@@ -161,15 +161,17 @@ __global__ void __launch_bounds__(256) rmsa_attn_kernel(const float* __restrict_
     float inv = 1.f / l_run[hh];
     float* orow = o + ((size_t)rho * P + q) * D + h * HD + 2 * t;
 #pragma unroll
-    for (int nd = 0; nd < KS; ++nd)
-      *reinterpret_cast<float2*>(orow + nd * 8) =
-          make_float2(oacc[nd][hh * 2] * inv, oacc[nd][hh * 2 + 1] * inv);
+    for (int nd = 0; nd < KS; ++nd) {
+      float a = oacc[nd][hh * 2] * inv, b = oacc[nd][hh * 2 + 1] * inv;
+      if (round_out) { a = to_tf32(a); b = to_tf32(b); }
+      *reinterpret_cast<float2*>(orow + nd * 8) = make_float2(a, b);
+    }
   }
 }
 
 template <int HD>
 cudaError_t launch(const float* qkv, const float* taps, float* o, const Grid& grid, int D,
-                   int heads, int epeg_k, cudaStream_t stream) {
+                   int heads, int epeg_k, bool round_out, cudaStream_t stream) {
   int nb = (grid.P + 15) / 16;
   int chunks = (nb + 7) / 8;
   int W = (nb + chunks - 1) / chunks;
@@ -182,19 +184,20 @@ cudaError_t launch(const float* qkv, const float* taps, float* o, const Grid& gr
   const float kLog2e = 1.4426950408889634f;
   float qscale = kLog2e / sqrtf((float)HD);
   dim3 g(chunks, heads, grid.R);
-  rmsa_attn_kernel<HD><<<g, 32 * W, smem, stream>>>(qkv, taps, o, grid, D, epeg_k, qscale);
+  rmsa_attn_kernel<HD><<<g, 32 * W, smem, stream>>>(qkv, taps, o, grid, D, epeg_k, qscale, round_out);
   return cudaGetLastError();
 }
 }  // namespace
 
 cudaError_t launch_rmsa_attention(const float* qkv, const float* taps, float* o, const Grid& grid,
-                                  int D, int heads, int epeg_k, cudaStream_t stream) {
+                                  int D, int heads, int epeg_k, bool round_out,
+                                  cudaStream_t stream) {
   if (heads <= 0 || D % heads) return cudaErrorInvalidValue;
   if (grid.R > 65535) return cudaErrorInvalidValue;
   switch (D / heads) {
-    case 32: return launch<32>(qkv, taps, o, grid, D, heads, epeg_k, stream);
-    case 64: return launch<64>(qkv, taps, o, grid, D, heads, epeg_k, stream);
-    case 128: return launch<128>(qkv, taps, o, grid, D, heads, epeg_k, stream);
+    case 32: return launch<32>(qkv, taps, o, grid, D, heads, epeg_k, round_out, stream);
+    case 64: return launch<64>(qkv, taps, o, grid, D, heads, epeg_k, round_out, stream);
+    case 128: return launch<128>(qkv, taps, o, grid, D, heads, epeg_k, round_out, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -139,6 +139,7 @@ class RRTEncoder(nn.Module):
         cfg.math_mode = cabi.RRT_MATH_TF32
         self._cfg = cfg
         self._crmsa_mlp = bool(crmsa_mlp)
+        self._shadow = {}
 
         if need_init:
             self.apply(initialize_weights)
@@ -160,18 +161,43 @@ class RRTEncoder(nn.Module):
             raise RuntimeError("RRTEncoder parameters must be contiguous")
         return t.data_ptr()
 
-    def _attn_weights(self, inner: InnerAttention, dst: cabi.RrtAttnWeights, device):
+    def _tf32_shadow(self, param: torch.Tensor):
+        """tf32-rounded copy of a GEMM weight (the form the tcgen05 kernels consume), cached in eval
+        mode and refreshed when the parameter's storage or version counter changes.  In training
+        mode (weights change every step) no shadow is passed and the library rounds per call.
+        In-place edits through ``.data`` bypass the version counter: call
+        ``invalidate_weight_cache()`` after such edits."""
+        if self.training:
+            return None
+        key = id(param)
+        ent = self._shadow.get(key)
+        if ent is None or ent[0] != (param.data_ptr(), param._version):
+            buf = torch.empty_like(param.detach())
+            rc = cabi.lib().rrt_round_tf32(param.data_ptr(), buf.data_ptr(), param.numel(),
+                                           torch.cuda.current_stream(param.device).cuda_stream)
+            cabi.check(rc, "rrt_round_tf32")
+            ent = ((param.data_ptr(), param._version), buf)
+            self._shadow[key] = ent
+        return ent[1].data_ptr()
+
+    def invalidate_weight_cache(self) -> None:
+        self._shadow.clear()
+
+    def _attn_weights(self, inner: InnerAttention, dst: cabi.RrtAttnWeights, device, shadows=False):
         p = self._ptr
         dst.qkv_w, dst.qkv_b = p(inner.qkv.weight, device), p(inner.qkv.bias, device)
         dst.proj_w, dst.proj_b = p(inner.proj.weight, device), p(inner.proj.bias, device)
         dst.pe_w = p(inner.pe.weight, device) if inner.pe is not None else None
+        if shadows:
+            dst.qkv_w_tf32 = self._tf32_shadow(inner.qkv.weight)
+            dst.proj_w_tf32 = self._tf32_shadow(inner.proj.weight)
 
     def _weights(self, device) -> cabi.RrtWeights:
         w, p = cabi.RrtWeights(), self._ptr
         w.norm_w, w.norm_b = p(self.norm.weight, device), p(self.norm.bias, device)
         for i, layer in enumerate(self.layers):
             w.layer_norm_w[i], w.layer_norm_b[i] = p(layer.norm.weight, device), p(layer.norm.bias, device)
-            self._attn_weights(layer.attn.attn, w.layer_attn[i], device)
+            self._attn_weights(layer.attn.attn, w.layer_attn[i], device, shadows=True)
         if self._cfg.cr_msa:
             cr = self.cr_msa
             w.cr_norm_w, w.cr_norm_b = p(cr.norm.weight, device), p(cr.norm.bias, device)
@@ -179,7 +205,7 @@ class RRTEncoder(nn.Module):
                 w.cr_phi_w1, w.cr_phi_w2 = p(cr.attn.phi[0].weight, device), p(cr.attn.phi[2].weight, device)
             else:
                 w.cr_phi = p(cr.attn.phi, device)
-            self._attn_weights(cr.attn.attn, w.cr_attn, device)
+            self._attn_weights(cr.attn.attn, w.cr_attn, device, shadows=True)
         return w
 
     def _check_mode(self, x):

@@ -76,5 +76,5 @@ def test_workspace_bytes_and_config_validation(lib):
 def test_struct_layout_matches_header_sizes():
     # 64-bit ABI: config = 6 int32 + double + 9 int32 (padded to 8) ; weights = pointer table
     assert C.sizeof(cabi.RrtConfig) == 72
-    assert C.sizeof(cabi.RrtAttnWeights) == 5 * 8
-    assert C.sizeof(cabi.RrtWeights) == 8 * (2 + 2 * 8 + 5 * 8 + 5 + 5)
+    assert C.sizeof(cabi.RrtAttnWeights) == 7 * 8
+    assert C.sizeof(cabi.RrtWeights) == 8 * (2 + 2 * 8 + 7 * 8 + 5 + 7)

@@ -100,6 +100,33 @@ def test_linear_matches_fp64(M, N, K):
     assert O.rel_err(y0.cpu(), ref - b) < TOL_TF32
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (9216, 1536, 512), (9216, 512, 512), (576, 1536, 512),
+                                   (100, 384, 128), (64, 256, 256), (192, 1536, 512), (1, 4, 32),
+                                   (50176, 1536, 512), (3000, 3072, 1024)])
+def test_tcgen05_linear_matches_fp64(M, N, K):
+    """The TMA + tcgen05 + TMEM GEMM (QKV / proj layers): M, N tails, single tile, many waves."""
+    g = torch.Generator().manual_seed(M * 13 + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    y = G.linear_tf32(a.cuda(), w.cuda(), b.cuda())
+    torch.cuda.synchronize()
+    ref = a.double() @ w.double().T + b.double()
+    assert O.rel_err(y.cpu(), ref) < TOL_TF32
+    # against the SAME rounded operands the error is fp32-accumulation only
+    ar, wr = G.round_tf32(a.cuda()).cpu().double(), G.round_tf32(w.cuda()).cpu().double()
+    assert O.rel_err(y.cpu(), ar @ wr.T + b.double()) < 2e-6
+    y2 = G.linear_tf32(a.cuda(), w.cuda(), b.cuda())
+    assert torch.equal(y, y2)
+
+
+def test_round_tf32_is_round_to_nearest():
+    x = torch.randn(4096, generator=torch.Generator().manual_seed(1)).cuda()
+    r = G.round_tf32(x)
+    assert ((r.view(torch.int32) & 0x1FFF) == 0).all()            # 13 low mantissa bits cleared
+    assert ((r - x).abs() <= x.abs() * 2.0 ** -11 * 1.0001).all()  # half an ulp of a 10-bit mantissa
+
+
 def test_linear_is_linear():
     g = torch.Generator().manual_seed(3)
     a1, a2 = torch.randn(500, 512, generator=g).cuda(), torch.randn(500, 512, generator=g).cuda()
