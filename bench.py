@@ -229,7 +229,7 @@ def run_b200_arm(args):
 
     def step():
         with torch.no_grad():
-            enc.forward_bags(bags, outs)
+            enc.forward_bags(bags, outs, lanes=args.lanes)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -315,6 +315,7 @@ def run_b200_arm(args):
                                    "tf32 tensor-core operands, fp32 accumulate",
                        "bags_per_step_per_gpu": B, "l2_policy": f"inputs larger than L2: {B} distinct bags "
                        f"({bytes_step / 1e6:.0f} MB in, same out) per step",
+                       "bags_in_flight_per_gpu": args.lanes,
                        "parallelism": f"bag-parallel x{world}, no data-path collective"},
             "us_per_bag": ms_total / args.steps / B * 1e3,
             "encoder_tflops": fl_bag * B * args.steps / (ms_total * 1e-3) / 1e12,
@@ -344,6 +345,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bags", type=int, default=16, help="distinct bags per step per GPU")
     ap.add_argument("--e2e-streams", type=int, default=3)
+    ap.add_argument("--lanes", type=int, default=4, help="bags in flight per GPU (internal streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -33,10 +33,11 @@ extern "C" {
 #define RRT_API __attribute__((visibility("default")))
 #endif
 
-#define RRT_ABI_VERSION 2
+#define RRT_ABI_VERSION 3
 #define RRT_MAX_RMSA_LAYERS 8 /* n_layers-1 R-MSA TransLayers (modules/rrt.py:143) */
 #define RRT_MAX_CRMSA_K 16    /* crmsa_k landmarks per region                         */
 #define RRT_MAX_EPEG_K 63     /* odd EPEG kernel length                               */
+#define RRT_MAX_LANES 4       /* concurrent bags inside rrt_encoder_forward_batch     */
 
 enum {
   RRT_OK = 0,
@@ -47,7 +48,8 @@ enum {
 
 /* math_mode: what the tensor-core contractions compute in.  I/O is always fp32. */
 enum {
-  RRT_MATH_TF32 = 0 /* tf32 operands, fp32 accumulate: meets the 1e-3 rel "fp32" bar */
+  RRT_MATH_F16 = 0 /* fp16 operands (10 mantissa bits, like tf32), fp32 accumulate / softmax /
+                      LayerNorm / residual stream: meets the 1e-3 rel "fp32" bar of the north star */
 };
 
 /* Constructor options of RRTEncoder that reach the hot path
@@ -80,11 +82,11 @@ typedef struct rrt_attn_weights {
   const float* proj_w; /* [D, D] */
   const float* proj_b; /* [D] */
   const float* pe_w;   /* [heads, epeg_k] or NULL */
-  /* Optional tf32-rounded shadows of qkv_w / proj_w (rrt_round_tf32), the form the tcgen05 GEMMs
-   * consume.  NULL: the library rounds into its workspace on every call (correct, ~2 us slower).
-   * The Python binding keeps shadows and refreshes them when a parameter changes. */
-  const float* qkv_w_tf32;
-  const float* proj_w_tf32;
+  /* Optional fp16 shadows of qkv_w / proj_w (rrt_convert_f16), the form the tcgen05 GEMMs
+   * consume.  NULL: the library converts into its workspace on every call (correct, a few us
+   * slower).  The Python binding keeps shadows and refreshes them when a parameter changes. */
+  const void* qkv_w_f16;  /* [3D, D] fp16 */
+  const void* proj_w_f16; /* [D, D] fp16 */
 } rrt_attn_weights;
 
 /* state_dict of one RRTEncoder, by reference name. */
@@ -99,6 +101,7 @@ typedef struct rrt_weights {
   const float* cr_phi;    /* cr_msa.attn.phi [D, k]           (crmsa_mlp = 0) */
   const float* cr_phi_w1; /* cr_msa.attn.phi.0.weight [D/4,D] (crmsa_mlp = 1) */
   const float* cr_phi_w2; /* cr_msa.attn.phi.2.weight [k,D/4] (crmsa_mlp = 1) */
+  const void* cr_phi_w1_f16; /* optional fp16 shadow of cr_phi_w1 */
   rrt_attn_weights cr_attn; /* cr_msa.attn.attn.* (pe_w NULL) */
 } rrt_weights;
 
@@ -122,9 +125,13 @@ RRT_API int rrt_encoder_forward(const rrt_config* cfg, const rrt_weights* w, con
                                 float* out, int64_t L, void* workspace, size_t workspace_bytes,
                                 void* stream);
 
-/* n_bags independent bags back to back on `stream` (one bag per forward, exactly as n_bags calls
- * of rrt_encoder_forward; the workspace is reused and must fit the longest bag).  xs / outs / Ls
- * are HOST arrays of device pointers / lengths. */
+/* n_bags independent bags (one bag per forward, results exactly as n_bags calls of
+ * rrt_encoder_forward).  xs / outs / Ls are HOST arrays of device pointers / lengths.
+ * Bags are independent, so when the workspace holds room for several bags
+ * (workspace_bytes >= lanes * rrt_workspace_bytes(longest bag), lanes <= RRT_MAX_LANES) the library
+ * runs `lanes` bags concurrently on internal streams that fork from and join back into `stream`
+ * (event fork/join: legal inside CUDA-graph capture); the small latency-bound kernels of one bag
+ * then fill the SMs the other bags leave idle.  With room for one bag the bags run back to back. */
 RRT_API int rrt_encoder_forward_batch(const rrt_config* cfg, const rrt_weights* w,
                                       const float* const* xs, float* const* outs,
                                       const int64_t* Ls, int32_t n_bags, void* workspace,
@@ -153,14 +160,18 @@ RRT_API int rrt_crmsa_block_forward(const rrt_config* cfg, const rrt_weights* w,
                                     int32_t apply_final_norm, void* workspace,
                                     size_t workspace_bytes, void* stream);
 
-/* dst[i] = src[i] rounded to nearest tf32 (10-bit mantissa), kept as fp32.  n % 4 == 0. */
-RRT_API int rrt_round_tf32(const float* src, float* dst, int64_t n, void* stream);
+/* Debug: when non-NULL, the first 8 CTAs of every tcgen05 GEMM launch write clock64 stamps of their
+ * pipeline phases into device_buffer[8][16] (int64).  NULL switches the trace off (default). */
+RRT_API int rrt_debug_set_gemm_trace(void* device_buffer);
 
-/* The tcgen05/TMA/TMEM GEMM the bag-sized layers run on, exposed for parity tests:
- * c[M,N] = a[M,K] @ w[N,K]^T + bias[N].  a and w must be tf32-representable (rrt_round_tf32),
- * 16-byte aligned; K % 32 == 0, N % 4 == 0. */
-RRT_API int rrt_linear_tf32_forward(const float* a, const float* w, const float* bias, float* c,
-                                    int64_t M, int32_t N, int32_t K, void* stream);
+/* dst[i] = fp16(src[i]), round to nearest, saturating at +-65504.  dst is n fp16 values; n % 4 == 0. */
+RRT_API int rrt_convert_f16(const float* src, void* dst, int64_t n, void* stream);
+
+/* The tcgen05/TMA/TMEM GEMM every linear layer of the path runs on, exposed for parity tests:
+ * c[M,N] (fp32) = a[M,K] (fp16) @ w[N,K]^T (fp16) + bias[N] (fp32, may be NULL).
+ * 16-byte aligned pointers; K % 64 == 0, N % 4 == 0. */
+RRT_API int rrt_linear_f16_forward(const void* a_f16, const void* w_f16, const float* bias, float* c,
+                                   int64_t M, int32_t N, int32_t K, void* stream);
 
 /* c[M,N] = a[M,K] @ w[N,K]^T + bias[N]   (nn.Linear; bias may be NULL).  K % 32 == 0. */
 RRT_API int rrt_linear_forward(const float* a, const float* w, const float* bias, float* c,

@@ -12,12 +12,13 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librrt_b200.so")
 
-RRT_ABI_VERSION = 2
+RRT_ABI_VERSION = 3
 RRT_MAX_RMSA_LAYERS = 8
 RRT_MAX_CRMSA_K = 16
 RRT_MAX_EPEG_K = 63
+RRT_MAX_LANES = 4
 RRT_OK, RRT_E_INVALID, RRT_E_WORKSPACE, RRT_E_CUDA = 0, -1, -2, -3
-RRT_MATH_TF32 = 0
+RRT_MATH_F16 = 0
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 
@@ -35,8 +36,8 @@ class RrtConfig(C.Structure):
 
 class RrtAttnWeights(C.Structure):
     _fields_ = [("qkv_w", c_float_p), ("qkv_b", c_float_p), ("proj_w", c_float_p),
-                ("proj_b", c_float_p), ("pe_w", c_float_p), ("qkv_w_tf32", c_float_p),
-                ("proj_w_tf32", c_float_p)]
+                ("proj_b", c_float_p), ("pe_w", c_float_p), ("qkv_w_f16", c_float_p),
+                ("proj_w_f16", c_float_p)]
 
 
 class RrtWeights(C.Structure):
@@ -46,7 +47,8 @@ class RrtWeights(C.Structure):
         ("layer_norm_b", c_float_p * RRT_MAX_RMSA_LAYERS),
         ("layer_attn", RrtAttnWeights * RRT_MAX_RMSA_LAYERS),
         ("cr_norm_w", c_float_p), ("cr_norm_b", c_float_p), ("cr_phi", c_float_p),
-        ("cr_phi_w1", c_float_p), ("cr_phi_w2", c_float_p), ("cr_attn", RrtAttnWeights),
+        ("cr_phi_w1", c_float_p), ("cr_phi_w2", c_float_p), ("cr_phi_w1_f16", c_float_p),
+        ("cr_attn", RrtAttnWeights),
     ]
 
 
@@ -74,8 +76,9 @@ SIGNATURES = {
     "rrt_stage_count": (C.c_int32, []),
     "rrt_stage_name": (C.c_char_p, [C.c_int32]),
     "rrt_stage_timing_read": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
-    "rrt_round_tf32": (C.c_int, [_P, _P, C.c_int64, _P]),
-    "rrt_linear_tf32_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "rrt_debug_set_gemm_trace": (C.c_int, [_P]),
+    "rrt_convert_f16": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "rrt_linear_f16_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "rrt_linear_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "rrt_layernorm_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
 }

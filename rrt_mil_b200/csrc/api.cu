@@ -150,26 +150,26 @@ int check_config(const rrt_config* c) {
     if (c->crmsa_heads < 1 || c->dim % c->crmsa_heads || (c->dim / c->crmsa_heads) % 32)
       return fail(RRT_E_INVALID, "CR-MSA head_dim must be a multiple of 32");
   }
-  if (c->math_mode != RRT_MATH_TF32) return fail(RRT_E_INVALID, "unknown math_mode");
+  if (c->math_mode != RRT_MATH_F16) return fail(RRT_E_INVALID, "unknown math_mode");
   return RRT_OK;
 }
 
 // ---- workspace ----------------------------------------------------------------------------
 struct Workspace {
-  float* z;        // [Np_r, D]   LN'd, padded, region-ordered tokens (also z2 for crmsa_mlp)
-  float* qkv;      // [Np_r, 3D]
-  float* o;        // [Np_r, D]
+  __half* z;       // [Np_r, D]   LN'd, padded, region-ordered tokens (also z2 for crmsa_mlp)
+  __half* qkv;     // [Np_r, 3D]
+  __half* o;       // [Np_r, D]
   float* xa;       // [L, D] residual stream ping
   float* xb;       // [L, D] residual stream pong
   float2* stats;   // [Np_c]
   float* logits;   // [Np_c, k]
   float2* rstat;   // [R_c, k]
-  float* lm;       // [k*R_c, D]
+  __half* lm;      // [k*R_c, D]
   float* lqkv;     // [k*R_c, 3D]
-  float* lo;       // [k*R_c, D]
+  __half* lo;      // [k*R_c, D]
   float* lout;     // [k*R_c, D]
   float* hidden;   // [Np_c, D/4] (crmsa_mlp)
-  float* wround;   // [3D*D + D*D] tf32-rounded weights when the caller passes no shadow
+  __half* wconv;   // [3D*D + D*D] fp16 weights when the caller passes no shadow
   size_t bytes;
 };
 
@@ -198,20 +198,20 @@ bool carve(const rrt_config* c, int64_t L, void* base, Workspace* ws) {
     off += align_up(nbytes);
     return r;
   };
-  ws->z = (float*)take(np_z * D * 4);
-  ws->qkv = (float*)take(np_r * 3 * D * 4);
-  ws->o = (float*)take(np_r * D * 4);
+  ws->z = (__half*)take(np_z * D * 2);
+  ws->qkv = (__half*)take(np_r * 3 * D * 2);
+  ws->o = (__half*)take(np_r * D * 2);
   ws->xa = (float*)take((size_t)L * D * 4);
   ws->xb = (float*)take((size_t)L * D * 4);
   ws->stats = (float2*)take(np_c * 8);
   ws->logits = (float*)take(np_c * k * 4);
   ws->rstat = (float2*)take(64 * k * 8);
-  ws->lm = (float*)take(T * D * 4);
+  ws->lm = (__half*)take(T * D * 2);
   ws->lqkv = (float*)take(T * 3 * D * 4);
-  ws->lo = (float*)take(T * D * 4);
+  ws->lo = (__half*)take(T * D * 2);
   ws->lout = (float*)take(T * D * 4);
   ws->hidden = (float*)take((c->cr_msa && c->crmsa_mlp) ? np_c * (D / 4) * 4 : 0);
-  ws->wround = (float*)take(4 * D * D * 4);
+  ws->wconv = (__half*)take(4 * D * D * 2);
   ws->bytes = off + 256;
   return true;
 }
@@ -225,6 +225,19 @@ int check_ws(const rrt_config* cfg, int64_t L, void* workspace, size_t workspace
 }
 
 // ---- blocks -------------------------------------------------------------------------------
+// fp16 form of a GEMM weight: the caller's shadow, or a conversion into the workspace
+int f16_weight(const float* w32, const void* shadow, __half* scratch, size_t n, cudaStream_t st,
+               const __half** out) {
+  if (shadow) {
+    *out = static_cast<const __half*>(shadow);
+    return RRT_OK;
+  }
+  StageScope s_(kStOther, st);
+  RRT_CUDA(rrt::launch_convert_f16(w32, scratch, n, st), "convert weight to fp16");
+  *out = scratch;
+  return RRT_OK;
+}
+
 int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
                const rrt_attn_weights* a, const float* x, float* x1, int64_t L, Workspace& ws,
                cudaStream_t st) {
@@ -232,39 +245,24 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
   if (!make_grid(L, c->region_num, c->region_size, c->min_region_num, c->min_region_ratio, &g))
     return fail(RRT_E_INVALID, "bad geometry");
   const int D = c->dim;
-  // bag-sized GEMMs run on tcgen05 (tf32 operands pre-rounded by the producing kernels)
-  const bool tc = rrt::gemm_tcgen05_supported(g.Np, 3 * D, D);
-  const float* wq = a->qkv_w;
-  const float* wp = a->proj_w;
-  if (tc) {
-    wq = a->qkv_w_tf32;
-    wp = a->proj_w_tf32;
-    if (!wq || !wp) {
-      StageScope s_(kStOther, st, 2);
-      if (!wq) {
-        RRT_CUDA(rrt::launch_round_tf32(a->qkv_w, ws.wround, (size_t)3 * D * D, st), "round qkv_w");
-        wq = ws.wround;
-      }
-      if (!wp) {
-        RRT_CUDA(rrt::launch_round_tf32(a->proj_w, ws.wround + (size_t)3 * D * D, (size_t)D * D, st),
-                 "round proj_w");
-        wp = ws.wround + (size_t)3 * D * D;
-      }
-    }
-  }
-  { StageScope s_(kStLnPartition, st); RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws.z, g, D, tc, st), "ln_partition"); }
+  const __half *wq, *wp;
+  int rc = f16_weight(a->qkv_w, a->qkv_w_f16, ws.wconv, (size_t)3 * D * D, st, &wq);
+  if (rc) return rc;
+  rc = f16_weight(a->proj_w, a->proj_w_f16, ws.wconv + (size_t)3 * D * D, (size_t)D * D, st, &wp);
+  if (rc) return rc;
+  { StageScope s_(kStLnPartition, st);
+    RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws.z, g, D, st), "ln_partition"); }
   rrt::GemmEpilogue e1;
   e1.bias = c->qkv_bias ? a->qkv_b : nullptr;
   { StageScope s_(kStQkvGemm, st);
-    if (tc) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.z, wq, ws.qkv, g.Np, 3 * D, D, e1, st), "qkv gemm (tcgen05)");
-    else RRT_CUDA(rrt::launch_gemm_mma(ws.z, wq, ws.qkv, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
+    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.z, wq, ws.qkv, true, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
   { StageScope s_(kStRmsaAttn, st);
     const float* taps = c->epeg ? a->pe_w : nullptr;
     if (rrt::rmsa_attention_f16_supported(g, D, c->n_heads))
-      RRT_CUDA(rrt::launch_rmsa_attention_f16(ws.qkv, taps, ws.o, g, D, c->n_heads, c->epeg_k, tc, st),
+      RRT_CUDA(rrt::launch_rmsa_attention_f16(ws.qkv, taps, ws.o, g, D, c->n_heads, c->epeg_k, st),
                "rmsa attention (region-resident)");
     else
-      RRT_CUDA(rrt::launch_rmsa_attention(ws.qkv, taps, ws.o, g, D, c->n_heads, c->epeg_k, tc, st),
+      RRT_CUDA(rrt::launch_rmsa_attention(ws.qkv, taps, ws.o, g, D, c->n_heads, c->epeg_k, st),
                "rmsa attention (flash)"); }
   rrt::GemmEpilogue e2;
   e2.mode = rrt::kEpiResidualUnpart;
@@ -272,8 +270,7 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
   e2.resid = x;
   e2.grid = g;
   { StageScope s_(kStProjGemm, st);
-    if (tc) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.o, wp, x1, g.Np, D, D, e2, st), "proj gemm (tcgen05)");
-    else RRT_CUDA(rrt::launch_gemm_mma(ws.o, wp, x1, g.Np, D, D, e2, st), "proj gemm"); }
+    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.o, wp, x1, false, g.Np, D, D, e2, st), "proj gemm"); }
   return RRT_OK;
 }
 
@@ -287,12 +284,15 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
     { StageScope s_(kStCrLogits, st);
       RRT_CUDA(rrt::launch_crmsa_stats_logits(x1, w->cr_norm_w, w->cr_norm_b, nullptr, ws.stats,
                                               nullptr, g, D, k, st), "crmsa stats"); }
+    const __half* w1;
+    int rc = f16_weight(w->cr_phi_w1, w->cr_phi_w1_f16, ws.wconv, (size_t)(D / 4) * D, st, &w1);
+    if (rc) return rc;
     StageScope s_mlp(kStCrMlp, st, 3);
-    RRT_CUDA(rrt::launch_ln_partition(x1, w->cr_norm_w, w->cr_norm_b, ws.z, g, D, false, st),
+    RRT_CUDA(rrt::launch_ln_partition(x1, w->cr_norm_w, w->cr_norm_b, ws.z, g, D, st),
              "crmsa ln_partition");
     rrt::GemmEpilogue eh;
     eh.mode = rrt::kEpiTanh;
-    RRT_CUDA(rrt::launch_gemm_mma(ws.z, w->cr_phi_w1, ws.hidden, g.Np, D / 4, D, eh, st), "phi.0");
+    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.z, w1, ws.hidden, false, g.Np, D / 4, D, eh, st), "phi.0");
     RRT_CUDA(rrt::launch_crmsa_mlp_logits(ws.hidden, w->cr_phi_w2, ws.logits, g.Np, D / 4, k, st),
              "phi.2");
   } else {
@@ -301,43 +301,26 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
     RRT_CUDA(rrt::launch_crmsa_stats_logits(x1, w->cr_norm_w, w->cr_norm_b, w->cr_phi, ws.stats,
                                             ws.logits, g, D, k, st), "crmsa logits");
   }
-  // landmark GEMMs (M = k*64 rows) on the narrow-tile tcgen05 kernel; operands rounded by producers
-  const bool tc = rrt::gemm_tcgen05_supported(T, 3 * D, D);
-  const float* wq = w->cr_attn.qkv_w;
-  const float* wp = w->cr_attn.proj_w;
-  if (tc) {
-    wq = w->cr_attn.qkv_w_tf32;
-    wp = w->cr_attn.proj_w_tf32;
-    if (!wq || !wp) {
-      if (!ws.wround) return fail(RRT_E_WORKSPACE, "no room for rounded landmark weights");
-      StageScope s_(kStOther, st, 2);
-      if (!wq) {
-        RRT_CUDA(rrt::launch_round_tf32(w->cr_attn.qkv_w, ws.wround, (size_t)3 * D * D, st), "round");
-        wq = ws.wround;
-      }
-      if (!wp) {
-        RRT_CUDA(rrt::launch_round_tf32(w->cr_attn.proj_w, ws.wround + (size_t)3 * D * D,
-                                        (size_t)D * D, st), "round");
-        wp = ws.wround + (size_t)3 * D * D;
-      }
-    }
-  }
+  const __half *wq, *wp;
+  int rc = f16_weight(w->cr_attn.qkv_w, w->cr_attn.qkv_w_f16, ws.wconv, (size_t)3 * D * D, st, &wq);
+  if (rc) return rc;
+  rc = f16_weight(w->cr_attn.proj_w, w->cr_attn.proj_w_f16, ws.wconv + (size_t)3 * D * D,
+                  (size_t)D * D, st, &wp);
+  if (rc) return rc;
   { StageScope s_(kStCrCombine, st);
     RRT_CUDA(rrt::launch_crmsa_combine(x1, w->cr_norm_w, w->cr_norm_b, ws.stats, ws.logits, ws.lm,
-                                       ws.rstat, g, D, k, tc, st), "crmsa combine"); }
+                                       ws.rstat, g, D, k, st), "crmsa combine"); }
   rrt::GemmEpilogue e1;
   e1.bias = c->qkv_bias ? w->cr_attn.qkv_b : nullptr;
   { StageScope s_(kStLmQkv, st);
-    if (tc) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lm, wq, ws.lqkv, T, 3 * D, D, e1, st), "landmark qkv");
-    else RRT_CUDA(rrt::launch_gemm_mma(ws.lm, wq, ws.lqkv, T, 3 * D, D, e1, st), "landmark qkv"); }
+    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lm, wq, ws.lqkv, false, T, 3 * D, D, e1, st), "landmark qkv"); }
   { StageScope s_(kStLmAttn, st);
-    RRT_CUDA(rrt::launch_landmark_attention(ws.lqkv, ws.lo, k, g.R, D, c->crmsa_heads, tc, st),
+    RRT_CUDA(rrt::launch_landmark_attention(ws.lqkv, ws.lo, k, g.R, D, c->crmsa_heads, st),
              "landmark attention"); }
   rrt::GemmEpilogue e2;
   e2.bias = w->cr_attn.proj_b;
   { StageScope s_(kStLmProj, st);
-    if (tc) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lo, wp, ws.lout, T, D, D, e2, st), "landmark proj");
-    else RRT_CUDA(rrt::launch_gemm_mma(ws.lo, wp, ws.lout, T, D, D, e2, st), "landmark proj"); }
+    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lo, wp, ws.lout, false, T, D, D, e2, st), "landmark proj"); }
   { StageScope s_(kStCrDispatch, st);
     RRT_CUDA(rrt::launch_crmsa_dispatch(x1, x0, ws.logits, ws.rstat, ws.lout,
                                         final_norm ? w->norm_w : nullptr,
@@ -406,6 +389,30 @@ RRT_API int rrt_encoder_forward(const rrt_config* cfg, const rrt_weights* w, con
   return encoder_forward(cfg, w, x, out, L, ws, (cudaStream_t)stream);
 }
 
+namespace {
+// Internal fork/join lanes of the batch entry point (one process drives one GPU).
+struct Lanes {
+  cudaStream_t stream[RRT_MAX_LANES] = {};
+  cudaEvent_t done[RRT_MAX_LANES] = {};
+  cudaEvent_t fork = nullptr;
+  bool ready = false;
+};
+Lanes g_lanes;
+std::mutex g_lanes_mu;
+
+cudaError_t ensure_lanes() {
+  std::lock_guard<std::mutex> l(g_lanes_mu);
+  if (g_lanes.ready) return cudaSuccess;
+  cudaError_t e = cudaEventCreateWithFlags(&g_lanes.fork, cudaEventDisableTiming);
+  for (int i = 1; i < RRT_MAX_LANES && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&g_lanes.stream[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_lanes.done[i], cudaEventDisableTiming);
+  }
+  g_lanes.ready = (e == cudaSuccess);
+  return e;
+}
+}  // namespace
+
 RRT_API int rrt_encoder_forward_batch(const rrt_config* cfg, const rrt_weights* w,
                                       const float* const* xs, float* const* outs,
                                       const int64_t* Ls, int32_t n_bags, void* workspace,
@@ -413,15 +420,43 @@ RRT_API int rrt_encoder_forward_batch(const rrt_config* cfg, const rrt_weights* 
   int rc = check_config(cfg);
   if (rc) return rc;
   if (!w || !xs || !outs || !Ls || n_bags < 0) return fail(RRT_E_INVALID, "bad argument");
+  if (n_bags == 0) return RRT_OK;
+  if (!workspace || (((uintptr_t)workspace) & 255))
+    return fail(RRT_E_INVALID, "workspace must be non-NULL and 256-byte aligned");
+  size_t per_bag = 0;
   for (int i = 0; i < n_bags; ++i) {
     if (!xs[i] || !outs[i] || xs[i] == outs[i]) return fail(RRT_E_INVALID, "bad bag pointer");
     Workspace ws{};
-    rc = check_ws(cfg, Ls[i], workspace, workspace_bytes, &ws);
-    if (rc) return rc;
-    rc = encoder_forward(cfg, w, xs[i], outs[i], Ls[i], ws, (cudaStream_t)stream);
-    if (rc) return rc;
+    if (!carve(cfg, Ls[i], nullptr, &ws)) return fail(RRT_E_INVALID, "bad bag length / geometry");
+    if (ws.bytes > per_bag) per_bag = ws.bytes;
   }
-  return RRT_OK;
+  per_bag = align_up(per_bag);
+  if (workspace_bytes < per_bag) return fail(RRT_E_WORKSPACE, "workspace too small");
+  int lanes = (int)(workspace_bytes / per_bag);
+  if (lanes > RRT_MAX_LANES) lanes = RRT_MAX_LANES;
+  if (lanes > n_bags) lanes = n_bags;
+  cudaStream_t user = (cudaStream_t)stream;
+  cudaStream_t lane_stream[RRT_MAX_LANES] = {user, user, user, user};
+  if (lanes > 1) {
+    RRT_CUDA(ensure_lanes(), "lane streams");
+    RRT_CUDA(cudaEventRecord(g_lanes.fork, user), "fork");
+    for (int l = 1; l < lanes; ++l) {
+      lane_stream[l] = g_lanes.stream[l];
+      RRT_CUDA(cudaStreamWaitEvent(lane_stream[l], g_lanes.fork, 0), "fork wait");
+    }
+  }
+  for (int i = 0; i < n_bags; ++i) {
+    const int l = i % lanes;
+    Workspace ws{};
+    carve(cfg, Ls[i], (char*)workspace + (size_t)l * per_bag, &ws);
+    rc = encoder_forward(cfg, w, xs[i], outs[i], Ls[i], ws, lane_stream[l]);
+    if (rc) break;
+  }
+  for (int l = 1; l < lanes; ++l) {  // always join, also on error, so `stream` stays ordered
+    cudaEventRecord(g_lanes.done[l], lane_stream[l]);
+    cudaStreamWaitEvent(user, g_lanes.done[l], 0);
+  }
+  return rc;
 }
 
 RRT_API int rrt_encoder_forward_host(const rrt_config* cfg, const rrt_weights* w,
@@ -507,21 +542,29 @@ RRT_API int rrt_linear_forward(const float* a, const float* w, const float* bias
   return RRT_OK;
 }
 
-RRT_API int rrt_round_tf32(const float* src, float* dst, int64_t n, void* stream) {
-  if (!src || !dst || n < 0 || n % 4) return fail(RRT_E_INVALID, "bad argument");
-  StageScope s_(kStOther, (cudaStream_t)stream);
-  RRT_CUDA(rrt::launch_round_tf32(src, dst, (size_t)n, (cudaStream_t)stream), "round_tf32");
+RRT_API int rrt_debug_set_gemm_trace(void* device_buffer) {
+  rrt::g_gemm_trace = static_cast<long long*>(device_buffer);
   return RRT_OK;
 }
 
-RRT_API int rrt_linear_tf32_forward(const float* a, const float* w, const float* bias, float* c,
-                                    int64_t M, int32_t N, int32_t K, void* stream) {
-  if (!a || !w || !c || M < 1 || M > (1 << 30)) return fail(RRT_E_INVALID, "bad argument");
+RRT_API int rrt_convert_f16(const float* src, void* dst, int64_t n, void* stream) {
+  if (!src || !dst || n < 0 || n % 4) return fail(RRT_E_INVALID, "bad argument");
+  StageScope s_(kStOther, (cudaStream_t)stream);
+  RRT_CUDA(rrt::launch_convert_f16(src, static_cast<__half*>(dst), (size_t)n, (cudaStream_t)stream),
+           "convert_f16");
+  return RRT_OK;
+}
+
+RRT_API int rrt_linear_f16_forward(const void* a_f16, const void* w_f16, const float* bias, float* c,
+                                   int64_t M, int32_t N, int32_t K, void* stream) {
+  if (!a_f16 || !w_f16 || !c || M < 1 || M > (1 << 30)) return fail(RRT_E_INVALID, "bad argument");
   if (!rrt::gemm_tcgen05_supported((int)M, N, K)) return fail(RRT_E_INVALID, "shape not supported");
   rrt::GemmEpilogue e;
   e.bias = bias;
   StageScope s_(kStOther, (cudaStream_t)stream);
-  RRT_CUDA(rrt::launch_gemm_tcgen05(a, w, c, (int)M, N, K, e, (cudaStream_t)stream), "linear (tcgen05)");
+  RRT_CUDA(rrt::launch_gemm_tcgen05(static_cast<const __half*>(a_f16), static_cast<const __half*>(w_f16),
+                                    c, false, (int)M, N, K, e, (cudaStream_t)stream),
+           "linear (tcgen05)");
   return RRT_OK;
 }
 

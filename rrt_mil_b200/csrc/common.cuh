@@ -1,5 +1,6 @@
 // Shared device/host helpers for the RRTEncoder kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
@@ -60,6 +61,26 @@ __device__ __forceinline__ uint32_t tf32_bits(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
+}
+
+// two fp32 -> packed fp16x2 (lo in bits 0..15), round to nearest, saturating to +-65504 instead of
+// overflowing to inf.  fp16 keeps 10 mantissa bits, the same as tf32: it is the storage format of
+// every INTERNAL activation (LayerNorm output, q/k/v, attention output, landmarks) and of the
+// weight shadows the tensor cores read; the residual stream, statistics and accumulators are fp32.
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint2 pack_h4(float4 v) {
+  return make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+__device__ __forceinline__ float4 unpack_h4(uint2 u) {
+  float2 a = unpack_h2(u.x), b = unpack_h2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
 }
 
 // D(16x8,f32) += A(16x8,tf32,row) * B(8x8,tf32,col)

@@ -104,8 +104,7 @@ template <int KMAX>
 __global__ void __launch_bounds__(256) crmsa_combine_kernel(
     const float* __restrict__ x1, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float2* __restrict__ stats, const float* __restrict__ logits,
-    float* __restrict__ landmarks, float2* __restrict__ rstat, Grid grid, int D, int k,
-    bool round_out) {
+    __half* __restrict__ landmarks, float2* __restrict__ rstat, Grid grid, int D, int k) {
   extern __shared__ __align__(16) float smem[];
   const int P = grid.P, rho = blockIdx.y, chunk = blockIdx.x;
   float* cw = smem;                                   // [P][k]
@@ -189,15 +188,15 @@ __global__ void __launch_bounds__(256) crmsa_combine_kernel(
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += part[((size_t)(w * k + n)) * 128 + c];
-    landmarks[((size_t)n * grid.R + rho) * D + chunk * 128 + c] = round_out ? to_tf32(s) : s;
+    landmarks[((size_t)n * grid.R + rho) * D + chunk * 128 + c] = __float2half_rn(s);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // grid (heads, k), 256 threads; sequence length R = 64 (the CR-MSA grid is always 8x8 regions).
 __global__ void __launch_bounds__(256) landmark_attn_kernel(const float* __restrict__ lqkv,
-                                                            float* __restrict__ lo, int D,
-                                                            int heads, float scale, bool round_out) {
+                                                            __half* __restrict__ lo, int D,
+                                                            int heads, float scale) {
   constexpr int R = 64, CH = 32;
   __shared__ float qs[R][CH + 1];
   __shared__ float ks[R][CH + 1];
@@ -270,11 +269,9 @@ __global__ void __launch_bounds__(256) landmark_attn_kernel(const float* __restr
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (round_out) { o[i][0] = to_tf32(o[i][0]); o[i][1] = to_tf32(o[i][1]); }
-      *reinterpret_cast<float2*>(lo + ((size_t)n * R + ty * 4 + i) * D + h * dh + c0 + tx * 2) =
-          make_float2(o[i][0], o[i][1]);
-    }
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<uint32_t*>(lo + ((size_t)n * R + ty * 4 + i) * D + h * dh + c0 + tx * 2) =
+          pack_h2(o[i][0], o[i][1]);
   }
 }
 
@@ -392,8 +389,8 @@ cudaError_t launch_crmsa_mlp_logits(const float* hidden, const float* w2, float*
 }
 
 cudaError_t launch_crmsa_combine(const float* x1, const float* gamma, const float* beta,
-                                 const float2* stats, const float* logits, float* landmarks,
-                                 float2* rstat, const Grid& grid, int D, int k, bool round_out,
+                                 const float2* stats, const float* logits, __half* landmarks,
+                                 float2* rstat, const Grid& grid, int D, int k,
                                  cudaStream_t stream) {
   if (D % 128 || k < 1 || k > 16) return cudaErrorInvalidValue;
   size_t smem = ((((size_t)grid.P * k + 3) & ~(size_t)3) + (size_t)8 * k * 128) * sizeof(float);
@@ -405,18 +402,18 @@ cudaError_t launch_crmsa_combine(const float* x1, const float* gamma, const floa
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
     if (e != cudaSuccess) return e;                                                              \
     crmsa_combine_kernel<KM><<<g, 256, smem, stream>>>(x1, gamma, beta, stats, logits, landmarks, \
-                                                       rstat, grid, D, k, round_out);            \
+                                                       rstat, grid, D, k);                       \
   }
   if (k <= 4) RRT_COMBINE(4) else if (k <= 8) RRT_COMBINE(8) else RRT_COMBINE(16)
 #undef RRT_COMBINE
   return cudaGetLastError();
 }
 
-cudaError_t launch_landmark_attention(const float* lqkv, float* lo, int k, int R, int D, int heads,
-                                      bool round_out, cudaStream_t stream) {
+cudaError_t launch_landmark_attention(const float* lqkv, __half* lo, int k, int R, int D, int heads,
+                                      cudaStream_t stream) {
   if (R != 64 || heads <= 0 || D % heads || (D / heads) % 32) return cudaErrorInvalidValue;
   float scale = 1.f / sqrtf((float)(D / heads));
-  landmark_attn_kernel<<<dim3(heads, k), 256, 0, stream>>>(lqkv, lo, D, heads, scale, round_out);
+  landmark_attn_kernel<<<dim3(heads, k), 256, 0, stream>>>(lqkv, lo, D, heads, scale);
   return cudaGetLastError();
 }
 

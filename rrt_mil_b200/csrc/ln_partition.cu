@@ -4,11 +4,18 @@
 
 namespace rrt {
 
-template <int V>  // D = 128 * V
+__device__ __forceinline__ void store4(float* row, int idx4, float4 v) {
+  reinterpret_cast<float4*>(row)[idx4] = v;
+}
+__device__ __forceinline__ void store4(__half* row, int idx4, float4 v) {
+  reinterpret_cast<uint2*>(row)[idx4] = pack_h4(v);
+}
+
+template <int V, typename OutT>  // D = 128 * V
 __device__ __forceinline__ void ln_row(const float* __restrict__ xrow, const float* __restrict__ x0row,
                                        const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, float* __restrict__ orow,
-                                       int lane, bool round_tf32) {
+                                       const float* __restrict__ beta, OutT* __restrict__ orow,
+                                       int lane) {
   float4 v[V];
   float s = 0.f;
 #pragma unroll
@@ -38,8 +45,7 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ xrow, const flo
     o.y = (v[i].y - mean) * rstd * gm.y + bt.y;
     o.z = (v[i].z - mean) * rstd * gm.z + bt.z;
     o.w = (v[i].w - mean) * rstd * gm.w + bt.w;
-    if (round_tf32) { o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w); }
-    reinterpret_cast<float4*>(orow)[lane + 32 * i] = o;
+    store4(orow, lane + 32 * i, o);
   }
 }
 
@@ -47,21 +53,19 @@ template <int V>
 __global__ void __launch_bounds__(256) ln_partition_kernel(const float* __restrict__ x,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta,
-                                                           float* __restrict__ z, Grid grid,
-                                                           bool round_tf32) {
+                                                           __half* __restrict__ z, Grid grid) {
   const int D = 128 * V;
   int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (slot >= grid.Np) return;
   int t = grid.slot_to_token(slot);
-  float* zrow = z + (size_t)slot * D;
+  __half* zrow = z + (size_t)slot * D;
   if (t >= grid.L) {  // pad token: exact zeros AFTER the norm (modules/rmsa.py:200)
 #pragma unroll
-    for (int i = 0; i < V; ++i)
-      reinterpret_cast<float4*>(zrow)[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < V; ++i) reinterpret_cast<uint2*>(zrow)[lane + 32 * i] = make_uint2(0u, 0u);
     return;
   }
-  ln_row<V>(x + (size_t)t * D, nullptr, gamma, beta, zrow, lane, round_tf32);
+  ln_row<V>(x + (size_t)t * D, nullptr, gamma, beta, zrow, lane);
 }
 
 template <int V>
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
   int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= L) return;
   ln_row<V>(x1 + (size_t)t * D, x0 ? x0 + (size_t)t * D : nullptr, gamma, beta,
-            out + (size_t)t * D, threadIdx.x & 31, false);
+            out + (size_t)t * D, threadIdx.x & 31);
 }
 
 #define RRT_DISPATCH_V(D, ...)                         \
@@ -88,12 +92,12 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
     default: return cudaErrorInvalidValue;             \
   }
 
-cudaError_t launch_ln_partition(const float* x, const float* gamma, const float* beta, float* z,
-                                const Grid& grid, int D, bool round_tf32, cudaStream_t stream) {
+cudaError_t launch_ln_partition(const float* x, const float* gamma, const float* beta, __half* z,
+                                const Grid& grid, int D, cudaStream_t stream) {
   if (D % 128) return cudaErrorInvalidValue;
   const int wpb = 8;
   int blocks = (grid.Np + wpb - 1) / wpb;
-  RRT_DISPATCH_V(D, ln_partition_kernel<V><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, z, grid, round_tf32));
+  RRT_DISPATCH_V(D, ln_partition_kernel<V><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, z, grid));
   return cudaGetLastError();
 }
 

@@ -2,8 +2,9 @@
 //   Q' = scale * (Q + dwconv1d_P(Q; taps_h))      -- EPEG moved from the logit map onto Q
 //   O  = softmax(Q' K^T) V                          -- flash-style, online softmax over KV tiles
 // (modules/rmsa.py:103-122; SURVEY.md 0.2-1 for the EPEG identity.)
-// Generic in P (any region size, KV tiled by 64) and head_dim in {32,64,128}.  Tensor math on
-// mma.sync m16n8k8 tf32 with fp32 accumulation and fp32 softmax state.
+// Generic in P (any region size, KV tiled by 64) and head_dim in {32,64,128}: the fallback for
+// regions of more than 256 tokens (rmsa_attn_f16.cu covers the rest).  fp16 q/k/v in, fp16 O out;
+// tensor math on mma.sync m16n8k8 tf32 with fp32 accumulation and fp32 softmax state.
 #include "kernels.cuh"
 
 namespace rrt {
@@ -12,10 +13,10 @@ namespace {
 constexpr int BKV = 64;
 
 template <int HD>
-__global__ void __launch_bounds__(256) rmsa_attn_kernel(const float* __restrict__ qkv,
+__global__ void __launch_bounds__(256) rmsa_attn_kernel(const __half* __restrict__ qkv,
                                                         const float* __restrict__ taps,
-                                                        float* __restrict__ o, Grid grid, int D,
-                                                        int epeg_k, float qscale, bool round_out) {
+                                                        __half* __restrict__ o, Grid grid, int D,
+                                                        int epeg_k, float qscale) {
   constexpr int LDS = HD + 4;
   constexpr int KS = HD / 8;  // k-steps over head_dim; also n-tiles of the output
   extern __shared__ __align__(16) float smem[];
@@ -31,14 +32,14 @@ __global__ void __launch_bounds__(256) rmsa_attn_kernel(const float* __restrict_
   const int rho = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 16 * W;
   const int P = grid.P;
   const size_t ld = 3 * (size_t)D;
-  const float* base = qkv + (size_t)rho * P * ld + h * HD;
+  const __half* base = qkv + (size_t)rho * P * ld + h * HD;
 
   // ---- stage Q rows (with the conv halo) and the taps of this head
   for (int i = tid; i < qrows * (HD / 4); i += blockDim.x) {
     int r = i / (HD / 4), c = (i - r * (HD / 4)) * 4;
     int p = q0 - pad + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p >= 0 && p < P) v = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * ld + c));
+    if (p >= 0 && p < P) v = unpack_h4(__ldg(reinterpret_cast<const uint2*>(base + (size_t)p * ld + c)));
     *reinterpret_cast<float4*>(Qs + r * LDS + c) = v;
   }
   if (taps)
@@ -77,13 +78,15 @@ __global__ void __launch_bounds__(256) rmsa_attn_kernel(const float* __restrict_
     for (int i = tid; i < BKV * (HD / 4); i += blockDim.x) {
       int r = i / (HD / 4), c = (i - r * (HD / 4)) * 4;
       int p = kt0 + r;
-      bool ok = p < P;
-      const float* src = base + (size_t)(ok ? p : 0) * ld + c;
-      cp_async16(Ks + r * LDS + c, src + D, ok);
-      cp_async16(Vs + r * LDS + c, src + 2 * D, ok);
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (p < P) {
+        const __half* src = base + (size_t)p * ld + c;
+        kv = unpack_h4(__ldg(reinterpret_cast<const uint2*>(src + D)));
+        vv = unpack_h4(__ldg(reinterpret_cast<const uint2*>(src + 2 * D)));
+      }
+      *reinterpret_cast<float4*>(Ks + r * LDS + c) = kv;
+      *reinterpret_cast<float4*>(Vs + r * LDS + c) = vv;
     }
-    cp_async_commit();
-    cp_async_wait<0>();
     __syncthreads();
 
     float s[BKV / 8][4];
@@ -159,19 +162,17 @@ __global__ void __launch_bounds__(256) rmsa_attn_kernel(const float* __restrict_
     int q = q0 + 16 * warp + g + hh * 8;
     if (q >= P) continue;
     float inv = 1.f / l_run[hh];
-    float* orow = o + ((size_t)rho * P + q) * D + h * HD + 2 * t;
+    __half* orow = o + ((size_t)rho * P + q) * D + h * HD + 2 * t;
 #pragma unroll
-    for (int nd = 0; nd < KS; ++nd) {
-      float a = oacc[nd][hh * 2] * inv, b = oacc[nd][hh * 2 + 1] * inv;
-      if (round_out) { a = to_tf32(a); b = to_tf32(b); }
-      *reinterpret_cast<float2*>(orow + nd * 8) = make_float2(a, b);
-    }
+    for (int nd = 0; nd < KS; ++nd)
+      *reinterpret_cast<uint32_t*>(orow + nd * 8) =
+          pack_h2(oacc[nd][hh * 2] * inv, oacc[nd][hh * 2 + 1] * inv);
   }
 }
 
 template <int HD>
-cudaError_t launch(const float* qkv, const float* taps, float* o, const Grid& grid, int D,
-                   int heads, int epeg_k, bool round_out, cudaStream_t stream) {
+cudaError_t launch(const __half* qkv, const float* taps, __half* o, const Grid& grid, int D,
+                   int heads, int epeg_k, cudaStream_t stream) {
   int nb = (grid.P + 15) / 16;
   int chunks = (nb + 7) / 8;
   int W = (nb + chunks - 1) / chunks;
@@ -184,20 +185,19 @@ cudaError_t launch(const float* qkv, const float* taps, float* o, const Grid& gr
   const float kLog2e = 1.4426950408889634f;
   float qscale = kLog2e / sqrtf((float)HD);
   dim3 g(chunks, heads, grid.R);
-  rmsa_attn_kernel<HD><<<g, 32 * W, smem, stream>>>(qkv, taps, o, grid, D, epeg_k, qscale, round_out);
+  rmsa_attn_kernel<HD><<<g, 32 * W, smem, stream>>>(qkv, taps, o, grid, D, epeg_k, qscale);
   return cudaGetLastError();
 }
 }  // namespace
 
-cudaError_t launch_rmsa_attention(const float* qkv, const float* taps, float* o, const Grid& grid,
-                                  int D, int heads, int epeg_k, bool round_out,
-                                  cudaStream_t stream) {
+cudaError_t launch_rmsa_attention(const __half* qkv, const float* taps, __half* o, const Grid& grid,
+                                  int D, int heads, int epeg_k, cudaStream_t stream) {
   if (heads <= 0 || D % heads) return cudaErrorInvalidValue;
   if (grid.R > 65535) return cudaErrorInvalidValue;
   switch (D / heads) {
-    case 32: return launch<32>(qkv, taps, o, grid, D, heads, epeg_k, round_out, stream);
-    case 64: return launch<64>(qkv, taps, o, grid, D, heads, epeg_k, round_out, stream);
-    case 128: return launch<128>(qkv, taps, o, grid, D, heads, epeg_k, round_out, stream);
+    case 32: return launch<32>(qkv, taps, o, grid, D, heads, epeg_k, stream);
+    case 64: return launch<64>(qkv, taps, o, grid, D, heads, epeg_k, stream);
+    case 128: return launch<128>(qkv, taps, o, grid, D, heads, epeg_k, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -1,14 +1,14 @@
 // R-MSA attention core for regions of up to 256 tokens (every configuration the reference ships:
 // P = 144 at N = 9000 / region_num 8, P = 196 at N = 50000 / region_num 16), one CTA per
-// (region, head), the whole region resident in shared memory:
-//   load   Q (with the EPEG halo), K, V rows of this head: fp32 global -> fp16 smem
-//   conv   Q' = scale*log2e * (Q + dwconv1d_P(Q; taps_h))   fp32 math, fp16 result in smem
-//   core   one warp per 16 query rows: S = Q' K^T (ldmatrix + mma.sync m16n8k16, fp32 accum),
-//          online softmax in registers over KV tiles of 48 or 64 keys, O += P V
+// (region, head), the whole region resident in shared memory (fp16, as written by the QKV GEMM):
+//   load   Q rows (with the EPEG halo), K, V of this head: cp.async 16-byte copies, no conversion
+//   EPEG   Q' = scale*log2e * (Q + dwconv1d_P(Q; taps_h)) as a banded-Toeplitz product on the
+//          tensor path: Q'[16 rows] = C[16 x (16+k-1)] . Q[halo rows], C[i][r] = taps[r-i] (+1 on the
+//          diagonal); the fp32 accumulator fragment IS the A fragment of the next product
+//   core   one warp per 16 query rows: S = Q' K^T (ldmatrix + mma.sync m16n8k16, fp32 accumulate),
+//          online softmax in registers over KV tiles of 48 or 64 keys, O += P V, fp16 O out
 // fp16 operands carry the same 10-bit mantissa as tf32; softmax state and accumulators are fp32.
 // (modules/rmsa.py:103-122; SURVEY.md 0.2-1 for the EPEG-on-Q identity.)
-#include <cuda_fp16.h>
-
 #include "kernels.cuh"
 
 namespace rrt {
@@ -34,94 +34,109 @@ __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
-  __half2 h = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
-// HD: head dim; NT: 8-key n-tiles per KV tile (6 -> 48 keys, 8 -> 64 keys)
-template <int HD, int NT>
-__global__ void __launch_bounds__(512) rmsa_attn_f16_kernel(const float* __restrict__ qkv,
-                                                            const float* __restrict__ taps,
-                                                            float* __restrict__ o, Grid grid, int D,
-                                                            int epeg_k, float qscale, int n_kv_tiles,
-                                                            bool round_out) {
+// HD: head dim; NT: 8-key n-tiles per KV tile (6 -> 48 keys, 8 -> 64 keys); MAXW: warps per CTA cap
+template <int HD, int NT, int MAXW>
+__global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) rmsa_attn_f16_kernel(const __half* __restrict__ qkv,
+                                                                  const float* __restrict__ taps,
+                                                                  __half* __restrict__ o, Grid grid,
+                                                                  int D, int epeg_k, float qscale,
+                                                                  int n_kv_tiles, int q_rows) {
   constexpr int LDH = HD + 8;   // halves per smem row: 16-byte row skew keeps ldmatrix conflict-free
   constexpr int KS = HD / 16;   // k16 steps over head_dim
-  constexpr int ND = HD / 8;    // 8-wide n-tiles of the output
+  constexpr int ND = HD / 8;    // 8-wide n-tiles over head_dim
   constexpr int KV = 8 * NT;    // keys per KV tile
+  constexpr int C8 = HD / 8;    // 16-byte chunks per row
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int W = blockDim.x >> 5;
   const int P = grid.P;
   const int pad = taps ? epeg_k / 2 : 0;
-  const int prow = 16 * W;            // query rows incl. padding of the last warp
-  const int pk = n_kv_tiles * KV;     // key rows incl. padding of the last tile
-  __half* Qraw = reinterpret_cast<__half*>(smem_raw);   // [prow + 2*pad][LDH]
-  __half* Qp = Qraw + (size_t)(prow + 2 * pad) * LDH;   // [prow][LDH]
-  __half* Ks = Qp + (size_t)prow * LDH;                 // [pk][LDH]
-  __half* Vs = Ks + (size_t)pk * LDH;                   // [pk][LDH]
+  const int pk = n_kv_tiles * KV;  // key rows incl. padding of the last tile
+  __half* Qs = reinterpret_cast<__half*>(smem_raw);  // [q_rows][LDH]: row r holds Q[r - pad]
+  __half* Ks = Qs + (size_t)q_rows * LDH;             // [pk][LDH]
+  __half* Vs = Ks + (size_t)pk * LDH;                 // [pk][LDH]
   float* Ts = reinterpret_cast<float*>(Vs + (size_t)pk * LDH);  // [epeg_k]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int rho = blockIdx.x;  // region
-  const int h = blockIdx.y;
+  const int rho = blockIdx.x, h = blockIdx.y;
   const size_t ld = 3 * (size_t)D;
-  const float* base = qkv + (size_t)rho * P * ld + h * HD;
+  const __half* base = qkv + (size_t)rho * P * ld + h * HD;
 
-  // ---- stage Q (halo), K, V as fp16 ---------------------------------------------------------
-  constexpr int C4 = HD / 4;
-  for (int i = tid; i < (prow + 2 * pad) * C4; i += blockDim.x) {
-    int r = i / C4, c = (i - r * C4) * 4;
+  // ---- stage Q (halo), K, V: asynchronous 16-byte copies, zero fill outside the region ----------
+  for (int i = tid; i < q_rows * C8; i += blockDim.x) {
+    int r = i / C8, c = (i - r * C8) * 8;
     int p = r - pad;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p >= 0 && p < P) v = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * ld + c));
-    uint2 u = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
-    *reinterpret_cast<uint2*>(Qraw + (size_t)r * LDH + c) = u;
+    bool ok = p >= 0 && p < P;
+    cp_async16(Qs + (size_t)r * LDH + c, base + (size_t)(ok ? p : 0) * ld + c, ok);
   }
-  for (int i = tid; i < pk * C4; i += blockDim.x) {
-    int r = i / C4, c = (i - r * C4) * 4;
-    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-    if (r < P) {
-      kv = __ldg(reinterpret_cast<const float4*>(base + (size_t)r * ld + D + c));
-      vv = __ldg(reinterpret_cast<const float4*>(base + (size_t)r * ld + 2 * D + c));
-    }
-    *reinterpret_cast<uint2*>(Ks + (size_t)r * LDH + c) = make_uint2(pack_h2(kv.x, kv.y), pack_h2(kv.z, kv.w));
-    *reinterpret_cast<uint2*>(Vs + (size_t)r * LDH + c) = make_uint2(pack_h2(vv.x, vv.y), pack_h2(vv.z, vv.w));
+  for (int i = tid; i < pk * C8; i += blockDim.x) {
+    int r = i / C8, c = (i - r * C8) * 8;
+    bool ok = r < P;
+    const __half* src = base + (size_t)(ok ? r : 0) * ld + c;
+    cp_async16(Ks + (size_t)r * LDH + c, src + D, ok);
+    cp_async16(Vs + (size_t)r * LDH + c, src + 2 * D, ok);
   }
+  cp_async_commit();
   if (taps)
     for (int i = tid; i < epeg_k; i += blockDim.x) Ts[i] = __ldg(taps + h * epeg_k + i);
+  cp_async_wait<0>();
   __syncthreads();
 
-  // ---- EPEG on Q: warp w produces exactly the 16 rows it consumes -----------------------------
-  {
-    const int r0 = 16 * warp;
-    for (int cp = lane; cp < HD / 2; cp += 32) {
-      for (int r = 0; r < 16; ++r) {
-        float2 acc = __half22float2(*reinterpret_cast<const __half2*>(Qraw + (size_t)(r0 + r + pad) * LDH + 2 * cp));
-        if (taps) {
-          float2 cv = make_float2(0.f, 0.f);
-          for (int j = 0; j < epeg_k; ++j) {
-            float2 q = __half22float2(*reinterpret_cast<const __half2*>(Qraw + (size_t)(r0 + r + j) * LDH + 2 * cp));
-            float wj = Ts[j];
-            cv.x = fmaf(wj, q.x, cv.x);
-            cv.y = fmaf(wj, q.y, cv.y);
-          }
-          acc.x += cv.x;
-          acc.y += cv.y;
+  // ---- Q' fragments ----------------------------------------------------------------------------
+  const int i0 = 16 * warp;  // first query row of this warp (= first halo row of its band)
+  uint32_t qa[KS][4];
+  if (taps) {
+    float qacc[ND][4];
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) qacc[i][e] = 0.f;
+    const int nkc = (16 + epeg_k - 1 + 15) / 16;  // k16 steps that cover the band of 16+k-1 rows
+    for (int kc = 0; kc < nkc; ++kc) {
+      // A fragment of the Toeplitz band: element (row i, halo row r) = taps[r-i] (+1 at r-i = pad)
+      uint32_t ca[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ro = g + (e & 1) * 8;                    // row offset within the warp's 16 rows
+        const int co = 16 * kc + 2 * t + (e >> 1) * 8;     // halo-row offset of the first column
+        float v[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          int d = co + u - ro;
+          float x = (d >= 0 && d < epeg_k) ? Ts[d] : 0.f;
+          v[u] = x + (d == pad ? 1.f : 0.f);
         }
-        *reinterpret_cast<__half2*>(Qp + (size_t)(r0 + r) * LDH + 2 * cp) =
-            __floats2half2_rn(acc.x * qscale, acc.y * qscale);
+        ca[e] = pack_h2(v[0], v[1]);
+      }
+#pragma unroll
+      for (int np = 0; np < ND / 2; ++np) {
+        uint32_t b[4];
+        ldsm_x4_trans(b, Qs + (size_t)(i0 + 16 * kc + (lane & 7) + ((lane >> 3) & 1) * 8) * LDH +
+                             np * 16 + (lane >> 4) * 8);
+        mma_f16_16x8x16(qacc[2 * np], ca, b[0], b[1]);
+        mma_f16_16x8x16(qacc[2 * np + 1], ca, b[2], b[3]);
+      }
+    }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      qa[ks][0] = pack_h2(qacc[2 * ks][0] * qscale, qacc[2 * ks][1] * qscale);
+      qa[ks][1] = pack_h2(qacc[2 * ks][2] * qscale, qacc[2 * ks][3] * qscale);
+      qa[ks][2] = pack_h2(qacc[2 * ks + 1][0] * qscale, qacc[2 * ks + 1][1] * qscale);
+      qa[ks][3] = pack_h2(qacc[2 * ks + 1][2] * qscale, qacc[2 * ks + 1][3] * qscale);
+    }
+  } else {
+    const __half2 sc = __float2half2_rn(qscale);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      ldsm_x4(qa[ks], Qs + (size_t)(i0 + (lane & 15)) * LDH + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __half2 v = __hmul2(*reinterpret_cast<__half2*>(&qa[ks][e]), sc);
+        qa[ks][e] = *reinterpret_cast<uint32_t*>(&v);
       }
     }
   }
-  __syncwarp();
 
   // ---- attention core ---------------------------------------------------------------------------
-  uint32_t qa[KS][4];
-#pragma unroll
-  for (int ks = 0; ks < KS; ++ks)
-    ldsm_x4(qa[ks], Qp + (size_t)(16 * warp + (lane & 15)) * LDH + ks * 16 + (lane >> 4) * 8);
-
   float oacc[ND][4];
 #pragma unroll
   for (int i = 0; i < ND; ++i)
@@ -205,51 +220,61 @@ __global__ void __launch_bounds__(512) rmsa_attn_f16_kernel(const float* __restr
   }
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
-    int q = 16 * warp + g + hh * 8;
+    int q = i0 + g + hh * 8;
     if (q >= P) continue;
     float inv = 1.f / l_run[hh];
-    float* orow = o + ((size_t)rho * P + q) * D + h * HD + 2 * t;
+    __half* orow = o + ((size_t)rho * P + q) * D + h * HD + 2 * t;
 #pragma unroll
-    for (int nd = 0; nd < ND; ++nd) {
-      float a = oacc[nd][hh * 2] * inv, b = oacc[nd][hh * 2 + 1] * inv;
-      if (round_out) { a = to_tf32(a); b = to_tf32(b); }
-      *reinterpret_cast<float2*>(orow + nd * 8) = make_float2(a, b);
-    }
+    for (int nd = 0; nd < ND; ++nd)
+      *reinterpret_cast<uint32_t*>(orow + nd * 8) =
+          pack_h2(oacc[nd][hh * 2] * inv, oacc[nd][hh * 2 + 1] * inv);
   }
 }
 
-template <int HD, int NT>
-cudaError_t launch(const float* qkv, const float* taps, float* o, const Grid& grid, int D, int heads,
-                   int epeg_k, bool round_out, cudaStream_t stream) {
+template <int HD, int NT, int MAXW>
+cudaError_t launch(const __half* qkv, const float* taps, __half* o, const Grid& grid, int D,
+                   int heads, int epeg_k, cudaStream_t stream) {
   const int W = (grid.P + 15) / 16;
   const int KV = 8 * NT;
   const int tiles = (grid.P + KV - 1) / KV;
   const int pad = taps ? epeg_k / 2 : 0;
-  size_t smem = ((size_t)(16 * W + 2 * pad) + 16 * W + 2 * (size_t)tiles * KV) * (HD + 8) * sizeof(__half) +
+  // halo'd Q rows: every warp's band [16w, 16w + 16*nkc) must exist (zero filled past the data)
+  const int nkc = taps ? (16 + epeg_k - 1 + 15) / 16 : 1;
+  int q_rows = 16 * (W - 1) + 16 * nkc;
+  if (q_rows < 16 * W + 2 * pad) q_rows = 16 * W + 2 * pad;
+  size_t smem = ((size_t)q_rows + 2 * (size_t)tiles * KV) * (HD + 8) * sizeof(__half) +
                 (taps ? epeg_k : 0) * sizeof(float) + 16;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(rmsa_attn_f16_kernel<HD, NT>,
+    cudaError_t e = cudaFuncSetAttribute(rmsa_attn_f16_kernel<HD, NT, MAXW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(rmsa_attn_f16_kernel<HD, NT, MAXW>,
+                               cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const float kLog2e = 1.4426950408889634f;
   float qscale = kLog2e / sqrtf((float)HD);
   dim3 g(grid.R, heads);
-  rmsa_attn_f16_kernel<HD, NT><<<g, 32 * W, smem, stream>>>(qkv, taps, o, grid, D, epeg_k, qscale,
-                                                            tiles, round_out);
+  rmsa_attn_f16_kernel<HD, NT, MAXW><<<g, 32 * W, smem, stream>>>(qkv, taps, o, grid, D, epeg_k,
+                                                                  qscale, tiles, q_rows);
   return cudaGetLastError();
 }
 
 template <int HD>
-cudaError_t launch_hd(const float* qkv, const float* taps, float* o, const Grid& grid, int D,
-                      int heads, int epeg_k, bool round_out, cudaStream_t stream) {
-  // KV tile of 48 or 64 keys, whichever pads the region's keys less
+cudaError_t launch_hd(const __half* qkv, const float* taps, __half* o, const Grid& grid, int D,
+                      int heads, int epeg_k, cudaStream_t stream) {
+  // KV tile of 48 or 64 keys, whichever pads the region's keys less; <= 9 warps (P <= 144) gets the
+  // tighter register budget so that two CTAs fit the per-scheduler register files
   int pad48 = (grid.P + 47) / 48 * 48, pad64 = (grid.P + 63) / 64 * 64;
-  if (pad48 < pad64) return launch<HD, 6>(qkv, taps, o, grid, D, heads, epeg_k, round_out, stream);
-  return launch<HD, 8>(qkv, taps, o, grid, D, heads, epeg_k, round_out, stream);
+  const bool small = grid.P <= 144;
+  if (pad48 < pad64)
+    return small ? launch<HD, 6, 9>(qkv, taps, o, grid, D, heads, epeg_k, stream)
+                 : launch<HD, 6, 16>(qkv, taps, o, grid, D, heads, epeg_k, stream);
+  return small ? launch<HD, 8, 9>(qkv, taps, o, grid, D, heads, epeg_k, stream)
+               : launch<HD, 8, 16>(qkv, taps, o, grid, D, heads, epeg_k, stream);
 }
 }  // namespace
 
@@ -258,14 +283,14 @@ bool rmsa_attention_f16_supported(const Grid& grid, int D, int heads) {
   return grid.P <= 256 && (hd == 32 || hd == 64 || hd == 128) && heads <= 65535;
 }
 
-cudaError_t launch_rmsa_attention_f16(const float* qkv, const float* taps, float* o,
+cudaError_t launch_rmsa_attention_f16(const __half* qkv, const float* taps, __half* o,
                                       const Grid& grid, int D, int heads, int epeg_k,
-                                      bool round_out, cudaStream_t stream) {
+                                      cudaStream_t stream) {
   if (!rmsa_attention_f16_supported(grid, D, heads)) return cudaErrorInvalidValue;
   switch (D / heads) {
-    case 32: return launch_hd<32>(qkv, taps, o, grid, D, heads, epeg_k, round_out, stream);
-    case 64: return launch_hd<64>(qkv, taps, o, grid, D, heads, epeg_k, round_out, stream);
-    default: return launch_hd<128>(qkv, taps, o, grid, D, heads, epeg_k, round_out, stream);
+    case 32: return launch_hd<32>(qkv, taps, o, grid, D, heads, epeg_k, stream);
+    case 64: return launch_hd<64>(qkv, taps, o, grid, D, heads, epeg_k, stream);
+    default: return launch_hd<128>(qkv, taps, o, grid, D, heads, epeg_k, stream);
   }
 }
 

@@ -136,7 +136,7 @@ class RRTEncoder(nn.Module):
         cfg.epeg, cfg.epeg_k, cfg.qkv_bias = int(bool(epeg)), int(epeg_k), int(bool(qkv_bias))
         cfg.cr_msa, cfg.crmsa_k, cfg.crmsa_heads = int(bool(cr_msa)), int(crmsa_k), int(crmsa_heads)
         cfg.crmsa_mlp, cfg.all_shortcut = int(bool(crmsa_mlp)), int(bool(all_shortcut))
-        cfg.math_mode = cabi.RRT_MATH_TF32
+        cfg.math_mode = cabi.RRT_MATH_F16
         self._cfg = cfg
         self._crmsa_mlp = bool(crmsa_mlp)
         self._shadow = {}
@@ -161,10 +161,10 @@ class RRTEncoder(nn.Module):
             raise RuntimeError("RRTEncoder parameters must be contiguous")
         return t.data_ptr()
 
-    def _tf32_shadow(self, param: torch.Tensor):
-        """tf32-rounded copy of a GEMM weight (the form the tcgen05 kernels consume), cached in eval
-        mode and refreshed when the parameter's storage or version counter changes.  In training
-        mode (weights change every step) no shadow is passed and the library rounds per call.
+    def _f16_shadow(self, param: torch.Tensor):
+        """fp16 copy of a GEMM weight (the form the tcgen05 kernels consume), cached in eval mode and
+        refreshed when the parameter's storage or version counter changes.  In training mode
+        (weights change every step) no shadow is passed and the library converts per call.
         In-place edits through ``.data`` bypass the version counter: call
         ``invalidate_weight_cache()`` after such edits."""
         if self.training:
@@ -172,10 +172,10 @@ class RRTEncoder(nn.Module):
         key = id(param)
         ent = self._shadow.get(key)
         if ent is None or ent[0] != (param.data_ptr(), param._version):
-            buf = torch.empty_like(param.detach())
-            rc = cabi.lib().rrt_round_tf32(param.data_ptr(), buf.data_ptr(), param.numel(),
-                                           torch.cuda.current_stream(param.device).cuda_stream)
-            cabi.check(rc, "rrt_round_tf32")
+            buf = torch.empty(param.shape, dtype=torch.float16, device=param.device)
+            rc = cabi.lib().rrt_convert_f16(param.data_ptr(), buf.data_ptr(), param.numel(),
+                                            torch.cuda.current_stream(param.device).cuda_stream)
+            cabi.check(rc, "rrt_convert_f16")
             ent = ((param.data_ptr(), param._version), buf)
             self._shadow[key] = ent
         return ent[1].data_ptr()
@@ -189,8 +189,8 @@ class RRTEncoder(nn.Module):
         dst.proj_w, dst.proj_b = p(inner.proj.weight, device), p(inner.proj.bias, device)
         dst.pe_w = p(inner.pe.weight, device) if inner.pe is not None else None
         if shadows:
-            dst.qkv_w_tf32 = self._tf32_shadow(inner.qkv.weight)
-            dst.proj_w_tf32 = self._tf32_shadow(inner.proj.weight)
+            dst.qkv_w_f16 = self._f16_shadow(inner.qkv.weight)
+            dst.proj_w_f16 = self._f16_shadow(inner.proj.weight)
 
     def _weights(self, device) -> cabi.RrtWeights:
         w, p = cabi.RrtWeights(), self._ptr
@@ -203,6 +203,7 @@ class RRTEncoder(nn.Module):
             w.cr_norm_w, w.cr_norm_b = p(cr.norm.weight, device), p(cr.norm.bias, device)
             if self._crmsa_mlp:
                 w.cr_phi_w1, w.cr_phi_w2 = p(cr.attn.phi[0].weight, device), p(cr.attn.phi[2].weight, device)
+                w.cr_phi_w1_f16 = self._f16_shadow(cr.attn.phi[0].weight)
             else:
                 w.cr_phi = p(cr.attn.phi, device)
             self._attn_weights(cr.attn.attn, w.cr_attn, device, shadows=True)
@@ -243,9 +244,11 @@ class RRTEncoder(nn.Module):
         cabi.check(rc, "rrt_encoder_forward")
         return out
 
-    def forward_bags(self, bags, outs=None):
-        """Independent bags ``[N_i, D]`` back to back on the current stream with ONE C call
-        (amortises the host-side cost of a call; results equal per-bag ``forward``)."""
+    def forward_bags(self, bags, outs=None, lanes: int = cabi.RRT_MAX_LANES):
+        """Independent bags ``[N_i, D]`` with ONE C call; results equal per-bag ``forward``.
+        Up to ``lanes`` bags run concurrently on the library's internal streams, forked from and
+        joined back into the current stream (bags are independent; the small latency-bound kernels
+        of one bag fill the SMs another bag leaves idle).  ``lanes=1`` runs them back to back."""
         if not bags:
             return []
         for x in bags:
@@ -260,7 +263,8 @@ class RRTEncoder(nn.Module):
         n = len(bags)
         lib, cfg = cabi.lib(), self._cfg
         with torch.cuda.device(device):
-            nbytes = cabi.workspace_bytes(cfg, max(x.shape[0] for x in bags))
+            per_bag = (cabi.workspace_bytes(cfg, max(x.shape[0] for x in bags)) + 255) // 256 * 256
+            nbytes = per_bag * max(1, min(int(lanes), n, cabi.RRT_MAX_LANES))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
             w = self._weights(device)
             xs = (C.c_void_p * n)(*[x.data_ptr() for x in bags])

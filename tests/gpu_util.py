@@ -57,21 +57,21 @@ def linear(a, w, b):
     return c
 
 
-def round_tf32(x):
-    out = torch.empty_like(x)
-    cabi.check(cabi.lib().rrt_round_tf32(x.data_ptr(), out.data_ptr(), x.numel(), stream_ptr()), "rrt_round_tf32")
+def convert_f16(x):
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    cabi.check(cabi.lib().rrt_convert_f16(x.data_ptr(), out.data_ptr(), x.numel(), stream_ptr()), "rrt_convert_f16")
     return out
 
 
-def linear_tf32(a, w, b):
-    """The tcgen05 GEMM; operands rounded to tf32 first (its contract)."""
+def linear_f16(a, w, b):
+    """The tcgen05 GEMM: fp16 operands (converted here with the library's own kernel), fp32 out."""
     M, K = a.shape
     N = w.shape[0]
-    a, w = round_tf32(a.contiguous()), round_tf32(w.contiguous())
+    a, w = convert_f16(a.contiguous()), convert_f16(w.contiguous())
     c = torch.empty(M, N, device=a.device, dtype=torch.float32)
-    rc = cabi.lib().rrt_linear_tf32_forward(a.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None,
-                                            c.data_ptr(), M, N, K, stream_ptr())
-    cabi.check(rc, "rrt_linear_tf32_forward")
+    rc = cabi.lib().rrt_linear_f16_forward(a.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None,
+                                           c.data_ptr(), M, N, K, stream_ptr())
+    cabi.check(rc, "rrt_linear_f16_forward")
     return c
 
 
