@@ -82,7 +82,7 @@ def stage_algorithmic(stage, L):
         return "hbm", 0.0, 4.0 * (L * D + np_r * D)
     if stage == "crmsa_stats_logits":
         return "hbm", 0.0, 4.0 * L * D
-    if stage == "crmsa_combine":
+    if stage == "crmsa_landmarks":
         return "hbm", 0.0, 4.0 * L * D
     if stage == "crmsa_dispatch_final_ln":
         return "hbm", 0.0, 4.0 * 2 * L * D

@@ -36,7 +36,7 @@ enum Stage {
 };
 const char* const kStageNames[kStCount] = {
     "ln_partition", "qkv_gemm", "rmsa_attention", "proj_gemm_residual", "crmsa_stats_logits",
-    "crmsa_mlp_phi", "crmsa_combine", "landmark_qkv_gemm", "landmark_attention",
+    "crmsa_mlp_phi", "crmsa_landmarks", "landmark_qkv_gemm", "landmark_attention",
     "landmark_proj_gemm", "crmsa_dispatch_final_ln", "final_layernorm", "other"};
 
 std::atomic<int64_t> g_launches{0};
@@ -279,11 +279,11 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   rrt::Grid g{};
   if (!crmsa_grid(L, &g)) return fail(RRT_E_INVALID, "bad geometry");
   const int D = c->dim, k = c->crmsa_k, T = k * g.R;
+  const bool fused_front = rrt::crmsa_landmarks_supported(g, D, k);
+  const float* phi = nullptr;
   if (c->crmsa_mlp) {
+    // logits = Linear(D/4 -> k)(tanh(Linear(D -> D/4)(LN(x1))))   (modules/rmsa.py:248-252,305)
     if (!w->cr_phi_w1 || !w->cr_phi_w2) return fail(RRT_E_INVALID, "crmsa_mlp weights missing");
-    { StageScope s_(kStCrLogits, st);
-      RRT_CUDA(rrt::launch_crmsa_stats_logits(x1, w->cr_norm_w, w->cr_norm_b, nullptr, ws.stats,
-                                              nullptr, g, D, k, st), "crmsa stats"); }
     const __half* w1;
     int rc = f16_weight(w->cr_phi_w1, w->cr_phi_w1_f16, ws.wconv, (size_t)(D / 4) * D, st, &w1);
     if (rc) return rc;
@@ -297,9 +297,7 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
              "phi.2");
   } else {
     if (!w->cr_phi) return fail(RRT_E_INVALID, "cr_phi missing");
-    StageScope s_(kStCrLogits, st);
-    RRT_CUDA(rrt::launch_crmsa_stats_logits(x1, w->cr_norm_w, w->cr_norm_b, w->cr_phi, ws.stats,
-                                            ws.logits, g, D, k, st), "crmsa logits");
+    phi = w->cr_phi;
   }
   const __half *wq, *wp;
   int rc = f16_weight(w->cr_attn.qkv_w, w->cr_attn.qkv_w_f16, ws.wconv, (size_t)3 * D * D, st, &wq);
@@ -307,16 +305,35 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   rc = f16_weight(w->cr_attn.proj_w, w->cr_attn.proj_w_f16, ws.wconv + (size_t)3 * D * D,
                   (size_t)D * D, st, &wp);
   if (rc) return rc;
-  { StageScope s_(kStCrCombine, st);
+  if (fused_front) {
+    StageScope s_(kStCrCombine, st);
+    RRT_CUDA(rrt::launch_crmsa_landmarks(x1, w->cr_norm_w, w->cr_norm_b, phi, ws.logits, ws.lm,
+                                         ws.rstat, g, D, k, st), "crmsa landmarks (fused)");
+  } else {
+    { StageScope s_(kStCrLogits, st);
+      RRT_CUDA(rrt::launch_crmsa_stats_logits(x1, w->cr_norm_w, w->cr_norm_b, phi, ws.stats,
+                                              phi ? ws.logits : nullptr, g, D, k, st),
+               "crmsa stats / logits"); }
+    StageScope s_(kStCrCombine, st);
     RRT_CUDA(rrt::launch_crmsa_combine(x1, w->cr_norm_w, w->cr_norm_b, ws.stats, ws.logits, ws.lm,
-                                       ws.rstat, g, D, k, st), "crmsa combine"); }
+                                       ws.rstat, g, D, k, st), "crmsa combine");
+  }
+  // landmark MHA: batch = k, sequence = the 64 regions.  With a tensor-friendly head_dim the QKV GEMM
+  // emits fp16 and the attention core is the R-MSA kernel with P = 64 and no EPEG.
+  rrt::Grid lg{};
+  lg.L = T; lg.H = 0; lg.rs = 0; lg.g = 0; lg.P = g.R; lg.R = k; lg.Np = T;
+  const bool tc_attn = rrt::rmsa_attention_f16_supported(lg, D, c->crmsa_heads);
   rrt::GemmEpilogue e1;
   e1.bias = c->qkv_bias ? w->cr_attn.qkv_b : nullptr;
   { StageScope s_(kStLmQkv, st);
-    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lm, wq, ws.lqkv, false, T, 3 * D, D, e1, st), "landmark qkv"); }
+    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lm, wq, ws.lqkv, tc_attn, T, 3 * D, D, e1, st), "landmark qkv"); }
   { StageScope s_(kStLmAttn, st);
-    RRT_CUDA(rrt::launch_landmark_attention(ws.lqkv, ws.lo, k, g.R, D, c->crmsa_heads, st),
-             "landmark attention"); }
+    if (tc_attn)
+      RRT_CUDA(rrt::launch_rmsa_attention_f16(reinterpret_cast<const __half*>(ws.lqkv), nullptr, ws.lo,
+                                              lg, D, c->crmsa_heads, 1, st), "landmark attention");
+    else
+      RRT_CUDA(rrt::launch_landmark_attention(ws.lqkv, ws.lo, k, g.R, D, c->crmsa_heads, st),
+               "landmark attention (fp32)"); }
   rrt::GemmEpilogue e2;
   e2.bias = w->cr_attn.proj_b;
   { StageScope s_(kStLmProj, st);

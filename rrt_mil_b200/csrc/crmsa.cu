@@ -193,6 +193,236 @@ __global__ void __launch_bounds__(256) crmsa_combine_kernel(
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused CR-MSA front end, one CTA per region (16 warps), two passes over the region's rows (which
+// are L2-resident: the projection GEMM has just written them):
+//   pass 1  warp per row, 3 rows in flight: LayerNorm statistics and the k logits from ONE batched
+//           butterfly: with G[c,n] = gamma[c]*phi[c,n], A[n] = sum_c G[c,n], B[n] = sum_c beta[c]*phi[c,n]
+//             logits[n] = rstd * (sum_c x[c]*G[c,n] - mean*A[n]) + B[n]      (== LN(x) . phi[:, n])
+//           so sum(x) and the k dot products reduce together; sum((x-mean)^2) is the second round.
+//           (phi == null: the logits come from the crmsa_mlp path and are only read)
+//   mid     warp per landmark: softmax over the P tokens, min / max  -> cw[p, n], rstat[rho, n]
+//   pass 2  warps tiled (row group x 128-column group): landmarks[n, :] += cw[p, n] * LN(x1)[p, :]
+// Replaces the separate stats/logits and combine kernels: one launch, every load batched.
+template <int V, int KMAX>
+__global__ void __launch_bounds__(512) crmsa_landmarks_kernel(
+    const float* __restrict__ x1, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ phi, float* __restrict__ logits, __half* __restrict__ landmarks,
+    float2* __restrict__ rstat, Grid grid, int k) {
+  constexpr int D = 128 * V;
+  constexpr int NW = 16;           // warps
+  constexpr int CG = V;            // 128-column groups
+  constexpr int RG = NW / CG;      // row groups of pass 2
+  extern __shared__ __align__(16) float smem[];
+  const int P = grid.P, rho = blockIdx.x;
+  float* gam = smem;                       // [D]
+  float* bet = gam + D;                    // [D]
+  float* Gt = bet + D;                     // [k][D]  gamma[c] * phi[c, n]
+  float* lg = Gt + (size_t)k * D;          // [P][k]  logits, then combine weights
+  float2* st = reinterpret_cast<float2*>(lg + (((size_t)P * k + 3) & ~(size_t)3));  // [P] mean, rstd
+  int* tok = reinterpret_cast<int*>(st + ((P + 1) & ~1));                            // [P]
+  float* AB = reinterpret_cast<float*>(tok + ((P + 3) & ~3));                        // [2][KMAX]
+  float* part = AB + 2 * 16;                                                         // [RG][k][D]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < D; i += 512) { gam[i] = __ldg(gamma + i); bet[i] = __ldg(beta + i); }
+  for (int p = tid; p < P; p += 512) {
+    int t = grid.slot_to_token(rho * P + p);
+    tok[p] = t < grid.L ? t : -1;
+  }
+  if (!phi)
+    for (int i = tid; i < P * k; i += 512) lg[i] = __ldg(logits + (size_t)rho * P * k + i);
+  __syncthreads();
+  if (phi) {
+    for (int n = warp; n < k; n += NW) {  // one warp per landmark column of phi
+      float a = 0.f, b = 0.f;
+      for (int c = lane; c < D; c += 32) {
+        float ph = __ldg(phi + (size_t)c * k + n);
+        float gph = gam[c] * ph;
+        Gt[n * D + c] = gph;
+        a += gph;
+        b = fmaf(bet[c], ph, b);
+      }
+      a = warp_sum(a);
+      b = warp_sum(b);
+      if (lane == 0) { AB[n] = a; AB[16 + n] = b; }
+    }
+    __syncthreads();
+  }
+
+  // ---- pass 1: statistics (+ logits) -----------------------------------------------------------
+  constexpr int U1 = 3;  // rows in flight per warp
+  for (int p0 = warp; p0 < P; p0 += NW * U1) {
+    float4 v[U1][V];
+    int tk[U1];
+#pragma unroll
+    for (int u = 0; u < U1; ++u) {
+      int p = p0 + u * NW;
+      tk[u] = p < P ? tok[p] : -1;
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        v[u][i] = tk[u] >= 0
+                      ? __ldg(reinterpret_cast<const float4*>(x1 + (size_t)tk[u] * D) + lane + 32 * i)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // round 1: sum(x) and the k dot products with G, all rows of the batch in one butterfly
+    float red[U1][1 + KMAX];
+#pragma unroll
+    for (int u = 0; u < U1; ++u) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) s += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+      red[u][0] = s;
+#pragma unroll
+      for (int n = 0; n < KMAX; ++n) red[u][1 + n] = 0.f;
+    }
+    if (phi) {
+#pragma unroll
+      for (int n = 0; n < KMAX; ++n) {
+        if (n < k) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            float4 gq = *reinterpret_cast<const float4*>(Gt + n * D + 4 * (lane + 32 * i));
+#pragma unroll
+            for (int u = 0; u < U1; ++u) {
+              float d = red[u][1 + n];
+              d = fmaf(v[u][i].x, gq.x, d); d = fmaf(v[u][i].y, gq.y, d);
+              d = fmaf(v[u][i].z, gq.z, d); d = fmaf(v[u][i].w, gq.w, d);
+              red[u][1 + n] = d;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < U1; ++u)
+#pragma unroll
+        for (int j = 0; j < 1 + KMAX; ++j)
+          if (j == 0 || (phi && j - 1 < k)) red[u][j] += __shfl_xor_sync(0xffffffffu, red[u][j], o);
+    // round 2: centred second moment
+    float q[U1];
+#pragma unroll
+    for (int u = 0; u < U1; ++u) {
+      float mean = red[u][0] * (1.f / D);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float a = v[u][i].x - mean, b = v[u][i].y - mean, c = v[u][i].z - mean, d = v[u][i].w - mean;
+        acc += (a * a + b * b) + (c * c + d * d);
+      }
+      q[u] = acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < U1; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o);
+#pragma unroll
+    for (int u = 0; u < U1; ++u) {
+      int p = p0 + u * NW;
+      if (p >= P) continue;
+      if (tk[u] < 0) {  // zero pad token: LN output forced to 0 -> logits 0
+        if (lane == 0) st[p] = make_float2(0.f, 0.f);
+        if (phi && lane < k) {
+          lg[p * k + lane] = 0.f;
+          logits[((size_t)rho * P + p) * k + lane] = 0.f;
+        }
+        continue;
+      }
+      float mean = red[u][0] * (1.f / D);
+      float rstd = rsqrtf(q[u] * (1.f / D) + kLnEps);
+      if (lane == 0) st[p] = make_float2(mean, rstd);
+      if (phi) {
+        float mine = 0.f;  // lane n keeps logit n
+#pragma unroll
+        for (int n = 0; n < KMAX; ++n)
+          if (lane == n) mine = rstd * (red[u][1 + n] - mean * AB[n]) + AB[16 + n];
+        if (lane < k) {
+          lg[p * k + lane] = mine;
+          logits[((size_t)rho * P + p) * k + lane] = mine;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- per landmark: softmax over the region's tokens, min, max --------------------------------
+  for (int n = warp; n < k; n += NW) {
+    float mx = -INFINITY, mn = INFINITY;
+    for (int p = lane; p < P; p += 32) {
+      float v = lg[p * k + n];
+      mx = fmaxf(mx, v);
+      mn = fminf(mn, v);
+    }
+    mx = warp_max(mx);
+    mn = warp_min(mn);
+    float sum = 0.f;
+    for (int p = lane; p < P; p += 32) {
+      float e = __expf(lg[p * k + n] - mx);
+      lg[p * k + n] = e;
+      sum += e;
+    }
+    float inv = 1.f / warp_sum(sum);
+    for (int p = lane; p < P; p += 32) lg[p * k + n] *= inv;
+    if (lane == 0) rstat[(size_t)rho * k + n] = make_float2(mn, mx);
+  }
+  __syncthreads();
+
+  // ---- pass 2: landmarks = cw^T . LN(x1) ---------------------------------------------------------
+  {
+    const int cg = warp % CG, rg = warp / CG;
+    const int c0 = cg * 128 + lane * 4;
+    const float4 gm = *reinterpret_cast<const float4*>(gam + c0);
+    const float4 bt = *reinterpret_cast<const float4*>(bet + c0);
+    float4 acc[KMAX];
+#pragma unroll
+    for (int n = 0; n < KMAX; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int U2 = 8;
+    for (int p0 = rg; p0 < P; p0 += RG * U2) {
+      float4 xv[U2];
+      int pt[U2];
+#pragma unroll
+      for (int u = 0; u < U2; ++u) {
+        int p = p0 + u * RG;
+        pt[u] = p < P ? tok[p] : -1;
+        xv[u] = pt[u] >= 0 ? __ldg(reinterpret_cast<const float4*>(x1 + (size_t)pt[u] * D + c0))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U2; ++u) {
+        if (pt[u] < 0) continue;  // pad rows are exact zeros after the norm
+        int p = p0 + u * RG;
+        float2 ms = st[p];
+        float4 z;
+        z.x = (xv[u].x - ms.x) * ms.y * gm.x + bt.x;
+        z.y = (xv[u].y - ms.x) * ms.y * gm.y + bt.y;
+        z.z = (xv[u].z - ms.x) * ms.y * gm.z + bt.z;
+        z.w = (xv[u].w - ms.x) * ms.y * gm.w + bt.w;
+#pragma unroll
+        for (int n = 0; n < KMAX; ++n) {
+          if (n < k) {
+            float wgt = lg[p * k + n];
+            acc[n].x = fmaf(wgt, z.x, acc[n].x); acc[n].y = fmaf(wgt, z.y, acc[n].y);
+            acc[n].z = fmaf(wgt, z.z, acc[n].z); acc[n].w = fmaf(wgt, z.w, acc[n].w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < KMAX; ++n)
+      if (n < k) *reinterpret_cast<float4*>(part + ((size_t)(rg * k + n)) * D + c0) = acc[n];
+  }
+  __syncthreads();
+  for (int i = tid; i < k * D; i += 512) {
+    int n = i / D, c = i - n * D;
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < RG; ++r) s += part[((size_t)(r * k + n)) * D + c];
+    landmarks[((size_t)n * grid.R + rho) * D + c] = __float2half_rn(s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // grid (heads, k), 256 threads; sequence length R = 64 (the CR-MSA grid is always 8x8 regions).
 __global__ void __launch_bounds__(256) landmark_attn_kernel(const float* __restrict__ lqkv,
                                                             __half* __restrict__ lo, int D,
@@ -406,6 +636,48 @@ cudaError_t launch_crmsa_combine(const float* x1, const float* gamma, const floa
   }
   if (k <= 4) RRT_COMBINE(4) else if (k <= 8) RRT_COMBINE(8) else RRT_COMBINE(16)
 #undef RRT_COMBINE
+  return cudaGetLastError();
+}
+
+static size_t landmarks_smem_bytes(const Grid& grid, int D, int k) {
+  const int V = D / 128, RG = 16 / (V > 0 ? V : 1);
+  size_t fl = 2 * (size_t)D + (size_t)k * D + (((size_t)grid.P * k + 3) & ~(size_t)3) +
+              2 * (size_t)((grid.P + 1) & ~1) + ((grid.P + 3) & ~3) + 32 + (size_t)RG * k * D;
+  return fl * sizeof(float);
+}
+
+bool crmsa_landmarks_supported(const Grid& grid, int D, int k) {
+  const int V = D / 128;
+  if (D % 128 || k < 1 || k > RRT_MAX_K_DEV) return false;
+  if (V != 1 && V != 2 && V != 4 && V != 8) return false;
+  return landmarks_smem_bytes(grid, D, k) <= 227 * 1024;
+}
+
+cudaError_t launch_crmsa_landmarks(const float* x1, const float* gamma, const float* beta,
+                                   const float* phi, float* logits, __half* landmarks,
+                                   float2* rstat, const Grid& grid, int D, int k,
+                                   cudaStream_t stream) {
+  if (!crmsa_landmarks_supported(grid, D, k)) return cudaErrorInvalidValue;
+  const int V = D / 128;
+  size_t smem = landmarks_smem_bytes(grid, D, k);
+#define RRT_LM(VV, KM)                                                                           \
+  {                                                                                              \
+    cudaError_t e = cudaFuncSetAttribute(crmsa_landmarks_kernel<VV, KM>,                         \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+    if (e != cudaSuccess) return e;                                                              \
+    crmsa_landmarks_kernel<VV, KM><<<grid.R, 512, smem, stream>>>(x1, gamma, beta, phi, logits,  \
+                                                                  landmarks, rstat, grid, k);    \
+  }
+#define RRT_LM_K(VV) \
+  { if (k <= 4) RRT_LM(VV, 4) else if (k <= 8) RRT_LM(VV, 8) else RRT_LM(VV, 16) }
+  switch (V) {
+    case 1: RRT_LM_K(1) break;
+    case 2: RRT_LM_K(2) break;
+    case 4: RRT_LM_K(4) break;
+    default: RRT_LM_K(8) break;
+  }
+#undef RRT_LM_K
+#undef RRT_LM
   return cudaGetLastError();
 }
 

@@ -79,6 +79,14 @@ cudaError_t launch_crmsa_combine(const float* x1, const float* gamma, const floa
                                  const float2* stats, const float* logits, __half* landmarks,
                                  float2* rstat, const Grid& grid, int D, int k,
                                  cudaStream_t stream);
+// Fused front end (stats + logits + combine) with one CTA per region; cudaErrorInvalidValue when
+// the region does not fit shared memory (callers then use the split kernels above).
+// phi == null: `logits` already holds the crmsa_mlp logits and is only read.
+bool crmsa_landmarks_supported(const Grid& grid, int D, int k);
+cudaError_t launch_crmsa_landmarks(const float* x1, const float* gamma, const float* beta,
+                                   const float* phi, float* logits, __half* landmarks,
+                                   float2* rstat, const Grid& grid, int D, int k,
+                                   cudaStream_t stream);
 // MHA core over the landmarks: batch = k, sequence = R (64), heads, head_dim = D/heads, plain
 // softmax(q k^T * scale) v, fp32 math.  lqkv: [k*R, 3D] fp32 rows (n, rho); lo: [k*R, D] f16.
 cudaError_t launch_landmark_attention(const float* lqkv, __half* lo, int k, int R, int D, int heads,
