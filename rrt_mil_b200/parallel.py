@@ -1,0 +1,83 @@
+"""Bag-parallel execution across GPUs: one process per GPU, bags sharded round-robin, no collective
+on the data path (bags are independent forwards); ONE gather at the end brings the
+per-bag results to every rank (or to rank 0).
+
+The reference has no distributed code at all (single device, batch 1: main.py:103,639).  The host
+logic here (sharding, ragged gather) is backend-agnostic: NCCL over NVLink on the B200 box, gloo in
+the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_bags: int, world_size: int, rank: int) -> List[int]:
+    """Bags of rank ``rank``: i with i % world_size == rank (bag i -> GPU i mod W)."""
+    return list(range(rank, n_bags, world_size))
+
+
+def gather_ragged(local: Sequence[torch.Tensor], n_bags: int, group=None,
+                  dst: Optional[int] = None) -> Optional[List[torch.Tensor]]:
+    """All ranks hold the outputs of their ``shard_indices`` bags (``[N_i, D]`` each, ragged N_i).
+    Returns the ``n_bags`` outputs in bag order on every rank (``dst=None``) or on ``dst`` only.
+
+    One collective for the sizes (tiny) and ONE for the payload: the local bags are packed into a
+    single padded ``[rows_max, D]`` buffer and all-gathered; views are then cut per bag.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = shard_indices(n_bags, world, rank)
+    if len(mine) != len(local):
+        raise ValueError(f"rank {rank} holds {len(local)} bags, expected {len(mine)}")
+    device = local[0].device if local else torch.device("cpu")
+    dtype = local[0].dtype if local else torch.float32
+    width = local[0].shape[1] if local else 0
+    per_rank = (n_bags + world - 1) // world
+    # sizes: [world, per_rank + 1] (last column = feature width, so empty ranks learn it too)
+    sizes = torch.zeros(per_rank + 1, dtype=torch.int64, device=device)
+    for j, t in enumerate(local):
+        sizes[j] = t.shape[0]
+    sizes[per_rank] = width
+    all_sizes = torch.empty(world * (per_rank + 1), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(all_sizes, sizes, group=group)
+    all_sizes = all_sizes.view(world, per_rank + 1).cpu()
+    width = int(all_sizes[:, per_rank].max())
+    rows = all_sizes[:, :per_rank].sum(1)
+    rows_max = int(rows.max())
+    send = torch.zeros(rows_max, width, dtype=dtype, device=device)
+    off = 0
+    for t in local:
+        send[off:off + t.shape[0]] = t
+        off += t.shape[0]
+    recv = torch.empty(world * rows_max, width, dtype=dtype, device=device)
+    dist.all_gather_into_tensor(recv, send, group=group)  # the single payload collective
+    recv = recv.view(world, rows_max, width)
+    if dst is not None and rank != dst:
+        return None
+    out: List[Optional[torch.Tensor]] = [None] * n_bags
+    for r in range(world):
+        off = 0
+        for j, i in enumerate(shard_indices(n_bags, world, r)):
+            n = int(all_sizes[r, j])
+            out[i] = recv[r, off:off + n]
+            off += n
+    return out  # type: ignore[return-value]
+
+
+@torch.no_grad()
+def encode_bags_parallel(encoder, bags: Sequence[torch.Tensor], group=None, gather: bool = True,
+                         dst: Optional[int] = None):
+    """Every rank receives the same list of bags (host or device tensors), encodes its shard on its
+    own GPU with ``encoder.forward_bags`` and, if ``gather``, returns all outputs in bag order."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = shard_indices(len(bags), world, rank)
+    dev = next(encoder.parameters()).device
+    local_in = [bags[i].to(dev, non_blocking=True).contiguous() for i in mine]
+    local_out = encoder.forward_bags(local_in) if local_in else []
+    if not gather:
+        return local_out
+    return gather_ragged(local_out, len(bags), group=group, dst=dst)

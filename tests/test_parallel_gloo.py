@@ -1,0 +1,64 @@
+"""Bag-parallel host logic over world_size-2 gloo on CPU: sharding and the single ragged gather.
+(The encoder itself is CUDA-only; here the per-rank "encoder" is a deterministic CPU stand-in so
+that the collective plumbing is what is tested.)"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rrt_mil_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _StandIn(torch.nn.Module):
+    """forward_bags(x) = 2*x + rank-independent bias: any rank must produce the same result."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.ones(1))
+
+    def forward_bags(self, bags):
+        return [2.0 * b + 1.0 for b in bags]
+
+
+def _worker(rank, world, port, lens, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        bags = [torch.randn(n, 8, generator=g) for n in lens]
+        outs = parallel.encode_bags_parallel(_StandIn(), bags)
+        ok = len(outs) == len(bags) and all(torch.equal(o, 2.0 * b + 1.0) for o, b in zip(outs, bags))
+        only0 = parallel.encode_bags_parallel(_StandIn(), bags, dst=0)
+        ok = ok and ((only0 is None) == (rank != 0))
+        local = parallel.encode_bags_parallel(_StandIn(), bags, gather=False)
+        ok = ok and len(local) == len(parallel.shard_indices(len(bags), world, rank))
+        results[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lens", [[5, 3, 9, 1, 7], [4], [6, 6], [2, 0 + 1, 3]])
+def test_sharded_encode_and_single_gather_world2(lens):
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, port, lens, results), nprocs=world, join=True)
+    assert dict(results) == {0: True, 1: True}
+
+
+def test_shard_indices_partition_the_bags():
+    for n in (0, 1, 7, 8, 9):
+        for w in (1, 2, 4, 8):
+            seen = sorted(i for r in range(w) for i in parallel.shard_indices(n, w, r))
+            assert seen == list(range(n))
