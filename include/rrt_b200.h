@@ -161,8 +161,13 @@ RRT_API int rrt_crmsa_block_forward(const rrt_config* cfg, const rrt_weights* w,
                                     size_t workspace_bytes, void* stream);
 
 /* Debug: when non-NULL, the first 8 CTAs of every tcgen05 GEMM launch write clock64 stamps of their
- * pipeline phases into device_buffer[8][16] (int64).  NULL switches the trace off (default). */
+ * pipeline phases into device_buffer[launch % 8][8][16] (int64).  NULL switches the trace off. */
 RRT_API int rrt_debug_set_gemm_trace(void* device_buffer);
+
+/* Debug / tuning: thread-block cluster shape of the bag-sized tcgen05 GEMMs (TMA multicast of the
+ * operand tiles): 11 = no clusters (default: fastest on B200), 21 = 2x1, 22 = 2x2.  Results do not
+ * depend on it. */
+RRT_API int rrt_debug_set_gemm_cluster(int32_t mode);
 
 /* dst[i] = fp16(src[i]), round to nearest, saturating at +-65504.  dst is n fp16 values; n % 4 == 0. */
 RRT_API int rrt_convert_f16(const float* src, void* dst, int64_t n, void* stream);

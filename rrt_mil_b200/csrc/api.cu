@@ -564,6 +564,12 @@ RRT_API int rrt_debug_set_gemm_trace(void* device_buffer) {
   return RRT_OK;
 }
 
+RRT_API int rrt_debug_set_gemm_cluster(int32_t mode) {
+  if (mode != 22 && mode != 21 && mode != 11) return fail(RRT_E_INVALID, "mode must be 22, 21 or 11");
+  rrt::set_gemm_cluster_mode(mode);
+  return RRT_OK;
+}
+
 RRT_API int rrt_convert_f16(const float* src, void* dst, int64_t n, void* stream) {
   if (!src || !dst || n < 0 || n % 4) return fail(RRT_E_INVALID, "bad argument");
   StageScope s_(kStOther, (cudaStream_t)stream);

@@ -66,11 +66,21 @@ __device__ __forceinline__ void store_out4(__half* base, size_t off, float4 v) {
   *reinterpret_cast<uint2*>(base + off) = pack_h4(v);
 }
 
-template <int MODE, int BN, typename OutT>
+// CM x CN: thread-block cluster shape.  CTA (ci, cj) of a cluster computes output tile
+// (m-block mc*CM+ci, n-tile nc*CN+cj).  The A tile of a cluster row is needed by its CN CTAs and the
+// W tile of a cluster column by its CM CTAs: every CTA TMA-loads a 1/CN slice of its A tile and a
+// 1/CM slice of its W tile and MULTICASTS them to the CTAs that share them, which divides the L2->SMEM
+// operand traffic (the measured bound of the 1x1 kernel) by up to 2 for a 2x2 cluster.
+template <int MODE, int BN, typename OutT, int CM, int CN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                        const __grid_constant__ CUtensorMap tmB, Tc05Params p) {
+                        const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmC, Tc05Params p) {
   using Cfg = TileCfg<BN>;
+  constexpr int CSIZE = CM * CN;
+  // plain stores (kEpiStore): the epilogue hands each 32x32 chunk to the TMA engine; the scatter /
+  // tanh epilogues keep st.global (rows are permuted resp. the layer is tiny)
+  constexpr bool kTmaStore = MODE == kEpiStore;
   constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int TMEM_COLS = Cfg::TMEM_COLS;
   constexpr int NCHUNK = BN / 32;                 // 32-column chunks of the accumulator
@@ -92,10 +102,11 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
   if (warp == 0 && lane == 0) prefetch_tensormap(&tmA);
   if (warp == 3 && lane == 0) prefetch_tensormap(&tmB);
+  if (kTmaStore && warp == 2 && lane == 0) prefetch_tensormap(&tmC);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 2);   // the A producer and the B producer each arrive once (+ their bytes)
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], CM + CN - 1);  // MMA commits of every CTA that multicasts into this stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -105,30 +116,46 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (CSIZE > 1) cluster_sync_all(); else __syncthreads();  // barriers of every peer are initialised
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) stamp(p, 1);
 
-  const int tiles_n = (p.N + BN - 1) / BN;
-  const int num_tiles = ((p.M + BM - 1) / BM) * tiles_n;
+  // cluster-tile schedule: every CTA of a cluster walks the same list, so that the multicast
+  // producers / consumers of the peers stay in lock step stage by stage
+  const int crank = CSIZE > 1 ? (int)cluster_ctarank() : 0;
+  const int ci = crank % CM, cj = crank / CM;
+  const int cluster_id = blockIdx.x / CSIZE, num_clusters = gridDim.x / CSIZE;
+  const int tiles_mc = ((p.M + BM - 1) / BM + CM - 1) / CM;
+  const int tiles_nc = ((p.N + BN - 1) / BN + CN - 1) / CN;
+  const int num_ctiles = tiles_mc * tiles_nc;
   const int KB = p.K / BK;
+  // peers that share my A tile (same ci) / my W tile (same cj); rank = ci + CM * cj
+  uint16_t mask_a = 0, mask_b = 0;
+#pragma unroll
+  for (int j = 0; j < CN; ++j) mask_a |= (uint16_t)(1u << (ci + CM * j));
+#pragma unroll
+  for (int i = 0; i < CM; ++i) mask_b |= (uint16_t)(1u << (i + CM * cj));
 
   if (warp == 0 || warp == 3) {
-    if (lane == 0) {  // ===== TMA producers: warp 0 streams A tiles, warp 3 streams W tiles =====
+    if (lane == 0) {  // ===== TMA producers: warp 0 streams A slices, warp 3 streams W slices =====
       const bool is_a = warp == 0;
       int s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+        const int m0 = ((ct / tiles_nc) * CM + ci) * BM, n0 = ((ct % tiles_nc) * CN + cj) * BN;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait(&empty[s], ph ^ 1);  // every CTA that reads or refills this stage has released it
           if (is_a) {
-            mbar_arrive_expect_tx(&full[s], A_BYTES);
-            tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, m0);
-            if (tile == (int)blockIdx.x && kb == 0) stamp(p, 2);
+            mbar_arrive_expect_tx(&full[s], A_BYTES);  // my slice + the peers' slices of MY tile
+            uint8_t* dst = sA + s * A_BYTES + cj * (A_BYTES / CN);
+            if (CN > 1) tma_load_2d_mcast(dst, &tmA, &full[s], kb * BK, m0 + cj * (BM / CN), mask_a);
+            else tma_load_2d(dst, &tmA, &full[s], kb * BK, m0);
+            if (ct == cluster_id && kb == 0) stamp(p, 2);
           } else {
             mbar_arrive_expect_tx(&full[s], B_BYTES);
-            tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BK, n0);
+            uint8_t* dst = sB + s * B_BYTES + ci * (B_BYTES / CM);
+            if (CM > 1) tma_load_2d_mcast(dst, &tmB, &full[s], kb * BK, n0 + ci * (BN / CM), mask_b);
+            else tma_load_2d(dst, &tmB, &full[s], kb * BK, n0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -140,20 +167,22 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (lane == 0) {  // ===== MMA issuer =====
       constexpr uint32_t idesc = umma_idesc(kFmtF16, BM, BN);
       int s = 0, ph = 0, acc = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
         mbar_wait(&tempty[acc], aph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          if (tile == (int)blockIdx.x && kb == 0) stamp(p, 4);
+          if (ct == cluster_id && kb == 0) stamp(p, 4);
           const uint64_t ad = umma_desc_k_sw128(smem_u32(sA + s * A_BYTES));
           const uint64_t bd = umma_desc_k_sw128(smem_u32(sB + s * B_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)  // 16 fp16 = 32 bytes per MMA along K: +2 in 16-B units
             umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
+          // smem stage reusable once these MMAs have read it: tell every CTA that writes into it
+          if (CSIZE > 1) umma_commit_mcast(&empty[s], (uint16_t)(mask_a | mask_b));
+          else umma_commit(&empty[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull[acc]);  // accumulator complete
@@ -170,8 +199,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     OutT* const out = reinterpret_cast<OutT*>(p.C);
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
     int acc = 0, aph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+      const int m0 = ((ct / tiles_nc) * CM + ci) * BM, n0 = ((ct % tiles_nc) * CN + cj) * BN;
       // output row of each of the 8 row groups this lane stores (mode 2: region slot -> token)
       long long orow[8];
 #pragma unroll
@@ -188,15 +217,45 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         }
         orow[i] = o;
       }
+      // TMA-store mode: thread = row needs the bias of all 32 columns of a chunk; lane l keeps
+      // column l of every chunk and the value is broadcast with a shuffle when used
+      float bias_l[NC];
+      if (kTmaStore) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const int gc = n0 + (c_begin + j) * 32 + lane;
+          bias_l[j] = (p.bias && gc < p.N) ? __ldg(p.bias + gc) : 0.f;
+        }
+      }
+      // bias of this warp's chunks: fetched while the MMA warp is still producing the accumulator
+      float4 bias_r[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int gc = n0 + (c_begin + j) * 32 + sub_c;
+        bias_r[j] = (p.bias && gc < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + gc))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float4 v[8];
+      auto load_resid = [&](int j) {  // residual rows of chunk j: eight independent 16-byte loads
+        const int gc = n0 + (c_begin + j) * 32 + sub_c;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (orow[i] >= 0 && gc < p.N)
+            v[i] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)orow[i] * p.N + gc));
+        }
+      };
+      if (MODE == kEpiResidualUnpart) load_resid(0);
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
-      if (tile == (int)blockIdx.x && threadIdx.x == 128) stamp(p, 6);
+      if (ct == cluster_id && threadIdx.x == 128) stamp(p, 6);
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c_begin * 32;
       uint32_t r[2][32];
       tmem_ld_32x32(t_addr, r[0]);
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         tmem_ld_wait();  // chunk j is in registers
+        if (ct == cluster_id && threadIdx.x == 128 && j < 2) stamp(p, 10 + 3 * j);
         if (j + 1 < NC) {
           tmem_ld_32x32(t_addr + (j + 1) * 32, r[(j + 1) & 1]);  // overlaps the stores of chunk j
         } else {
@@ -205,27 +264,57 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
+        const uint32_t* rr = r[j & 1];
+        if (kTmaStore) {
+          // thread = output row; +bias, convert, write the 32-column row segment into this warp's
+          // staging buffer in the TMA swizzle of its row pitch, then one lane issues the tile store
+          constexpr int ROWB = 32 * (int)sizeof(OutT);      // 64 B (f16) or 128 B (fp32) per row
+          constexpr int NCH = ROWB / 16;                     // 16-byte chunks per row
+          // the 4 KB scratch of this warp holds two f16 staging tiles or one fp32 tile
+          constexpr int NBUF = (2 * 32 * ROWB <= 32 * EPI_LD * 4) ? 2 : 1;
+          uint8_t* stage = reinterpret_cast<uint8_t*>(scratch) + (j % NBUF) * (32 * ROWB);
+          if (j >= NBUF) {  // the store that last read this buffer must have drained it
+            if (lane == 0) tma_store_wait_read<NBUF - 1>();
+            __syncwarp();
+          }
+          uint8_t* rowp = stage + lane * ROWB;
+          // swizzle: 16-B chunk index ^= bits of the row (128B pattern: row%8; 64B pattern: (row/2)%4)
+          const int sw = ROWB == 128 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+          for (int q = 0; q < NCH; ++q) {
+            constexpr int EPC = 16 / (int)sizeof(OutT);      // elements per 16-byte chunk
+            float f[EPC];
+#pragma unroll
+            for (int e = 0; e < EPC; ++e)
+              f[e] = __uint_as_float(rr[q * EPC + e]) + __shfl_sync(0xffffffffu, bias_l[j], q * EPC + e);
+            uint4 pk;
+            if (sizeof(OutT) == 2) {
+              pk = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4 % EPC], f[5 % EPC]),
+                              pack_h2(f[6 % EPC], f[7 % EPC]));
+            } else {
+              pk = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                              __float_as_uint(f[3]));
+            }
+            *reinterpret_cast<uint4*>(rowp + 16 * (q ^ sw)) = pk;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, stage, n0 + (c_begin + j) * 32, m0 + quad * 32);
+            tma_store_commit();
+          }
+          if (ct == cluster_id && threadIdx.x == 128 && j < 2) stamp(p, 11 + 3 * j);
+        } else {
         const int gc = n0 + (c_begin + j) * 32 + sub_c;
         const bool col_ok = gc < p.N;
-        float4 v[8];
-        if (MODE == kEpiResidualUnpart) {
-          // residual rows: all eight loads in flight while the chunk is transposed through smem
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (orow[i] >= 0 && col_ok)
-              v[i] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)orow[i] * p.N + gc));
-          }
-        }
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(p.bias + gc));
-        const uint32_t* rr = r[j & 1];
+        const float4 bv = bias_r[j];
 #pragma unroll
         for (int q = 0; q < 8; ++q)  // row = lane; 16-byte slot q lands at slot q ^ (row & 7)
           *reinterpret_cast<float4*>(scratch + lane * EPI_LD + 4 * (q ^ (lane & 7))) =
               make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
                           __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
         __syncwarp();
+        if (ct == cluster_id && threadIdx.x == 128 && j < 2) stamp(p, 11 + 3 * j);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = 4 * i + sub_r;
@@ -242,15 +331,24 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           if (orow[i] >= 0 && col_ok) store_out4(out, (size_t)orow[i] * p.N + gc, v[i]);
+        if (ct == cluster_id && threadIdx.x == 128 && j < 2) stamp(p, 12 + 3 * j);
+        if (MODE == kEpiResidualUnpart && j + 1 < NC) load_resid(j + 1);  // next chunk's residual rows
+        __syncwarp();
+        }  // !kTmaStore
+      }
+      if (kTmaStore) {  // both staging buffers are free again before the next tile reuses them
+        if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
       }
       if (++acc == 2) { acc = 0; aph ^= 1; }
-      if (threadIdx.x == 128) stamp(p, tile == (int)blockIdx.x ? 7 : 8);
+      if (threadIdx.x == 128) stamp(p, ct == cluster_id ? 7 : 8);
     }
   }
 
+  if (kTmaStore && warp >= 4 && lane == 0) tma_store_wait_all<0>();  // smem must outlive the stores
   tc_fence_before();
-  __syncthreads();
+  // no CTA may exit while a peer can still multicast into its smem or arrive on its barriers
+  if (CSIZE > 1) cluster_sync_all(); else __syncthreads();
   if (threadIdx.x == 0) stamp(p, 9);
   if (warp == 2) {
     tc_fence_after();
@@ -296,6 +394,21 @@ bool make_map(CUtensorMap* m, const __half* base, int rows, int K, int box_rows)
   return r == CUDA_SUCCESS;
 }
 
+// output [rows, N] of 2- or 4-byte elements -> 32 x 32 element boxes; swizzle = the box row pitch
+bool make_store_map(CUtensorMap* m, void* base, int rows, int N, int elem_bytes) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)N * elem_bytes};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                  2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  elem_bytes == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int sm_count() {
   static int n = 0;
   if (!n) {
@@ -317,38 +430,72 @@ cudaError_t launch_convert_f16(const float* src, __half* dst, size_t n, cudaStre
   return cudaGetLastError();
 }
 
-long long* g_gemm_trace = nullptr;  // debug hook (rrt_debug_set_gemm_trace)
+long long* g_gemm_trace = nullptr;  // debug hook (rrt_debug_set_gemm_trace): [8 launches][8 CTAs][16]
+static int g_trace_launch = 0;
 
 bool gemm_tcgen05_supported(int M, int N, int K) {
   return M >= 1 && N >= 4 && (N % 4) == 0 && K >= BK && (K % BK) == 0;
 }
 
 namespace {
-template <int MODE, int BN, typename OutT>
+template <int MODE, int BN, typename OutT, int CM, int CN>
 cudaError_t launch_cfg(const __half* a, const __half* w, const Tc05Params& p, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
-  CUtensorMap tmA, tmB;
-  if (!make_map(&tmA, a, p.M, p.K, BM) || !make_map(&tmB, w, p.N, p.K, BN)) return cudaErrorUnknown;
+  constexpr int CSIZE = CM * CN;
+  CUtensorMap tmA, tmB, tmC;
+  if (!make_map(&tmA, a, p.M, p.K, BM / CN) || !make_map(&tmB, w, p.N, p.K, BN / CM))
+    return cudaErrorUnknown;
+  if (MODE == kEpiStore) {
+    if (!make_store_map(&tmC, p.C, p.M, p.N, (int)sizeof(OutT))) return cudaErrorUnknown;
+  } else {
+    tmC = tmA;  // unused by the st.global epilogues
+  }
+  auto kern = gemm_f16_tcgen05_kernel<MODE, BN, OutT, CM, CN>;
   static bool configured = false;  // per instantiation; one process drives one GPU
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<MODE, BN, OutT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-  int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_f16_tcgen05_kernel<MODE, BN, OutT><<<grid, NTHREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  return cudaGetLastError();
+  const int ctiles = (((p.M + BM - 1) / BM + CM - 1) / CM) * (((p.N + BN - 1) / BN + CN - 1) / CN);
+  int clusters = sm_count() / CSIZE;
+  if (ctiles < clusters) clusters = ctiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CSIZE);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CSIZE;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CSIZE > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p);
 }
+
+// CM*10 + CN for the bag-sized GEMMs (rrt_debug_set_gemm_cluster).  Measured on B200 (bench_v8):
+// 1x1 23.0 us, 2x1 23.4 us, 2x2 38.8 us for the QKV GEMM -- L2 already de-duplicates the operand
+// reads of neighbouring CTAs, and the lock-step coupling of a cluster costs more than it saves, so
+// clusters stay OFF by default; the code path is kept for tuning.
+int g_gemm_cluster = 11;
 
 template <int MODE, typename OutT>
 cudaError_t launch_mode(const __half* a, const __half* w, const Tc05Params& p, cudaStream_t stream) {
   // small problems: narrower tiles so that more SMs share the (latency-bound) work
-  const bool narrow = ((p.M + BM - 1) / BM) * ((p.N + 255) / 256) < sm_count() / 2;
-  return narrow ? launch_cfg<MODE, 64, OutT>(a, w, p, stream) : launch_cfg<MODE, 256, OutT>(a, w, p, stream);
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n256 = (p.N + 255) / 256;
+  if (tiles_m * tiles_n256 < sm_count() / 2) return launch_cfg<MODE, 64, OutT, 1, 1>(a, w, p, stream);
+  // bag-sized problems: clusters with multicast operand tiles when the tile grid allows it
+  if (g_gemm_cluster == 22 && tiles_m >= 2 && tiles_n256 >= 2 && tiles_n256 % 2 == 0)
+    return launch_cfg<MODE, 256, OutT, 2, 2>(a, w, p, stream);
+  if (g_gemm_cluster >= 21 && tiles_m >= 2) return launch_cfg<MODE, 256, OutT, 2, 1>(a, w, p, stream);
+  return launch_cfg<MODE, 256, OutT, 1, 1>(a, w, p, stream);
 }
 }  // namespace
+
+void set_gemm_cluster_mode(int mode) { g_gemm_cluster = mode; }
 
 cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool out_f16, int M, int N,
                                 int K, const GemmEpilogue& epi, cudaStream_t stream) {
@@ -359,7 +506,7 @@ cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool 
   Tc05Params p;
   p.M = M; p.N = N; p.K = K;
   p.bias = epi.bias; p.C = c; p.resid = epi.resid; p.grid = epi.grid;
-  p.trace = g_gemm_trace;
+  p.trace = g_gemm_trace ? g_gemm_trace + (size_t)(g_trace_launch++ % 8) * 128 : nullptr;
   if (epi.mode == kEpiResidualUnpart)
     return out_f16 ? cudaErrorInvalidValue : launch_mode<kEpiResidualUnpart, float>(a, w, p, stream);
   if (epi.mode == kEpiTanh)

@@ -6,12 +6,12 @@ import torch
 from rrt_mil_b200 import cabi, RRTEncoder
 import gpu_util as G
 
-NAMES = ["start", "setup", "tma0", "tmaN", "opnd0", "mmaN", "acc0", "epi0", "epiN", "end"]
+NAMES = ["start", "setup", "tma0", "tmaN", "opnd0", "mmaN", "acc0", "epi0", "epiN", "end", "c0ld", "c0tr", "c0st", "c1ld", "c1tr", "c1st"]
 
 
-def show(tag, tr):
-    tr = tr.cpu()
-    for cta in range(3):
+def show(tag, tr, launch=0):
+    tr = tr.cpu()[launch]
+    for cta in range(2):
         t = tr[cta].tolist()
         base = t[0]
         print(f"  {tag} cta{cta}: " + " ".join(f"{n}={t[i]-base if t[i] else -1}" for i, n in enumerate(NAMES)))
@@ -19,7 +19,7 @@ def show(tag, tr):
 
 def main():
     lib = cabi.lib()
-    tr = torch.zeros(8, 16, dtype=torch.int64, device="cuda")
+    tr = torch.zeros(8, 8, 16, dtype=torch.int64, device="cuda")
     for (M, N, K) in [(9216, 1536, 512), (9216, 512, 512), (192, 1536, 512)]:
         a = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5
         b = torch.randn(N, device="cuda")
@@ -30,7 +30,9 @@ def main():
         G.linear_f16(a, w, b)
         torch.cuda.synchronize()
         lib.rrt_debug_set_gemm_trace(None)
-        show(f"linear {M}x{N}x{K}", tr)
+        for l in range(8):
+            if int(tr[l, 0, 9]) != 0:
+                show(f"linear {M}x{N}x{K} (fp32 out)", tr, l)
     # the proj GEMM inside the R-MSA block (residual-scatter epilogue): last GEMM of the block
     m = RRTEncoder(need_init=True).cuda().eval()
     x = torch.randn(9000, 512, device="cuda")
@@ -42,7 +44,9 @@ def main():
         G.rmsa_block(m, 0, x)
         torch.cuda.synchronize()
         lib.rrt_debug_set_gemm_trace(None)
-    show("rmsa block: LAST gemm = proj (stamps of qkv overwritten)", tr)
+    for l in range(8):
+        if int(tr[l, 0, 9]) != 0:
+            show(f"rmsa block gemm (launch slot {l}: qkv f16-out first, then proj)", tr, l)
 
 
 if __name__ == "__main__":
