@@ -37,7 +37,7 @@ extern "C" {
 #define RRT_MAX_RMSA_LAYERS 8 /* n_layers-1 R-MSA TransLayers (modules/rrt.py:143) */
 #define RRT_MAX_CRMSA_K 16    /* crmsa_k landmarks per region                         */
 #define RRT_MAX_EPEG_K 63     /* odd EPEG kernel length                               */
-#define RRT_MAX_LANES 4       /* concurrent bags inside rrt_encoder_forward_batch     */
+#define RRT_MAX_LANES 8       /* concurrent bags inside rrt_encoder_forward_batch     */
 
 enum {
   RRT_OK = 0,
@@ -164,9 +164,12 @@ RRT_API int rrt_crmsa_block_forward(const rrt_config* cfg, const rrt_weights* w,
  * pipeline phases into device_buffer[launch % 8][8][16] (int64).  NULL switches the trace off. */
 RRT_API int rrt_debug_set_gemm_trace(void* device_buffer);
 
-/* Debug / tuning: thread-block cluster shape of the bag-sized tcgen05 GEMMs (TMA multicast of the
- * operand tiles): 11 = no clusters (default: fastest on B200), 21 = 2x1, 22 = 2x2.  Results do not
- * depend on it. */
+/* Debug: same for the region-resident attention kernel: device_buffer[8][8] (int64). */
+RRT_API int rrt_debug_set_attn_trace(void* device_buffer);
+
+/* Debug / tuning: kernel variant of the bag-sized tcgen05 GEMMs.  11 = single-CTA 128x256 tiles
+ * (default, fastest at these sizes); 2 = CTA pairs (cta_group::2, M=256 tiles); 21 / 22 = single-CTA
+ * tiles with 2x1 / 2x2 cluster TMA multicast.  Results do not depend on it. */
 RRT_API int rrt_debug_set_gemm_cluster(int32_t mode);
 
 /* dst[i] = fp16(src[i]), round to nearest, saturating at +-65504.  dst is n fp16 values; n % 4 == 0. */

@@ -16,7 +16,7 @@ RRT_ABI_VERSION = 3
 RRT_MAX_RMSA_LAYERS = 8
 RRT_MAX_CRMSA_K = 16
 RRT_MAX_EPEG_K = 63
-RRT_MAX_LANES = 4
+RRT_MAX_LANES = 8
 RRT_OK, RRT_E_INVALID, RRT_E_WORKSPACE, RRT_E_CUDA = 0, -1, -2, -3
 RRT_MATH_F16 = 0
 
@@ -77,6 +77,7 @@ SIGNATURES = {
     "rrt_stage_name": (C.c_char_p, [C.c_int32]),
     "rrt_stage_timing_read": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "rrt_debug_set_gemm_trace": (C.c_int, [_P]),
+    "rrt_debug_set_attn_trace": (C.c_int, [_P]),
     "rrt_debug_set_gemm_cluster": (C.c_int, [C.c_int32]),
     "rrt_convert_f16": (C.c_int, [_P, _P, C.c_int64, _P]),
     "rrt_linear_f16_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),

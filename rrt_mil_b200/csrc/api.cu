@@ -564,8 +564,14 @@ RRT_API int rrt_debug_set_gemm_trace(void* device_buffer) {
   return RRT_OK;
 }
 
+RRT_API int rrt_debug_set_attn_trace(void* device_buffer) {
+  rrt::g_attn_trace = static_cast<long long*>(device_buffer);
+  return RRT_OK;
+}
+
 RRT_API int rrt_debug_set_gemm_cluster(int32_t mode) {
-  if (mode != 22 && mode != 21 && mode != 11) return fail(RRT_E_INVALID, "mode must be 22, 21 or 11");
+  if (mode != 2 && mode != 22 && mode != 21 && mode != 11)
+    return fail(RRT_E_INVALID, "mode must be 2, 11, 21 or 22");
   rrt::set_gemm_cluster_mode(mode);
   return RRT_OK;
 }

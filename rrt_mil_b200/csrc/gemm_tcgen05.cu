@@ -66,6 +66,161 @@ __device__ __forceinline__ void store_out4(__half* base, size_t off, float4 v) {
   *reinterpret_cast<uint2*>(base + off) = pack_h4(v);
 }
 
+// Epilogue of one 128 x BN accumulator for one of the 8 epilogue warps (two per TMEM lane quadrant):
+// software-pipelined tcgen05.ld, accumulator released (release()) as soon as this warp's slice is in
+// registers, then either TMA tile stores (kEpiStore) or transpose + st.global (tanh / residual scatter).
+template <int MODE, int BN, typename OutT, typename ReleaseFn>
+__device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtensorMap* tmC,
+                                              uint32_t tmem_acc, uint64_t* tfull_bar,
+                                              uint32_t tfull_parity, int m0, int n0, int ew, int lane,
+                                              float* scratch, bool first, ReleaseFn release) {
+  constexpr bool kTmaStore = MODE == kEpiStore;
+  constexpr int NC = (BN / 32) / 2;  // chunks per epilogue warp
+  const int quad = ew & 3;           // TMEM lanes [32*quad, 32*quad+32) are readable by this warp
+  const int c_begin = (ew >> 2) * NC;
+  OutT* const out = reinterpret_cast<OutT*>(p.C);
+  const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+    // output row of each of the 8 row groups this lane stores (mode 2: region slot -> token)
+    long long orow[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int gr = m0 + quad * 32 + 4 * i + sub_r;
+      long long o = -1;
+      if (gr < p.M) {
+        if (MODE == kEpiResidualUnpart) {
+          int tok = p.grid.slot_to_token(gr);
+          if (tok < p.grid.L) o = tok;
+        } else {
+          o = gr;
+        }
+      }
+      orow[i] = o;
+    }
+    // TMA-store mode: thread = row needs the bias of all 32 columns of a chunk; lane l keeps
+    // column l of every chunk and the value is broadcast with a shuffle when used
+    float bias_l[NC];
+    if (kTmaStore) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int gc = n0 + (c_begin + j) * 32 + lane;
+        bias_l[j] = (p.bias && gc < p.N) ? __ldg(p.bias + gc) : 0.f;
+      }
+    }
+    // bias of this warp's chunks: fetched while the MMA warp is still producing the accumulator
+    float4 bias_r[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int gc = n0 + (c_begin + j) * 32 + sub_c;
+      bias_r[j] = (p.bias && gc < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + gc))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 v[8];
+    auto load_resid = [&](int j) {  // residual rows of chunk j: eight independent 16-byte loads
+      const int gc = n0 + (c_begin + j) * 32 + sub_c;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (orow[i] >= 0 && gc < p.N)
+          v[i] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)orow[i] * p.N + gc));
+      }
+    };
+    if (MODE == kEpiResidualUnpart) load_resid(0);
+    mbar_wait(tfull_bar, tfull_parity);
+    tc_fence_after();
+    if (first && threadIdx.x == 128) stamp(p, 6);
+    const uint32_t t_addr = tmem_acc + ((uint32_t)(quad * 32) << 16) + c_begin * 32;
+    uint32_t r[2][32];
+    tmem_ld_32x32(t_addr, r[0]);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      tmem_ld_wait();  // chunk j is in registers
+      if (first && threadIdx.x == 128 && j < 2) stamp(p, 10 + 3 * j);
+      if (j + 1 < NC) {
+        tmem_ld_32x32(t_addr + (j + 1) * 32, r[(j + 1) & 1]);  // overlaps the stores of chunk j
+      } else {
+        // the whole accumulator slice of this warp has left TMEM: release it to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        release();
+      }
+      const uint32_t* rr = r[j & 1];
+      if (kTmaStore) {
+        // thread = output row; +bias, convert, write the 32-column row segment into this warp's
+        // staging buffer in the TMA swizzle of its row pitch, then one lane issues the tile store
+        constexpr int ROWB = 32 * (int)sizeof(OutT);      // 64 B (f16) or 128 B (fp32) per row
+        constexpr int NCH = ROWB / 16;                     // 16-byte chunks per row
+        // the 4 KB scratch of this warp holds two f16 staging tiles or one fp32 tile
+        constexpr int NBUF = (2 * 32 * ROWB <= 32 * EPI_LD * 4) ? 2 : 1;
+        uint8_t* stage = reinterpret_cast<uint8_t*>(scratch) + (j % NBUF) * (32 * ROWB);
+        if (j >= NBUF) {  // the store that last read this buffer must have drained it
+          if (lane == 0) tma_store_wait_read<NBUF - 1>();
+          __syncwarp();
+        }
+        uint8_t* rowp = stage + lane * ROWB;
+        // swizzle: 16-B chunk index ^= bits of the row (128B pattern: row%8; 64B pattern: (row/2)%4)
+        const int sw = ROWB == 128 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+          constexpr int EPC = 16 / (int)sizeof(OutT);      // elements per 16-byte chunk
+          float f[EPC];
+#pragma unroll
+          for (int e = 0; e < EPC; ++e)
+            f[e] = __uint_as_float(rr[q * EPC + e]) + __shfl_sync(0xffffffffu, bias_l[j], q * EPC + e);
+          uint4 pk;
+          if (sizeof(OutT) == 2) {
+            pk = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4 % EPC], f[5 % EPC]),
+                            pack_h2(f[6 % EPC], f[7 % EPC]));
+          } else {
+            pk = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                            __float_as_uint(f[3]));
+          }
+          *reinterpret_cast<uint4*>(rowp + 16 * (q ^ sw)) = pk;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmC, stage, n0 + (c_begin + j) * 32, m0 + quad * 32);
+          tma_store_commit();
+        }
+        if (first && threadIdx.x == 128 && j < 2) stamp(p, 11 + 3 * j);
+      } else {
+      const int gc = n0 + (c_begin + j) * 32 + sub_c;
+      const bool col_ok = gc < p.N;
+      const float4 bv = bias_r[j];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)  // row = lane; 16-byte slot q lands at slot q ^ (row & 7)
+        *reinterpret_cast<float4*>(scratch + lane * EPI_LD + 4 * (q ^ (lane & 7))) =
+            make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
+                        __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
+      __syncwarp();
+      if (first && threadIdx.x == 128 && j < 2) stamp(p, 11 + 3 * j);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = 4 * i + sub_r;
+        float4 a = *reinterpret_cast<const float4*>(scratch + rl * EPI_LD +
+                                                    4 * ((lane & 7) ^ (rl & 7)));
+        if (MODE == kEpiResidualUnpart) {
+          v[i].x += a.x + bv.x; v[i].y += a.y + bv.y; v[i].z += a.z + bv.z; v[i].w += a.w + bv.w;
+        } else {
+          v[i] = make_float4(a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w);
+          if (MODE == kEpiTanh)
+            v[i] = make_float4(tanhf(v[i].x), tanhf(v[i].y), tanhf(v[i].z), tanhf(v[i].w));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (orow[i] >= 0 && col_ok) store_out4(out, (size_t)orow[i] * p.N + gc, v[i]);
+      if (first && threadIdx.x == 128 && j < 2) stamp(p, 12 + 3 * j);
+      if (MODE == kEpiResidualUnpart && j + 1 < NC) load_resid(j + 1);  // next chunk's residual rows
+      __syncwarp();
+      }  // !kTmaStore
+    }
+    if (kTmaStore) {  // both staging buffers are free again before the next tile reuses them
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+    }
+}
+
 // CM x CN: thread-block cluster shape.  CTA (ci, cj) of a cluster computes output tile
 // (m-block mc*CM+ci, n-tile nc*CN+cj).  The A tile of a cluster row is needed by its CN CTAs and the
 // W tile of a cluster column by its CM CTAs: every CTA TMA-loads a 1/CN slice of its A tile and a
@@ -83,8 +238,6 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   constexpr bool kTmaStore = MODE == kEpiStore;
   constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int TMEM_COLS = Cfg::TMEM_COLS;
-  constexpr int NCHUNK = BN / 32;                 // 32-column chunks of the accumulator
-  constexpr int NC = NCHUNK / 2;                  // chunks per epilogue warp (two warps per quadrant)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -193,153 +346,13 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     __syncwarp();
   } else if (warp >= 4) {  // ===== epilogue: 8 warps, two per TMEM lane quadrant =====
     const int ew = warp - 4;
-    const int quad = ew & 3;          // TMEM lanes [32*quad, 32*quad+32) are readable by this warp
-    const int c_begin = (ew >> 2) * NC;  // first accumulator chunk of this warp
     float* scratch = sEpi + ew * 32 * EPI_LD;
-    OutT* const out = reinterpret_cast<OutT*>(p.C);
-    const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
     int acc = 0, aph = 0;
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
       const int m0 = ((ct / tiles_nc) * CM + ci) * BM, n0 = ((ct % tiles_nc) * CN + cj) * BN;
-      // output row of each of the 8 row groups this lane stores (mode 2: region slot -> token)
-      long long orow[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int gr = m0 + quad * 32 + 4 * i + sub_r;
-        long long o = -1;
-        if (gr < p.M) {
-          if (MODE == kEpiResidualUnpart) {
-            int tok = p.grid.slot_to_token(gr);
-            if (tok < p.grid.L) o = tok;
-          } else {
-            o = gr;
-          }
-        }
-        orow[i] = o;
-      }
-      // TMA-store mode: thread = row needs the bias of all 32 columns of a chunk; lane l keeps
-      // column l of every chunk and the value is broadcast with a shuffle when used
-      float bias_l[NC];
-      if (kTmaStore) {
-#pragma unroll
-        for (int j = 0; j < NC; ++j) {
-          const int gc = n0 + (c_begin + j) * 32 + lane;
-          bias_l[j] = (p.bias && gc < p.N) ? __ldg(p.bias + gc) : 0.f;
-        }
-      }
-      // bias of this warp's chunks: fetched while the MMA warp is still producing the accumulator
-      float4 bias_r[NC];
-#pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        const int gc = n0 + (c_begin + j) * 32 + sub_c;
-        bias_r[j] = (p.bias && gc < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + gc))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      float4 v[8];
-      auto load_resid = [&](int j) {  // residual rows of chunk j: eight independent 16-byte loads
-        const int gc = n0 + (c_begin + j) * 32 + sub_c;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (orow[i] >= 0 && gc < p.N)
-            v[i] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)orow[i] * p.N + gc));
-        }
-      };
-      if (MODE == kEpiResidualUnpart) load_resid(0);
-      mbar_wait(&tfull[acc], aph);
-      tc_fence_after();
-      if (ct == cluster_id && threadIdx.x == 128) stamp(p, 6);
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c_begin * 32;
-      uint32_t r[2][32];
-      tmem_ld_32x32(t_addr, r[0]);
-#pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        tmem_ld_wait();  // chunk j is in registers
-        if (ct == cluster_id && threadIdx.x == 128 && j < 2) stamp(p, 10 + 3 * j);
-        if (j + 1 < NC) {
-          tmem_ld_32x32(t_addr + (j + 1) * 32, r[(j + 1) & 1]);  // overlaps the stores of chunk j
-        } else {
-          // the whole accumulator slice of this warp has left TMEM: release it to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
-        }
-        const uint32_t* rr = r[j & 1];
-        if (kTmaStore) {
-          // thread = output row; +bias, convert, write the 32-column row segment into this warp's
-          // staging buffer in the TMA swizzle of its row pitch, then one lane issues the tile store
-          constexpr int ROWB = 32 * (int)sizeof(OutT);      // 64 B (f16) or 128 B (fp32) per row
-          constexpr int NCH = ROWB / 16;                     // 16-byte chunks per row
-          // the 4 KB scratch of this warp holds two f16 staging tiles or one fp32 tile
-          constexpr int NBUF = (2 * 32 * ROWB <= 32 * EPI_LD * 4) ? 2 : 1;
-          uint8_t* stage = reinterpret_cast<uint8_t*>(scratch) + (j % NBUF) * (32 * ROWB);
-          if (j >= NBUF) {  // the store that last read this buffer must have drained it
-            if (lane == 0) tma_store_wait_read<NBUF - 1>();
-            __syncwarp();
-          }
-          uint8_t* rowp = stage + lane * ROWB;
-          // swizzle: 16-B chunk index ^= bits of the row (128B pattern: row%8; 64B pattern: (row/2)%4)
-          const int sw = ROWB == 128 ? (lane & 7) : ((lane >> 1) & 3);
-#pragma unroll
-          for (int q = 0; q < NCH; ++q) {
-            constexpr int EPC = 16 / (int)sizeof(OutT);      // elements per 16-byte chunk
-            float f[EPC];
-#pragma unroll
-            for (int e = 0; e < EPC; ++e)
-              f[e] = __uint_as_float(rr[q * EPC + e]) + __shfl_sync(0xffffffffu, bias_l[j], q * EPC + e);
-            uint4 pk;
-            if (sizeof(OutT) == 2) {
-              pk = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4 % EPC], f[5 % EPC]),
-                              pack_h2(f[6 % EPC], f[7 % EPC]));
-            } else {
-              pk = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
-                              __float_as_uint(f[3]));
-            }
-            *reinterpret_cast<uint4*>(rowp + 16 * (q ^ sw)) = pk;
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmC, stage, n0 + (c_begin + j) * 32, m0 + quad * 32);
-            tma_store_commit();
-          }
-          if (ct == cluster_id && threadIdx.x == 128 && j < 2) stamp(p, 11 + 3 * j);
-        } else {
-        const int gc = n0 + (c_begin + j) * 32 + sub_c;
-        const bool col_ok = gc < p.N;
-        const float4 bv = bias_r[j];
-#pragma unroll
-        for (int q = 0; q < 8; ++q)  // row = lane; 16-byte slot q lands at slot q ^ (row & 7)
-          *reinterpret_cast<float4*>(scratch + lane * EPI_LD + 4 * (q ^ (lane & 7))) =
-              make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
-                          __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
-        __syncwarp();
-        if (ct == cluster_id && threadIdx.x == 128 && j < 2) stamp(p, 11 + 3 * j);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = 4 * i + sub_r;
-          float4 a = *reinterpret_cast<const float4*>(scratch + rl * EPI_LD +
-                                                      4 * ((lane & 7) ^ (rl & 7)));
-          if (MODE == kEpiResidualUnpart) {
-            v[i].x += a.x + bv.x; v[i].y += a.y + bv.y; v[i].z += a.z + bv.z; v[i].w += a.w + bv.w;
-          } else {
-            v[i] = make_float4(a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w);
-            if (MODE == kEpiTanh)
-              v[i] = make_float4(tanhf(v[i].x), tanhf(v[i].y), tanhf(v[i].z), tanhf(v[i].w));
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (orow[i] >= 0 && col_ok) store_out4(out, (size_t)orow[i] * p.N + gc, v[i]);
-        if (ct == cluster_id && threadIdx.x == 128 && j < 2) stamp(p, 12 + 3 * j);
-        if (MODE == kEpiResidualUnpart && j + 1 < NC) load_resid(j + 1);  // next chunk's residual rows
-        __syncwarp();
-        }  // !kTmaStore
-      }
-      if (kTmaStore) {  // both staging buffers are free again before the next tile reuses them
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-      }
+      uint64_t* te = &tempty[acc];
+      epilogue_tile<MODE, BN, OutT>(p, &tmC, tmem_base + acc * BN, &tfull[acc], aph, m0, n0, ew, lane,
+                                    scratch, ct == cluster_id, [&] { if (lane == 0) mbar_arrive(te); });
       if (++acc == 2) { acc = 0; aph ^= 1; }
       if (threadIdx.x == 128) stamp(p, ct == cluster_id ? 7 : 8);
     }
@@ -353,6 +366,148 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a cluster compute one 256 x 256 output
+// tile with M=256 MMAs issued by the leader CTA.  Each CTA stages its own 128 rows of A and only HALF
+// of the W tile (128 of 256 rows); the tensor core reads the other half from the peer's shared
+// memory.  Per SM that is 32 KB of operands per k-block instead of 48 KB -- the operand fill rate per
+// SM, not L2 bandwidth, was the measured limit of the single-CTA main loop (tools/gemm_trace.py) --
+// and the smaller stage buys a 6-deep ring.  Accumulators stay per CTA (rows 0..127 / 128..255 of the
+// pair tile), so the epilogue is the same as the single-CTA kernel's.
+constexpr int P2_STAGES = 6;
+constexpr int P2_BN = 256;
+constexpr int P2_BHALF_BYTES = (P2_BN / 2) * BK * 2;
+constexpr int P2_STAGE_BYTES = A_BYTES + P2_BHALF_BYTES;
+constexpr int P2_SMEM_BYTES = 1024 + P2_STAGES * P2_STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+static_assert(P2_SMEM_BYTES <= 227 * 1024, "dynamic shared memory budget exceeded");
+
+template <int MODE, typename OutT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
+                             const __grid_constant__ CUtensorMap tmB,
+                             const __grid_constant__ CUtensorMap tmC, Tc05Params p) {
+  constexpr int BN = P2_BN, STAGES = P2_STAGES;
+  constexpr bool kTmaStore = MODE == kEpiStore;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;                               // [STAGES][128 x 64] my rows of A
+  uint8_t* sB = smem + STAGES * A_BYTES;            // [STAGES][128 x 64] my half of the W tile
+  float* sEpi = reinterpret_cast<float*>(smem + STAGES * P2_STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * P2_STAGE_BYTES + EPI_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  if (threadIdx.x == 0) stamp(p, 0);
+
+  if (warp == 0 && lane == 0) prefetch_tensormap(&tmA);
+  if (warp == 3 && lane == 0) prefetch_tensormap(&tmB);
+  if (kTmaStore && warp == 2 && lane == 0) prefetch_tensormap(&tmC);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 2);   // leader only: its two producers arm the bytes of BOTH CTAs
+      mbar_init(&empty[i], 1);  // both CTAs: multicast commit of the leader's MMA warp
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);               // both CTAs: multicast commit
+      mbar_init(&tempty[i], 2 * kEpiWarps);  // leader only: the epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2cta(tmem_slot, 2 * BN);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(p, 1);
+
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_ptiles = ((p.M + 2 * BM - 1) / (2 * BM)) * tiles_n;
+  const int KB = p.K / BK;
+
+  if (warp == 0 || warp == 3) {
+    if (lane == 0) {  // ===== TMA producers (both CTAs): warp 0 = my A rows, warp 3 = my W half =====
+      const bool is_a = warp == 0;
+      int s = 0, ph = 0;
+      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+        const int m0 = (pt / tiles_n) * 2 * BM + (int)crank * BM;
+        const int n0 = (pt % tiles_n) * BN + (int)crank * (BN / 2);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          // the leader's barrier collects the bytes of both CTAs; only the leader's producers arm it
+          if (crank == 0) mbar_arrive_expect_tx(&full[s], 2 * (is_a ? A_BYTES : P2_BHALF_BYTES));
+          if (is_a) {
+            tma_load_2d_2cta(sA + s * A_BYTES, &tmA, &full[s], kb * BK, m0);
+            if (pt == pair_id && kb == 0) stamp(p, 2);
+          } else {
+            tma_load_2d_2cta(sB + s * P2_BHALF_BYTES, &tmB, &full[s], kb * BK, n0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+      if (is_a) stamp(p, 3);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (crank == 0 && lane == 0) {  // ===== MMA issuer: leader CTA only =====
+      constexpr uint32_t idesc = umma_idesc(kFmtF16, 2 * BM, BN);
+      int s = 0, ph = 0, acc = 0, aph = 0;
+      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+        mbar_wait(&tempty[acc], aph ^ 1);  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          if (pt == pair_id && kb == 0) stamp(p, 4);
+          const uint64_t ad = umma_desc_k_sw128(smem_u32(sA + s * A_BYTES));
+          const uint64_t bd = umma_desc_k_sw128(smem_u32(sB + s * P2_BHALF_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_2cta(&empty[s], 0b11);  // stage free in both CTAs
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2cta(&tfull[acc], 0b11);  // accumulator halves complete in both CTAs
+        if (++acc == 2) { acc = 0; aph ^= 1; }
+      }
+      stamp(p, 5);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {  // ===== epilogue (both CTAs, own accumulator half) =====
+    const int ew = warp - 4;
+    float* scratch = sEpi + ew * 32 * EPI_LD;
+    int acc = 0, aph = 0;
+    for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+      const int m0 = (pt / tiles_n) * 2 * BM + (int)crank * BM, n0 = (pt % tiles_n) * BN;
+      uint64_t* te = &tempty[acc];
+      epilogue_tile<MODE, BN, OutT>(p, &tmC, tmem_base + acc * BN, &tfull[acc], aph, m0, n0, ew, lane,
+                                    scratch, pt == pair_id, [&] {
+                                      if (lane == 0) {
+                                        if (crank == 0) mbar_arrive(te);
+                                        else mbar_arrive_remote(te, 0);
+                                      }
+                                    });
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+      if (threadIdx.x == 128) stamp(p, pt == pair_id ? 7 : 8);
+    }
+  }
+
+  if (kTmaStore && warp >= 4 && lane == 0) tma_store_wait_all<0>();
+  tc_fence_before();
+  cluster_sync_all();  // the peer's smem / barriers / TMEM half stay valid until both are done
+  if (threadIdx.x == 0) stamp(p, 9);
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 2 * BN);
   }
 }
 
@@ -481,12 +636,51 @@ cudaError_t launch_cfg(const __half* a, const __half* w, const Tc05Params& p, cu
 // reads of neighbouring CTAs, and the lock-step coupling of a cluster costs more than it saves, so
 // clusters stay OFF by default; the code path is kept for tuning.
 int g_gemm_cluster = 11;
+// 1: bag-sized GEMMs on the cta_group::2 kernel (rrt_debug_set_gemm_cluster(2)).  Measured (bench_v11):
+// main loop 5.2k cycles/tile vs 5.7k single-CTA (5.7k IS the cuBLAS-measured tensor rate), but the
+// cluster set-up and the longer tail cost more than that buys at 3 tiles per CTA: QKV 23.0 vs 20.9 us.
+int g_gemm_pair = 0;
+
+template <int MODE, typename OutT>
+cudaError_t launch_pair(const __half* a, const __half* w, const Tc05Params& p, cudaStream_t stream) {
+  CUtensorMap tmA, tmB, tmC;
+  if (!make_map(&tmA, a, p.M, p.K, BM) || !make_map(&tmB, w, p.N, p.K, P2_BN / 2)) return cudaErrorUnknown;
+  if (MODE == kEpiStore) {
+    if (!make_store_map(&tmC, p.C, p.M, p.N, (int)sizeof(OutT))) return cudaErrorUnknown;
+  } else {
+    tmC = tmA;
+  }
+  auto kern = gemm_f16_tcgen05_2cta_kernel<MODE, OutT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int ptiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + P2_BN - 1) / P2_BN);
+  int pairs = sm_count() / 2;
+  if (ptiles < pairs) pairs = ptiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(pairs * 2);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = P2_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p);
+}
 
 template <int MODE, typename OutT>
 cudaError_t launch_mode(const __half* a, const __half* w, const Tc05Params& p, cudaStream_t stream) {
   // small problems: narrower tiles so that more SMs share the (latency-bound) work
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n256 = (p.N + 255) / 256;
   if (tiles_m * tiles_n256 < sm_count() / 2) return launch_cfg<MODE, 64, OutT, 1, 1>(a, w, p, stream);
+  if (g_gemm_pair && tiles_m >= 2) return launch_pair<MODE, OutT>(a, w, p, stream);
   // bag-sized problems: clusters with multicast operand tiles when the tile grid allows it
   if (g_gemm_cluster == 22 && tiles_m >= 2 && tiles_n256 >= 2 && tiles_n256 % 2 == 0)
     return launch_cfg<MODE, 256, OutT, 2, 2>(a, w, p, stream);
@@ -495,7 +689,11 @@ cudaError_t launch_mode(const __half* a, const __half* w, const Tc05Params& p, c
 }
 }  // namespace
 
-void set_gemm_cluster_mode(int mode) { g_gemm_cluster = mode; }
+void set_gemm_cluster_mode(int mode) {
+  if (mode == 2) { g_gemm_pair = 1; return; }
+  g_gemm_pair = 0;
+  g_gemm_cluster = mode;
+}
 
 cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool out_f16, int M, int N,
                                 int K, const GemmEpilogue& epi, cudaStream_t stream) {

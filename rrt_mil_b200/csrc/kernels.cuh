@@ -58,6 +58,7 @@ cudaError_t launch_gemm_mma(const float* a, const float* w, float* c, int M, int
 // qkv: [Np, 3D] f16, slot order, row layout (3, heads, d).  o: [Np, D] f16, (heads, d).
 // taps: [heads, epeg_k] fp32 or null.
 // Region-resident kernel (P <= 256) and the flash-style fallback for larger regions.
+extern long long* g_attn_trace;  // debug: device buffer [8 CTAs][8] of clock64 stamps, or null
 bool rmsa_attention_f16_supported(const Grid& grid, int D, int heads);
 cudaError_t launch_rmsa_attention_f16(const __half* qkv, const float* taps, __half* o,
                                       const Grid& grid, int D, int heads, int epeg_k,

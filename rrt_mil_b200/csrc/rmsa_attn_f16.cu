@@ -12,7 +12,11 @@
 #include "kernels.cuh"
 
 namespace rrt {
+long long* g_attn_trace = nullptr;  // debug: clock64 stamps of CTA 0..7 (tools/attn_trace.py)
 namespace {
+__device__ __forceinline__ void astamp(long long* tr, int slot) {
+  if (tr && blockIdx.x < 8 && blockIdx.y == 0 && threadIdx.x == 0) tr[blockIdx.x * 8 + slot] = clock64();
+}
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
   uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
@@ -41,7 +45,8 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
                                                                   const float* __restrict__ taps,
                                                                   __half* __restrict__ o, Grid grid,
                                                                   int D, int epeg_k, float qscale,
-                                                                  int n_kv_tiles, int q_rows) {
+                                                                  int n_kv_tiles, int q_rows,
+                                                                  long long* tr) {
   constexpr int LDH = HD + 8;   // halves per smem row: 16-byte row skew keeps ldmatrix conflict-free
   constexpr int KS = HD / 16;   // k16 steps over head_dim
   constexpr int ND = HD / 8;    // 8-wide n-tiles over head_dim
@@ -58,6 +63,7 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int rho = blockIdx.x, h = blockIdx.y;
+  astamp(tr, 0);
   const size_t ld = 3 * (size_t)D;
   const __half* base = qkv + (size_t)rho * P * ld + h * HD;
 
@@ -78,8 +84,10 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
   cp_async_commit();
   if (taps)
     for (int i = tid; i < epeg_k; i += blockDim.x) Ts[i] = __ldg(taps + h * epeg_k + i);
+  astamp(tr, 1);
   cp_async_wait<0>();
   __syncthreads();
+  astamp(tr, 2);
 
   // ---- Q' fragments ----------------------------------------------------------------------------
   const int i0 = 16 * warp;  // first query row of this warp (= first halo row of its band)
@@ -136,6 +144,7 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
     }
   }
 
+  astamp(tr, 3);
   // ---- attention core ---------------------------------------------------------------------------
   float oacc[ND][4];
 #pragma unroll
@@ -213,6 +222,7 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
     }
   }
 
+  astamp(tr, 4);
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 1);
@@ -229,6 +239,7 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
       *reinterpret_cast<uint32_t*>(orow + nd * 8) =
           pack_h2(oacc[nd][hh * 2] * inv, oacc[nd][hh * 2 + 1] * inv);
   }
+  astamp(tr, 5);
 }
 
 template <int HD, int NT, int MAXW>
@@ -259,7 +270,7 @@ cudaError_t launch(const __half* qkv, const float* taps, __half* o, const Grid& 
   float qscale = kLog2e / sqrtf((float)HD);
   dim3 g(grid.R, heads);
   rmsa_attn_f16_kernel<HD, NT, MAXW><<<g, 32 * W, smem, stream>>>(qkv, taps, o, grid, D, epeg_k,
-                                                                  qscale, tiles, q_rows);
+                                                                  qscale, tiles, q_rows, g_attn_trace);
   return cudaGetLastError();
 }
 
