@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -305,7 +306,20 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   rc = f16_weight(w->cr_attn.proj_w, w->cr_attn.proj_w_f16, ws.wconv + (size_t)3 * D * D,
                   (size_t)D * D, st, &wp);
   if (rc) return rc;
-  if (fused_front) {
+  static const int front_mode = [] {  // tuning knob: RRT_CRMSA_FRONT=split (default) | fused | legacy
+    const char* e = getenv("RRT_CRMSA_FRONT");
+    return !e ? 0 : (!strcmp(e, "fused") ? 1 : (!strcmp(e, "legacy") ? 2 : 0));
+  }();
+  bool front_done = false;
+  if (front_mode == 0) {
+    StageScope s_(kStCrCombine, st, 2);
+    cudaError_t e = rrt::launch_crmsa_front_split(x1, w->cr_norm_w, w->cr_norm_b, phi, ws.stats,
+                                                  ws.logits, ws.lm, ws.rstat, g, D, k, st);
+    if (e == cudaSuccess) front_done = true;
+    else if (e != cudaErrorNotSupported) return fail_cuda(e, "crmsa front (split)");
+  }
+  if (front_done) {
+  } else if (fused_front && front_mode != 2) {
     StageScope s_(kStCrCombine, st);
     RRT_CUDA(rrt::launch_crmsa_landmarks(x1, w->cr_norm_w, w->cr_norm_b, phi, ws.logits, ws.lm,
                                          ws.rstat, g, D, k, st), "crmsa landmarks (fused)");

@@ -8,6 +8,7 @@
 
 namespace rrt {
 namespace {
+__device__ long long* g_attn_trace_dev = nullptr;  // debug stamps (shared with tools/attn_trace.py)
 
 // ------------------------------------------------------------------------------------------
 template <int V>
@@ -193,6 +194,224 @@ __global__ void __launch_bounds__(256) crmsa_combine_kernel(
 }
 
 // ------------------------------------------------------------------------------------------
+// CR-MSA front end, split in two all-SM kernels (the profile of the one-CTA-per-region kernel below:
+// 6 M warp-instructions, FFMA only 20 % of them, 64 SMs busy -> instruction-bound).
+//
+// (1) crmsa_rowstats_kernel: warp per padded slot, grid-stride.  LayerNorm statistics and the k
+//     logits from ONE batched butterfly:  G[c,n] = gamma[c]*phi[c,n], A[n] = sum_c G[c,n],
+//     B[n] = sum_c beta[c]*phi[c,n]  ->  logits[n] = rstd*(x.G[:,n] - mean*A[n]) + B[n].
+//     Writes logits [Np,k] and stats [Np] = (mean, rstd); rstd = 0 marks a zero pad slot.
+// (2) crmsa_combine2_kernel: CTA per (region, 128-column chunk).  With w'[p,n] = cw[p,n]*rstd_p,
+//     S1[n] = sum_p w'[p,n]*mean_p, S0[n] = sum_{real p} cw[p,n]:
+//       landmarks[n,c] = gamma[c]*(sum_p w'[p,n]*x1[p,c] - S1[n]) + beta[c]*S0[n]
+//     so the inner loop is one 16-byte load and k FMAs per 4 elements -- no per-element LayerNorm.
+template <int V, int KMAX>
+__global__ void __launch_bounds__(256) crmsa_rowstats_kernel(
+    const float* __restrict__ x1, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ phi, float2* __restrict__ stats, float* __restrict__ logits, Grid grid,
+    int k) {
+  constexpr int D = 128 * V;
+  extern __shared__ __align__(16) float smem[];
+  float* Gt = smem;            // [KMAX][D]
+  float* AB = Gt + KMAX * D;   // [2][KMAX]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wpb = blockDim.x >> 5;
+  if (phi) {
+    for (int n = warp; n < k; n += wpb) {
+      float a = 0.f, b = 0.f;
+      for (int c = lane; c < D; c += 32) {
+        float ph = __ldg(phi + (size_t)c * k + n);
+        float gph = __ldg(gamma + c) * ph;
+        Gt[n * D + c] = gph;
+        a += gph;
+        b = fmaf(__ldg(beta + c), ph, b);
+      }
+      a = warp_sum(a);
+      b = warp_sum(b);
+      if (lane == 0) { AB[n] = a; AB[KMAX + n] = b; }
+    }
+    __syncthreads();
+  }
+  constexpr int U = 2;  // rows in flight per warp
+  const int stride = gridDim.x * wpb * U;
+  for (int s0 = (blockIdx.x * wpb + warp) * U; s0 < grid.Np; s0 += stride) {
+    float4 v[U][V];
+    int tk[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int slot = s0 + u;
+      int t = slot < grid.Np ? grid.slot_to_token(slot) : grid.L;
+      tk[u] = t < grid.L ? t : -1;
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        v[u][i] = tk[u] >= 0
+                      ? __ldg(reinterpret_cast<const float4*>(x1 + (size_t)tk[u] * D) + lane + 32 * i)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float red[U][1 + KMAX];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) sacc += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+      red[u][0] = sacc;
+#pragma unroll
+      for (int n = 0; n < KMAX; ++n) red[u][1 + n] = 0.f;
+    }
+    if (phi) {
+#pragma unroll
+      for (int n = 0; n < KMAX; ++n) {
+        if (n < k) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            float4 gq = *reinterpret_cast<const float4*>(Gt + n * D + 4 * (lane + 32 * i));
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              float d = red[u][1 + n];
+              d = fmaf(v[u][i].x, gq.x, d); d = fmaf(v[u][i].y, gq.y, d);
+              d = fmaf(v[u][i].z, gq.z, d); d = fmaf(v[u][i].w, gq.w, d);
+              red[u][1 + n] = d;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < 1 + KMAX; ++j) red[u][j] += __shfl_xor_sync(0xffffffffu, red[u][j], o);
+    float q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float mean = red[u][0] * (1.f / D);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float a = v[u][i].x - mean, b = v[u][i].y - mean, c = v[u][i].z - mean, d = v[u][i].w - mean;
+        acc += (a * a + b * b) + (c * c + d * d);
+      }
+      q[u] = acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int slot = s0 + u;
+      if (slot >= grid.Np) continue;
+      float mean = red[u][0] * (1.f / D);
+      float rstd = tk[u] >= 0 ? rsqrtf(q[u] * (1.f / D) + kLnEps) : 0.f;
+      if (lane == 0) stats[slot] = make_float2(tk[u] >= 0 ? mean : 0.f, rstd);
+      if (phi) {
+        float mine = 0.f;
+#pragma unroll
+        for (int n = 0; n < KMAX; ++n)
+          if (lane == n) mine = tk[u] >= 0 ? rstd * (red[u][1 + n] - mean * AB[n]) + AB[KMAX + n] : 0.f;
+        if (lane < k) logits[(size_t)slot * k + lane] = mine;
+      }
+    }
+  }
+}
+
+// grid (D/128, R), 256 threads.  smem: wq[P][KMAX] | tok[P] | part[8][KMAX][128] | s01[2][KMAX]
+template <int KMAX>
+__global__ void __launch_bounds__(256) crmsa_combine2_kernel(
+    const float* __restrict__ x1, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float2* __restrict__ stats, const float* __restrict__ logits, __half* __restrict__ landmarks,
+    float2* __restrict__ rstat, Grid grid, int D, int k) {
+  extern __shared__ __align__(16) float smem[];
+  const int P = grid.P, rho = blockIdx.y, chunk = blockIdx.x;
+  float* wq = smem;                                          // [P][KMAX]: logits -> cw*rstd
+  int* tok = reinterpret_cast<int*>(wq + (size_t)P * KMAX);  // [P]
+  float* part = reinterpret_cast<float*>(tok + ((P + 3) & ~3));  // [8][KMAX][128]
+  float* s01 = part + 8 * KMAX * 128;                        // [2][KMAX]: S0, S1
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int p = tid; p < P; p += 256) {
+    int slot = rho * P + p;
+    float2 st = __ldg(stats + slot);
+    tok[p] = st.y != 0.f ? grid.slot_to_token(slot) : -1;
+#pragma unroll
+    for (int n = 0; n < KMAX; ++n) wq[p * KMAX + n] = n < k ? __ldg(logits + (size_t)slot * k + n) : 0.f;
+  }
+  __syncthreads();
+  // per landmark: softmax over the region, min, max; then w' = cw * rstd, S0, S1
+  for (int n = warp; n < k; n += 8) {
+    float mx = -INFINITY, mn = INFINITY;
+    for (int p = lane; p < P; p += 32) {
+      float v = wq[p * KMAX + n];
+      mx = fmaxf(mx, v);
+      mn = fminf(mn, v);
+    }
+    mx = warp_max(mx);
+    mn = warp_min(mn);
+    float sum = 0.f;
+    for (int p = lane; p < P; p += 32) sum += __expf(wq[p * KMAX + n] - mx);
+    float inv = 1.f / warp_sum(sum);
+    float s0 = 0.f, s1 = 0.f;
+    for (int p = lane; p < P; p += 32) {
+      float cw = __expf(wq[p * KMAX + n] - mx) * inv;
+      float2 st = __ldg(stats + rho * P + p);
+      float w = cw * st.y;  // rstd = 0 for pad rows: they contribute nothing
+      wq[p * KMAX + n] = w;
+      if (st.y != 0.f) s0 += cw;
+      s1 = fmaf(w, st.x, s1);
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0) {
+      s01[n] = s0;
+      s01[KMAX + n] = s1;
+      if (chunk == 0) rstat[(size_t)rho * k + n] = make_float2(mn, mx);
+    }
+  }
+  __syncthreads();
+
+  const int c0 = chunk * 128 + lane * 4;
+  float4 acc[KMAX];
+#pragma unroll
+  for (int n = 0; n < KMAX; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int U = 6;  // rows in flight per warp
+  for (int p0 = warp; p0 < P; p0 += 8 * U) {
+    float4 xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int p = p0 + 8 * u;
+      int t = p < P ? tok[p] : -1;
+      xv[u] = t >= 0 ? __ldg(reinterpret_cast<const float4*>(x1 + (size_t)t * D + c0))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int p = p0 + 8 * u;
+      if (p >= P) break;
+      const float4 wv = *reinterpret_cast<const float4*>(wq + p * KMAX);  // KMAX = 4: one LDS.128
+#pragma unroll
+      for (int n = 0; n < KMAX; ++n) {
+        float wgt = KMAX == 4 ? (n == 0 ? wv.x : n == 1 ? wv.y : n == 2 ? wv.z : wv.w) : wq[p * KMAX + n];
+        acc[n].x = fmaf(wgt, xv[u].x, acc[n].x); acc[n].y = fmaf(wgt, xv[u].y, acc[n].y);
+        acc[n].z = fmaf(wgt, xv[u].z, acc[n].z); acc[n].w = fmaf(wgt, xv[u].w, acc[n].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < KMAX; ++n)
+    *reinterpret_cast<float4*>(part + ((size_t)(warp * KMAX + n)) * 128 + lane * 4) = acc[n];
+  __syncthreads();
+  for (int i = tid; i < k * 128; i += 256) {
+    int n = i >> 7, c = i & 127;
+    float sacc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sacc += part[((size_t)(w * KMAX + n)) * 128 + c];
+    int gc = chunk * 128 + c;
+    float val = __ldg(gamma + gc) * (sacc - s01[KMAX + n]) + __ldg(beta + gc) * s01[n];
+    landmarks[((size_t)n * grid.R + rho) * D + gc] = __float2half_rn(val);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Fused CR-MSA front end, one CTA per region (16 warps), two passes over the region's rows (which
 // are L2-resident: the projection GEMM has just written them):
 //   pass 1  warp per row, 3 rows in flight: LayerNorm statistics and the k logits from ONE batched
@@ -203,6 +422,16 @@ __global__ void __launch_bounds__(256) crmsa_combine_kernel(
 //   mid     warp per landmark: softmax over the P tokens, min / max  -> cw[p, n], rstat[rho, n]
 //   pass 2  warps tiled (row group x 128-column group): landmarks[n, :] += cw[p, n] * LN(x1)[p, :]
 // Replaces the separate stats/logits and combine kernels: one launch, every load batched.
+__device__ __forceinline__ void lstamp(int slot) {
+  if (g_attn_trace_dev && blockIdx.x < 64 && threadIdx.x == 0) {
+    long long t;
+    if (slot == 0 || slot == 5) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));   // ns, comparable across SMs
+      g_attn_trace_dev[blockIdx.x * 8 + (slot == 0 ? 6 : 7)] = t;
+    }
+    g_attn_trace_dev[blockIdx.x * 8 + slot] = clock64();
+  }
+}
 template <int V, int KMAX>
 __global__ void __launch_bounds__(512) crmsa_landmarks_kernel(
     const float* __restrict__ x1, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -224,6 +453,7 @@ __global__ void __launch_bounds__(512) crmsa_landmarks_kernel(
   float* part = AB + 2 * 16;                                                         // [RG][k][D]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  lstamp(0);
   for (int i = tid; i < D; i += 512) { gam[i] = __ldg(gamma + i); bet[i] = __ldg(beta + i); }
   for (int p = tid; p < P; p += 512) {
     int t = grid.slot_to_token(rho * P + p);
@@ -249,6 +479,7 @@ __global__ void __launch_bounds__(512) crmsa_landmarks_kernel(
     __syncthreads();
   }
 
+  lstamp(1);
   // ---- pass 1: statistics (+ logits) -----------------------------------------------------------
   constexpr int U1 = 3;  // rows in flight per warp
   for (int p0 = warp; p0 < P; p0 += NW * U1) {
@@ -345,6 +576,7 @@ __global__ void __launch_bounds__(512) crmsa_landmarks_kernel(
     }
   }
   __syncthreads();
+  lstamp(2);
 
   // ---- per landmark: softmax over the region's tokens, min, max --------------------------------
   for (int n = warp; n < k; n += NW) {
@@ -368,6 +600,7 @@ __global__ void __launch_bounds__(512) crmsa_landmarks_kernel(
   }
   __syncthreads();
 
+  lstamp(3);
   // ---- pass 2: landmarks = cw^T . LN(x1) ---------------------------------------------------------
   {
     const int cg = warp % CG, rg = warp / CG;
@@ -413,6 +646,7 @@ __global__ void __launch_bounds__(512) crmsa_landmarks_kernel(
       if (n < k) *reinterpret_cast<float4*>(part + ((size_t)(rg * k + n)) * D + c0) = acc[n];
   }
   __syncthreads();
+  lstamp(4);
   for (int i = tid; i < k * D; i += 512) {
     int n = i / D, c = i - n * D;
     float s = 0.f;
@@ -420,6 +654,7 @@ __global__ void __launch_bounds__(512) crmsa_landmarks_kernel(
     for (int r = 0; r < RG; ++r) s += part[((size_t)(r * k + n)) * D + c];
     landmarks[((size_t)n * grid.R + rho) * D + c] = __float2half_rn(s);
   }
+  lstamp(5);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -602,10 +837,12 @@ cudaError_t launch_crmsa_stats_logits(const float* x1, const float* gamma, const
   if (blocks > 148 * 4) blocks = 148 * 4;  // grid-stride over rows: phi is staged once per block
   size_t smem = phi ? (size_t)D * k * sizeof(float) : 0;
   RRT_DISPATCH_V(D, {
-    if (smem > 48 * 1024) {
+    static bool configured = false;  // per instantiation: the attribute call is slow (~25 us)
+    if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(crmsa_stats_logits_kernel<V>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return e;
+      configured = true;
     }
     crmsa_stats_logits_kernel<V><<<blocks, 256, smem, stream>>>(x1, gamma, beta, phi, stats, logits, grid, k);
   });
@@ -628,9 +865,13 @@ cudaError_t launch_crmsa_combine(const float* x1, const float* gamma, const floa
   dim3 g(D / 128, grid.R);
 #define RRT_COMBINE(KM)                                                                          \
   {                                                                                              \
-    cudaError_t e = cudaFuncSetAttribute(crmsa_combine_kernel<KM>,                               \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-    if (e != cudaSuccess) return e;                                                              \
+    static bool configured = false;                                                              \
+    if (!configured) {                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(crmsa_combine_kernel<KM>,                             \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      if (e != cudaSuccess) return e;                                                            \
+      configured = true;                                                                         \
+    }                                                                                            \
     crmsa_combine_kernel<KM><<<g, 256, smem, stream>>>(x1, gamma, beta, stats, logits, landmarks, \
                                                        rstat, grid, D, k);                       \
   }
@@ -658,13 +899,25 @@ cudaError_t launch_crmsa_landmarks(const float* x1, const float* gamma, const fl
                                    float2* rstat, const Grid& grid, int D, int k,
                                    cudaStream_t stream) {
   if (!crmsa_landmarks_supported(grid, D, k)) return cudaErrorInvalidValue;
+  {
+    static long long* last = nullptr;
+    if (last != g_attn_trace) {  // debug hook: mirror the host pointer into the device symbol
+      cudaMemcpyToSymbolAsync(g_attn_trace_dev, &g_attn_trace, sizeof(g_attn_trace), 0,
+                              cudaMemcpyHostToDevice, stream);
+      last = g_attn_trace;
+    }
+  }
   const int V = D / 128;
   size_t smem = landmarks_smem_bytes(grid, D, k);
 #define RRT_LM(VV, KM)                                                                           \
   {                                                                                              \
-    cudaError_t e = cudaFuncSetAttribute(crmsa_landmarks_kernel<VV, KM>,                         \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-    if (e != cudaSuccess) return e;                                                              \
+    static bool configured = false; /* per instantiation: the attribute call is slow (~25 us) */ \
+    if (!configured) {                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(crmsa_landmarks_kernel<VV, KM>,                       \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      if (e != cudaSuccess) return e;                                                            \
+      configured = true;                                                                         \
+    }                                                                                            \
     crmsa_landmarks_kernel<VV, KM><<<grid.R, 512, smem, stream>>>(x1, gamma, beta, phi, logits,  \
                                                                   landmarks, rstat, grid, k);    \
   }
@@ -678,6 +931,64 @@ cudaError_t launch_crmsa_landmarks(const float* x1, const float* gamma, const fl
   }
 #undef RRT_LM_K
 #undef RRT_LM
+  return cudaGetLastError();
+}
+
+// The split front end (default): row statistics / logits on all SMs, then the folded combine.
+cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const float* beta,
+                                     const float* phi, float2* stats, float* logits,
+                                     __half* landmarks, float2* rstat, const Grid& grid, int D, int k,
+                                     cudaStream_t stream) {
+  if (D % 128 || k < 1 || k > RRT_MAX_K_DEV) return cudaErrorInvalidValue;
+  const int V = D / 128;
+  if (V != 1 && V != 2 && V != 4 && V != 8) return cudaErrorNotSupported;
+  const int KM = k <= 4 ? 4 : (k <= 8 ? 8 : 16);
+  {
+    size_t smem = ((size_t)KM * D + 2 * KM) * sizeof(float);
+    int blocks = (grid.Np + 15) / 16;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+#define RRT_RS(VV, KK)                                                                            \
+  {                                                                                                \
+    static bool configured = false;                                                                \
+    if (!configured) {                                                                             \
+      cudaError_t e = cudaFuncSetAttribute(crmsa_rowstats_kernel<VV, KK>,                          \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+      if (e != cudaSuccess) return e;                                                              \
+      configured = true;                                                                           \
+    }                                                                                              \
+    crmsa_rowstats_kernel<VV, KK><<<blocks, 256, smem, stream>>>(x1, gamma, beta, phi, stats, logits, grid, k); \
+  }
+#define RRT_RS_K(VV) { if (KM == 4) RRT_RS(VV, 4) else if (KM == 8) RRT_RS(VV, 8) else RRT_RS(VV, 16) }
+    switch (V) {
+      case 1: RRT_RS_K(1) break;
+      case 2: RRT_RS_K(2) break;
+      case 4: RRT_RS_K(4) break;
+      default: RRT_RS_K(8) break;
+    }
+#undef RRT_RS_K
+#undef RRT_RS
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  {
+    size_t smem = ((size_t)grid.P * KM + ((grid.P + 3) & ~3) + (size_t)8 * KM * 128 + 2 * KM) * sizeof(float);
+    if (smem > 227 * 1024) return cudaErrorNotSupported;
+    dim3 g(D / 128, grid.R);
+#define RRT_C2(KK)                                                                                 \
+  {                                                                                                \
+    static bool configured = false;                                                                \
+    if (!configured) {                                                                             \
+      cudaError_t e = cudaFuncSetAttribute(crmsa_combine2_kernel<KK>,                              \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      if (e != cudaSuccess) return e;                                                              \
+      configured = true;                                                                           \
+    }                                                                                              \
+    crmsa_combine2_kernel<KK><<<g, 256, smem, stream>>>(x1, gamma, beta, stats, logits, landmarks, \
+                                                        rstat, grid, D, k);                        \
+  }
+    if (KM == 4) RRT_C2(4) else if (KM == 8) RRT_C2(8) else RRT_C2(16)
+#undef RRT_C2
+  }
   return cudaGetLastError();
 }
 

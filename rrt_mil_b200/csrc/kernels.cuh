@@ -89,6 +89,12 @@ cudaError_t launch_crmsa_landmarks(const float* x1, const float* gamma, const fl
                                    const float* phi, float* logits, __half* landmarks,
                                    float2* rstat, const Grid& grid, int D, int k,
                                    cudaStream_t stream);
+// Split front end (default): all-SM row statistics / logits kernel + folded combine kernel.
+// phi == null: `logits` already holds the crmsa_mlp logits (only the statistics are computed).
+cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const float* beta,
+                                     const float* phi, float2* stats, float* logits,
+                                     __half* landmarks, float2* rstat, const Grid& grid, int D, int k,
+                                     cudaStream_t stream);
 // MHA core over the landmarks: batch = k, sequence = R (64), heads, head_dim = D/heads, plain
 // softmax(q k^T * scale) v, fp32 math.  lqkv: [k*R, 3D] fp32 rows (n, rho); lo: [k*R, D] f16.
 cudaError_t launch_landmark_attention(const float* lqkv, __half* lo, int k, int R, int D, int heads,

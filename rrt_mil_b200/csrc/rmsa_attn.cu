@@ -179,9 +179,13 @@ cudaError_t launch(const __half* qkv, const float* taps, __half* o, const Grid& 
   int pad = taps ? epeg_k / 2 : 0;
   size_t smem = ((size_t)(2 * BKV + 16 * W + 2 * pad) * (HD + 4) + (taps ? epeg_k : 0)) * sizeof(float);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(rmsa_attn_kernel<HD>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e != cudaSuccess) return e;
+  static bool configured = false;  // per instantiation: the attribute call is slow
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(rmsa_attn_kernel<HD>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
   const float kLog2e = 1.4426950408889634f;
   float qscale = kLog2e / sqrtf((float)HD);
   dim3 g(chunks, heads, grid.R);

@@ -8,7 +8,7 @@ import gpu_util as G
 NAMES = ["start", "issued", "landed", "qprime", "core", "end"]
 m = RRTEncoder(need_init=True).cuda().eval()
 x = torch.randn(9000, 512, device="cuda")
-tr = torch.zeros(8, 8, dtype=torch.int64, device="cuda")
+tr = torch.zeros(64, 8, dtype=torch.int64, device="cuda")
 with torch.no_grad():
     G.rmsa_block(m, 0, x); G.rmsa_block(m, 0, x)
     torch.cuda.synchronize()
@@ -19,3 +19,24 @@ with torch.no_grad():
 for c in range(4):
     t = tr[c].tolist()
     print(f"cta{c}: " + " ".join(f"{n}={t[i]-t[0]}" for i, n in enumerate(NAMES)))
+
+# fused CR-MSA landmarks kernel (same debug buffer)
+NAMES2 = ["start", "setup", "pass1", "softmax", "pass2", "end"]
+x1 = torch.randn(9000, 512, device="cuda")
+tr.zero_()
+with torch.no_grad():
+    G.crmsa_block(m, x1, None, True)
+    torch.cuda.synchronize()
+    cabi.lib().rrt_debug_set_attn_trace(tr.data_ptr())
+    G.crmsa_block(m, x1, None, True)
+    torch.cuda.synchronize()
+    cabi.lib().rrt_debug_set_attn_trace(None)
+for c in range(3):
+    t = tr[c].tolist()
+    print(f"landmarks cta{c}: " + " ".join(f"{n}={t[i]-t[0]}" for i, n in enumerate(NAMES2)))
+
+g0 = tr[:, 6].cpu(); g1 = tr[:, 7].cpu()
+base = int(g0.min())
+print("landmarks globaltimer (ns): CTA start offsets", sorted((g0 - base).tolist())[:6], "...", sorted((g0 - base).tolist())[-4:])
+print("   CTA end offsets", sorted((g1 - base).tolist())[:4], "...", sorted((g1 - base).tolist())[-4:])
+print("   per-CTA durations ns: min %d max %d" % (int((g1 - g0).min()), int((g1 - g0).max())))
