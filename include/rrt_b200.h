@@ -167,6 +167,10 @@ RRT_API int rrt_debug_set_gemm_trace(void* device_buffer);
 /* Debug: same for the region-resident attention kernel: device_buffer[8][8] (int64). */
 RRT_API int rrt_debug_set_attn_trace(void* device_buffer);
 
+/* Debug / tuning: R-MSA attention core: 1 = tcgen05 kernel (head_dim 64, regions <= 256 tokens),
+ * 0 = mma.sync kernel.  Results agree within the parity tolerance. */
+RRT_API int rrt_debug_set_attention_kernel(int32_t use_tcgen05);
+
 /* Debug / tuning: kernel variant of the bag-sized tcgen05 GEMMs.  11 = single-CTA 128x256 tiles
  * (default, fastest at these sizes); 2 = CTA pairs (cta_group::2, M=256 tiles); 21 / 22 = single-CTA
  * tiles with 2x1 / 2x2 cluster TMA multicast.  Results do not depend on it. */

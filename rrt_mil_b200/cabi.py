@@ -78,6 +78,7 @@ SIGNATURES = {
     "rrt_stage_timing_read": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "rrt_debug_set_gemm_trace": (C.c_int, [_P]),
     "rrt_debug_set_attn_trace": (C.c_int, [_P]),
+    "rrt_debug_set_attention_kernel": (C.c_int, [C.c_int32]),
     "rrt_debug_set_gemm_cluster": (C.c_int, [C.c_int32]),
     "rrt_convert_f16": (C.c_int, [_P, _P, C.c_int64, _P]),
     "rrt_linear_f16_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
@@ -110,6 +111,8 @@ def lib() -> C.CDLL:
                 fn.restype, fn.argtypes = res, args
             if handle.rrt_abi_version() != RRT_ABI_VERSION:
                 raise RuntimeError("librrt_b200.so ABI version mismatch: rebuild it")
+            if os.environ.get("RRT_ATTN"):  # tuning knob: tc05 | mma
+                handle.rrt_debug_set_attention_kernel(int(os.environ["RRT_ATTN"] == "tc05"))
             if os.environ.get("RRT_GEMM_CLUSTER"):  # tuning knob: 22 (default), 21, 11
                 handle.rrt_debug_set_gemm_cluster(int(os.environ["RRT_GEMM_CLUSTER"]))
             _lib = handle

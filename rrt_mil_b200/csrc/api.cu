@@ -259,7 +259,10 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
     RRT_CUDA(rrt::launch_gemm_tcgen05(ws.z, wq, ws.qkv, true, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
   { StageScope s_(kStRmsaAttn, st);
     const float* taps = c->epeg ? a->pe_w : nullptr;
-    if (rrt::rmsa_attention_f16_supported(g, D, c->n_heads))
+    if (rrt::g_attn_tc05 && rrt::rmsa_attention_tc05_supported(g, D, c->n_heads))
+      RRT_CUDA(rrt::launch_rmsa_attention_tc05(ws.qkv, taps, ws.o, g, D, c->n_heads, c->epeg_k, st),
+               "rmsa attention (tcgen05)");
+    else if (rrt::rmsa_attention_f16_supported(g, D, c->n_heads))
       RRT_CUDA(rrt::launch_rmsa_attention_f16(ws.qkv, taps, ws.o, g, D, c->n_heads, c->epeg_k, st),
                "rmsa attention (region-resident)");
     else
@@ -580,6 +583,11 @@ RRT_API int rrt_debug_set_gemm_trace(void* device_buffer) {
 
 RRT_API int rrt_debug_set_attn_trace(void* device_buffer) {
   rrt::g_attn_trace = static_cast<long long*>(device_buffer);
+  return RRT_OK;
+}
+
+RRT_API int rrt_debug_set_attention_kernel(int32_t use_tcgen05) {
+  rrt::g_attn_tc05 = use_tcgen05 ? 1 : 0;
   return RRT_OK;
 }
 

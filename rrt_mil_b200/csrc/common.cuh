@@ -7,6 +7,20 @@
 
 namespace rrt {
 
+// One-time per-device kernel configuration (cudaFuncSetAttribute is slow, ~25 us, and function
+// attributes are per device): `flags` is a static array owned by the call site.
+struct DeviceOnce {
+  bool done[32] = {};
+  bool needed() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 31;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default (modules/rrt.py:47,139)
 #define RRT_MAX_K_DEV 16  // == RRT_MAX_CRMSA_K in include/rrt_b200.h
 
@@ -81,6 +95,14 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
 __device__ __forceinline__ float4 unpack_h4(uint2 u) {
   float2 a = unpack_h2(u.x), b = unpack_h2(u.y);
   return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// 2^x on the SFU in one instruction (exp2f() wraps MUFU.EX2 in three range fix-up instructions);
+// softmax arguments are <= 0 and results below 2^-126 may flush to zero
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // D(16x8,f32) += A(16x8,tf32,row) * B(8x8,tf32,col)

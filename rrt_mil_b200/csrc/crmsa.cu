@@ -837,12 +837,11 @@ cudaError_t launch_crmsa_stats_logits(const float* x1, const float* gamma, const
   if (blocks > 148 * 4) blocks = 148 * 4;  // grid-stride over rows: phi is staged once per block
   size_t smem = phi ? (size_t)D * k * sizeof(float) : 0;
   RRT_DISPATCH_V(D, {
-    static bool configured = false;  // per instantiation: the attribute call is slow (~25 us)
-    if (!configured) {
+    static DeviceOnce configured;  // per instantiation: the attribute call is slow (~25 us)
+    if (configured.needed()) {
       cudaError_t e = cudaFuncSetAttribute(crmsa_stats_logits_kernel<V>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return e;
-      configured = true;
     }
     crmsa_stats_logits_kernel<V><<<blocks, 256, smem, stream>>>(x1, gamma, beta, phi, stats, logits, grid, k);
   });
@@ -865,12 +864,11 @@ cudaError_t launch_crmsa_combine(const float* x1, const float* gamma, const floa
   dim3 g(D / 128, grid.R);
 #define RRT_COMBINE(KM)                                                                          \
   {                                                                                              \
-    static bool configured = false;                                                              \
-    if (!configured) {                                                                           \
+    static DeviceOnce configured;                                                              \
+    if (configured.needed()) {                                                                           \
       cudaError_t e = cudaFuncSetAttribute(crmsa_combine_kernel<KM>,                             \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
       if (e != cudaSuccess) return e;                                                            \
-      configured = true;                                                                         \
     }                                                                                            \
     crmsa_combine_kernel<KM><<<g, 256, smem, stream>>>(x1, gamma, beta, stats, logits, landmarks, \
                                                        rstat, grid, D, k);                       \
@@ -911,12 +909,11 @@ cudaError_t launch_crmsa_landmarks(const float* x1, const float* gamma, const fl
   size_t smem = landmarks_smem_bytes(grid, D, k);
 #define RRT_LM(VV, KM)                                                                           \
   {                                                                                              \
-    static bool configured = false; /* per instantiation: the attribute call is slow (~25 us) */ \
-    if (!configured) {                                                                           \
+    static DeviceOnce configured; /* per instantiation: the attribute call is slow (~25 us) */ \
+    if (configured.needed()) {                                                                           \
       cudaError_t e = cudaFuncSetAttribute(crmsa_landmarks_kernel<VV, KM>,                       \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
       if (e != cudaSuccess) return e;                                                            \
-      configured = true;                                                                         \
     }                                                                                            \
     crmsa_landmarks_kernel<VV, KM><<<grid.R, 512, smem, stream>>>(x1, gamma, beta, phi, logits,  \
                                                                   landmarks, rstat, grid, k);    \
@@ -949,12 +946,11 @@ cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const 
     if (blocks > 148 * 4) blocks = 148 * 4;
 #define RRT_RS(VV, KK)                                                                            \
   {                                                                                                \
-    static bool configured = false;                                                                \
-    if (!configured) {                                                                             \
+    static DeviceOnce configured;                                                                \
+    if (configured.needed()) {                                                                             \
       cudaError_t e = cudaFuncSetAttribute(crmsa_rowstats_kernel<VV, KK>,                          \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
       if (e != cudaSuccess) return e;                                                              \
-      configured = true;                                                                           \
     }                                                                                              \
     crmsa_rowstats_kernel<VV, KK><<<blocks, 256, smem, stream>>>(x1, gamma, beta, phi, stats, logits, grid, k); \
   }
@@ -976,12 +972,11 @@ cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const 
     dim3 g(D / 128, grid.R);
 #define RRT_C2(KK)                                                                                 \
   {                                                                                                \
-    static bool configured = false;                                                                \
-    if (!configured) {                                                                             \
+    static DeviceOnce configured;                                                                \
+    if (configured.needed()) {                                                                             \
       cudaError_t e = cudaFuncSetAttribute(crmsa_combine2_kernel<KK>,                              \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
       if (e != cudaSuccess) return e;                                                              \
-      configured = true;                                                                           \
     }                                                                                              \
     crmsa_combine2_kernel<KK><<<g, 256, smem, stream>>>(x1, gamma, beta, stats, logits, landmarks, \
                                                         rstat, grid, D, k);                        \

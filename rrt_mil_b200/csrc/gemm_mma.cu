@@ -116,12 +116,11 @@ template <int BM>
 cudaError_t launch(const float* a, const float* w, float* c, int M, int N, int K,
                    const GemmEpilogue& epi, cudaStream_t stream) {
   size_t smem = (size_t)STAGES * (BM + BN) * LDS * sizeof(float);
-  static bool configured = false;  // per template instance
-  if (!configured) {
+  static DeviceOnce configured;  // per template instance
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_mma_kernel<BM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   gemm_tf32_mma_kernel<BM><<<grid, NTHREADS, smem, stream>>>(a, w, c, M, N, K, epi);

@@ -606,12 +606,11 @@ cudaError_t launch_cfg(const __half* a, const __half* w, const Tc05Params& p, cu
     tmC = tmA;  // unused by the st.global epilogues
   }
   auto kern = gemm_f16_tcgen05_kernel<MODE, BN, OutT, CM, CN>;
-  static bool configured = false;  // per instantiation; one process drives one GPU
-  if (!configured) {
+  static DeviceOnce configured;  // per instantiation; one process drives one GPU
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int ctiles = (((p.M + BM - 1) / BM + CM - 1) / CM) * (((p.N + BN - 1) / BN + CN - 1) / CN);
   int clusters = sm_count() / CSIZE;
@@ -651,11 +650,10 @@ cudaError_t launch_pair(const __half* a, const __half* w, const Tc05Params& p, c
     tmC = tmA;
   }
   auto kern = gemm_f16_tcgen05_2cta_kernel<MODE, OutT>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int ptiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + P2_BN - 1) / P2_BN);
   int pairs = sm_count() / 2;

@@ -65,6 +65,12 @@ cudaError_t launch_rmsa_attention_f16(const __half* qkv, const float* taps, __ha
                                       cudaStream_t stream);
 cudaError_t launch_rmsa_attention(const __half* qkv, const float* taps, __half* o, const Grid& grid,
                                   int D, int heads, int epeg_k, cudaStream_t stream);
+// ---- rmsa_attn_tc05.cu: same contract, S and O products on tcgen05 (head_dim 64, P <= 256) ----
+extern int g_attn_tc05;  // 1: use it when supported (rrt_debug_set_attention_kernel / RRT_ATTN=tc05)
+bool rmsa_attention_tc05_supported(const Grid& grid, int D, int heads);
+cudaError_t launch_rmsa_attention_tc05(const __half* qkv, const float* taps, __half* o,
+                                       const Grid& grid, int D, int heads, int epeg_k,
+                                       cudaStream_t stream);
 
 // ---- crmsa.cu -------------------------------------------------------------------------
 // Per padded slot of the CR-MSA grid: LayerNorm statistics of x1 (mean, rstd; rstd = 0 marks a pad

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) rmsa_attn_kernel(const __half* __restrict
       mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
       mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
     }
-    float corr[2] = {exp2f(m_run[0] - mx[0]), exp2f(m_run[1] - mx[1])};
+    float corr[2] = {fast_exp2(m_run[0] - mx[0]), fast_exp2(m_run[1] - mx[1])};
     m_run[0] = mx[0];
     m_run[1] = mx[1];
     l_run[0] *= corr[0];
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) rmsa_attn_kernel(const __half* __restrict
     for (int nt = 0; nt < BKV / 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float pv = exp2f(s[nt][e] - mx[e >> 1]);
+        float pv = fast_exp2(s[nt][e] - mx[e >> 1]);
         l_run[e >> 1] += pv;
         s[nt][e] = pv;
       }
@@ -179,12 +179,11 @@ cudaError_t launch(const __half* qkv, const float* taps, __half* o, const Grid& 
   int pad = taps ? epeg_k / 2 : 0;
   size_t smem = ((size_t)(2 * BKV + 16 * W + 2 * pad) * (HD + 4) + (taps ? epeg_k : 0)) * sizeof(float);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static bool configured = false;  // per instantiation: the attribute call is slow
-  if (!configured) {
+  static DeviceOnce configured;  // per instantiation: the attribute call is slow
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(rmsa_attn_kernel<HD>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const float kLog2e = 1.4426950408889634f;
   float qscale = kLog2e / sqrtf((float)HD);

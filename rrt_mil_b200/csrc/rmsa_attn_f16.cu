@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
       mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
       mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
     }
-    const float corr[2] = {exp2f(m_run[0] - mx[0]), exp2f(m_run[1] - mx[1])};
+    const float corr[2] = {fast_exp2(m_run[0] - mx[0]), fast_exp2(m_run[1] - mx[1])};
     m_run[0] = mx[0];
     m_run[1] = mx[1];
     l_run[0] *= corr[0];
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float pv = exp2f(s[nt][e] - mx[e >> 1]);
+        float pv = fast_exp2(s[nt][e] - mx[e >> 1]);
         l_run[e >> 1] += pv;
         s[nt][e] = pv;
       }
@@ -256,15 +256,14 @@ cudaError_t launch(const __half* qkv, const float* taps, __half* o, const Grid& 
   size_t smem = ((size_t)q_rows + 2 * (size_t)tiles * KV) * (HD + 8) * sizeof(__half) +
                 (taps ? epeg_k : 0) * sizeof(float) + 16;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(rmsa_attn_f16_kernel<HD, NT, MAXW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(rmsa_attn_f16_kernel<HD, NT, MAXW>,
                                cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const float kLog2e = 1.4426950408889634f;
   float qscale = kLog2e / sqrtf((float)HD);

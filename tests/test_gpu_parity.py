@@ -203,6 +203,30 @@ def test_concurrent_lanes_equal_serial_per_bag_forward():
                 assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("knob,value,restore", [
+    ("rrt_debug_set_attention_kernel", 1, 0),   # tcgen05 attention core (S, O on tcgen05.mma, TMEM softmax)
+    ("rrt_debug_set_gemm_cluster", 2, 11),      # cta_group::2 GEMM (CTA pairs, M=256 tiles)
+    ("rrt_debug_set_gemm_cluster", 21, 11),     # 2x1 cluster, TMA multicast of the W tile
+    ("rrt_debug_set_gemm_cluster", 22, 11),     # 2x2 cluster, multicast of both operand tiles
+])
+def test_alternative_kernel_variants_keep_parity(knob, value, restore):
+    """The selectable kernel variants (kept for tuning) must meet the same parity bar
+    as the default kernels on golden cases with one and with two 128-row attention blocks."""
+    from rrt_mil_b200 import cabi
+    lib = cabi.lib()
+    getattr(lib, knob)(value)
+    try:
+        for name in ("c2_n9000_d512", "plip_k9_shortcut", "c4_n50000_g16"):
+            cfg, w, x, gold = load_case(name)
+            m = G.make_encoder(cfg, w)
+            with torch.no_grad():
+                y = m(x.float().cuda())
+            torch.cuda.synchronize()
+            assert_matches_golden(y, gold, TOL_TF32, f"{knob}={value} {name}")
+    finally:
+        getattr(lib, knob)(restore)
+
+
 def test_tiny_bag_crmsa_contributes_nothing():
     """N < 64: every token is its own region, min-max normalised dispatch weight is 0/(0+1e-8)=0
      -> the CR-MSA block is the identity on x1."""
