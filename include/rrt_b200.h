@@ -189,6 +189,32 @@ RRT_API int rrt_linear_f16_forward(const void* a_f16, const void* w_f16, const f
 RRT_API int rrt_linear_forward(const float* a, const float* w, const float* bias, float* c,
                                int64_t M, int32_t N, int32_t K, void* stream);
 
+/* ---- SURVEY.md 8(f) "next" rows f1 / f2: the layers RRTMIL wraps around the encoder ------------ */
+/* activation codes of the two entries below */
+enum { RRT_ACT_NONE = 0, RRT_ACT_RELU = 1, RRT_ACT_GELU = 2, RRT_ACT_TANH = 3 };
+
+/* Device workspace (bytes) of rrt_patch_embed_forward / rrt_attn_pool_forward. */
+RRT_API int rrt_mil_head_workspace_bytes(int64_t L, int32_t in_dim, int32_t dim, int32_t hid,
+                                         size_t* bytes);
+
+/* patch_to_emb: out[L, out_dim] = act(x[L, in_dim] @ w[out_dim, in_dim]^T + b)   (modules/rrt.py:208-217,
+ * 228).  w_f16 = optional fp16 shadow of w (rrt_convert_f16) or NULL.  in_dim % 64 == 0. */
+RRT_API int rrt_patch_embed_forward(const float* x, int64_t L, int32_t in_dim, int32_t out_dim,
+                                    const float* w, const float* b, const void* w_f16, int32_t act,
+                                    float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* DAttention pooling + predictor (modules/datten.py:5-38,85-101, modules/rrt.py:221-241):
+ *   A = act(h @ w1^T + b1) @ w2^T + b2  [L];  a = softmax_L(A);  pooled[dim] = a @ h;
+ *   logits[n_classes] = pooled @ pred_w^T + pred_b   (pred_w may be NULL: pooling only).
+ * attn (optional, [L]) receives a, or the raw scores A when attn_raw != 0 (the reference's no_norm).
+ * b1 / b2 / pred_b / w1_f16 may be NULL. */
+RRT_API int rrt_attn_pool_forward(const float* h, int64_t L, int32_t dim, int32_t hid,
+                                  const float* w1, const float* b1, const void* w1_f16, int32_t act,
+                                  const float* w2, const float* b2, const float* pred_w,
+                                  const float* pred_b, int32_t n_classes, float* pooled,
+                                  float* logits, float* attn, int32_t attn_raw, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------- */
 /* Kernel launches issued by this library in this process so far. */
 RRT_API int64_t rrt_launch_count(void);

@@ -60,6 +60,13 @@ CASES = [
     ("d128_h2_k3", 400, dict(mlp_dim=128, n_heads=2, crmsa_heads=2, epeg_k=3), 7, "randn"),
 ]
 
+# RRTMIL end-to-end: name, L, input_dim, n_classes, act, da_act, da_bias, encoder overrides
+MIL_CASES = [
+    ("mil_r50_n3000", 3000, 1024, 2, "relu", "relu", False, dict()),
+    ("mil_plip_n1200_gelu_bias", 1200, 512, 4, "gelu", "tanh", True, dict(epeg_k=9, all_shortcut=True)),
+    ("mil_n9000_k21", 9000, 1024, 2, "relu", "relu", False, dict(epeg_k=21, crmsa_k=5)),
+]
+
 MAX_ROWS = 96
 WEIGHT_SEED = 2021  # the reference's default --seed (main.py:645)
 MIN_LOGIT_RANGE = 1e-2  # see crmsa_conditioning
@@ -114,6 +121,24 @@ def generate(name, L, overrides, bag_seed, kind):
                 weight_seed=WEIGHT_SEED, bag_seed=bag_seed, min_crmsa_logit_range=cond)
 
 
+def generate_mil(name, L, input_dim, n_classes, act, da_act, da_bias, overrides):
+    cfg = O.EncoderConfig(**overrides)
+    w = O.make_mil_weights(cfg, input_dim, n_classes, WEIGHT_SEED, da_bias=da_bias)
+    x = O.make_bag(L, input_dim, 7, kind="randn")
+    ref = shim.import_reference_rrt()
+    m = ref.RRTMIL(input_dim=input_dim, n_classes=n_classes, act=act, da_act=da_act, da_bias=da_bias,
+                   region_num=cfg.region_num, n_layers=cfg.n_layers, epeg_k=cfg.epeg_k,
+                   crmsa_k=cfg.crmsa_k, all_shortcut=cfg.all_shortcut, crmsa_heads=cfg.crmsa_heads,
+                   crmsa_mlp=cfg.crmsa_mlp).double().eval()
+    m.load_state_dict(w, strict=True)
+    with torch.no_grad():
+        logits, attn = m(x.unsqueeze(0), return_attn=True)
+    np.savez(os.path.join(GOLDEN_DIR, name + ".npz"), logits=logits[0].numpy(),
+             attn=attn[0].numpy().astype(np.float32))
+    return dict(name=name, L=L, input_dim=input_dim, n_classes=n_classes, act=act, da_act=da_act,
+                da_bias=da_bias, config=cfg.to_dict(), weight_seed=WEIGHT_SEED, bag_seed=7)
+
+
 def main():
     if not shim.available():
         sys.exit("reference tree not present; goldens can only be generated in the build container")
@@ -127,8 +152,12 @@ def main():
     sub = os.path.join(shim.REFERENCE_ROOT, ".SUBMODULES.json")
     if os.path.isfile(sub):
         ref_commit = json.load(open(sub)).get("commit")
+    mil = []
+    for case in MIL_CASES:
+        mil.append(generate_mil(*case))
+        print("golden", case[0], flush=True)
     json.dump(dict(reference_commit=ref_commit, torch=torch.__version__, numpy=np.__version__,
-                   cases=manifest),
+                   cases=manifest, mil_cases=mil),
               open(os.path.join(GOLDEN_DIR, "manifest.json"), "w"), indent=1)
 
 

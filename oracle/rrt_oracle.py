@@ -230,6 +230,52 @@ def encoder_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderCon
 
 
 # ----------------------------------------------------------------------------------------
+# RRTMIL = patch_to_emb -> encoder -> DAttention pooling -> predictor
+# ----------------------------------------------------------------------------------------
+def _act(name):
+    return {"relu": torch.relu, "gelu": F.gelu, "tanh": torch.tanh}.get(name, lambda t: t)
+
+
+def mil_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfig, act: str = "relu",
+                da_act: str = "relu", order: str = "reference"):
+    """``RRTMIL.forward`` (eval) for one bag ``x`` [L, input_dim] -> (logits [C], attention [L])
+    (modules/rrt.py:227-246, modules/datten.py:28-38,94-101).  Encoder weights carry the reference's
+    ``online_encoder.`` prefix."""
+    h = _act(act)(F.linear(x, w["patch_to_emb.0.weight"], w["patch_to_emb.0.bias"]))
+    enc = {k[len("online_encoder."):]: v for k, v in w.items() if k.startswith("online_encoder.")}
+    h = encoder_forward(h, enc, cfg, order)
+    keys = sorted(k for k in w if k.startswith("pool_fn.attention.attention.") and k.endswith("weight"))
+    k0, k1 = keys[0], keys[-1]
+    a = _act(da_act)(F.linear(h, w[k0], w.get(k0[:-6] + "bias")))
+    a = F.linear(a, w[k1], w.get(k1[:-6] + "bias")).squeeze(-1)  # [L]
+    attn = torch.softmax(a, 0)
+    pooled = attn @ h
+    logits = F.linear(pooled, w["predictor.weight"], w["predictor.bias"])
+    return logits, attn
+
+
+def make_mil_weights(cfg: EncoderConfig, input_dim: int, n_classes: int, seed: int, da_bias: bool = False,
+                     dtype=torch.float64) -> Dict[str, torch.Tensor]:
+    enc = make_weights(cfg, seed, dtype)
+    rs = np.random.RandomState(seed + 1)
+
+    def lin(o, i):
+        return torch.from_numpy(rs.standard_normal((o, i)) * math.sqrt(2.0 / (o + i))).to(dtype)
+
+    def vec(n):
+        return torch.from_numpy(0.1 * rs.standard_normal(n)).to(dtype)
+
+    w = {"online_encoder." + k: v for k, v in enc.items()}
+    w["patch_to_emb.0.weight"], w["patch_to_emb.0.bias"] = lin(512, input_dim), vec(512)
+    w["pool_fn.attention.attention.0.weight"] = lin(128, cfg.mlp_dim)
+    w["pool_fn.attention.attention.2.weight"] = lin(1, 128)
+    if da_bias:
+        w["pool_fn.attention.attention.0.bias"], w["pool_fn.attention.attention.2.bias"] = vec(128), vec(1)
+    w["predictor.weight"], w["predictor.bias"] = lin(n_classes, cfg.mlp_dim), vec(n_classes)
+    return w
+
+
+# ----------------------------------------------------------------------------------------
 # seeded synthetic weights / inputs (platform-stable: numpy legacy RandomState streams)
 # ----------------------------------------------------------------------------------------
 def weight_shapes(cfg: EncoderConfig) -> Dict[str, Tuple[int, ...]]:

@@ -5,6 +5,7 @@
 through the C ABI in ``include/rrt_b200.h`` (``librrt_b200.so``).  There is no CPU / eager fallback.
 """
 from .encoder import RRTEncoder, initialize_weights  # noqa: F401
+from .mil import RRTMIL, DAttention  # noqa: F401
 from . import cabi  # noqa: F401
 
-__all__ = ["RRTEncoder", "initialize_weights", "cabi"]
+__all__ = ["RRTEncoder", "RRTMIL", "DAttention", "initialize_weights", "cabi"]

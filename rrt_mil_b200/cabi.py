@@ -19,6 +19,7 @@ RRT_MAX_EPEG_K = 63
 RRT_MAX_LANES = 8
 RRT_OK, RRT_E_INVALID, RRT_E_WORKSPACE, RRT_E_CUDA = 0, -1, -2, -3
 RRT_MATH_F16 = 0
+RRT_ACT_NONE, RRT_ACT_RELU, RRT_ACT_GELU, RRT_ACT_TANH = 0, 1, 2, 3
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 
@@ -71,6 +72,11 @@ SIGNATURES = {
                                          _P, _P, C.c_int64, _P, C.c_size_t, _P]),
     "rrt_crmsa_block_forward": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P, _P,
                                           C.c_int64, C.c_int32, _P, C.c_size_t, _P]),
+    "rrt_mil_head_workspace_bytes": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "rrt_patch_embed_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P,
+                                          C.c_size_t, _P]),
+    "rrt_attn_pool_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P,
+                                        C.c_int32, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),
     "rrt_launch_count": (C.c_int64, []),
     "rrt_stage_timing_enable": (C.c_int, [C.c_int32]),
     "rrt_stage_count": (C.c_int32, []),

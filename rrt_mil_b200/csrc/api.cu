@@ -542,6 +542,99 @@ RRT_API int rrt_crmsa_block_forward(const rrt_config* cfg, const rrt_weights* w,
                      ws, (cudaStream_t)stream);
 }
 
+namespace {
+size_t head_ws_bytes(int64_t L, int in_dim, int dim, int hid) {
+  size_t a = align_up((size_t)L * (in_dim > dim ? in_dim : dim) * 2);      // f16 copy of the GEMM input
+  size_t b = align_up((size_t)(in_dim > dim ? in_dim : dim) * (dim > hid ? dim : hid) * 2);  // f16 weight
+  size_t c = align_up(rrt::attn_pool_scratch_floats((int)L, dim, hid) * 4);
+  return a + b + c + 256;
+}
+int act_code(int32_t act, int* out) {
+  switch (act) {
+    case RRT_ACT_NONE: *out = rrt::kActNone; return RRT_OK;
+    case RRT_ACT_RELU: *out = rrt::kActRelu; return RRT_OK;
+    case RRT_ACT_GELU: *out = rrt::kActGelu; return RRT_OK;
+    case RRT_ACT_TANH: *out = rrt::kActTanh; return RRT_OK;
+    default: return fail(RRT_E_INVALID, "unknown activation");
+  }
+}
+}  // namespace
+
+RRT_API int rrt_mil_head_workspace_bytes(int64_t L, int32_t in_dim, int32_t dim, int32_t hid,
+                                         size_t* bytes) {
+  if (!bytes || L < 1 || L > (1 << 28) || in_dim < 1 || dim < 1 || hid < 1)
+    return fail(RRT_E_INVALID, "bad argument");
+  *bytes = head_ws_bytes(L, in_dim, dim, hid);
+  return RRT_OK;
+}
+
+RRT_API int rrt_patch_embed_forward(const float* x, int64_t L, int32_t in_dim, int32_t out_dim,
+                                    const float* w, const float* b, const void* w_f16, int32_t act,
+                                    float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !w || !out || L < 1 || L > (1 << 28)) return fail(RRT_E_INVALID, "bad argument");
+  if (in_dim % 64 || out_dim % 4 || !rrt::gemm_tcgen05_supported((int)L, out_dim, in_dim))
+    return fail(RRT_E_INVALID, "patch_embed: in_dim must be a multiple of 64, out_dim of 4");
+  int a;
+  int rc = act_code(act, &a);
+  if (rc) return rc;
+  if (!workspace || (((uintptr_t)workspace) & 255) || workspace_bytes < head_ws_bytes(L, in_dim, out_dim, 1))
+    return fail(RRT_E_WORKSPACE, "workspace too small or misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  __half* x16 = (__half*)workspace;
+  __half* w16s = (__half*)((char*)workspace + align_up((size_t)L * (in_dim > out_dim ? in_dim : out_dim) * 2));
+  StageScope s_(kStOther, st, 2 + (w_f16 ? 0 : 1));
+  RRT_CUDA(rrt::launch_convert_f16(x, x16, (size_t)L * in_dim, st), "patch_embed: convert input");
+  const __half* w16 = (const __half*)w_f16;
+  if (!w16) {
+    RRT_CUDA(rrt::launch_convert_f16(w, w16s, (size_t)out_dim * in_dim, st), "patch_embed: convert weight");
+    w16 = w16s;
+  }
+  rrt::GemmEpilogue e;
+  e.bias = b;
+  e.act = a;
+  RRT_CUDA(rrt::launch_gemm_tcgen05(x16, w16, out, false, (int)L, out_dim, in_dim, e, st), "patch_embed gemm");
+  return RRT_OK;
+}
+
+RRT_API int rrt_attn_pool_forward(const float* h, int64_t L, int32_t dim, int32_t hid,
+                                  const float* w1, const float* b1, const void* w1_f16, int32_t act,
+                                  const float* w2, const float* b2, const float* pred_w,
+                                  const float* pred_b, int32_t n_classes, float* pooled,
+                                  float* logits, float* attn, int32_t attn_raw, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  if (!h || !w1 || !w2 || !pooled || L < 1 || L > (1 << 28)) return fail(RRT_E_INVALID, "bad argument");
+  if (pred_w && (!logits || n_classes < 1)) return fail(RRT_E_INVALID, "logits buffer missing");
+  if (dim % 64 || hid % 4 || !rrt::gemm_tcgen05_supported((int)L, hid, dim))
+    return fail(RRT_E_INVALID, "attn_pool: dim must be a multiple of 64, hid of 4");
+  int a;
+  int rc = act_code(act, &a);
+  if (rc) return rc;
+  if (!workspace || (((uintptr_t)workspace) & 255) || workspace_bytes < head_ws_bytes(L, dim, dim, hid))
+    return fail(RRT_E_WORKSPACE, "workspace too small or misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* p = (char*)workspace;
+  __half* h16 = (__half*)p;
+  p += align_up((size_t)L * dim * 2);
+  __half* w16s = (__half*)p;
+  p += align_up((size_t)dim * (dim > hid ? dim : hid) * 2);
+  float* hidden = (float*)p;
+  float* scratch = hidden + (size_t)L * hid;
+  StageScope s_(kStOther, st, 5 + (w1_f16 ? 0 : 1) + (attn ? 1 : 0));
+  RRT_CUDA(rrt::launch_convert_f16(h, h16, (size_t)L * dim, st), "attn_pool: convert input");
+  const __half* w16 = (const __half*)w1_f16;
+  if (!w16) {
+    RRT_CUDA(rrt::launch_convert_f16(w1, w16s, (size_t)hid * dim, st), "attn_pool: convert weight");
+    w16 = w16s;
+  }
+  rrt::GemmEpilogue e;
+  e.bias = b1;
+  e.act = a;
+  RRT_CUDA(rrt::launch_gemm_tcgen05(h16, w16, hidden, false, (int)L, hid, dim, e, st), "attn_pool gemm");
+  RRT_CUDA(rrt::launch_attn_pool(h, hidden, w2, b2, pred_w, pred_b, pred_w ? n_classes : 0, scratch, pooled,
+                                 logits, attn, attn_raw, (int)L, dim, hid, st), "attn_pool");
+  return RRT_OK;
+}
+
 RRT_API int64_t rrt_launch_count(void) { return g_launches.load(); }
 
 RRT_API int rrt_stage_timing_enable(int32_t on) {

@@ -49,8 +49,19 @@ struct Tc05Params {
   void* C;  // OutT[M or L, N]
   const float* resid;
   Grid grid;
+  int act;           // GemmActivation, store mode only
   long long* trace;  // debug: per-CTA clock64 stamps (tools/gemm_trace.py), null in production
 };
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case kActRelu: return fmaxf(v, 0.f);
+    case kActGelu: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));  // nn.GELU() (erf form)
+    case kActTanh: return tanhf(v);
+    case kActSigmoid: return 1.f / (1.f + __expf(-v));
+    default: return v;
+  }
+}
 
 // trace slots: 0 start, 1 setup done, 2 first TMA issued, 3 last TMA issued, 4 first operands landed,
 // 5 last MMA committed, 6 first accumulator ready (epilogue), 7 epilogue of first tile done,
@@ -164,8 +175,10 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
           constexpr int EPC = 16 / (int)sizeof(OutT);      // elements per 16-byte chunk
           float f[EPC];
 #pragma unroll
-          for (int e = 0; e < EPC; ++e)
+          for (int e = 0; e < EPC; ++e) {
             f[e] = __uint_as_float(rr[q * EPC + e]) + __shfl_sync(0xffffffffu, bias_l[j], q * EPC + e);
+            if (p.act != kActNone) f[e] = apply_act(f[e], p.act);
+          }
           uint4 pk;
           if (sizeof(OutT) == 2) {
             pk = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4 % EPC], f[5 % EPC]),
@@ -702,11 +715,10 @@ cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool 
   Tc05Params p;
   p.M = M; p.N = N; p.K = K;
   p.bias = epi.bias; p.C = c; p.resid = epi.resid; p.grid = epi.grid;
+  p.act = epi.mode == kEpiTanh ? (int)kActTanh : epi.act;
   p.trace = g_gemm_trace ? g_gemm_trace + (size_t)(g_trace_launch++ % 8) * 128 : nullptr;
   if (epi.mode == kEpiResidualUnpart)
     return out_f16 ? cudaErrorInvalidValue : launch_mode<kEpiResidualUnpart, float>(a, w, p, stream);
-  if (epi.mode == kEpiTanh)
-    return out_f16 ? cudaErrorInvalidValue : launch_mode<kEpiTanh, float>(a, w, p, stream);
   return out_f16 ? launch_mode<kEpiStore, __half>(a, w, p, stream)
                  : launch_mode<kEpiStore, float>(a, w, p, stream);
 }

@@ -28,8 +28,10 @@ enum GemmEpilogueMode {
   kEpiTanh = 1,           // c[m,n] = tanh(acc + bias[n])
   kEpiResidualUnpart = 2  // row m is a region slot: out[token(m),n] = resid[token(m),n] + acc + bias[n]
 };
+enum GemmActivation { kActNone = 0, kActRelu = 1, kActGelu = 2, kActTanh = 3, kActSigmoid = 4 };
 struct GemmEpilogue {
   int mode = kEpiStore;
+  int act = kActNone;            // applied to acc + bias (tcgen05 kernel, store mode)
   const float* bias = nullptr;   // [N] or null
   const float* resid = nullptr;  // [L, N] (mode 2)
   Grid grid{};                   // (mode 2)
@@ -110,5 +112,12 @@ cudaError_t launch_crmsa_dispatch(const float* x1, const float* x0, const float*
                                   const float2* rstat, const float* lm, const float* gamma,
                                   const float* beta, float* out, const Grid& grid, int D, int k,
                                   cudaStream_t stream);
+
+// ---- mil_head.cu: DAttention pooling + predictor behind the encoder ---------
+size_t attn_pool_scratch_floats(int L, int D, int hid);
+cudaError_t launch_attn_pool(const float* h, const float* hidden, const float* w2, const float* b2,
+                             const float* pred_w, const float* pred_b, int n_classes, float* scratch,
+                             float* pooled, float* logits, float* attn, int attn_raw, int L, int D,
+                             int hid, cudaStream_t stream);
 
 }  // namespace rrt

@@ -1,0 +1,139 @@
+"""``RRTMIL`` -- the reference's end-to-end model (modules/rrt.py:204-246) on the B200 kernels:
+``patch_to_emb`` (Linear + act) -> ``RRTEncoder`` -> ``DAttention`` pooling -> ``predictor``.
+SURVEY.md 8(f) rows f1 (pooling head) and f2 (patch_to_emb front end).
+
+Same constructor keywords, parameter tree and ``state_dict`` keys as the reference, so reference
+checkpoints load with ``strict=True``.  Inference only (eval mode), like the encoder; options the
+kernels do not cover raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import cabi
+from .encoder import RRTEncoder, initialize_weights
+
+_ACT = {"relu": (nn.ReLU, cabi.RRT_ACT_RELU), "gelu": (nn.GELU, cabi.RRT_ACT_GELU),
+        "tanh": (nn.Tanh, cabi.RRT_ACT_TANH)}
+
+
+class Attention(nn.Module):
+    """Parameters of modules/datten.py:5-26 (``attention`` = Linear(L,128)-act-[Dropout]-Linear(128,1))."""
+
+    def __init__(self, input_dim=512, act='relu', bias=False, dropout=False):
+        super().__init__()
+        self.L, self.D, self.K = input_dim, 128, 1
+        layers = [nn.Linear(self.L, self.D, bias=bias)]
+        self.act_code = cabi.RRT_ACT_NONE
+        if act in _ACT:
+            layers.append(_ACT[act][0]())
+            self.act_code = _ACT[act][1]
+        if dropout:
+            layers.append(nn.Dropout(0.25))
+        layers.append(nn.Linear(self.D, self.K, bias=bias))
+        self.attention = nn.Sequential(*layers)
+
+
+class DAttention(nn.Module):
+    """modules/datten.py:85-101."""
+
+    def __init__(self, input_dim=512, act='relu', gated=False, bias=False, dropout=False):
+        super().__init__()
+        if gated:
+            raise NotImplementedError("da_gated=True (AttentionGated) is not built")
+        self.gated = gated
+        self.attention = Attention(input_dim, act, bias, dropout)
+
+
+class RRTMIL(nn.Module):
+    def __init__(self, input_dim=1024, mlp_dim=512, act='relu', n_classes=2, dropout=0.25, pos_pos=0,
+                 pos='none', peg_k=7, attn='rmsa', pool='attn', region_num=8, n_layers=2, n_heads=8,
+                 drop_path=0., da_act='relu', trans_dropout=0.1, ffn=False, ffn_act='gelu', mlp_ratio=4.,
+                 da_gated=False, da_bias=False, da_dropout=False, trans_dim=64, epeg=True,
+                 min_region_num=0, qkv_bias=True, **kwargs):
+        super().__init__()
+        if pool != 'attn':
+            raise NotImplementedError("pool != 'attn' is not built (and is shape-broken in the reference)")
+        if mlp_dim != 512:
+            raise ValueError("the reference's patch_to_emb always emits 512 channels (modules/rrt.py:208)")
+        layers = [nn.Linear(input_dim, 512)]
+        self._fc_act = cabi.RRT_ACT_NONE
+        if act.lower() in ("relu", "gelu"):
+            layers.append(_ACT[act.lower()][0]())
+            self._fc_act = _ACT[act.lower()][1]
+        self.dp = nn.Dropout(dropout) if dropout > 0. else nn.Identity()
+        self.patch_to_emb = nn.Sequential(*layers)
+        self.online_encoder = RRTEncoder(mlp_dim=mlp_dim, pos_pos=pos_pos, pos=pos, peg_k=peg_k, attn=attn,
+                                         region_num=region_num, n_layers=n_layers, n_heads=n_heads,
+                                         drop_path=drop_path, drop_out=trans_dropout, ffn=ffn,
+                                         ffn_act=ffn_act, mlp_ratio=mlp_ratio, trans_dim=trans_dim,
+                                         epeg=epeg, min_region_num=min_region_num, qkv_bias=qkv_bias,
+                                         **kwargs)
+        self.pool_fn = DAttention(self.online_encoder.final_dim, da_act, gated=da_gated, bias=da_bias,
+                                  dropout=da_dropout)
+        self.predictor = nn.Linear(self.online_encoder.final_dim, n_classes)
+        self.apply(initialize_weights)
+        self._shadow = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _f16(self, param):
+        key = id(param)
+        ent = self._shadow.get(key)
+        if ent is None or ent[0] != (param.data_ptr(), param._version):
+            buf = torch.empty(param.shape, dtype=torch.float16, device=param.device)
+            cabi.check(cabi.lib().rrt_convert_f16(param.data_ptr(), buf.data_ptr(), param.numel(),
+                                                  torch.cuda.current_stream(param.device).cuda_stream),
+                       "rrt_convert_f16")
+            ent = ((param.data_ptr(), param._version), buf)
+            self._shadow[key] = ent
+        return ent[1].data_ptr()
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else t.data_ptr()
+
+    def forward(self, x, return_attn=False, no_norm=False):
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        if x.dim() != 3 or x.shape[0] != 1:
+            raise ValueError("RRTMIL processes one bag [1, N, input_dim] per call")
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise RuntimeError("RRTMIL (rrt_mil_b200) needs float32 CUDA input; there is no CPU fallback")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("backward kernels are not built yet: call under torch.no_grad()")
+        if self.training:
+            raise NotImplementedError("training-mode dropout is not built: use .eval()")
+        bag = x[0].contiguous()
+        L, in_dim = bag.shape
+        dev = bag.device
+        lib = cabi.lib()
+        fc, att, pred = self.patch_to_emb[0], self.pool_fn.attention, self.predictor
+        a0, a2 = att.attention[0], att.attention[-1]
+        hid, dim, ncls = a0.out_features, self.online_encoder.final_dim, pred.out_features
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            n = C.c_size_t()
+            cabi.check(lib.rrt_mil_head_workspace_bytes(L, max(in_dim, dim), dim, hid, C.byref(n)), "workspace")
+            ws = torch.empty(n.value, dtype=torch.uint8, device=dev)
+            h0 = torch.empty(L, dim, device=dev)
+            cabi.check(lib.rrt_patch_embed_forward(bag.data_ptr(), L, in_dim, dim, fc.weight.data_ptr(),
+                                                   self._p(fc.bias), self._f16(fc.weight), self._fc_act,
+                                                   h0.data_ptr(), ws.data_ptr(), n.value, st),
+                       "rrt_patch_embed_forward")
+            h1 = self.online_encoder.forward_bag(h0)
+            pooled = torch.empty(dim, device=dev)
+            logits = torch.empty(ncls, device=dev)
+            attn = torch.empty(L, device=dev) if return_attn else None
+            cabi.check(lib.rrt_attn_pool_forward(h1.data_ptr(), L, dim, hid, a0.weight.data_ptr(),
+                                                 self._p(a0.bias), self._f16(a0.weight), att.act_code,
+                                                 a2.weight.data_ptr(), self._p(a2.bias),
+                                                 pred.weight.data_ptr(), self._p(pred.bias), ncls,
+                                                 pooled.data_ptr(), logits.data_ptr(), self._p(attn),
+                                                 int(bool(no_norm)), ws.data_ptr(), n.value, st),
+                       "rrt_attn_pool_forward")
+        if return_attn:
+            return logits.unsqueeze(0), attn.unsqueeze(0)
+        return logits.unsqueeze(0)
