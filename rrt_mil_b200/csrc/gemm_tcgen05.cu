@@ -53,6 +53,12 @@ struct Tc05Params {
   long long* trace;  // debug: per-CTA clock64 stamps (tools/gemm_trace.py), null in production
 };
 
+// internal compile-time mode: kEpiStore with a run-time activation.  Kept apart from kEpiStore so that
+// the bag-sized QKV / landmark GEMMs do not carry the erff/tanhf code in their epilogue (measured:
+// 20.9 -> 31.5 us for the QKV GEMM when the switch sat in the common kernel).
+constexpr int kEpiStoreAct = 3;
+__host__ __device__ constexpr bool is_store_mode(int mode) { return mode == kEpiStore || mode == kEpiStoreAct; }
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case kActRelu: return fmaxf(v, 0.f);
@@ -85,7 +91,7 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
                                               uint32_t tmem_acc, uint64_t* tfull_bar,
                                               uint32_t tfull_parity, int m0, int n0, int ew, int lane,
                                               float* scratch, bool first, ReleaseFn release) {
-  constexpr bool kTmaStore = MODE == kEpiStore;
+  constexpr bool kTmaStore = is_store_mode(MODE);
   constexpr int NC = (BN / 32) / 2;  // chunks per epilogue warp
   const int quad = ew & 3;           // TMEM lanes [32*quad, 32*quad+32) are readable by this warp
   const int c_begin = (ew >> 2) * NC;
@@ -177,7 +183,7 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
 #pragma unroll
           for (int e = 0; e < EPC; ++e) {
             f[e] = __uint_as_float(rr[q * EPC + e]) + __shfl_sync(0xffffffffu, bias_l[j], q * EPC + e);
-            if (p.act != kActNone) f[e] = apply_act(f[e], p.act);
+            if (MODE == kEpiStoreAct) f[e] = apply_act(f[e], p.act);
           }
           uint4 pk;
           if (sizeof(OutT) == 2) {
@@ -248,7 +254,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   constexpr int CSIZE = CM * CN;
   // plain stores (kEpiStore): the epilogue hands each 32x32 chunk to the TMA engine; the scatter /
   // tanh epilogues keep st.global (rows are permuted resp. the layer is tiny)
-  constexpr bool kTmaStore = MODE == kEpiStore;
+  constexpr bool kTmaStore = is_store_mode(MODE);
   constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int TMEM_COLS = Cfg::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
@@ -403,7 +409,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
                              const __grid_constant__ CUtensorMap tmB,
                              const __grid_constant__ CUtensorMap tmC, Tc05Params p) {
   constexpr int BN = P2_BN, STAGES = P2_STAGES;
-  constexpr bool kTmaStore = MODE == kEpiStore;
+  constexpr bool kTmaStore = is_store_mode(MODE);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -613,7 +619,7 @@ cudaError_t launch_cfg(const __half* a, const __half* w, const Tc05Params& p, cu
   CUtensorMap tmA, tmB, tmC;
   if (!make_map(&tmA, a, p.M, p.K, BM / CN) || !make_map(&tmB, w, p.N, p.K, BN / CM))
     return cudaErrorUnknown;
-  if (MODE == kEpiStore) {
+  if (is_store_mode(MODE)) {
     if (!make_store_map(&tmC, p.C, p.M, p.N, (int)sizeof(OutT))) return cudaErrorUnknown;
   } else {
     tmC = tmA;  // unused by the st.global epilogues
@@ -657,7 +663,7 @@ template <int MODE, typename OutT>
 cudaError_t launch_pair(const __half* a, const __half* w, const Tc05Params& p, cudaStream_t stream) {
   CUtensorMap tmA, tmB, tmC;
   if (!make_map(&tmA, a, p.M, p.K, BM) || !make_map(&tmB, w, p.N, p.K, P2_BN / 2)) return cudaErrorUnknown;
-  if (MODE == kEpiStore) {
+  if (is_store_mode(MODE)) {
     if (!make_store_map(&tmC, p.C, p.M, p.N, (int)sizeof(OutT))) return cudaErrorUnknown;
   } else {
     tmC = tmA;
@@ -691,6 +697,7 @@ cudaError_t launch_mode(const __half* a, const __half* w, const Tc05Params& p, c
   // small problems: narrower tiles so that more SMs share the (latency-bound) work
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n256 = (p.N + 255) / 256;
   if (tiles_m * tiles_n256 < sm_count() / 2) return launch_cfg<MODE, 64, OutT, 1, 1>(a, w, p, stream);
+  if (MODE == kEpiStoreAct) return launch_cfg<MODE, 256, OutT, 1, 1>(a, w, p, stream);  // no tuning variants
   if (g_gemm_pair && tiles_m >= 2) return launch_pair<MODE, OutT>(a, w, p, stream);
   // bag-sized problems: clusters with multicast operand tiles when the tile grid allows it
   if (g_gemm_cluster == 22 && tiles_m >= 2 && tiles_n256 >= 2 && tiles_n256 % 2 == 0)
@@ -719,6 +726,9 @@ cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool 
   p.trace = g_gemm_trace ? g_gemm_trace + (size_t)(g_trace_launch++ % 8) * 128 : nullptr;
   if (epi.mode == kEpiResidualUnpart)
     return out_f16 ? cudaErrorInvalidValue : launch_mode<kEpiResidualUnpart, float>(a, w, p, stream);
+  if (p.act != kActNone)
+    return out_f16 ? launch_mode<kEpiStoreAct, __half>(a, w, p, stream)
+                   : launch_mode<kEpiStoreAct, float>(a, w, p, stream);
   return out_f16 ? launch_mode<kEpiStore, __half>(a, w, p, stream)
                  : launch_mode<kEpiStore, float>(a, w, p, stream);
 }
