@@ -33,7 +33,7 @@ extern "C" {
 #define RRT_API __attribute__((visibility("default")))
 #endif
 
-#define RRT_ABI_VERSION 3
+#define RRT_ABI_VERSION 4
 #define RRT_MAX_RMSA_LAYERS 8 /* n_layers-1 R-MSA TransLayers (modules/rrt.py:143) */
 #define RRT_MAX_CRMSA_K 16    /* crmsa_k landmarks per region                         */
 #define RRT_MAX_EPEG_K 63     /* odd EPEG kernel length                               */
@@ -214,6 +214,59 @@ RRT_API int rrt_attn_pool_forward(const float* h, int64_t L, int32_t dim, int32_
                                   const float* pred_b, int32_t n_classes, float* pooled,
                                   float* logits, float* attn, int32_t attn_raw, void* workspace,
                                   size_t workspace_bytes, void* stream);
+
+/* ---- training: forward with a tape + backward (autograd of modules/rrt.py:165-202) ---------------
+ * Dropout is not applied (drop_out = 0 or eval mode); the Python module raises for active dropout.
+ * rrt_encoder_forward_train computes exactly what rrt_encoder_forward computes and keeps, in the
+ * caller-owned `tape` (rrt_train_tape_bytes), what the backward pass re-reads: per R-MSA layer the
+ * LayerNorm output, q/k/v, the attention output (fp16) and the layer output (fp32); for CR-MSA the
+ * logits, min/max, landmarks and the landmark MHA's q/k/v, o and output.  The attention
+ * probabilities are recomputed.  rrt_encoder_backward takes d(loss)/d(out) and writes d(loss)/dx and
+ * every parameter gradient.  Gradient buffers follow rrt_weights (same shapes, fp32) and MUST be
+ * zero-initialised by the caller (bias / LayerNorm / tap / phi gradients are accumulated with
+ * atomics; weight gradients are overwritten).  Tensor-core operands of the backward GEMMs are fp16
+ * with automatic per-stage power-of-two scaling (csrc/backward.cuh), accumulators fp32.
+ * Not covered (RRT_E_INVALID): crmsa_mlp, crmsa_k > 8, head_dim 128, regions > 256 tokens. */
+typedef struct rrt_attn_grads {
+  float* qkv_w;  /* [3D, D] */
+  float* qkv_b;  /* [3D] or NULL */
+  float* proj_w; /* [D, D] */
+  float* proj_b; /* [D] */
+  float* pe_w;   /* [heads, epeg_k] or NULL (pe.bias has an exactly zero gradient) */
+} rrt_attn_grads;
+
+typedef struct rrt_grads {
+  float* norm_w;
+  float* norm_b;
+  float* layer_norm_w[RRT_MAX_RMSA_LAYERS];
+  float* layer_norm_b[RRT_MAX_RMSA_LAYERS];
+  rrt_attn_grads layer_attn[RRT_MAX_RMSA_LAYERS];
+  float* cr_norm_w;
+  float* cr_norm_b;
+  float* cr_phi; /* [D, k] */
+  rrt_attn_grads cr_attn;
+} rrt_grads;
+
+RRT_API int rrt_train_tape_bytes(const rrt_config* cfg, int64_t L, size_t* bytes);
+RRT_API int rrt_encoder_forward_train(const rrt_config* cfg, const rrt_weights* w, const float* x,
+                                      float* out, int64_t L, void* tape, size_t tape_bytes,
+                                      void* stream);
+RRT_API int rrt_backward_workspace_bytes(const rrt_config* cfg, int64_t L, size_t* bytes);
+/* x: the forward input; dout: d(loss)/d(out) [L, D]; dx: d(loss)/dx [L, D] (may not alias dout). */
+RRT_API int rrt_encoder_backward(const rrt_config* cfg, const rrt_weights* w, const float* x,
+                                 const float* dout, int64_t L, const void* tape, size_t tape_bytes,
+                                 const rrt_grads* grads, float* dx, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
+/* Building blocks of the backward pass, exposed for the parity tests.
+ * rrt_attention_backward: qkv [R*P, 3D] fp16 and o [R*P, D] fp16 as the forward wrote them,
+ * d_o [R*P, D] fp16 -> d_qkv [R*P, 3D] fp16, d_taps [heads, epeg_k] fp32 (+=; taps/d_taps NULL: no EPEG).
+ * rrt_layernorm_backward: y = LayerNorm(x): dy [L, D] fp32 -> dx, dgamma (+=), dbeta (+=). */
+RRT_API int rrt_attention_backward(const void* qkv, const void* o, const void* d_o, const float* taps,
+                                   void* d_qkv, float* d_taps, int32_t R, int32_t P, int32_t dim,
+                                   int32_t heads, int32_t epeg_k, void* stream);
+RRT_API int rrt_layernorm_backward(const float* x, const float* gamma, const float* dy, float* dx,
+                                   float* dgamma, float* dbeta, int64_t L, int32_t dim, void* stream);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------- */
 /* Kernel launches issued by this library in this process so far. */

@@ -12,7 +12,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librrt_b200.so")
 
-RRT_ABI_VERSION = 3
+RRT_ABI_VERSION = 4
 RRT_MAX_RMSA_LAYERS = 8
 RRT_MAX_CRMSA_K = 16
 RRT_MAX_EPEG_K = 63
@@ -53,6 +53,22 @@ class RrtWeights(C.Structure):
     ]
 
 
+class RrtAttnGrads(C.Structure):
+    _fields_ = [("qkv_w", c_float_p), ("qkv_b", c_float_p), ("proj_w", c_float_p),
+                ("proj_b", c_float_p), ("pe_w", c_float_p)]
+
+
+class RrtGrads(C.Structure):
+    _fields_ = [
+        ("norm_w", c_float_p), ("norm_b", c_float_p),
+        ("layer_norm_w", c_float_p * RRT_MAX_RMSA_LAYERS),
+        ("layer_norm_b", c_float_p * RRT_MAX_RMSA_LAYERS),
+        ("layer_attn", RrtAttnGrads * RRT_MAX_RMSA_LAYERS),
+        ("cr_norm_w", c_float_p), ("cr_norm_b", c_float_p), ("cr_phi", c_float_p),
+        ("cr_attn", RrtAttnGrads),
+    ]
+
+
 # name -> (restype, argtypes); must list every RRT_API symbol of include/rrt_b200.h
 _P = C.c_void_p
 SIGNATURES = {
@@ -72,6 +88,15 @@ SIGNATURES = {
                                          _P, _P, C.c_int64, _P, C.c_size_t, _P]),
     "rrt_crmsa_block_forward": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P, _P,
                                           C.c_int64, C.c_int32, _P, C.c_size_t, _P]),
+    "rrt_train_tape_bytes": (C.c_int, [C.POINTER(RrtConfig), C.c_int64, C.POINTER(C.c_size_t)]),
+    "rrt_encoder_forward_train": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P,
+                                            C.c_int64, _P, C.c_size_t, _P]),
+    "rrt_backward_workspace_bytes": (C.c_int, [C.POINTER(RrtConfig), C.c_int64, C.POINTER(C.c_size_t)]),
+    "rrt_encoder_backward": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P, C.c_int64,
+                                       _P, C.c_size_t, C.POINTER(RrtGrads), _P, _P, C.c_size_t, _P]),
+    "rrt_attention_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_int32, _P]),
+    "rrt_layernorm_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "rrt_mil_head_workspace_bytes": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "rrt_patch_embed_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P,
                                           C.c_size_t, _P]),

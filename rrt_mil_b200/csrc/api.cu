@@ -33,12 +33,15 @@ int fail_cuda(cudaError_t e, const char* where) {
 // ---- measurement hooks ---------------------------------------------------------------------
 enum Stage {
   kStLnPartition = 0, kStQkvGemm, kStRmsaAttn, kStProjGemm, kStCrLogits, kStCrMlp, kStCrCombine,
-  kStLmQkv, kStLmAttn, kStLmProj, kStCrDispatch, kStFinalLn, kStOther, kStCount
+  kStLmQkv, kStLmAttn, kStLmProj, kStCrDispatch, kStFinalLn, kStOther,
+  kStBwdPrep, kStBwdDgrad, kStBwdWgrad, kStBwdAttn, kStBwdLn, kStBwdCr, kStCount
 };
 const char* const kStageNames[kStCount] = {
     "ln_partition", "qkv_gemm", "rmsa_attention", "proj_gemm_residual", "crmsa_stats_logits",
     "crmsa_mlp_phi", "crmsa_landmarks", "landmark_qkv_gemm", "landmark_attention",
-    "landmark_proj_gemm", "crmsa_dispatch_final_ln", "final_layernorm", "other"};
+    "landmark_proj_gemm", "crmsa_dispatch_final_ln", "final_layernorm", "other",
+    "bwd_partition_transpose", "bwd_dgrad_gemm", "bwd_wgrad_gemm", "bwd_attention", "bwd_layernorm",
+    "bwd_crmsa"};
 
 std::atomic<int64_t> g_launches{0};
 std::atomic<bool> g_timing{false};
@@ -157,11 +160,14 @@ int check_config(const rrt_config* c) {
 
 // ---- workspace ----------------------------------------------------------------------------
 struct Workspace {
-  __half* z;       // [Np_r, D]   LN'd, padded, region-ordered tokens (also z2 for crmsa_mlp)
-  __half* qkv;     // [Np_r, 3D]
-  __half* o;       // [Np_r, D]
-  float* xa;       // [L, D] residual stream ping
-  float* xb;       // [L, D] residual stream pong
+  // Per R-MSA layer.  Inference: every layer aliases the same z/qkv/o and the residual stream
+  // ping-pongs between two buffers.  Training (the tape of rrt_encoder_forward_train): every layer
+  // owns its buffers, because the backward pass re-reads z, q/k/v, o and the layer inputs.
+  __half* z[RRT_MAX_RMSA_LAYERS];    // [Np_r, D]   LN'd, padded, region-ordered tokens
+  __half* qkv[RRT_MAX_RMSA_LAYERS];  // [Np_r, 3D]
+  __half* o[RRT_MAX_RMSA_LAYERS];    // [Np_r, D]
+  float* xs[RRT_MAX_RMSA_LAYERS];    // [L, D] output of layer i (residual stream)
+  __half* zc;      // [Np_c, D] CR-MSA LN output (crmsa_mlp only)
   float2* stats;   // [Np_c]
   float* logits;   // [Np_c, k]
   float2* rstat;   // [R_c, k]
@@ -176,7 +182,7 @@ struct Workspace {
 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
-bool carve(const rrt_config* c, int64_t L, void* base, Workspace* ws) {
+bool carve(const rrt_config* c, int64_t L, void* base, Workspace* ws, bool train = false) {
   rrt::Grid gr{}, gc{};
   size_t np_r = 0;
   if (c->n_rmsa_layers > 0) {
@@ -190,8 +196,9 @@ bool carve(const rrt_config* c, int64_t L, void* base, Workspace* ws) {
     np_c = gc.Np;
   }
   const size_t D = c->dim, k = c->cr_msa ? c->crmsa_k : 0, T = k * 64;
+  const bool mlp = c->cr_msa && c->crmsa_mlp;
   size_t np_z = np_r;
-  if (c->cr_msa && c->crmsa_mlp && np_c > np_z) np_z = np_c;
+  if (!train && mlp && np_c > np_z) np_z = np_c;
   char* p = (char*)base;
   size_t off = 0;
   auto take = [&](size_t nbytes) {
@@ -199,11 +206,26 @@ bool carve(const rrt_config* c, int64_t L, void* base, Workspace* ws) {
     off += align_up(nbytes);
     return r;
   };
-  ws->z = (__half*)take(np_z * D * 2);
-  ws->qkv = (__half*)take(np_r * 3 * D * 2);
-  ws->o = (__half*)take(np_r * D * 2);
-  ws->xa = (float*)take((size_t)L * D * 4);
-  ws->xb = (float*)take((size_t)L * D * 4);
+  if (train) {
+    for (int i = 0; i < c->n_rmsa_layers; ++i) {
+      ws->z[i] = (__half*)take(np_r * D * 2);
+      ws->qkv[i] = (__half*)take(np_r * 3 * D * 2);
+      ws->o[i] = (__half*)take(np_r * D * 2);
+      ws->xs[i] = (float*)take((size_t)L * D * 4);
+    }
+    ws->zc = (__half*)take(mlp ? np_c * D * 2 : 0);
+  } else {
+    __half* z = (__half*)take(np_z * D * 2);
+    __half* qkv = (__half*)take(np_r * 3 * D * 2);
+    __half* o = (__half*)take(np_r * D * 2);
+    float* xa = (float*)take((size_t)L * D * 4);
+    float* xb = (float*)take((size_t)L * D * 4);
+    for (int i = 0; i < RRT_MAX_RMSA_LAYERS; ++i) {
+      ws->z[i] = z; ws->qkv[i] = qkv; ws->o[i] = o;
+      ws->xs[i] = (i & 1) ? xb : xa;
+    }
+    ws->zc = z;
+  }
   ws->stats = (float2*)take(np_c * 8);
   ws->logits = (float*)take(np_c * k * 4);
   ws->rstat = (float2*)take(64 * k * 8);
@@ -211,7 +233,7 @@ bool carve(const rrt_config* c, int64_t L, void* base, Workspace* ws) {
   ws->lqkv = (float*)take(T * 3 * D * 4);
   ws->lo = (__half*)take(T * D * 2);
   ws->lout = (float*)take(T * D * 4);
-  ws->hidden = (float*)take((c->cr_msa && c->crmsa_mlp) ? np_c * (D / 4) * 4 : 0);
+  ws->hidden = (float*)take(mlp ? np_c * (D / 4) * 4 : 0);
   ws->wconv = (__half*)take(4 * D * D * 2);
   ws->bytes = off + 256;
   return true;
@@ -241,7 +263,10 @@ int f16_weight(const float* w32, const void* shadow, __half* scratch, size_t n, 
 
 int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
                const rrt_attn_weights* a, const float* x, float* x1, int64_t L, Workspace& ws,
-               cudaStream_t st) {
+               cudaStream_t st, int layer = 0) {
+  __half* const ws_z = ws.z[layer];
+  __half* const ws_qkv = ws.qkv[layer];
+  __half* const ws_o = ws.o[layer];
   rrt::Grid g{};
   if (!make_grid(L, c->region_num, c->region_size, c->min_region_num, c->min_region_ratio, &g))
     return fail(RRT_E_INVALID, "bad geometry");
@@ -252,21 +277,21 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
   rc = f16_weight(a->proj_w, a->proj_w_f16, ws.wconv + (size_t)3 * D * D, (size_t)D * D, st, &wp);
   if (rc) return rc;
   { StageScope s_(kStLnPartition, st);
-    RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws.z, g, D, st), "ln_partition"); }
+    RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws_z, g, D, st), "ln_partition"); }
   rrt::GemmEpilogue e1;
   e1.bias = c->qkv_bias ? a->qkv_b : nullptr;
   { StageScope s_(kStQkvGemm, st);
-    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.z, wq, ws.qkv, true, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
+    RRT_CUDA(rrt::launch_gemm_tcgen05(ws_z, wq, ws_qkv, true, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
   { StageScope s_(kStRmsaAttn, st);
     const float* taps = c->epeg ? a->pe_w : nullptr;
     if (rrt::g_attn_tc05 && rrt::rmsa_attention_tc05_supported(g, D, c->n_heads))
-      RRT_CUDA(rrt::launch_rmsa_attention_tc05(ws.qkv, taps, ws.o, g, D, c->n_heads, c->epeg_k, st),
+      RRT_CUDA(rrt::launch_rmsa_attention_tc05(ws_qkv, taps, ws_o, g, D, c->n_heads, c->epeg_k, st),
                "rmsa attention (tcgen05)");
     else if (rrt::rmsa_attention_f16_supported(g, D, c->n_heads))
-      RRT_CUDA(rrt::launch_rmsa_attention_f16(ws.qkv, taps, ws.o, g, D, c->n_heads, c->epeg_k, st),
+      RRT_CUDA(rrt::launch_rmsa_attention_f16(ws_qkv, taps, ws_o, g, D, c->n_heads, c->epeg_k, st),
                "rmsa attention (region-resident)");
     else
-      RRT_CUDA(rrt::launch_rmsa_attention(ws.qkv, taps, ws.o, g, D, c->n_heads, c->epeg_k, st),
+      RRT_CUDA(rrt::launch_rmsa_attention(ws_qkv, taps, ws_o, g, D, c->n_heads, c->epeg_k, st),
                "rmsa attention (flash)"); }
   rrt::GemmEpilogue e2;
   e2.mode = rrt::kEpiResidualUnpart;
@@ -274,7 +299,7 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
   e2.resid = x;
   e2.grid = g;
   { StageScope s_(kStProjGemm, st);
-    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.o, wp, x1, false, g.Np, D, D, e2, st), "proj gemm"); }
+    RRT_CUDA(rrt::launch_gemm_tcgen05(ws_o, wp, x1, false, g.Np, D, D, e2, st), "proj gemm"); }
   return RRT_OK;
 }
 
@@ -292,11 +317,11 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
     int rc = f16_weight(w->cr_phi_w1, w->cr_phi_w1_f16, ws.wconv, (size_t)(D / 4) * D, st, &w1);
     if (rc) return rc;
     StageScope s_mlp(kStCrMlp, st, 3);
-    RRT_CUDA(rrt::launch_ln_partition(x1, w->cr_norm_w, w->cr_norm_b, ws.z, g, D, st),
+    RRT_CUDA(rrt::launch_ln_partition(x1, w->cr_norm_w, w->cr_norm_b, ws.zc, g, D, st),
              "crmsa ln_partition");
     rrt::GemmEpilogue eh;
     eh.mode = rrt::kEpiTanh;
-    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.z, w1, ws.hidden, false, g.Np, D / 4, D, eh, st), "phi.0");
+    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.zc, w1, ws.hidden, false, g.Np, D / 4, D, eh, st), "phi.0");
     RRT_CUDA(rrt::launch_crmsa_mlp_logits(ws.hidden, w->cr_phi_w2, ws.logits, g.Np, D / 4, k, st),
              "phi.2");
   } else {
@@ -368,9 +393,9 @@ int encoder_forward(const rrt_config* cfg, const rrt_weights* w, const float* x,
   const int D = cfg->dim;
   const float* cur = x;
   for (int i = 0; i < cfg->n_rmsa_layers; ++i) {
-    float* nxt = (cur == ws.xa) ? ws.xb : ws.xa;
+    float* nxt = ws.xs[i];
     int rc = rmsa_block(cfg, w->layer_norm_w[i], w->layer_norm_b[i], &w->layer_attn[i], cur, nxt, L,
-                        ws, st);
+                        ws, st, i);
     if (rc) return rc;
     cur = nxt;
   }
@@ -717,6 +742,301 @@ RRT_API int rrt_layernorm_forward(const float* x, const float* gamma, const floa
   if (!x || !gamma || !beta || !out) return fail(RRT_E_INVALID, "NULL pointer");
   StageScope s_(kStOther, (cudaStream_t)stream);
   RRT_CUDA(rrt::launch_layernorm(x, gamma, beta, out, (int)L, D, (cudaStream_t)stream), "layernorm");
+  return RRT_OK;
+}
+
+}  // extern "C"
+
+// ===============================================================================================
+// Training: forward with a tape, backward.
+namespace {
+
+struct BwdWorkspace {
+  // zero-initialised at the start of every backward call (one memset)
+  uint32_t* amax;  // [32] stage amax words (backward.cuh)
+  float2* rgrad;   // [64, k] d lo / d hi of the min-max normaliser
+  float* dLp;      // [k*64, D] gradient wrt the landmark MHA output
+  size_t zero_bytes;
+  float* dw;       // [Np_c, k] d(dispatch weight)
+  __half* dy;      // [M, D]    scaled gradient rows (slot order)
+  __half* dyT;     // [D, M64]
+  __half* dO;      // [M, D]
+  __half* actT;    // [D, M64]  o^T, then z^T
+  __half* dqkv;    // [M, 3D]
+  __half* dqkvT;   // [3D, M64]
+  __half* dz;      // [M, D]
+  __half* wT;      // [3D*D]    transposed fp16 weight
+  float* dh;       // [L, D] gradient wrt the final norm's input
+  float* ga;       // [L, D] residual-stream gradient ping
+  float* gb;       // [L, D] pong
+  size_t bytes;
+};
+
+bool carve_bwd(const rrt_config* c, int64_t L, void* base, BwdWorkspace* b) {
+  rrt::Grid gr{}, gc{};
+  size_t M = 0, np_c = 0;
+  if (c->n_rmsa_layers > 0) {
+    if (!make_grid(L, c->region_num, c->region_size, c->min_region_num, c->min_region_ratio, &gr))
+      return false;
+    M = gr.Np;
+  }
+  const size_t D = c->dim, k = c->cr_msa ? c->crmsa_k : 0, T = k * 64;
+  if (c->cr_msa) {
+    if (!crmsa_grid(L, &gc)) return false;
+    np_c = gc.Np;
+    if (T > M) M = T;
+  }
+  const size_t M64 = (M + 63) / 64 * 64;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t nbytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(nbytes);
+    return r;
+  };
+  b->amax = (uint32_t*)take(32 * 4);
+  b->rgrad = (float2*)take(64 * k * 8);
+  b->dLp = (float*)take(T * D * 4);
+  b->zero_bytes = off;
+  b->dw = (float*)take(np_c * k * 4);
+  b->dy = (__half*)take(M * D * 2);
+  b->dyT = (__half*)take(D * M64 * 2);
+  b->dO = (__half*)take(M * D * 2);
+  b->actT = (__half*)take(D * M64 * 2);
+  b->dqkv = (__half*)take(M * 3 * D * 2);
+  b->dqkvT = (__half*)take(3 * D * M64 * 2);
+  b->dz = (__half*)take(M * D * 2);
+  b->wT = (__half*)take(3 * D * D * 2);
+  b->dh = (float*)take((size_t)L * D * 4);
+  b->ga = (float*)take((size_t)L * D * 4);
+  b->gb = (float*)take((size_t)L * D * 4);
+  b->bytes = off + 256;
+  return true;
+}
+
+int check_backward_support(const rrt_config* c, int64_t L) {
+  if (c->cr_msa && c->crmsa_mlp) return fail(RRT_E_INVALID, "backward: crmsa_mlp is not covered");
+  if (c->n_rmsa_layers == 0 && !c->cr_msa) return fail(RRT_E_INVALID, "backward: encoder has no block");
+  if (c->n_rmsa_layers > 0) {
+    rrt::Grid g{};
+    if (!make_grid(L, c->region_num, c->region_size, c->min_region_num, c->min_region_ratio, &g))
+      return fail(RRT_E_INVALID, "bad geometry");
+    if (!rrt::rmsa_attention_bwd_supported(g.P, c->dim, c->n_heads, c->epeg ? c->epeg_k : 1) ||
+        !rrt::rmsa_attention_f16_supported(g, c->dim, c->n_heads))
+      return fail(RRT_E_INVALID, "backward: R-MSA needs regions <= 256 tokens and head_dim 32 or 64");
+  }
+  if (c->cr_msa) {
+    if (!rrt::crmsa_backward_supported(c->dim, c->crmsa_k))
+      return fail(RRT_E_INVALID, "backward: CR-MSA needs dim in {128,256,512,1024} and crmsa_k <= 8");
+    if (!rrt::rmsa_attention_bwd_supported(64, c->dim, c->crmsa_heads, 1))
+      return fail(RRT_E_INVALID, "backward: CR-MSA head_dim must be 32 or 64");
+  }
+  return RRT_OK;
+}
+
+// Backward of y = act_rows . W^T + b followed by whatever produced `dy` (fp16, scaled rows [M, C_out]
+// with transpose dyT):   d_in = dy . W  (fp16 rows [M, C_in]),  dW = dy^T . act  (fp32 [C_out, C_in]).
+// act: the forward's fp16 input rows [M, C_in].
+int linear_backward(const __half* dy, const __half* dyT, const __half* act, const float* w, int M,
+                    int C_out, int C_in, const uint32_t* amax, __half* d_in, float* dW,
+                    BwdWorkspace& b, cudaStream_t st) {
+  const int M64 = (M + 63) / 64 * 64;
+  rrt::GemmEpilogue e;
+  if (d_in) {
+    { StageScope s_(kStBwdPrep, st);
+      RRT_CUDA(rrt::launch_wt_convert(w, b.wT, C_out, C_in, st), "weight transpose"); }
+    StageScope s_(kStBwdDgrad, st);
+    RRT_CUDA(rrt::launch_gemm_tcgen05(dy, b.wT, d_in, true, M, C_in, C_out, e, st), "dgrad gemm");
+  }
+  { StageScope s_(kStBwdPrep, st);
+    RRT_CUDA(rrt::launch_transpose_f16(act, M, C_in, b.actT, nullptr, nullptr, st), "activation transpose"); }
+  { StageScope s_(kStBwdWgrad, st, 2);
+    RRT_CUDA(rrt::launch_gemm_tcgen05(dyT, b.actT, dW, false, C_out, C_in, M64, e, st), "wgrad gemm");
+    RRT_CUDA(rrt::launch_scale_by_inv(dW, (size_t)C_out * C_in, amax, st), "wgrad unscale"); }
+  return RRT_OK;
+}
+
+// Backward of one attention module on rows in slot order: dy (scaled fp16 [M, D], + transpose) is the
+// gradient wrt the projection output.  Leaves the gradient wrt the module input (z / landmarks) in b.dz.
+int attention_module_backward(const rrt_config* c, const rrt_attn_weights* a, const rrt_attn_grads* ga,
+                              const __half* z, const __half* qkv, const __half* o, int R, int P,
+                              int heads, bool epeg, const uint32_t* amax, BwdWorkspace& b,
+                              cudaStream_t st) {
+  const int D = c->dim, M = R * P;
+  int rc = linear_backward(b.dy, b.dyT, o, a->proj_w, M, D, D, amax, b.dO, ga->proj_w, b, st);
+  if (rc) return rc;
+  { StageScope s_(kStBwdAttn, st);
+    RRT_CUDA(rrt::launch_rmsa_attention_bwd(qkv, o, b.dO, epeg ? a->pe_w : nullptr, b.dqkv,
+                                            epeg ? ga->pe_w : nullptr, amax, R, P, D, heads,
+                                            epeg ? c->epeg_k : 1, st), "attention backward"); }
+  { StageScope s_(kStBwdPrep, st);
+    RRT_CUDA(rrt::launch_transpose_f16(b.dqkv, M, 3 * D, b.dqkvT, c->qkv_bias ? ga->qkv_b : nullptr,
+                                       amax, st), "dqkv transpose"); }
+  return linear_backward(b.dqkv, b.dqkvT, z, a->qkv_w, M, 3 * D, D, amax, b.dz, ga->qkv_w, b, st);
+}
+
+int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, const float* dout,
+                     int64_t L, const Workspace& tp, const rrt_grads* gr, float* dx, BwdWorkspace& b,
+                     cudaStream_t st) {
+  const int D = c->dim, nl = c->n_rmsa_layers;
+  RRT_CUDA(cudaMemsetAsync(b.amax, 0, b.zero_bytes, st), "zero backward scalars");
+  const float* x_last = nl > 0 ? tp.xs[nl - 1] : x;
+  const float* x0 = c->all_shortcut ? x : nullptr;
+  rrt::Grid ident{};
+  const float* g = nullptr;  // gradient wrt x_last
+  int am = 0;                // index of g's amax word
+  if (c->cr_msa) {
+    rrt::Grid gc{};
+    if (!crmsa_grid(L, &gc)) return fail(RRT_E_INVALID, "bad geometry");
+    const int k = c->crmsa_k, T = k * gc.R;
+    if (!gr->norm_w || !gr->norm_b || !gr->cr_norm_w || !gr->cr_norm_b || !gr->cr_phi ||
+        !gr->cr_attn.qkv_w || !gr->cr_attn.proj_w || !gr->cr_attn.proj_b ||
+        (c->qkv_bias && !gr->cr_attn.qkv_b))
+      return fail(RRT_E_INVALID, "NULL gradient buffer");
+    { StageScope s_(kStBwdCr, st);
+      RRT_CUDA(rrt::launch_crmsa_dispatch_bwd(x_last, x0, tp.logits, tp.rstat, tp.lout, w->norm_w, dout,
+                                              b.dh, b.dw, b.dLp, b.rgrad, gr->norm_w, gr->norm_b, gc, D,
+                                              k, st), "crmsa dispatch backward"); }
+    // landmark MHA backward on T = k*64 rows (batch k, sequence 64, no EPEG)
+    ident.L = T; ident.Np = T;
+    { StageScope s_(kStBwdPrep, st, 2);
+      RRT_CUDA(rrt::launch_amax(b.dLp, (size_t)T * D, &b.amax[0], st), "amax");
+      RRT_CUDA(rrt::launch_grad_partition(b.dLp, ident, T, D, &b.amax[0], b.dy, b.dyT,
+                                          gr->cr_attn.proj_b, st), "landmark grad rows"); }
+    int rc = attention_module_backward(c, &w->cr_attn, &gr->cr_attn, tp.lm,
+                                       reinterpret_cast<const __half*>(tp.lqkv), tp.lo, k, gc.R,
+                                       c->crmsa_heads, false, &b.amax[0], b, st);
+    if (rc) return rc;
+    float* out = nl > 0 ? b.ga : dx;
+    const float dh_weight = (nl == 0 && c->all_shortcut) ? 2.f : 1.f;
+    { StageScope s_(kStBwdCr, st);
+      RRT_CUDA(rrt::launch_crmsa_combine_bwd(x_last, w->cr_norm_w, w->cr_norm_b, w->cr_phi, tp.logits,
+                                             tp.rstat, tp.lm, b.dz, &b.amax[0], b.dw, b.rgrad, b.dh,
+                                             dh_weight, out, gr->cr_phi, gr->cr_norm_w, gr->cr_norm_b,
+                                             &b.amax[1], gc, D, k, st), "crmsa combine backward"); }
+    g = out;
+    am = 1;
+  } else {
+    if (!gr->norm_w || !gr->norm_b) return fail(RRT_E_INVALID, "NULL gradient buffer");
+    ident.L = (int)L; ident.Np = (int)L;
+    StageScope s_(kStBwdLn, st);
+    RRT_CUDA(rrt::launch_ln_backward(x_last, x0, w->norm_w, dout, false, nullptr, nullptr, nullptr,
+                                     b.dh, gr->norm_w, gr->norm_b, &b.amax[1], ident, D, st),
+             "final norm backward");
+    g = b.dh;
+    am = 1;
+  }
+  if (nl == 0) return RRT_OK;
+  rrt::Grid gg{};
+  if (!make_grid(L, c->region_num, c->region_size, c->min_region_num, c->min_region_ratio, &gg))
+    return fail(RRT_E_INVALID, "bad geometry");
+  for (int i = nl - 1; i >= 0; --i) {
+    const rrt_attn_grads* ga = &gr->layer_attn[i];
+    if (!gr->layer_norm_w[i] || !gr->layer_norm_b[i] || !ga->qkv_w || !ga->proj_w || !ga->proj_b ||
+        (c->qkv_bias && !ga->qkv_b) || (c->epeg && !ga->pe_w))
+      return fail(RRT_E_INVALID, "NULL gradient buffer");
+    const float* x_in = i > 0 ? tp.xs[i - 1] : x;
+    { StageScope s_(kStBwdPrep, st);
+      RRT_CUDA(rrt::launch_grad_partition(g, gg, gg.Np, D, &b.amax[am], b.dy, b.dyT, ga->proj_b, st),
+               "gradient partition"); }
+    int rc = attention_module_backward(c, &w->layer_attn[i], ga, tp.z[i], tp.qkv[i], tp.o[i], gg.R, gg.P,
+                                       c->n_heads, c->epeg != 0, &b.amax[am], b, st);
+    if (rc) return rc;
+    float* out = i == 0 ? dx : (g == b.ga ? b.gb : b.ga);
+    { StageScope s_(kStBwdLn, st);
+      RRT_CUDA(rrt::launch_ln_backward(x_in, nullptr, w->layer_norm_w[i], b.dz, true, &b.amax[am], g,
+                                       (i == 0 && c->all_shortcut) ? b.dh : nullptr, out,
+                                       gr->layer_norm_w[i], gr->layer_norm_b[i], &b.amax[am + 1], gg, D,
+                                       st), "layer norm backward"); }
+    g = out;
+    ++am;
+  }
+  return RRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+RRT_API int rrt_train_tape_bytes(const rrt_config* cfg, int64_t L, size_t* bytes) {
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (!bytes) return fail(RRT_E_INVALID, "NULL output");
+  Workspace ws{};
+  if (!carve(cfg, L, nullptr, &ws, true)) return fail(RRT_E_INVALID, "bad bag length / geometry");
+  *bytes = ws.bytes;
+  return RRT_OK;
+}
+
+RRT_API int rrt_encoder_forward_train(const rrt_config* cfg, const rrt_weights* w, const float* x,
+                                      float* out, int64_t L, void* tape, size_t tape_bytes,
+                                      void* stream) {
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (!w || !x || !out || x == out) return fail(RRT_E_INVALID, "bad pointer");
+  Workspace ws{};
+  if (!carve(cfg, L, tape, &ws, true)) return fail(RRT_E_INVALID, "bad bag length / geometry");
+  if (!tape || tape_bytes < ws.bytes) return fail(RRT_E_WORKSPACE, "tape too small");
+  if (((uintptr_t)tape) & 255) return fail(RRT_E_INVALID, "tape must be 256-byte aligned");
+  return encoder_forward(cfg, w, x, out, L, ws, (cudaStream_t)stream);
+}
+
+RRT_API int rrt_backward_workspace_bytes(const rrt_config* cfg, int64_t L, size_t* bytes) {
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (!bytes) return fail(RRT_E_INVALID, "NULL output");
+  BwdWorkspace b{};
+  if (!carve_bwd(cfg, L, nullptr, &b)) return fail(RRT_E_INVALID, "bad bag length / geometry");
+  *bytes = b.bytes;
+  return RRT_OK;
+}
+
+RRT_API int rrt_encoder_backward(const rrt_config* cfg, const rrt_weights* w, const float* x,
+                                 const float* dout, int64_t L, const void* tape, size_t tape_bytes,
+                                 const rrt_grads* grads, float* dx, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (!w || !x || !dout || !grads || !dx || dx == dout) return fail(RRT_E_INVALID, "bad pointer");
+  rc = check_backward_support(cfg, L);
+  if (rc) return rc;
+  Workspace tp{};
+  if (!carve(cfg, L, const_cast<void*>(tape), &tp, true)) return fail(RRT_E_INVALID, "bad geometry");
+  if (!tape || tape_bytes < tp.bytes) return fail(RRT_E_WORKSPACE, "tape too small");
+  BwdWorkspace b{};
+  if (!carve_bwd(cfg, L, workspace, &b)) return fail(RRT_E_INVALID, "bad geometry");
+  if (!workspace || workspace_bytes < b.bytes) return fail(RRT_E_WORKSPACE, "workspace too small");
+  if ((((uintptr_t)workspace) | ((uintptr_t)tape)) & 255)
+    return fail(RRT_E_INVALID, "tape and workspace must be 256-byte aligned");
+  return encoder_backward(cfg, w, x, dout, L, tp, grads, dx, b, (cudaStream_t)stream);
+}
+
+RRT_API int rrt_attention_backward(const void* qkv, const void* o, const void* d_o, const float* taps,
+                                   void* d_qkv, float* d_taps, int32_t R, int32_t P, int32_t dim,
+                                   int32_t heads, int32_t epeg_k, void* stream) {
+  if (!qkv || !o || !d_o || !d_qkv || R < 1) return fail(RRT_E_INVALID, "bad argument");
+  if (!taps) epeg_k = 1;
+  if (heads < 1 || dim % heads || !rrt::rmsa_attention_bwd_supported(P, dim, heads, epeg_k) ||
+      (taps && epeg_k % 2 == 0))
+    return fail(RRT_E_INVALID, "attention backward: P <= 256, head_dim 32 or 64, odd epeg_k <= 63");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  RRT_CUDA(rrt::launch_rmsa_attention_bwd((const __half*)qkv, (const __half*)o, (const __half*)d_o,
+                                          taps, (__half*)d_qkv, taps ? d_taps : nullptr, nullptr, R, P,
+                                          dim, heads, epeg_k, (cudaStream_t)stream),
+           "attention backward");
+  return RRT_OK;
+}
+
+RRT_API int rrt_layernorm_backward(const float* x, const float* gamma, const float* dy, float* dx,
+                                   float* dgamma, float* dbeta, int64_t L, int32_t dim, void* stream) {
+  if (!x || !gamma || !dy || !dx || L < 0 || L > (1 << 28) || dim % 128)
+    return fail(RRT_E_INVALID, "bad argument");
+  rrt::Grid ident{};
+  ident.L = (int)L; ident.Np = (int)L;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  RRT_CUDA(rrt::launch_ln_backward(x, nullptr, gamma, dy, false, nullptr, nullptr, nullptr, dx, dgamma,
+                                   dbeta, nullptr, ident, dim, (cudaStream_t)stream),
+           "layernorm backward");
   return RRT_OK;
 }
 

@@ -1,0 +1,411 @@
+// Backward of the CR-MSA block (+ the encoder's final LayerNorm), fp32 streaming kernels around the
+// landmark-MHA backward (which reuses the GEMM and attention-backward kernels on k*64 rows).
+// Autograd of modules/rmsa.py:290-337 in the rank-k form the forward kernels use:
+//   l[p,n]  = z[p,:] . phi[:,n]                z = LN_cr(x1) (0 on pad slots)
+//   cw      = softmax_p(l)      L[n,:]  = sum_p cw[p,n] z[p,:]          (combine)
+//   dp      = softmax_n(l)      mm[p,n] = (l - lo_n) / (hi_n - lo_n + 1e-8)
+//   y[p,:]  = sum_n dp*mm * L'[n,:]            L' = MHA(L)               (dispatch)
+//   out     = LN_f(x1 + y (+ x0))
+// Two token-parallel passes with the per-region reductions between them:
+//   crmsa_dispatch_bwd_kernel  dh = LN_f backward, dw[p,n] = dh . L'_n, dL'[n,:] += w dh,
+//                              d lo_n / d hi_n partial sums, final-norm gamma/beta gradients
+//   (landmark MHA backward:    dL' -> dL)
+//   crmsa_combine_bwd_kernel   dl (three paths), dz, dphi, LN_cr backward -> dx1 = dh + ...
+// torch.min/max(dim) send their gradient to ONE arg-min/max element; here every element equal to the
+// extremum receives it.  Ties only occur among zero pad slots, whose logit gradient is discarded.
+#include "backward.cuh"
+#include "kernels.cuh"
+
+namespace rrt {
+namespace {
+
+template <int V>
+__device__ __forceinline__ void load_row(float4 (&v)[V], const float* row, int lane) {
+#pragma unroll
+  for (int i = 0; i < V; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(row) + lane + 32 * i);
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b) {
+  return (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w);
+}
+__device__ __forceinline__ void axpy4(float4& y, float a, float4 x) {
+  y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z); y.w = fmaf(a, x.w, y.w);
+}
+
+// CTA-wide sum of per-lane column partials part[V] (columns 4*(lane+32i)..+3) over the 8 warps, then
+// one atomicAdd per column: dst[c * stride] += sum.  `red` is [8][D] shared floats.
+template <int V>
+__device__ __forceinline__ void cta_colsum_atomic(const float4 (&part)[V], float* red, float* dst,
+                                                  int stride, int warp, int lane) {
+  constexpr int D = 128 * V;
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+    *reinterpret_cast<float4*>(red + warp * D + 4 * (lane + 32 * i)) = part[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w * D + c];
+    if (s != 0.f) atomicAdd(dst + (size_t)c * stride, s);
+  }
+  __syncthreads();
+}
+
+// grid (R, chunks), 256 threads; smem: Ls[KMAX][D] | red[8][D]
+template <int V, int KMAX>
+__global__ void __launch_bounds__(256) crmsa_dispatch_bwd_kernel(
+    const float* __restrict__ x1, const float* __restrict__ x0, const float* __restrict__ logits,
+    const float2* __restrict__ rstat, const float* __restrict__ lmp, const float* __restrict__ gamma_f,
+    const float* __restrict__ dout, float* __restrict__ dh, float* __restrict__ dw,
+    float* __restrict__ dLp, float2* __restrict__ rgrad, float* __restrict__ dgamma_f,
+    float* __restrict__ dbeta_f, Grid grid, int k, int tpc) {
+  constexpr int D = 128 * V;
+  extern __shared__ __align__(16) float smem[];
+  float* Ls = smem;
+  float* red = Ls + KMAX * D;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rho = blockIdx.x, P = grid.P;
+  for (int i = tid; i < k * (D / 4); i += 256) {
+    int n = i / (D / 4), c4 = i - n * (D / 4);
+    reinterpret_cast<float4*>(Ls + n * D)[c4] =
+        __ldg(reinterpret_cast<const float4*>(lmp + ((size_t)n * grid.R + rho) * D) + c4);
+  }
+  __syncthreads();
+
+  float4 acc[KMAX][V], dg[V], db[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int n = 0; n < KMAX; ++n) acc[n][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float my_dlo = 0.f, my_dhi = 0.f;
+  const float2 mm = lane < k ? __ldg(rstat + (size_t)rho * k + lane) : make_float2(0.f, 1.f);
+  const float rng = mm.y - mm.x + 1e-8f;
+  int p_end = (blockIdx.y + 1) * tpc;
+  if (p_end > P) p_end = P;
+  for (int p = blockIdx.y * tpc + warp; p < p_end; p += 8) {
+    const int slot = rho * P + p;
+    const int tok = grid.slot_to_token(slot);
+    if (tok >= grid.L) continue;
+    float4 v[V], d[V];
+    load_row<V>(v, x1 + (size_t)tok * D, lane);
+    load_row<V>(d, dout + (size_t)tok * D, lane);
+    if (x0) {
+      float4 u[V];
+      load_row<V>(u, x0 + (size_t)tok * D, lane);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { v[i].x += u[i].x; v[i].y += u[i].y; v[i].z += u[i].z; v[i].w += u[i].w; }
+    }
+    const float lg = lane < k ? __ldg(logits + (size_t)slot * k + lane) : -INFINITY;
+    const float mx = warp_max(lg);
+    const float ex = lane < k ? __expf(lg - mx) : 0.f;
+    const float dpn = ex / warp_sum(ex);
+    const float mmn = lane < k ? (lg - mm.x) / rng : 0.f;
+    const float my_w = dpn * mmn;
+#pragma unroll
+    for (int n = 0; n < KMAX; ++n) {
+      if (n < k) {
+        const float w = __shfl_sync(0xffffffffu, my_w, n);
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+          axpy4(v[i], w, *reinterpret_cast<const float4*>(Ls + n * D + 4 * (lane + 32 * i)));
+      }
+    }
+    if (gamma_f) {  // backward of out = LN_f(h), v = h
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      const float mean = warp_sum(s) * (1.f / D);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += dot4(v[i], v[i]);
+      }
+      const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + kLnEps);
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
+        dg[i].x = fmaf(d[i].x, v[i].x, dg[i].x); dg[i].y = fmaf(d[i].y, v[i].y, dg[i].y);
+        dg[i].z = fmaf(d[i].z, v[i].z, dg[i].z); dg[i].w = fmaf(d[i].w, v[i].w, dg[i].w);
+        db[i].x += d[i].x; db[i].y += d[i].y; db[i].z += d[i].z; db[i].w += d[i].w;
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma_f) + lane + 32 * i);
+        d[i].x *= gm.x; d[i].y *= gm.y; d[i].z *= gm.z; d[i].w *= gm.w;
+        m1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+        m2 += dot4(d[i], v[i]);
+      }
+      m1 = warp_sum(m1) * (1.f / D);
+      m2 = warp_sum(m2) * (1.f / D);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        d[i].x = rstd * (d[i].x - m1 - v[i].x * m2); d[i].y = rstd * (d[i].y - m1 - v[i].y * m2);
+        d[i].z = rstd * (d[i].z - m1 - v[i].z * m2); d[i].w = rstd * (d[i].w - m1 - v[i].w * m2);
+      }
+    }
+    // d = dh
+#pragma unroll
+    for (int i = 0; i < V; ++i) reinterpret_cast<float4*>(dh + (size_t)tok * D)[lane + 32 * i] = d[i];
+    float my_dw = 0.f;
+#pragma unroll
+    for (int n = 0; n < KMAX; ++n) {
+      if (n < k) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+          s += dot4(d[i], *reinterpret_cast<const float4*>(Ls + n * D + 4 * (lane + 32 * i)));
+        s = warp_sum(s);
+        if (lane == n) my_dw = s;
+        const float w = __shfl_sync(0xffffffffu, my_w, n);
+#pragma unroll
+        for (int i = 0; i < V; ++i) axpy4(acc[n][i], w, d[i]);
+      }
+    }
+    if (lane < k) {
+      dw[(size_t)slot * k + lane] = my_dw;
+      const float dmm = my_dw * dpn;
+      my_dlo += dmm * (mmn - 1.f) / rng;
+      my_dhi -= dmm * mmn / rng;
+    }
+  }
+  if (lane < k) {
+    if (my_dlo != 0.f) atomicAdd(&rgrad[(size_t)rho * k + lane].x, my_dlo);
+    if (my_dhi != 0.f) atomicAdd(&rgrad[(size_t)rho * k + lane].y, my_dhi);
+  }
+#pragma unroll
+  for (int n = 0; n < KMAX; ++n)
+    if (n < k) cta_colsum_atomic<V>(acc[n], red, dLp + ((size_t)n * grid.R + rho) * D, 1, warp, lane);
+  if (gamma_f) {
+    cta_colsum_atomic<V>(dg, red, dgamma_f, 1, warp, lane);
+    cta_colsum_atomic<V>(db, red, dbeta_f, 1, warp, lane);
+  }
+}
+
+// grid (R, chunks), 256 threads; smem: dLs[KMAX][D] | Ph[KMAX][D] | red[8][D] | rs[4][KMAX]
+template <int V, int KMAX>
+__global__ void __launch_bounds__(256) crmsa_combine_bwd_kernel(
+    const float* __restrict__ x1, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ phi, const float* __restrict__ logits, const float2* __restrict__ rstat,
+    const __half* __restrict__ lm16, const __half* __restrict__ dlm16,
+    const uint32_t* __restrict__ amax_l, const float* __restrict__ dw, const float2* __restrict__ rgrad,
+    const float* __restrict__ dh, float dh_weight, float* __restrict__ dx1, float* __restrict__ dphi,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, uint32_t* __restrict__ amax_out, Grid grid,
+    int k, int tpc) {
+  constexpr int D = 128 * V;
+  extern __shared__ __align__(16) float smem[];
+  float* dLs = smem;              // unscaled dL rows of this region
+  float* Ph = dLs + KMAX * D;     // phi^T
+  float* red = Ph + KMAX * D;     // [8][D]
+  float* rs = red + 8 * D;        // [0]: softmax_p max, [1]: 1/sum, [2]: c_n = dL_n . L_n
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rho = blockIdx.x, P = grid.P;
+  const float inv_s = amax_l ? grad_inv_scale(__ldg(amax_l)) : 1.f;
+  for (int i = tid; i < k * D; i += 256) {
+    int n = i / D, c = i - n * D;
+    dLs[i] = __half2float(dlm16[((size_t)n * grid.R + rho) * D + c]) * inv_s;
+    Ph[i] = __ldg(phi + (size_t)c * k + n);
+  }
+  __syncthreads();
+  for (int n = warp; n < k; n += 8) {
+    float mx = -INFINITY;
+    for (int p = lane; p < P; p += 32) mx = fmaxf(mx, __ldg(logits + ((size_t)rho * P + p) * k + n));
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int p = lane; p < P; p += 32) sum += __expf(__ldg(logits + ((size_t)rho * P + p) * k + n) - mx);
+    sum = warp_sum(sum);
+    float c = 0.f;
+    for (int j = lane; j < D; j += 32)
+      c = fmaf(dLs[n * D + j], __half2float(lm16[((size_t)n * grid.R + rho) * D + j]), c);
+    c = warp_sum(c);
+    if (lane == 0) { rs[n] = mx; rs[KMAX + n] = 1.f / sum; rs[2 * KMAX + n] = c; }
+  }
+  __syncthreads();
+
+  float4 aphi[KMAX][V], dg[V], db[V], gm[V], bt[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    bt[i] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+#pragma unroll
+    for (int n = 0; n < KMAX; ++n) aphi[n][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float2 mm = lane < k ? __ldg(rstat + (size_t)rho * k + lane) : make_float2(0.f, 1.f);
+  const float2 rg = lane < k ? __ldg(rgrad + (size_t)rho * k + lane) : make_float2(0.f, 0.f);
+  const float rng = mm.y - mm.x + 1e-8f;
+  const float pmx = lane < k ? rs[lane] : 0.f, pinv = lane < k ? rs[KMAX + lane] : 0.f;
+  const float cn = lane < k ? rs[2 * KMAX + lane] : 0.f;
+  float amax = 0.f;
+  int p_end = (blockIdx.y + 1) * tpc;
+  if (p_end > P) p_end = P;
+  for (int p = blockIdx.y * tpc + warp; p < p_end; p += 8) {
+    const int slot = rho * P + p;
+    const int tok = grid.slot_to_token(slot);
+    if (tok >= grid.L) continue;
+    float4 zh[V], z[V];
+    load_row<V>(zh, x1 + (size_t)tok * D, lane);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += (zh[i].x + zh[i].y) + (zh[i].z + zh[i].w);
+    const float mean = warp_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      zh[i].x -= mean; zh[i].y -= mean; zh[i].z -= mean; zh[i].w -= mean;
+      q += dot4(zh[i], zh[i]);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + kLnEps);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      zh[i].x *= rstd; zh[i].y *= rstd; zh[i].z *= rstd; zh[i].w *= rstd;
+      z[i].x = fmaf(zh[i].x, gm[i].x, bt[i].x); z[i].y = fmaf(zh[i].y, gm[i].y, bt[i].y);
+      z[i].z = fmaf(zh[i].z, gm[i].z, bt[i].z); z[i].w = fmaf(zh[i].w, gm[i].w, bt[i].w);
+    }
+    const float lg = lane < k ? __ldg(logits + (size_t)slot * k + lane) : -INFINITY;
+    const float cw = lane < k ? __expf(lg - pmx) * pinv : 0.f;
+    const float mxk = warp_max(lg);
+    const float ex = lane < k ? __expf(lg - mxk) : 0.f;
+    const float dpn = ex / warp_sum(ex);
+    const float mmn = lane < k ? (lg - mm.x) / rng : 0.f;
+    const float dwn = lane < k ? __ldg(dw + (size_t)slot * k + lane) : 0.f;
+    const float ddp = dwn * mmn, dmm = dwn * dpn;
+    const float sdp = warp_sum(dpn * ddp);
+    float dcw = 0.f;
+#pragma unroll
+    for (int n = 0; n < KMAX; ++n) {
+      if (n < k) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+          t += dot4(z[i], *reinterpret_cast<const float4*>(dLs + n * D + 4 * (lane + 32 * i)));
+        t = warp_sum(t);
+        if (lane == n) dcw = t;
+      }
+    }
+    float dl = 0.f;
+    if (lane < k) {
+      dl = cw * (dcw - cn) + dpn * (ddp - sdp) + dmm / rng;
+      if (lg == mm.x) dl += rg.x;
+      if (lg == mm.y) dl += rg.y;
+    }
+    float4 dz[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) dz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int n = 0; n < KMAX; ++n) {
+      if (n < k) {
+        const float cwn = __shfl_sync(0xffffffffu, cw, n), dln = __shfl_sync(0xffffffffu, dl, n);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          axpy4(dz[i], cwn, *reinterpret_cast<const float4*>(dLs + n * D + 4 * (lane + 32 * i)));
+          axpy4(dz[i], dln, *reinterpret_cast<const float4*>(Ph + n * D + 4 * (lane + 32 * i)));
+          axpy4(aphi[n][i], dln, z[i]);
+        }
+      }
+    }
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      dg[i].x = fmaf(dz[i].x, zh[i].x, dg[i].x); dg[i].y = fmaf(dz[i].y, zh[i].y, dg[i].y);
+      dg[i].z = fmaf(dz[i].z, zh[i].z, dg[i].z); dg[i].w = fmaf(dz[i].w, zh[i].w, dg[i].w);
+      db[i].x += dz[i].x; db[i].y += dz[i].y; db[i].z += dz[i].z; db[i].w += dz[i].w;
+      dz[i].x *= gm[i].x; dz[i].y *= gm[i].y; dz[i].z *= gm[i].z; dz[i].w *= gm[i].w;
+      m1 += (dz[i].x + dz[i].y) + (dz[i].z + dz[i].w);
+      m2 += dot4(dz[i], zh[i]);
+    }
+    m1 = warp_sum(m1) * (1.f / D);
+    m2 = warp_sum(m2) * (1.f / D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(dh + (size_t)tok * D) + lane + 32 * i);
+      float4 o;
+      o.x = fmaf(dh_weight, r.x, rstd * (dz[i].x - m1 - zh[i].x * m2));
+      o.y = fmaf(dh_weight, r.y, rstd * (dz[i].y - m1 - zh[i].y * m2));
+      o.z = fmaf(dh_weight, r.z, rstd * (dz[i].z - m1 - zh[i].z * m2));
+      o.w = fmaf(dh_weight, r.w, rstd * (dz[i].w - m1 - zh[i].w * m2));
+      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+      reinterpret_cast<float4*>(dx1 + (size_t)tok * D)[lane + 32 * i] = o;
+    }
+  }
+  if (amax_out) {
+    amax = warp_max(amax);
+    if (lane == 0 && amax > 0.f) atomic_amax(amax_out, amax);
+  }
+#pragma unroll
+  for (int n = 0; n < KMAX; ++n)
+    if (n < k) cta_colsum_atomic<V>(aphi[n], red, dphi + n, k, warp, lane);
+  cta_colsum_atomic<V>(dg, red, dgamma, 1, warp, lane);
+  cta_colsum_atomic<V>(db, red, dbeta, 1, warp, lane);
+}
+
+int token_chunks(const Grid& g) {
+  int chunks = (2 * 148 + g.R - 1) / g.R;
+  if (chunks > (g.P + 7) / 8) chunks = (g.P + 7) / 8;
+  return chunks < 1 ? 1 : chunks;
+}
+
+#define RRT_CRB_DISPATCH(D, k, ...)                                                  \
+  switch ((D) / 128) {                                                               \
+    case 1: { constexpr int V = 1; if ((k) <= 4) { constexpr int KM = 4; __VA_ARGS__; } else { constexpr int KM = 8; __VA_ARGS__; } break; } \
+    case 2: { constexpr int V = 2; if ((k) <= 4) { constexpr int KM = 4; __VA_ARGS__; } else { constexpr int KM = 8; __VA_ARGS__; } break; } \
+    case 4: { constexpr int V = 4; if ((k) <= 4) { constexpr int KM = 4; __VA_ARGS__; } else { constexpr int KM = 8; __VA_ARGS__; } break; } \
+    case 8: { constexpr int V = 8; if ((k) <= 4) { constexpr int KM = 4; __VA_ARGS__; } else { constexpr int KM = 8; __VA_ARGS__; } break; } \
+    default: return cudaErrorInvalidValue;                                           \
+  }
+
+template <typename K>
+cudaError_t set_smem(K kern, size_t bytes) {
+  return bytes > 48 * 1024
+             ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
+             : cudaSuccess;
+}
+
+}  // namespace
+
+bool crmsa_backward_supported(int D, int k) {
+  return (D == 128 || D == 256 || D == 512 || D == 1024) && k >= 1 && k <= 8;
+}
+
+cudaError_t launch_crmsa_dispatch_bwd(const float* x1, const float* x0, const float* logits,
+                                      const float2* rstat, const float* lmp, const float* gamma_f,
+                                      const float* dout, float* dh, float* dw, float* dLp,
+                                      float2* rgrad, float* dgamma_f, float* dbeta_f, const Grid& grid,
+                                      int D, int k, cudaStream_t stream) {
+  if (!crmsa_backward_supported(D, k)) return cudaErrorInvalidValue;
+  const int chunks = token_chunks(grid), tpc = (grid.P + chunks - 1) / chunks;
+  dim3 gr(grid.R, chunks);
+  RRT_CRB_DISPATCH(D, k, {
+    size_t smem = (size_t)(KM + 8) * D * sizeof(float);
+    auto kern = crmsa_dispatch_bwd_kernel<V, KM>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<gr, 256, smem, stream>>>(x1, x0, logits, rstat, lmp, gamma_f, dout, dh, dw, dLp, rgrad,
+                                    dgamma_f, dbeta_f, grid, k, tpc);
+  });
+  return cudaGetLastError();
+}
+
+cudaError_t launch_crmsa_combine_bwd(const float* x1, const float* gamma, const float* beta,
+                                     const float* phi, const float* logits, const float2* rstat,
+                                     const __half* lm16, const __half* dlm16, const uint32_t* amax_l,
+                                     const float* dw, const float2* rgrad, const float* dh,
+                                     float dh_weight, float* dx1, float* dphi, float* dgamma,
+                                     float* dbeta, uint32_t* amax_out, const Grid& grid, int D, int k,
+                                     cudaStream_t stream) {
+  if (!crmsa_backward_supported(D, k)) return cudaErrorInvalidValue;
+  const int chunks = token_chunks(grid), tpc = (grid.P + chunks - 1) / chunks;
+  dim3 gr(grid.R, chunks);
+  RRT_CRB_DISPATCH(D, k, {
+    size_t smem = ((size_t)(2 * KM + 8) * D + 4 * KM) * sizeof(float);
+    auto kern = crmsa_combine_bwd_kernel<V, KM>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<gr, 256, smem, stream>>>(x1, gamma, beta, phi, logits, rstat, lm16, dlm16, amax_l, dw, rgrad,
+                                    dh, dh_weight, dx1, dphi, dgamma, dbeta, amax_out, grid, k, tpc);
+  });
+  return cudaGetLastError();
+}
+
+}  // namespace rrt

@@ -120,4 +120,43 @@ cudaError_t launch_attn_pool(const float* h, const float* hidden, const float* w
                              float* pooled, float* logits, float* attn, int attn_raw, int L, int D,
                              int hid, cudaStream_t stream);
 
+// ---- backward pass (backward.cu, rmsa_attn_bwd.cu, crmsa_bwd.cu; conventions in backward.cuh) ----
+// amax words: IEEE bits of max|g| of a stage's fp32 input gradient (zero-initialised, atomicMax);
+// consumers derive the power-of-two fp16 scale S from them.
+cudaError_t launch_amax(const float* x, size_t n, uint32_t* amax, cudaStream_t stream);
+// g: fp32 [grid.L, C] token order -> rows: fp16 [M, C] slot order, * S(amax), pad slots 0 (grid.H == 0:
+// identity, M == grid.L); rowsT: fp16 [C, M64] transpose; colsum[c] += sum of the unscaled column
+cudaError_t launch_grad_partition(const float* g, const Grid& grid, int M, int C, const uint32_t* amax,
+                                  __half* rows, __half* rowsT, float* colsum, cudaStream_t stream);
+// in: fp16 [M, C] -> outT fp16 [C, M64] (columns >= M zero); colsum[c] += column sum * 1/S(amax)
+cudaError_t launch_transpose_f16(const __half* in, int M, int C, __half* outT, float* colsum,
+                                 const uint32_t* amax, cudaStream_t stream);
+// LayerNorm backward of y = LN(x (+ x_add)); dz fp16 slot-order scaled (dz_f16) or fp32 token order
+cudaError_t launch_ln_backward(const float* x, const float* x_add, const float* gamma, const void* dz,
+                               bool dz_f16, const uint32_t* amax_in, const float* dres,
+                               const float* dres2, float* dx, float* dgamma, float* dbeta,
+                               uint32_t* amax_out, const Grid& grid, int D, cudaStream_t stream);
+cudaError_t launch_wt_convert(const float* w, __half* wT, int N, int K, cudaStream_t stream);
+cudaError_t launch_scale_by_inv(float* x, size_t n, const uint32_t* amax, cudaStream_t stream);
+// attention core backward: qkv/o as written by the forward, dO fp16 [R*P, D] (scaled) ->
+// dqkv fp16 [R*P, 3D] (scaled), dtaps[heads, epeg_k] += unscaled tap gradients (taps may be null)
+bool rmsa_attention_bwd_supported(int P, int D, int heads, int epeg_k);
+cudaError_t launch_rmsa_attention_bwd(const __half* qkv, const __half* o, const __half* dO,
+                                      const float* taps, __half* dqkv, float* dtaps,
+                                      const uint32_t* amax, int R, int P, int D, int heads, int epeg_k,
+                                      cudaStream_t stream);
+bool crmsa_backward_supported(int D, int k);
+cudaError_t launch_crmsa_dispatch_bwd(const float* x1, const float* x0, const float* logits,
+                                      const float2* rstat, const float* lmp, const float* gamma_f,
+                                      const float* dout, float* dh, float* dw, float* dLp,
+                                      float2* rgrad, float* dgamma_f, float* dbeta_f, const Grid& grid,
+                                      int D, int k, cudaStream_t stream);
+cudaError_t launch_crmsa_combine_bwd(const float* x1, const float* gamma, const float* beta,
+                                     const float* phi, const float* logits, const float2* rstat,
+                                     const __half* lm16, const __half* dlm16, const uint32_t* amax_l,
+                                     const float* dw, const float2* rgrad, const float* dh,
+                                     float dh_weight, float* dx1, float* dphi, float* dgamma,
+                                     float* dbeta, uint32_t* amax_out, const Grid& grid, int D, int k,
+                                     cudaStream_t stream);
+
 }  // namespace rrt

@@ -10,33 +10,13 @@
 // fp16 operands carry the same 10-bit mantissa as tf32; softmax state and accumulators are fp32.
 // (modules/rmsa.py:103-122; SURVEY.md 0.2-1 for the EPEG-on-Q identity.)
 #include "kernels.cuh"
+#include "mma_f16.cuh"
 
 namespace rrt {
 long long* g_attn_trace = nullptr;  // debug: clock64 stamps of CTA 0..7 (tools/attn_trace.py)
 namespace {
 __device__ __forceinline__ void astamp(long long* tr, int slot) {
   if (tr && blockIdx.x < 8 && blockIdx.y == 0 && threadIdx.x == 0) tr[blockIdx.x * 8 + slot] = clock64();
-}
-
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
-  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(a));
-}
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
-  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(a));
-}
-__device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
-                                                uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-      "{%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // HD: head dim; NT: 8-key n-tiles per KV tile (6 -> 48 keys, 8 -> 64 keys); MAXW: warps per CTA cap

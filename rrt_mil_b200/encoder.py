@@ -83,6 +83,59 @@ class TransLayer(_ParamHolder):
         self.attn = attn_module
 
 
+class _EncoderFunction(torch.autograd.Function):
+    """Autograd bridge: forward with a tape (``rrt_encoder_forward_train``), backward through
+    ``rrt_encoder_backward``.  Parameters travel as explicit inputs so that autograd routes their
+    gradients; all arithmetic stays in the library."""
+
+    @staticmethod
+    def forward(ctx, enc, x, *params):
+        lib, cfg, N = cabi.lib(), enc._cfg, x.shape[0]
+        with torch.cuda.device(x.device):
+            n = C.c_size_t()
+            cabi.check(lib.rrt_train_tape_bytes(C.byref(cfg), N, C.byref(n)), "rrt_train_tape_bytes")
+            tape = torch.empty(n.value, dtype=torch.uint8, device=x.device)
+            out = torch.empty_like(x)
+            w = enc._weights(x.device)
+            rc = lib.rrt_encoder_forward_train(C.byref(cfg), C.byref(w), x.data_ptr(), out.data_ptr(), N,
+                                               tape.data_ptr(), n.value,
+                                               torch.cuda.current_stream(x.device).cuda_stream)
+        cabi.check(rc, "rrt_encoder_forward_train")
+        ctx.enc = enc
+        ctx.save_for_backward(x, tape, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        enc = ctx.enc
+        x, tape, *params = ctx.saved_tensors
+        lib, cfg, N = cabi.lib(), enc._cfg, x.shape[0]
+        dout = dout.contiguous().float()
+        names = [n for n, _ in enc.named_parameters()]
+        # one zero-initialised flat buffer for every parameter gradient (64-float aligned views)
+        offs, total = [], 0
+        for p_ in params:
+            offs.append(total)
+            total += (p_.numel() + 63) // 64 * 64
+        with torch.cuda.device(x.device):
+            flat = torch.zeros(total, dtype=torch.float32, device=x.device)
+            views = [flat[o:o + p_.numel()].view(p_.shape) for o, p_ in zip(offs, params)]
+            g = enc._grads(dict(zip(names, views)))
+            n = C.c_size_t()
+            cabi.check(lib.rrt_backward_workspace_bytes(C.byref(cfg), N, C.byref(n)),
+                       "rrt_backward_workspace_bytes")
+            ws = torch.empty(n.value, dtype=torch.uint8, device=x.device)
+            dx = torch.empty_like(x)
+            w = enc._weights(x.device)
+            rc = lib.rrt_encoder_backward(C.byref(cfg), C.byref(w), x.data_ptr(), dout.data_ptr(), N,
+                                          tape.data_ptr(), tape.numel(), C.byref(g), dx.data_ptr(),
+                                          ws.data_ptr(), n.value,
+                                          torch.cuda.current_stream(x.device).cuda_stream)
+        cabi.check(rc, "rrt_encoder_backward")
+        grads = [v if p_.requires_grad else None for v, p_ in zip(views, params)]
+        return (None, dx if ctx.needs_input_grad[1] else None, *grads)
+
+
 class RRTEncoder(nn.Module):
     def __init__(self, mlp_dim=512, pos_pos=0, pos='none', peg_k=7, attn='rmsa', region_num=8,
                  drop_out=0.1, n_layers=2, n_heads=8, drop_path=0., ffn=False, ffn_act='gelu',
@@ -209,29 +262,59 @@ class RRTEncoder(nn.Module):
             self._attn_weights(cr.attn.attn, w.cr_attn, device, shadows=True)
         return w
 
-    def _check_mode(self, x):
+    def _grads(self, by_name) -> cabi.RrtGrads:
+        """``rrt_grads`` over gradient buffers keyed by parameter name (``named_parameters``)."""
+        g = cabi.RrtGrads()
+
+        def ptr(name):
+            t = by_name.get(name)
+            return t.data_ptr() if t is not None else None
+
+        def attn(prefix, dst):
+            dst.qkv_w, dst.qkv_b = ptr(prefix + "qkv.weight"), ptr(prefix + "qkv.bias")
+            dst.proj_w, dst.proj_b = ptr(prefix + "proj.weight"), ptr(prefix + "proj.bias")
+            dst.pe_w = ptr(prefix + "pe.weight")   # pe.bias: exactly zero gradient, never written
+
+        g.norm_w, g.norm_b = ptr("norm.weight"), ptr("norm.bias")
+        for i in range(len(self.layers)):
+            g.layer_norm_w[i], g.layer_norm_b[i] = ptr(f"layers.{i}.norm.weight"), ptr(f"layers.{i}.norm.bias")
+            attn(f"layers.{i}.attn.attn.", g.layer_attn[i])
+        if self._cfg.cr_msa:
+            g.cr_norm_w, g.cr_norm_b = ptr("cr_msa.norm.weight"), ptr("cr_msa.norm.bias")
+            g.cr_phi = ptr("cr_msa.attn.phi")
+            attn("cr_msa.attn.attn.", g.cr_attn)
+        return g
+
+    def _needs_grad(self, x) -> bool:
+        return torch.is_grad_enabled() and (
+            x.requires_grad or any(p.requires_grad for p in self.parameters()))
+
+    def _check_mode(self, x, allow_grad=False):
         if not x.is_cuda:
             raise RuntimeError("RRTEncoder (rrt_mil_b200) runs on CUDA only; there is no CPU fallback")
         if x.dtype != torch.float32:
             raise NotImplementedError(f"input dtype {x.dtype}: only float32 bags are supported")
-        needs_grad = torch.is_grad_enabled() and (
-            x.requires_grad or any(p.requires_grad for p in self.parameters()))
-        if needs_grad:
-            raise NotImplementedError(
-                "backward kernels are not built yet: call under torch.no_grad() / inference_mode()")
+        if self._needs_grad(x):
+            if not allow_grad:
+                raise NotImplementedError("forward_bags is inference-only: call it under "
+                                          "torch.no_grad(), or use forward() for autograd")
+            if self._crmsa_mlp:
+                raise NotImplementedError("backward through crmsa_mlp=True is not built")
         if self.training and (self.drop_out > 0 or self.drop_path_rate > 0):
             raise NotImplementedError("training-mode dropout / drop_path is not built: use .eval() "
                                       "or drop_out=0")
 
     def forward_bag(self, x: torch.Tensor) -> torch.Tensor:
         """One bag ``[N, D]`` float32 CUDA -> ``[N, D]``; enqueues on the current stream."""
-        self._check_mode(x)
+        self._check_mode(x, allow_grad=True)
         if x.dim() != 2 or x.shape[1] != self.final_dim:
             raise ValueError(f"expected a [N, {self.final_dim}] bag, got {tuple(x.shape)}")
         N = x.shape[0]
         if N < 1:
             raise ValueError("empty bag")
         x = x.contiguous()
+        if self._needs_grad(x):   # autograd path: forward with a tape, backward kernels
+            return _EncoderFunction.apply(self, x, *self.parameters())
         lib, cfg = cabi.lib(), self._cfg
         with torch.cuda.device(x.device):
             nbytes = cabi.workspace_bytes(cfg, N)

@@ -1,0 +1,166 @@
+"""Backward pass (through the C ABI / autograd bridge) against torch autograd over the fp64 oracle.
+
+Tolerances: the backward GEMMs and the attention backward use fp16 tensor-core operands (10 mantissa
+bits, fp32 accumulation) with automatic power-of-two scaling, like the forward; gradients go through
+about twice as many rounding stages as activations, so the bar is rel <= 3e-3 per gradient tensor
+(Frobenius), 1e-5 for the fp32 streaming kernels."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import rrt_oracle as O
+import gpu_util as G
+from rrt_mil_b200 import cabi
+
+pytestmark = pytest.mark.gpu
+
+TOL_GRAD = 3e-3
+TOL_FP32 = 1e-5
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+@pytest.mark.parametrize("L,D", [(300, 512), (1, 128), (1000, 1024), (77, 256)])
+def test_layernorm_backward(L, D):
+    g = torch.Generator().manual_seed(L + D)
+    x = torch.randn(L, D, generator=g, dtype=torch.float64) * 2 + 0.3
+    gam = (1 + 0.1 * torch.randn(D, generator=g, dtype=torch.float64))
+    bet = 0.1 * torch.randn(D, generator=g, dtype=torch.float64)
+    dy = torch.randn(L, D, generator=g, dtype=torch.float64)
+    xr, gr, br = x.clone().requires_grad_(), gam.clone().requires_grad_(), bet.clone().requires_grad_()
+    (F.layer_norm(xr, (D,), gr, br) * dy).sum().backward()
+    xd, gd, dyd = x.float().cuda(), gam.float().cuda(), dy.float().cuda()
+    dx = torch.empty_like(xd)
+    dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    rc = cabi.lib().rrt_layernorm_backward(xd.data_ptr(), gd.data_ptr(), dyd.data_ptr(), dx.data_ptr(),
+                                           dg.data_ptr(), db.data_ptr(), L, D, G.stream_ptr())
+    cabi.check(rc, "rrt_layernorm_backward")
+    torch.cuda.synchronize()
+    assert rel(dx, xr.grad) < TOL_FP32
+    assert rel(dg, gr.grad) < TOL_FP32
+    assert rel(db, br.grad) < TOL_FP32
+
+
+def attention_ref(qkv, taps, heads, P):
+    """fp64 attention core in the EPEG-on-Q form (oracle order 'spec'); qkv [R*P, 3D] rows (3, heads, d)."""
+    M, D3 = qkv.shape
+    D, R = D3 // 3, M // P
+    d = D // heads
+    t = qkv.view(R, P, 3, heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = t[0], t[1], t[2]
+    if taps is not None:
+        kk = taps.shape[1]
+        w = taps.repeat_interleave(d, 0).unsqueeze(1)
+        qc = F.conv1d(q.permute(0, 1, 3, 2).reshape(R, heads * d, P), w, padding=kk // 2, groups=heads * d)
+        q = q + qc.view(R, heads, d, P).permute(0, 1, 3, 2)
+    a = torch.softmax((q * d ** -0.5) @ k.transpose(-1, -2), -1)
+    return (a @ v).permute(0, 2, 1, 3).reshape(M, D)
+
+
+@pytest.mark.parametrize("R,P,D,heads,kk", [
+    (3, 144, 512, 8, 15), (2, 9, 512, 8, 15), (3, 64, 512, 8, None), (2, 196, 512, 8, 21),
+    (2, 256, 256, 8, 7), (1, 1, 128, 4, 3), (2, 100, 512, 8, None), (5, 144, 512, 8, 1)])
+def test_attention_backward(R, P, D, heads, kk):
+    g = torch.Generator().manual_seed(R * 1000 + P)
+    M = R * P
+    qkv16 = (torch.randn(M, 3 * D, generator=g) * 1.2).half()
+    do16 = torch.randn(M, D, generator=g).half()
+    taps = (0.2 * torch.randn(heads, kk, generator=g)).float() if kk else None
+    qkv = qkv16.double().requires_grad_()
+    tp = taps.double().requires_grad_() if kk else None
+    o = attention_ref(qkv, tp, heads, P)
+    (o * do16.double()).sum().backward()
+    o16 = o.detach().half().cuda()
+    qd, dod = qkv16.cuda(), do16.cuda()
+    dqkv = torch.zeros(M, 3 * D, dtype=torch.float16, device="cuda")
+    dt = torch.zeros(heads, kk, device="cuda") if kk else None
+    td = taps.cuda() if kk else None
+    rc = cabi.lib().rrt_attention_backward(qd.data_ptr(), o16.data_ptr(), dod.data_ptr(),
+                                           td.data_ptr() if kk else None, dqkv.data_ptr(),
+                                           dt.data_ptr() if kk else None, R, P, D, heads, kk or 1,
+                                           G.stream_ptr())
+    cabi.check(rc, "rrt_attention_backward")
+    torch.cuda.synchronize()
+    gq = qkv.grad
+    if P == 1:   # softmax over one key: dq = dk = dtaps = 0 exactly, dv = dO
+        assert float(dqkv[:, :2 * D].float().abs().max()) < 1e-2 and float(dt.abs().max()) < 1e-2
+        assert rel(dqkv[:, 2 * D:], gq[:, 2 * D:]) < TOL_GRAD
+        return
+    errs = {n: rel(dqkv[:, i * D:(i + 1) * D], gq[:, i * D:(i + 1) * D]) for i, n in enumerate("qkv")}
+    if kk:
+        errs["taps"] = rel(dt, tp.grad)
+    print(R, P, D, heads, kk, errs)
+    assert torch.isfinite(dqkv.float()).all()
+    for n, e in errs.items():
+        assert e < TOL_GRAD, (n, e, errs)
+
+
+def oracle_grads(cfg, w, x, gout):
+    w64 = {k: v.double().clone().requires_grad_() for k, v in w.items()}
+    x64 = x.double().clone().requires_grad_()
+    y = O.encoder_forward(x64, w64, cfg, "spec")
+    (y * gout.double()).sum().backward()
+    return y.detach(), x64.grad, {k: v.grad for k, v in w64.items()}
+
+
+ENC_CASES = [
+    ("rmsa_only", 300, dict(cr_msa=False)),
+    ("rmsa_only_noepeg", 200, dict(cr_msa=False, epeg=False, qkv_bias=False, mlp_dim=256)),
+    ("crmsa_only", 300, dict(n_layers=1)),
+    ("default_512", 512, dict()),
+    ("default_1000", 1000, dict()),
+    ("shortcut_d256", 300, dict(mlp_dim=256, region_num=4, epeg_k=5, crmsa_k=4, crmsa_heads=4, all_shortcut=True)),
+    ("three_layers", 2500, dict(region_num=16, n_layers=3, epeg_k=21, crmsa_k=5)),
+    ("tiny", 50, dict()),
+    ("n9000", 9000, dict()),
+]
+
+
+@pytest.mark.parametrize("name,L,over", ENC_CASES, ids=[c[0] for c in ENC_CASES])
+def test_encoder_backward_matches_oracle_autograd(name, L, over):
+    cfg = O.EncoderConfig(**over)
+    w = O.make_weights(cfg, 41)
+    x = O.make_bag(L, cfg.mlp_dim, 42, kind="relu")
+    gout = torch.randn(L, cfg.mlp_dim, generator=torch.Generator().manual_seed(43), dtype=torch.float64)
+    if name == "n9000":
+        gout = gout * 1e-7   # the automatic fp16 scaling must cope with tiny upstream gradients
+    y_ref, dx_ref, dw_ref = oracle_grads(cfg, w, x, gout)
+
+    m = G.make_encoder(cfg, w)
+    xd = x.float().cuda().requires_grad_()
+    y = m(xd)
+    with torch.no_grad():
+        y_inf = m(xd.detach())
+    assert torch.equal(y.detach(), y_inf), "training forward must equal the inference forward bit for bit"
+    assert O.rel_err(y.detach().cpu(), y_ref) < 1e-3
+    (y * gout.float().cuda()).sum().backward()
+    torch.cuda.synchronize()
+    errs = {"x": rel(xd.grad, dx_ref)}
+    for n, p in m.named_parameters():
+        ref = dw_ref[n]
+        if ref is None or float(ref.norm()) < 1e-12 * max(1.0, float(gout.norm())):
+            # exactly-zero reference gradient (pe.bias; taps when regions hold one token): rounding noise only
+            assert p.grad is None or float(p.grad.abs().max()) <= 1e-4 * float(gout.abs().max()), n
+            continue
+        assert p.grad is not None, n
+        errs[n] = rel(p.grad, ref)
+    worst = max(errs, key=errs.get)
+    print(name, "worst", worst, errs[worst], {k: f"{v:.1e}" for k, v in errs.items()})
+    for n, e in errs.items():
+        assert e < TOL_GRAD, (n, e)
+
+
+def test_backward_rejects_unsupported():
+    cfg = O.EncoderConfig(crmsa_mlp=True, crmsa_heads=1, crmsa_k=5)
+    m = G.make_encoder(cfg, O.make_weights(cfg, 3))
+    x = O.make_bag(200, 512, 4).float().cuda().requires_grad_()
+    with pytest.raises(NotImplementedError):
+        m(x)
+    m2 = G.make_encoder(O.EncoderConfig(), O.make_weights(O.EncoderConfig(), 3)).train()
+    with pytest.raises(NotImplementedError):     # default drop_out = 0.1 is active in training mode
+        m2(x)
