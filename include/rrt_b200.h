@@ -173,8 +173,14 @@ RRT_API int rrt_debug_set_attention_kernel(int32_t use_tcgen05);
 
 /* Debug / tuning: kernel variant of the bag-sized tcgen05 GEMMs.  11 = single-CTA 128x256 tiles
  * (default, fastest at these sizes); 2 = CTA pairs (cta_group::2, M=256 tiles); 21 / 22 = single-CTA
- * tiles with 2x1 / 2x2 cluster TMA multicast.  Results do not depend on it. */
+ * tiles with 2x1 / 2x2 cluster TMA multicast; 128 / 256 = tile width of the GEMMs that have at most one
+ * 256-column tile per CTA (proj; default 256).  Results do not depend on it. */
 RRT_API int rrt_debug_set_gemm_cluster(int32_t mode);
+
+/* Debug / measurement only: bit i set = the kernels of stage i (rrt_stage_name order) are NOT launched.
+ * Results are then wrong by construction; tools/marginal_cost.py uses it to time what each stage costs
+ * while several bags are in flight (where per-kernel intervals overlap and cannot be summed). */
+RRT_API int rrt_debug_skip_stages(uint32_t mask);
 
 /* dst[i] = fp16(src[i]), round to nearest, saturating at +-65504.  dst is n fp16 values; n % 4 == 0. */
 RRT_API int rrt_convert_f16(const float* src, void* dst, int64_t n, void* stream);

@@ -44,6 +44,7 @@ const char* const kStageNames[kStCount] = {
     "bwd_crmsa"};
 
 std::atomic<int64_t> g_launches{0};
+std::atomic<uint32_t> g_skip_mask{0};  // rrt_debug_skip_stages (measurement only)
 std::atomic<bool> g_timing{false};
 std::mutex g_timing_mu;
 struct Interval { int stage; cudaEvent_t a, b; };
@@ -61,6 +62,7 @@ cudaEvent_t take_event() {
 
 struct StageScope {
   int stage; cudaStream_t st; cudaEvent_t a = nullptr; bool on;
+  bool skip() const { return (g_skip_mask.load(std::memory_order_relaxed) >> stage) & 1u; }
   StageScope(int stage_, cudaStream_t st_, int n_launches = 1) : stage(stage_), st(st_) {
     g_launches.fetch_add(n_launches, std::memory_order_relaxed);
     on = g_timing.load(std::memory_order_relaxed);
@@ -277,14 +279,15 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
   rc = f16_weight(a->proj_w, a->proj_w_f16, ws.wconv + (size_t)3 * D * D, (size_t)D * D, st, &wp);
   if (rc) return rc;
   { StageScope s_(kStLnPartition, st);
-    RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws_z, g, D, st), "ln_partition"); }
+    if (!s_.skip()) RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws_z, g, D, st), "ln_partition"); }
   rrt::GemmEpilogue e1;
   e1.bias = c->qkv_bias ? a->qkv_b : nullptr;
   { StageScope s_(kStQkvGemm, st);
-    RRT_CUDA(rrt::launch_gemm_tcgen05(ws_z, wq, ws_qkv, true, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
+    if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws_z, wq, ws_qkv, true, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
   { StageScope s_(kStRmsaAttn, st);
     const float* taps = c->epeg ? a->pe_w : nullptr;
-    if (rrt::g_attn_tc05 && rrt::rmsa_attention_tc05_supported(g, D, c->n_heads))
+    if (s_.skip()) {
+    } else if (rrt::g_attn_tc05 && rrt::rmsa_attention_tc05_supported(g, D, c->n_heads))
       RRT_CUDA(rrt::launch_rmsa_attention_tc05(ws_qkv, taps, ws_o, g, D, c->n_heads, c->epeg_k, st),
                "rmsa attention (tcgen05)");
     else if (rrt::rmsa_attention_f16_supported(g, D, c->n_heads))
@@ -299,7 +302,7 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
   e2.resid = x;
   e2.grid = g;
   { StageScope s_(kStProjGemm, st);
-    RRT_CUDA(rrt::launch_gemm_tcgen05(ws_o, wp, x1, false, g.Np, D, D, e2, st), "proj gemm"); }
+    if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws_o, wp, x1, false, g.Np, D, D, e2, st), "proj gemm"); }
   return RRT_OK;
 }
 
@@ -341,8 +344,9 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   bool front_done = false;
   if (front_mode == 0) {
     StageScope s_(kStCrCombine, st, 2);
-    cudaError_t e = rrt::launch_crmsa_front_split(x1, w->cr_norm_w, w->cr_norm_b, phi, ws.stats,
-                                                  ws.logits, ws.lm, ws.rstat, g, D, k, st);
+    cudaError_t e = s_.skip() ? cudaSuccess
+                              : rrt::launch_crmsa_front_split(x1, w->cr_norm_w, w->cr_norm_b, phi, ws.stats,
+                                                              ws.logits, ws.lm, ws.rstat, g, D, k, st);
     if (e == cudaSuccess) front_done = true;
     else if (e != cudaErrorNotSupported) return fail_cuda(e, "crmsa front (split)");
   }
@@ -368,9 +372,10 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   rrt::GemmEpilogue e1;
   e1.bias = c->qkv_bias ? w->cr_attn.qkv_b : nullptr;
   { StageScope s_(kStLmQkv, st);
-    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lm, wq, ws.lqkv, tc_attn, T, 3 * D, D, e1, st), "landmark qkv"); }
+    if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lm, wq, ws.lqkv, tc_attn, T, 3 * D, D, e1, st), "landmark qkv"); }
   { StageScope s_(kStLmAttn, st);
-    if (tc_attn)
+    if (s_.skip()) {
+    } else if (tc_attn)
       RRT_CUDA(rrt::launch_rmsa_attention_f16(reinterpret_cast<const __half*>(ws.lqkv), nullptr, ws.lo,
                                               lg, D, c->crmsa_heads, 1, st), "landmark attention");
     else
@@ -379,9 +384,9 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   rrt::GemmEpilogue e2;
   e2.bias = w->cr_attn.proj_b;
   { StageScope s_(kStLmProj, st);
-    RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lo, wp, ws.lout, false, T, D, D, e2, st), "landmark proj"); }
+    if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lo, wp, ws.lout, false, T, D, D, e2, st), "landmark proj"); }
   { StageScope s_(kStCrDispatch, st);
-    RRT_CUDA(rrt::launch_crmsa_dispatch(x1, x0, ws.logits, ws.rstat, ws.lout,
+    if (!s_.skip()) RRT_CUDA(rrt::launch_crmsa_dispatch(x1, x0, ws.logits, ws.rstat, ws.lout,
                                         final_norm ? w->norm_w : nullptr,
                                         final_norm ? w->norm_b : nullptr, out, g, D, k, st),
              "crmsa dispatch"); }
@@ -709,9 +714,14 @@ RRT_API int rrt_debug_set_attention_kernel(int32_t use_tcgen05) {
   return RRT_OK;
 }
 
+RRT_API int rrt_debug_skip_stages(uint32_t mask) {
+  g_skip_mask.store(mask);
+  return RRT_OK;
+}
+
 RRT_API int rrt_debug_set_gemm_cluster(int32_t mode) {
-  if (mode != 2 && mode != 22 && mode != 21 && mode != 11)
-    return fail(RRT_E_INVALID, "mode must be 2, 11, 21 or 22");
+  if (mode != 2 && mode != 22 && mode != 21 && mode != 11 && mode != 128 && mode != 256)
+    return fail(RRT_E_INVALID, "mode must be 2, 11, 21, 22, 128 or 256");
   rrt::set_gemm_cluster_mode(mode);
   return RRT_OK;
 }

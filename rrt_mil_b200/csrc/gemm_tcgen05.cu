@@ -32,10 +32,13 @@ constexpr int NTHREADS = 32 * (4 + kEpiWarps);
 
 // Tile configuration: 128 x BN output tile, STAGES-deep operand ring, two BN-column accumulators.
 //   BN = 256: bag-sized GEMMs (M ~ 10^4): fewest operand bytes per MAC
+//   BN = 128: bag-sized GEMMs with a narrow output (proj: N = D): at 256 columns every CTA would own
+//             ONE tile and run prologue, main loop and epilogue back to back; two 128-column tiles
+//             per CTA let the second main loop hide the first (HBM-bound, residual) epilogue
 //   BN =  64: landmark GEMMs (M = k*64 rows): 4x more CTAs, 4x shorter MMA chain per tile
 template <int BN_>
 struct TileCfg {
-  static constexpr int STAGES = BN_ == 256 ? 4 : 8;
+  static constexpr int STAGES = BN_ == 256 ? 4 : (BN_ == 128 ? 6 : 8);
   static constexpr int B_BYTES = BN_ * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
@@ -141,7 +144,20 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
           v[i] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)orow[i] * p.N + gc));
       }
     };
-    if (MODE == kEpiResidualUnpart) load_resid(0);
+    if (MODE == kEpiResidualUnpart) {
+      load_resid(0);
+      // the residual rows of the later chunks: pull them into L2 while the MMA warp is still busy, so
+      // that the per-chunk loads below are L2 hits instead of NC serial HBM round trips
+      if ((lane & 7) == 0) {
+#pragma unroll
+        for (int j = 1; j < NC; ++j) {
+          const int gc = n0 + (c_begin + j) * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (orow[i] >= 0 && gc < p.N) prefetch_l2(p.resid + (size_t)orow[i] * p.N + gc);
+        }
+      }
+    }
     mbar_wait(tfull_bar, tfull_parity);
     tc_fence_after();
     if (first && threadIdx.x == 128) stamp(p, 6);
@@ -658,6 +674,11 @@ int g_gemm_cluster = 11;
 // main loop 5.2k cycles/tile vs 5.7k single-CTA (5.7k IS the cuBLAS-measured tensor rate), but the
 // cluster set-up and the longer tail cost more than that buys at 3 tiles per CTA: QKV 23.0 vs 20.9 us.
 int g_gemm_pair = 0;
+// 1: 128-column tiles for bag-sized GEMMs that would otherwise run one 256-column tile per CTA
+// (rrt_debug_set_gemm_cluster(128)).  Measured (s3_marginal): 16 bags, 4 lanes: 74.1 us/bag with 128-column
+// proj tiles vs 71.3 with 256 -- two narrow tiles ingest 2 x 256 KB of operands per CTA instead of 384 KB and
+// the main loop is operand-ingest bound (~67 B/clk/SM), which costs more than the hidden epilogue saves.
+int g_gemm_narrow = 0;
 
 template <int MODE, typename OutT>
 cudaError_t launch_pair(const __half* a, const __half* w, const Tc05Params& p, cudaStream_t stream) {
@@ -697,6 +718,9 @@ cudaError_t launch_mode(const __half* a, const __half* w, const Tc05Params& p, c
   // small problems: narrower tiles so that more SMs share the (latency-bound) work
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n256 = (p.N + 255) / 256;
   if (tiles_m * tiles_n256 < sm_count() / 2) return launch_cfg<MODE, 64, OutT, 1, 1>(a, w, p, stream);
+  // at most one 256-column tile per CTA: halve the tile width so that every CTA pipelines two tiles
+  if (g_gemm_narrow && tiles_m * tiles_n256 <= sm_count() && p.N % 128 == 0)
+    return launch_cfg<MODE, 128, OutT, 1, 1>(a, w, p, stream);
   if (MODE == kEpiStoreAct) return launch_cfg<MODE, 256, OutT, 1, 1>(a, w, p, stream);  // no tuning variants
   if (g_gemm_pair && tiles_m >= 2) return launch_pair<MODE, OutT>(a, w, p, stream);
   // bag-sized problems: clusters with multicast operand tiles when the tile grid allows it
@@ -708,6 +732,7 @@ cudaError_t launch_mode(const __half* a, const __half* w, const Tc05Params& p, c
 }  // namespace
 
 void set_gemm_cluster_mode(int mode) {
+  if (mode == 128 || mode == 256) { g_gemm_narrow = mode == 128; return; }
   if (mode == 2) { g_gemm_pair = 1; return; }
   g_gemm_pair = 0;
   g_gemm_cluster = mode;

@@ -54,18 +54,23 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
     bool ok = p >= 0 && p < P;
     cp_async16(Qs + (size_t)r * LDH + c, base + (size_t)(ok ? p : 0) * ld + c, ok);
   }
+  cp_async_commit();  // group 0: Q (needed first, by the EPEG product)
   for (int i = tid; i < pk * C8; i += blockDim.x) {
     int r = i / C8, c = (i - r * C8) * 8;
     bool ok = r < P;
-    const __half* src = base + (size_t)(ok ? r : 0) * ld + c;
-    cp_async16(Ks + (size_t)r * LDH + c, src + D, ok);
-    cp_async16(Vs + (size_t)r * LDH + c, src + 2 * D, ok);
+    cp_async16(Ks + (size_t)r * LDH + c, base + (size_t)(ok ? r : 0) * ld + c + D, ok);
   }
-  cp_async_commit();
+  cp_async_commit();  // group 1: K (first needed by S = Q'K^T)
+  for (int i = tid; i < pk * C8; i += blockDim.x) {
+    int r = i / C8, c = (i - r * C8) * 8;
+    bool ok = r < P;
+    cp_async16(Vs + (size_t)r * LDH + c, base + (size_t)(ok ? r : 0) * ld + c + 2 * D, ok);
+  }
+  cp_async_commit();  // group 2: V (first needed by the first P.V): lands behind the work on Q and K
   if (taps)
     for (int i = tid; i < epeg_k; i += blockDim.x) Ts[i] = __ldg(taps + h * epeg_k + i);
   astamp(tr, 1);
-  cp_async_wait<0>();
+  cp_async_wait<2>();
   __syncthreads();
   astamp(tr, 2);
 
@@ -125,6 +130,8 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
   }
 
   astamp(tr, 3);
+  cp_async_wait<1>();
+  __syncthreads();  // K has landed
   // ---- attention core ---------------------------------------------------------------------------
   float oacc[ND][4];
 #pragma unroll
@@ -186,6 +193,10 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
         l_run[e >> 1] += pv;
         s[nt][e] = pv;
       }
+    if (kt == 0) {  // V has landed (uniform branch: every warp runs the same KV tiles)
+      cp_async_wait<0>();
+      __syncthreads();
+    }
 #pragma unroll
     for (int j = 0; j < NT / 2; ++j) {  // 16 keys per step: two S n-tiles form one A fragment
       uint32_t pa[4] = {pack_h2(s[2 * j][0], s[2 * j][1]), pack_h2(s[2 * j][2], s[2 * j][3]),

@@ -247,7 +247,10 @@ def test_input_rank_handling_and_errors():
     assert y3.shape == (1, 400, 512) and y2.shape == (400, 512) and y4.shape == (1, 512, 20, 20)
     assert torch.equal(y3[0], y2)
     assert torch.equal(y4.reshape(1, 512, 400).transpose(1, 2)[0], y2)
-    with pytest.raises(NotImplementedError):
-        m(x.unsqueeze(0).requires_grad_())          # backward not built: must raise, not fall back
+    xg = x.unsqueeze(0).clone().requires_grad_()    # grad mode runs the taped forward + CUDA backward
+    yg = m(xg)
+    assert torch.allclose(yg.detach(), y3, rtol=0, atol=1e-5)
+    yg.square().sum().backward()
+    assert xg.grad is not None and xg.grad.shape == xg.shape and torch.isfinite(xg.grad).all()
     with torch.no_grad(), pytest.raises(NotImplementedError):
         m(x.half())
