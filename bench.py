@@ -299,13 +299,46 @@ def run_b200_arm(args):
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(e2e_steps):
-        pipe.run(hx, hy)  # returns after the last device->host copy has landed
+    hy2 = [torch.empty(N_TOKENS, DIM).pin_memory() for _ in range(B)]
+    for i in range(e2e_steps):
+        # steps are streamed: step i+1's uploads start while step i's results are still going back
+        # (alternating host result buffers); the clock stops when the LAST result is in host memory
+        pipe.run(hx, hy if i % 2 == 0 else hy2, sync=False)
+    pipe.wait()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_val = world * patches_per_step * e2e_steps / float(t_e2e.item())
     bytes_step = B * N_TOKENS * DIM * 4
+
+    # ---- forward + backward (BASELINE configs[1] names fwd+bwd on 1 GPU): training-mode step of one
+    # bag through the autograd bridge (taped forward with proj dropout 0.1, backward kernels), reported
+    # beside the headline; not part of `value`
+    train = None
+    if not args.no_train:
+        enc_t = RRTEncoder(need_init=True, **ENC_KW).to(dev).train()
+        xt = bags[0].clone().requires_grad_()
+        gout = torch.randn_like(xt)
+        def train_step():
+            y = enc_t(xt)
+            y.backward(gout)
+        for _ in range(3):
+            train_step()
+        torch.cuda.synchronize()
+        n_tr = max(5, min(args.steps, 20))
+        l0 = cabi.launch_count()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(n_tr):
+            train_step()
+        t1e.record()
+        torch.cuda.synchronize()
+        us = t0e.elapsed_time(t1e) * 1e3 / n_tr
+        train = {"us_per_bag_fwd_bwd": us, "patches_per_s": N_TOKENS / (us * 1e-6), "drop_out": 0.1,
+                 "launches_per_step": (cabi.launch_count() - l0) // n_tr,
+                 "what": "RRTEncoder.train() forward (tape + proj dropout) + backward of one N=9000 bag "
+                         "through torch.autograd, all parameter gradients, one stream, CUDA events"}
+        del enc_t, xt, gout
 
     line = None
     if rank == 0:
@@ -329,7 +362,10 @@ def run_b200_arm(args):
             "stages_share": {k: round(v, 4) for k, v in stage_share.items()},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": bytes_step,
                     "d2h_bytes_per_step": bytes_step, "steps": e2e_steps,
-                    "how": f"HostPipeline.run over pinned host bags, {args.e2e_streams} streams, wall clock"},
+                    "how": f"HostPipeline.run over pinned host bags: H2D stream -> compute stream -> D2H "
+                           f"stream over a ring of {args.e2e_streams} device buffers, steps streamed back to "
+                           "back, wall clock until the last result is in host memory"},
+            "train_step": train,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
         }
@@ -352,6 +388,7 @@ def main():
     ap.add_argument("--e2e-streams", type=int, default=3)
     ap.add_argument("--lanes", type=int, default=4, help="bags in flight per GPU (internal streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the forward+backward measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -33,7 +33,7 @@ extern "C" {
 #define RRT_API __attribute__((visibility("default")))
 #endif
 
-#define RRT_ABI_VERSION 4
+#define RRT_ABI_VERSION 5
 #define RRT_MAX_RMSA_LAYERS 8 /* n_layers-1 R-MSA TransLayers (modules/rrt.py:143) */
 #define RRT_MAX_CRMSA_K 16    /* crmsa_k landmarks per region                         */
 #define RRT_MAX_EPEG_K 63     /* odd EPEG kernel length                               */
@@ -254,15 +254,25 @@ typedef struct rrt_grads {
 } rrt_grads;
 
 RRT_API int rrt_train_tape_bytes(const rrt_config* cfg, int64_t L, size_t* bytes);
+/* drop_p / seed: training-mode proj_drop of every InnerAttention (modules/rmsa.py:70,132; the
+ * reference's drop_out, default 0.1; 0 = eval-mode arithmetic).  The mask is counter-based (splitmix64 of
+ * seed, mask stream and element index; csrc/common.cuh) and is regenerated by rrt_encoder_backward, which
+ * must be given the same drop_p and seed.  Mask streams: R-MSA layer i -> i (mask over [L, D], token
+ * order), landmark MHA of CR-MSA -> RRT_DROP_STREAM_CRMSA (mask over [k*64, D]).  It is the reference's
+ * dropout in distribution, not torch's Philox stream; rrt_dropout_mask exposes it for parity tests. */
+#define RRT_DROP_STREAM_CRMSA 64
 RRT_API int rrt_encoder_forward_train(const rrt_config* cfg, const rrt_weights* w, const float* x,
                                       float* out, int64_t L, void* tape, size_t tape_bytes,
-                                      void* stream);
+                                      float drop_p, uint64_t seed, void* stream);
+/* out[i] = keep(i) / (1 - drop_p) for i < n (n % 4 == 0): the factor the forward multiplies element i by. */
+RRT_API int rrt_dropout_mask(float* out, int64_t n, float drop_p, uint64_t seed, uint32_t mask_stream,
+                             void* stream);
 RRT_API int rrt_backward_workspace_bytes(const rrt_config* cfg, int64_t L, size_t* bytes);
 /* x: the forward input; dout: d(loss)/d(out) [L, D]; dx: d(loss)/dx [L, D] (may not alias dout). */
 RRT_API int rrt_encoder_backward(const rrt_config* cfg, const rrt_weights* w, const float* x,
                                  const float* dout, int64_t L, const void* tape, size_t tape_bytes,
                                  const rrt_grads* grads, float* dx, void* workspace,
-                                 size_t workspace_bytes, void* stream);
+                                 size_t workspace_bytes, float drop_p, uint64_t seed, void* stream);
 
 /* Building blocks of the backward pass, exposed for the parity tests.
  * rrt_attention_backward: qkv [R*P, 3D] fp16 and o [R*P, D] fp16 as the forward wrote them,

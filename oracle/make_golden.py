@@ -67,6 +67,24 @@ MIL_CASES = [
     ("mil_n9000_k21", 9000, 1024, 2, "relu", "relu", False, dict(epeg_k=21, crmsa_k=5)),
 ]
 
+# Training mode (proj_drop active) + backward: name, L, config overrides, drop_out, dropout seed.
+# The reference runs in .train() with every InnerAttention.proj_drop (nn.Dropout, modules/rmsa.py:70)
+# replaced by a module that multiplies by the library's counter-based mask (oracle.dropout_mask), so
+# the fixture pins WHERE the dropout acts and its backward; the mask itself is pinned bit for bit by
+# tests/test_gpu_backward.py::test_dropout_mask_matches_oracle.
+# The dropout seed (bag seed when p = 0) is the FIRST one at or after the listed value whose bag keeps the
+# two smallest / two largest CR-MSA logits of every region apart (crmsa_tie_gap): the reference's min-max
+# normaliser (modules/rmsa.py:312-314) routes d/d(min), d/d(max) to the argmin / argmax token, so its
+# GRADIENT jumps when two logits tie, and a fixture on such a tie pins rounding noise, not the backward.
+MIN_TIE_GAP = 1e-3
+TRAIN_CASES = [
+    ("train_n700_p10", 700, dict(), 0.1, 20240229),
+    ("train_d256_shortcut_p25", 500, dict(mlp_dim=256, region_num=4, epeg_k=5, crmsa_k=4, crmsa_heads=4,
+                                          all_shortcut=True, n_layers=3), 0.25, 77),
+    ("train_n700_p0", 700, dict(), 0.0, 0),   # eval-arithmetic backward pinned against reference autograd
+]
+GRAD_SEED = 43
+
 MAX_ROWS = 96
 WEIGHT_SEED = 2021  # the reference's default --seed (main.py:645)
 MIN_LOGIT_RANGE = 1e-2  # see crmsa_conditioning
@@ -121,6 +139,101 @@ def generate(name, L, overrides, bag_seed, kind):
                 weight_seed=WEIGHT_SEED, bag_seed=bag_seed, min_crmsa_logit_range=cond)
 
 
+class _MaskMul(torch.nn.Module):
+    """Stands in for nn.Dropout in the reference: multiplies by a fixed keep/(1-p) tensor."""
+
+    def __init__(self, mask):
+        super().__init__()
+        self.mask = mask
+
+    def forward(self, t):
+        return t * self.mask.view(t.shape)
+
+
+def install_dropout_masks(model, cfg, L, p, seed):
+    """Replace the reference's proj_drop modules by the library's masks, re-laid out the way each
+    proj_drop sees its input: [R, P, D] region slots for R-MSA (pad slots keep 1), [k, 64, D] landmarks."""
+    D = cfg.mlp_dim
+    H, rs, _ = O.grid_geometry(L, cfg.region_num, cfg.region_size, cfg.min_region_num, cfg.min_region_ratio)
+    for i in range(cfg.n_layers - 1):
+        m = O.dropout_mask(L, D, p, seed, i)
+        mp = torch.cat([m, torch.ones(H * H - L, D, dtype=m.dtype)]) if H * H > L else m
+        g = H // rs
+        model.layers[i].attn.attn.proj_drop = _MaskMul(
+            mp.view(g, rs, g, rs, D).transpose(1, 2).reshape(g * g, rs * rs, D).contiguous())
+    if cfg.cr_msa:
+        model.cr_msa.attn.attn.proj_drop = _MaskMul(
+            O.dropout_mask(cfg.crmsa_k * 64, D, p, seed, O.DROP_STREAM_CRMSA).view(cfg.crmsa_k, 64, D))
+
+
+def sample_rows(a, max_rows=MAX_ROWS):
+    a2 = a.reshape(a.shape[0], -1) if a.ndim > 1 else a.reshape(1, -1)
+    stride = max(1, -(-a2.shape[0] // max_rows))
+    return a2[::stride].astype(np.float32), stride
+
+
+def crmsa_tie_gap(x, w, cfg, drop):
+    """Smallest gap between the two lowest / two highest CR-MSA logits of a region, relative to the
+    region's logit range (exact ties between zero pad slots do not count: pads carry no gradient)."""
+    if not cfg.cr_msa:
+        return float("inf")
+    L, D = x.shape
+    h = x
+    for i in range(cfg.n_layers - 1):
+        p = f"layers.{i}."
+        m = O.dropout_mask(L, D, drop[0], drop[1], i) if drop[0] > 0 else None
+        h = h + O.rmsa_block(O.layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w, p + "attn.", cfg,
+                             "spec", m)
+    H, rs, _ = O.grid_geometry(L, 8)
+    if rs == 1:
+        return float("inf")
+    z = O._to_regions(O.layer_norm(h, w["cr_msa.norm.weight"], w["cr_msa.norm.bias"]), L, H, rs)
+    srt = (z @ w["cr_msa.attn.phi"]).sort(1).values  # [R,P,k]
+    rng = (srt[:, -1] - srt[:, 0]).clamp_min(1e-300)
+    gaps = torch.cat([(srt[:, 1] - srt[:, 0]) / rng, (srt[:, -1] - srt[:, -2]) / rng])
+    real = (O.region_slot_map(H, rs) < L).view(-1, rs * rs).any(1).repeat(2)
+    gaps = gaps[real]
+    return float(gaps[gaps > 0].min())
+
+
+def generate_train(name, L, overrides, p, seed):
+    cfg = O.EncoderConfig(**overrides)
+    w = O.make_weights(cfg, WEIGHT_SEED)
+    bag_seed = 7
+    for _ in range(400):
+        x = O.make_bag(L, cfg.mlp_dim, bag_seed, kind="relu")
+        gap = crmsa_tie_gap(x, w, cfg, (p, seed))
+        if gap >= MIN_TIE_GAP:
+            break
+        if p > 0:
+            seed += 1
+        else:
+            bag_seed += 1
+    else:
+        raise SystemExit(f"{name}: no seed with a CR-MSA tie gap >= {MIN_TIE_GAP}")
+    gout = torch.randn(L, cfg.mlp_dim, generator=torch.Generator().manual_seed(GRAD_SEED), dtype=torch.float64)
+    model = shim.build_reference_encoder(cfg, w).train()
+    install_dropout_masks(model, cfg, L, p, seed)
+    with torch.enable_grad():
+        xr = x.clone().requires_grad_()
+        y = model(xr.unsqueeze(0))[0]
+        (y * gout).sum().backward()
+    out = {}
+    yn, dxn = y.detach().numpy(), xr.grad.numpy()
+    out["out_rows"], stride = sample_rows(yn)
+    out["dx_rows"], _ = sample_rows(dxn)
+    out["row_stride"] = np.array(stride)
+    out["out_fro"], out["dx_fro"] = np.array(np.linalg.norm(yn)), np.array(np.linalg.norm(dxn))
+    out["out_row_sum"], out["dx_row_sum"] = yn.sum(1).astype(np.float32), dxn.sum(1).astype(np.float32)
+    for n_, p_ in model.named_parameters():
+        g = p_.grad.numpy() if p_.grad is not None else np.zeros(tuple(p_.shape))
+        out["g:" + n_], _ = sample_rows(g)
+        out["gfro:" + n_] = np.array(np.linalg.norm(g))
+    np.savez(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+    return dict(name=name, L=L, config=cfg.to_dict(), drop_out=p, dropout_seed=seed, weight_seed=WEIGHT_SEED,
+                bag_seed=bag_seed, bag_kind="relu", grad_seed=GRAD_SEED, min_crmsa_tie_gap=gap)
+
+
 def generate_mil(name, L, input_dim, n_classes, act, da_act, da_bias, overrides):
     cfg = O.EncoderConfig(**overrides)
     w = O.make_mil_weights(cfg, input_dim, n_classes, WEIGHT_SEED, da_bias=da_bias)
@@ -144,8 +257,21 @@ def main():
         sys.exit("reference tree not present; goldens can only be generated in the build container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_grad_enabled(False)
+    only_new = "--only-missing" in sys.argv   # keep fixtures that already exist (they are deterministic)
+    old = {}
+    mpath = os.path.join(GOLDEN_DIR, "manifest.json")
+    if only_new and os.path.isfile(mpath):
+        om = json.load(open(mpath))
+        old = {c["name"]: c for k in ("cases", "mil_cases", "train_cases") for c in om.get(k, [])}
+
+    def have(name):
+        return only_new and name in old and os.path.isfile(os.path.join(GOLDEN_DIR, name + ".npz"))
+
     manifest = []
     for case in CASES:
+        if have(case[0]):
+            manifest.append(old[case[0]])
+            continue
         manifest.append(generate(*case))
         print("golden", case[0], flush=True)
     ref_commit = None
@@ -154,10 +280,20 @@ def main():
         ref_commit = json.load(open(sub)).get("commit")
     mil = []
     for case in MIL_CASES:
+        if have(case[0]):
+            mil.append(old[case[0]])
+            continue
         mil.append(generate_mil(*case))
         print("golden", case[0], flush=True)
+    train = []
+    for case in TRAIN_CASES:
+        if have(case[0]):
+            train.append(old[case[0]])
+            continue
+        train.append(generate_train(*case))
+        print("golden", case[0], flush=True)
     json.dump(dict(reference_commit=ref_commit, torch=torch.__version__, numpy=np.__version__,
-                   cases=manifest, mil_cases=mil),
+                   cases=manifest, mil_cases=mil, train_cases=train),
               open(os.path.join(GOLDEN_DIR, "manifest.json"), "w"), indent=1)
 
 

@@ -111,6 +111,35 @@ def region_slot_map(H: int, rs: int) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------
+# training-mode proj_drop (modules/rmsa.py:70,132)
+# ----------------------------------------------------------------------------------------
+DROP_STREAM_CRMSA = 64  # == RRT_DROP_STREAM_CRMSA (include/rrt_b200.h); R-MSA layer i uses stream i
+_M64 = (1 << 64) - 1
+
+
+def dropout_mask(rows: int, D: int, p: float, seed: int, stream: int, dtype=torch.float64) -> torch.Tensor:
+    """keep/(1-p) factors [rows, D] of the library's counter-based dropout (csrc/common.cuh):
+    one splitmix64 hash per 4 consecutive elements (flat index), 16 bits per element, dropped when
+    the 16-bit field is < round(p * 65536).  It is ``nn.Dropout(p)`` in distribution; the reference
+    draws its masks from torch's Philox stream, which no other implementation can reproduce, so
+    parity is checked by giving the reference / the oracle THIS mask (oracle/make_golden.py)."""
+    assert (rows * D) % 4 == 0
+    p32 = np.float32(p)
+    if not p32 > 0:
+        return torch.ones(rows, D, dtype=dtype)
+    thresh = min(int(float(p32) * 65536.0 + 0.5), 65535)
+    scale = float(np.float32(1.0) / (np.float32(1.0) - p32))
+    key = np.uint64((seed + (stream + 1) * 0x9E3779B97F4A7C15) & _M64)
+    with np.errstate(over="ignore"):
+        z = np.arange(rows * D // 4, dtype=np.uint64) + key
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    fields = np.stack([(z >> np.uint64(16 * j)) & np.uint64(0xFFFF) for j in range(4)], 1).reshape(rows, D)
+    return torch.from_numpy(np.where(fields >= thresh, scale, 0.0)).to(dtype)
+
+
+# ----------------------------------------------------------------------------------------
 # building blocks
 # ----------------------------------------------------------------------------------------
 def layer_norm(x, w, b):
@@ -167,16 +196,19 @@ def inner_attention(xr: torch.Tensor, w: Dict[str, torch.Tensor], prefix: str, h
     return F.linear(o, w[prefix + "proj.weight"], w[prefix + "proj.bias"])
 
 
-def rmsa_block(z, w, prefix, cfg: EncoderConfig, order):
-    """RegionAttntion.forward on an already-normalised [L,D] (modules/rmsa.py:204-230)."""
+def rmsa_block(z, w, prefix, cfg: EncoderConfig, order, mask=None):
+    """RegionAttntion.forward on an already-normalised [L,D] (modules/rmsa.py:204-230).
+    ``mask`` [L,D]: training-mode proj_drop factors in token order (pad rows are dropped afterwards,
+    so their mask is irrelevant)."""
     L = z.shape[0]
     H, rs, _ = grid_geometry(L, cfg.region_num, cfg.region_size, cfg.min_region_num,
                              cfg.min_region_ratio)
     y = inner_attention(_to_regions(z, L, H, rs), w, prefix + "attn.", cfg.n_heads, order)
-    return _from_regions(y, L, H, rs)
+    y = _from_regions(y, L, H, rs)
+    return y if mask is None else y * mask
 
 
-def crmsa_block(z, w, prefix, cfg: EncoderConfig, order):
+def crmsa_block(z, w, prefix, cfg: EncoderConfig, order, mask=None):
     """CrossRegionAttntion.forward on an already-normalised [L,D] (modules/rmsa.py:290-337).
 
     The CR-MSA TransLayer is built without ``n_region`` / ``region_size`` / ``min_region_*``
@@ -200,7 +232,9 @@ def crmsa_block(z, w, prefix, cfg: EncoderConfig, order):
         lm = (xr.unsqueeze(1) * combine.unsqueeze(-1)).sum(-2)  # [R,k,P,D] -> [R,k,D]
     else:
         lm = combine @ xr  # [R,k,D]
-    lm = inner_attention(lm.transpose(0, 1), w, prefix + "attn.", cfg.crmsa_heads, order)
+    lm = inner_attention(lm.transpose(0, 1), w, prefix + "attn.", cfg.crmsa_heads, order)  # [k,R,D]
+    if mask is not None:  # proj_drop of the landmark MHA: factors [k*R, D], row = n*R + rho
+        lm = lm * mask.view(lm.shape)
     lm = lm.transpose(0, 1)  # [R,k,D]
     if order == "reference":
         y = lm.unsqueeze(2) * dispatch_mm.unsqueeze(-1)  # [R,k,P,D]
@@ -211,19 +245,25 @@ def crmsa_block(z, w, prefix, cfg: EncoderConfig, order):
 
 
 def encoder_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfig,
-                    order: str = "reference") -> torch.Tensor:
-    """``RRTEncoder.forward`` for one bag ``x`` [L,D] -> [L,D] (modules/rrt.py:165-202)."""
+                    order: str = "reference", drop=None) -> torch.Tensor:
+    """``RRTEncoder.forward`` for one bag ``x`` [L,D] -> [L,D] (modules/rrt.py:165-202).
+    ``drop=(p, seed)``: training mode with ``drop_out=p`` (proj_drop masks from ``dropout_mask``)."""
     assert order in ("reference", "spec")
     assert x.dim() == 2 and x.shape[1] == cfg.mlp_dim
+    L, D = x.shape
+
+    def mask(rows, stream):
+        return None if drop is None else dropout_mask(rows, D, drop[0], drop[1], stream, x.dtype)
+
     h = x
     for i in range(cfg.n_layers - 1):
         p = f"layers.{i}."
         h = h + rmsa_block(layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w,
-                           p + "attn.", cfg, order)
+                           p + "attn.", cfg, order, mask(L, i))
     if cfg.cr_msa:
         p = "cr_msa."
         h = h + crmsa_block(layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w,
-                            p + "attn.", cfg, order)
+                            p + "attn.", cfg, order, mask(cfg.crmsa_k * 64, DROP_STREAM_CRMSA))
     if cfg.all_shortcut:
         h = h + x
     return layer_norm(h, w["norm.weight"], w["norm.bias"])

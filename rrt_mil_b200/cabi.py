@@ -12,7 +12,8 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librrt_b200.so")
 
-RRT_ABI_VERSION = 4
+RRT_ABI_VERSION = 5
+RRT_DROP_STREAM_CRMSA = 64
 RRT_MAX_RMSA_LAYERS = 8
 RRT_MAX_CRMSA_K = 16
 RRT_MAX_EPEG_K = 63
@@ -90,10 +91,12 @@ SIGNATURES = {
                                           C.c_int64, C.c_int32, _P, C.c_size_t, _P]),
     "rrt_train_tape_bytes": (C.c_int, [C.POINTER(RrtConfig), C.c_int64, C.POINTER(C.c_size_t)]),
     "rrt_encoder_forward_train": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P,
-                                            C.c_int64, _P, C.c_size_t, _P]),
+                                            C.c_int64, _P, C.c_size_t, C.c_float, C.c_uint64, _P]),
+    "rrt_dropout_mask": (C.c_int, [_P, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, _P]),
     "rrt_backward_workspace_bytes": (C.c_int, [C.POINTER(RrtConfig), C.c_int64, C.POINTER(C.c_size_t)]),
     "rrt_encoder_backward": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P, C.c_int64,
-                                       _P, C.c_size_t, C.POINTER(RrtGrads), _P, _P, C.c_size_t, _P]),
+                                       _P, C.c_size_t, C.POINTER(RrtGrads), _P, _P, C.c_size_t,
+                                       C.c_float, C.c_uint64, _P]),
     "rrt_attention_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_int32, _P]),
     "rrt_layernorm_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),

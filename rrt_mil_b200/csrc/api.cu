@@ -263,9 +263,14 @@ int f16_weight(const float* w32, const void* shadow, __half* scratch, size_t n, 
   return RRT_OK;
 }
 
+// training-mode proj_drop (modules/rmsa.py:70,132): probability and the seed of this step; the mask
+// stream of R-MSA layer i is i, the landmark MHA of CR-MSA uses kCrDropStream
+struct TrainOpts { float drop_p = 0.f; unsigned long long seed = 0; };
+constexpr unsigned kCrDropStream = 64;
+
 int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
                const rrt_attn_weights* a, const float* x, float* x1, int64_t L, Workspace& ws,
-               cudaStream_t st, int layer = 0) {
+               cudaStream_t st, int layer = 0, const TrainOpts& tr = TrainOpts{}) {
   __half* const ws_z = ws.z[layer];
   __half* const ws_qkv = ws.qkv[layer];
   __half* const ws_o = ws.o[layer];
@@ -297,7 +302,8 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
       RRT_CUDA(rrt::launch_rmsa_attention(ws_qkv, taps, ws_o, g, D, c->n_heads, c->epeg_k, st),
                "rmsa attention (flash)"); }
   rrt::GemmEpilogue e2;
-  e2.mode = rrt::kEpiResidualUnpart;
+  e2.mode = tr.drop_p > 0.f ? rrt::kEpiResidualUnpartDrop : rrt::kEpiResidualUnpart;
+  e2.drop = rrt::dropout_make(tr.drop_p, tr.seed, (unsigned)layer);
   e2.bias = a->proj_b;
   e2.resid = x;
   e2.grid = g;
@@ -307,7 +313,8 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
 }
 
 int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, const float* x0,
-                float* out, int64_t L, bool final_norm, Workspace& ws, cudaStream_t st) {
+                float* out, int64_t L, bool final_norm, Workspace& ws, cudaStream_t st,
+                const TrainOpts& tr = TrainOpts{}) {
   rrt::Grid g{};
   if (!crmsa_grid(L, &g)) return fail(RRT_E_INVALID, "bad geometry");
   const int D = c->dim, k = c->crmsa_k, T = k * g.R;
@@ -384,7 +391,13 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   rrt::GemmEpilogue e2;
   e2.bias = w->cr_attn.proj_b;
   { StageScope s_(kStLmProj, st);
-    if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lo, wp, ws.lout, false, T, D, D, e2, st), "landmark proj"); }
+    if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lo, wp, ws.lout, false, T, D, D, e2, st), "landmark proj");
+    if (tr.drop_p > 0.f) {  // L' = dropout(proj(...)): the tape keeps the masked landmarks
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      RRT_CUDA(rrt::launch_dropout_inplace(ws.lout, (size_t)T * D,
+                                           rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream), st),
+               "landmark proj dropout");
+    } }
   { StageScope s_(kStCrDispatch, st);
     if (!s_.skip()) RRT_CUDA(rrt::launch_crmsa_dispatch(x1, x0, ws.logits, ws.rstat, ws.lout,
                                         final_norm ? w->norm_w : nullptr,
@@ -394,18 +407,18 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
 }
 
 int encoder_forward(const rrt_config* cfg, const rrt_weights* w, const float* x, float* out,
-                    int64_t L, Workspace& ws, cudaStream_t st) {
+                    int64_t L, Workspace& ws, cudaStream_t st, const TrainOpts& tr = TrainOpts{}) {
   const int D = cfg->dim;
   const float* cur = x;
   for (int i = 0; i < cfg->n_rmsa_layers; ++i) {
     float* nxt = ws.xs[i];
     int rc = rmsa_block(cfg, w->layer_norm_w[i], w->layer_norm_b[i], &w->layer_attn[i], cur, nxt, L,
-                        ws, st, i);
+                        ws, st, i, tr);
     if (rc) return rc;
     cur = nxt;
   }
   const float* x0 = cfg->all_shortcut ? x : nullptr;
-  if (cfg->cr_msa) return crmsa_block(cfg, w, cur, x0, out, L, true, ws, st);
+  if (cfg->cr_msa) return crmsa_block(cfg, w, cur, x0, out, L, true, ws, st, tr);
   { StageScope s_(kStFinalLn, st); RRT_CUDA(rrt::launch_add_layernorm(cur, x0, w->norm_w, w->norm_b, out, (int)L, D, st), "final norm"); }
   return RRT_OK;
 }
@@ -887,7 +900,7 @@ int attention_module_backward(const rrt_config* c, const rrt_attn_weights* a, co
 
 int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, const float* dout,
                      int64_t L, const Workspace& tp, const rrt_grads* gr, float* dx, BwdWorkspace& b,
-                     cudaStream_t st) {
+                     cudaStream_t st, const TrainOpts& tr) {
   const int D = c->dim, nl = c->n_rmsa_layers;
   RRT_CUDA(cudaMemsetAsync(b.amax, 0, b.zero_bytes, st), "zero backward scalars");
   const float* x_last = nl > 0 ? tp.xs[nl - 1] : x;
@@ -912,7 +925,9 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
     { StageScope s_(kStBwdPrep, st, 2);
       RRT_CUDA(rrt::launch_amax(b.dLp, (size_t)T * D, &b.amax[0], st), "amax");
       RRT_CUDA(rrt::launch_grad_partition(b.dLp, ident, T, D, &b.amax[0], b.dy, b.dyT,
-                                          gr->cr_attn.proj_b, st), "landmark grad rows"); }
+                                          gr->cr_attn.proj_b, st,
+                                          rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream)),
+               "landmark grad rows"); }
     int rc = attention_module_backward(c, &w->cr_attn, &gr->cr_attn, tp.lm,
                                        reinterpret_cast<const __half*>(tp.lqkv), tp.lo, k, gc.R,
                                        c->crmsa_heads, false, &b.amax[0], b, st);
@@ -947,7 +962,8 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
       return fail(RRT_E_INVALID, "NULL gradient buffer");
     const float* x_in = i > 0 ? tp.xs[i - 1] : x;
     { StageScope s_(kStBwdPrep, st);
-      RRT_CUDA(rrt::launch_grad_partition(g, gg, gg.Np, D, &b.amax[am], b.dy, b.dyT, ga->proj_b, st),
+      RRT_CUDA(rrt::launch_grad_partition(g, gg, gg.Np, D, &b.amax[am], b.dy, b.dyT, ga->proj_b, st,
+                                          rrt::dropout_make(tr.drop_p, tr.seed, (unsigned)i)),
                "gradient partition"); }
     int rc = attention_module_backward(c, &w->layer_attn[i], ga, tp.z[i], tp.qkv[i], tp.o[i], gg.R, gg.P,
                                        c->n_heads, c->epeg != 0, &b.amax[am], b, st);
@@ -978,9 +994,16 @@ RRT_API int rrt_train_tape_bytes(const rrt_config* cfg, int64_t L, size_t* bytes
   return RRT_OK;
 }
 
+namespace {
+int check_drop(float p) {
+  if (!(p >= 0.f) || p >= 1.f) return fail(RRT_E_INVALID, "drop_p must be in [0, 1)");
+  return RRT_OK;
+}
+}  // namespace
+
 RRT_API int rrt_encoder_forward_train(const rrt_config* cfg, const rrt_weights* w, const float* x,
                                       float* out, int64_t L, void* tape, size_t tape_bytes,
-                                      void* stream) {
+                                      float drop_p, uint64_t seed, void* stream) {
   int rc = check_config(cfg);
   if (rc) return rc;
   if (!w || !x || !out || x == out) return fail(RRT_E_INVALID, "bad pointer");
@@ -988,7 +1011,12 @@ RRT_API int rrt_encoder_forward_train(const rrt_config* cfg, const rrt_weights* 
   if (!carve(cfg, L, tape, &ws, true)) return fail(RRT_E_INVALID, "bad bag length / geometry");
   if (!tape || tape_bytes < ws.bytes) return fail(RRT_E_WORKSPACE, "tape too small");
   if (((uintptr_t)tape) & 255) return fail(RRT_E_INVALID, "tape must be 256-byte aligned");
-  return encoder_forward(cfg, w, x, out, L, ws, (cudaStream_t)stream);
+  rc = check_drop(drop_p);
+  if (rc) return rc;
+  TrainOpts tr;
+  tr.drop_p = drop_p;
+  tr.seed = seed;
+  return encoder_forward(cfg, w, x, out, L, ws, (cudaStream_t)stream, tr);
 }
 
 RRT_API int rrt_backward_workspace_bytes(const rrt_config* cfg, int64_t L, size_t* bytes) {
@@ -1004,10 +1032,15 @@ RRT_API int rrt_backward_workspace_bytes(const rrt_config* cfg, int64_t L, size_
 RRT_API int rrt_encoder_backward(const rrt_config* cfg, const rrt_weights* w, const float* x,
                                  const float* dout, int64_t L, const void* tape, size_t tape_bytes,
                                  const rrt_grads* grads, float* dx, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
+                                 size_t workspace_bytes, float drop_p, uint64_t seed, void* stream) {
   int rc = check_config(cfg);
   if (rc) return rc;
   if (!w || !x || !dout || !grads || !dx || dx == dout) return fail(RRT_E_INVALID, "bad pointer");
+  rc = check_drop(drop_p);
+  if (rc) return rc;
+  TrainOpts tr;
+  tr.drop_p = drop_p;
+  tr.seed = seed;
   rc = check_backward_support(cfg, L);
   if (rc) return rc;
   Workspace tp{};
@@ -1018,7 +1051,7 @@ RRT_API int rrt_encoder_backward(const rrt_config* cfg, const rrt_weights* w, co
   if (!workspace || workspace_bytes < b.bytes) return fail(RRT_E_WORKSPACE, "workspace too small");
   if ((((uintptr_t)workspace) | ((uintptr_t)tape)) & 255)
     return fail(RRT_E_INVALID, "tape and workspace must be 256-byte aligned");
-  return encoder_backward(cfg, w, x, dout, L, tp, grads, dx, b, (cudaStream_t)stream);
+  return encoder_backward(cfg, w, x, dout, L, tp, grads, dx, b, (cudaStream_t)stream, tr);
 }
 
 RRT_API int rrt_attention_backward(const void* qkv, const void* o, const void* d_o, const float* taps,
@@ -1034,6 +1067,17 @@ RRT_API int rrt_attention_backward(const void* qkv, const void* o, const void* d
                                           taps, (__half*)d_qkv, taps ? d_taps : nullptr, nullptr, R, P,
                                           dim, heads, epeg_k, (cudaStream_t)stream),
            "attention backward");
+  return RRT_OK;
+}
+
+RRT_API int rrt_dropout_mask(float* out, int64_t n, float drop_p, uint64_t seed, uint32_t mask_stream,
+                             void* stream) {
+  if (!out || n < 0 || n % 4) return fail(RRT_E_INVALID, "bad argument");
+  int rc = check_drop(drop_p);
+  if (rc) return rc;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  RRT_CUDA(rrt::launch_dropout_mask(out, (size_t)n, rrt::dropout_make(drop_p, seed, mask_stream),
+                                    (cudaStream_t)stream), "dropout mask");
   return RRT_OK;
 }
 

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) grad_tile_kernel(const void* __restrict__
                                                         __half* __restrict__ outT,
                                                         float* __restrict__ colsum,
                                                         const uint32_t* __restrict__ amax, Grid grid,
-                                                        int M, int M64, int C) {
+                                                        int M, int M64, int C, Dropout drop) {
   __shared__ __align__(16) __half tile[kTileR * kLdt];
   __shared__ float red[8][kTileC];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -50,8 +50,13 @@ __global__ void __launch_bounds__(256) grad_tile_kernel(const void* __restrict__
     if (slot < M) {
       if (IN_F32) {
         int t = grid.H > 0 ? grid.slot_to_token(slot) : slot;
-        if (t < grid.L)
+        if (t < grid.L) {
           v = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(in_) + (size_t)t * C + c0) + lane);
+          if (drop.on()) {
+            const float4 m = dropout_scale4(drop, (unsigned long long)t * C + c0 + 4 * lane);
+            v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+          }
+        }
       } else {
         v = unpack_h4(__ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(in_) + (size_t)slot * C + c0) + lane));
       }
@@ -226,11 +231,43 @@ cudaError_t launch_amax(const float* x, size_t n, uint32_t* amax, cudaStream_t s
 }
 
 cudaError_t launch_grad_partition(const float* g, const Grid& grid, int M, int C, const uint32_t* amax,
-                                  __half* rows, __half* rowsT, float* colsum, cudaStream_t stream) {
+                                  __half* rows, __half* rowsT, float* colsum, cudaStream_t stream,
+                                  const Dropout& drop) {
   if (C % kTileC || M <= 0) return cudaErrorInvalidValue;
   const int M64 = (M + 63) / 64 * 64;
   dim3 gr(M64 / kTileR, C / kTileC);
-  grad_tile_kernel<true><<<gr, 256, 0, stream>>>(g, rows, rowsT, colsum, amax, grid, M, M64, C);
+  grad_tile_kernel<true><<<gr, 256, 0, stream>>>(g, rows, rowsT, colsum, amax, grid, M, M64, C, drop);
+  return cudaGetLastError();
+}
+
+namespace {
+template <bool MASK_ONLY>
+__global__ void __launch_bounds__(256) dropout_kernel(float* __restrict__ x, size_t n4, Dropout drop) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 m = dropout_scale4(drop, 4ull * i);
+    float4 v = MASK_ONLY ? make_float4(1.f, 1.f, 1.f, 1.f) : reinterpret_cast<float4*>(x)[i];
+    reinterpret_cast<float4*>(x)[i] = make_float4(v.x * m.x, v.y * m.y, v.z * m.z, v.w * m.w);
+  }
+}
+}  // namespace
+
+cudaError_t launch_dropout_inplace(float* x, size_t n, const Dropout& drop, cudaStream_t stream) {
+  if (n % 4) return cudaErrorInvalidValue;
+  if (n == 0 || !drop.on()) return cudaSuccess;
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dropout_kernel<false><<<blocks, 256, 0, stream>>>(x, n / 4, drop);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dropout_mask(float* out, size_t n, const Dropout& drop, cudaStream_t stream) {
+  if (n % 4) return cudaErrorInvalidValue;
+  if (n == 0) return cudaSuccess;
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  Dropout d = drop;
+  if (!d.on()) { d.thresh = 0; d.scale = 1.f; }
+  dropout_kernel<true><<<blocks, 256, 0, stream>>>(out, n / 4, d);
   return cudaGetLastError();
 }
 
@@ -240,7 +277,7 @@ cudaError_t launch_transpose_f16(const __half* in, int M, int C, __half* outT, f
   const int M64 = (M + 63) / 64 * 64;
   dim3 gr(M64 / kTileR, C / kTileC);
   Grid none{};
-  grad_tile_kernel<false><<<gr, 256, 0, stream>>>(in, nullptr, outT, colsum, amax, none, M, M64, C);
+  grad_tile_kernel<false><<<gr, 256, 0, stream>>>(in, nullptr, outT, colsum, amax, none, M, M64, C, Dropout{});
   return cudaGetLastError();
 }
 

@@ -49,6 +49,43 @@ struct Grid {
   }
 };
 
+// proj_drop of InnerAttention in training mode (modules/rmsa.py:70,132): counter-based, so the
+// backward pass regenerates the mask of the forward instead of storing it.  One splitmix64 hash per
+// group of 4 consecutive elements (flat index of the [rows, D] tensor the dropout acts on, token
+// order), 16 bits per element: an element is dropped when its 16-bit field is < thresh, survivors
+// are scaled by 1/(1-p).  oracle/rrt_oracle.py::dropout_mask restates the same rule in numpy.
+struct Dropout {
+  unsigned long long key = 0;  // seed + stream * golden ratio (host side: dropout_make)
+  uint32_t thresh = 0;         // round(p * 65536); 0 = off
+  float scale = 1.f;           // 1 / (1 - p)
+  __host__ __device__ bool on() const { return thresh != 0; }
+};
+inline Dropout dropout_make(float p, unsigned long long seed, unsigned stream_id) {
+  Dropout d;
+  if (p > 0.f) {
+    double t = (double)p * 65536.0 + 0.5;
+    d.thresh = t >= 65535.0 ? 65535u : (uint32_t)t;
+    d.scale = 1.f / (1.f - p);
+    d.key = seed + (unsigned long long)(stream_id + 1) * 0x9E3779B97F4A7C15ull;
+  }
+  return d;
+}
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// keep-and-scale factors of the 4 elements at flat indices idx .. idx+3 (idx % 4 == 0)
+__device__ __forceinline__ float4 dropout_scale4(const Dropout& d, unsigned long long idx) {
+  const unsigned long long h = splitmix64((idx >> 2) + d.key);
+  float4 m;
+  m.x = (uint32_t)(h & 0xffffu) >= d.thresh ? d.scale : 0.f;
+  m.y = (uint32_t)((h >> 16) & 0xffffu) >= d.thresh ? d.scale : 0.f;
+  m.z = (uint32_t)((h >> 32) & 0xffffu) >= d.thresh ? d.scale : 0.f;
+  m.w = (uint32_t)(h >> 48) >= d.thresh ? d.scale : 0.f;
+  return m;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

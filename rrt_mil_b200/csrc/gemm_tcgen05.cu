@@ -53,6 +53,7 @@ struct Tc05Params {
   const float* resid;
   Grid grid;
   int act;           // GemmActivation, store mode only
+  Dropout drop;      // kEpiResidualUnpartDrop only
   long long* trace;  // debug: per-CTA clock64 stamps (tools/gemm_trace.py), null in production
 };
 
@@ -61,6 +62,9 @@ struct Tc05Params {
 // 20.9 -> 31.5 us for the QKV GEMM when the switch sat in the common kernel).
 constexpr int kEpiStoreAct = 3;
 __host__ __device__ constexpr bool is_store_mode(int mode) { return mode == kEpiStore || mode == kEpiStoreAct; }
+__host__ __device__ constexpr bool is_resid_mode(int mode) {
+  return mode == kEpiResidualUnpart || mode == kEpiResidualUnpartDrop;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -107,7 +111,7 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
       int gr = m0 + quad * 32 + 4 * i + sub_r;
       long long o = -1;
       if (gr < p.M) {
-        if (MODE == kEpiResidualUnpart) {
+        if (is_resid_mode(MODE)) {
           int tok = p.grid.slot_to_token(gr);
           if (tok < p.grid.L) o = tok;
         } else {
@@ -144,7 +148,7 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
           v[i] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)orow[i] * p.N + gc));
       }
     };
-    if (MODE == kEpiResidualUnpart) {
+    if (is_resid_mode(MODE)) {
       load_resid(0);
       // the residual rows of the later chunks: pull them into L2 while the MMA warp is still busy, so
       // that the per-chunk loads below are L2 hits instead of NC serial HBM round trips
@@ -234,7 +238,12 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
         const int rl = 4 * i + sub_r;
         float4 a = *reinterpret_cast<const float4*>(scratch + rl * EPI_LD +
                                                     4 * ((lane & 7) ^ (rl & 7)));
-        if (MODE == kEpiResidualUnpart) {
+        if (MODE == kEpiResidualUnpartDrop) {  // x1 = x + dropout(o Wp^T + b)   (modules/rmsa.py:131-132)
+          float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (orow[i] >= 0) m = dropout_scale4(p.drop, (unsigned long long)orow[i] * p.N + gc);
+          v[i].x = fmaf(a.x + bv.x, m.x, v[i].x); v[i].y = fmaf(a.y + bv.y, m.y, v[i].y);
+          v[i].z = fmaf(a.z + bv.z, m.z, v[i].z); v[i].w = fmaf(a.w + bv.w, m.w, v[i].w);
+        } else if (is_resid_mode(MODE)) {
           v[i].x += a.x + bv.x; v[i].y += a.y + bv.y; v[i].z += a.z + bv.z; v[i].w += a.w + bv.w;
         } else {
           v[i] = make_float4(a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w);
@@ -246,7 +255,7 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
       for (int i = 0; i < 8; ++i)
         if (orow[i] >= 0 && col_ok) store_out4(out, (size_t)orow[i] * p.N + gc, v[i]);
       if (first && threadIdx.x == 128 && j < 2) stamp(p, 12 + 3 * j);
-      if (MODE == kEpiResidualUnpart && j + 1 < NC) load_resid(j + 1);  // next chunk's residual rows
+      if (is_resid_mode(MODE) && j + 1 < NC) load_resid(j + 1);  // next chunk's residual rows
       __syncwarp();
       }  // !kTmaStore
     }
@@ -749,7 +758,10 @@ cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool 
   p.bias = epi.bias; p.C = c; p.resid = epi.resid; p.grid = epi.grid;
   p.act = epi.mode == kEpiTanh ? (int)kActTanh : epi.act;
   p.trace = g_gemm_trace ? g_gemm_trace + (size_t)(g_trace_launch++ % 8) * 128 : nullptr;
-  if (epi.mode == kEpiResidualUnpart)
+  p.drop = epi.drop;
+  if (epi.mode == kEpiResidualUnpartDrop && epi.drop.on())
+    return out_f16 ? cudaErrorInvalidValue : launch_mode<kEpiResidualUnpartDrop, float>(a, w, p, stream);
+  if (is_resid_mode(epi.mode))
     return out_f16 ? cudaErrorInvalidValue : launch_mode<kEpiResidualUnpart, float>(a, w, p, stream);
   if (p.act != kActNone)
     return out_f16 ? launch_mode<kEpiStoreAct, __half>(a, w, p, stream)

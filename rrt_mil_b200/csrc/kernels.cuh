@@ -26,7 +26,9 @@ cudaError_t launch_add_layernorm(const float* x1, const float* x0, const float* 
 enum GemmEpilogueMode {
   kEpiStore = 0,          // c[m,n] = acc + bias[n]
   kEpiTanh = 1,           // c[m,n] = tanh(acc + bias[n])
-  kEpiResidualUnpart = 2  // row m is a region slot: out[token(m),n] = resid[token(m),n] + acc + bias[n]
+  kEpiResidualUnpart = 2, // row m is a region slot: out[token(m),n] = resid[token(m),n] + acc + bias[n]
+  // 3 is internal (store + run-time activation)
+  kEpiResidualUnpartDrop = 4  // training: ... + dropout(acc + bias[n]) (GemmEpilogue::drop)
 };
 enum GemmActivation { kActNone = 0, kActRelu = 1, kActGelu = 2, kActTanh = 3, kActSigmoid = 4 };
 struct GemmEpilogue {
@@ -35,6 +37,7 @@ struct GemmEpilogue {
   const float* bias = nullptr;   // [N] or null
   const float* resid = nullptr;  // [L, N] (mode 2)
   Grid grid{};                   // (mode 2)
+  Dropout drop{};                // (mode 4) mask index = token * N + n
 };
 
 // ---- gemm_tcgen05.cu ------------------------------------------------------------------
@@ -126,8 +129,14 @@ cudaError_t launch_attn_pool(const float* h, const float* hidden, const float* w
 cudaError_t launch_amax(const float* x, size_t n, uint32_t* amax, cudaStream_t stream);
 // g: fp32 [grid.L, C] token order -> rows: fp16 [M, C] slot order, * S(amax), pad slots 0 (grid.H == 0:
 // identity, M == grid.L); rowsT: fp16 [C, M64] transpose; colsum[c] += sum of the unscaled column
+// drop.on(): g is the gradient wrt the OUTPUT of a dropout; it is multiplied by the forward's mask first
 cudaError_t launch_grad_partition(const float* g, const Grid& grid, int M, int C, const uint32_t* amax,
-                                  __half* rows, __half* rowsT, float* colsum, cudaStream_t stream);
+                                  __half* rows, __half* rowsT, float* colsum, cudaStream_t stream,
+                                  const Dropout& drop = Dropout{});
+// x[i] *= mask(i) / (1-p) in place, x fp32 [rows, C] (the landmark projection output in training mode)
+cudaError_t launch_dropout_inplace(float* x, size_t n, const Dropout& drop, cudaStream_t stream);
+// mask(i)/(1-p) of n elements as fp32 (parity tests: the oracle consumes the same mask)
+cudaError_t launch_dropout_mask(float* out, size_t n, const Dropout& drop, cudaStream_t stream);
 // in: fp16 [M, C] -> outT fp16 [C, M64] (columns >= M zero); colsum[c] += column sum * 1/S(amax)
 cudaError_t launch_transpose_f16(const __half* in, int M, int C, __half* outT, float* colsum,
                                  const uint32_t* amax, cudaStream_t stream);

@@ -91,6 +91,7 @@ class _EncoderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, enc, x, *params):
         lib, cfg, N = cabi.lib(), enc._cfg, x.shape[0]
+        drop_p, seed = enc._train_dropout()
         with torch.cuda.device(x.device):
             n = C.c_size_t()
             cabi.check(lib.rrt_train_tape_bytes(C.byref(cfg), N, C.byref(n)), "rrt_train_tape_bytes")
@@ -98,10 +99,11 @@ class _EncoderFunction(torch.autograd.Function):
             out = torch.empty_like(x)
             w = enc._weights(x.device)
             rc = lib.rrt_encoder_forward_train(C.byref(cfg), C.byref(w), x.data_ptr(), out.data_ptr(), N,
-                                               tape.data_ptr(), n.value,
+                                               tape.data_ptr(), n.value, drop_p, seed,
                                                torch.cuda.current_stream(x.device).cuda_stream)
         cabi.check(rc, "rrt_encoder_forward_train")
         ctx.enc = enc
+        ctx.drop = (drop_p, seed)
         ctx.save_for_backward(x, tape, *params)
         return out
 
@@ -129,7 +131,7 @@ class _EncoderFunction(torch.autograd.Function):
             w = enc._weights(x.device)
             rc = lib.rrt_encoder_backward(C.byref(cfg), C.byref(w), x.data_ptr(), dout.data_ptr(), N,
                                           tape.data_ptr(), tape.numel(), C.byref(g), dx.data_ptr(),
-                                          ws.data_ptr(), n.value,
+                                          ws.data_ptr(), n.value, ctx.drop[0], ctx.drop[1],
                                           torch.cuda.current_stream(x.device).cuda_stream)
         cabi.check(rc, "rrt_encoder_backward")
         grads = [v if p_.requires_grad else None for v, p_ in zip(views, params)]
@@ -193,6 +195,8 @@ class RRTEncoder(nn.Module):
         self._cfg = cfg
         self._crmsa_mlp = bool(crmsa_mlp)
         self._shadow = {}
+        self._dropout_seed = None       # tests: pin the dropout seed of the next training forwards
+        self.last_dropout_seed = None   # seed the last training forward used
 
         if need_init:
             self.apply(initialize_weights)
@@ -285,6 +289,18 @@ class RRTEncoder(nn.Module):
             attn("cr_msa.attn.attn.", g.cr_attn)
         return g
 
+    def _train_dropout(self):
+        """(p, seed) of this forward: ``drop_out`` is active in training mode only, like ``nn.Dropout``.
+        The seed comes from torch's CPU generator, so ``torch.manual_seed`` makes steps reproducible
+        (and no device synchronisation is needed to draw it); ``_dropout_seed`` pins it (tests)."""
+        if not self.training or self.drop_out <= 0.0:
+            return 0.0, 0
+        seed = self._dropout_seed
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        self.last_dropout_seed = seed
+        return float(self.drop_out), seed
+
     def _needs_grad(self, x) -> bool:
         return torch.is_grad_enabled() and (
             x.requires_grad or any(p.requires_grad for p in self.parameters()))
@@ -300,9 +316,10 @@ class RRTEncoder(nn.Module):
                                           "torch.no_grad(), or use forward() for autograd")
             if self._crmsa_mlp:
                 raise NotImplementedError("backward through crmsa_mlp=True is not built")
-        if self.training and (self.drop_out > 0 or self.drop_path_rate > 0):
-            raise NotImplementedError("training-mode dropout / drop_path is not built: use .eval() "
-                                      "or drop_out=0")
+        if self.training and self.drop_path_rate > 0:
+            raise NotImplementedError("training-mode drop_path (default 0) is not built")
+        if self.training and self.drop_out > 0 and not allow_grad:
+            raise NotImplementedError("forward_bags is inference-only (no dropout): call .eval() first")
 
     def forward_bag(self, x: torch.Tensor) -> torch.Tensor:
         """One bag ``[N, D]`` float32 CUDA -> ``[N, D]``; enqueues on the current stream."""
@@ -313,7 +330,8 @@ class RRTEncoder(nn.Module):
         if N < 1:
             raise ValueError("empty bag")
         x = x.contiguous()
-        if self._needs_grad(x):   # autograd path: forward with a tape, backward kernels
+        if self._needs_grad(x) or (self.training and self.drop_out > 0):
+            # autograd / training path: forward with a tape (+ proj dropout), backward kernels
             return _EncoderFunction.apply(self, x, *self.parameters())
         lib, cfg = cabi.lib(), self._cfg
         with torch.cuda.device(x.device):

@@ -12,7 +12,8 @@ import torch.nn.functional as F
 
 from oracle import rrt_oracle as O
 import gpu_util as G
-from rrt_mil_b200 import cabi
+from golden_util import TRAIN_CASES, load_train_case, train_errors
+from rrt_mil_b200 import RRTEncoder, cabi
 
 pytestmark = pytest.mark.gpu
 
@@ -155,12 +156,67 @@ def test_encoder_backward_matches_oracle_autograd(name, L, over):
         assert e < TOL_GRAD, (n, e)
 
 
+@pytest.mark.parametrize("rows,D,p,seed,stream", [(700, 512, 0.1, 20240229, 0), (192, 512, 0.1, 5, 64),
+                                                  (333, 256, 0.25, 2 ** 61 + 12345, 3), (8, 128, 0.5, 0, 1)])
+def test_dropout_mask_matches_oracle(rows, D, p, seed, stream):
+    """The library's counter-based mask, bit for bit against the numpy restatement."""
+    out = torch.empty(rows, D, device="cuda")
+    rc = cabi.lib().rrt_dropout_mask(out.data_ptr(), rows * D, p, seed, stream, G.stream_ptr())
+    cabi.check(rc, "rrt_dropout_mask")
+    ref = O.dropout_mask(rows, D, p, seed, stream, dtype=torch.float32)
+    assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("name", sorted(TRAIN_CASES))
+def test_training_mode_matches_reference_fixture(name):
+    """.train() forward (proj_drop active) + backward through the CUDA kernels against the fixture the
+    REFERENCE produced in .train() with the same masks installed (oracle/make_golden.py)."""
+    cfg, w, x, gout, (p, seed), gold = load_train_case(name)
+    m = RRTEncoder(**cfg.to_dict(), drop_out=p).cuda().train()
+    m.load_state_dict({k: v.float() for k, v in w.items()}, strict=True)
+    m._dropout_seed = seed
+    xd = x.float().cuda().requires_grad_()
+    y = m(xd)
+    (y * gout.float().cuda()).sum().backward()
+    torch.cuda.synchronize()
+    e = train_errors(y, xd.grad, {n: q.grad for n, q in m.named_parameters()}, gold)
+    print(name, {k: f"{v:.1e}" for k, v in e.items()})
+    for k, v in e.items():
+        tol = 1e-3 if k.startswith("out") else TOL_GRAD
+        assert v < tol, (k, v, e)
+    if p > 0:   # a different seed gives a different (but equally valid) result; eval ignores drop_out
+        m._dropout_seed = seed + 1
+        with torch.no_grad():
+            y2 = m(xd.detach())
+            y_eval = m.eval()(xd.detach())
+        assert rel(y2, y.detach()) > 1e-2
+        assert rel(y_eval, y.detach()) > 1e-2
+        ref_eval = O.encoder_forward(x, w, cfg, "spec")
+        assert O.rel_err(y_eval.cpu(), ref_eval) < 1e-3
+
+
+def test_training_dropout_is_reproducible_under_manual_seed():
+    cfg = O.EncoderConfig()
+    m = G.make_encoder(cfg, O.make_weights(cfg, 3)).train()
+    x = O.make_bag(300, 512, 4).float().cuda()
+    torch.manual_seed(7)
+    a = m(x)
+    s1 = m.last_dropout_seed
+    b = m(x)
+    torch.manual_seed(7)
+    c = m(x)
+    assert m.last_dropout_seed == s1
+    assert torch.equal(a, c) and not torch.equal(a, b)
+
+
 def test_backward_rejects_unsupported():
     cfg = O.EncoderConfig(crmsa_mlp=True, crmsa_heads=1, crmsa_k=5)
     m = G.make_encoder(cfg, O.make_weights(cfg, 3))
     x = O.make_bag(200, 512, 4).float().cuda().requires_grad_()
     with pytest.raises(NotImplementedError):
         m(x)
+    with pytest.raises(NotImplementedError):     # drop_path (stochastic depth, default 0) is not built
+        RRTEncoder(drop_path=0.1).cuda().train()(x.detach())
     m2 = G.make_encoder(O.EncoderConfig(), O.make_weights(O.EncoderConfig(), 3)).train()
-    with pytest.raises(NotImplementedError):     # default drop_out = 0.1 is active in training mode
-        m2(x)
+    with pytest.raises(NotImplementedError):     # the batch entry point is inference-only
+        m2.forward_bags([x.detach()])

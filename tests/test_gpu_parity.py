@@ -254,3 +254,23 @@ def test_input_rank_handling_and_errors():
     assert xg.grad is not None and xg.grad.shape == xg.shape and torch.isfinite(xg.grad).all()
     with torch.no_grad(), pytest.raises(NotImplementedError):
         m(x.half())
+
+
+def test_host_pipeline_equals_per_bag_forward():
+    """Host buffers in / out through the three-stream pipeline (ragged bags, more bags than ring slots,
+    a slot that has to grow) == one forward per bag, bit for bit."""
+    from rrt_mil_b200.pipeline import HostPipeline
+    cfg, m = _default_encoder()
+    lens = [700, 300, 1500, 64, 2000, 999, 1500, 31]
+    hx = [O.make_bag(n, 512, 100 + i, dtype=torch.float32).pin_memory() for i, n in enumerate(lens)]
+    hy = [torch.empty(n, 512).pin_memory() for n in lens]
+    pipe = HostPipeline(m, n_streams=3)
+    hy2 = [torch.empty(n, 512).pin_memory() for n in lens]
+    pipe.run(hx, hy)
+    pipe.run(hx, hy2, sync=False)      # streamed calls: no wait in between
+    pipe.run(hx[::-1], hy[::-1], sync=False)
+    pipe.wait()
+    with torch.no_grad():
+        for x, y, y2 in zip(hx, hy, hy2):
+            ref = m(x.cuda()).cpu()
+            assert torch.equal(ref, y) and torch.equal(ref, y2)

@@ -6,7 +6,7 @@ import torch
 
 from oracle import rrt_oracle as O
 from oracle import _reference_shim as shim
-from golden_util import CASES, load_case, assert_matches_golden
+from golden_util import CASES, TRAIN_CASES, load_case, load_train_case, train_errors, assert_matches_golden
 
 # the 50k-token case needs ~2 GB in float64 reference order; keep it but only in "spec" order
 BIG = {"c4_n50000_g16"}
@@ -65,3 +65,33 @@ def test_region_slot_map_is_permutation_and_matches_view_permute():
     g = H // rs
     t = torch.arange(H * H).view(1, g, rs, g, rs).permute(0, 1, 3, 2, 4).reshape(-1)
     assert torch.equal(m, t)
+
+
+@pytest.mark.parametrize("name", sorted(TRAIN_CASES))
+@pytest.mark.parametrize("order", ["reference", "spec"])
+def test_oracle_training_mode_matches_reference_autograd(name, order):
+    """proj_drop placement + backward: oracle (with the counter-based masks) + torch autograd vs the
+    fixture produced by the reference in .train() with the same masks installed."""
+    cfg, w, x, gout, drop, gold = load_train_case(name)
+    w = {k: v.clone().requires_grad_() for k, v in w.items()}
+    xr = x.clone().requires_grad_()
+    y = O.encoder_forward(xr, w, cfg, order, drop=drop if drop[0] > 0 else None)
+    (y * gout).sum().backward()
+    e = train_errors(y, xr.grad, {k: v.grad for k, v in w.items()}, gold)
+    bad = {k: v for k, v in e.items() if not v <= 2e-6}
+    assert not bad, (bad, e)
+
+
+def test_dropout_mask_statistics_and_streams():
+    m = O.dropout_mask(4096, 512, 0.1, 123, 0)
+    keep = (m != 0).double().mean().item()
+    assert abs(keep - 0.9) < 2e-3 and abs(m.mean().item() - 1.0) < 3e-3
+    assert set(m.unique().tolist()) == {0.0, float(torch.tensor(1.0 / 0.9, dtype=torch.float32))}
+    assert not torch.equal(m, O.dropout_mask(4096, 512, 0.1, 123, 1))      # streams differ
+    assert not torch.equal(m, O.dropout_mask(4096, 512, 0.1, 124, 0))      # seeds differ
+    assert torch.equal(m, O.dropout_mask(4096, 512, 0.1, 123, 0))          # counter-based: reproducible
+    assert torch.equal(O.dropout_mask(8, 128, 0.0, 1, 0), torch.ones(8, 128, dtype=torch.float64))
+    # rows / columns are uncorrelated: per-row and per-column keep rates stay inside 6 sigma
+    k = (m != 0).double()
+    assert (k.mean(1) - 0.9).abs().max() < 6 * (0.09 / 512) ** 0.5
+    assert (k.mean(0) - 0.9).abs().max() < 6 * (0.09 / 4096) ** 0.5
