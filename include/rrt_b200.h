@@ -71,7 +71,13 @@ typedef struct rrt_config {
   int32_t crmsa_mlp;        /* phi = Linear-tanh-Linear instead of a [D,k] matrix      */
   int32_t all_shortcut;
   int32_t math_mode;        /* RRT_MATH_*                                              */
+  /* ablation positional encoding (modules/rrt.py:150-160, modules/emb_position.py:24-82) */
+  int32_t pos;              /* RRT_POS_NONE / RRT_POS_PEG / RRT_POS_PPEG                */
+  int32_t pos_pos;          /* -1: before the first layer; 0: before R-MSA layer 1      */
+  int32_t peg_k;            /* odd kernel size of the first conv                        */
+  int32_t peg_1d;           /* (k,1) column kernels instead of k x k                    */
 } rrt_config;
+enum { RRT_POS_NONE = 0, RRT_POS_PEG = 1, RRT_POS_PPEG = 2 };
 
 /* One InnerAttention (modules/rmsa.py:56-89).  qkv_b may be NULL (qkv_bias=False);
  * pe_w is the depthwise EPEG taps [heads, epeg_k] (= pe.weight[h,0,:,0]) or NULL.
@@ -103,6 +109,10 @@ typedef struct rrt_weights {
   const float* cr_phi_w2; /* cr_msa.attn.phi.2.weight [k,D/4] (crmsa_mlp = 1) */
   const void* cr_phi_w1_f16; /* optional fp16 shadow of cr_phi_w1 */
   rrt_attn_weights cr_attn; /* cr_msa.attn.attn.* (pe_w NULL) */
+  /* pos_embedding.proj / proj1 / proj2 .weight [D,1,k,k] ([D,1,k,1] with peg_1d) and .bias [D] or NULL;
+   * PEG uses index 0 only, PPEG all three (kernel sizes peg_k, 5, 3) */
+  const float* pos_w[3];
+  const float* pos_b[3];
 } rrt_weights;
 
 /* ---- housekeeping ------------------------------------------------------------------- */
@@ -296,6 +306,12 @@ RRT_API int rrt_stage_timing_enable(int32_t on);
 RRT_API int32_t rrt_stage_count(void);
 RRT_API const char* rrt_stage_name(int32_t stage);
 RRT_API int rrt_stage_timing_read(int32_t stage, double* total_ms, int64_t* launches);
+
+/* PEG / PPEG alone (parity tests): out[L,D] = pos_embedding(x[L,D]); ppeg != 0: three convs (k, 5, 3).
+ * w / b: arrays of 3 device pointers as in rrt_weights.pos_w / pos_b.  x != out. */
+RRT_API int rrt_peg_forward(const float* x, float* out, int64_t L, int32_t dim, int32_t peg_k,
+                            int32_t ppeg, int32_t peg_1d, const float* const* w, const float* const* b,
+                            void* stream);
 
 /* out[L,D] = LayerNorm(x[L,D]) (eps 1e-5). */
 RRT_API int rrt_layernorm_forward(const float* x, const float* gamma, const float* beta,

@@ -58,6 +58,11 @@ CASES = [
     ("d256_min_region_num", 600, dict(mlp_dim=256, min_region_num=700), 7, "randn"),
     ("d256_min_region_ratio", 300, dict(mlp_dim=256, min_region_ratio=5.0, region_num=16), 7, "randn"),
     ("d128_h2_k3", 400, dict(mlp_dim=128, n_heads=2, crmsa_heads=2, epeg_k=3), 7, "randn"),
+    # PEG / PPEG ablation positional encodings (modules/emb_position.py:24-82)
+    ("ppeg_before_layers", 1000, dict(pos="ppeg", pos_pos=-1), 7, "relu"),
+    ("peg_k5_between_layers", 900, dict(mlp_dim=256, pos="peg", pos_pos=0, peg_k=5, n_layers=3, peg_bias=False), 7, "randn"),
+    ("ppeg_1d_tiny_grid", 30, dict(mlp_dim=128, n_heads=4, crmsa_heads=4, pos="ppeg", pos_pos=-1, peg_1d=True, peg_k=3), 7, "randn"),
+    ("ppeg_n9000", 9000, dict(pos="ppeg", pos_pos=-1), 7, "relu"),
 ]
 
 # RRTMIL end-to-end: name, L, input_dim, n_classes, act, da_act, da_bias, encoder overrides

@@ -63,6 +63,12 @@ class EncoderConfig:
     all_shortcut: bool = False
     crmsa_mlp: bool = False
     crmsa_heads: int = 8
+    # ablation positional encoding (modules/rrt.py:150-160)
+    pos: str = "none"
+    pos_pos: int = 0
+    peg_k: int = 7
+    peg_bias: bool = True
+    peg_1d: bool = False
 
     def to_dict(self):
         return asdict(self)
@@ -244,6 +250,26 @@ def crmsa_block(z, w, prefix, cfg: EncoderConfig, order, mask=None):
     return _from_regions(y, L, H, rs)
 
 
+def pos_embedding(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfig) -> torch.Tensor:
+    """PEG / PPEG on one bag [L,D] (modules/emb_position.py:36-58, 66-82): fold the tokens row-major
+    into a ceil(sqrt(L)) square, filling the tail with the FIRST tokens; PPEG zero-extends grids smaller
+    than 7x7; depthwise "same" convs (k; PPEG also 5 and 3) plus the identity; drop the fill."""
+    L, D = x.shape
+    H = _ceil_sqrt(L)
+    add = H * H - L
+    g = torch.cat([x, x[:add]]) if add > 0 else x
+    if cfg.pos == "ppeg" and H < 7:
+        g = torch.cat([g, torch.zeros(49 - H * H, D, dtype=x.dtype)])
+        H = 7
+    feat = g.t().reshape(1, D, H, H)
+    out = feat
+    for name, k in (("proj", cfg.peg_k),) + ((("proj1", 5), ("proj2", 3)) if cfg.pos == "ppeg" else ()):
+        pad = (k // 2, 0) if cfg.peg_1d else k // 2
+        out = out + F.conv2d(feat, w[f"pos_embedding.{name}.weight"], w.get(f"pos_embedding.{name}.bias"),
+                             padding=pad, groups=D)
+    return out.reshape(D, H * H).t()[:L]
+
+
 def encoder_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfig,
                     order: str = "reference", drop=None) -> torch.Tensor:
     """``RRTEncoder.forward`` for one bag ``x`` [L,D] -> [L,D] (modules/rrt.py:165-202).
@@ -255,8 +281,13 @@ def encoder_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderCon
     def mask(rows, stream):
         return None if drop is None else dropout_mask(rows, D, drop[0], drop[1], stream, x.dtype)
 
+    has_pos = cfg.pos in ("peg", "ppeg")
     h = x
+    if has_pos and cfg.pos_pos == -1:                      # modules/rrt.py:181-182
+        h = pos_embedding(h, w, cfg)
     for i in range(cfg.n_layers - 1):
+        if i == 1 and has_pos and cfg.pos_pos == 0:        # modules/rrt.py:186-187
+            h = pos_embedding(h, w, cfg)
         p = f"layers.{i}."
         h = h + rmsa_block(layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w,
                            p + "attn.", cfg, order, mask(L, i))
@@ -346,6 +377,12 @@ def weight_shapes(cfg: EncoderConfig) -> Dict[str, Tuple[int, ...]]:
         else:
             shp["cr_msa.attn.phi"] = (D, cfg.crmsa_k)
         attn("cr_msa.attn.attn.", False)
+    # last, so that the seeded streams of the entries above do not move when pos is switched on
+    if cfg.pos in ("peg", "ppeg"):
+        for name, k in (("proj", cfg.peg_k),) + ((("proj1", 5), ("proj2", 3)) if cfg.pos == "ppeg" else ()):
+            shp[f"pos_embedding.{name}.weight"] = (D, 1, k, 1 if cfg.peg_1d else k)
+            if cfg.peg_bias:
+                shp[f"pos_embedding.{name}.bias"] = (D,)
     return shp
 
 
@@ -361,6 +398,8 @@ def make_weights(cfg: EncoderConfig, seed: int, dtype=torch.float64,
             a = 1.0 + 0.1 * rs.standard_normal(shape) if randomize_bias else np.ones(shape)
         elif name.endswith("bias"):
             a = 0.1 * rs.standard_normal(shape) if randomize_bias else np.zeros(shape)
+        elif name.startswith("pos_embedding.") and name.endswith("weight"):
+            a = rs.standard_normal(shape) * (0.5 / math.sqrt(shape[2] * shape[3]))
         elif name.endswith("pe.weight"):
             fan = shape[2]  # Conv2d(h,h,(k,1),groups=h): fan_in = fan_out = k per group
             a = rs.standard_normal(shape) * math.sqrt(2.0 / (fan + fan))

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "librrt_b200.so")
 
 RRT_ABI_VERSION = 5
 RRT_DROP_STREAM_CRMSA = 64
+RRT_POS_NONE, RRT_POS_PEG, RRT_POS_PPEG = 0, 1, 2
 RRT_MAX_RMSA_LAYERS = 8
 RRT_MAX_CRMSA_K = 16
 RRT_MAX_EPEG_K = 63
@@ -33,6 +34,7 @@ class RrtConfig(C.Structure):
         ("qkv_bias", C.c_int32), ("cr_msa", C.c_int32), ("crmsa_k", C.c_int32),
         ("crmsa_heads", C.c_int32), ("crmsa_mlp", C.c_int32), ("all_shortcut", C.c_int32),
         ("math_mode", C.c_int32),
+        ("pos", C.c_int32), ("pos_pos", C.c_int32), ("peg_k", C.c_int32), ("peg_1d", C.c_int32),
     ]
 
 
@@ -51,6 +53,7 @@ class RrtWeights(C.Structure):
         ("cr_norm_w", c_float_p), ("cr_norm_b", c_float_p), ("cr_phi", c_float_p),
         ("cr_phi_w1", c_float_p), ("cr_phi_w2", c_float_p), ("cr_phi_w1_f16", c_float_p),
         ("cr_attn", RrtAttnWeights),
+        ("pos_w", c_float_p * 3), ("pos_b", c_float_p * 3),
     ]
 
 
@@ -92,6 +95,8 @@ SIGNATURES = {
     "rrt_train_tape_bytes": (C.c_int, [C.POINTER(RrtConfig), C.c_int64, C.POINTER(C.c_size_t)]),
     "rrt_encoder_forward_train": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P,
                                             C.c_int64, _P, C.c_size_t, C.c_float, C.c_uint64, _P]),
+    "rrt_peg_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.POINTER(c_float_p), C.POINTER(c_float_p), _P]),
     "rrt_dropout_mask": (C.c_int, [_P, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, _P]),
     "rrt_backward_workspace_bytes": (C.c_int, [C.POINTER(RrtConfig), C.c_int64, C.POINTER(C.c_size_t)]),
     "rrt_encoder_backward": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P, C.c_int64,

@@ -157,6 +157,12 @@ int check_config(const rrt_config* c) {
       return fail(RRT_E_INVALID, "CR-MSA head_dim must be a multiple of 32");
   }
   if (c->math_mode != RRT_MATH_F16) return fail(RRT_E_INVALID, "unknown math_mode");
+  if (c->pos != RRT_POS_NONE) {
+    if (c->pos != RRT_POS_PEG && c->pos != RRT_POS_PPEG) return fail(RRT_E_INVALID, "unknown pos");
+    if (c->pos_pos != -1 && c->pos_pos != 0) return fail(RRT_E_INVALID, "pos_pos must be -1 or 0");
+    if (c->peg_k < 1 || c->peg_k > 31 || c->peg_k % 2 == 0)
+      return fail(RRT_E_INVALID, "peg_k must be odd and <= 31");
+  }
   return RRT_OK;
 }
 
@@ -179,6 +185,8 @@ struct Workspace {
   float* lout;     // [k*R_c, D]
   float* hidden;   // [Np_c, D/4] (crmsa_mlp)
   __half* wconv;   // [3D*D + D*D] fp16 weights when the caller passes no shadow
+  float* pe_out;   // [L, D] output of the PEG / PPEG positional encoding (pos != none)
+  float* pe_w;     // folded depthwise kernel + bias (peg_scratch_floats)
   size_t bytes;
 };
 
@@ -237,6 +245,10 @@ bool carve(const rrt_config* c, int64_t L, void* base, Workspace* ws, bool train
   ws->lout = (float*)take(T * D * 4);
   ws->hidden = (float*)take(mlp ? np_c * (D / 4) * 4 : 0);
   ws->wconv = (__half*)take(4 * D * D * 2);
+  const bool pos = c->pos != RRT_POS_NONE;
+  ws->pe_out = (float*)take(pos ? (size_t)L * D * 4 : 0);
+  ws->pe_w = (float*)take(pos ? rrt::peg_scratch_floats((int)D, c->peg_k, c->pos == RRT_POS_PPEG,
+                                                         c->peg_1d != 0) * 4 : 0);
   ws->bytes = off + 256;
   return true;
 }
@@ -410,7 +422,25 @@ int encoder_forward(const rrt_config* cfg, const rrt_weights* w, const float* x,
                     int64_t L, Workspace& ws, cudaStream_t st, const TrainOpts& tr = TrainOpts{}) {
   const int D = cfg->dim;
   const float* cur = x;
+  // ablation positional encoding: before the first layer (pos_pos = -1) or before R-MSA layer 1
+  // (pos_pos = 0; a no-op unless n_layers >= 3, exactly as modules/rrt.py:181-188)
+  auto pos_embed = [&]() -> int {
+    if (!w->pos_w[0]) return fail(RRT_E_INVALID, "pos_embedding weights missing");
+    StageScope s_(kStOther, st, 2);
+    RRT_CUDA(rrt::launch_peg(cur, ws.pe_out, (int)L, D, cfg->peg_k, cfg->pos == RRT_POS_PPEG,
+                             cfg->peg_1d != 0, w->pos_w, w->pos_b, ws.pe_w, st), "pos_embedding");
+    cur = ws.pe_out;
+    return RRT_OK;
+  };
+  if (cfg->pos != RRT_POS_NONE && cfg->pos_pos == -1) {
+    int rc = pos_embed();
+    if (rc) return rc;
+  }
   for (int i = 0; i < cfg->n_rmsa_layers; ++i) {
+    if (i == 1 && cfg->pos != RRT_POS_NONE && cfg->pos_pos == 0) {
+      int rc = pos_embed();
+      if (rc) return rc;
+    }
     float* nxt = ws.xs[i];
     int rc = rmsa_block(cfg, w->layer_norm_w[i], w->layer_norm_b[i], &w->layer_attn[i], cur, nxt, L,
                         ws, st, i, tr);
@@ -760,6 +790,23 @@ RRT_API int rrt_linear_f16_forward(const void* a_f16, const void* w_f16, const f
   return RRT_OK;
 }
 
+RRT_API int rrt_peg_forward(const float* x, float* out, int64_t L, int32_t dim, int32_t peg_k,
+                            int32_t ppeg, int32_t peg_1d, const float* const* w, const float* const* b,
+                            void* stream) {
+  if (!x || !out || x == out || !w || !b || L < 1 || L > (1 << 28) || dim < 4 || dim % 4 ||
+      peg_k < 1 || peg_k > 31 || peg_k % 2 == 0)
+    return fail(RRT_E_INVALID, "bad argument");
+  float* scratch = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  RRT_CUDA(cudaMallocAsync((void**)&scratch, rrt::peg_scratch_floats(dim, peg_k, ppeg != 0, peg_1d != 0) * 4, st),
+           "peg scratch");
+  StageScope s_(kStOther, st, 2);
+  cudaError_t e = rrt::launch_peg(x, out, (int)L, dim, peg_k, ppeg != 0, peg_1d != 0, w, b, scratch, st);
+  cudaFreeAsync(scratch, st);
+  if (e != cudaSuccess) return fail_cuda(e, "peg");
+  return RRT_OK;
+}
+
 RRT_API int rrt_layernorm_forward(const float* x, const float* gamma, const float* beta,
                                   float* out, int64_t L, int32_t D, void* stream) {
   if (!x || !gamma || !beta || !out) return fail(RRT_E_INVALID, "NULL pointer");
@@ -838,6 +885,7 @@ bool carve_bwd(const rrt_config* c, int64_t L, void* base, BwdWorkspace* b) {
 }
 
 int check_backward_support(const rrt_config* c, int64_t L) {
+  if (c->pos != RRT_POS_NONE) return fail(RRT_E_INVALID, "backward: PEG / PPEG (ablation) is not covered");
   if (c->cr_msa && c->crmsa_mlp) return fail(RRT_E_INVALID, "backward: crmsa_mlp is not covered");
   if (c->n_rmsa_layers == 0 && !c->cr_msa) return fail(RRT_E_INVALID, "backward: encoder has no block");
   if (c->n_rmsa_layers > 0) {

@@ -116,6 +116,13 @@ cudaError_t launch_crmsa_dispatch(const float* x1, const float* x0, const float*
                                   const float* beta, float* out, const Grid& grid, int D, int k,
                                   cudaStream_t stream);
 
+// ---- peg.cu: PEG / PPEG depthwise-conv positional encodings ------------------
+// out[L,D] = x + sum_j conv_kj(grid(x)) (+ biases); w/b: the 1 (PEG) or 3 (PPEG: k, 5, 3) reference
+// Conv2d weights [D,1,k,k] ([D,1,k,1] with conv_1d) and biases (nullable).  scratch: peg_scratch_floats.
+size_t peg_scratch_floats(int D, int peg_k, bool ppeg, bool conv_1d);
+cudaError_t launch_peg(const float* x, float* out, int L, int D, int peg_k, bool ppeg, bool conv_1d,
+                       const float* const* w, const float* const* b, float* scratch, cudaStream_t stream);
+
 // ---- mil_head.cu: DAttention pooling + predictor behind the encoder ---------
 size_t attn_pool_scratch_floats(int L, int D, int hid);
 cudaError_t launch_attn_pool(const float* h, const float* hidden, const float* w2, const float* b2,

@@ -83,6 +83,28 @@ class TransLayer(_ParamHolder):
         self.attn = attn_module
 
 
+class PEG(_ParamHolder):
+    """Parameters of modules/emb_position.py:60-82: one depthwise Conv2d ``proj``."""
+
+    def __init__(self, dim=512, k=7, bias=True, conv_1d=False):
+        super().__init__()
+        ks, pad = ((k, 1), (k // 2, 0)) if conv_1d else (k, k // 2)
+        self.proj = nn.Conv2d(dim, dim, ks, 1, pad, groups=dim, bias=bias)
+
+
+class PPEG(_ParamHolder):
+    """Parameters of modules/emb_position.py:24-58: depthwise Conv2d ``proj`` (k), ``proj1`` (5), ``proj2`` (3)."""
+
+    def __init__(self, dim=512, k=7, conv_1d=False, bias=True):
+        super().__init__()
+
+        def conv(kk):
+            ks, pad = ((kk, 1), (kk // 2, 0)) if conv_1d else (kk, kk // 2)
+            return nn.Conv2d(dim, dim, ks, 1, pad, groups=dim, bias=bias)
+
+        self.proj, self.proj1, self.proj2 = conv(k), conv(5), conv(3)
+
+
 class _EncoderFunction(torch.autograd.Function):
     """Autograd bridge: forward with a tape (``rrt_encoder_forward_train``), backward through
     ``rrt_encoder_backward``.  Parameters travel as explicit inputs so that autograd routes their
@@ -150,8 +172,12 @@ class RRTEncoder(nn.Module):
         if attn != 'rmsa':
             raise NotImplementedError(f"attn={attn!r}: only 'rmsa' is built (the reference also "
                                       "raises for unknown values, modules/rrt.py:89-90)")
-        if pos not in ('none', None):
-            raise NotImplementedError(f"pos={pos!r}: ablation positional encodings are not built")
+        if pos not in ('none', None, 'peg', 'ppeg'):
+            # 'sincos' cannot be constructed in the reference either with numpy >= 1.24 (np.float,
+            # modules/emb_position.py:97); any other string is nn.Identity there
+            raise NotImplementedError(f"pos={pos!r}: only 'none', 'peg' and 'ppeg' are built")
+        if pos in ('peg', 'ppeg') and (peg_k % 2 == 0 or peg_k > 31 or pos_pos not in (-1, 0)):
+            raise ValueError("peg_k must be odd and <= 31, pos_pos -1 or 0")
         if ffn:
             raise NotImplementedError("ffn=True (ablation MLP) is not built")
         epeg_2d = kwargs.pop('epeg_2d', False)
@@ -182,7 +208,12 @@ class RRTEncoder(nn.Module):
         self.cr_msa = (TransLayer(mlp_dim, CrossRegionAttention(mlp_dim, crmsa_heads, qkv_bias,
                                                                 crmsa_k, crmsa_mlp))
                        if cr_msa else nn.Identity())
-        self.pos_embedding = nn.Identity()
+        if pos == 'ppeg':
+            self.pos_embedding = PPEG(dim=mlp_dim, k=peg_k, bias=peg_bias, conv_1d=peg_1d)
+        elif pos == 'peg':
+            self.pos_embedding = PEG(mlp_dim, k=peg_k, bias=peg_bias, conv_1d=peg_1d)
+        else:
+            self.pos_embedding = nn.Identity()
 
         cfg = cabi.RrtConfig()
         cfg.dim, cfg.n_rmsa_layers, cfg.n_heads = mlp_dim, n_layers - 1, n_heads
@@ -192,6 +223,8 @@ class RRTEncoder(nn.Module):
         cfg.cr_msa, cfg.crmsa_k, cfg.crmsa_heads = int(bool(cr_msa)), int(crmsa_k), int(crmsa_heads)
         cfg.crmsa_mlp, cfg.all_shortcut = int(bool(crmsa_mlp)), int(bool(all_shortcut))
         cfg.math_mode = cabi.RRT_MATH_F16
+        cfg.pos = {'peg': cabi.RRT_POS_PEG, 'ppeg': cabi.RRT_POS_PPEG}.get(pos, cabi.RRT_POS_NONE)
+        cfg.pos_pos, cfg.peg_k, cfg.peg_1d = int(pos_pos), int(peg_k), int(bool(peg_1d))
         self._cfg = cfg
         self._crmsa_mlp = bool(crmsa_mlp)
         self._shadow = {}
@@ -264,6 +297,10 @@ class RRTEncoder(nn.Module):
             else:
                 w.cr_phi = p(cr.attn.phi, device)
             self._attn_weights(cr.attn.attn, w.cr_attn, device, shadows=True)
+        if self._cfg.pos != cabi.RRT_POS_NONE:
+            pe = self.pos_embedding
+            for j, conv in enumerate([pe.proj] + ([pe.proj1, pe.proj2] if self._cfg.pos == cabi.RRT_POS_PPEG else [])):
+                w.pos_w[j], w.pos_b[j] = p(conv.weight, device), p(conv.bias, device)
         return w
 
     def _grads(self, by_name) -> cabi.RrtGrads:
@@ -316,6 +353,8 @@ class RRTEncoder(nn.Module):
                                           "torch.no_grad(), or use forward() for autograd")
             if self._crmsa_mlp:
                 raise NotImplementedError("backward through crmsa_mlp=True is not built")
+            if self._cfg.pos != cabi.RRT_POS_NONE:
+                raise NotImplementedError("backward through the PEG / PPEG ablation is not built")
         if self.training and self.drop_path_rate > 0:
             raise NotImplementedError("training-mode drop_path (default 0) is not built")
         if self.training and self.drop_out > 0 and not allow_grad:

@@ -73,8 +73,27 @@ def test_workspace_bytes_and_config_validation(lib):
     assert b"geometry" in lib.rrt_last_error() or b"bag" in lib.rrt_last_error()
 
 
-def test_struct_layout_matches_header_sizes():
-    # 64-bit ABI: config = 6 int32 + double + 9 int32 (padded to 8) ; weights = pointer table
-    assert C.sizeof(cabi.RrtConfig) == 72
-    assert C.sizeof(cabi.RrtAttnWeights) == 7 * 8
-    assert C.sizeof(cabi.RrtWeights) == 8 * (2 + 2 * 8 + 7 * 8 + 6 + 7)
+def test_struct_layout_matches_header_sizes(tmp_path):
+    """The ctypes mirrors against the header itself: gcc compiles include/rrt_b200.h and prints the
+    sizes and a few offsets of the POD structs."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "rrt_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(rrt_config), sizeof(rrt_attn_weights),
+         sizeof(rrt_weights), sizeof(rrt_grads), offsetof(rrt_config, min_region_ratio),
+         offsetof(rrt_config, pos), offsetof(rrt_weights, cr_attn), offsetof(rrt_weights, pos_w),
+         offsetof(rrt_grads, cr_attn));
+  return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(cabi.RrtConfig), C.sizeof(cabi.RrtAttnWeights), C.sizeof(cabi.RrtWeights),
+            C.sizeof(cabi.RrtGrads), cabi.RrtConfig.min_region_ratio.offset, cabi.RrtConfig.pos.offset,
+            cabi.RrtWeights.cr_attn.offset, cabi.RrtWeights.pos_w.offset, cabi.RrtGrads.cr_attn.offset]
+    assert got == want

@@ -274,3 +274,38 @@ def test_host_pipeline_equals_per_bag_forward():
         for x, y, y2 in zip(hx, hy, hy2):
             ref = m(x.cuda()).cpu()
             assert torch.equal(ref, y) and torch.equal(ref, y2)
+
+
+@pytest.mark.parametrize("L,D,kind,k,one_d,bias", [
+    (1000, 512, "ppeg", 7, False, True), (900, 256, "peg", 5, False, False), (30, 128, "ppeg", 3, True, True),
+    (1, 128, "ppeg", 7, False, True), (49, 128, "peg", 7, False, True), (2, 128, "peg", 3, False, True),
+    (5000, 384, "ppeg", 9, True, False)])
+def test_peg_ppeg_match_oracle(L, D, kind, k, one_d, bias):
+    """PEG / PPEG alone through rrt_peg_forward: wrap-around fill with the first tokens, PPEG's zero
+    extension below 7x7, 2-D and (k,1) kernels, with and without bias; fp32 streaming kernel -> 1e-5."""
+    import ctypes as C
+    from rrt_mil_b200 import cabi
+    cfg = O.EncoderConfig(mlp_dim=D, pos=kind, pos_pos=-1, peg_k=k, peg_1d=one_d, peg_bias=bias,
+                          n_heads=4, crmsa_heads=4)
+    w = O.make_weights(cfg, 17)
+    x = O.make_bag(L, D, 18)
+    ref = O.pos_embedding(x, w, cfg)
+    names = ["proj"] + (["proj1", "proj2"] if kind == "ppeg" else [])
+    wd = [w[f"pos_embedding.{n}.weight"].float().cuda().contiguous() for n in names]
+    bd = [w[f"pos_embedding.{n}.bias"].float().cuda() for n in names] if bias else []
+    wp = (C.c_void_p * 3)(*([t.data_ptr() for t in wd] + [None] * (3 - len(wd))))
+    bp = (C.c_void_p * 3)(*([t.data_ptr() for t in bd] + [None] * (3 - len(bd))))
+    xd = x.float().cuda()
+    out = torch.empty_like(xd)
+    rc = cabi.lib().rrt_peg_forward(xd.data_ptr(), out.data_ptr(), L, D, k, int(kind == "ppeg"), int(one_d),
+                                    wp, bp, G.stream_ptr())
+    cabi.check(rc, "rrt_peg_forward")
+    torch.cuda.synchronize()
+    assert O.rel_err(out.cpu(), ref) < TOL_FP32
+
+
+def test_peg_encoder_rejects_autograd():
+    cfg = O.EncoderConfig(pos="ppeg", pos_pos=-1)
+    m = G.make_encoder(cfg, O.make_weights(cfg, 3))
+    with pytest.raises(NotImplementedError):
+        m(O.make_bag(100, 512, 1).float().cuda().requires_grad_())

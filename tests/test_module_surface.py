@@ -16,6 +16,8 @@ VARIANTS = [
     dict(qkv_bias=False, epeg=False),
     dict(n_layers=3, cr_msa=False),
     dict(mlp_dim=256, region_num=16, epeg_bias=False),
+    dict(pos='ppeg', pos_pos=-1),
+    dict(pos='peg', peg_k=5, peg_1d=True, peg_bias=False, n_layers=3),
 ]
 
 
@@ -62,7 +64,9 @@ def test_unsupported_options_raise_loudly():
     with pytest.raises(NotImplementedError):
         RRTEncoder(attn='ntrans')
     with pytest.raises(NotImplementedError):
-        RRTEncoder(pos='ppeg')
+        RRTEncoder(pos='sincos')
+    with pytest.raises(ValueError):
+        RRTEncoder(pos='ppeg', peg_k=4)
     with pytest.raises(NotImplementedError):
         RRTEncoder(ffn=True)
     with pytest.raises(NotImplementedError):
