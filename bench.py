@@ -335,7 +335,14 @@ def run_b200_arm(args):
         t1e.record()
         torch.cuda.synchronize()
         us = t0e.elapsed_time(t1e) * 1e3 / n_tr
+        cabi.stage_timing(True)
+        for _ in range(3):
+            train_step()
+        torch.cuda.synchronize()
+        tr_stages = {k: round(v[0] / 3 * 1e3, 1) for k, v in cabi.read_stage_timing().items()}
+        cabi.stage_timing(False)
         train = {"us_per_bag_fwd_bwd": us, "patches_per_s": N_TOKENS / (us * 1e-6), "drop_out": 0.1,
+                 "stages_us_per_step": tr_stages,
                  "launches_per_step": (cabi.launch_count() - l0) // n_tr,
                  "what": "RRTEncoder.train() forward (tape + proj dropout) + backward of one N=9000 bag "
                          "through torch.autograd, all parameter gradients, one stream, CUDA events"}
