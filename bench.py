@@ -329,10 +329,12 @@ def run_b200_arm(args):
         n_tr = max(5, min(args.steps, 20))
         l0 = cabi.launch_count()
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        th0 = time.perf_counter()
         t0e.record()
         for _ in range(n_tr):
             train_step()
         t1e.record()
+        host_us = (time.perf_counter() - th0) * 1e6 / n_tr   # enqueue time (the loop never synchronises)
         torch.cuda.synchronize()
         us = t0e.elapsed_time(t1e) * 1e3 / n_tr
         cabi.stage_timing(True)
@@ -342,7 +344,7 @@ def run_b200_arm(args):
         tr_stages = {k: round(v[0] / 3 * 1e3, 1) for k, v in cabi.read_stage_timing().items()}
         cabi.stage_timing(False)
         train = {"us_per_bag_fwd_bwd": us, "patches_per_s": N_TOKENS / (us * 1e-6), "drop_out": 0.1,
-                 "stages_us_per_step": tr_stages,
+                 "host_enqueue_us_per_step": host_us, "stages_us_per_step": tr_stages,
                  "launches_per_step": (cabi.launch_count() - l0) // n_tr,
                  "what": "RRTEncoder.train() forward (tape + proj dropout) + backward of one N=9000 bag "
                          "through torch.autograd, all parameter gradients, one stream, CUDA events"}

@@ -294,6 +294,23 @@ RRT_API int rrt_attention_backward(const void* qkv, const void* o, const void* d
 RRT_API int rrt_layernorm_backward(const float* x, const float* gamma, const float* dy, float* dx,
                                    float* dgamma, float* dbeta, int64_t L, int32_t dim, void* stream);
 
+/* ---- optimizer step of the training harness (main.py:224-233: torch.optim.Adam, lr 2e-4, wd 1e-5) ----
+ * One launch updates every tensor of the list with torch.optim.Adam (decoupled = 0: L2 weight decay
+ * added to the gradient) or AdamW (decoupled = 1) semantics, step = 1, 2, ...:
+ *   g = grad * grad_scale;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *   p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)
+ * All pointers are device fp32 arrays of n elements; the struct array itself is host memory. */
+typedef struct rrt_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+} rrt_adam_tensor;
+RRT_API int rrt_adam_step(const rrt_adam_tensor* tensors, int32_t n_tensors, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, int32_t decoupled, int64_t step,
+                          float grad_scale, void* stream);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------- */
 /* Kernel launches issued by this library in this process so far. */
 RRT_API int64_t rrt_launch_count(void);

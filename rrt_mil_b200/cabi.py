@@ -57,6 +57,11 @@ class RrtWeights(C.Structure):
     ]
 
 
+class RrtAdamTensor(C.Structure):
+    _fields_ = [("param", c_float_p), ("grad", c_float_p), ("exp_avg", c_float_p),
+                ("exp_avg_sq", c_float_p), ("n", C.c_int64)]
+
+
 class RrtAttnGrads(C.Structure):
     _fields_ = [("qkv_w", c_float_p), ("qkv_b", c_float_p), ("proj_w", c_float_p),
                 ("proj_b", c_float_p), ("pe_w", c_float_p)]
@@ -97,6 +102,8 @@ SIGNATURES = {
                                             C.c_int64, _P, C.c_size_t, C.c_float, C.c_uint64, _P]),
     "rrt_peg_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.POINTER(c_float_p), C.POINTER(c_float_p), _P]),
+    "rrt_adam_step": (C.c_int, [C.POINTER(RrtAdamTensor), C.c_int32, C.c_float, C.c_float, C.c_float,
+                                C.c_float, C.c_float, C.c_int32, C.c_int64, C.c_float, _P]),
     "rrt_dropout_mask": (C.c_int, [_P, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, _P]),
     "rrt_backward_workspace_bytes": (C.c_int, [C.POINTER(RrtConfig), C.c_int64, C.POINTER(C.c_size_t)]),
     "rrt_encoder_backward": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P, C.c_int64,

@@ -921,8 +921,12 @@ int linear_backward(const __half* dy, const __half* dyT, const __half* act, cons
   }
   { StageScope s_(kStBwdPrep, st);
     RRT_CUDA(rrt::launch_transpose_f16(act, M, C_in, b.actT, nullptr, nullptr, st), "activation transpose"); }
-  { StageScope s_(kStBwdWgrad, st, 2);
-    RRT_CUDA(rrt::launch_gemm_tcgen05(dyT, b.actT, dW, false, C_out, C_in, M64, e, st), "wgrad gemm");
+  { StageScope s_(kStBwdWgrad, st, 3);
+    // few output tiles, K = every token of the bag: split-K over all SMs into the zeroed gradient
+    rrt::GemmEpilogue ew;
+    ew.mode = rrt::kEpiAtomicAdd;
+    RRT_CUDA(cudaMemsetAsync(dW, 0, (size_t)C_out * C_in * sizeof(float), st), "zero weight gradient");
+    RRT_CUDA(rrt::launch_gemm_tcgen05(dyT, b.actT, dW, false, C_out, C_in, M64, ew, st), "wgrad gemm");
     RRT_CUDA(rrt::launch_scale_by_inv(dW, (size_t)C_out * C_in, amax, st), "wgrad unscale"); }
   return RRT_OK;
 }
@@ -1115,6 +1119,30 @@ RRT_API int rrt_attention_backward(const void* qkv, const void* o, const void* d
                                           taps, (__half*)d_qkv, taps ? d_taps : nullptr, nullptr, R, P,
                                           dim, heads, epeg_k, (cudaStream_t)stream),
            "attention backward");
+  return RRT_OK;
+}
+
+RRT_API int rrt_adam_step(const rrt_adam_tensor* tensors, int32_t n_tensors, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, int32_t decoupled, int64_t step,
+                          float grad_scale, void* stream) {
+  if (n_tensors < 0 || (n_tensors > 0 && !tensors) || step < 1 || !(beta1 >= 0.f && beta1 < 1.f) ||
+      !(beta2 >= 0.f && beta2 < 1.f) || !(eps >= 0.f))
+    return fail(RRT_E_INVALID, "bad argument");
+  std::vector<float*> p(n_tensors), m(n_tensors), v(n_tensors);
+  std::vector<const float*> g(n_tensors);
+  std::vector<long long> n(n_tensors);
+  for (int i = 0; i < n_tensors; ++i) {
+    const rrt_adam_tensor& t = tensors[i];
+    if (t.n < 0 || (t.n > 0 && (!t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq)))
+      return fail(RRT_E_INVALID, "NULL tensor in the Adam list");
+    p[i] = t.param; g[i] = t.grad; m[i] = t.exp_avg; v[i] = t.exp_avg_sq; n[i] = t.n;
+  }
+  int launches = 0;
+  cudaError_t e = rrt::launch_adam(p.data(), g.data(), m.data(), v.data(), n.data(), n_tensors, lr, beta1,
+                                   beta2, eps, weight_decay, decoupled != 0, step, grad_scale, &launches,
+                                   (cudaStream_t)stream);
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
+  if (e != cudaSuccess) return fail_cuda(e, "adam step");
   return RRT_OK;
 }
 

@@ -54,6 +54,7 @@ struct Tc05Params {
   Grid grid;
   int act;           // GemmActivation, store mode only
   Dropout drop;      // kEpiResidualUnpartDrop only
+  int ksplit;        // >= 1: the K loop of every tile is cut into ksplit work items (kEpiAtomicAdd)
   long long* trace;  // debug: per-CTA clock64 stamps (tools/gemm_trace.py), null in production
 };
 
@@ -89,6 +90,13 @@ __device__ __forceinline__ void store_out4(float* base, size_t off, float4 v) {
 __device__ __forceinline__ void store_out4(__half* base, size_t off, float4 v) {
   *reinterpret_cast<uint2*>(base + off) = pack_h4(v);
 }
+// split-K partial sums: one 16-byte reduction per 4 outputs (no return value: fire and forget)
+__device__ __forceinline__ void red_add4(float* base, size_t off, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + off), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void red_add4(__half*, size_t, float4) {}
 
 // Epilogue of one 128 x BN accumulator for one of the 8 epilogue warps (two per TMEM lane quadrant):
 // software-pipelined tcgen05.ld, accumulator released (release()) as soon as this warp's slice is in
@@ -253,7 +261,10 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (orow[i] >= 0 && col_ok) store_out4(out, (size_t)orow[i] * p.N + gc, v[i]);
+        if (orow[i] >= 0 && col_ok) {
+          if (MODE == kEpiAtomicAdd) red_add4(out, (size_t)orow[i] * p.N + gc, v[i]);
+          else store_out4(out, (size_t)orow[i] * p.N + gc, v[i]);
+        }
       if (first && threadIdx.x == 128 && j < 2) stamp(p, 12 + 3 * j);
       if (is_resid_mode(MODE) && j + 1 < NC) load_resid(j + 1);  // next chunk's residual rows
       __syncwarp();
@@ -327,6 +338,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int tiles_nc = ((p.N + BN - 1) / BN + CN - 1) / CN;
   const int num_ctiles = tiles_mc * tiles_nc;
   const int KB = p.K / BK;
+  // split-K (kEpiAtomicAdd): work item wt = (tile wt % num_ctiles, K slice wt / num_ctiles of KS)
+  const int KS = MODE == kEpiAtomicAdd ? p.ksplit : 1;
+  const int num_work = num_ctiles * KS;
   // peers that share my A tile (same ci) / my W tile (same cj); rank = ci + CM * cj
   uint16_t mask_a = 0, mask_b = 0;
 #pragma unroll
@@ -338,16 +352,17 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (lane == 0) {  // ===== TMA producers: warp 0 streams A slices, warp 3 streams W slices =====
       const bool is_a = warp == 0;
       int s = 0, ph = 0;
-      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+      for (int wt = cluster_id; wt < num_work; wt += num_clusters) {
+        const int ct = wt % num_ctiles, ks = wt / num_ctiles;
         const int m0 = ((ct / tiles_nc) * CM + ci) * BM, n0 = ((ct % tiles_nc) * CN + cj) * BN;
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = ks * KB / KS, kb1 = (ks + 1) * KB / KS; kb < kb1; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);  // every CTA that reads or refills this stage has released it
           if (is_a) {
             mbar_arrive_expect_tx(&full[s], A_BYTES);  // my slice + the peers' slices of MY tile
             uint8_t* dst = sA + s * A_BYTES + cj * (A_BYTES / CN);
             if (CN > 1) tma_load_2d_mcast(dst, &tmA, &full[s], kb * BK, m0 + cj * (BM / CN), mask_a);
             else tma_load_2d(dst, &tmA, &full[s], kb * BK, m0);
-            if (ct == cluster_id && kb == 0) stamp(p, 2);
+            if (wt == cluster_id && kb == 0) stamp(p, 2);
           } else {
             mbar_arrive_expect_tx(&full[s], B_BYTES);
             uint8_t* dst = sB + s * B_BYTES + ci * (B_BYTES / CM);
@@ -364,19 +379,21 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (lane == 0) {  // ===== MMA issuer =====
       constexpr uint32_t idesc = umma_idesc(kFmtF16, BM, BN);
       int s = 0, ph = 0, acc = 0, aph = 0;
-      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+      for (int wt = cluster_id; wt < num_work; wt += num_clusters) {
+        const int ks = wt / num_ctiles;
         mbar_wait(&tempty[acc], aph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < KB; ++kb) {
+        const int kb0 = ks * KB / KS;
+        for (int kb = kb0, kb1 = (ks + 1) * KB / KS; kb < kb1; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          if (ct == cluster_id && kb == 0) stamp(p, 4);
+          if (wt == cluster_id && kb == kb0) stamp(p, 4);
           const uint64_t ad = umma_desc_k_sw128(smem_u32(sA + s * A_BYTES));
           const uint64_t bd = umma_desc_k_sw128(smem_u32(sB + s * B_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)  // 16 fp16 = 32 bytes per MMA along K: +2 in 16-B units
-            umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+            umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, ((kb - kb0) | k) != 0);
           // smem stage reusable once these MMAs have read it: tell every CTA that writes into it
           if (CSIZE > 1) umma_commit_mcast(&empty[s], (uint16_t)(mask_a | mask_b));
           else umma_commit(&empty[s]);
@@ -392,13 +409,14 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int ew = warp - 4;
     float* scratch = sEpi + ew * 32 * EPI_LD;
     int acc = 0, aph = 0;
-    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+    for (int wt = cluster_id; wt < num_work; wt += num_clusters) {
+      const int ct = wt % num_ctiles;
       const int m0 = ((ct / tiles_nc) * CM + ci) * BM, n0 = ((ct % tiles_nc) * CN + cj) * BN;
       uint64_t* te = &tempty[acc];
       epilogue_tile<MODE, BN, OutT>(p, &tmC, tmem_base + acc * BN, &tfull[acc], aph, m0, n0, ew, lane,
-                                    scratch, ct == cluster_id, [&] { if (lane == 0) mbar_arrive(te); });
+                                    scratch, wt == cluster_id, [&] { if (lane == 0) mbar_arrive(te); });
       if (++acc == 2) { acc = 0; aph ^= 1; }
-      if (threadIdx.x == 128) stamp(p, ct == cluster_id ? 7 : 8);
+      if (threadIdx.x == 128) stamp(p, wt == cluster_id ? 7 : 8);
     }
   }
 
@@ -656,7 +674,8 @@ cudaError_t launch_cfg(const __half* a, const __half* w, const Tc05Params& p, cu
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
   }
-  const int ctiles = (((p.M + BM - 1) / BM + CM - 1) / CM) * (((p.N + BN - 1) / BN + CN - 1) / CN);
+  const int ctiles = (((p.M + BM - 1) / BM + CM - 1) / CM) * (((p.N + BN - 1) / BN + CN - 1) / CN) *
+                     (MODE == kEpiAtomicAdd ? p.ksplit : 1);
   int clusters = sm_count() / CSIZE;
   if (ctiles < clusters) clusters = ctiles;
   cudaLaunchConfig_t cfg{};
@@ -759,6 +778,18 @@ cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool 
   p.act = epi.mode == kEpiTanh ? (int)kActTanh : epi.act;
   p.trace = g_gemm_trace ? g_gemm_trace + (size_t)(g_trace_launch++ % 8) * 128 : nullptr;
   p.drop = epi.drop;
+  p.ksplit = 1;
+  if (epi.mode == kEpiAtomicAdd) {
+    // c (fp32, zeroed by the caller) += a @ w^T, the K loop of every 128x256 tile cut into as many slices
+    // as it takes to give every SM a work item (weight gradients: few output tiles, K = the bag's tokens)
+    if (out_f16 || epi.bias) return cudaErrorInvalidValue;
+    const int tiles = ((M + BM - 1) / BM) * ((N + 255) / 256), KB = K / BK;
+    int ksplit = sm_count() / tiles;
+    if (ksplit > KB) ksplit = KB;
+    if (ksplit < 1) ksplit = 1;
+    p.ksplit = ksplit;
+    return launch_cfg<kEpiAtomicAdd, 256, float, 1, 1>(a, w, p, stream);
+  }
   if (epi.mode == kEpiResidualUnpartDrop && epi.drop.on())
     return out_f16 ? cudaErrorInvalidValue : launch_mode<kEpiResidualUnpartDrop, float>(a, w, p, stream);
   if (is_resid_mode(epi.mode))

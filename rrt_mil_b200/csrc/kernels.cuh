@@ -28,7 +28,8 @@ enum GemmEpilogueMode {
   kEpiTanh = 1,           // c[m,n] = tanh(acc + bias[n])
   kEpiResidualUnpart = 2, // row m is a region slot: out[token(m),n] = resid[token(m),n] + acc + bias[n]
   // 3 is internal (store + run-time activation)
-  kEpiResidualUnpartDrop = 4  // training: ... + dropout(acc + bias[n]) (GemmEpilogue::drop)
+  kEpiResidualUnpartDrop = 4, // training: ... + dropout(acc + bias[n]) (GemmEpilogue::drop)
+  kEpiAtomicAdd = 5           // split-K: c[m,n] += acc (fp32 red.global.add; c zeroed by the caller, no bias)
 };
 enum GemmActivation { kActNone = 0, kActRelu = 1, kActGelu = 2, kActTanh = 3, kActSigmoid = 4 };
 struct GemmEpilogue {
@@ -122,6 +123,12 @@ cudaError_t launch_crmsa_dispatch(const float* x1, const float* x0, const float*
 size_t peg_scratch_floats(int D, int peg_k, bool ppeg, bool conv_1d);
 cudaError_t launch_peg(const float* x, float* out, int L, int D, int peg_k, bool ppeg, bool conv_1d,
                        const float* const* w, const float* const* b, float* scratch, cudaStream_t stream);
+
+// ---- optim.cu: multi-tensor Adam / AdamW step, torch.optim semantics ----------
+cudaError_t launch_adam(float* const* p, const float* const* g, float* const* m, float* const* v,
+                        const long long* n, int count, float lr, float beta1, float beta2, float eps,
+                        float wd, bool decoupled, long long step, float grad_scale, int* launches,
+                        cudaStream_t stream);
 
 // ---- mil_head.cu: DAttention pooling + predictor behind the encoder ---------
 size_t attn_pool_scratch_floats(int L, int D, int hid);

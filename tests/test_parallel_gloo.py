@@ -62,3 +62,38 @@ def test_shard_indices_partition_the_bags():
         for w in (1, 2, 4, 8):
             seen = sorted(i for r in range(w) for i in parallel.shard_indices(n, w, r))
             assert seen == list(range(n))
+
+
+def _grad_worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4))
+        frozen = torch.nn.Parameter(torch.ones(3))            # never receives a gradient on any rank
+        params = list(model.parameters()) + [frozen]
+        g = torch.Generator().manual_seed(1)
+        bags = [torch.randn(10 + 3 * i, 16, generator=g) for i in range(world)]   # one bag per rank
+        model(bags[rank]).square().mean().backward()
+        n_coll = parallel.allreduce_gradients(params, bucket_bytes=1024)           # several buckets
+        # serial oracle: average of the per-bag gradients
+        ref = [torch.zeros_like(p) for p in params]
+        for b in bags:
+            m2 = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4))
+            m2.load_state_dict(model.state_dict())
+            m2(b).square().mean().backward()
+            for r, p in zip(ref, m2.parameters()):
+                r += p.grad / world
+        ok = n_coll >= 2 and all(torch.allclose(p.grad, r, rtol=1e-6, atol=1e-7) for p, r in zip(params, ref))
+        ok = ok and float(frozen.grad.abs().sum()) == 0.0
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_gradients_equals_serial_average_world2():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_grad_worker, args=(world, port, results), nprocs=world, join=True)
+    assert dict(results) == {0: True, 1: True}
