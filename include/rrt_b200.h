@@ -76,6 +76,10 @@ typedef struct rrt_config {
   int32_t pos_pos;          /* -1: before the first layer; 0: before R-MSA layer 1      */
   int32_t peg_k;            /* odd kernel size of the first conv                        */
   int32_t peg_1d;           /* (k,1) column kernels instead of k x k                    */
+  /* ablation FFN of every TransLayer (modules/rrt.py:25-41,106,128-129): x += fc2(act(fc1(norm2(x)))) */
+  int32_t ffn;              /* on/off                                                   */
+  int32_t ffn_act;          /* RRT_ACT_GELU (ffn_act='gelu', default) or RRT_ACT_RELU    */
+  int32_t ffn_hidden;       /* int(dim * mlp_ratio); multiple of 64                     */
 } rrt_config;
 enum { RRT_POS_NONE = 0, RRT_POS_PEG = 1, RRT_POS_PPEG = 2 };
 
@@ -95,6 +99,18 @@ typedef struct rrt_attn_weights {
   const void* proj_w_f16; /* [D, D] fp16 */
 } rrt_attn_weights;
 
+/* One Mlp + its pre-norm (TransLayer.norm2 / TransLayer.mlp, modules/rrt.py:47,106); all NULL when ffn = 0. */
+typedef struct rrt_ffn_weights {
+  const float* norm_w;  /* norm2.weight [D] */
+  const float* norm_b;
+  const float* fc1_w;   /* mlp.fc1.weight [H, D] */
+  const float* fc1_b;   /* [H] */
+  const float* fc2_w;   /* mlp.fc2.weight [D, H] */
+  const float* fc2_b;   /* [D] */
+  const void* fc1_w_f16; /* optional fp16 shadows */
+  const void* fc2_w_f16;
+} rrt_ffn_weights;
+
 /* state_dict of one RRTEncoder, by reference name. */
 typedef struct rrt_weights {
   const float* norm_w; /* norm.weight [D] (final LayerNorm) */
@@ -113,6 +129,8 @@ typedef struct rrt_weights {
    * PEG uses index 0 only, PPEG all three (kernel sizes peg_k, 5, 3) */
   const float* pos_w[3];
   const float* pos_b[3];
+  rrt_ffn_weights layer_ffn[RRT_MAX_RMSA_LAYERS]; /* layers.i.norm2.* / layers.i.mlp.* */
+  rrt_ffn_weights cr_ffn;                          /* cr_msa.norm2.* / cr_msa.mlp.*     */
 } rrt_weights;
 
 /* ---- housekeeping ------------------------------------------------------------------- */

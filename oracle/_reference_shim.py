@@ -70,7 +70,8 @@ def build_reference_encoder(cfg, weights, dtype=torch.float64):
                        cr_msa=cfg.cr_msa, crmsa_k=cfg.crmsa_k, all_shortcut=cfg.all_shortcut,
                        crmsa_mlp=cfg.crmsa_mlp, crmsa_heads=cfg.crmsa_heads,
                        epeg_bias=cfg.epeg_bias, pos=cfg.pos, pos_pos=cfg.pos_pos, peg_k=cfg.peg_k,
-                       peg_bias=cfg.peg_bias, peg_1d=cfg.peg_1d)
+                       peg_bias=cfg.peg_bias, peg_1d=cfg.peg_1d, ffn=cfg.ffn, ffn_act=cfg.ffn_act,
+                       mlp_ratio=cfg.mlp_ratio)
     m = m.to(dtype).eval()
     m.load_state_dict({k: v.to(dtype) for k, v in weights.items()}, strict=True)
     return m

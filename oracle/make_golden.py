@@ -63,6 +63,11 @@ CASES = [
     ("peg_k5_between_layers", 900, dict(mlp_dim=256, pos="peg", pos_pos=0, peg_k=5, n_layers=3, peg_bias=False), 7, "randn"),
     ("ppeg_1d_tiny_grid", 30, dict(mlp_dim=128, n_heads=4, crmsa_heads=4, pos="ppeg", pos_pos=-1, peg_1d=True, peg_k=3), 7, "randn"),
     ("ppeg_n9000", 9000, dict(pos="ppeg", pos_pos=-1), 7, "relu"),
+    # A8 ablation: FFN after every TransLayer (modules/rrt.py:25-41,128-129)
+    ("ffn_gelu_n1000", 1000, dict(ffn=True), 7, "relu"),
+    ("ffn_relu_d256_3layers", 700, dict(mlp_dim=256, ffn=True, ffn_act="relu", mlp_ratio=2.0, n_layers=3,
+                                        all_shortcut=True), 7, "randn"),
+    ("ffn_nocr", 500, dict(mlp_dim=256, ffn=True, cr_msa=False), 7, "randn"),
 ]
 
 # RRTMIL end-to-end: name, L, input_dim, n_classes, act, da_act, da_bias, encoder overrides

@@ -69,6 +69,10 @@ class EncoderConfig:
     peg_k: int = 7
     peg_bias: bool = True
     peg_1d: bool = False
+    # ablation FFN (modules/rrt.py:25-41,106,128-129)
+    ffn: bool = False
+    ffn_act: str = "gelu"
+    mlp_ratio: float = 4.0
 
     def to_dict(self):
         return asdict(self)
@@ -270,6 +274,14 @@ def pos_embedding(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfi
     return out.reshape(D, H * H).t()[:L]
 
 
+def ffn_block(h: torch.Tensor, w: Dict[str, torch.Tensor], prefix: str, cfg: EncoderConfig) -> torch.Tensor:
+    """``x + mlp(norm2(x))`` of one TransLayer (modules/rrt.py:128-129, 35-41), eval mode."""
+    z = layer_norm(h, w[prefix + "norm2.weight"], w[prefix + "norm2.bias"])
+    z = F.linear(z, w[prefix + "mlp.fc1.weight"], w[prefix + "mlp.fc1.bias"])
+    z = F.gelu(z) if cfg.ffn_act == "gelu" else torch.relu(z)
+    return h + F.linear(z, w[prefix + "mlp.fc2.weight"], w[prefix + "mlp.fc2.bias"])
+
+
 def encoder_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfig,
                     order: str = "reference", drop=None) -> torch.Tensor:
     """``RRTEncoder.forward`` for one bag ``x`` [L,D] -> [L,D] (modules/rrt.py:165-202).
@@ -291,10 +303,14 @@ def encoder_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderCon
         p = f"layers.{i}."
         h = h + rmsa_block(layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w,
                            p + "attn.", cfg, order, mask(L, i))
+        if cfg.ffn:
+            h = ffn_block(h, w, p, cfg)
     if cfg.cr_msa:
         p = "cr_msa."
         h = h + crmsa_block(layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w,
                             p + "attn.", cfg, order, mask(cfg.crmsa_k * 64, DROP_STREAM_CRMSA))
+        if cfg.ffn:
+            h = ffn_block(h, w, p, cfg)
     if cfg.all_shortcut:
         h = h + x
     return layer_norm(h, w["norm.weight"], w["norm.bias"])
@@ -383,6 +399,12 @@ def weight_shapes(cfg: EncoderConfig) -> Dict[str, Tuple[int, ...]]:
             shp[f"pos_embedding.{name}.weight"] = (D, 1, k, 1 if cfg.peg_1d else k)
             if cfg.peg_bias:
                 shp[f"pos_embedding.{name}.bias"] = (D,)
+    if cfg.ffn:
+        hid = int(D * cfg.mlp_ratio)
+        for pre in [f"layers.{i}." for i in range(cfg.n_layers - 1)] + (["cr_msa."] if cfg.cr_msa else []):
+            shp[pre + "norm2.weight"], shp[pre + "norm2.bias"] = (D,), (D,)
+            shp[pre + "mlp.fc1.weight"], shp[pre + "mlp.fc1.bias"] = (hid, D), (hid,)
+            shp[pre + "mlp.fc2.weight"], shp[pre + "mlp.fc2.bias"] = (D, hid), (D,)
     return shp
 
 
@@ -394,7 +416,7 @@ def make_weights(cfg: EncoderConfig, seed: int, dtype=torch.float64,
     rs = np.random.RandomState(seed)
     out = {}
     for name, shape in weight_shapes(cfg).items():
-        if name.endswith("norm.weight"):
+        if name.endswith("norm.weight") or name.endswith("norm2.weight"):
             a = 1.0 + 0.1 * rs.standard_normal(shape) if randomize_bias else np.ones(shape)
         elif name.endswith("bias"):
             a = 0.1 * rs.standard_normal(shape) if randomize_bias else np.zeros(shape)

@@ -35,6 +35,7 @@ class RrtConfig(C.Structure):
         ("crmsa_heads", C.c_int32), ("crmsa_mlp", C.c_int32), ("all_shortcut", C.c_int32),
         ("math_mode", C.c_int32),
         ("pos", C.c_int32), ("pos_pos", C.c_int32), ("peg_k", C.c_int32), ("peg_1d", C.c_int32),
+        ("ffn", C.c_int32), ("ffn_act", C.c_int32), ("ffn_hidden", C.c_int32),
     ]
 
 
@@ -42,6 +43,11 @@ class RrtAttnWeights(C.Structure):
     _fields_ = [("qkv_w", c_float_p), ("qkv_b", c_float_p), ("proj_w", c_float_p),
                 ("proj_b", c_float_p), ("pe_w", c_float_p), ("qkv_w_f16", c_float_p),
                 ("proj_w_f16", c_float_p)]
+
+
+class RrtFfnWeights(C.Structure):
+    _fields_ = [(n, c_float_p) for n in ("norm_w", "norm_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
+                                         "fc1_w_f16", "fc2_w_f16")]
 
 
 class RrtWeights(C.Structure):
@@ -54,6 +60,7 @@ class RrtWeights(C.Structure):
         ("cr_phi_w1", c_float_p), ("cr_phi_w2", c_float_p), ("cr_phi_w1_f16", c_float_p),
         ("cr_attn", RrtAttnWeights),
         ("pos_w", c_float_p * 3), ("pos_b", c_float_p * 3),
+        ("layer_ffn", RrtFfnWeights * RRT_MAX_RMSA_LAYERS), ("cr_ffn", RrtFfnWeights),
     ]
 
 

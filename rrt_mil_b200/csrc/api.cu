@@ -157,6 +157,12 @@ int check_config(const rrt_config* c) {
       return fail(RRT_E_INVALID, "CR-MSA head_dim must be a multiple of 32");
   }
   if (c->math_mode != RRT_MATH_F16) return fail(RRT_E_INVALID, "unknown math_mode");
+  if (c->ffn) {
+    if (c->ffn_act != RRT_ACT_GELU && c->ffn_act != RRT_ACT_RELU)
+      return fail(RRT_E_INVALID, "ffn_act must be RRT_ACT_GELU or RRT_ACT_RELU");
+    if (c->ffn_hidden < 64 || c->ffn_hidden % 64 || c->ffn_hidden > 8192)
+      return fail(RRT_E_INVALID, "ffn_hidden must be a multiple of 64 in [64, 8192]");
+  }
   if (c->pos != RRT_POS_NONE) {
     if (c->pos != RRT_POS_PEG && c->pos != RRT_POS_PPEG) return fail(RRT_E_INVALID, "unknown pos");
     if (c->pos_pos != -1 && c->pos_pos != 0) return fail(RRT_E_INVALID, "pos_pos must be -1 or 0");
@@ -185,6 +191,12 @@ struct Workspace {
   float* lout;     // [k*R_c, D]
   float* hidden;   // [Np_c, D/4] (crmsa_mlp)
   __half* wconv;   // [3D*D + D*D] fp16 weights when the caller passes no shadow
+  __half* ffn_z;   // [Hi*Hi, D] LayerNorm(norm2) rows of the FFN (ffn = 1; Hi = ceil(sqrt(L)))
+  __half* ffn_h;   // [L, ffn_hidden] fp16 hidden activations
+  float* ffn_out;  // [L, D] x + mlp(norm2(x))
+  float* ffn_out2; // [L, D] second FFN buffer (the CR-MSA layer's)
+  float* ffn_x2;   // [L, D] output of the CR-MSA block ahead of its FFN
+  __half* ffn_w;   // [ffn_hidden * D] fp16 weight when the caller passes no shadow
   float* pe_out;   // [L, D] output of the PEG / PPEG positional encoding (pos != none)
   float* pe_w;     // folded depthwise kernel + bias (peg_scratch_floats)
   size_t bytes;
@@ -245,6 +257,13 @@ bool carve(const rrt_config* c, int64_t L, void* base, Workspace* ws, bool train
   ws->lout = (float*)take(T * D * 4);
   ws->hidden = (float*)take(mlp ? np_c * (D / 4) * 4 : 0);
   ws->wconv = (__half*)take(4 * D * D * 2);
+  const size_t Hi = (size_t)ceil_sqrt(L), FH = c->ffn ? (size_t)c->ffn_hidden : 0;
+  ws->ffn_z = (__half*)take(c->ffn ? Hi * Hi * D * 2 : 0);
+  ws->ffn_h = (__half*)take((size_t)L * FH * 2);
+  ws->ffn_out = (float*)take(c->ffn ? (size_t)L * D * 4 : 0);
+  ws->ffn_out2 = (float*)take(c->ffn ? (size_t)L * D * 4 : 0);
+  ws->ffn_x2 = (float*)take(c->ffn && c->cr_msa ? (size_t)L * D * 4 : 0);
+  ws->ffn_w = (__half*)take(FH * D * 2);
   const bool pos = c->pos != RRT_POS_NONE;
   ws->pe_out = (float*)take(pos ? (size_t)L * D * 4 : 0);
   ws->pe_w = (float*)take(pos ? rrt::peg_scratch_floats((int)D, c->peg_k, c->pos == RRT_POS_PPEG,
@@ -418,6 +437,38 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   return RRT_OK;
 }
 
+// Ablation FFN of a TransLayer (modules/rrt.py:128-129, eval): out = x + fc2(act(fc1(LayerNorm(x)))).
+// Built from the path's own kernels: ln_partition over an identity "grid" (one region = the whole
+// square), the tcgen05 GEMM with the activation epilogue (fp16 hidden rows) and the tcgen05 GEMM with
+// the residual epilogue.
+int ffn_block(const rrt_config* c, const rrt_ffn_weights* f, const float* x, float* out, int64_t L,
+              Workspace& ws, cudaStream_t st) {
+  if (!f->norm_w || !f->norm_b || !f->fc1_w || !f->fc1_b || !f->fc2_w || !f->fc2_b)
+    return fail(RRT_E_INVALID, "ffn weights missing");
+  const int D = c->dim, FH = c->ffn_hidden;
+  rrt::Grid id{};   // slot == token: one region covering the Hi x Hi square
+  id.L = (int)L; id.H = ceil_sqrt(L); id.rs = id.H; id.g = 1; id.P = id.H * id.H; id.R = 1; id.Np = id.P;
+  StageScope s_(kStOther, st, 3);
+  RRT_CUDA(rrt::launch_ln_partition(x, f->norm_w, f->norm_b, ws.ffn_z, id, D, st), "ffn norm2");
+  const __half* w1;
+  int rc = f16_weight(f->fc1_w, f->fc1_w_f16, ws.ffn_w, (size_t)FH * D, st, &w1);
+  if (rc) return rc;
+  rrt::GemmEpilogue e1;
+  e1.bias = f->fc1_b;
+  e1.act = c->ffn_act == RRT_ACT_GELU ? rrt::kActGelu : rrt::kActRelu;
+  RRT_CUDA(rrt::launch_gemm_tcgen05(ws.ffn_z, w1, ws.ffn_h, true, (int)L, FH, D, e1, st), "ffn fc1");
+  const __half* w2;
+  rc = f16_weight(f->fc2_w, f->fc2_w_f16, ws.ffn_w, (size_t)FH * D, st, &w2);
+  if (rc) return rc;
+  rrt::GemmEpilogue e2;
+  e2.mode = rrt::kEpiResidualUnpart;
+  e2.bias = f->fc2_b;
+  e2.resid = x;
+  e2.grid = id;
+  RRT_CUDA(rrt::launch_gemm_tcgen05(ws.ffn_h, w2, out, false, (int)L, D, FH, e2, st), "ffn fc2");
+  return RRT_OK;
+}
+
 int encoder_forward(const rrt_config* cfg, const rrt_weights* w, const float* x, float* out,
                     int64_t L, Workspace& ws, cudaStream_t st, const TrainOpts& tr = TrainOpts{}) {
   const int D = cfg->dim;
@@ -446,8 +497,24 @@ int encoder_forward(const rrt_config* cfg, const rrt_weights* w, const float* x,
                         ws, st, i, tr);
     if (rc) return rc;
     cur = nxt;
+    if (cfg->ffn) {
+      rc = ffn_block(cfg, &w->layer_ffn[i], cur, ws.ffn_out, L, ws, st);
+      if (rc) return rc;
+      cur = ws.ffn_out;
+    }
   }
   const float* x0 = cfg->all_shortcut ? x : nullptr;
+  if (cfg->cr_msa && cfg->ffn) {
+    // x2 = x1 + crmsa(...) ; x3 = x2 + mlp(norm2(x2)) ; out = LN(x3 (+ x))   (modules/rrt.py:190-195)
+    float* x2 = ws.ffn_x2;
+    int rc = crmsa_block(cfg, w, cur, nullptr, x2, L, false, ws, st, tr);
+    if (rc) return rc;
+    rc = ffn_block(cfg, &w->cr_ffn, x2, ws.ffn_out2, L, ws, st);
+    if (rc) return rc;
+    StageScope s_(kStFinalLn, st);
+    RRT_CUDA(rrt::launch_add_layernorm(ws.ffn_out2, x0, w->norm_w, w->norm_b, out, (int)L, D, st), "final norm");
+    return RRT_OK;
+  }
   if (cfg->cr_msa) return crmsa_block(cfg, w, cur, x0, out, L, true, ws, st, tr);
   { StageScope s_(kStFinalLn, st); RRT_CUDA(rrt::launch_add_layernorm(cur, x0, w->norm_w, w->norm_b, out, (int)L, D, st), "final norm"); }
   return RRT_OK;
@@ -886,6 +953,7 @@ bool carve_bwd(const rrt_config* c, int64_t L, void* base, BwdWorkspace* b) {
 
 int check_backward_support(const rrt_config* c, int64_t L) {
   if (c->pos != RRT_POS_NONE) return fail(RRT_E_INVALID, "backward: PEG / PPEG (ablation) is not covered");
+  if (c->ffn) return fail(RRT_E_INVALID, "backward: the FFN ablation is not covered");
   if (c->cr_msa && c->crmsa_mlp) return fail(RRT_E_INVALID, "backward: crmsa_mlp is not covered");
   if (c->n_rmsa_layers == 0 && !c->cr_msa) return fail(RRT_E_INVALID, "backward: encoder has no block");
   if (c->n_rmsa_layers > 0) {

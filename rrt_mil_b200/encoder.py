@@ -74,13 +74,29 @@ class CrossRegionAttention(_ParamHolder):
             nn.init.kaiming_uniform_(self.phi, a=math.sqrt(5))
 
 
-class TransLayer(_ParamHolder):
-    """modules/rrt.py:43-106: pre-LayerNorm + attention (+ residual, done in the kernels)."""
+class Mlp(_ParamHolder):
+    """Parameters of modules/rrt.py:25-41 (the FFN ablation)."""
 
-    def __init__(self, dim, attn_module):
+    def __init__(self, in_features, hidden_features, act_layer, drop):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, in_features)
+        self.drop = nn.Dropout(drop)
+
+
+class TransLayer(_ParamHolder):
+    """modules/rrt.py:43-106: pre-LayerNorm + attention (+ residual, done in the kernels); with
+    ``ffn`` also ``norm2`` + ``mlp``."""
+
+    def __init__(self, dim, attn_module, ffn=False, ffn_act='gelu', mlp_ratio=4., drop_out=0.1):
         super().__init__()
         self.norm = nn.LayerNorm(dim)
+        self.norm2 = nn.LayerNorm(dim) if ffn else nn.Identity()
         self.attn = attn_module
+        self.ffn = ffn
+        self.mlp = (Mlp(dim, int(dim * mlp_ratio), nn.GELU if ffn_act == 'gelu' else nn.ReLU, drop_out)
+                    if ffn else nn.Identity())
 
 
 class PEG(_ParamHolder):
@@ -178,8 +194,8 @@ class RRTEncoder(nn.Module):
             raise NotImplementedError(f"pos={pos!r}: only 'none', 'peg' and 'ppeg' are built")
         if pos in ('peg', 'ppeg') and (peg_k % 2 == 0 or peg_k > 31 or pos_pos not in (-1, 0)):
             raise ValueError("peg_k must be odd and <= 31, pos_pos -1 or 0")
-        if ffn:
-            raise NotImplementedError("ffn=True (ablation MLP) is not built")
+        if ffn and (int(mlp_dim * mlp_ratio) % 64 or int(mlp_dim * mlp_ratio) < 64):
+            raise ValueError("ffn: int(mlp_dim * mlp_ratio) must be a multiple of 64")
         epeg_2d = kwargs.pop('epeg_2d', False)
         epeg_type = kwargs.pop('epeg_type', 'attn')
         epeg_bias = kwargs.pop('epeg_bias', True)
@@ -203,10 +219,12 @@ class RRTEncoder(nn.Module):
         self.pos_pos = pos_pos
         self.norm = nn.LayerNorm(mlp_dim)
         self.layers = nn.Sequential(*[
-            TransLayer(mlp_dim, RegionAttention(mlp_dim, n_heads, qkv_bias, epeg, epeg_k, epeg_bias))
+            TransLayer(mlp_dim, RegionAttention(mlp_dim, n_heads, qkv_bias, epeg, epeg_k, epeg_bias),
+                       ffn, ffn_act, mlp_ratio, drop_out)
             for _ in range(n_layers - 1)])
         self.cr_msa = (TransLayer(mlp_dim, CrossRegionAttention(mlp_dim, crmsa_heads, qkv_bias,
-                                                                crmsa_k, crmsa_mlp))
+                                                                crmsa_k, crmsa_mlp),
+                                  ffn, ffn_act, mlp_ratio, drop_out)
                        if cr_msa else nn.Identity())
         if pos == 'ppeg':
             self.pos_embedding = PPEG(dim=mlp_dim, k=peg_k, bias=peg_bias, conv_1d=peg_1d)
@@ -225,6 +243,8 @@ class RRTEncoder(nn.Module):
         cfg.math_mode = cabi.RRT_MATH_F16
         cfg.pos = {'peg': cabi.RRT_POS_PEG, 'ppeg': cabi.RRT_POS_PPEG}.get(pos, cabi.RRT_POS_NONE)
         cfg.pos_pos, cfg.peg_k, cfg.peg_1d = int(pos_pos), int(peg_k), int(bool(peg_1d))
+        cfg.ffn, cfg.ffn_hidden = int(bool(ffn)), int(mlp_dim * mlp_ratio) if ffn else 0
+        cfg.ffn_act = cabi.RRT_ACT_GELU if ffn_act == 'gelu' else cabi.RRT_ACT_RELU
         self._cfg = cfg
         self._crmsa_mlp = bool(crmsa_mlp)
         self._shadow = {}
@@ -297,6 +317,17 @@ class RRTEncoder(nn.Module):
             else:
                 w.cr_phi = p(cr.attn.phi, device)
             self._attn_weights(cr.attn.attn, w.cr_attn, device, shadows=True)
+        if self._cfg.ffn:
+            def ffn_w(layer, dst):
+                dst.norm_w, dst.norm_b = p(layer.norm2.weight, device), p(layer.norm2.bias, device)
+                dst.fc1_w, dst.fc1_b = p(layer.mlp.fc1.weight, device), p(layer.mlp.fc1.bias, device)
+                dst.fc2_w, dst.fc2_b = p(layer.mlp.fc2.weight, device), p(layer.mlp.fc2.bias, device)
+                dst.fc1_w_f16 = self._f16_shadow(layer.mlp.fc1.weight)
+                dst.fc2_w_f16 = self._f16_shadow(layer.mlp.fc2.weight)
+            for i, layer in enumerate(self.layers):
+                ffn_w(layer, w.layer_ffn[i])
+            if self._cfg.cr_msa:
+                ffn_w(self.cr_msa, w.cr_ffn)
         if self._cfg.pos != cabi.RRT_POS_NONE:
             pe = self.pos_embedding
             for j, conv in enumerate([pe.proj] + ([pe.proj1, pe.proj2] if self._cfg.pos == cabi.RRT_POS_PPEG else [])):
@@ -355,6 +386,8 @@ class RRTEncoder(nn.Module):
                 raise NotImplementedError("backward through crmsa_mlp=True is not built")
             if self._cfg.pos != cabi.RRT_POS_NONE:
                 raise NotImplementedError("backward through the PEG / PPEG ablation is not built")
+            if self._cfg.ffn:
+                raise NotImplementedError("backward through the FFN ablation is not built")
         if self.training and self.drop_path_rate > 0:
             raise NotImplementedError("training-mode drop_path (default 0) is not built")
         if self.training and self.drop_out > 0 and not allow_grad:

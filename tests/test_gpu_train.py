@@ -66,4 +66,8 @@ def test_encoder_training_loop_reduces_the_loss():
     l2, p2 = run()
     assert l1[-1] < 0.97 * l1[0] and all(b < a for a, b in zip(l1, l1[1:])), l1   # measured: 1.034 -> 0.945
     assert torch.allclose(torch.tensor(l1), torch.tensor(l2), rtol=1e-4)
-    assert torch.allclose(p1, p2, rtol=0, atol=1e-5)
+    # Adam divides by sqrt(v): an element whose gradient is ~0 can flip the sign of its (lr-sized) update
+    # when the fp32 atomic reductions of the backward sum in another order, so compare in the mean and
+    # bound the worst case by the distance 8 steps of size lr can cover
+    d = (p1 - p2).abs()
+    assert float(d.mean()) < 1e-5 and float(d.max()) <= 2 * 8 * 2e-4

@@ -18,6 +18,8 @@ VARIANTS = [
     dict(mlp_dim=256, region_num=16, epeg_bias=False),
     dict(pos='ppeg', pos_pos=-1),
     dict(pos='peg', peg_k=5, peg_1d=True, peg_bias=False, n_layers=3),
+    dict(ffn=True),
+    dict(ffn=True, ffn_act='relu', mlp_ratio=2.0, mlp_dim=256, n_layers=3, cr_msa=False),
 ]
 
 
@@ -67,8 +69,8 @@ def test_unsupported_options_raise_loudly():
         RRTEncoder(pos='sincos')
     with pytest.raises(ValueError):
         RRTEncoder(pos='ppeg', peg_k=4)
-    with pytest.raises(NotImplementedError):
-        RRTEncoder(ffn=True)
+    with pytest.raises(ValueError):
+        RRTEncoder(ffn=True, mlp_ratio=0.3)
     with pytest.raises(NotImplementedError):
         RRTEncoder(epeg_2d=True)
     with pytest.raises(NotImplementedError):
