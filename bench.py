@@ -320,7 +320,11 @@ def run_b200_arm(args):
         enc_t = RRTEncoder(need_init=True, **ENC_KW).to(dev).train()
         xt = bags[0].clone().requires_grad_()
         gout = torch.randn_like(xt)
+        tparams = list(enc_t.parameters())
         def train_step():
+            for q in tparams:      # optimizer.zero_grad(set_to_none=True)
+                q.grad = None
+            xt.grad = None
             y = enc_t(xt)
             y.backward(gout)
         for _ in range(3):

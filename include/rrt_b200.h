@@ -306,6 +306,10 @@ RRT_API int rrt_encoder_backward(const rrt_config* cfg, const rrt_weights* w, co
  * rrt_attention_backward: qkv [R*P, 3D] fp16 and o [R*P, D] fp16 as the forward wrote them,
  * d_o [R*P, D] fp16 -> d_qkv [R*P, 3D] fp16, d_taps [heads, epeg_k] fp32 (+=; taps/d_taps NULL: no EPEG).
  * rrt_layernorm_backward: y = LayerNorm(x): dy [L, D] fp32 -> dx, dgamma (+=), dbeta (+=). */
+/* The weight-gradient GEMM, exposed for parity tests: dw[c_out, c_in] = dy[rows, c_out]^T @ act[rows, c_in]
+ * (fp16 row-major inputs read MN-major by tcgen05 -- no transposed copies -- fp32 split-K accumulation). */
+RRT_API int rrt_linear_wgrad_f16(const void* dy_f16, const void* act_f16, float* dw, int64_t rows,
+                                 int32_t c_out, int32_t c_in, void* stream);
 RRT_API int rrt_attention_backward(const void* qkv, const void* o, const void* d_o, const float* taps,
                                    void* d_qkv, float* d_taps, int32_t R, int32_t P, int32_t dim,
                                    int32_t heads, int32_t epeg_k, void* stream);

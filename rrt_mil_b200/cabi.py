@@ -109,6 +109,7 @@ SIGNATURES = {
                                             C.c_int64, _P, C.c_size_t, C.c_float, C.c_uint64, _P]),
     "rrt_peg_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.POINTER(c_float_p), C.POINTER(c_float_p), _P]),
+    "rrt_linear_wgrad_f16": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "rrt_adam_step": (C.c_int, [C.POINTER(RrtAdamTensor), C.c_int32, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_int32, C.c_int64, C.c_float, _P]),
     "rrt_dropout_mask": (C.c_int, [_P, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, _P]),

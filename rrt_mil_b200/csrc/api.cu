@@ -976,6 +976,13 @@ int check_backward_support(const rrt_config* c, int64_t L) {
 // Backward of y = act_rows . W^T + b followed by whatever produced `dy` (fp16, scaled rows [M, C_out]
 // with transpose dyT):   d_in = dy . W  (fp16 rows [M, C_in]),  dW = dy^T . act  (fp32 [C_out, C_in]).
 // act: the forward's fp16 input rows [M, C_in].
+// 1 (default): weight gradients read dy / act MN-major straight from their row-major buffers
+// (launch_gemm_tcgen05_wgrad); 0 (RRT_WGRAD=transpose): transposed fp16 copies + the K-major GEMM.
+bool wgrad_mn() {
+  static const bool on = [] { const char* e = getenv("RRT_WGRAD"); return !(e && !strcmp(e, "transpose")); }();
+  return on;
+}
+
 int linear_backward(const __half* dy, const __half* dyT, const __half* act, const float* w, int M,
                     int C_out, int C_in, const uint32_t* amax, __half* d_in, float* dW,
                     BwdWorkspace& b, cudaStream_t st) {
@@ -986,6 +993,13 @@ int linear_backward(const __half* dy, const __half* dyT, const __half* act, cons
       RRT_CUDA(rrt::launch_wt_convert(w, b.wT, C_out, C_in, st), "weight transpose"); }
     StageScope s_(kStBwdDgrad, st);
     RRT_CUDA(rrt::launch_gemm_tcgen05(dy, b.wT, d_in, true, M, C_in, C_out, e, st), "dgrad gemm");
+  }
+  if (wgrad_mn()) {
+    StageScope s_(kStBwdWgrad, st, 3);
+    RRT_CUDA(cudaMemsetAsync(dW, 0, (size_t)C_out * C_in * sizeof(float), st), "zero weight gradient");
+    RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad(dy, act, dW, M, C_out, C_in, st), "wgrad gemm (MN-major)");
+    RRT_CUDA(rrt::launch_scale_by_inv(dW, (size_t)C_out * C_in, amax, st), "wgrad unscale");
+    return RRT_OK;
   }
   { StageScope s_(kStBwdPrep, st);
     RRT_CUDA(rrt::launch_transpose_f16(act, M, C_in, b.actT, nullptr, nullptr, st), "activation transpose"); }
@@ -1013,8 +1027,10 @@ int attention_module_backward(const rrt_config* c, const rrt_attn_weights* a, co
                                             epeg ? ga->pe_w : nullptr, amax, R, P, D, heads,
                                             epeg ? c->epeg_k : 1, st), "attention backward"); }
   { StageScope s_(kStBwdPrep, st);
-    RRT_CUDA(rrt::launch_transpose_f16(b.dqkv, M, 3 * D, b.dqkvT, c->qkv_bias ? ga->qkv_b : nullptr,
-                                       amax, st), "dqkv transpose"); }
+    float* colsum = c->qkv_bias ? ga->qkv_b : nullptr;   // qkv.bias gradient = column sums of dqkv
+    __half* dqkvT = wgrad_mn() ? nullptr : b.dqkvT;
+    if (colsum || dqkvT)
+      RRT_CUDA(rrt::launch_transpose_f16(b.dqkv, M, 3 * D, dqkvT, colsum, amax, st), "dqkv transpose"); }
   return linear_backward(b.dqkv, b.dqkvT, z, a->qkv_w, M, 3 * D, D, amax, b.dz, ga->qkv_w, b, st);
 }
 
@@ -1044,7 +1060,7 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
     ident.L = T; ident.Np = T;
     { StageScope s_(kStBwdPrep, st, 2);
       RRT_CUDA(rrt::launch_amax(b.dLp, (size_t)T * D, &b.amax[0], st), "amax");
-      RRT_CUDA(rrt::launch_grad_partition(b.dLp, ident, T, D, &b.amax[0], b.dy, b.dyT,
+      RRT_CUDA(rrt::launch_grad_partition(b.dLp, ident, T, D, &b.amax[0], b.dy, wgrad_mn() ? nullptr : b.dyT,
                                           gr->cr_attn.proj_b, st,
                                           rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream)),
                "landmark grad rows"); }
@@ -1082,7 +1098,8 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
       return fail(RRT_E_INVALID, "NULL gradient buffer");
     const float* x_in = i > 0 ? tp.xs[i - 1] : x;
     { StageScope s_(kStBwdPrep, st);
-      RRT_CUDA(rrt::launch_grad_partition(g, gg, gg.Np, D, &b.amax[am], b.dy, b.dyT, ga->proj_b, st,
+      RRT_CUDA(rrt::launch_grad_partition(g, gg, gg.Np, D, &b.amax[am], b.dy, wgrad_mn() ? nullptr : b.dyT,
+                                          ga->proj_b, st,
                                           rrt::dropout_make(tr.drop_p, tr.seed, (unsigned)i)),
                "gradient partition"); }
     int rc = attention_module_backward(c, &w->layer_attn[i], ga, tp.z[i], tp.qkv[i], tp.o[i], gg.R, gg.P,
@@ -1187,6 +1204,18 @@ RRT_API int rrt_attention_backward(const void* qkv, const void* o, const void* d
                                           taps, (__half*)d_qkv, taps ? d_taps : nullptr, nullptr, R, P,
                                           dim, heads, epeg_k, (cudaStream_t)stream),
            "attention backward");
+  return RRT_OK;
+}
+
+RRT_API int rrt_linear_wgrad_f16(const void* dy_f16, const void* act_f16, float* dw, int64_t rows,
+                                 int32_t c_out, int32_t c_in, void* stream) {
+  if (!dy_f16 || !act_f16 || !dw || rows < 1 || rows > (1 << 30) || c_out < 8 || c_in < 8 || c_out % 8 || c_in % 8)
+    return fail(RRT_E_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  StageScope s_(kStOther, st, 2);
+  RRT_CUDA(cudaMemsetAsync(dw, 0, (size_t)c_out * c_in * sizeof(float), st), "zero dw");
+  RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad((const __half*)dy_f16, (const __half*)act_f16, dw, (int)rows, c_out,
+                                          c_in, st), "wgrad gemm");
   return RRT_OK;
 }
 

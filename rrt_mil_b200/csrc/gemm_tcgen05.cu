@@ -281,7 +281,11 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
 // W tile of a cluster column by its CM CTAs: every CTA TMA-loads a 1/CN slice of its A tile and a
 // 1/CM slice of its W tile and MULTICASTS them to the CTAs that share them, which divides the L2->SMEM
 // operand traffic (the measured bound of the 1x1 kernel) by up to 2 for a 2x2 cluster.
-template <int MODE, int BN, typename OutT, int CM, int CN>
+// MNMAJOR: both operands arrive MN-major -- A = a[K, M], W = w[K, N] row-major, i.e. C = a^T @ w with the
+// contraction over ROWS (the weight-gradient GEMM: dW[C_out, C_in] = dY[tokens, C_out]^T act[tokens, C_in],
+// straight from the row-major activations, no transposed copies).  Tiles are staged as 64 x 64 TMA boxes
+// (sm100.cuh::umma_desc_mn_sw128).
+template <int MODE, int BN, typename OutT, int CM, int CN, bool MNMAJOR = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                         const __grid_constant__ CUtensorMap tmB,
@@ -337,7 +341,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int tiles_mc = ((p.M + BM - 1) / BM + CM - 1) / CM;
   const int tiles_nc = ((p.N + BN - 1) / BN + CN - 1) / CN;
   const int num_ctiles = tiles_mc * tiles_nc;
-  const int KB = p.K / BK;
+  const int KB = (p.K + BK - 1) / BK;  // (K % 64 != 0 only with MNMAJOR: TMA zero-fills the missing rows)
   // split-K (kEpiAtomicAdd): work item wt = (tile wt % num_ctiles, K slice wt / num_ctiles of KS)
   const int KS = MODE == kEpiAtomicAdd ? p.ksplit : 1;
   const int num_work = num_ctiles * KS;
@@ -360,13 +364,21 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           if (is_a) {
             mbar_arrive_expect_tx(&full[s], A_BYTES);  // my slice + the peers' slices of MY tile
             uint8_t* dst = sA + s * A_BYTES + cj * (A_BYTES / CN);
-            if (CN > 1) tma_load_2d_mcast(dst, &tmA, &full[s], kb * BK, m0 + cj * (BM / CN), mask_a);
+            if (MNMAJOR) {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)  // 64 (M) x 64 (K rows) boxes, 8 KB each
+                tma_load_2d(dst + j * 8192, &tmA, &full[s], m0 + 64 * j, kb * BK);
+            } else if (CN > 1) tma_load_2d_mcast(dst, &tmA, &full[s], kb * BK, m0 + cj * (BM / CN), mask_a);
             else tma_load_2d(dst, &tmA, &full[s], kb * BK, m0);
             if (wt == cluster_id && kb == 0) stamp(p, 2);
           } else {
             mbar_arrive_expect_tx(&full[s], B_BYTES);
             uint8_t* dst = sB + s * B_BYTES + ci * (B_BYTES / CM);
-            if (CM > 1) tma_load_2d_mcast(dst, &tmB, &full[s], kb * BK, n0 + ci * (BN / CM), mask_b);
+            if (MNMAJOR) {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(dst + j * 8192, &tmB, &full[s], n0 + 64 * j, kb * BK);
+            } else if (CM > 1) tma_load_2d_mcast(dst, &tmB, &full[s], kb * BK, n0 + ci * (BN / CM), mask_b);
             else tma_load_2d(dst, &tmB, &full[s], kb * BK, n0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -377,7 +389,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc(kFmtF16, BM, BN);
+      constexpr uint32_t idesc = umma_idesc(kFmtF16, BM, BN) | (MNMAJOR ? kIdescMnMajorAB : 0u);
       int s = 0, ph = 0, acc = 0, aph = 0;
       for (int wt = cluster_id; wt < num_work; wt += num_clusters) {
         const int ks = wt / num_ctiles;
@@ -389,11 +401,15 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           mbar_wait(&full[s], ph);
           tc_fence_after();
           if (wt == cluster_id && kb == kb0) stamp(p, 4);
-          const uint64_t ad = umma_desc_k_sw128(smem_u32(sA + s * A_BYTES));
-          const uint64_t bd = umma_desc_k_sw128(smem_u32(sB + s * B_BYTES));
+          const uint64_t ad = MNMAJOR ? umma_desc_mn_sw128(smem_u32(sA + s * A_BYTES))
+                                      : umma_desc_k_sw128(smem_u32(sA + s * A_BYTES));
+          const uint64_t bd = MNMAJOR ? umma_desc_mn_sw128(smem_u32(sB + s * B_BYTES))
+                                      : umma_desc_k_sw128(smem_u32(sB + s * B_BYTES));
+          // K-major: 16 fp16 = 32 bytes per MMA along K (+2 in 16-B units); MN-major: 16 rows of 128 B (+128)
+          constexpr int kstep = MNMAJOR ? 128 : 2;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // 16 fp16 = 32 bytes per MMA along K: +2 in 16-B units
-            umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, ((kb - kb0) | k) != 0);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(d_tmem, ad + kstep * k, bd + kstep * k, idesc, ((kb - kb0) | k) != 0);
           // smem stage reusable once these MMAs have read it: tell every CTA that writes into it
           if (CSIZE > 1) umma_commit_mcast(&empty[s], (uint16_t)(mask_a | mask_b));
           else umma_commit(&empty[s]);
@@ -626,6 +642,20 @@ bool make_store_map(CUtensorMap* m, void* base, int rows, int N, int elem_bytes)
   return r == CUDA_SUCCESS;
 }
 
+// row-major fp16 [rows = K, cols = MN] -> 64 x 64 boxes (128-byte row segments), 128-byte swizzle
+bool make_map_mn(CUtensorMap* m, const __half* base, int k_rows, int mn_cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)mn_cols, (cuuint64_t)k_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)mn_cols * sizeof(__half)};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int sm_count() {
   static int n = 0;
   if (!n) {
@@ -758,6 +788,39 @@ cudaError_t launch_mode(const __half* a, const __half* w, const Tc05Params& p, c
   return launch_cfg<MODE, 256, OutT, 1, 1>(a, w, p, stream);
 }
 }  // namespace
+
+// dw[C_out, C_in] (fp32, zeroed by the caller) += dy[rows, C_out]^T @ act[rows, C_in]: both operands
+// MN-major straight from the row-major activations, split-K over the rows so that every SM has work.
+cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float* dw, int rows, int C_out,
+                                      int C_in, cudaStream_t stream) {
+  if (rows < 1 || C_out < 8 || C_in < 8 || (C_out % 8) || (C_in % 8)) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(act) | reinterpret_cast<uintptr_t>(dw)) & 15)
+    return cudaErrorInvalidValue;
+  constexpr int BN = 256;
+  using Cfg = TileCfg<BN>;
+  Tc05Params p{};
+  p.M = C_out; p.N = C_in; p.K = rows;
+  p.C = dw;
+  p.act = kActNone;
+  p.trace = nullptr;
+  const int tiles = ((C_out + BM - 1) / BM) * ((C_in + BN - 1) / BN), KB = (rows + BK - 1) / BK;
+  int ksplit = sm_count() / tiles;
+  if (ksplit > KB) ksplit = KB;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = ksplit;
+  CUtensorMap tmA, tmB;
+  if (!make_map_mn(&tmA, dy, rows, C_out) || !make_map_mn(&tmB, act, rows, C_in)) return cudaErrorUnknown;
+  auto kern = gemm_f16_tcgen05_kernel<kEpiAtomicAdd, BN, float, 1, 1, true>;
+  static DeviceOnce configured;
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+  }
+  int ctas = tiles * ksplit;
+  if (ctas > sm_count()) ctas = sm_count();
+  kern<<<ctas, NTHREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA, p);
+  return cudaGetLastError();
+}
 
 void set_gemm_cluster_mode(int mode) {
   if (mode == 128 || mode == 256) { g_gemm_narrow = mode == 128; return; }

@@ -47,6 +47,9 @@ struct GemmEpilogue {
 bool gemm_tcgen05_supported(int M, int N, int K);
 cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool out_f16, int M,
                                 int N, int K, const GemmEpilogue& epi, cudaStream_t stream);
+// weight gradient: dw[C_out, C_in] (fp32, zeroed) += dy[rows, C_out]^T @ act[rows, C_in] (fp16, row-major)
+cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float* dw, int rows, int C_out,
+                                      int C_in, cudaStream_t stream);
 void set_gemm_cluster_mode(int mode);  // debug/tuning: 22 = 2x2 clusters, 21 = 2x1, 11 = none
 extern long long* g_gemm_trace;  // debug: device buffer [8 CTAs][16] of clock64 stamps, or null
 // dst[i] = fp16(src[i]) round-to-nearest, saturating; n % 4 == 0

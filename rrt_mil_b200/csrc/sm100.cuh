@@ -162,6 +162,24 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
   return d;
 }
+// MN-major operand tile (the contraction index K is the SLOW index in memory: rows = K, 128-byte row
+// segments = 64 consecutive M/N elements), as TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B from a
+// row-major [K, MN] tensor in boxes of 64 (MN) x 64 (K): canonical layout
+// ((8 x 16 B, n), (8 rows, k)) : ((1, LBO), (128 B, SBO)) -- CUTLASS make_umma_desc<Major::MN>, B128.
+//   LBO = distance between consecutive 64-element MN chunks = one 64 x 64 box = 8192 B
+//   SBO = distance between consecutive 8-row K groups                        = 1024 B
+// One K=16 MMA spans two 8-row groups; the next MMA of a k-block starts 2048 B further.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(8192 >> 4) << 16;  // leading byte offset
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+constexpr uint32_t kIdescMnMajorAB = (1u << 15) | (1u << 16);  // a_major = b_major = MN
+
 // kind::tf32 / kind::f16 instruction descriptor: fp32 accumulate, both operands K-major
 enum UmmaFmt { kFmtF16 = 0, kFmtBF16 = 1, kFmtTF32 = 2 };
 __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {

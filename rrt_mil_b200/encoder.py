@@ -151,7 +151,7 @@ class _EncoderFunction(torch.autograd.Function):
         x, tape, *params = ctx.saved_tensors
         lib, cfg, N = cabi.lib(), enc._cfg, x.shape[0]
         dout = dout.contiguous().float()
-        names = [n for n, _ in enc.named_parameters()]
+        names = enc._named_param_cache()[0]
         # one zero-initialised flat buffer for every parameter gradient (64-float aligned views)
         offs, total = [], 0
         for p_ in params:
@@ -357,6 +357,20 @@ class RRTEncoder(nn.Module):
             attn("cr_msa.attn.attn.", g.cr_attn)
         return g
 
+    def _named_param_cache(self):
+        """(names, parameters) in ``named_parameters()`` order.  Walking the module tree costs ~150 us
+        per training step; the tree of an encoder is fixed after construction, so the walk is cached
+        and redone only if a parameter object was replaced (``module.weight = nn.Parameter(...)``)."""
+        c = self.__dict__.get("_np_cache")
+        if c is None or any(self_p is not q for self_p, q in zip(c[1], c[2]())):
+            named = list(self.named_parameters())
+            holders = [(self.get_submodule(n.rpartition(".")[0]) if "." in n else self, n.rpartition(".")[2])
+                       for n, _ in named]
+            getter = lambda: [h._parameters[k] for h, k in holders]  # noqa: E731
+            c = ([n for n, _ in named], [p for _, p in named], getter)
+            self.__dict__["_np_cache"] = c
+        return c
+
     def _train_dropout(self):
         """(p, seed) of this forward: ``drop_out`` is active in training mode only, like ``nn.Dropout``.
         The seed comes from torch's CPU generator, so ``torch.manual_seed`` makes steps reproducible
@@ -371,7 +385,7 @@ class RRTEncoder(nn.Module):
 
     def _needs_grad(self, x) -> bool:
         return torch.is_grad_enabled() and (
-            x.requires_grad or any(p.requires_grad for p in self.parameters()))
+            x.requires_grad or any(p.requires_grad for p in self._named_param_cache()[1]))
 
     def _check_mode(self, x, allow_grad=False):
         if not x.is_cuda:
@@ -404,7 +418,7 @@ class RRTEncoder(nn.Module):
         x = x.contiguous()
         if self._needs_grad(x) or (self.training and self.drop_out > 0):
             # autograd / training path: forward with a tape (+ proj dropout), backward kernels
-            return _EncoderFunction.apply(self, x, *self.parameters())
+            return _EncoderFunction.apply(self, x, *self._named_param_cache()[1])
         lib, cfg = cabi.lib(), self._cfg
         with torch.cuda.device(x.device):
             nbytes = cabi.workspace_bytes(cfg, N)
