@@ -613,8 +613,36 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled costs 1-2 us of host time and a bag needs a dozen descriptors; the same
+// buffers (workspace, weight shadows) come back call after call, so encoded maps are kept in a small
+// per-thread direct-mapped cache keyed by everything that goes into the descriptor.
+struct MapKey {
+  const void* base; int a, b, c, kind;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && a == o.a && b == o.b && c == o.c && kind == o.kind;
+  }
+};
+struct MapSlot { MapKey key; CUtensorMap map; bool valid; };
+constexpr int kMapSlots = 128;
+bool cached_map(const MapKey& k, CUtensorMap* out, bool (*encode)(const MapKey&, CUtensorMap*)) {
+  static thread_local MapSlot slots[kMapSlots] = {};
+  size_t h = (reinterpret_cast<uintptr_t>(k.base) >> 8) * 0x9E3779B97F4A7C15ull;
+  h ^= (size_t)k.a * 0x85EBCA6Bull ^ (size_t)k.b * 0xC2B2AE35ull ^ (size_t)k.c * 0x27D4EB2Full ^ (size_t)k.kind;
+  MapSlot& s = slots[(h >> 20) % kMapSlots];
+  if (s.valid && s.key == k) { *out = s.map; return true; }
+  if (!encode(k, out)) return false;
+  s.key = k; s.map = *out; s.valid = true;
+  return true;
+}
+
 // row-major fp16 [rows, K] -> tiles of box_rows x 64 halves (128 bytes), 128-byte swizzle
+bool encode_map(const MapKey& k, CUtensorMap* m);
 bool make_map(CUtensorMap* m, const __half* base, int rows, int K, int box_rows) {
+  return cached_map(MapKey{base, rows, K, box_rows, 0}, m, encode_map);
+}
+bool encode_map(const MapKey& key, CUtensorMap* m) {
+  const __half* base = static_cast<const __half*>(key.base);
+  const int rows = key.a, K = key.b, box_rows = key.c;
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -628,7 +656,13 @@ bool make_map(CUtensorMap* m, const __half* base, int rows, int K, int box_rows)
 }
 
 // output [rows, N] of 2- or 4-byte elements -> 32 x 32 element boxes; swizzle = the box row pitch
+bool encode_store_map(const MapKey& k, CUtensorMap* m);
 bool make_store_map(CUtensorMap* m, void* base, int rows, int N, int elem_bytes) {
+  return cached_map(MapKey{base, rows, N, elem_bytes, 1}, m, encode_store_map);
+}
+bool encode_store_map(const MapKey& key, CUtensorMap* m) {
+  void* base = const_cast<void*>(key.base);
+  const int rows = key.a, N = key.b, elem_bytes = key.c;
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows};
@@ -643,7 +677,13 @@ bool make_store_map(CUtensorMap* m, void* base, int rows, int N, int elem_bytes)
 }
 
 // row-major fp16 [rows = K, cols = MN] -> 64 x 64 boxes (128-byte row segments), 128-byte swizzle
+bool encode_map_mn(const MapKey& k, CUtensorMap* m);
 bool make_map_mn(CUtensorMap* m, const __half* base, int k_rows, int mn_cols) {
+  return cached_map(MapKey{base, k_rows, mn_cols, 0, 2}, m, encode_map_mn);
+}
+bool encode_map_mn(const MapKey& key, CUtensorMap* m) {
+  const __half* base = static_cast<const __half*>(key.base);
+  const int k_rows = key.a, mn_cols = key.b;
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)mn_cols, (cuuint64_t)k_rows};

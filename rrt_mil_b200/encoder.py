@@ -292,6 +292,7 @@ class RRTEncoder(nn.Module):
 
     def invalidate_weight_cache(self) -> None:
         self._shadow.clear()
+        self.__dict__.pop("_w_cache", None)
 
     def _attn_weights(self, inner: InnerAttention, dst: cabi.RrtAttnWeights, device, shadows=False):
         p = self._ptr
@@ -303,6 +304,19 @@ class RRTEncoder(nn.Module):
             dst.proj_w_f16 = self._f16_shadow(inner.proj.weight)
 
     def _weights(self, device) -> cabi.RrtWeights:
+        """``rrt_weights`` over the parameters (and, in eval mode, their fp16 shadows).  Building it walks
+        ~60 pointers with device / dtype / layout checks (~100 us); it is rebuilt only when a parameter's
+        storage or version counter, the device or the train/eval mode changed."""
+        params = self._named_param_cache()[1]
+        key = (device, self.training, tuple((q.data_ptr(), q._version) for q in params))
+        c = self.__dict__.get("_w_cache")
+        if c is not None and c[0] == key:
+            return c[1]
+        w = self._build_weights(device)
+        self.__dict__["_w_cache"] = (key, w)
+        return w
+
+    def _build_weights(self, device) -> cabi.RrtWeights:
         w, p = cabi.RrtWeights(), self._ptr
         w.norm_w, w.norm_b = p(self.norm.weight, device), p(self.norm.bias, device)
         for i, layer in enumerate(self.layers):
