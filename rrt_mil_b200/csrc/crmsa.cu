@@ -952,6 +952,7 @@ cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const 
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
       if (e != cudaSuccess) return e;                                                              \
     }                                                                                              \
+    prefer_max_shared(crmsa_rowstats_kernel<VV, KK>);                                                      \
     crmsa_rowstats_kernel<VV, KK><<<blocks, 256, smem, stream>>>(x1, gamma, beta, phi, stats, logits, grid, k); \
   }
 #define RRT_RS_K(VV) { if (KM == 4) RRT_RS(VV, 4) else if (KM == 8) RRT_RS(VV, 8) else RRT_RS(VV, 16) }
@@ -978,6 +979,7 @@ cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const 
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
       if (e != cudaSuccess) return e;                                                              \
     }                                                                                              \
+    prefer_max_shared(crmsa_combine2_kernel<KK>);                                                  \
     crmsa_combine2_kernel<KK><<<g, 256, smem, stream>>>(x1, gamma, beta, stats, logits, landmarks, \
                                                         rstat, grid, D, k);                        \
   }
@@ -1002,7 +1004,7 @@ cudaError_t launch_crmsa_dispatch(const float* x1, const float* x0, const float*
   if (D % 128 || k < 1 || k > RRT_MAX_K_DEV) return cudaErrorInvalidValue;
   if (grid.L == 0) return cudaSuccess;
   int blocks = (grid.L + 7) / 8;
-  RRT_DISPATCH_V(D, crmsa_dispatch_kernel<V><<<blocks, 256, 0, stream>>>(x1, x0, logits, rstat, lm, gamma, beta, out, grid, k));
+  RRT_DISPATCH_V(D, prefer_max_shared(crmsa_dispatch_kernel<V>); crmsa_dispatch_kernel<V><<<blocks, 256, 0, stream>>>(x1, x0, logits, rstat, lm, gamma, beta, out, grid, k));
   return cudaGetLastError();
 }
 

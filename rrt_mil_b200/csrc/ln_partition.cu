@@ -97,7 +97,7 @@ cudaError_t launch_ln_partition(const float* x, const float* gamma, const float*
   if (D % 128) return cudaErrorInvalidValue;
   const int wpb = 8;
   int blocks = (grid.Np + wpb - 1) / wpb;
-  RRT_DISPATCH_V(D, ln_partition_kernel<V><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, z, grid));
+  RRT_DISPATCH_V(D, prefer_max_shared(ln_partition_kernel<V>); ln_partition_kernel<V><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, z, grid));
   return cudaGetLastError();
 }
 
@@ -108,7 +108,7 @@ cudaError_t launch_add_layernorm(const float* x1, const float* x0, const float* 
   if (L == 0) return cudaSuccess;
   const int wpb = 8;
   int blocks = (L + wpb - 1) / wpb;
-  RRT_DISPATCH_V(D, add_layernorm_kernel<V><<<blocks, wpb * 32, 0, stream>>>(x1, x0, gamma, beta, out, L));
+  RRT_DISPATCH_V(D, prefer_max_shared(add_layernorm_kernel<V>); add_layernorm_kernel<V><<<blocks, wpb * 32, 0, stream>>>(x1, x0, gamma, beta, out, L));
   return cudaGetLastError();
 }
 
