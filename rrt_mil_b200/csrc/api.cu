@@ -619,6 +619,8 @@ RRT_API int rrt_encoder_forward_batch(const rrt_config* cfg, const rrt_weights* 
       RRT_CUDA(cudaStreamWaitEvent(lane_stream[l], g_lanes.fork, 0), "fork wait");
     }
   }
+  // >= 4 bags in flight: the bag-sized GEMMs keep to 64 SMs (csrc/gemm_tcgen05.cu, "SM cap")
+  rrt::set_gemm_sm_cap(lanes >= 4 ? 64 : 0);
   for (int i = 0; i < n_bags; ++i) {
     const int l = i % lanes;
     Workspace ws{};
@@ -626,6 +628,7 @@ RRT_API int rrt_encoder_forward_batch(const rrt_config* cfg, const rrt_weights* 
     rc = encoder_forward(cfg, w, xs[i], outs[i], Ls[i], ws, lane_stream[l]);
     if (rc) break;
   }
+  rrt::set_gemm_sm_cap(0);
   for (int l = 1; l < lanes; ++l) {  // always join, also on error, so `stream` stays ordered
     cudaEventRecord(g_lanes.done[l], lane_stream[l]);
     cudaStreamWaitEvent(user, g_lanes.done[l], 0);

@@ -15,6 +15,7 @@
 // fp16 carries the same 10 mantissa bits as tf32 (parity bar: 1e-3 rel) at twice the tensor rate
 // and half the operand traffic; with fp32 (tf32) tiles this kernel was bound by L2->SMEM operand
 // bytes (profiles/r01_ncu_full_v2_tf32_summary.csv).
+#include <cstdlib>
 #include "kernels.cuh"
 #include "sm100.cuh"
 
@@ -717,6 +718,8 @@ cudaError_t launch_convert_f16(const float* src, __half* dst, size_t n, cudaStre
   return cudaGetLastError();
 }
 
+// SM cap of the bag-sized GEMMs; the batch entry point sets it while several bags are in flight
+static thread_local int g_gemm_sm_cap = 0;
 long long* g_gemm_trace = nullptr;  // debug hook (rrt_debug_set_gemm_trace): [8 launches][8 CTAs][16]
 static int g_trace_launch = 0;
 
@@ -747,6 +750,14 @@ cudaError_t launch_cfg(const __half* a, const __half* w, const Tc05Params& p, cu
   const int ctiles = (((p.M + BM - 1) / BM + CM - 1) / CM) * (((p.N + BN - 1) / BN + CN - 1) / CN) *
                      (MODE == kEpiAtomicAdd ? p.ksplit : 1);
   int clusters = sm_count() / CSIZE;
+  // SM cap (set_gemm_sm_cap / RRT_GEMM_SMS=n, 0 = none): persistent grid of at most n CTAs for the bag-sized
+  // GEMMs.  With several bags in flight the GEMMs (tensor / operand-ingest bound, ~7 % of DRAM bandwidth)
+  // then share the GPU with the HBM-bound kernels of the other bags instead of taking turns with them, and
+  // every CTA pipelines 7 tiles instead of 3 (prologue and last epilogue amortised).  Measured, 16 bags,
+  // 4 lanes: 71.2 us/bag on 148 SMs, 70.6 / 69.8 / 69.4 / 68.4 on 132 / 111 / 96 / 74, 67.7 on 64 and 56.
+  static const int env_cap = [] { const char* e = getenv("RRT_GEMM_SMS"); return e ? atoi(e) : -1; }();
+  const int sm_cap = env_cap >= 0 ? env_cap : g_gemm_sm_cap;
+  if (sm_cap > 0 && BN == 256 && clusters > sm_cap / CSIZE) clusters = sm_cap / CSIZE > 0 ? sm_cap / CSIZE : 1;
   if (ctiles < clusters) clusters = ctiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CSIZE);
@@ -861,6 +872,8 @@ cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float
   kern<<<ctas, NTHREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA, p);
   return cudaGetLastError();
 }
+
+void set_gemm_sm_cap(int n) { g_gemm_sm_cap = n; }
 
 void set_gemm_cluster_mode(int mode) {
   if (mode == 128 || mode == 256) { g_gemm_narrow = mode == 128; return; }

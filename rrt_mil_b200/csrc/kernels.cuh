@@ -50,7 +50,9 @@ cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool 
 // weight gradient: dw[C_out, C_in] (fp32, zeroed) += dy[rows, C_out]^T @ act[rows, C_in] (fp16, row-major)
 cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float* dw, int rows, int C_out,
                                       int C_in, cudaStream_t stream);
-void set_gemm_cluster_mode(int mode);  // debug/tuning: 22 = 2x2 clusters, 21 = 2x1, 11 = none
+void set_gemm_cluster_mode(int mode);
+// at most n SMs for the bag-sized GEMMs launched by THIS host thread from now on (0 = all)
+void set_gemm_sm_cap(int n);  // debug/tuning: 22 = 2x2 clusters, 21 = 2x1, 11 = none
 extern long long* g_gemm_trace;  // debug: device buffer [8 CTAs][16] of clock64 stamps, or null
 // dst[i] = fp16(src[i]) round-to-nearest, saturating; n % 4 == 0
 cudaError_t launch_convert_f16(const float* src, __half* dst, size_t n, cudaStream_t stream);
