@@ -232,10 +232,23 @@ RRT_API int rrt_mil_head_workspace_bytes(int64_t L, int32_t in_dim, int32_t dim,
                                          size_t* bytes);
 
 /* patch_to_emb: out[L, out_dim] = act(x[L, in_dim] @ w[out_dim, in_dim]^T + b)   (modules/rrt.py:208-217,
- * 228).  w_f16 = optional fp16 shadow of w (rrt_convert_f16) or NULL.  in_dim % 64 == 0. */
+ * 228).  w_f16 = optional fp16 shadow of w (rrt_convert_f16) or NULL.  in_dim % 64 == 0.
+ * drop_p / seed: RRTMIL.dp (nn.Dropout(0.25), modules/rrt.py:215,229) in training mode, counter-based mask
+ * stream RRT_DROP_STREAM_PATCH over [L, out_dim]; 0 = eval.  After the call the workspace starts with the
+ * fp16 copy of x, which rrt_patch_embed_backward reads as its tape. */
+#define RRT_DROP_STREAM_PATCH 65
 RRT_API int rrt_patch_embed_forward(const float* x, int64_t L, int32_t in_dim, int32_t out_dim,
                                     const float* w, const float* b, const void* w_f16, int32_t act,
-                                    float* out, void* workspace, size_t workspace_bytes, void* stream);
+                                    float* out, void* workspace, size_t workspace_bytes, float drop_p,
+                                    uint64_t seed, void* stream);
+/* Backward of patch_to_emb (+ dp): dout [L, out_dim] = gradient wrt the forward's `out`; dw [out_dim, in_dim],
+ * db [out_dim] (nullable) are overwritten.  act = RRT_ACT_RELU (mask read off `out`) or RRT_ACT_NONE (dropout
+ * mask regenerated from drop_p / seed).  tape = the forward's workspace, untouched since.  No gradient wrt x
+ * (the bag's features are data).  workspace >= 512 + L * out_dim * 2 bytes (256-aligned). */
+RRT_API int rrt_patch_embed_backward(const float* dout, const float* out, int64_t L, int32_t in_dim,
+                                     int32_t out_dim, int32_t act, float drop_p, uint64_t seed,
+                                     const void* tape, size_t tape_bytes, float* dw, float* db,
+                                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* DAttention pooling + predictor (modules/datten.py:5-38,85-101, modules/rrt.py:221-241):
  *   A = act(h @ w1^T + b1) @ w2^T + b2  [L];  a = softmax_L(A);  pooled[dim] = a @ h;
@@ -315,6 +328,18 @@ RRT_API int rrt_attention_backward(const void* qkv, const void* o, const void* d
                                    int32_t heads, int32_t epeg_k, void* stream);
 RRT_API int rrt_layernorm_backward(const float* x, const float* gamma, const float* dy, float* dx,
                                    float* dgamma, float* dbeta, int64_t L, int32_t dim, void* stream);
+
+/* Backward of rrt_attn_pool_forward (autograd of modules/datten.py:28-38 + the predictor): dlogits
+ * [n_classes] -> dh [L, dim] (overwritten) and the gradients of w1 [hid, dim], b1 [hid] (nullable), w2 [hid],
+ * b2 [1] (nullable), pred_w [n_classes, dim], pred_b [n_classes] (nullable), all overwritten.  pooled = the
+ * forward's output; tape = the forward's workspace, untouched since.  act = relu | tanh | none. */
+RRT_API int rrt_mil_head_backward_workspace_bytes(int64_t L, int32_t dim, int32_t hid, size_t* bytes);
+RRT_API int rrt_attn_pool_backward(const float* h, int64_t L, int32_t dim, int32_t hid, const float* w1,
+                                   int32_t act, const float* w2, const float* pred_w, int32_t n_classes,
+                                   const float* pooled, const float* dlogits, const void* tape,
+                                   size_t tape_bytes, float* dh, float* dw1, float* db1, float* dw2,
+                                   float* db2, float* dpred_w, float* dpred_b, void* workspace,
+                                   size_t workspace_bytes, void* stream);
 
 /* ---- optimizer step of the training harness (main.py:224-233: torch.optim.Adam, lr 2e-4, wd 1e-5) ----
  * One launch updates every tensor of the list with torch.optim.Adam (decoupled = 0: L2 weight decay

@@ -94,6 +94,13 @@ TRAIN_CASES = [
     ("train_n700_p0", 700, dict(), 0.0, 0),   # eval-arithmetic backward pinned against reference autograd
 ]
 GRAD_SEED = 43
+# Full RRTMIL train step: name, L, input_dim, n_classes, da_act, da_bias, label, encoder
+# overrides, dp p, trans_dropout p, first seed.  Reference RRTMIL in .train(), its nn.Dropout modules (dp and
+# every proj_drop) replaced by the library's masks, loss = CrossEntropy(logits, label) (main.py:436-447).
+MIL_TRAIN_CASES = [
+    ("miltrain_r50_n800", 800, 1024, 2, "relu", False, 1, dict(), 0.25, 0.1, 500),
+    ("miltrain_tanh_bias_n600", 600, 512, 3, "tanh", True, 2, dict(epeg_k=9, all_shortcut=True), 0.25, 0.1, 900),
+]
 
 MAX_ROWS = 96
 WEIGHT_SEED = 2021  # the reference's default --seed (main.py:645)
@@ -244,6 +251,43 @@ def generate_train(name, L, overrides, p, seed):
                 bag_seed=bag_seed, bag_kind="relu", grad_seed=GRAD_SEED, min_crmsa_tie_gap=gap)
 
 
+def generate_mil_train(name, L, input_dim, n_classes, da_act, da_bias, label, overrides, p_dp, p_enc, seed):
+    cfg = O.EncoderConfig(**overrides)
+    w = O.make_mil_weights(cfg, input_dim, n_classes, WEIGHT_SEED, da_bias=da_bias)
+    x = O.make_bag(L, input_dim, 7, kind="randn")
+    enc_w = {k[len("online_encoder."):]: v for k, v in w.items() if k.startswith("online_encoder.")}
+    for _ in range(400):   # first seed whose bag stays off the CR-MSA argmin / argmax ties (crmsa_tie_gap)
+        h0 = torch.relu(torch.nn.functional.linear(x, w["patch_to_emb.0.weight"], w["patch_to_emb.0.bias"]))
+        h0 = h0 * O.dropout_mask(L, 512, p_dp, seed, O.DROP_STREAM_PATCH)
+        gap = crmsa_tie_gap(h0, enc_w, cfg, (p_enc, seed + 1))
+        if gap >= MIN_TIE_GAP:
+            break
+        seed += 2
+    else:
+        raise SystemExit(f"{name}: no seed with a CR-MSA tie gap >= {MIN_TIE_GAP}")
+    ref = shim.import_reference_rrt()
+    m = ref.RRTMIL(input_dim=input_dim, n_classes=n_classes, act="relu", da_act=da_act, da_bias=da_bias,
+                   dropout=p_dp, trans_dropout=p_enc, region_num=cfg.region_num, n_layers=cfg.n_layers,
+                   epeg_k=cfg.epeg_k, crmsa_k=cfg.crmsa_k, all_shortcut=cfg.all_shortcut,
+                   crmsa_heads=cfg.crmsa_heads).double().train()
+    m.load_state_dict(w, strict=True)
+    m.dp = _MaskMul(O.dropout_mask(L, 512, p_dp, seed, O.DROP_STREAM_PATCH))
+    install_dropout_masks(m.online_encoder, cfg, L, p_enc, seed + 1)
+    with torch.enable_grad():
+        logits = m(x.unsqueeze(0))
+        loss = torch.nn.functional.cross_entropy(logits, torch.tensor([label]))
+        loss.backward()
+    out = {"logits": logits[0].detach().numpy(), "loss": np.array(float(loss))}
+    for n_, p_ in m.named_parameters():
+        g = p_.grad.numpy() if p_.grad is not None else np.zeros(tuple(p_.shape))
+        out["g:" + n_], _ = sample_rows(g)
+        out["gfro:" + n_] = np.array(np.linalg.norm(g))
+    np.savez(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+    return dict(name=name, L=L, input_dim=input_dim, n_classes=n_classes, da_act=da_act, da_bias=da_bias,
+                label=label, config=cfg.to_dict(), dropout=p_dp, trans_dropout=p_enc, seed=seed,
+                weight_seed=WEIGHT_SEED, bag_seed=7, min_crmsa_tie_gap=gap)
+
+
 def generate_mil(name, L, input_dim, n_classes, act, da_act, da_bias, overrides):
     cfg = O.EncoderConfig(**overrides)
     w = O.make_mil_weights(cfg, input_dim, n_classes, WEIGHT_SEED, da_bias=da_bias)
@@ -272,7 +316,8 @@ def main():
     mpath = os.path.join(GOLDEN_DIR, "manifest.json")
     if only_new and os.path.isfile(mpath):
         om = json.load(open(mpath))
-        old = {c["name"]: c for k in ("cases", "mil_cases", "train_cases") for c in om.get(k, [])}
+        old = {c["name"]: c for k in ("cases", "mil_cases", "train_cases", "mil_train_cases")
+               for c in om.get(k, [])}
 
     def have(name):
         return only_new and name in old and os.path.isfile(os.path.join(GOLDEN_DIR, name + ".npz"))
@@ -302,8 +347,15 @@ def main():
             continue
         train.append(generate_train(*case))
         print("golden", case[0], flush=True)
+    mil_train = []
+    for case in MIL_TRAIN_CASES:
+        if have(case[0]):
+            mil_train.append(old[case[0]])
+            continue
+        mil_train.append(generate_mil_train(*case))
+        print("golden", case[0], flush=True)
     json.dump(dict(reference_commit=ref_commit, torch=torch.__version__, numpy=np.__version__,
-                   cases=manifest, mil_cases=mil, train_cases=train),
+                   cases=manifest, mil_cases=mil, train_cases=train, mil_train_cases=mil_train),
               open(os.path.join(GOLDEN_DIR, "manifest.json"), "w"), indent=1)
 
 

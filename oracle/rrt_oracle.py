@@ -124,6 +124,7 @@ def region_slot_map(H: int, rs: int) -> torch.Tensor:
 # training-mode proj_drop (modules/rmsa.py:70,132)
 # ----------------------------------------------------------------------------------------
 DROP_STREAM_CRMSA = 64  # == RRT_DROP_STREAM_CRMSA (include/rrt_b200.h); R-MSA layer i uses stream i
+DROP_STREAM_PATCH = 65  # == RRT_DROP_STREAM_PATCH: RRTMIL.dp behind patch_to_emb
 _M64 = (1 << 64) - 1
 
 
@@ -324,13 +325,17 @@ def _act(name):
 
 
 def mil_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfig, act: str = "relu",
-                da_act: str = "relu", order: str = "reference"):
+                da_act: str = "relu", order: str = "reference", drop=None):
     """``RRTMIL.forward`` (eval) for one bag ``x`` [L, input_dim] -> (logits [C], attention [L])
     (modules/rrt.py:227-246, modules/datten.py:28-38,94-101).  Encoder weights carry the reference's
     ``online_encoder.`` prefix."""
     h = _act(act)(F.linear(x, w["patch_to_emb.0.weight"], w["patch_to_emb.0.bias"]))
+    enc_drop = None
+    if drop is not None:   # training mode: drop = (dp p, dp seed, trans_dropout p, encoder seed)
+        h = h * dropout_mask(h.shape[0], h.shape[1], drop[0], drop[1], DROP_STREAM_PATCH, h.dtype)
+        enc_drop = (drop[2], drop[3]) if drop[2] > 0 else None
     enc = {k[len("online_encoder."):]: v for k, v in w.items() if k.startswith("online_encoder.")}
-    h = encoder_forward(h, enc, cfg, order)
+    h = encoder_forward(h, enc, cfg, order, drop=enc_drop)
     keys = sorted(k for k in w if k.startswith("pool_fn.attention.attention.") and k.endswith("weight"))
     k0, k1 = keys[0], keys[-1]
     a = _act(da_act)(F.linear(h, w[k0], w.get(k0[:-6] + "bias")))

@@ -713,7 +713,9 @@ RRT_API int rrt_mil_head_workspace_bytes(int64_t L, int32_t in_dim, int32_t dim,
 
 RRT_API int rrt_patch_embed_forward(const float* x, int64_t L, int32_t in_dim, int32_t out_dim,
                                     const float* w, const float* b, const void* w_f16, int32_t act,
-                                    float* out, void* workspace, size_t workspace_bytes, void* stream) {
+                                    float* out, void* workspace, size_t workspace_bytes, float drop_p,
+                                    uint64_t seed, void* stream) {
+  if (!(drop_p >= 0.f) || drop_p >= 1.f) return fail(RRT_E_INVALID, "drop_p must be in [0, 1)");
   if (!x || !w || !out || L < 1 || L > (1 << 28)) return fail(RRT_E_INVALID, "bad argument");
   if (in_dim % 64 || out_dim % 4 || !rrt::gemm_tcgen05_supported((int)L, out_dim, in_dim))
     return fail(RRT_E_INVALID, "patch_embed: in_dim must be a multiple of 64, out_dim of 4");
@@ -736,6 +738,12 @@ RRT_API int rrt_patch_embed_forward(const float* x, int64_t L, int32_t in_dim, i
   e.bias = b;
   e.act = a;
   RRT_CUDA(rrt::launch_gemm_tcgen05(x16, w16, out, false, (int)L, out_dim, in_dim, e, st), "patch_embed gemm");
+  if (drop_p > 0.f) {  // RRTMIL.dp (modules/rrt.py:215,229), training mode
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    RRT_CUDA(rrt::launch_dropout_inplace(out, (size_t)L * out_dim,
+                                         rrt::dropout_make(drop_p, seed, RRT_DROP_STREAM_PATCH), st),
+             "patch_embed dropout");
+  }
   return RRT_OK;
 }
 
@@ -775,6 +783,114 @@ RRT_API int rrt_attn_pool_forward(const float* h, int64_t L, int32_t dim, int32_
   RRT_CUDA(rrt::launch_gemm_tcgen05(h16, w16, hidden, false, (int)L, hid, dim, e, st), "attn_pool gemm");
   RRT_CUDA(rrt::launch_attn_pool(h, hidden, w2, b2, pred_w, pred_b, pred_w ? n_classes : 0, scratch, pooled,
                                  logits, attn, attn_raw, (int)L, dim, hid, st), "attn_pool");
+  return RRT_OK;
+}
+
+// ---- backward of the two RRTMIL layers around the encoder ---------------------------
+namespace {
+size_t head_bwd_ws_bytes(int64_t L, int dim, int hid) {
+  return 256 + align_up((size_t)(dim + 4) * 4) + align_up((size_t)L * hid * 4) + align_up((size_t)L * hid * 2) +
+         align_up((size_t)hid * dim * 2) + align_up((size_t)L * dim * 2) + 256;
+}
+}  // namespace
+
+RRT_API int rrt_mil_head_backward_workspace_bytes(int64_t L, int32_t dim, int32_t hid, size_t* bytes) {
+  if (!bytes || L < 1 || L > (1 << 28) || dim < 1 || hid < 1) return fail(RRT_E_INVALID, "bad argument");
+  *bytes = head_bwd_ws_bytes(L, dim, hid);
+  return RRT_OK;
+}
+
+RRT_API int rrt_patch_embed_backward(const float* dout, const float* out, int64_t L, int32_t in_dim,
+                                     int32_t out_dim, int32_t act, float drop_p, uint64_t seed,
+                                     const void* tape, size_t tape_bytes, float* dw, float* db,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dout || !out || !tape || !dw || L < 1 || L > (1 << 28)) return fail(RRT_E_INVALID, "bad argument");
+  if (in_dim % 64 || out_dim % 128) return fail(RRT_E_INVALID, "patch_embed backward: in_dim % 64, out_dim % 128");
+  if (act != RRT_ACT_RELU && act != RRT_ACT_NONE)
+    return fail(RRT_E_INVALID, "patch_embed backward covers act = relu | none (gelu needs the pre-activation)");
+  if (!(drop_p >= 0.f) || drop_p >= 1.f) return fail(RRT_E_INVALID, "drop_p must be in [0, 1)");
+  if (tape_bytes < head_ws_bytes(L, in_dim, out_dim, 1)) return fail(RRT_E_WORKSPACE, "tape too small");
+  const size_t need = 256 + align_up((size_t)L * out_dim * 2) + 256;
+  if (!workspace || (((uintptr_t)workspace | (uintptr_t)tape) & 255) || workspace_bytes < need)
+    return fail(RRT_E_WORKSPACE, "workspace too small or misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const __half* x16 = static_cast<const __half*>(tape);      // the forward's fp16 copy of x
+  uint32_t* amax = static_cast<uint32_t*>(workspace);
+  __half* dz16 = reinterpret_cast<__half*>(static_cast<char*>(workspace) + 256);
+  StageScope s_(kStOther, st, 5);
+  RRT_CUDA(cudaMemsetAsync(amax, 0, 256, st), "zero amax");
+  if (db) RRT_CUDA(cudaMemsetAsync(db, 0, (size_t)out_dim * 4, st), "zero db");
+  RRT_CUDA(rrt::launch_amax(dout, (size_t)L * out_dim, amax, st), "amax");
+  rrt::Grid ident{};
+  ident.L = (int)L; ident.Np = (int)L;
+  // dz = dout * [out != 0] / (1 - p) for ReLU (+ dropout); act = none: the dropout mask is regenerated
+  const bool relu = act == RRT_ACT_RELU;
+  RRT_CUDA(rrt::launch_grad_partition(dout, ident, (int)L, out_dim, amax, dz16, nullptr, db, st,
+                                      relu ? rrt::Dropout{} : rrt::dropout_make(drop_p, seed, RRT_DROP_STREAM_PATCH),
+                                      relu ? out : nullptr, relu && drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f),
+           "patch_embed grad rows");
+  RRT_CUDA(cudaMemsetAsync(dw, 0, (size_t)out_dim * in_dim * 4, st), "zero dw");
+  RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad(dz16, x16, dw, (int)L, out_dim, in_dim, st), "patch_embed wgrad");
+  RRT_CUDA(rrt::launch_scale_by_inv(dw, (size_t)out_dim * in_dim, amax, st), "patch_embed unscale");
+  return RRT_OK;
+}
+
+RRT_API int rrt_attn_pool_backward(const float* h, int64_t L, int32_t dim, int32_t hid, const float* w1,
+                                   int32_t act, const float* w2, const float* pred_w, int32_t n_classes,
+                                   const float* pooled, const float* dlogits, const void* tape,
+                                   size_t tape_bytes, float* dh, float* dw1, float* db1, float* dw2,
+                                   float* db2, float* dpred_w, float* dpred_b, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  if (!h || !w1 || !w2 || !pred_w || !pooled || !dlogits || !tape || !dh || !dw1 || !dw2 || !dpred_w ||
+      L < 1 || L > (1 << 28) || n_classes < 1)
+    return fail(RRT_E_INVALID, "bad argument");
+  if (dim % 128 || dim > 1024 || hid % 128 || hid > 256)
+    return fail(RRT_E_INVALID, "attn_pool backward: dim % 128 (<= 1024), hid in {128, 256}");
+  if (act != RRT_ACT_RELU && act != RRT_ACT_TANH && act != RRT_ACT_NONE)
+    return fail(RRT_E_INVALID, "attn_pool backward covers act = relu | tanh | none (gelu needs the pre-activation)");
+  if (tape_bytes < head_ws_bytes(L, dim, dim, hid)) return fail(RRT_E_WORKSPACE, "tape too small");
+  if (!workspace || (((uintptr_t)workspace | (uintptr_t)tape) & 255) || workspace_bytes < head_bwd_ws_bytes(L, dim, hid))
+    return fail(RRT_E_WORKSPACE, "workspace too small or misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  // the forward's workspace (rrt_attn_pool_forward): h16 | weight scratch | hidden | scores | partials | (M, Z)
+  const char* tp = static_cast<const char*>(tape);
+  const __half* h16 = reinterpret_cast<const __half*>(tp);
+  tp += align_up((size_t)L * dim * 2);
+  tp += align_up((size_t)dim * (dim > hid ? dim : hid) * 2);
+  const float* hidden = reinterpret_cast<const float*>(tp);
+  const float* scores = hidden + (size_t)L * hid;
+  const int nblocks = (int)((L + 63) / 64);
+  const float* mz = scores + (((size_t)L + 3) & ~(size_t)3) + (size_t)nblocks * (4 + dim);
+  char* p = static_cast<char*>(workspace);
+  uint32_t* amax = reinterpret_cast<uint32_t*>(p);                 p += 256;
+  float* dp_cdot = reinterpret_cast<float*>(p);                    p += align_up((size_t)(dim + 4) * 4);
+  float* dhid = reinterpret_cast<float*>(p);                       p += align_up((size_t)L * hid * 4);
+  __half* dhid16 = reinterpret_cast<__half*>(p);                   p += align_up((size_t)L * hid * 2);
+  __half* wT = reinterpret_cast<__half*>(p);                       p += align_up((size_t)hid * dim * 2);
+  __half* dz16 = reinterpret_cast<__half*>(p);
+  StageScope s_(kStOther, st, 10);
+  RRT_CUDA(cudaMemsetAsync(amax, 0, 256, st), "zero amax");
+  RRT_CUDA(cudaMemsetAsync(dw2, 0, (size_t)hid * 4, st), "zero dw2");
+  if (db2) RRT_CUDA(cudaMemsetAsync(db2, 0, 4, st), "zero db2");
+  if (db1) RRT_CUDA(cudaMemsetAsync(db1, 0, (size_t)hid * 4, st), "zero db1");
+  RRT_CUDA(rrt::launch_pool_bwd_head(dlogits, pred_w, pooled, n_classes, dim, dp_cdot, dpred_w, dpred_b, st),
+           "pool backward (head)");
+  int a;
+  int rc = act_code(act, &a);
+  if (rc) return rc;
+  RRT_CUDA(rrt::launch_pool_bwd_rows(h, hidden, scores, mz, dp_cdot, w2, a, dh, dhid, dw2, db2, amax, (int)L, dim,
+                                     hid, st), "pool backward (rows)");
+  rrt::Grid ident{};
+  ident.L = (int)L; ident.Np = (int)L;
+  RRT_CUDA(rrt::launch_grad_partition(dhid, ident, (int)L, hid, amax, dhid16, nullptr, db1, st), "dhid rows");
+  // score-MLP first layer: dh += dhid W1 (dgrad), dW1 = dhid^T h (wgrad, both operands MN-major)
+  rrt::GemmEpilogue e;
+  RRT_CUDA(rrt::launch_wt_convert(w1, wT, hid, dim, st), "w1 transpose");
+  RRT_CUDA(rrt::launch_gemm_tcgen05(dhid16, wT, dz16, true, (int)L, dim, hid, e, st), "pool dgrad");
+  RRT_CUDA(rrt::launch_add_scaled_f16(dh, dz16, (size_t)L * dim, amax, st), "pool dh accumulate");
+  RRT_CUDA(cudaMemsetAsync(dw1, 0, (size_t)hid * dim * 4, st), "zero dw1");
+  RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad(dhid16, h16, dw1, (int)L, hid, dim, st), "pool wgrad");
+  RRT_CUDA(rrt::launch_scale_by_inv(dw1, (size_t)hid * dim, amax, st), "pool wgrad unscale");
   return RRT_OK;
 }
 

@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(256) grad_tile_kernel(const void* __restrict__
                                                         __half* __restrict__ outT,
                                                         float* __restrict__ colsum,
                                                         const uint32_t* __restrict__ amax, Grid grid,
-                                                        int M, int M64, int C, Dropout drop) {
+                                                        int M, int M64, int C, Dropout drop,
+                                                        const float* __restrict__ mask_src, float mask_scale) {
   __shared__ __align__(16) __half tile[kTileR * kLdt];
   __shared__ float red[8][kTileC];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -55,6 +56,11 @@ __global__ void __launch_bounds__(256) grad_tile_kernel(const void* __restrict__
           if (drop.on()) {
             const float4 m = dropout_scale4(drop, (unsigned long long)t * C + c0 + 4 * lane);
             v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+          }
+          if (IN_F32 && mask_src) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mask_src + (size_t)t * C + c0) + lane);
+            v.x = m.x != 0.f ? v.x * mask_scale : 0.f; v.y = m.y != 0.f ? v.y * mask_scale : 0.f;
+            v.z = m.z != 0.f ? v.z * mask_scale : 0.f; v.w = m.w != 0.f ? v.w * mask_scale : 0.f;
           }
         }
       } else {
@@ -232,11 +238,12 @@ cudaError_t launch_amax(const float* x, size_t n, uint32_t* amax, cudaStream_t s
 
 cudaError_t launch_grad_partition(const float* g, const Grid& grid, int M, int C, const uint32_t* amax,
                                   __half* rows, __half* rowsT, float* colsum, cudaStream_t stream,
-                                  const Dropout& drop) {
+                                  const Dropout& drop, const float* mask_src, float mask_scale) {
   if (C % kTileC || M <= 0) return cudaErrorInvalidValue;
   const int M64 = (M + 63) / 64 * 64;
   dim3 gr(M64 / kTileR, C / kTileC);
-  grad_tile_kernel<true><<<gr, 256, 0, stream>>>(g, rows, rowsT, colsum, amax, grid, M, M64, C, drop);
+  grad_tile_kernel<true><<<gr, 256, 0, stream>>>(g, rows, rowsT, colsum, amax, grid, M, M64, C, drop, mask_src,
+                                                 mask_scale);
   return cudaGetLastError();
 }
 
@@ -277,7 +284,8 @@ cudaError_t launch_transpose_f16(const __half* in, int M, int C, __half* outT, f
   const int M64 = (M + 63) / 64 * 64;
   dim3 gr(M64 / kTileR, C / kTileC);
   Grid none{};
-  grad_tile_kernel<false><<<gr, 256, 0, stream>>>(in, nullptr, outT, colsum, amax, none, M, M64, C, Dropout{});
+  grad_tile_kernel<false><<<gr, 256, 0, stream>>>(in, nullptr, outT, colsum, amax, none, M, M64, C, Dropout{},
+                                                  nullptr, 1.f);
   return cudaGetLastError();
 }
 

@@ -142,6 +142,16 @@ cudaError_t launch_attn_pool(const float* h, const float* hidden, const float* w
                              float* pooled, float* logits, float* attn, int attn_raw, int L, int D,
                              int hid, cudaStream_t stream);
 
+// backward of the pooling head (mil_head.cu): dp_cdot = dpooled[D] | pooled . dpooled
+cudaError_t launch_pool_bwd_head(const float* dlogits, const float* pred_w, const float* pooled, int n_classes,
+                                 int D, float* dp_cdot, float* dpred_w, float* dpred_b, cudaStream_t stream);
+cudaError_t launch_pool_bwd_rows(const float* h, const float* hidden, const float* scores, const float* mz,
+                                 const float* dp_cdot, const float* w2, int act, float* dh, float* dhid,
+                                 float* dw2, float* db2, uint32_t* amax, int L, int D, int hid,
+                                 cudaStream_t stream);
+cudaError_t launch_add_scaled_f16(float* dh, const __half* dz, size_t n, const uint32_t* amax,
+                                  cudaStream_t stream);
+
 // ---- backward pass (backward.cu, rmsa_attn_bwd.cu, crmsa_bwd.cu; conventions in backward.cuh) ----
 // amax words: IEEE bits of max|g| of a stage's fp32 input gradient (zero-initialised, atomicMax);
 // consumers derive the power-of-two fp16 scale S from them.
@@ -149,9 +159,12 @@ cudaError_t launch_amax(const float* x, size_t n, uint32_t* amax, cudaStream_t s
 // g: fp32 [grid.L, C] token order -> rows: fp16 [M, C] slot order, * S(amax), pad slots 0 (grid.H == 0:
 // identity, M == grid.L); rowsT: fp16 [C, M64] transpose; colsum[c] += sum of the unscaled column
 // drop.on(): g is the gradient wrt the OUTPUT of a dropout; it is multiplied by the forward's mask first
+// mask_src (nullable, [grid.L, C]): g is multiplied by mask_scale where mask_src != 0 and by 0 elsewhere (the
+// backward of ReLU followed by dropout, read off the layer's OUTPUT: out != 0 <=> pre-activation > 0 and kept)
 cudaError_t launch_grad_partition(const float* g, const Grid& grid, int M, int C, const uint32_t* amax,
                                   __half* rows, __half* rowsT, float* colsum, cudaStream_t stream,
-                                  const Dropout& drop = Dropout{});
+                                  const Dropout& drop = Dropout{}, const float* mask_src = nullptr,
+                                  float mask_scale = 1.f);
 // x[i] *= mask(i) / (1-p) in place, x fp32 [rows, C] (the landmark projection output in training mode)
 cudaError_t launch_dropout_inplace(float* x, size_t n, const Dropout& drop, cudaStream_t stream);
 // mask(i)/(1-p) of n elements as fp32 (parity tests: the oracle consumes the same mask)

@@ -160,3 +160,185 @@ cudaError_t launch_attn_pool(const float* h, const float* hidden, const float* w
 }
 
 }  // namespace rrt
+
+// ================================================================================================
+// Backward of the pooling head (the RRTMIL train step).  Autograd of
+// modules/datten.py:28-38 + modules/rrt.py:241:
+//   logits = pooled Wp^T + bp,  pooled = sum_l a_l h_l,  a = softmax_L(s),  s_l = hid_l . w2 + b2,
+//   hid = act(h W1^T + b1)
+//   dpooled = Wp^T dlogits;  dWp = dlogits (x) pooled;  dbp = dlogits
+//   da_l = a_l (h_l . dpooled - pooled . dpooled);  dh_l = a_l dpooled  (+ the path through the score MLP)
+//   dw2 = sum_l da_l hid_l;  db2 = sum_l da_l;  dhid_l = da_l w2 * act'(hid_l)
+// and dW1 / db1 / the MLP part of dh come from the shared linear-layer backward (tcgen05 GEMMs).
+namespace rrt {
+namespace {
+
+// one block: dpooled[D] | cdot (= pooled . dpooled) into `out`; dpred_w, dpred_b
+__global__ void __launch_bounds__(512) pool_bwd_head_kernel(const float* __restrict__ dlogits,
+                                                            const float* __restrict__ pred_w,
+                                                            const float* __restrict__ pooled,
+                                                            int n_classes, int D, float* __restrict__ out,
+                                                            float* __restrict__ dpred_w,
+                                                            float* __restrict__ dpred_b) {
+  __shared__ float red[16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float dot = 0.f;
+  for (int c = tid; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    const float pc = __ldg(pooled + c);
+    for (int j = 0; j < n_classes; ++j) {
+      const float g = __ldg(dlogits + j);
+      acc = fmaf(g, __ldg(pred_w + (size_t)j * D + c), acc);
+      dpred_w[(size_t)j * D + c] = g * pc;
+    }
+    out[c] = acc;
+    dot = fmaf(acc, pc, dot);
+  }
+  if (dpred_b)
+    for (int j = tid; j < n_classes; j += blockDim.x) dpred_b[j] = __ldg(dlogits + j);
+  dot = warp_sum(dot);
+  if (lane == 0) red[warp] = dot;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    out[D] = s;
+  }
+}
+
+// warp per token (grid-stride).  V = D / 128; hid <= 128 * HV.  act: kActRelu | kActTanh | kActNone
+template <int V, int HV>
+__global__ void __launch_bounds__(256) pool_bwd_rows_kernel(
+    const float* __restrict__ h, const float* __restrict__ hidden, const float* __restrict__ scores,
+    const float* __restrict__ mz, const float* __restrict__ dp_cdot, const float* __restrict__ w2, int act,
+    float* __restrict__ dh, float* __restrict__ dhid, float* __restrict__ dw2, float* __restrict__ db2,
+    uint32_t* __restrict__ amax, int L, int hid) {
+  constexpr int D = 128 * V;
+  __shared__ float s_dw2[128 * HV];
+  __shared__ float s_db2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpb = blockDim.x >> 5;
+  for (int i = tid; i < hid; i += blockDim.x) s_dw2[i] = 0.f;
+  if (tid == 0) s_db2 = 0.f;
+  __syncthreads();
+  float4 dp[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) dp[i] = __ldg(reinterpret_cast<const float4*>(dp_cdot) + lane + 32 * i);
+  const float cdot = __ldg(dp_cdot + D), M = __ldg(mz), invZ = 1.f / __ldg(mz + 1);
+  float w2r[HV * 4], acc_dw2[HV * 4];
+#pragma unroll
+  for (int j = 0; j < HV * 4; ++j) {
+    const int c = 4 * lane + 128 * (j / 4) + (j & 3);
+    w2r[j] = c < hid ? __ldg(w2 + c) : 0.f;
+    acc_dw2[j] = 0.f;
+  }
+  float acc_db2 = 0.f, amx = 0.f;
+  for (int l = blockIdx.x * wpb + warp; l < L; l += gridDim.x * wpb) {
+    const float4* hrow = reinterpret_cast<const float4*>(h + (size_t)l * D);
+    float4 hv[V];
+    float ds = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      hv[i] = __ldg(hrow + lane + 32 * i);
+      ds += hv[i].x * dp[i].x + hv[i].y * dp[i].y + hv[i].z * dp[i].z + hv[i].w * dp[i].w;
+    }
+    ds = warp_sum(ds);
+    const float a = __expf(__ldg(scores + l) - M) * invZ;
+    const float da = a * (ds - cdot);
+    float4* drow = reinterpret_cast<float4*>(dh + (size_t)l * D);
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      drow[lane + 32 * i] = make_float4(a * dp[i].x, a * dp[i].y, a * dp[i].z, a * dp[i].w);
+    acc_db2 += da;   // identical on every lane
+#pragma unroll
+    for (int q = 0; q < HV; ++q) {
+      const int c = 4 * lane + 128 * q;
+      if (c < hid) {
+        const float4 hd = __ldg(reinterpret_cast<const float4*>(hidden + (size_t)l * hid + c));
+        const float hv4[4] = {hd.x, hd.y, hd.z, hd.w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc_dw2[4 * q + e] = fmaf(da, hv4[e], acc_dw2[4 * q + e]);
+          const float d = act == kActRelu ? (hv4[e] > 0.f ? 1.f : 0.f)
+                                          : (act == kActTanh ? 1.f - hv4[e] * hv4[e] : 1.f);
+          o[e] = da * w2r[4 * q + e] * d;
+          amx = fmaxf(amx, fabsf(o[e]));
+        }
+        *reinterpret_cast<float4*>(dhid + (size_t)l * hid + c) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < HV * 4; ++j) {
+    const int c = 4 * lane + 128 * (j / 4) + (j & 3);
+    if (c < hid && acc_dw2[j] != 0.f) atomicAdd(&s_dw2[c], acc_dw2[j]);
+  }
+  if (lane == 0 && acc_db2 != 0.f) atomicAdd(&s_db2, acc_db2);
+  amx = warp_max(amx);
+  if (lane == 0 && amx > 0.f) atomicMax(amax, __float_as_uint(amx));
+  __syncthreads();
+  for (int i = tid; i < hid; i += blockDim.x)
+    if (s_dw2[i] != 0.f) atomicAdd(dw2 + i, s_dw2[i]);
+  if (tid == 0 && db2 && s_db2 != 0.f) atomicAdd(db2, s_db2);
+}
+
+// dh[i] += inv_scale(amax) * dz16[i]
+__global__ void __launch_bounds__(256) add_scaled_f16_kernel(float* __restrict__ dh, const __half* __restrict__ dz,
+                                                             size_t n4, const uint32_t* __restrict__ amax) {
+  const uint32_t ab = __ldg(amax);
+  uint32_t eb = (ab & 0x7fffffffu) >> 23;
+  eb = (eb == 0u || eb >= 255u) ? 135u : (eb < 20u ? 20u : (eb > 240u ? 240u : eb));
+  const float inv = __uint_as_float((eb - 8u) << 23);   // == grad_inv_scale (backward.cuh)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(dh)[i];
+    const float4 b = unpack_h4(__ldg(reinterpret_cast<const uint2*>(dz) + i));
+    a.x = fmaf(inv, b.x, a.x); a.y = fmaf(inv, b.y, a.y); a.z = fmaf(inv, b.z, a.z); a.w = fmaf(inv, b.w, a.w);
+    reinterpret_cast<float4*>(dh)[i] = a;
+  }
+}
+}  // namespace
+
+cudaError_t launch_pool_bwd_head(const float* dlogits, const float* pred_w, const float* pooled, int n_classes,
+                                 int D, float* dp_cdot, float* dpred_w, float* dpred_b, cudaStream_t stream) {
+  pool_bwd_head_kernel<<<1, 512, 0, stream>>>(dlogits, pred_w, pooled, n_classes, D, dp_cdot, dpred_w, dpred_b);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pool_bwd_rows(const float* h, const float* hidden, const float* scores, const float* mz,
+                                 const float* dp_cdot, const float* w2, int act, float* dh, float* dhid,
+                                 float* dw2, float* db2, uint32_t* amax, int L, int D, int hid,
+                                 cudaStream_t stream) {
+  if (D % 128 || D > 1024 || hid % 4 || hid > 256) return cudaErrorInvalidValue;
+  int blocks = (L + 7) / 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+#define RRT_PB(VV)                                                                                          \
+  {                                                                                                         \
+    if (hid <= 128)                                                                                         \
+      pool_bwd_rows_kernel<VV, 1><<<blocks, 256, 0, stream>>>(h, hidden, scores, mz, dp_cdot, w2, act, dh,  \
+                                                              dhid, dw2, db2, amax, L, hid);                \
+    else                                                                                                    \
+      pool_bwd_rows_kernel<VV, 2><<<blocks, 256, 0, stream>>>(h, hidden, scores, mz, dp_cdot, w2, act, dh,  \
+                                                              dhid, dw2, db2, amax, L, hid);                \
+  }
+  switch (D / 128) {
+    case 1: RRT_PB(1) break;
+    case 2: RRT_PB(2) break;
+    case 4: RRT_PB(4) break;
+    case 8: RRT_PB(8) break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef RRT_PB
+  return cudaGetLastError();
+}
+
+cudaError_t launch_add_scaled_f16(float* dh, const __half* dz, size_t n, const uint32_t* amax,
+                                  cudaStream_t stream) {
+  if (n % 4) return cudaErrorInvalidValue;
+  if (n == 0) return cudaSuccess;
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  add_scaled_f16_kernel<<<blocks, 256, 0, stream>>>(dh, dz, n / 4, amax);
+  return cudaGetLastError();
+}
+
+}  // namespace rrt

@@ -16,7 +16,8 @@ namespace rrt {
 long long* g_attn_trace = nullptr;  // debug: clock64 stamps of CTA 0..7 (tools/attn_trace.py)
 namespace {
 __device__ __forceinline__ void astamp(long long* tr, int slot) {
-  if (tr && blockIdx.x < 8 && blockIdx.y == 0 && threadIdx.x == 0) tr[blockIdx.x * 8 + slot] = clock64();
+  if (tr && blockIdx.x + blockIdx.y < 8 && (blockIdx.x == 0 || blockIdx.y == 0) && threadIdx.x == 0)
+    tr[(blockIdx.x + blockIdx.y) * 8 + slot] = clock64();
 }
 
 // HD: head dim; NT: 8-key n-tiles per KV tile (6 -> 48 keys, 8 -> 64 keys); MAXW: warps per CTA cap
@@ -26,7 +27,7 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
                                                                   __half* __restrict__ o, Grid grid,
                                                                   int D, int epeg_k, float qscale,
                                                                   int n_kv_tiles, int q_rows,
-                                                                  long long* tr) {
+                                                                  long long* tr, int heads_fastest) {
   constexpr int LDH = HD + 8;   // halves per smem row: 16-byte row skew keeps ldmatrix conflict-free
   constexpr int KS = HD / 16;   // k16 steps over head_dim
   constexpr int ND = HD / 8;    // 8-wide n-tiles over head_dim
@@ -42,7 +43,9 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
   float* Ts = reinterpret_cast<float*>(Vs + (size_t)pk * LDH);  // [epeg_k]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int rho = blockIdx.x, h = blockIdx.y;
+  // heads fastest: the CTAs that run side by side read ADJACENT 128-byte segments of the same qkv rows
+  // (one DRAM page / L2 line neighbourhood) instead of the same segment of rows 144 * 3 KB apart
+  const int rho = heads_fastest ? blockIdx.y : blockIdx.x, h = heads_fastest ? blockIdx.x : blockIdx.y;
   astamp(tr, 0);
   const size_t ld = 3 * (size_t)D;
   const __half* base = qkv + (size_t)rho * P * ld + h * HD;
@@ -258,9 +261,13 @@ cudaError_t launch(const __half* qkv, const float* taps, __half* o, const Grid& 
   }
   const float kLog2e = 1.4426950408889634f;
   float qscale = kLog2e / sqrtf((float)HD);
-  dim3 g(grid.R, heads);
+  // tuning knob RRT_ATTN_ORDER=region: regions fastest (the first version's order)
+  static const bool region_major = [] { const char* e = getenv("RRT_ATTN_ORDER"); return e && !strcmp(e, "region"); }();
+  const int heads_fastest = (!region_major && grid.R <= 65535) ? 1 : 0;
+  dim3 g = heads_fastest ? dim3(heads, grid.R) : dim3(grid.R, heads);
   rmsa_attn_f16_kernel<HD, NT, MAXW><<<g, 32 * W, smem, stream>>>(qkv, taps, o, grid, D, epeg_k,
-                                                                  qscale, tiles, q_rows, g_attn_trace);
+                                                                  qscale, tiles, q_rows, g_attn_trace,
+                                                                  heads_fastest);
   return cudaGetLastError();
 }
 

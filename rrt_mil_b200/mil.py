@@ -3,8 +3,11 @@
 SURVEY.md 8(f) rows f1 (pooling head) and f2 (patch_to_emb front end).
 
 Same constructor keywords, parameter tree and ``state_dict`` keys as the reference, so reference
-checkpoints load with ``strict=True``.  Inference only (eval mode), like the encoder; options the
-kernels do not cover raise.
+checkpoints load with ``strict=True``.  Eval mode / ``torch.no_grad()`` run the inference kernels; grad
+mode or ``.train()`` run the training path: ``patch_to_emb`` + ``dp`` dropout, the taped
+encoder and the pooling head each behind a ``torch.autograd.Function`` whose backward is CUDA
+(``rrt_patch_embed_backward``, ``rrt_encoder_backward``, ``rrt_attn_pool_backward``), so
+``loss.backward()`` fills the gradient of every parameter.  Options the kernels do not cover raise.
 """
 from __future__ import annotations
 
@@ -48,6 +51,97 @@ class DAttention(nn.Module):
         self.attention = Attention(input_dim, act, bias, dropout)
 
 
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+class _PatchEmbedFunction(torch.autograd.Function):
+    """h0 = dp(act(x W^T + b)) (modules/rrt.py:228-229); no gradient for the bag's features."""
+
+    @staticmethod
+    def forward(ctx, mil, bag, weight, bias):
+        lib, dev = cabi.lib(), bag.device
+        L, in_dim = bag.shape
+        dim = weight.shape[0]
+        drop_p, seed = mil._train_dropout()
+        with torch.cuda.device(dev):
+            n = C.c_size_t()
+            cabi.check(lib.rrt_mil_head_workspace_bytes(L, max(in_dim, dim), dim, 128, C.byref(n)), "workspace")
+            tape = torch.empty(n.value, dtype=torch.uint8, device=dev)
+            out = torch.empty(L, dim, device=dev)
+            cabi.check(lib.rrt_patch_embed_forward(bag.data_ptr(), L, in_dim, dim, weight.data_ptr(),
+                                                   RRTMIL._p(bias), None, mil._fc_act, out.data_ptr(),
+                                                   tape.data_ptr(), n.value, drop_p, seed, _stream(dev)),
+                       "rrt_patch_embed_forward")
+        ctx.mil, ctx.drop, ctx.shape = mil, (drop_p, seed), (L, in_dim, dim)
+        ctx.save_for_backward(out, tape, weight, bias)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        out, tape, weight, bias = ctx.saved_tensors
+        lib, dev = cabi.lib(), out.device
+        L, in_dim, dim = ctx.shape
+        dout = dout.contiguous().float()
+        with torch.cuda.device(dev):
+            dw = torch.empty_like(weight)
+            db = torch.empty_like(bias) if bias is not None else None
+            nws = 512 + L * dim * 2 + 256
+            ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+            cabi.check(lib.rrt_patch_embed_backward(dout.data_ptr(), out.data_ptr(), L, in_dim, dim,
+                                                    ctx.mil._fc_act, ctx.drop[0], ctx.drop[1], tape.data_ptr(),
+                                                    tape.numel(), dw.data_ptr(), RRTMIL._p(db), ws.data_ptr(),
+                                                    nws, _stream(dev)), "rrt_patch_embed_backward")
+        return None, None, dw, db
+
+
+class _AttnPoolFunction(torch.autograd.Function):
+    """logits = predictor(DAttention(h)) (modules/datten.py:28-38, modules/rrt.py:241)."""
+
+    @staticmethod
+    def forward(ctx, mil, h, w1, b1, w2, b2, pw, pb):
+        lib, dev = cabi.lib(), h.device
+        L, dim = h.shape
+        hid, ncls = w1.shape[0], pw.shape[0]
+        with torch.cuda.device(dev):
+            n = C.c_size_t()
+            cabi.check(lib.rrt_mil_head_workspace_bytes(L, dim, dim, hid, C.byref(n)), "workspace")
+            tape = torch.empty(n.value, dtype=torch.uint8, device=dev)
+            pooled, logits = torch.empty(dim, device=dev), torch.empty(ncls, device=dev)
+            cabi.check(lib.rrt_attn_pool_forward(h.data_ptr(), L, dim, hid, w1.data_ptr(), RRTMIL._p(b1), None,
+                                                 mil.pool_fn.attention.act_code, w2.data_ptr(), RRTMIL._p(b2),
+                                                 pw.data_ptr(), RRTMIL._p(pb), ncls, pooled.data_ptr(),
+                                                 logits.data_ptr(), None, 0, tape.data_ptr(), n.value,
+                                                 _stream(dev)), "rrt_attn_pool_forward")
+        ctx.mil = mil
+        ctx.save_for_backward(h, tape, pooled, w1, b1, w2, b2, pw, pb)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        h, tape, pooled, w1, b1, w2, b2, pw, pb = ctx.saved_tensors
+        lib, dev = cabi.lib(), h.device
+        L, dim = h.shape
+        hid, ncls = w1.shape[0], pw.shape[0]
+        dlogits = dlogits.contiguous().float()
+        with torch.cuda.device(dev):
+            n = C.c_size_t()
+            cabi.check(lib.rrt_mil_head_backward_workspace_bytes(L, dim, hid, C.byref(n)), "workspace")
+            ws = torch.empty(n.value, dtype=torch.uint8, device=dev)
+            dh = torch.empty_like(h)
+            dw1, dw2, dpw = torch.empty_like(w1), torch.empty_like(w2), torch.empty_like(pw)
+            db1 = torch.empty_like(b1) if b1 is not None else None
+            db2 = torch.empty_like(b2) if b2 is not None else None
+            dpb = torch.empty_like(pb) if pb is not None else None
+            cabi.check(lib.rrt_attn_pool_backward(h.data_ptr(), L, dim, hid, w1.data_ptr(),
+                                                  ctx.mil.pool_fn.attention.act_code, w2.data_ptr(), pw.data_ptr(),
+                                                  ncls, pooled.data_ptr(), dlogits.data_ptr(), tape.data_ptr(),
+                                                  tape.numel(), dh.data_ptr(), dw1.data_ptr(), RRTMIL._p(db1),
+                                                  dw2.data_ptr(), RRTMIL._p(db2), dpw.data_ptr(), RRTMIL._p(dpb),
+                                                  ws.data_ptr(), n.value, _stream(dev)), "rrt_attn_pool_backward")
+        return None, dh, dw1, db1, dw2, db2, dpw, dpb
+
+
 class RRTMIL(nn.Module):
     def __init__(self, input_dim=1024, mlp_dim=512, act='relu', n_classes=2, dropout=0.25, pos_pos=0,
                  pos='none', peg_k=7, attn='rmsa', pool='attn', region_num=8, n_layers=2, n_heads=8,
@@ -77,6 +171,8 @@ class RRTMIL(nn.Module):
         self.predictor = nn.Linear(self.online_encoder.final_dim, n_classes)
         self.apply(initialize_weights)
         self._shadow = {}
+        self.dropout_p = float(dropout)
+        self._dropout_seed = None   # tests: pin the dp seed (the encoder has its own ``_dropout_seed``)
 
     # ------------------------------------------------------------------------------------------
     def _f16(self, param):
@@ -95,6 +191,32 @@ class RRTMIL(nn.Module):
     def _p(t):
         return None if t is None else t.data_ptr()
 
+    def _train_dropout(self):
+        """(p, seed) of ``dp`` for this forward; active in training mode only."""
+        if not self.training or self.dropout_p <= 0.0:
+            return 0.0, 0
+        seed = self._dropout_seed
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        return self.dropout_p, seed
+
+    def _forward_train(self, bag):
+        """Autograd / training path: three CUDA-backed autograd Functions in a row."""
+        fc, att, pred = self.patch_to_emb[0], self.pool_fn.attention, self.predictor
+        a0, a2 = att.attention[0], att.attention[-1]
+        if self._fc_act == cabi.RRT_ACT_GELU or att.act_code == cabi.RRT_ACT_GELU:
+            raise NotImplementedError("training through act='gelu' / da_act='gelu' is not built "
+                                      "(the backward would need the pre-activations)")
+        if self.training and any(isinstance(m, nn.Dropout) for m in att.attention):
+            raise NotImplementedError("da_dropout=True is not built for training")
+        if fc.out_features % 128 or a0.out_features % 128:
+            raise NotImplementedError("training needs 128-aligned layer widths")
+        h0 = _PatchEmbedFunction.apply(self, bag, fc.weight, fc.bias)
+        h1 = self.online_encoder.forward_bag(h0)
+        logits = _AttnPoolFunction.apply(self, h1, a0.weight, a0.bias, a2.weight.view(-1), a2.bias, pred.weight,
+                                         pred.bias)
+        return logits.unsqueeze(0)
+
     def forward(self, x, return_attn=False, no_norm=False):
         if x.dim() == 2:
             x = x.unsqueeze(0)
@@ -102,11 +224,12 @@ class RRTMIL(nn.Module):
             raise ValueError("RRTMIL processes one bag [1, N, input_dim] per call")
         if not x.is_cuda or x.dtype != torch.float32:
             raise RuntimeError("RRTMIL (rrt_mil_b200) needs float32 CUDA input; there is no CPU fallback")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("backward kernels are not built yet: call under torch.no_grad()")
-        if self.training:
-            raise NotImplementedError("training-mode dropout is not built: use .eval()")
         bag = x[0].contiguous()
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad or self.training:
+            if return_attn:
+                raise NotImplementedError("return_attn is an inference option")
+            return self._forward_train(bag)
         L, in_dim = bag.shape
         dev = bag.device
         lib = cabi.lib()
@@ -121,7 +244,7 @@ class RRTMIL(nn.Module):
             h0 = torch.empty(L, dim, device=dev)
             cabi.check(lib.rrt_patch_embed_forward(bag.data_ptr(), L, in_dim, dim, fc.weight.data_ptr(),
                                                    self._p(fc.bias), self._f16(fc.weight), self._fc_act,
-                                                   h0.data_ptr(), ws.data_ptr(), n.value, st),
+                                                   h0.data_ptr(), ws.data_ptr(), n.value, 0.0, 0, st),
                        "rrt_patch_embed_forward")
             h1 = self.online_encoder.forward_bag(h0)
             pooled = torch.empty(dim, device=dev)
