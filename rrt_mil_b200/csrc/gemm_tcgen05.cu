@@ -756,7 +756,11 @@ cudaError_t launch_cfg(const __half* a, const __half* w, const Tc05Params& p, cu
   // every CTA pipelines 7 tiles instead of 3 (prologue and last epilogue amortised).  Measured, 16 bags,
   // 4 lanes: 71.2 us/bag on 148 SMs, 70.6 / 69.8 / 69.4 / 68.4 on 132 / 111 / 96 / 74, 67.7 on 64 and 56.
   static const int env_cap = [] { const char* e = getenv("RRT_GEMM_SMS"); return e ? atoi(e) : -1; }();
-  const int sm_cap = env_cap >= 0 ? env_cap : g_gemm_sm_cap;
+  // (RRT_GEMM_SMS_RESID: separate tuning knob for the residual-epilogue (proj) GEMM)
+  static const int env_cap_resid = [] { const char* e = getenv("RRT_GEMM_SMS_RESID"); return e ? atoi(e) : -1; }();
+  const int sm_cap = (is_resid_mode(MODE) && env_cap_resid >= 0 && g_gemm_sm_cap > 0)
+                         ? env_cap_resid
+                         : (env_cap >= 0 ? env_cap : g_gemm_sm_cap);
   if (sm_cap > 0 && BN == 256 && clusters > sm_cap / CSIZE) clusters = sm_cap / CSIZE > 0 ? sm_cap / CSIZE : 1;
   if (ctiles < clusters) clusters = ctiles;
   cudaLaunchConfig_t cfg{};
