@@ -57,6 +57,12 @@ class Adam(torch.optim.Optimizer):
                                            group["eps"], group["weight_decay"], int(group["decoupled"]), step,
                                            float(grad_scale), torch.cuda.current_stream(dev).cuda_stream)
                 cabi.check(rc, "rrt_adam_step")
+                # the kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed
+                # on the version counter, e.g. the encoder's fp16 weight shadows) that they changed
+                for p, _, st in items:
+                    torch.autograd.graph.increment_version(p)
+                    torch.autograd.graph.increment_version(st["exp_avg"])
+                    torch.autograd.graph.increment_version(st["exp_avg_sq"])
         return loss
 
 

@@ -71,3 +71,25 @@ def test_encoder_training_loop_reduces_the_loss():
     # bound the worst case by the distance 8 steps of size lr can cover
     d = (p1 - p2).abs()
     assert float(d.mean()) < 1e-5 and float(d.max()) <= 2 * 8 * 2e-4
+
+
+def test_eval_after_fused_adam_uses_the_updated_weights():
+    """The fused step writes parameters through raw pointers; the eval-mode fp16 weight shadows (cached by
+    storage + version counter) must notice: eval output after training == a fresh module with the same state."""
+    cfg = O.EncoderConfig()
+    m = G.make_encoder(cfg, O.make_weights(cfg, 3))
+    x = O.make_bag(500, 512, 4).float().cuda()
+    with torch.no_grad():
+        y_before = m(x)                     # builds the shadows
+    m.train()
+    opt = Adam(m.parameters(), lr=1e-2)
+    v0 = m.norm.weight._version
+    m(x).square().mean().backward()
+    opt.step()
+    assert m.norm.weight._version > v0
+    m.eval()
+    fresh = RRTEncoder(**cfg.to_dict()).cuda().eval()
+    fresh.load_state_dict(m.state_dict(), strict=True)
+    with torch.no_grad():
+        y_after, y_fresh = m(x), fresh(x)
+    assert torch.equal(y_after, y_fresh) and not torch.equal(y_after, y_before)
