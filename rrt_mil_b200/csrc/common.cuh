@@ -47,6 +47,36 @@ inline void prefer_max_shared(K kernel) {
   prefer_max_shared_impl(reinterpret_cast<const void*>(kernel));
 }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------
+// The kernels of one bag form a strict chain on one stream; between two of them the GPU otherwise idles for
+// the grid-launch latency plus the next kernel's prologue (~2-3 us per boundary, ten boundaries per bag).
+// Every chain kernel therefore (1) signals `launch_dependents` on entry, so that the NEXT kernel's CTAs may be
+// scheduled as soon as all of this kernel's CTAs have started, and (2) executes `griddepcontrol.wait` before
+// its first access to global memory that a predecessor may have written or may still read.  `wait` returns
+// only when the predecessor grid has COMPLETED and flushed; since the predecessor itself waited for its own
+// predecessor, everything earlier in the stream is complete too, so all RAW / WAR / WAW orderings of plain
+// stream order are kept.  Both instructions are no-ops for a kernel launched without the attribute.
+// The attribute is only set while ONE bag runs at a time (g_pdl): with several bags in flight a pre-launched
+// CTA would sit on an SM (the GEMMs take a whole one) that another bag's kernels could be using.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+extern thread_local bool g_pdl;  // api.cu
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                       cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default (modules/rrt.py:47,139)
 #define RRT_MAX_K_DEV 16  // == RRT_MAX_CRMSA_K in include/rrt_b200.h
 

@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(256) crmsa_rowstats_kernel(
   float* Gt = smem;            // [KMAX][D]
   float* AB = Gt + KMAX * D;   // [2][KMAX]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wpb = blockDim.x >> 5;
-  if (phi) {
+  pdl_launch_dependents();
+  if (phi) {  // weights only: runs ahead of the predecessor's completion
     for (int n = warp; n < k; n += wpb) {
       float a = 0.f, b = 0.f;
       for (int c = lane; c < D; c += 32) {
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(256) crmsa_rowstats_kernel(
     }
     __syncthreads();
   }
+  pdl_wait();
   constexpr int U = 2;  // rows in flight per warp
   const int stride = gridDim.x * wpb * U;
   for (int s0 = (blockIdx.x * wpb + warp) * U; s0 < grid.Np; s0 += stride) {
@@ -328,6 +330,8 @@ __global__ void __launch_bounds__(256) crmsa_combine2_kernel(
   float* part = reinterpret_cast<float*>(tok + ((P + 3) & ~3));  // [8][KMAX][128]
   float* s01 = part + 8 * KMAX * 128;                        // [2][KMAX]: S0, S1
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
+  pdl_wait();
 
   for (int p = tid; p < P; p += 256) {
     int slot = rho * P + p;
@@ -747,6 +751,8 @@ __global__ void __launch_bounds__(256) crmsa_dispatch_kernel(
     const float2* __restrict__ rstat, const float* __restrict__ lm, const float* __restrict__ gamma,
     const float* __restrict__ beta, float* __restrict__ out, Grid grid, int k) {
   constexpr int D = 128 * V;
+  pdl_launch_dependents();
+  pdl_wait();
   int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (tok >= grid.L) return;
@@ -953,7 +959,9 @@ cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const 
       if (e != cudaSuccess) return e;                                                              \
     }                                                                                              \
     prefer_max_shared(crmsa_rowstats_kernel<VV, KK>);                                                      \
-    crmsa_rowstats_kernel<VV, KK><<<blocks, 256, smem, stream>>>(x1, gamma, beta, phi, stats, logits, grid, k); \
+    cudaError_t le = launch_chain_kernel(crmsa_rowstats_kernel<VV, KK>, dim3(blocks), dim3(256), smem, stream, x1, \
+                                         gamma, beta, phi, stats, logits, grid, k);                 \
+    if (le != cudaSuccess) return le;                                                              \
   }
 #define RRT_RS_K(VV) { if (KM == 4) RRT_RS(VV, 4) else if (KM == 8) RRT_RS(VV, 8) else RRT_RS(VV, 16) }
     switch (V) {
@@ -980,8 +988,9 @@ cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const 
       if (e != cudaSuccess) return e;                                                              \
     }                                                                                              \
     prefer_max_shared(crmsa_combine2_kernel<KK>);                                                  \
-    crmsa_combine2_kernel<KK><<<g, 256, smem, stream>>>(x1, gamma, beta, stats, logits, landmarks, \
-                                                        rstat, grid, D, k);                        \
+    cudaError_t le = launch_chain_kernel(crmsa_combine2_kernel<KK>, g, dim3(256), smem, stream, x1, gamma, beta, \
+                                         stats, logits, landmarks, rstat, grid, D, k);             \
+    if (le != cudaSuccess) return le;                                                              \
   }
     if (KM == 4) RRT_C2(4) else if (KM == 8) RRT_C2(8) else RRT_C2(16)
 #undef RRT_C2
@@ -1004,7 +1013,9 @@ cudaError_t launch_crmsa_dispatch(const float* x1, const float* x0, const float*
   if (D % 128 || k < 1 || k > RRT_MAX_K_DEV) return cudaErrorInvalidValue;
   if (grid.L == 0) return cudaSuccess;
   int blocks = (grid.L + 7) / 8;
-  RRT_DISPATCH_V(D, prefer_max_shared(crmsa_dispatch_kernel<V>); crmsa_dispatch_kernel<V><<<blocks, 256, 0, stream>>>(x1, x0, logits, rstat, lm, gamma, beta, out, grid, k));
+  RRT_DISPATCH_V(D, prefer_max_shared(crmsa_dispatch_kernel<V>);
+                 return launch_chain_kernel(crmsa_dispatch_kernel<V>, dim3(blocks), dim3(256), 0, stream, x1, x0,
+                                            logits, rstat, lm, gamma, beta, out, grid, k));
   return cudaGetLastError();
 }
 

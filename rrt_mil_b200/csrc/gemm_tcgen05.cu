@@ -312,6 +312,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) stamp(p, 0);
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) prefetch_tensormap(&tmA);
   if (warp == 3 && lane == 0) prefetch_tensormap(&tmB);
@@ -333,6 +334,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) stamp(p, 1);
+  // PDL (common.cuh): barriers, TMEM and descriptor prefetch above ran while the predecessor was finishing;
+  // nothing below may touch its output before it has completed
+  pdl_wait();
 
   // cluster-tile schedule: every CTA of a cluster walks the same list, so that the multicast
   // producers / consumers of the peers stay in lock step stage by stage
@@ -768,13 +772,21 @@ cudaError_t launch_cfg(const __half* a, const __half* w, const Tc05Params& p, cu
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CSIZE;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CSIZE > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CSIZE;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  } else if (g_pdl) {  // programmatic dependent launch of the serial chain (common.cuh)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CSIZE > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p);
 }
 

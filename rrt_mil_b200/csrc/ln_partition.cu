@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(256) ln_partition_kernel(const float* __restri
                                                            const float* __restrict__ beta,
                                                            __half* __restrict__ z, Grid grid) {
   const int D = 128 * V;
+  pdl_launch_dependents();
+  pdl_wait();
   int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (slot >= grid.Np) return;
@@ -97,7 +99,9 @@ cudaError_t launch_ln_partition(const float* x, const float* gamma, const float*
   if (D % 128) return cudaErrorInvalidValue;
   const int wpb = 8;
   int blocks = (grid.Np + wpb - 1) / wpb;
-  RRT_DISPATCH_V(D, prefer_max_shared(ln_partition_kernel<V>); ln_partition_kernel<V><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, z, grid));
+  RRT_DISPATCH_V(D, prefer_max_shared(ln_partition_kernel<V>);
+                 return launch_chain_kernel(ln_partition_kernel<V>, dim3(blocks), dim3(wpb * 32), 0, stream, x,
+                                            gamma, beta, z, grid));
   return cudaGetLastError();
 }
 

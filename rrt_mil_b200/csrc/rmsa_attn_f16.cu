@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(32 * MAXW) __maxnreg__(MAXW <= 9 ? 96 : 128) r
   float* Ts = reinterpret_cast<float*>(Vs + (size_t)pk * LDH);  // [epeg_k]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  pdl_launch_dependents();
+  pdl_wait();
   // heads fastest: the CTAs that run side by side read ADJACENT 128-byte segments of the same qkv rows
   // (one DRAM page / L2 line neighbourhood) instead of the same segment of rows 144 * 3 KB apart
   const int rho = heads_fastest ? blockIdx.y : blockIdx.x, h = heads_fastest ? blockIdx.x : blockIdx.y;
@@ -265,10 +267,8 @@ cudaError_t launch(const __half* qkv, const float* taps, __half* o, const Grid& 
   static const bool region_major = [] { const char* e = getenv("RRT_ATTN_ORDER"); return e && !strcmp(e, "region"); }();
   const int heads_fastest = (!region_major && grid.R <= 65535) ? 1 : 0;
   dim3 g = heads_fastest ? dim3(heads, grid.R) : dim3(grid.R, heads);
-  rmsa_attn_f16_kernel<HD, NT, MAXW><<<g, 32 * W, smem, stream>>>(qkv, taps, o, grid, D, epeg_k,
-                                                                  qscale, tiles, q_rows, g_attn_trace,
-                                                                  heads_fastest);
-  return cudaGetLastError();
+  return launch_chain_kernel(rmsa_attn_f16_kernel<HD, NT, MAXW>, g, dim3(32 * W), smem, stream, qkv, taps, o,
+                             grid, D, epeg_k, qscale, tiles, q_rows, g_attn_trace, heads_fastest);
 }
 
 template <int HD>
