@@ -1289,6 +1289,7 @@ RRT_API int rrt_encoder_forward_train(const rrt_config* cfg, const rrt_weights* 
   TrainOpts tr;
   tr.drop_p = drop_p;
   tr.seed = seed;
+  PdlScope pdl(!g_timing.load(std::memory_order_relaxed));
   return encoder_forward(cfg, w, x, out, L, ws, (cudaStream_t)stream, tr);
 }
 
