@@ -15,6 +15,7 @@
 
 namespace rrt {
 thread_local bool g_pdl = false;  // common.cuh: programmatic dependent launch of the serial kernel chain
+thread_local bool g_pdl_light = false;
 }
 
 namespace {
@@ -24,8 +25,10 @@ struct PdlScope {
   explicit PdlScope(bool on) {
     static const int mode = [] { const char* e = getenv("RRT_PDL"); return e ? atoi(e) : 1; }();  // 2: always
     rrt::g_pdl = mode == 2 || (on && mode == 1);
+    rrt::g_pdl_light = mode == 3 || (!on && mode == 1 && kLightWhenMany);
   }
-  ~PdlScope() { rrt::g_pdl = false; }
+  ~PdlScope() { rrt::g_pdl = false; rrt::g_pdl_light = false; }
+  static constexpr bool kLightWhenMany = false;
 };
 
 thread_local std::string g_last_error;

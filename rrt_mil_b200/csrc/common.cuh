@@ -60,7 +60,8 @@ inline void prefer_max_shared(K kernel) {
 // CTA would sit on an SM (the GEMMs take a whole one) that another bag's kernels could be using.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-extern thread_local bool g_pdl;  // api.cu
+extern thread_local bool g_pdl;       // api.cu: every chain kernel
+extern thread_local bool g_pdl_light;  // api.cu: the streaming / attention kernels only (not the whole-SM GEMMs)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_chain_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                        cudaStream_t stream, Args&&... args) {
@@ -73,7 +74,7 @@ inline cudaError_t launch_chain_kernel(void (*kernel)(KArgs...), dim3 grid, dim3
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = (g_pdl || g_pdl_light) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
