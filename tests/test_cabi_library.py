@@ -97,3 +97,23 @@ int main(void) {
             C.sizeof(cabi.RrtGrads), cabi.RrtConfig.min_region_ratio.offset, cabi.RrtConfig.pos.offset,
             cabi.RrtWeights.cr_attn.offset, cabi.RrtWeights.pos_w.offset, cabi.RrtGrads.cr_attn.offset]
     assert got == want
+
+
+def test_integration_md_stub_structs_match_the_header():
+    """The ctypes mirrors printed in INTEGRATION.md (what a reference maintainer would paste) must have the
+    layout of the library's structs -- a stale field list there would corrupt memory silently."""
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n# modules/rrt_b200_stub.py.*?```", text, re.S).group(0)
+    code = block[len("```python\n"):-3]
+    code = code.split("def rrt_forward_b200")[0]                      # the struct definitions only
+    code = code.replace('C.CDLL("librrt_b200.so")', "None").replace("import ctypes as C, torch", "import ctypes as C")
+    ns = {}
+    exec(code, ns)
+    assert C.sizeof(ns["_Cfg"]) == C.sizeof(cabi.RrtConfig)
+    assert C.sizeof(ns["_Attn"]) == C.sizeof(cabi.RrtAttnWeights)
+    assert C.sizeof(ns["_Ffn"]) == C.sizeof(cabi.RrtFfnWeights)
+    assert C.sizeof(ns["_W"]) == C.sizeof(cabi.RrtWeights)
+    assert [n for n, _ in ns["_Cfg"]._fields_] == [n for n, *_ in cabi.RrtConfig._fields_]
+    assert [n for n, _ in ns["_W"]._fields_] == [n for n, *_ in cabi.RrtWeights._fields_]
