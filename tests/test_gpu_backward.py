@@ -137,6 +137,7 @@ ENC_CASES = [
     ("three_layers", 2500, dict(region_num=16, n_layers=3, epeg_k=21, crmsa_k=5)),
     ("tiny", 50, dict()),
     ("n9000", 9000, dict()),
+    ("n50000_g16", 50000, dict(region_num=16)),     # BASELINE configs[3] shape: P = 196 (R-MSA), 784 (CR-MSA)
 ]
 
 
@@ -170,8 +171,18 @@ def test_encoder_backward_matches_oracle_autograd(name, L, over):
         errs[n] = rel(p.grad, ref)
     worst = max(errs, key=errs.get)
     print(name, "worst", worst, errs[worst], {k: f"{v:.1e}" for k, v in errs.items()})
+    # The reference's min-max dispatch normaliser sends d/dmin, d/dmax to the argmin / argmax token of each
+    # region, so its gradient wrt the CR-MSA logits JUMPS when two logits tie.  With 784 tokens per region
+    # (N = 50000) the two smallest / largest logits of some region always sit within 1e-4 of the range
+    # (crmsa_tie_gap; 2.3e-5 here), closer than the forward's fp16-operand rounding, so the parameters that
+    # feed the logits (phi, cr_msa.norm) and everything upstream of them cannot be held to the smooth-function
+    # bar; measured 1.1e-2 on phi, <= 2.7e-3 elsewhere.
+    from oracle.make_golden import crmsa_tie_gap
+    on_a_tie = name == "n50000_g16" and crmsa_tie_gap(x, w, cfg, (0.0, 0)) < 5e-5   # smaller cases: gap >= 5e-5, tight bar
     for n, e in errs.items():
-        assert e < TOL_GRAD, (n, e)
+        tol = 3e-2 if on_a_tie and (n.startswith("cr_msa.norm") or n == "cr_msa.attn.phi") else \
+            (2 * TOL_GRAD if on_a_tie else TOL_GRAD)
+        assert e < tol, (n, e)
 
 
 @pytest.mark.parametrize("rows,D,p,seed,stream", [(700, 512, 0.1, 20240229, 0), (192, 512, 0.1, 5, 64),
