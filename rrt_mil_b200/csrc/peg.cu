@@ -10,6 +10,8 @@
 //   peg_apply_kernel  one thread per (token, 4 channels): <= K*KW float4 loads of neighbours (L1/L2
 //                     resident: every token row is read K*KW times by adjacent threads) and of w_eff.
 // Token-major [L, D] in and out, channel fastest: every load and store is a coalesced 16-byte access.
+#include <cstdlib>
+#include <cstring>
 #include "kernels.cuh"
 
 namespace rrt {
@@ -83,6 +85,91 @@ __global__ void __launch_bounds__(256) peg_apply_kernel(const float* __restrict_
   }
 }
 
+// Tiled version: CTA = 8 x 16 output cells x 32 channels.  The (8+K-1) x (16+KW-1) halo of the tile (wrap /
+// zero rules applied while filling) and the 32-channel slab of the folded kernel are staged in shared
+// memory once (coalesced 128-byte cell rows); a thread owns one channel quad and a horizontal strip of 4
+// cells, so every tap is 4 LDS.128 of activations + 1 of weights for 16 FMAs.  Activations are read from
+// HBM / L2 (K+7)(KW+15)/128 times instead of K*KW times through L1.
+// CK / CKW > 0: compile-time kernel size -- the tap loops unroll and a thread keeps the CKW+3 cells of a halo
+// row in registers (sliding window: (CKW+3) + CKW loads per tap row instead of 5 CKW); 0: run-time sizes.
+constexpr int kTileH = 8, kTileW = 16, kSlab = 32;
+template <int CK, int CKW>
+__global__ void __launch_bounds__(256) peg_apply_tiled_kernel(const float* __restrict__ x,
+                                                              const float* __restrict__ weff,
+                                                              const float* __restrict__ beff,
+                                                              float* __restrict__ out, PegGeom g) {
+  extern __shared__ __align__(16) float sm[];
+  const int K = CK > 0 ? CK : g.K, KW = CK > 0 ? CKW : g.KW;
+  const int HH = kTileH + K - 1, HW = kTileW + KW - 1;
+  float4* sx = reinterpret_cast<float4*>(sm);                       // [HH][HW][8 quads]
+  float4* sw = sx + (size_t)HH * HW * (kSlab / 4);                   // [K*KW][8 quads]
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.z * kSlab;                                 // first channel of the slab
+  const int r0 = blockIdx.y * kTileH, col0 = blockIdx.x * kTileW;    // first output cell of the tile
+  const int py = K / 2, px = KW == 1 ? 0 : K / 2;
+  const int wrap_end = g.Hn * g.Hn;
+  for (int i = tid; i < HH * HW * (kSlab / 4); i += blockDim.x) {
+    const int q = i & 7, cell_i = i >> 3;
+    const int hy = cell_i / HW, hx = cell_i - hy * HW;
+    const int rr = r0 + hy - py, cc = col0 + hx - px;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rr >= 0 && rr < g.Hg && cc >= 0 && cc < g.Hg) {
+      const int cell = rr * g.Hg + cc;
+      const int src = cell < g.L ? cell : (cell < wrap_end ? cell - g.L : -1);
+      if (src >= 0) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)src * g.D + c0) + q);
+    }
+    sx[i] = v;
+  }
+  for (int i = tid; i < K * KW * (kSlab / 4); i += blockDim.x)
+    sw[i] = __ldg(reinterpret_cast<const float4*>(weff + (size_t)(i >> 3) * g.D + c0) + (i & 7));
+  __syncthreads();
+  const int q = tid & 7, strip = tid >> 3;          // 32 strips of 4 cells: 8 rows x 4 strips
+  const int ty = strip >> 2, tx = (strip & 3) * 4;
+  const float4 b = __ldg(reinterpret_cast<const float4*>(beff + c0) + q);
+  float4 acc[4] = {b, b, b, b};
+  if (CK > 0) {
+#pragma unroll
+    for (int ky = 0; ky < (CK > 0 ? CK : 1); ++ky) {
+      const float4* row = sx + ((size_t)(ty + ky) * HW + tx) * (kSlab / 4) + q;
+      float4 xin[(CKW > 0 ? CKW : 1) + 3];
+#pragma unroll
+      for (int i = 0; i < (CKW > 0 ? CKW : 1) + 3; ++i) xin[i] = row[(size_t)i * (kSlab / 4)];
+#pragma unroll
+      for (int kx = 0; kx < (CKW > 0 ? CKW : 1); ++kx) {
+        const float4 w = sw[(ky * KW + kx) * (kSlab / 4) + q];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = xin[kx + j];
+          acc[j].x = fmaf(v.x, w.x, acc[j].x); acc[j].y = fmaf(v.y, w.y, acc[j].y);
+          acc[j].z = fmaf(v.z, w.z, acc[j].z); acc[j].w = fmaf(v.w, w.w, acc[j].w);
+        }
+      }
+    }
+  } else {
+    for (int ky = 0; ky < K; ++ky) {
+      const float4* row = sx + ((size_t)(ty + ky) * HW + tx) * (kSlab / 4) + q;
+      for (int kx = 0; kx < KW; ++kx) {
+        const float4 w = sw[(ky * KW + kx) * (kSlab / 4) + q];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = row[(size_t)(kx + j) * (kSlab / 4)];
+          acc[j].x = fmaf(v.x, w.x, acc[j].x); acc[j].y = fmaf(v.y, w.y, acc[j].y);
+          acc[j].z = fmaf(v.z, w.z, acc[j].z); acc[j].w = fmaf(v.w, w.w, acc[j].w);
+        }
+      }
+    }
+  }
+  const int r = r0 + ty;
+  if (r < g.Hg) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = col0 + tx + j;
+      const long long t = (long long)r * g.Hg + c;
+      if (c < g.Hg && t < g.L) reinterpret_cast<float4*>(out + (size_t)t * g.D + c0)[q] = acc[j];
+    }
+  }
+}
+
 int ceil_sqrt_i(long long n) {
   long long r = (long long)floor(sqrt((double)n));
   while (r * r > n) --r;
@@ -115,6 +202,44 @@ cudaError_t launch_peg(const float* x, float* out, int L, int D, int peg_k, bool
                                                        D, g.K, g.KW);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  // tiled kernel when the channel count splits into 32-wide slabs and the halo tile fits shared memory;
+  // the direct kernel otherwise (RRT_PEG=direct forces it: tuning knob / cross-check)
+  const size_t smem = ((size_t)(kTileH + g.K - 1) * (kTileW + g.KW - 1) + (size_t)g.K * g.KW) * kSlab * sizeof(float);
+  static const bool direct = [] { const char* e = getenv("RRT_PEG"); return e && !strcmp(e, "direct"); }();
+  const int tiles = (g.Hg + kTileH - 1) / kTileH;
+  if (!direct && D % kSlab == 0 && smem <= 160 * 1024 && tiles <= 65535 && D / kSlab <= 65535) {
+    dim3 grid((g.Hg + kTileW - 1) / kTileW, tiles, D / kSlab);
+    auto run = [&](auto kern) -> cudaError_t {
+      // once per (kernel instantiation, device): cudaFuncSetAttribute costs ~25 us of host time.
+      // MaxShared carve-out: without it the driver keeps a small shared-memory split and ONE 46 KB CTA per SM
+      // (measured: 170 us instead of the direct kernel's 95)
+      static thread_local const void* seen[16];
+      static thread_local int seen_dev[16], n_seen = 0;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      bool done = false;
+      for (int i = 0; i < n_seen; ++i) done = done || (seen[i] == (const void*)kern && seen_dev[i] == dev);
+      if (!done) {
+        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (ce == cudaSuccess)
+          ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared);
+        if (ce != cudaSuccess) return ce;
+        if (n_seen < 16) { seen[n_seen] = (const void*)kern; seen_dev[n_seen] = dev; ++n_seen; }
+      }
+      kern<<<grid, 256, smem, stream>>>(x, weff, beff, out, g);
+      return cudaGetLastError();
+    };
+    const int key = g.K * 100 + g.KW;
+    switch (key) {
+      case 707: return run(peg_apply_tiled_kernel<7, 7>);
+      case 505: return run(peg_apply_tiled_kernel<5, 5>);
+      case 303: return run(peg_apply_tiled_kernel<3, 3>);
+      case 701: return run(peg_apply_tiled_kernel<7, 1>);
+      case 501: return run(peg_apply_tiled_kernel<5, 1>);
+      default: return run(peg_apply_tiled_kernel<0, 0>);
+    }
+  }
   long long items = (long long)L * (D / 4);
   long long blocks = (items + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
