@@ -83,6 +83,36 @@ def encode_bags_parallel(encoder, bags: Sequence[torch.Tensor], group=None, gath
     return gather_ragged(local_out, len(bags), group=group, dst=dst)
 
 
+@torch.no_grad()
+def classify_bags_parallel(model, bags: Sequence[torch.Tensor], group=None, dst: Optional[int] = None):
+    """BASELINE configs[2]: a pooling head follows the encoder, so only the ``[n_classes]`` logits of each bag
+    leave a GPU.  Every rank receives the same list of bags ``[N_i, C_in]``, runs ``model`` (e.g. ``RRTMIL``) on
+    its shard and ONE all-gather of ``ceil(n_bags / world) * n_classes`` floats returns the ``[n_bags, n_classes]``
+    logits in bag order on every rank (on ``dst`` only if given)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = shard_indices(len(bags), world, rank)
+    dev = next(model.parameters()).device
+    local = [model(bags[i].to(dev, non_blocking=True).unsqueeze(0)).reshape(-1) for i in mine]
+    per_rank = (len(bags) + world - 1) // world
+    ncls = torch.tensor([local[0].numel() if local else 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(ncls, op=dist.ReduceOp.MAX, group=group)      # ranks without a bag learn the width
+    ncls = int(ncls.item())
+    send = torch.zeros(per_rank, ncls, dtype=torch.float32, device=dev)
+    for j, t in enumerate(local):
+        send[j] = t.float()
+    recv = torch.empty(world * per_rank, ncls, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)           # the single payload collective
+    if dst is not None and rank != dst:
+        return None
+    recv = recv.view(world, per_rank, ncls)
+    out = torch.empty(len(bags), ncls, dtype=torch.float32, device=dev)
+    for r in range(world):
+        for j, i in enumerate(shard_indices(len(bags), world, r)):
+            out[i] = recv[r, j]
+    return out
+
+
 def allreduce_gradients(params, group=None, bucket_bytes: int = 32 << 20, average: bool = True) -> int:
     """Data-parallel training step glue (training): every rank has run forward +
     backward on ITS bag; sum (mean) the gradients of ``params`` over the ranks.  Gradients are packed

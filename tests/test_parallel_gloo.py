@@ -97,3 +97,40 @@ def test_allreduce_gradients_equals_serial_average_world2():
     results = mgr.dict()
     mp.spawn(_grad_worker, args=(world, port, results), nprocs=world, join=True)
     assert dict(results) == {0: True, 1: True}
+
+
+class _StandInMil(torch.nn.Module):
+    """logits = (mean over tokens) @ W: deterministic, rank independent."""
+
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(3)
+        self.w = torch.nn.Parameter(torch.randn(8, 3, generator=g))
+
+    def forward(self, x):
+        return x[0].mean(0, keepdim=True) @ self.w
+
+
+def _logit_worker(rank, world, port, lens, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        bags = [torch.randn(n, 8, generator=g) for n in lens]
+        m = _StandInMil()
+        out = parallel.classify_bags_parallel(m, bags)
+        ref = torch.cat([m(b.unsqueeze(0)) for b in bags]).detach()
+        ok = out.shape == (len(bags), 3) and torch.allclose(out, ref, atol=1e-6)
+        only0 = parallel.classify_bags_parallel(m, bags, dst=0)
+        results[rank] = bool(ok and ((only0 is None) == (rank != 0)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lens", [[5, 3, 9, 1, 7], [4]])
+def test_logits_gather_world2(lens):
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_logit_worker, args=(world, port, lens, results), nprocs=world, join=True)
+    assert dict(results) == {0: True, 1: True}
