@@ -400,7 +400,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bags", type=int, default=16, help="distinct bags per step per GPU")
     ap.add_argument("--e2e-streams", type=int, default=3)
-    ap.add_argument("--lanes", type=int, default=4, help="bags in flight per GPU (internal streams)")
+    ap.add_argument("--lanes", type=int, default=8, help="bags in flight per GPU (internal streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the forward+backward measurement")
     args = ap.parse_args()

@@ -637,7 +637,8 @@ RRT_API int rrt_encoder_forward_batch(const rrt_config* cfg, const rrt_weights* 
     }
   }
   // >= 4 bags in flight: the bag-sized GEMMs keep to 64 SMs (csrc/gemm_tcgen05.cu, "SM cap")
-  rrt::set_gemm_sm_cap(lanes >= 4 ? 64 : 0);
+  // (measured, us per bag: 4 lanes x 64 SMs 67.9, 8 lanes x 64 67.8, 8 lanes x 48 67.6, 8 lanes x 37 66.4)
+  rrt::set_gemm_sm_cap(lanes >= 8 ? 37 : (lanes >= 4 ? 64 : 0));
   // programmatic dependent launch pays up to 3 bags in flight (measured, us/bag without -> with: 1 lane
   // 117.0 -> 96.9, 2 lanes 77.9 -> 72.1, 3 lanes 76.2 -> 72.9) and costs a little from 4 on (68.0 -> 69.2)
   PdlScope pdl(lanes <= 3 && !g_timing.load(std::memory_order_relaxed));
