@@ -195,6 +195,34 @@ def run_reference_arm(args):
                          "sample": f"{args.steps} steps x 1 bag of N={N_TOKENS}"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    # Informational extra ("beside the reference GPU-eager number"): the SAME reference-order
+    # ATen operator sequence on cuda:0, fp32, allow_tf32 off (PyTorch's default for matmul), no autocast --
+    # what the reference's eager forward costs on this GPU.  Not the arm's value; the unmodified reference
+    # itself cannot travel to this box.
+    if torch.cuda.is_available():
+        try:
+            from oracle import rrt_oracle as O
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            cfg = O.EncoderConfig(**{k: v for k, v in ENC_KW.items()})
+            wg = {k: v.cuda() for k, v in O.make_weights(cfg, 2021, dtype=torch.float32, randomize_bias=False).items()}
+            xg = O.make_bag(N_TOKENS, DIM, 7, dtype=torch.float32).cuda()
+            with torch.no_grad():
+                for _ in range(3):
+                    O.encoder_forward(xg, wg, cfg, "reference")
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    O.encoder_forward(xg, wg, cfg, "reference")
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            line["gpu_eager_port"] = {"value": N_TOKENS / (ms * 1e-3), "unit": UNIT, "ms_per_bag": ms,
+                                      "what": "oracle reference-order port (the reference's ATen sequence) on "
+                                              "cuda:0, fp32, TF32 off, eager, CUDA events, 10 bags back to back"}
+        except Exception as e:  # informational only
+            line["gpu_eager_port"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line), flush=True)
 
 

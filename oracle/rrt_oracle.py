@@ -161,7 +161,7 @@ def layer_norm(x, w, b):
 def _to_regions(z: torch.Tensor, L: int, H: int, rs: int) -> torch.Tensor:
     """[L,D] -> zero-pad to H*H tokens -> [R,P,D] (modules/rmsa.py:199-215)."""
     D, g = z.shape[-1], H // rs
-    zp = torch.cat([z, torch.zeros(H * H - L, D, dtype=z.dtype)]) if H * H > L else z
+    zp = torch.cat([z, torch.zeros(H * H - L, D, dtype=z.dtype, device=z.device)]) if H * H > L else z
     # grid (row, col) -> (region row, row in region, region col, col in region); the slot order of
     # ``region_slot_map`` is exactly this axis swap
     return zp.view(g, rs, g, rs, D).transpose(1, 2).reshape(g * g, rs * rs, D)
@@ -264,7 +264,7 @@ def pos_embedding(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfi
     add = H * H - L
     g = torch.cat([x, x[:add]]) if add > 0 else x
     if cfg.pos == "ppeg" and H < 7:
-        g = torch.cat([g, torch.zeros(49 - H * H, D, dtype=x.dtype)])
+        g = torch.cat([g, torch.zeros(49 - H * H, D, dtype=x.dtype, device=x.device)])
         H = 7
     feat = g.t().reshape(1, D, H, H)
     out = feat
