@@ -58,7 +58,7 @@ def test_module_behaves_like_an_nn_module():
     assert sum(p.numel() for p in m.parameters()) == 2_105_984
     seq = torch.nn.Sequential(torch.nn.Linear(1024, 512), torch.nn.ReLU(), m)
     assert any(isinstance(c, torch.nn.Conv2d) for c in seq.modules())
-    assert float(m.layers[0].attn.attn.qkv.bias.abs().sum()) == 0.0
+    assert float(m.layers[0].attn.attn.qkv.bias.detach().abs().sum()) == 0.0
     m.eval(); m.train(); repr(m)
 
 
