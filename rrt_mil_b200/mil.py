@@ -226,10 +226,12 @@ class RRTMIL(nn.Module):
             raise RuntimeError("RRTMIL (rrt_mil_b200) needs float32 CUDA input; there is no CPU fallback")
         bag = x[0].contiguous()
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if needs_grad or self.training:
-            if return_attn:
-                raise NotImplementedError("return_attn is an inference option")
+        if self.training and return_attn:
+            raise NotImplementedError("return_attn is an inference option: call .eval() first")
+        if (needs_grad or self.training) and not return_attn:
             return self._forward_train(bag)
+        # inference kernels (also for eval-mode attention maps requested outside torch.no_grad(): the map and
+        # the logits returned with it carry no autograd graph)
         L, in_dim = bag.shape
         dev = bag.device
         lib = cabi.lib()
