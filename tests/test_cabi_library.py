@@ -117,3 +117,41 @@ def test_integration_md_stub_structs_match_the_header():
     assert C.sizeof(ns["_W"]) == C.sizeof(cabi.RrtWeights)
     assert [n for n, _ in ns["_Cfg"]._fields_] == [n for n, *_ in cabi.RrtConfig._fields_]
     assert [n for n, _ in ns["_W"]._fields_] == [n for n, *_ in cabi.RrtWeights._fields_]
+
+
+def test_config_validation_of_the_ablation_options():
+    """pos / ffn options are validated by the library itself (no GPU needed: sizes only)."""
+    from rrt_mil_b200 import RRTEncoder
+    base = RRTEncoder()._cfg
+    n0 = cabi.workspace_bytes(base, 9000)
+    ffn = RRTEncoder(ffn=True)._cfg
+    assert cabi.workspace_bytes(ffn, 9000) > n0 + 9000 * 2048 * 2          # the fp16 hidden rows
+    peg = RRTEncoder(pos="ppeg", pos_pos=-1)._cfg
+    assert cabi.workspace_bytes(peg, 9000) >= n0 + 9000 * 512 * 4           # the PEG output
+    for field, bad in (("ffn_hidden", 100), ("ffn_act", 3), ("pos", 7), ("pos_pos", 2), ("peg_k", 4)):
+        cfg = RRTEncoder(ffn=True, pos="peg", pos_pos=-1)._cfg
+        setattr(cfg, field, bad)
+        with pytest.raises(ValueError):
+            cabi.workspace_bytes(cfg, 512)
+    n = C.c_size_t()
+    lib = cabi.lib()
+    assert lib.rrt_train_tape_bytes(C.byref(base), 9000, C.byref(n)) == 0 and n.value > 9216 * 512 * 2 * 5
+    assert lib.rrt_backward_workspace_bytes(C.byref(base), 9000, C.byref(n)) == 0 and n.value > 0
+    assert lib.rrt_mil_head_backward_workspace_bytes(9000, 512, 128, C.byref(n)) == 0 and n.value > 9000 * 512 * 2
+    assert lib.rrt_mil_head_backward_workspace_bytes(0, 512, 128, C.byref(n)) != 0
+
+
+def test_optimizer_rejects_what_it_cannot_update():
+    import torch
+    from rrt_mil_b200.optim import Adam, AdamW
+    with pytest.raises(ValueError):
+        Adam([torch.nn.Parameter(torch.zeros(3))], lr=-1.0)
+    with pytest.raises(ValueError):
+        AdamW([torch.nn.Parameter(torch.zeros(3))], betas=(1.0, 0.9))
+    p = torch.nn.Parameter(torch.zeros(3))
+    p.grad = torch.ones(3)
+    with pytest.raises(RuntimeError, match="CUDA"):      # no CPU fallback
+        Adam([p]).step()
+    q = torch.nn.Parameter(torch.zeros(3))
+    Adam([q]).step()                                       # no gradient: nothing to do, no device needed
+    assert float(q.abs().sum()) == 0.0
