@@ -99,3 +99,38 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+@pytest.mark.skipif(not shim.available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("host", ["attmil.DAttention", "attmil.AttentionGated", "mean_max.MeanMIL", "mean_max.MaxMIL"])
+def test_drops_into_the_reference_mil_hosts(host):
+    """The reference's own aggregators take the encoder as ``rrt=<module>`` (main.py:138-155).  Built once with
+    the reference encoder and once with ours they must have the same parameter tree, exchange checkpoints with
+    strict=True, and the host's own ``initialize_weights`` pass (isinstance checks on nn.Linear / nn.Conv2d /
+    nn.LayerNorm, modules/attmil.py:6-25) must reach the parameters our holders own."""
+    import importlib
+    ref_rrt = shim.import_reference_rrt()
+    mod_name, cls_name = host.split(".")
+    mod = importlib.import_module("modules." + mod_name)
+    cls = getattr(mod, cls_name)
+    kw = dict(input_dim=1024, n_classes=2, dropout=True, act="relu")
+
+    def build(enc):
+        try:
+            return cls(rrt=enc, **kw)
+        except TypeError:
+            return cls(rrt=enc, input_dim=1024, act="relu")   # AttentionGated(input_dim, act, bias, dropout, rrt)
+
+    enc_kw = dict(epeg_k=9, crmsa_k=5)
+    theirs, ours = build(ref_rrt.RRTEncoder(**enc_kw)), build(RRTEncoder(**enc_kw))
+    ks_t = {k: tuple(v.shape) for k, v in theirs.state_dict().items()}
+    ks_o = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    assert ks_t == ks_o
+    ours.load_state_dict(theirs.state_dict(), strict=True)
+    theirs.load_state_dict(ours.state_dict(), strict=True)
+    enc = [m for m in ours.modules() if isinstance(m, RRTEncoder)][0]
+    # the host's initialisation pass zeroed our biases and reset our LayerNorms
+    assert float(enc.layers[0].attn.attn.qkv.bias.detach().abs().sum()) == 0.0
+    assert float((enc.norm.weight.detach() - 1).abs().sum()) == 0.0
+    assert sum(p.numel() for p in enc.parameters()) == sum(
+        p.numel() for p in [m for m in theirs.modules() if isinstance(m, ref_rrt.RRTEncoder)][0].parameters())
