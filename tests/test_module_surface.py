@@ -102,7 +102,8 @@ def test_product_never_imports_the_oracle():
 
 
 @pytest.mark.skipif(not shim.available(), reason="/root/reference only exists in the build container")
-@pytest.mark.parametrize("host", ["attmil.DAttention", "attmil.AttentionGated", "mean_max.MeanMIL", "mean_max.MaxMIL"])
+@pytest.mark.parametrize("host", ["attmil.DAttention", "attmil.AttentionGated", "mean_max.MeanMIL", "mean_max.MaxMIL",
+                                  "dsmil.MILNet"])
 def test_drops_into_the_reference_mil_hosts(host):
     """The reference's own aggregators take the encoder as ``rrt=<module>`` (main.py:138-155).  Built once with
     the reference encoder and once with ours they must have the same parameter tree, exchange checkpoints with
@@ -116,6 +117,8 @@ def test_drops_into_the_reference_mil_hosts(host):
     kw = dict(input_dim=1024, n_classes=2, dropout=True, act="relu")
 
     def build(enc):
+        if cls_name == "MILNet":                                # dsmil: (n_classes, dropout, act, input_dim, rrt)
+            return cls(n_classes=2, dropout=True, act="relu", input_dim=1024, rrt=enc)
         try:
             return cls(rrt=enc, **kw)
         except TypeError:
