@@ -312,7 +312,7 @@ int f16_weight(const float* w32, const void* shadow, __half* scratch, size_t n, 
 
 // training-mode proj_drop (modules/rmsa.py:70,132): probability and the seed of this step; the mask
 // stream of R-MSA layer i is i, the landmark MHA of CR-MSA uses kCrDropStream
-struct TrainOpts { float drop_p = 0.f; unsigned long long seed = 0; };
+struct TrainOpts { float drop_p = 0.f; unsigned long long seed = 0; bool tape = false; };
 constexpr unsigned kCrDropStream = 64;
 
 int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
@@ -330,12 +330,19 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
   if (rc) return rc;
   rc = f16_weight(a->proj_w, a->proj_w_f16, ws.wconv + (size_t)3 * D * D, (size_t)D * D, st, &wp);
   if (rc) return rc;
-  { StageScope s_(kStLnPartition, st);
-    if (!s_.skip()) RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws_z, g, D, st), "ln_partition"); }
   rrt::GemmEpilogue e1;
   e1.bias = c->qkv_bias ? a->qkv_b : nullptr;
-  { StageScope s_(kStQkvGemm, st);
-    if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws_z, wq, ws_qkv, true, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
+  if (rrt::g_qkv_fused_ln && !tr.tape && rrt::gemm_lnqkv_supported(g, D, 3 * D)) {
+    // experimental (off by default): LayerNorm + partition fused into the QKV GEMM, z never exists
+    StageScope s_(kStQkvGemm, st);
+    if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_lnqkv_tcgen05(x, norm_w, norm_b, g, wq, e1.bias, ws_qkv, D, 3 * D, st),
+                             "ln + qkv gemm (fused)");
+  } else {
+    { StageScope s_(kStLnPartition, st);
+      if (!s_.skip()) RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws_z, g, D, st), "ln_partition"); }
+    { StageScope s_(kStQkvGemm, st);
+      if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws_z, wq, ws_qkv, true, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
+  }
   { StageScope s_(kStRmsaAttn, st);
     const float* taps = c->epeg ? a->pe_w : nullptr;
     if (s_.skip()) {
@@ -970,8 +977,8 @@ RRT_API int rrt_debug_skip_stages(uint32_t mask) {
 }
 
 RRT_API int rrt_debug_set_gemm_cluster(int32_t mode) {
-  if (mode != 2 && mode != 22 && mode != 21 && mode != 11 && mode != 128 && mode != 256)
-    return fail(RRT_E_INVALID, "mode must be 2, 11, 21, 22, 128 or 256");
+  if (mode != 2 && mode != 3 && mode != 30 && mode != 22 && mode != 21 && mode != 11 && mode != 128 && mode != 256)
+    return fail(RRT_E_INVALID, "mode must be 2, 3, 30, 11, 21, 22, 128 or 256");
   rrt::set_gemm_cluster_mode(mode);
   return RRT_OK;
 }
@@ -1293,6 +1300,7 @@ RRT_API int rrt_encoder_forward_train(const rrt_config* cfg, const rrt_weights* 
   TrainOpts tr;
   tr.drop_p = drop_p;
   tr.seed = seed;
+  tr.tape = true;  // the backward re-reads z, q/k/v, o: no kernel variant may skip an intermediate
   PdlScope pdl(!g_timing.load(std::memory_order_relaxed));
   return encoder_forward(cfg, w, x, out, L, ws, (cudaStream_t)stream, tr);
 }

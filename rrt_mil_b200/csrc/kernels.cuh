@@ -50,6 +50,14 @@ cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool 
 // weight gradient: dw[C_out, C_in] (fp32, zeroed) += dy[rows, C_out]^T @ act[rows, C_in] (fp16, row-major)
 cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float* dw, int rows, int C_out,
                                       int C_in, cudaStream_t stream);
+// EXPERIMENTAL (off by default): qkv[slot,:] = LN(x[token(slot),:]) @ w^T + bias in ONE kernel -- the 128-row
+// A tile is LayerNorm'ed from the fp32 residual stream into shared memory once and stays resident for all
+// N tiles (replaces launch_ln_partition + the QKV launch_gemm_tcgen05 in the inference forward).  D in {256, 512}.
+extern int g_qkv_fused_ln;  // RRT_QKV_FUSED_LN=1 / rrt_debug_set_gemm_cluster(3) on, (30) off
+bool gemm_lnqkv_supported(const Grid& grid, int D, int N);
+cudaError_t launch_gemm_lnqkv_tcgen05(const float* x, const float* gamma, const float* beta, const Grid& grid,
+                                      const __half* w, const float* bias, __half* qkv, int D, int N,
+                                      cudaStream_t stream);
 void set_gemm_cluster_mode(int mode);
 // at most n SMs for the bag-sized GEMMs launched by THIS host thread from now on (0 = all)
 void set_gemm_sm_cap(int n);  // debug/tuning: 22 = 2x2 clusters, 21 = 2x1, 11 = none

@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C ABI) against the oracle and the committed golden
 vectors.  Tolerance: the north-star's fp32 bar, rel <= 1e-3 (tf32 tensor-core operands, fp32
 accumulation / softmax / LayerNorm); the HBM-bound fp32 kernels are held to 1e-5."""
+import os
+
 import pytest
 import torch
 
@@ -225,6 +227,52 @@ def test_alternative_kernel_variants_keep_parity(knob, value, restore):
             assert_matches_golden(y, gold, TOL_TF32, f"{knob}={value} {name}")
     finally:
         getattr(lib, knob)(restore)
+
+
+@pytest.mark.skipif(os.environ.get("RRT_EXPERIMENTAL") != "1",
+                    reason="experimental kernel, not yet run on a B200: set RRT_EXPERIMENTAL=1 to test it")
+def test_experimental_fused_ln_qkv_gemm_keeps_parity():
+    """LayerNorm-fused QKV GEMM with a resident A tile (rrt_debug_set_gemm_cluster(3)):
+    same parity bar as the default path; R-MSA block close to the unfused kernels (the LayerNorm sums run in
+    a different order, so z may differ by an fp16 ulp); bags in flight exercise the A refill (several work
+    items per CTA under the SM cap)."""
+    from rrt_mil_b200 import cabi
+    lib = cabi.lib()
+    for L, over in [(512, dict()), (9000, dict()), (63, dict()), (65, dict()), (1300, dict(region_num=4, epeg_k=9)),
+                    (700, dict(mlp_dim=256, n_heads=4, crmsa_heads=4)), (20000, dict(region_num=16))]:
+        cfg, m = _default_encoder(**over)
+        x = O.make_bag(L, cfg.mlp_dim, 9, dtype=torch.float32).cuda()
+        ref = G.rmsa_block(m, 0, x)
+        lib.rrt_debug_set_gemm_cluster(3)
+        try:
+            got = G.rmsa_block(m, 0, x)
+            got2 = G.rmsa_block(m, 0, x)
+        finally:
+            lib.rrt_debug_set_gemm_cluster(30)
+        torch.cuda.synchronize()
+        assert torch.equal(got, got2), (L, over)
+        assert O.rel_err(got.cpu().double(), ref.cpu().double()) < 2e-4, (L, over)
+    lib.rrt_debug_set_gemm_cluster(3)
+    try:
+        for name in ("c1_n512_d512", "c2_n9000_d512", "c4_n50000_g16", "d256_g4", "n65"):
+            cfg, w, x, gold = load_case(name)
+            m = G.make_encoder(cfg, w)
+            with torch.no_grad():
+                y = m(x.float().cuda())
+            torch.cuda.synchronize()
+            assert_matches_golden(y, gold, TOL_TF32, f"fused ln+qkv {name}")
+        cfg, m = _default_encoder()
+        g = torch.Generator().manual_seed(5)
+        bags = [torch.randn(n, 512, generator=g).cuda() for n in [9000, 777, 8123, 1, 9216, 5000, 4097, 9000, 8999]]
+        with torch.no_grad():
+            serial = [m(b) for b in bags]
+            for lanes in (4, 8):
+                outs = m.forward_bags(bags, lanes=lanes)
+                torch.cuda.synchronize()
+                for a, b in zip(serial, outs):
+                    assert torch.equal(a, b)
+    finally:
+        lib.rrt_debug_set_gemm_cluster(30)
 
 
 def test_tiny_bag_crmsa_contributes_nothing():
