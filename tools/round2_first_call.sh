@@ -1,0 +1,26 @@
+#!/usr/bin/env bash
+# First GPU call of the next round: verify and measure the experimental LayerNorm-fused QKV GEMM
+#  before anything is built on it.  Run from the repo root on the GPU box:
+#   gpurun --timeout 900 -- 'bash tools/round2_first_call.sh'
+# Every step runs under its own timeout (a pipeline bug traps after ~2 s of SM clocks, it does not hang).
+set -u
+mkdir -p gpurun_out
+# 1. the default path still green (fast subset) -- the library was rebuilt with the new kernel in it
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/r2a_tests_default.log 2>&1
+echo "default parity rc=$?"
+# 2. parity of the experimental kernel (block level vs the default kernels, goldens, lanes == serial)
+RRT_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
+  -k experimental_fused > gpurun_out/r2a_tests_fused.log 2>&1
+echo "fused parity rc=$?"
+# 3. A/B: stage times, us/bag per lane count, phase trace
+timeout 300 python tools/fused_qkv_probe.py --trace > gpurun_out/r2a_fused_probe.log 2>&1
+echo "probe rc=$?"
+# 4. bench line with the fused kernel on (compare with profiles/r01c_bench_default.json)
+RRT_QKV_FUSED_LN=1 timeout 400 python bench.py > gpurun_out/r2a_bench_fused.json 2> gpurun_out/r2a_bench_fused.err
+echo "bench rc=$?"
+# 5. one ncu --set full capture of the fused kernel (1 GPU; never a bench number)
+RRT_QKV_FUSED_LN=1 timeout 600 ncu --set full --clock-control none --import-source on \
+  -k regex:gemm_lnqkv -c 2 -o gpurun_out/r2a_fused_qkv -f python tools/stage_probe.py \
+  > gpurun_out/r2a_ncu.log 2>&1
+echo "ncu rc=$?"
+tail -n 5 gpurun_out/r2a_tests_fused.log gpurun_out/r2a_fused_probe.log
