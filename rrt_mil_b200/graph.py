@@ -1,0 +1,88 @@
+"""CUDA-graph replay of the encoder forward for fixed bag geometries (EXPERIMENTAL: written after this
+round's GPU budget was spent; its GPU test runs only with ``RRT_EXPERIMENTAL=1``).
+
+A bag of a few hundred patches is launch-latency bound (10 kernels per bag: N=512 takes 77 us on a B200, of
+which the kernels themselves are a fraction).  The library call is capture-safe by construction -- no host
+synchronisation, caller-owned workspace, internal lanes forked from / joined into the caller's stream with
+events -- so the whole kernel chain of ``forward_bags`` for a FIXED list of bag lengths can be recorded once
+into a ``torch.cuda.CUDAGraph`` and replayed with a single launch.
+
+The graph bakes in the parameter pointers and, in eval mode, the fp16 weight shadows that existed at capture
+time; ``__call__`` re-captures when a parameter's storage or version counter changed since then (same test
+as ``RRTEncoder._weights``), so results always equal the eager path's.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+
+from . import cabi
+
+
+class GraphedForward:
+    """``g = GraphedForward(encoder, [N_0, N_1, ...]); outs = g(bags)`` -- inference only (eval mode).
+
+    ``bags[i]`` must be float32 CUDA ``[N_i, D]``; they are copied into the graph's static input buffers
+    (device-to-device, on the current stream) and the returned tensors are the graph's static outputs:
+    they are overwritten by the next call.  ``g.inputs`` / ``g.outputs`` are exposed so that a producer can
+    write the static inputs directly and call ``g.replay()``."""
+
+    def __init__(self, encoder, lengths: Sequence[int], lanes: int = cabi.RRT_MAX_LANES, device=None):
+        if encoder.training:
+            raise RuntimeError("GraphedForward is inference-only: call .eval() first")
+        if not lengths or any(int(n) < 1 for n in lengths):
+            raise ValueError("lengths must be a non-empty list of positive bag sizes")
+        self.enc = encoder
+        self.lengths = [int(n) for n in lengths]
+        self.lanes = max(1, min(int(lanes), cabi.RRT_MAX_LANES))
+        self.device = (torch.device(device) if device is not None
+                       else next(encoder.parameters()).device)
+        if self.device.type != "cuda":
+            raise RuntimeError("GraphedForward needs the encoder on a CUDA device; there is no CPU fallback")
+        D = encoder.final_dim
+        self.inputs: List[torch.Tensor] = [torch.zeros(n, D, device=self.device) for n in self.lengths]
+        self.outputs: List[torch.Tensor] = [torch.empty(n, D, device=self.device) for n in self.lengths]
+        self._graph = None
+        self._key = None
+        self.captures = 0
+
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.enc._named_param_cache()[1])
+
+    @torch.no_grad()
+    def _capture(self) -> None:
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):  # one-time work (function attributes, lane streams, TMA descriptor cache, shadows)
+                self.enc.forward_bags(self.inputs, self.outputs, lanes=self.lanes)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            # the workspace is allocated inside the capture: it lives in the graph's private pool
+            self.enc.forward_bags(self.inputs, self.outputs, lanes=self.lanes)
+        self._graph, self._key = graph, self._weights_key()
+        self.captures += 1
+
+    def replay(self) -> List[torch.Tensor]:
+        if self.enc.training:
+            raise RuntimeError("GraphedForward is inference-only: call .eval() first")
+        if self._graph is None or self._key != self._weights_key():
+            self._capture()
+        self._graph.replay()
+        return self.outputs
+
+    @torch.no_grad()
+    def __call__(self, bags: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        if len(bags) != len(self.lengths):
+            raise ValueError(f"expected {len(self.lengths)} bags, got {len(bags)}")
+        for x, buf in zip(bags, self.inputs):
+            if x.shape != buf.shape or x.dtype != torch.float32 or x.device != self.device:
+                raise ValueError(f"expected a float32 {tuple(buf.shape)} bag on {self.device}, "
+                                 f"got {x.dtype} {tuple(x.shape)} on {x.device}")
+        for x, buf in zip(bags, self.inputs):
+            if x.data_ptr() != buf.data_ptr():
+                buf.copy_(x, non_blocking=True)
+        return self.replay()
