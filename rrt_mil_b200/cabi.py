@@ -174,7 +174,7 @@ def lib() -> C.CDLL:
                 raise RuntimeError("librrt_b200.so ABI version mismatch: rebuild it")
             if os.environ.get("RRT_ATTN"):  # tuning knob: tc05 | mma
                 handle.rrt_debug_set_attention_kernel(int(os.environ["RRT_ATTN"] == "tc05"))
-            if os.environ.get("RRT_GEMM_CLUSTER"):  # tuning knob: 22 (default), 21, 11
+            if os.environ.get("RRT_GEMM_CLUSTER"):  # tuning knob: 11 (default), 2, 21, 22, 128, 256, 3 (experimental fused LN+QKV)
                 handle.rrt_debug_set_gemm_cluster(int(os.environ["RRT_GEMM_CLUSTER"]))
             _lib = handle
     return _lib
