@@ -625,6 +625,10 @@ struct LnFillParams {
 // LayerNorm of rows [16 ew, 16 ew + 16) of the M tile at m0 into the resident A tile.  Lane l owns the 8
 // consecutive columns 8 l + 256 j (j < V2): k-block 4 j + l / 8, 16-byte chunk l % 8 of the 128-byte row
 // segment; a quarter warp writes one whole 128-byte segment per store phase (no bank conflicts).
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 template <int V2>
 __device__ __forceinline__ void ln_fill_rows(const Tc05Params& p, const LnFillParams& f, uint8_t* sA, int m0,
                                              int ew, int lane, const float4 (&gm)[2 * V2],
@@ -632,6 +636,7 @@ __device__ __forceinline__ void ln_fill_rows(const Tc05Params& p, const LnFillPa
   constexpr int D = 256 * V2;
   constexpr float inv_d = 1.f / D;
   const int kb_l = lane >> 3, chunk = lane & 7;
+  const uint32_t sA_u32 = smem_u32(sA);
 #pragma unroll 1
   for (int rb = 0; rb < 16; rb += 4) {
     float4 v[4][2 * V2];
@@ -657,11 +662,10 @@ __device__ __forceinline__ void ln_fill_rows(const Tc05Params& p, const LnFillPa
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int r = ew * 16 + rb + q;
-      uint8_t* rowp = sA + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4);
+      const uint32_t rowp = sA_u32 + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4);
       if (tok[q] < 0) {  // pad slot (or a row past the last slot): exact zeros AFTER the norm
 #pragma unroll
-        for (int j = 0; j < V2; ++j)
-          *reinterpret_cast<uint4*>(rowp + (4 * j + kb_l) * A_BYTES) = make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 0; j < V2; ++j) sts128(rowp + (4 * j + kb_l) * A_BYTES, 0u, 0u, 0u, 0u);
         continue;
       }
       float s = 0.f;
@@ -684,7 +688,7 @@ __device__ __forceinline__ void ln_fill_rows(const Tc05Params& p, const LnFillPa
           h[2 * u] = pack_h2((xv.x - mean) * rstd * g4.x + b4.x, (xv.y - mean) * rstd * g4.y + b4.y);
           h[2 * u + 1] = pack_h2((xv.z - mean) * rstd * g4.z + b4.z, (xv.w - mean) * rstd * g4.w + b4.w);
         }
-        *reinterpret_cast<uint4*>(rowp + (4 * j + kb_l) * A_BYTES) = make_uint4(h[0], h[1], h[2], h[3]);
+        sts128(rowp + (4 * j + kb_l) * A_BYTES, h[0], h[1], h[2], h[3]);
       }
     }
   }
