@@ -977,8 +977,9 @@ RRT_API int rrt_debug_skip_stages(uint32_t mask) {
 }
 
 RRT_API int rrt_debug_set_gemm_cluster(int32_t mode) {
-  if (mode != 2 && mode != 3 && mode != 30 && mode != 22 && mode != 21 && mode != 11 && mode != 128 && mode != 256)
-    return fail(RRT_E_INVALID, "mode must be 2, 3, 30, 11, 21, 22, 128 or 256");
+  if (mode != 2 && mode != 3 && mode != 4 && mode != 30 && mode != 22 && mode != 21 && mode != 11 && mode != 128 &&
+      mode != 256)
+    return fail(RRT_E_INVALID, "mode must be 2, 3, 4, 30, 11, 21, 22, 128 or 256");
   rrt::set_gemm_cluster_mode(mode);
   return RRT_OK;
 }

@@ -631,12 +631,19 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 
 template <int V2>
 __device__ __forceinline__ void ln_fill_rows(const Tc05Params& p, const LnFillParams& f, uint8_t* sA, int m0,
-                                             int ew, int lane, const float4 (&gm)[2 * V2],
-                                             const float4 (&bt)[2 * V2]) {
+                                             int ew, int lane) {
   constexpr int D = 256 * V2;
   constexpr float inv_d = 1.f / D;
   const int kb_l = lane >> 3, chunk = lane & 7;
   const uint32_t sA_u32 = smem_u32(sA);
+  // LayerNorm affine parameters of this lane's columns (8 x 16 B from L1 / L2 per work item: cheaper than
+  // keeping 32 registers alive across the epilogue)
+  float4 gm[2 * V2], bt[2 * V2];
+#pragma unroll
+  for (int i = 0; i < 2 * V2; ++i) {
+    gm[i] = __ldg(reinterpret_cast<const float4*>(f.gamma) + 2 * lane + 64 * (i >> 1) + (i & 1));
+    bt[i] = __ldg(reinterpret_cast<const float4*>(f.beta) + 2 * lane + 64 * (i >> 1) + (i & 1));
+  }
 #pragma unroll 1
   for (int rb = 0; rb < 16; rb += 4) {
     float4 v[4][2 * V2];
@@ -731,17 +738,6 @@ gemm_lnqkv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 2 * BN);
-  // LayerNorm affine parameters of this lane's columns: weights, not written by any kernel of the chain
-  float4 gm[2 * V2], bt[2 * V2];
-  if (warp >= 4) {
-#pragma unroll
-    for (int j = 0; j < V2; ++j)
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        gm[2 * j + u] = __ldg(reinterpret_cast<const float4*>(f.gamma) + 2 * lane + 64 * j + u);
-        bt[2 * j + u] = __ldg(reinterpret_cast<const float4*>(f.beta) + 2 * lane + 64 * j + u);
-      }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -811,7 +807,7 @@ gemm_lnqkv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
       const int m0 = (wi / f.nsplit) * BM, part = wi % f.nsplit;
       // (not the first item: this warp's epilogue of the previous item's last tile has waited on that tile's
       // tfull barrier, i.e. every MMA that read the old A tile has completed)
-      ln_fill_rows<V2>(p, f, sA, m0, ew, lane, gm, bt);
+      ln_fill_rows<V2>(p, f, sA, m0, ew, lane);
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) mbar_arrive(afull);
@@ -834,6 +830,152 @@ gemm_lnqkv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// CTA-pair form of the kernel above (EXPERIMENTAL, RRT_QKV_FUSED_LN=2 or
+// rrt_debug_set_gemm_cluster(4)): the two CTAs of a cluster own 256 rows (each LayerNorms and keeps ITS 128) and
+// compute 256 x 256 tiles with cta_group::2 MMAs issued by the leader; each CTA streams only HALF of a W tile
+// (128 x 64 = 16 KB per k-block, the same bytes as the single-CTA kernel's whole 128-column tile), so the operand
+// ingest per MAC halves once more (32 B/clk/SM when MMA-bound).  Barrier placement follows
+// gemm_f16_tcgen05_2cta_kernel: full / tempty / afull live on the LEADER (the peer arrives remotely; TMA bytes of
+// both CTAs are accounted there), empty / tfull are multicast commits to both CTAs.
+template <int V2>  // K = 256 * V2
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_lnqkv_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                               Tc05Params p, LnFillParams f) {
+  constexpr int BN = 256, STAGES = LQ_STAGES, KB = 4 * V2;
+  constexpr int BHALF_BYTES = (BN / 2) * BK * 2;  // == LQ_B_BYTES
+  static_assert(BHALF_BYTES == LQ_B_BYTES, "the W ring is sized for 16 KB stages");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;                        // [KB][128 x 64] my 128 rows of LN(x), resident
+  uint8_t* sB = smem + LQ_KB_MAX * A_BYTES;  // [STAGES][128 x 64] my half of the W tile
+  float* sEpi = reinterpret_cast<float*>(sB + STAGES * BHALF_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* afull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  if (threadIdx.x == 0) stamp(p, 0);
+
+  if (warp == 0 && lane == 0) prefetch_tensormap(&tmB);
+  if (warp == 2 && lane == 0) prefetch_tensormap(&tmC);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);   // leader only: its W producer arms the bytes of BOTH halves
+      mbar_init(&empty[i], 1);  // both CTAs: multicast commit of the leader's MMA warp
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);               // both CTAs: multicast commit
+      mbar_init(&tempty[i], 2 * kEpiWarps);  // leader only: the epilogue warps of both CTAs
+    }
+    mbar_init(afull, 2 * kEpiWarps);         // leader only: the fill warps of both CTAs
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2cta(tmem_slot, 2 * BN);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(p, 1);
+
+  // work item wi = (pair M tile wi / nsplit, N share wi % nsplit) with 256-row / 256-column tiles
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int tiles_m2 = (p.M + 2 * BM - 1) / (2 * BM);
+  const int tpp = (p.N / BN) / f.nsplit;
+  const int num_items = tiles_m2 * f.nsplit;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== W producer (both CTAs: my half of every W tile) =====
+      int s = 0, ph = 0;
+      for (int wi = pair_id; wi < num_items; wi += num_pairs) {
+        const int part = wi % f.nsplit;
+        for (int nt = 0; nt < tpp; ++nt) {
+          const int n0 = (part * tpp + nt) * BN + (int)crank * (BN / 2);
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&empty[s], ph ^ 1);
+            if (crank == 0) mbar_arrive_expect_tx(&full[s], 2 * BHALF_BYTES);
+            tma_load_2d_2cta(sB + s * BHALF_BYTES, &tmB, &full[s], kb * BK, n0);
+            if (wi == pair_id && nt == 0 && kb == 0) stamp(p, 2);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (crank == 0 && lane == 0) {  // ===== MMA issuer: leader CTA only =====
+      constexpr uint32_t idesc = umma_idesc(kFmtF16, 2 * BM, BN);
+      int s = 0, ph = 0, acc = 0, aph = 0, item = 0;
+      for (int wi = pair_id; wi < num_items; wi += num_pairs, ++item) {
+        mbar_wait_cluster(afull, item & 1);  // both CTAs' halves of the resident A tile are filled
+        tc_fence_after();
+        if (item == 0) stamp(p, 3);
+        for (int nt = 0; nt < tpp; ++nt) {
+          mbar_wait(&tempty[acc], aph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (item == 0 && nt == 0 && kb == 0) stamp(p, 4);
+            const uint64_t ad = umma_desc_k_sw128(smem_u32(sA + kb * A_BYTES));
+            const uint64_t bd = umma_desc_k_sw128(smem_u32(sB + s * BHALF_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_2cta(&empty[s], 0b11);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+          umma_commit_2cta(&tfull[acc], 0b11);
+          if (++acc == 2) { acc = 0; aph ^= 1; }
+        }
+      }
+      stamp(p, 5);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {  // ===== LN fill of my 128 rows + epilogue of my accumulator half =====
+    const int ew = warp - 4;
+    float* scratch = sEpi + ew * 32 * EPI_LD;
+    int acc = 0, aph = 0;
+    for (int wi = pair_id; wi < num_items; wi += num_pairs) {
+      const int m0 = (wi / f.nsplit) * 2 * BM + (int)crank * BM, part = wi % f.nsplit;
+      ln_fill_rows<V2>(p, f, sA, m0, ew, lane);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (crank == 0) mbar_arrive(afull);
+        else mbar_arrive_remote(afull, 0);
+      }
+      for (int nt = 0; nt < tpp; ++nt) {
+        const int n0 = (part * tpp + nt) * BN;
+        uint64_t* te = &tempty[acc];
+        epilogue_tile<kEpiStore, BN, __half>(p, &tmC, tmem_base + acc * BN, &tfull[acc], aph, m0, n0, ew, lane,
+                                             scratch, wi == pair_id && nt == 0, [&] {
+                                               if (lane == 0) {
+                                                 if (crank == 0) mbar_arrive(te);
+                                                 else mbar_arrive_remote(te, 0);
+                                               }
+                                             });
+        if (++acc == 2) { acc = 0; aph ^= 1; }
+        if (threadIdx.x == 128) stamp(p, wi == pair_id && nt == 0 ? 7 : 8);
+      }
+    }
+  }
+
+  if (warp >= 4 && lane == 0) tma_store_wait_all<0>();
+  tc_fence_before();
+  cluster_sync_all();  // the peer's smem / barriers / TMEM half stay valid until both are done
+  if (threadIdx.x == 0) stamp(p, 9);
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 2 * BN);
   }
 }
 
@@ -1135,7 +1277,8 @@ cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float
 void set_gemm_sm_cap(int n) { g_gemm_sm_cap = n; }
 
 // 1: the QKV projection of the inference forward runs on gemm_lnqkv_tcgen05_kernel (LayerNorm fused, resident A
-// tile).  EXPERIMENTAL, default off; RRT_QKV_FUSED_LN=1 or rrt_debug_set_gemm_cluster(3) / (30) switch it.
+// tile; 2: its CTA-pair form).  EXPERIMENTAL, default off; RRT_QKV_FUSED_LN=1|2 or rrt_debug_set_gemm_cluster(3|4),
+// (30) = off.
 int g_qkv_fused_ln = [] { const char* e = getenv("RRT_QKV_FUSED_LN"); return e ? atoi(e) : 0; }();
 
 bool gemm_lnqkv_supported(const Grid& grid, int D, int N) {
@@ -1162,6 +1305,44 @@ cudaError_t launch_gemm_lnqkv_tcgen05(const float* x, const float* gamma, const 
   int sms = sm_count();
   const int cap = env_cap >= 0 ? env_cap : g_gemm_sm_cap;
   if (cap > 0 && cap < sms) sms = cap;
+  if (g_qkv_fused_ln == 2 && N % 256 == 0 && sms >= 2) {
+    // CTA pairs: 256-row x 256-column tiles, work items shared out over sms / 2 clusters
+    const int tiles_m2 = (grid.Np + 2 * BM - 1) / (2 * BM), tiles_n2 = N / 256, pairs_max = sms / 2;
+    int ns = 1;
+    for (int d = 1; d <= tiles_n2; ++d)
+      if (tiles_n2 % d == 0 && (long long)tiles_m2 * d <= pairs_max) ns = d;
+    LnFillParams f2{x, gamma, beta, ns};
+    const long long items2 = (long long)tiles_m2 * ns;
+    const int pairs = items2 < pairs_max ? (int)items2 : pairs_max;
+    cudaLaunchConfig_t c2{};
+    c2.gridDim = dim3(pairs * 2);
+    c2.blockDim = dim3(NTHREADS);
+    c2.dynamicSmemBytes = LQ_SMEM_BYTES;
+    c2.stream = stream;
+    cudaLaunchAttribute a2[1];
+    a2[0].id = cudaLaunchAttributeClusterDimension;
+    a2[0].val.clusterDim.x = 2;
+    a2[0].val.clusterDim.y = 1;
+    a2[0].val.clusterDim.z = 1;
+    c2.attrs = a2;
+    c2.numAttrs = 1;
+    if (D == 512) {
+      auto kern = gemm_lnqkv_tcgen05_2cta_kernel<2>;
+      static DeviceOnce configured;
+      if (configured.needed()) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LQ_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+      }
+      return cudaLaunchKernelEx(&c2, kern, tmB, tmC, p, f2);
+    }
+    auto kern = gemm_lnqkv_tcgen05_2cta_kernel<1>;
+    static DeviceOnce configured;
+    if (configured.needed()) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LQ_SMEM_BYTES);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaLaunchKernelEx(&c2, kern, tmB, tmC, p, f2);
+  }
   // the N tiles of an M tile are cut into nsplit shares (a divisor of N / 128) so that every SM has a work
   // item; each share LayerNorms the M tile again (L2 hits), so no more shares than that takes
   const int tiles_m = (grid.Np + BM - 1) / BM, tiles_n = N / LQ_BN;
@@ -1200,7 +1381,7 @@ cudaError_t launch_gemm_lnqkv_tcgen05(const float* x, const float* gamma, const 
 }
 
 void set_gemm_cluster_mode(int mode) {
-  if (mode == 3 || mode == 30) { g_qkv_fused_ln = mode == 3; return; }
+  if (mode == 3 || mode == 4 || mode == 30) { g_qkv_fused_ln = mode == 30 ? 0 : mode - 2; return; }  // 4: CTA pairs
   if (mode == 128 || mode == 256) { g_gemm_narrow = mode == 128; return; }
   if (mode == 2) { g_gemm_pair = 1; return; }
   g_gemm_pair = 0;

@@ -231,8 +231,9 @@ def test_alternative_kernel_variants_keep_parity(knob, value, restore):
 
 @pytest.mark.skipif(os.environ.get("RRT_EXPERIMENTAL") != "1",
                     reason="experimental kernel, not yet run on a B200: set RRT_EXPERIMENTAL=1 to test it")
-def test_experimental_fused_ln_qkv_gemm_keeps_parity():
-    """LayerNorm-fused QKV GEMM with a resident A tile (rrt_debug_set_gemm_cluster(3)):
+@pytest.mark.parametrize("mode", [3, 4])   # 3: single-CTA kernel, 4: CTA pairs (cta_group::2)
+def test_experimental_fused_ln_qkv_gemm_keeps_parity(mode):
+    """LayerNorm-fused QKV GEMM with a resident A tile (rrt_debug_set_gemm_cluster(3 | 4)):
     same parity bar as the default path; R-MSA block close to the unfused kernels (the LayerNorm sums run in
     a different order, so z may differ by an fp16 ulp); bags in flight exercise the A refill (several work
     items per CTA under the SM cap)."""
@@ -243,7 +244,7 @@ def test_experimental_fused_ln_qkv_gemm_keeps_parity():
         cfg, m = _default_encoder(**over)
         x = O.make_bag(L, cfg.mlp_dim, 9, dtype=torch.float32).cuda()
         ref = G.rmsa_block(m, 0, x)
-        lib.rrt_debug_set_gemm_cluster(3)
+        lib.rrt_debug_set_gemm_cluster(mode)
         try:
             got = G.rmsa_block(m, 0, x)
             got2 = G.rmsa_block(m, 0, x)
@@ -252,7 +253,7 @@ def test_experimental_fused_ln_qkv_gemm_keeps_parity():
         torch.cuda.synchronize()
         assert torch.equal(got, got2), (L, over)
         assert O.rel_err(got.cpu().double(), ref.cpu().double()) < 2e-4, (L, over)
-    lib.rrt_debug_set_gemm_cluster(3)
+    lib.rrt_debug_set_gemm_cluster(mode)
     try:
         for name in ("c1_n512_d512", "c2_n9000_d512", "c4_n50000_g16", "d256_g4", "n65"):
             cfg, w, x, gold = load_case(name)

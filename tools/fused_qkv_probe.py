@@ -3,6 +3,7 @@ against the default ln_partition + QKV GEMM pair.
 
     python tools/fused_qkv_probe.py            # parity vs the default path, stage times, us/bag per lane count
     python tools/fused_qkv_probe.py --trace    # + clock64 phase stamps of the fused kernel (2 CTAs)
+    python tools/fused_qkv_probe.py --pair     # the CTA-pair form (cta_group::2) instead of the single-CTA kernel
 
 Stamps of the fused kernel: start, setup, tma0 (first W tile issued), tmaN = A tile filled (MMA side),
 opnd0 (first W tile landed), mmaN (last MMA committed), acc0 (first accumulator ready), epi0 / epiN (first /
@@ -22,8 +23,11 @@ outs = [torch.empty_like(b) for b in bags]
 NAMES = ["start", "setup", "tma0", "afill", "opnd0", "mmaN", "acc0", "epi0", "epiN", "end"]
 
 
+MODE = 4 if "--pair" in sys.argv else 3   # 3: single-CTA fused kernel, 4: its CTA-pair form
+
+
 def fused(on):
-    lib.rrt_debug_set_gemm_cluster(3 if on else 30)
+    lib.rrt_debug_set_gemm_cluster(MODE if on else 30)
 
 
 def us_per_bag(lanes, steps=20):

@@ -18,6 +18,8 @@ echo "graph replay rc=$?"
 # 3. A/B: stage times, us/bag per lane count, phase trace
 timeout 300 python tools/fused_qkv_probe.py --trace > gpurun_out/r2a_fused_probe.log 2>&1
 echo "probe rc=$?"
+timeout 300 python tools/fused_qkv_probe.py --pair --trace > gpurun_out/r2a_fused_probe_pair.log 2>&1
+echo "probe (pair) rc=$?"
 # 4. bench line with the fused kernel on (compare with profiles/r01c_bench_default.json)
 RRT_QKV_FUSED_LN=1 timeout 400 python bench.py > gpurun_out/r2a_bench_fused.json 2> gpurun_out/r2a_bench_fused.err
 echo "bench rc=$?"
@@ -26,4 +28,4 @@ RRT_QKV_FUSED_LN=1 timeout 600 ncu --set full --clock-control none --import-sour
   -k regex:gemm_lnqkv -c 2 -o gpurun_out/r2a_fused_qkv -f python tools/stage_probe.py \
   > gpurun_out/r2a_ncu.log 2>&1
 echo "ncu rc=$?"
-tail -n 5 gpurun_out/r2a_tests_fused.log gpurun_out/r2a_fused_probe.log
+tail -n 5 gpurun_out/r2a_tests_fused.log gpurun_out/r2a_fused_probe.log gpurun_out/r2a_fused_probe_pair.log
