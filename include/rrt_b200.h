@@ -205,7 +205,8 @@ RRT_API int rrt_debug_set_attention_kernel(int32_t use_tcgen05);
  * 256-column tile per CTA (proj; default 256).  Results do not depend on it.
  * 3 / 4 / 30 = EXPERIMENTAL LayerNorm-fused QKV GEMM with a resident A tile: single-CTA / CTA-pair form / off
  * (default off, also RRT_QKV_FUSED_LN=1|2; inference forward only; results agree within the parity tolerance,
- * not bit for bit). */
+ * not bit for bit).  5 / 50 = EXPERIMENTAL one-kernel CR-MSA front end on thread-block clusters (DSMEM exchange
+ * of the row statistics) on / off (default off, also RRT_CRMSA_FRONT=cluster; same caveats). */
 RRT_API int rrt_debug_set_gemm_cluster(int32_t mode);
 
 /* Debug / measurement only: bit i set = the kernels of stage i (rrt_stage_name order) are NOT launched.

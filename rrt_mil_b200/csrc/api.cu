@@ -398,12 +398,21 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   rc = f16_weight(w->cr_attn.proj_w, w->cr_attn.proj_w_f16, ws.wconv + (size_t)3 * D * D,
                   (size_t)D * D, st, &wp);
   if (rc) return rc;
-  static const int front_mode = [] {  // tuning knob: RRT_CRMSA_FRONT=split (default) | fused | legacy
+  static const int front_mode = [] {  // tuning knob: RRT_CRMSA_FRONT=split (default) | fused | legacy | cluster
     const char* e = getenv("RRT_CRMSA_FRONT");
-    return !e ? 0 : (!strcmp(e, "fused") ? 1 : (!strcmp(e, "legacy") ? 2 : 0));
+    return !e ? 0 : (!strcmp(e, "fused") ? 1 : (!strcmp(e, "legacy") ? 2 : (!strcmp(e, "cluster") ? 3 : 0)));
   }();
   bool front_done = false;
-  if (front_mode == 0) {
+  if ((front_mode == 3 || rrt::g_crmsa_front_cluster) && !tr.tape) {
+    // experimental (off by default): one cluster kernel, x1 read once; falls through when not supported
+    StageScope s_(kStCrCombine, st);
+    cudaError_t e = s_.skip() ? cudaSuccess
+                              : rrt::launch_crmsa_front_cluster(x1, w->cr_norm_w, w->cr_norm_b, phi, ws.stats,
+                                                                ws.logits, ws.lm, ws.rstat, g, D, k, st);
+    if (e == cudaSuccess) front_done = true;
+    else if (e != cudaErrorNotSupported) return fail_cuda(e, "crmsa front (cluster)");
+  }
+  if (!front_done && (front_mode == 0 || front_mode == 3)) {
     StageScope s_(kStCrCombine, st, 2);
     cudaError_t e = s_.skip() ? cudaSuccess
                               : rrt::launch_crmsa_front_split(x1, w->cr_norm_w, w->cr_norm_b, phi, ws.stats,
@@ -977,9 +986,13 @@ RRT_API int rrt_debug_skip_stages(uint32_t mask) {
 }
 
 RRT_API int rrt_debug_set_gemm_cluster(int32_t mode) {
+  if (mode == 5 || mode == 50) {  // experimental cluster CR-MSA front end on / off
+    rrt::g_crmsa_front_cluster = mode == 5;
+    return RRT_OK;
+  }
   if (mode != 2 && mode != 3 && mode != 4 && mode != 30 && mode != 22 && mode != 21 && mode != 11 && mode != 128 &&
       mode != 256)
-    return fail(RRT_E_INVALID, "mode must be 2, 3, 4, 30, 11, 21, 22, 128 or 256");
+    return fail(RRT_E_INVALID, "mode must be 2, 3, 4, 30, 5, 50, 11, 21, 22, 128 or 256");
   rrt::set_gemm_cluster_mode(mode);
   return RRT_OK;
 }

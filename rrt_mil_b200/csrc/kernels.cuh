@@ -120,6 +120,13 @@ cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const 
                                      const float* phi, float2* stats, float* logits,
                                      __half* landmarks, float2* rstat, const Grid& grid, int D, int k,
                                      cudaStream_t stream);
+// EXPERIMENTAL (off by default): the same front end as ONE kernel on clusters of D/128 CTAs per region: every
+// CTA reads its 128-column slab of x1 once into shared memory, the per-row partial sums are exchanged through
+// distributed shared memory.  cudaErrorNotSupported (crmsa_mlp logits, P > 256, D > 1024): use the split path.
+extern int g_crmsa_front_cluster;  // rrt_debug_set_gemm_cluster(5) on / (50) off; RRT_CRMSA_FRONT=cluster
+cudaError_t launch_crmsa_front_cluster(const float* x1, const float* gamma, const float* beta,
+                                       const float* phi, float2* stats, float* logits, __half* landmarks,
+                                       float2* rstat, const Grid& grid, int D, int k, cudaStream_t stream);
 // MHA core over the landmarks: batch = k, sequence = R (64), heads, head_dim = D/heads, plain
 // softmax(q k^T * scale) v, fp32 math.  lqkv: [k*R, 3D] fp32 rows (n, rho); lo: [k*R, D] f16.
 cudaError_t launch_landmark_attention(const float* lqkv, __half* lo, int k, int R, int D, int heads,

@@ -12,6 +12,11 @@ echo "default parity rc=$?"
 RRT_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
   -k experimental_fused > gpurun_out/r2a_tests_fused.log 2>&1
 echo "fused parity rc=$?"
+RRT_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
+  -k experimental_cluster > gpurun_out/r2a_tests_cluster_front.log 2>&1
+echo "cluster CR-MSA front parity rc=$?"
+RRT_CRMSA_FRONT=cluster timeout 200 python tools/stage_probe.py > gpurun_out/r2a_stage_probe_cluster_front.log 2>&1
+timeout 200 python tools/stage_probe.py > gpurun_out/r2a_stage_probe_default.log 2>&1
 # 2b. CUDA-graph replay of the forward (rrt_mil_b200/graph.py)
 RRT_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_graph.py -m gpu -x -q > gpurun_out/r2a_tests_graph.log 2>&1
 echo "graph replay rc=$?"
