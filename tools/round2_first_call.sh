@@ -1,7 +1,8 @@
 #!/usr/bin/env bash
-# First GPU call of the next round: verify and measure the experimental LayerNorm-fused QKV GEMM
-#  before anything is built on it.  Run from the repo root on the GPU box:
-#   gpurun --timeout 900 -- 'bash tools/round2_first_call.sh'
+# First GPU call of the next round: verify and measure the code written after round 1's GPU budget was spent
+# (fused LN+QKV GEMM single-CTA / CTA-pair, cluster CR-MSA front end, CUDA-graph replay)
+# before anything is built on it.  Run from the repo root on the GPU box:
+#   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'   (typically ~6 min; every step has its own timeout)
 # Every step runs under its own timeout (a pipeline bug traps after ~2 s of SM clocks, it does not hang).
 set -u
 mkdir -p gpurun_out
