@@ -21,6 +21,8 @@ timeout 200 python tools/stage_probe.py > gpurun_out/r2a_stage_probe_default.log
 # 2b. CUDA-graph replay of the forward (rrt_mil_b200/graph.py)
 RRT_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_graph.py -m gpu -x -q > gpurun_out/r2a_tests_graph.log 2>&1
 echo "graph replay rc=$?"
+timeout 200 python tools/graph_probe.py > gpurun_out/r2a_graph_probe.log 2>&1
+echo "graph probe rc=$?"
 # 3. A/B: stage times, us/bag per lane count, phase trace
 timeout 300 python tools/fused_qkv_probe.py --trace > gpurun_out/r2a_fused_probe.log 2>&1
 echo "probe rc=$?"
