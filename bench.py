@@ -411,6 +411,11 @@ def run_b200_arm(args):
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
         }
+        # non-default kernel variants selected through the environment make the line self-describing
+        knobs = {k: v for k, v in os.environ.items()
+                 if k.startswith("RRT_") and k not in ("RRT_EXPERIMENTAL",)}
+        if knobs:
+            line["config"]["tuning_knobs"] = knobs
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = time_cpu_baseline()
         print(json.dumps(line), flush=True)
