@@ -202,11 +202,7 @@ RRT_API int rrt_debug_set_attention_kernel(int32_t use_tcgen05);
 /* Debug / tuning: kernel variant of the bag-sized tcgen05 GEMMs.  11 = single-CTA 128x256 tiles
  * (default, fastest at these sizes); 2 = CTA pairs (cta_group::2, M=256 tiles); 21 / 22 = single-CTA
  * tiles with 2x1 / 2x2 cluster TMA multicast; 128 / 256 = tile width of the GEMMs that have at most one
- * 256-column tile per CTA (proj; default 256).  Results do not depend on it.
- * 3 / 4 / 30 = EXPERIMENTAL LayerNorm-fused QKV GEMM with a resident A tile: single-CTA / CTA-pair form / off
- * (default off, also RRT_QKV_FUSED_LN=1|2; inference forward only; results agree within the parity tolerance,
- * not bit for bit).  5 / 50 = EXPERIMENTAL one-kernel CR-MSA front end on thread-block clusters (DSMEM exchange
- * of the row statistics) on / off (default off, also RRT_CRMSA_FRONT=cluster; same caveats). */
+ * 256-column tile per CTA (proj; default 256).  Results do not depend on it. */
 RRT_API int rrt_debug_set_gemm_cluster(int32_t mode);
 
 /* Debug / measurement only: bit i set = the kernels of stage i (rrt_stage_name order) are NOT launched.

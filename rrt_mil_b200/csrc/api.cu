@@ -332,17 +332,10 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
   if (rc) return rc;
   rrt::GemmEpilogue e1;
   e1.bias = c->qkv_bias ? a->qkv_b : nullptr;
-  if (rrt::g_qkv_fused_ln && !tr.tape && rrt::gemm_lnqkv_supported(g, D, 3 * D)) {
-    // experimental (off by default): LayerNorm + partition fused into the QKV GEMM, z never exists
-    StageScope s_(kStQkvGemm, st);
-    if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_lnqkv_tcgen05(x, norm_w, norm_b, g, wq, e1.bias, ws_qkv, D, 3 * D, st),
-                             "ln + qkv gemm (fused)");
-  } else {
-    { StageScope s_(kStLnPartition, st);
-      if (!s_.skip()) RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws_z, g, D, st), "ln_partition"); }
-    { StageScope s_(kStQkvGemm, st);
-      if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws_z, wq, ws_qkv, true, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
-  }
+  { StageScope s_(kStLnPartition, st);
+    if (!s_.skip()) RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws_z, g, D, st), "ln_partition"); }
+  { StageScope s_(kStQkvGemm, st);
+    if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws_z, wq, ws_qkv, true, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
   { StageScope s_(kStRmsaAttn, st);
     const float* taps = c->epeg ? a->pe_w : nullptr;
     if (s_.skip()) {
@@ -398,21 +391,12 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   rc = f16_weight(w->cr_attn.proj_w, w->cr_attn.proj_w_f16, ws.wconv + (size_t)3 * D * D,
                   (size_t)D * D, st, &wp);
   if (rc) return rc;
-  static const int front_mode = [] {  // tuning knob: RRT_CRMSA_FRONT=split (default) | fused | legacy | cluster
+  static const int front_mode = [] {  // tuning knob: RRT_CRMSA_FRONT=split (default) | fused | legacy
     const char* e = getenv("RRT_CRMSA_FRONT");
-    return !e ? 0 : (!strcmp(e, "fused") ? 1 : (!strcmp(e, "legacy") ? 2 : (!strcmp(e, "cluster") ? 3 : 0)));
+    return !e ? 0 : (!strcmp(e, "fused") ? 1 : (!strcmp(e, "legacy") ? 2 : 0));
   }();
   bool front_done = false;
-  if ((front_mode == 3 || rrt::g_crmsa_front_cluster) && !tr.tape) {
-    // experimental (off by default): one cluster kernel, x1 read once; falls through when not supported
-    StageScope s_(kStCrCombine, st);
-    cudaError_t e = s_.skip() ? cudaSuccess
-                              : rrt::launch_crmsa_front_cluster(x1, w->cr_norm_w, w->cr_norm_b, phi, ws.stats,
-                                                                ws.logits, ws.lm, ws.rstat, g, D, k, st);
-    if (e == cudaSuccess) front_done = true;
-    else if (e != cudaErrorNotSupported) return fail_cuda(e, "crmsa front (cluster)");
-  }
-  if (!front_done && (front_mode == 0 || front_mode == 3)) {
+  if (front_mode == 0) {
     StageScope s_(kStCrCombine, st, 2);
     cudaError_t e = s_.skip() ? cudaSuccess
                               : rrt::launch_crmsa_front_split(x1, w->cr_norm_w, w->cr_norm_b, phi, ws.stats,
@@ -986,13 +970,8 @@ RRT_API int rrt_debug_skip_stages(uint32_t mask) {
 }
 
 RRT_API int rrt_debug_set_gemm_cluster(int32_t mode) {
-  if (mode == 5 || mode == 50) {  // experimental cluster CR-MSA front end on / off
-    rrt::g_crmsa_front_cluster = mode == 5;
-    return RRT_OK;
-  }
-  if (mode != 2 && mode != 3 && mode != 4 && mode != 30 && mode != 22 && mode != 21 && mode != 11 && mode != 128 &&
-      mode != 256)
-    return fail(RRT_E_INVALID, "mode must be 2, 3, 4, 30, 5, 50, 11, 21, 22, 128 or 256");
+  if (mode != 2 && mode != 22 && mode != 21 && mode != 11 && mode != 128 && mode != 256)
+    return fail(RRT_E_INVALID, "mode must be 2, 11, 21, 22, 128 or 256");
   rrt::set_gemm_cluster_mode(mode);
   return RRT_OK;
 }

@@ -416,216 +416,6 @@ __global__ void __launch_bounds__(256) crmsa_combine2_kernel(
 }
 
 // ------------------------------------------------------------------------------------------
-// CR-MSA front end as ONE kernel on thread-block clusters (EXPERIMENTAL: RRT_CRMSA_FRONT=cluster or
-// rrt_debug_set_gemm_cluster(5) / (50); written after the round's GPU budget was spent, not yet run on a B200).
-// Cluster = the D/128 CTAs of one region, CTA = (region, 128-column slab), grid as crmsa_combine2_kernel.
-// Each CTA reads ITS slab of the region's rows from global memory exactly once and keeps it in shared memory
-// (P x 128 fp32 = 72 KB at P = 144); the per-row partial sums (sum x, the k dot products with G = gamma*phi,
-// then sum (x - mean)^2) are exchanged between the CTAs of the cluster through distributed shared memory and
-// added in rank order by every CTA, so all of them hold bit-identical statistics and logits.  The region
-// softmax and the folded combine then run from shared memory as in crmsa_combine2_kernel.
-// One launch and one pass over x1 instead of two of each (crmsa_rowstats_kernel + crmsa_combine2_kernel).
-__device__ __forceinline__ void cluster_sync_all_threads() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// element at the same shared-memory offset as `local` in CTA `rank` of the cluster
-__device__ __forceinline__ float ld_dsmem(const float* local, uint32_t rank) {
-  uint32_t a = (uint32_t)__cvta_generic_to_shared(local), ra;
-  float v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
-  return v;
-}
-
-// grid (D/128, R) in clusters of (D/128, 1, 1), 256 threads, P <= 256.
-// smem (floats): xs[P][128] | Gs[KMAX][128] | part[P][1+KMAX] | part2[P] | wq[P][KMAX] | tok[P] | meanv[P] |
-//                rstdv[P] | red[8][KMAX][128] | s01[2][KMAX] | AB[2][KMAX]
-template <int KMAX>
-__global__ void __launch_bounds__(256) crmsa_front_cluster_kernel(
-    const float* __restrict__ x1, const float* __restrict__ gamma, const float* __restrict__ beta,
-    const float* __restrict__ phi, float2* __restrict__ stats, float* __restrict__ logits,
-    __half* __restrict__ landmarks, float2* __restrict__ rstat, Grid grid, int D, int k) {
-  extern __shared__ __align__(16) float smem[];
-  constexpr int PW = 1 + KMAX;
-  const int P = grid.P, P4 = (P + 3) & ~3, rho = blockIdx.y, chunk = blockIdx.x, C = gridDim.x;
-  float* xs = smem;                                   // [P][128]
-  float* Gs = xs + (size_t)P * 128;                   // [KMAX][128]
-  float* part = Gs + KMAX * 128;                      // [P][PW]   (read by the peers)
-  float* part2 = part + (size_t)P4 * PW;              // [P]       (read by the peers)
-  float* wq = part2 + P4;                             // [P][KMAX]
-  int* tok = reinterpret_cast<int*>(wq + (size_t)P4 * KMAX);
-  float* meanv = reinterpret_cast<float*>(tok + P4);
-  float* rstdv = meanv + P4;
-  float* red = rstdv + P4;                            // [8][KMAX][128]
-  float* s01 = red + 8 * KMAX * 128;                  // [2][KMAX]
-  float* AB = s01 + 2 * KMAX;                         // [2][KMAX]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int c0 = chunk * 128 + lane * 4;
-  pdl_launch_dependents();
-  // weights only (ahead of the predecessor's completion): my slab of G, and A[n], B[n] over ALL columns
-  for (int i = tid; i < KMAX * 128; i += 256) {
-    const int n = i >> 7, c = chunk * 128 + (i & 127);
-    Gs[i] = n < k ? __ldg(gamma + c) * __ldg(phi + (size_t)c * k + n) : 0.f;
-  }
-  for (int n = warp; n < KMAX; n += 8) {
-    float a = 0.f, b = 0.f;
-    if (n < k)
-      for (int c = lane; c < D; c += 32) {
-        const float ph = __ldg(phi + (size_t)c * k + n);
-        a = fmaf(__ldg(gamma + c), ph, a);
-        b = fmaf(__ldg(beta + c), ph, b);
-      }
-    a = warp_sum(a);
-    b = warp_sum(b);
-    if (lane == 0) { AB[n] = a; AB[KMAX + n] = b; }
-  }
-  for (int p = tid; p < P; p += 256) {
-    const int t = grid.slot_to_token(rho * P + p);
-    tok[p] = t < grid.L ? t : -1;
-  }
-  __syncthreads();
-  pdl_wait();
-
-  // ---- pass over global memory: slab -> shared memory, per-row partial sums of my 128 columns -------------
-  constexpr int U = 9;  // rows in flight per warp (P = 144: two batches per warp)
-  for (int p0 = warp; p0 < P; p0 += 8 * U) {
-    float4 xv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = p0 + 8 * u;
-      const int t = p < P ? tok[p] : -1;
-      xv[u] = t >= 0 ? __ldg(reinterpret_cast<const float4*>(x1 + (size_t)t * D + c0))
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = p0 + 8 * u;
-      if (p >= P) break;
-      *reinterpret_cast<float4*>(xs + (size_t)p * 128 + lane * 4) = xv[u];
-      float r[PW];
-      r[0] = (xv[u].x + xv[u].y) + (xv[u].z + xv[u].w);
-#pragma unroll
-      for (int n = 0; n < KMAX; ++n) {
-        const float4 gq = *reinterpret_cast<const float4*>(Gs + n * 128 + lane * 4);
-        float d = xv[u].x * gq.x;
-        d = fmaf(xv[u].y, gq.y, d); d = fmaf(xv[u].z, gq.z, d); d = fmaf(xv[u].w, gq.w, d);
-        r[1 + n] = d;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int j = 0; j < PW; ++j) r[j] += __shfl_xor_sync(0xffffffffu, r[j], o);
-      float mine = 0.f;
-#pragma unroll
-      for (int j = 0; j < PW; ++j)
-        if (lane == j) mine = r[j];
-      if (lane < PW) part[(size_t)p * PW + lane] = mine;
-    }
-  }
-  cluster_sync_all_threads();  // #1: every CTA's part[] is complete and visible cluster-wide
-
-  // ---- row totals in rank order (identical in every CTA of the cluster) ----------------------------------
-  float tot[PW];
-#pragma unroll
-  for (int j = 0; j < PW; ++j) tot[j] = 0.f;
-  const bool owns_row = tid < P;
-  if (owns_row) {
-    for (int r = 0; r < C; ++r)
-#pragma unroll
-      for (int j = 0; j < PW; ++j) tot[j] += ld_dsmem(part + (size_t)tid * PW + j, (uint32_t)r);
-    meanv[tid] = tok[tid] >= 0 ? tot[0] / (float)D : 0.f;
-  }
-  __syncthreads();
-  for (int p = warp; p < P; p += 8) {  // centred sum of squares of my slab (two-pass variance)
-    const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)p * 128 + lane * 4);
-    const float m = meanv[p];
-    const float a = v.x - m, b = v.y - m, c = v.z - m, d = v.w - m;
-    const float q = warp_sum((a * a + b * b) + (c * c + d * d));
-    if (lane == 0) part2[p] = tok[p] >= 0 ? q : 0.f;
-  }
-  cluster_sync_all_threads();  // #2: part2[] complete and visible
-
-  if (owns_row) {
-    const int slot = rho * P + tid;
-    float q = 0.f;
-    for (int r = 0; r < C; ++r) q += ld_dsmem(part2 + tid, (uint32_t)r);
-    const bool real = tok[tid] >= 0;
-    const float mean = meanv[tid];
-    const float rstd = real ? rsqrtf(q / (float)D + kLnEps) : 0.f;  // rstd = 0 marks a zero pad slot
-    rstdv[tid] = rstd;
-    if (chunk == 0) stats[slot] = make_float2(mean, rstd);
-#pragma unroll
-    for (int n = 0; n < KMAX; ++n) {
-      const float lg = (real && n < k) ? rstd * (tot[1 + n] - mean * AB[n]) + AB[KMAX + n] : 0.f;
-      wq[(size_t)tid * KMAX + n] = lg;
-      if (chunk == 0 && n < k) logits[(size_t)slot * k + n] = lg;
-    }
-  }
-  __syncthreads();
-
-  // ---- per landmark: softmax over the region, min, max; w' = cw * rstd, S0, S1 (as crmsa_combine2_kernel) --
-  for (int n = warp; n < k; n += 8) {
-    float mx = -INFINITY, mn = INFINITY;
-    for (int p = lane; p < P; p += 32) {
-      const float v = wq[(size_t)p * KMAX + n];
-      mx = fmaxf(mx, v);
-      mn = fminf(mn, v);
-    }
-    mx = warp_max(mx);
-    mn = warp_min(mn);
-    float sum = 0.f;
-    for (int p = lane; p < P; p += 32) sum += __expf(wq[(size_t)p * KMAX + n] - mx);
-    const float inv = 1.f / warp_sum(sum);
-    float s0 = 0.f, s1 = 0.f;
-    for (int p = lane; p < P; p += 32) {
-      const float cw = __expf(wq[(size_t)p * KMAX + n] - mx) * inv;
-      const float rs = rstdv[p];
-      const float w = cw * rs;
-      wq[(size_t)p * KMAX + n] = w;
-      if (rs != 0.f) s0 += cw;
-      s1 = fmaf(w, meanv[p], s1);
-    }
-    s0 = warp_sum(s0);
-    s1 = warp_sum(s1);
-    if (lane == 0) {
-      s01[n] = s0;
-      s01[KMAX + n] = s1;
-      if (chunk == 0) rstat[(size_t)rho * k + n] = make_float2(mn, mx);
-    }
-  }
-  __syncthreads();
-
-  // ---- folded combine from the shared-memory slab ----------------------------------------------------------
-  float4 acc[KMAX];
-#pragma unroll
-  for (int n = 0; n < KMAX; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p = warp; p < P; p += 8) {
-    const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)p * 128 + lane * 4);
-#pragma unroll
-    for (int n = 0; n < KMAX; ++n) {
-      const float wgt = wq[(size_t)p * KMAX + n];
-      acc[n].x = fmaf(wgt, xv.x, acc[n].x); acc[n].y = fmaf(wgt, xv.y, acc[n].y);
-      acc[n].z = fmaf(wgt, xv.z, acc[n].z); acc[n].w = fmaf(wgt, xv.w, acc[n].w);
-    }
-  }
-#pragma unroll
-  for (int n = 0; n < KMAX; ++n)
-    *reinterpret_cast<float4*>(red + ((size_t)(warp * KMAX + n)) * 128 + lane * 4) = acc[n];
-  __syncthreads();
-  for (int i = tid; i < k * 128; i += 256) {
-    const int n = i >> 7, c = i & 127;
-    float sacc = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) sacc += red[((size_t)(w * KMAX + n)) * 128 + c];
-    const int gc = chunk * 128 + c;
-    const float val = __ldg(gamma + gc) * (sacc - s01[KMAX + n]) + __ldg(beta + gc) * s01[n];
-    landmarks[((size_t)n * grid.R + rho) * D + gc] = __float2half_rn(val);
-  }
-  cluster_sync_all_threads();  // #3: no CTA exits while a peer may still read its part2[]
-}
-
-// ------------------------------------------------------------------------------------------
 // Fused CR-MSA front end, one CTA per region (16 warps), two passes over the region's rows (which
 // are L2-resident: the projection GEMM has just written them):
 //   pass 1  warp per row, 3 rows in flight: LayerNorm statistics and the k logits from ONE batched
@@ -1206,46 +996,6 @@ cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const 
 #undef RRT_C2
   }
   return cudaGetLastError();
-}
-
-// EXPERIMENTAL cluster front end (one launch, x1 read once); cudaErrorNotSupported -> caller uses the split path.
-int g_crmsa_front_cluster = 0;  // rrt_debug_set_gemm_cluster(5) on / (50) off; RRT_CRMSA_FRONT=cluster
-cudaError_t launch_crmsa_front_cluster(const float* x1, const float* gamma, const float* beta,
-                                       const float* phi, float2* stats, float* logits, __half* landmarks,
-                                       float2* rstat, const Grid& grid, int D, int k, cudaStream_t stream) {
-  if (D % 128 || k < 1 || k > RRT_MAX_K_DEV) return cudaErrorInvalidValue;
-  const int C = D / 128;
-  if (!phi || C > 8 || grid.P > 256 || grid.P < 1) return cudaErrorNotSupported;
-  const int KM = k <= 4 ? 4 : (k <= 8 ? 8 : 16);
-  const size_t P = grid.P, P4 = (P + 3) & ~(size_t)3;
-  const size_t smem = (P * 128 + (size_t)KM * 128 + P4 * (1 + KM) + P4 + P4 * KM + 3 * P4 +
-                       (size_t)8 * KM * 128 + 4 * KM) * sizeof(float);
-  if (smem > 227 * 1024) return cudaErrorNotSupported;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(C, grid.R);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = C;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-#define RRT_FC(KK)                                                                                        \
-  {                                                                                                       \
-    static DeviceOnce configured;                                                                         \
-    if (configured.needed()) {                                                                            \
-      cudaError_t e = cudaFuncSetAttribute(crmsa_front_cluster_kernel<KK>,                                \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      \
-      if (e != cudaSuccess) return e;                                                                     \
-    }                                                                                                     \
-    return cudaLaunchKernelEx(&cfg, crmsa_front_cluster_kernel<KK>, x1, gamma, beta, phi, stats, logits,  \
-                              landmarks, rstat, grid, D, k);                                              \
-  }
-  if (KM == 4) RRT_FC(4) else if (KM == 8) RRT_FC(8) else RRT_FC(16)
-#undef RRT_FC
 }
 
 cudaError_t launch_landmark_attention(const float* lqkv, __half* lo, int k, int R, int D, int heads,

@@ -594,391 +594,6 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// LayerNorm-fused QKV projection with a RESIDENT A tile.  EXPERIMENTAL: off by
-// default (RRT_QKV_FUSED_LN=1 or rrt_debug_set_gemm_cluster(3)), inference only (the training tape keeps z).
-//   qkv[slot, :] = LN(x[token(slot), :]) @ Wqkv^T + b      (modules/rrt.py:123 + modules/rmsa.py:199-215,94)
-// Why: the bag-sized main loop above is operand-ingest bound (48 KB of A + W per 64-deep k-block at
-// ~67 B/clk/SM), and ln_partition + the z round trip cost another HBM pass.  Here a CTA owns one 128-row
-// M tile for ALL the N tiles of its share: the 8 epilogue warps LayerNorm its 128 rows straight from the
-// fp32 residual stream into shared memory in the K-major SWIZZLE_128B layout tcgen05.mma expects (what TMA
-// would have written from z), once; after that only W streams (16 KB per k-block per 128 x 128 tile).
-//   warp 0       W producer (TMA, 4-stage ring of 128 x 64 tiles; runs ahead across work items)
-//   warp 1       MMA issuer (M128 N128 K16; A descriptors point into the resident tile)
-//   warp 2       TMEM allocator (2 x 128 columns)
-//   warps 4..11  per work item: LN fill of 16 rows each -> fence.proxy.async -> a_full; then the ordinary
-//                epilogue of every tile (epilogue_tile, TMA stores).  The refill for the next work item starts
-//                after the warp's epilogue of the LAST tile, whose tfull wait proves every MMA that read A is done.
-// Shared memory: 8 x 16 KB (A, K <= 512) + 4 x 16 KB (W) + 32 KB (epilogue staging) = 224 KB.
-constexpr int LQ_BN = 128, LQ_STAGES = 4, LQ_KB_MAX = 8;
-constexpr int LQ_B_BYTES = LQ_BN * BK * 2;
-constexpr int LQ_SMEM_BYTES = 1024 + LQ_KB_MAX * A_BYTES + LQ_STAGES * LQ_B_BYTES + EPI_BYTES + BAR_BYTES;
-static_assert(LQ_SMEM_BYTES <= 227 * 1024, "dynamic shared memory budget exceeded");
-
-struct LnFillParams {
-  const float* x;      // [grid.L, K] fp32 residual stream, token order
-  const float* gamma;  // [K]
-  const float* beta;   // [K]
-  int nsplit;          // the N tiles of an M tile are shared by nsplit work items (divides N / 128)
-};
-
-// LayerNorm of rows [16 ew, 16 ew + 16) of the M tile at m0 into the resident A tile.  Lane l owns the 8
-// consecutive columns 8 l + 256 j (j < V2): k-block 4 j + l / 8, 16-byte chunk l % 8 of the 128-byte row
-// segment; a quarter warp writes one whole 128-byte segment per store phase (no bank conflicts).
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-template <int V2>
-__device__ __forceinline__ void ln_fill_rows(const Tc05Params& p, const LnFillParams& f, uint8_t* sA, int m0,
-                                             int ew, int lane) {
-  constexpr int D = 256 * V2;
-  constexpr float inv_d = 1.f / D;
-  const int kb_l = lane >> 3, chunk = lane & 7;
-  const uint32_t sA_u32 = smem_u32(sA);
-  // LayerNorm affine parameters of this lane's columns (8 x 16 B from L1 / L2 per work item: cheaper than
-  // keeping 32 registers alive across the epilogue)
-  float4 gm[2 * V2], bt[2 * V2];
-#pragma unroll
-  for (int i = 0; i < 2 * V2; ++i) {
-    gm[i] = __ldg(reinterpret_cast<const float4*>(f.gamma) + 2 * lane + 64 * (i >> 1) + (i & 1));
-    bt[i] = __ldg(reinterpret_cast<const float4*>(f.beta) + 2 * lane + 64 * (i >> 1) + (i & 1));
-  }
-#pragma unroll 1
-  for (int rb = 0; rb < 16; rb += 4) {
-    float4 v[4][2 * V2];
-    int tok[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {  // 4 rows in flight per warp: 4 x 2 KB of independent 16-byte loads
-      const int slot = m0 + ew * 16 + rb + q;
-      int t = -1;
-      if (slot < p.M) {
-        const int tt = p.grid.slot_to_token(slot);
-        if (tt < p.grid.L) t = tt;
-      }
-      tok[q] = t;
-      if (t >= 0) {
-        const float4* xr = reinterpret_cast<const float4*>(f.x + (size_t)t * D);
-#pragma unroll
-        for (int j = 0; j < V2; ++j) {
-          v[q][2 * j] = __ldg(xr + 2 * lane + 64 * j);
-          v[q][2 * j + 1] = __ldg(xr + 2 * lane + 64 * j + 1);
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int r = ew * 16 + rb + q;
-      const uint32_t rowp = sA_u32 + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4);
-      if (tok[q] < 0) {  // pad slot (or a row past the last slot): exact zeros AFTER the norm
-#pragma unroll
-        for (int j = 0; j < V2; ++j) sts128(rowp + (4 * j + kb_l) * A_BYTES, 0u, 0u, 0u, 0u);
-        continue;
-      }
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 2 * V2; ++i) s += (v[q][i].x + v[q][i].y) + (v[q][i].z + v[q][i].w);
-      const float mean = warp_sum(s) * inv_d;
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < 2 * V2; ++i) {
-        const float a = v[q][i].x - mean, b = v[q][i].y - mean, c = v[q][i].z - mean, d = v[q][i].w - mean;
-        ss += (a * a + b * b) + (c * c + d * d);
-      }
-      const float rstd = rsqrtf(warp_sum(ss) * inv_d + kLnEps);
-#pragma unroll
-      for (int j = 0; j < V2; ++j) {
-        uint32_t h[4];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const float4 xv = v[q][2 * j + u], g4 = gm[2 * j + u], b4 = bt[2 * j + u];
-          h[2 * u] = pack_h2((xv.x - mean) * rstd * g4.x + b4.x, (xv.y - mean) * rstd * g4.y + b4.y);
-          h[2 * u + 1] = pack_h2((xv.z - mean) * rstd * g4.z + b4.z, (xv.w - mean) * rstd * g4.w + b4.w);
-        }
-        sts128(rowp + (4 * j + kb_l) * A_BYTES, h[0], h[1], h[2], h[3]);
-      }
-    }
-  }
-}
-
-template <int V2>  // K = 256 * V2
-__global__ void __launch_bounds__(NTHREADS, 1)
-gemm_lnqkv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                          Tc05Params p, LnFillParams f) {
-  constexpr int BN = LQ_BN, STAGES = LQ_STAGES, KB = 4 * V2;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint8_t* sA = smem;                                  // [KB][128 x 64] resident LN(x) tile
-  uint8_t* sB = smem + LQ_KB_MAX * A_BYTES;            // [STAGES][128 x 64] W ring
-  float* sEpi = reinterpret_cast<float*>(sB + STAGES * LQ_B_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* afull = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) stamp(p, 0);
-  pdl_launch_dependents();
-
-  if (warp == 0 && lane == 0) prefetch_tensormap(&tmB);
-  if (warp == 2 && lane == 0) prefetch_tensormap(&tmC);
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);   // the W producer (+ its bytes)
-      mbar_init(&empty[i], 1);  // MMA commit
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kEpiWarps);
-    }
-    mbar_init(afull, kEpiWarps);  // one arrive per fill warp and work item
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 2 * BN);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) stamp(p, 1);
-  pdl_wait();
-
-  // work item wi = (M tile wi / nsplit, N share wi % nsplit): the items of one M tile are neighbours, so
-  // the CTAs that LayerNorm the same rows read them at the same time (one HBM read, L2 hits for the rest)
-  const int tiles_m = (p.M + BM - 1) / BM;
-  const int tpp = (p.N / BN) / f.nsplit;  // N tiles per work item
-  const int num_items = tiles_m * f.nsplit;
-
-  if (warp == 0) {
-    if (lane == 0) {  // ===== W producer =====
-      int s = 0, ph = 0;
-      for (int wi = blockIdx.x; wi < num_items; wi += gridDim.x) {
-        const int part = wi % f.nsplit;
-        for (int nt = 0; nt < tpp; ++nt) {
-          const int n0 = (part * tpp + nt) * BN;
-          for (int kb = 0; kb < KB; ++kb) {
-            mbar_wait(&empty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full[s], LQ_B_BYTES);
-            tma_load_2d(sB + s * LQ_B_BYTES, &tmB, &full[s], kb * BK, n0);
-            if (wi == (int)blockIdx.x && nt == 0 && kb == 0) stamp(p, 2);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc(kFmtF16, BM, BN);
-      int s = 0, ph = 0, acc = 0, aph = 0, item = 0;
-      for (int wi = blockIdx.x; wi < num_items; wi += gridDim.x, ++item) {
-        mbar_wait(afull, item & 1);  // the resident A tile of this work item is in shared memory
-        tc_fence_after();
-        if (item == 0) stamp(p, 3);
-        for (int nt = 0; nt < tpp; ++nt) {
-          mbar_wait(&tempty[acc], aph ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
-          for (int kb = 0; kb < KB; ++kb) {
-            mbar_wait(&full[s], ph);
-            tc_fence_after();
-            if (item == 0 && nt == 0 && kb == 0) stamp(p, 4);
-            const uint64_t ad = umma_desc_k_sw128(smem_u32(sA + kb * A_BYTES));
-            const uint64_t bd = umma_desc_k_sw128(smem_u32(sB + s * LQ_B_BYTES));
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-            umma_commit(&empty[s]);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
-          }
-          umma_commit(&tfull[acc]);
-          if (++acc == 2) { acc = 0; aph ^= 1; }
-        }
-      }
-      stamp(p, 5);
-    }
-    __syncwarp();
-  } else if (warp >= 4) {  // ===== LN fill + epilogue =====
-    const int ew = warp - 4;
-    float* scratch = sEpi + ew * 32 * EPI_LD;
-    int acc = 0, aph = 0;
-    for (int wi = blockIdx.x; wi < num_items; wi += gridDim.x) {
-      const int m0 = (wi / f.nsplit) * BM, part = wi % f.nsplit;
-      // (not the first item: this warp's epilogue of the previous item's last tile has waited on that tile's
-      // tfull barrier, i.e. every MMA that read the old A tile has completed)
-      ln_fill_rows<V2>(p, f, sA, m0, ew, lane);
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(afull);
-      for (int nt = 0; nt < tpp; ++nt) {
-        const int n0 = (part * tpp + nt) * BN;
-        uint64_t* te = &tempty[acc];
-        epilogue_tile<kEpiStore, BN, __half>(p, &tmC, tmem_base + acc * BN, &tfull[acc], aph, m0, n0, ew, lane,
-                                             scratch, wi == (int)blockIdx.x && nt == 0,
-                                             [&] { if (lane == 0) mbar_arrive(te); });
-        if (++acc == 2) { acc = 0; aph ^= 1; }
-        if (threadIdx.x == 128) stamp(p, wi == (int)blockIdx.x && nt == 0 ? 7 : 8);
-      }
-    }
-  }
-
-  if (warp >= 4 && lane == 0) tma_store_wait_all<0>();
-  tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0) stamp(p, 9);
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
-  }
-}
-
-// CTA-pair form of the kernel above (EXPERIMENTAL, RRT_QKV_FUSED_LN=2 or
-// rrt_debug_set_gemm_cluster(4)): the two CTAs of a cluster own 256 rows (each LayerNorms and keeps ITS 128) and
-// compute 256 x 256 tiles with cta_group::2 MMAs issued by the leader; each CTA streams only HALF of a W tile
-// (128 x 64 = 16 KB per k-block, the same bytes as the single-CTA kernel's whole 128-column tile), so the operand
-// ingest per MAC halves once more (32 B/clk/SM when MMA-bound).  Barrier placement follows
-// gemm_f16_tcgen05_2cta_kernel: full / tempty / afull live on the LEADER (the peer arrives remotely; TMA bytes of
-// both CTAs are accounted there), empty / tfull are multicast commits to both CTAs.
-template <int V2>  // K = 256 * V2
-__global__ void __launch_bounds__(NTHREADS, 1)
-gemm_lnqkv_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                               Tc05Params p, LnFillParams f) {
-  constexpr int BN = 256, STAGES = LQ_STAGES, KB = 4 * V2;
-  constexpr int BHALF_BYTES = (BN / 2) * BK * 2;  // == LQ_B_BYTES
-  static_assert(BHALF_BYTES == LQ_B_BYTES, "the W ring is sized for 16 KB stages");
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint8_t* sA = smem;                        // [KB][128 x 64] my 128 rows of LN(x), resident
-  uint8_t* sB = smem + LQ_KB_MAX * A_BYTES;  // [STAGES][128 x 64] my half of the W tile
-  float* sEpi = reinterpret_cast<float*>(sB + STAGES * BHALF_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + EPI_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* afull = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
-  if (threadIdx.x == 0) stamp(p, 0);
-
-  if (warp == 0 && lane == 0) prefetch_tensormap(&tmB);
-  if (warp == 2 && lane == 0) prefetch_tensormap(&tmC);
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);   // leader only: its W producer arms the bytes of BOTH halves
-      mbar_init(&empty[i], 1);  // both CTAs: multicast commit of the leader's MMA warp
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);               // both CTAs: multicast commit
-      mbar_init(&tempty[i], 2 * kEpiWarps);  // leader only: the epilogue warps of both CTAs
-    }
-    mbar_init(afull, 2 * kEpiWarps);         // leader only: the fill warps of both CTAs
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc_2cta(tmem_slot, 2 * BN);
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) stamp(p, 1);
-
-  // work item wi = (pair M tile wi / nsplit, N share wi % nsplit) with 256-row / 256-column tiles
-  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  const int tiles_m2 = (p.M + 2 * BM - 1) / (2 * BM);
-  const int tpp = (p.N / BN) / f.nsplit;
-  const int num_items = tiles_m2 * f.nsplit;
-
-  if (warp == 0) {
-    if (lane == 0) {  // ===== W producer (both CTAs: my half of every W tile) =====
-      int s = 0, ph = 0;
-      for (int wi = pair_id; wi < num_items; wi += num_pairs) {
-        const int part = wi % f.nsplit;
-        for (int nt = 0; nt < tpp; ++nt) {
-          const int n0 = (part * tpp + nt) * BN + (int)crank * (BN / 2);
-          for (int kb = 0; kb < KB; ++kb) {
-            mbar_wait(&empty[s], ph ^ 1);
-            if (crank == 0) mbar_arrive_expect_tx(&full[s], 2 * BHALF_BYTES);
-            tma_load_2d_2cta(sB + s * BHALF_BYTES, &tmB, &full[s], kb * BK, n0);
-            if (wi == pair_id && nt == 0 && kb == 0) stamp(p, 2);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (crank == 0 && lane == 0) {  // ===== MMA issuer: leader CTA only =====
-      constexpr uint32_t idesc = umma_idesc(kFmtF16, 2 * BM, BN);
-      int s = 0, ph = 0, acc = 0, aph = 0, item = 0;
-      for (int wi = pair_id; wi < num_items; wi += num_pairs, ++item) {
-        mbar_wait_cluster(afull, item & 1);  // both CTAs' halves of the resident A tile are filled
-        tc_fence_after();
-        if (item == 0) stamp(p, 3);
-        for (int nt = 0; nt < tpp; ++nt) {
-          mbar_wait(&tempty[acc], aph ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
-          for (int kb = 0; kb < KB; ++kb) {
-            mbar_wait(&full[s], ph);
-            tc_fence_after();
-            if (item == 0 && nt == 0 && kb == 0) stamp(p, 4);
-            const uint64_t ad = umma_desc_k_sw128(smem_u32(sA + kb * A_BYTES));
-            const uint64_t bd = umma_desc_k_sw128(smem_u32(sB + s * BHALF_BYTES));
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_f16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-            umma_commit_2cta(&empty[s], 0b11);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
-          }
-          umma_commit_2cta(&tfull[acc], 0b11);
-          if (++acc == 2) { acc = 0; aph ^= 1; }
-        }
-      }
-      stamp(p, 5);
-    }
-    __syncwarp();
-  } else if (warp >= 4) {  // ===== LN fill of my 128 rows + epilogue of my accumulator half =====
-    const int ew = warp - 4;
-    float* scratch = sEpi + ew * 32 * EPI_LD;
-    int acc = 0, aph = 0;
-    for (int wi = pair_id; wi < num_items; wi += num_pairs) {
-      const int m0 = (wi / f.nsplit) * 2 * BM + (int)crank * BM, part = wi % f.nsplit;
-      ln_fill_rows<V2>(p, f, sA, m0, ew, lane);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (crank == 0) mbar_arrive(afull);
-        else mbar_arrive_remote(afull, 0);
-      }
-      for (int nt = 0; nt < tpp; ++nt) {
-        const int n0 = (part * tpp + nt) * BN;
-        uint64_t* te = &tempty[acc];
-        epilogue_tile<kEpiStore, BN, __half>(p, &tmC, tmem_base + acc * BN, &tfull[acc], aph, m0, n0, ew, lane,
-                                             scratch, wi == pair_id && nt == 0, [&] {
-                                               if (lane == 0) {
-                                                 if (crank == 0) mbar_arrive(te);
-                                                 else mbar_arrive_remote(te, 0);
-                                               }
-                                             });
-        if (++acc == 2) { acc = 0; aph ^= 1; }
-        if (threadIdx.x == 128) stamp(p, wi == pair_id && nt == 0 ? 7 : 8);
-      }
-    }
-  }
-
-  if (warp >= 4 && lane == 0) tma_store_wait_all<0>();
-  tc_fence_before();
-  cluster_sync_all();  // the peer's smem / barriers / TMEM half stay valid until both are done
-  if (threadIdx.x == 0) stamp(p, 9);
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc_2cta(tmem_base, 2 * BN);
-  }
-}
-
 __global__ void convert_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n4) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -1276,112 +891,7 @@ cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float
 
 void set_gemm_sm_cap(int n) { g_gemm_sm_cap = n; }
 
-// 1: the QKV projection of the inference forward runs on gemm_lnqkv_tcgen05_kernel (LayerNorm fused, resident A
-// tile; 2: its CTA-pair form).  EXPERIMENTAL, default off; RRT_QKV_FUSED_LN=1|2 or rrt_debug_set_gemm_cluster(3|4),
-// (30) = off.
-int g_qkv_fused_ln = [] { const char* e = getenv("RRT_QKV_FUSED_LN"); return e ? atoi(e) : 0; }();
-
-bool gemm_lnqkv_supported(const Grid& grid, int D, int N) {
-  return (D == 256 || D == 512) && N >= LQ_BN && N % LQ_BN == 0 && grid.Np >= 1 && grid.L >= 1;
-}
-
-cudaError_t launch_gemm_lnqkv_tcgen05(const float* x, const float* gamma, const float* beta, const Grid& grid,
-                                      const __half* w, const float* bias, __half* qkv, int D, int N,
-                                      cudaStream_t stream) {
-  if (!gemm_lnqkv_supported(grid, D, N)) return cudaErrorInvalidValue;
-  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
-       reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(qkv)) & 15)
-    return cudaErrorInvalidValue;
-  Tc05Params p{};
-  p.M = grid.Np; p.N = N; p.K = D;
-  p.bias = bias; p.C = qkv; p.grid = grid;
-  p.act = kActNone;
-  p.ksplit = 1;
-  p.trace = g_gemm_trace ? g_gemm_trace + (size_t)(g_trace_launch++ % 8) * 128 : nullptr;
-  CUtensorMap tmB, tmC;
-  if (!make_map(&tmB, w, N, D, LQ_BN) || !make_store_map(&tmC, qkv, grid.Np, N, 2)) return cudaErrorUnknown;
-  // SM budget: all SMs, or the cap of the bag-sized GEMMs while several bags are in flight (launch_cfg)
-  static const int env_cap = [] { const char* e = getenv("RRT_GEMM_SMS"); return e ? atoi(e) : -1; }();
-  int sms = sm_count();
-  const int cap = env_cap >= 0 ? env_cap : g_gemm_sm_cap;
-  if (cap > 0 && cap < sms) sms = cap;
-  if (g_qkv_fused_ln == 2 && N % 256 == 0 && sms >= 2) {
-    // CTA pairs: 256-row x 256-column tiles, work items shared out over sms / 2 clusters
-    const int tiles_m2 = (grid.Np + 2 * BM - 1) / (2 * BM), tiles_n2 = N / 256, pairs_max = sms / 2;
-    int ns = 1;
-    for (int d = 1; d <= tiles_n2; ++d)
-      if (tiles_n2 % d == 0 && (long long)tiles_m2 * d <= pairs_max) ns = d;
-    LnFillParams f2{x, gamma, beta, ns};
-    const long long items2 = (long long)tiles_m2 * ns;
-    const int pairs = items2 < pairs_max ? (int)items2 : pairs_max;
-    cudaLaunchConfig_t c2{};
-    c2.gridDim = dim3(pairs * 2);
-    c2.blockDim = dim3(NTHREADS);
-    c2.dynamicSmemBytes = LQ_SMEM_BYTES;
-    c2.stream = stream;
-    cudaLaunchAttribute a2[1];
-    a2[0].id = cudaLaunchAttributeClusterDimension;
-    a2[0].val.clusterDim.x = 2;
-    a2[0].val.clusterDim.y = 1;
-    a2[0].val.clusterDim.z = 1;
-    c2.attrs = a2;
-    c2.numAttrs = 1;
-    if (D == 512) {
-      auto kern = gemm_lnqkv_tcgen05_2cta_kernel<2>;
-      static DeviceOnce configured;
-      if (configured.needed()) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LQ_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-      }
-      return cudaLaunchKernelEx(&c2, kern, tmB, tmC, p, f2);
-    }
-    auto kern = gemm_lnqkv_tcgen05_2cta_kernel<1>;
-    static DeviceOnce configured;
-    if (configured.needed()) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LQ_SMEM_BYTES);
-      if (e != cudaSuccess) return e;
-    }
-    return cudaLaunchKernelEx(&c2, kern, tmB, tmC, p, f2);
-  }
-  // the N tiles of an M tile are cut into nsplit shares (a divisor of N / 128) so that every SM has a work
-  // item; each share LayerNorms the M tile again (L2 hits), so no more shares than that takes
-  const int tiles_m = (grid.Np + BM - 1) / BM, tiles_n = N / LQ_BN;
-  int nsplit = 1;
-  for (int d = 1; d <= tiles_n; ++d)
-    if (tiles_n % d == 0 && (long long)tiles_m * d <= sms) nsplit = d;
-  LnFillParams f{x, gamma, beta, nsplit};
-  long long items = (long long)tiles_m * nsplit;
-  const int ctas = items < sms ? (int)items : sms;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(ctas);
-  cfg.blockDim = dim3(NTHREADS);
-  cfg.dynamicSmemBytes = LQ_SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
-  if (D == 512) {
-    auto kern = gemm_lnqkv_tcgen05_kernel<2>;
-    static DeviceOnce configured;
-    if (configured.needed()) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LQ_SMEM_BYTES);
-      if (e != cudaSuccess) return e;
-    }
-    return cudaLaunchKernelEx(&cfg, kern, tmB, tmC, p, f);
-  }
-  auto kern = gemm_lnqkv_tcgen05_kernel<1>;
-  static DeviceOnce configured;
-  if (configured.needed()) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LQ_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-  }
-  return cudaLaunchKernelEx(&cfg, kern, tmB, tmC, p, f);
-}
-
 void set_gemm_cluster_mode(int mode) {
-  if (mode == 3 || mode == 4 || mode == 30) { g_qkv_fused_ln = mode == 30 ? 0 : mode - 2; return; }  // 4: CTA pairs
   if (mode == 128 || mode == 256) { g_gemm_narrow = mode == 128; return; }
   if (mode == 2) { g_gemm_pair = 1; return; }
   g_gemm_pair = 0;

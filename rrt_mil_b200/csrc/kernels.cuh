@@ -50,14 +50,6 @@ cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool 
 // weight gradient: dw[C_out, C_in] (fp32, zeroed) += dy[rows, C_out]^T @ act[rows, C_in] (fp16, row-major)
 cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float* dw, int rows, int C_out,
                                       int C_in, cudaStream_t stream);
-// EXPERIMENTAL (off by default): qkv[slot,:] = LN(x[token(slot),:]) @ w^T + bias in ONE kernel -- the 128-row
-// A tile is LayerNorm'ed from the fp32 residual stream into shared memory once and stays resident for all
-// N tiles (replaces launch_ln_partition + the QKV launch_gemm_tcgen05 in the inference forward).  D in {256, 512}.
-extern int g_qkv_fused_ln;  // RRT_QKV_FUSED_LN=1 / rrt_debug_set_gemm_cluster(3) on, (30) off
-bool gemm_lnqkv_supported(const Grid& grid, int D, int N);
-cudaError_t launch_gemm_lnqkv_tcgen05(const float* x, const float* gamma, const float* beta, const Grid& grid,
-                                      const __half* w, const float* bias, __half* qkv, int D, int N,
-                                      cudaStream_t stream);
 void set_gemm_cluster_mode(int mode);
 // at most n SMs for the bag-sized GEMMs launched by THIS host thread from now on (0 = all)
 void set_gemm_sm_cap(int n);  // debug/tuning: 22 = 2x2 clusters, 21 = 2x1, 11 = none
@@ -120,13 +112,6 @@ cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const 
                                      const float* phi, float2* stats, float* logits,
                                      __half* landmarks, float2* rstat, const Grid& grid, int D, int k,
                                      cudaStream_t stream);
-// EXPERIMENTAL (off by default): the same front end as ONE kernel on clusters of D/128 CTAs per region: every
-// CTA reads its 128-column slab of x1 once into shared memory, the per-row partial sums are exchanged through
-// distributed shared memory.  cudaErrorNotSupported (crmsa_mlp logits, P > 256, D > 1024): use the split path.
-extern int g_crmsa_front_cluster;  // rrt_debug_set_gemm_cluster(5) on / (50) off; RRT_CRMSA_FRONT=cluster
-cudaError_t launch_crmsa_front_cluster(const float* x1, const float* gamma, const float* beta,
-                                       const float* phi, float2* stats, float* logits, __half* landmarks,
-                                       float2* rstat, const Grid& grid, int D, int k, cudaStream_t stream);
 // MHA core over the landmarks: batch = k, sequence = R (64), heads, head_dim = D/heads, plain
 // softmax(q k^T * scale) v, fp32 math.  lqkv: [k*R, 3D] fp32 rows (n, rho); lo: [k*R, D] f16.
 cudaError_t launch_landmark_attention(const float* lqkv, __half* lo, int k, int R, int D, int heads,

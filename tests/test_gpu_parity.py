@@ -229,90 +229,6 @@ def test_alternative_kernel_variants_keep_parity(knob, value, restore):
         getattr(lib, knob)(restore)
 
 
-@pytest.mark.skipif(os.environ.get("RRT_EXPERIMENTAL") != "1",
-                    reason="experimental kernel, not yet run on a B200: set RRT_EXPERIMENTAL=1 to test it")
-@pytest.mark.parametrize("mode", [3, 4])   # 3: single-CTA kernel, 4: CTA pairs (cta_group::2)
-def test_experimental_fused_ln_qkv_gemm_keeps_parity(mode):
-    """LayerNorm-fused QKV GEMM with a resident A tile (rrt_debug_set_gemm_cluster(3 | 4)):
-    same parity bar as the default path; R-MSA block close to the unfused kernels (the LayerNorm sums run in
-    a different order, so z may differ by an fp16 ulp); bags in flight exercise the A refill (several work
-    items per CTA under the SM cap)."""
-    from rrt_mil_b200 import cabi
-    lib = cabi.lib()
-    for L, over in [(512, dict()), (9000, dict()), (63, dict()), (65, dict()), (1300, dict(region_num=4, epeg_k=9)),
-                    (700, dict(mlp_dim=256, n_heads=4, crmsa_heads=4)), (20000, dict(region_num=16))]:
-        cfg, m = _default_encoder(**over)
-        x = O.make_bag(L, cfg.mlp_dim, 9, dtype=torch.float32).cuda()
-        ref = G.rmsa_block(m, 0, x)
-        lib.rrt_debug_set_gemm_cluster(mode)
-        try:
-            got = G.rmsa_block(m, 0, x)
-            got2 = G.rmsa_block(m, 0, x)
-        finally:
-            lib.rrt_debug_set_gemm_cluster(30)
-        torch.cuda.synchronize()
-        assert torch.equal(got, got2), (L, over)
-        assert O.rel_err(got.cpu().double(), ref.cpu().double()) < 2e-4, (L, over)
-    lib.rrt_debug_set_gemm_cluster(mode)
-    try:
-        for name in ("c1_n512_d512", "c2_n9000_d512", "c4_n50000_g16", "d256_g4", "n65"):
-            cfg, w, x, gold = load_case(name)
-            m = G.make_encoder(cfg, w)
-            with torch.no_grad():
-                y = m(x.float().cuda())
-            torch.cuda.synchronize()
-            assert_matches_golden(y, gold, TOL_TF32, f"fused ln+qkv {name}")
-        cfg, m = _default_encoder()
-        g = torch.Generator().manual_seed(5)
-        bags = [torch.randn(n, 512, generator=g).cuda() for n in [9000, 777, 8123, 1, 9216, 5000, 4097, 9000, 8999]]
-        with torch.no_grad():
-            serial = [m(b) for b in bags]
-            for lanes in (4, 8):
-                outs = m.forward_bags(bags, lanes=lanes)
-                torch.cuda.synchronize()
-                for a, b in zip(serial, outs):
-                    assert torch.equal(a, b)
-    finally:
-        lib.rrt_debug_set_gemm_cluster(30)
-
-
-@pytest.mark.skipif(os.environ.get("RRT_EXPERIMENTAL") != "1",
-                    reason="experimental kernel, not yet run on a B200: set RRT_EXPERIMENTAL=1 to test it")
-def test_experimental_cluster_crmsa_front_keeps_parity():
-    """One-kernel CR-MSA front end on thread-block clusters (rrt_debug_set_gemm_cluster(5)): the CR-MSA block must
-    agree with the default split kernels to fp32 summation-order noise, and the encoder must keep the golden
-    parity bar.  Unsupported shapes (crmsa_mlp, regions > 256 tokens) silently take the split path."""
-    from rrt_mil_b200 import cabi
-    lib = cabi.lib()
-    for L, over in [(512, dict()), (9000, dict()), (63, dict()), (65, dict()), (3000, dict(crmsa_k=5)),
-                    (700, dict(mlp_dim=256, n_heads=4, crmsa_heads=4, crmsa_k=9, all_shortcut=True)),
-                    (1000, dict(crmsa_mlp=True, crmsa_heads=1, crmsa_k=5)), (20000, dict(region_num=16))]:
-        cfg, m = _default_encoder(**over)
-        x1 = O.make_bag(L, cfg.mlp_dim, 11, dtype=torch.float32).cuda()
-        x0 = O.make_bag(L, cfg.mlp_dim, 12, dtype=torch.float32).cuda() if cfg.all_shortcut else None
-        ref = G.crmsa_block(m, x1, x0, True)
-        lib.rrt_debug_set_gemm_cluster(5)
-        try:
-            got = G.crmsa_block(m, x1, x0, True)
-            got2 = G.crmsa_block(m, x1, x0, True)
-        finally:
-            lib.rrt_debug_set_gemm_cluster(50)
-        torch.cuda.synchronize()
-        assert torch.equal(got, got2), (L, over)
-        assert O.rel_err(got.cpu().double(), ref.cpu().double()) < 1e-4, (L, over)
-    lib.rrt_debug_set_gemm_cluster(5)
-    try:
-        for name in ("c1_n512_d512", "c2_n9000_d512", "c5_n9000_k21_c5", "d256_g4", "n65", "tiny_n1"):
-            cfg, w, x, gold = load_case(name)
-            m = G.make_encoder(cfg, w)
-            with torch.no_grad():
-                y = m(x.float().cuda())
-            torch.cuda.synchronize()
-            assert_matches_golden(y, gold, TOL_TF32, f"cluster crmsa front {name}")
-    finally:
-        lib.rrt_debug_set_gemm_cluster(50)
-
-
 def test_tiny_bag_crmsa_contributes_nothing():
     """N < 64: every token is its own region, min-max normalised dispatch weight is 0/(0+1e-8)=0
      -> the CR-MSA block is the identity on x1."""

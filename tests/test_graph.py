@@ -1,7 +1,5 @@
 """GraphedForward (rrt_mil_b200/graph.py): CUDA-graph replay of the encoder forward for fixed bag lengths.
-CPU: argument validation.  GPU (EXPERIMENTAL, RRT_EXPERIMENTAL=1): replay == eager, bit for bit."""
-import os
-
+CPU: argument validation.  GPU: replay == eager, bit for bit."""
 import pytest
 import torch
 
@@ -23,8 +21,6 @@ def test_graphed_forward_validates_its_arguments():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("RRT_EXPERIMENTAL") != "1",
-                    reason="experimental, not yet run on a B200: set RRT_EXPERIMENTAL=1 to test it")
 def test_graph_replay_equals_eager_forward():
     torch.manual_seed(0)
     m = RRTEncoder(need_init=True).cuda().eval()
