@@ -16,6 +16,15 @@
  *   - the caller owns every buffer, including the workspace (size from rrt_workspace_bytes);
  *   - return value 0 = ok, negative = error (RRT_E_*), text from rrt_last_error();
  *   - there is no CPU fallback: without a CUDA device every compute entry returns RRT_E_CUDA.
+ *
+ * Threading / devices
+ *   - every entry point may be called from several host threads at once, on different streams and on different
+ *     devices of one process (cudaSetDevice first: a call runs on the device that is current in the calling
+ *     thread, and `stream` and all pointers must belong to it).  The library keeps no state that is shared between
+ *     calls except caches keyed by (thread, device): the internal lane streams / events of
+ *     rrt_encoder_forward_batch and the encoded TMA descriptors are per host thread and per device;
+ *   - the rrt_debug_* knobs and the stage timer are process-wide and meant for single-threaded tools;
+ *   - rrt_last_error() is per host thread.
  */
 #ifndef RRT_B200_H_
 #define RRT_B200_H_
@@ -33,7 +42,7 @@ extern "C" {
 #define RRT_API __attribute__((visibility("default")))
 #endif
 
-#define RRT_ABI_VERSION 5
+#define RRT_ABI_VERSION 6
 #define RRT_MAX_RMSA_LAYERS 8 /* n_layers-1 R-MSA TransLayers (modules/rrt.py:143) */
 #define RRT_MAX_CRMSA_K 16    /* crmsa_k landmarks per region                         */
 #define RRT_MAX_EPEG_K 63     /* odd EPEG kernel length                               */
@@ -195,9 +204,10 @@ RRT_API int rrt_debug_set_gemm_trace(void* device_buffer);
 /* Debug: same for the region-resident attention kernel: device_buffer[8][8] (int64). */
 RRT_API int rrt_debug_set_attn_trace(void* device_buffer);
 
-/* Debug / tuning: R-MSA attention core: 1 = tcgen05 kernel (head_dim 64, regions <= 256 tokens),
- * 0 = mma.sync kernel.  Results agree within the parity tolerance. */
-RRT_API int rrt_debug_set_attention_kernel(int32_t use_tcgen05);
+/* Debug / tuning: R-MSA attention core.  1 (default) = auto: the tcgen05 / TMEM kernel (head_dim 64) for regions
+ * of more than 128 tokens, the mma.sync kernel otherwise; 2 = the tcgen05 kernel wherever it is supported;
+ * 0 = the mma.sync kernel only.  Results agree within the parity tolerance. */
+RRT_API int rrt_debug_set_attention_kernel(int32_t mode);
 
 /* Debug / tuning: kernel variant of the bag-sized tcgen05 GEMMs.  11 = single-CTA 128x256 tiles
  * (default, fastest at these sizes); 2 = CTA pairs (cta_group::2, M=256 tiles); 21 / 22 = single-CTA
@@ -308,6 +318,13 @@ RRT_API int rrt_encoder_forward_train(const rrt_config* cfg, const rrt_weights* 
 /* out[i] = keep(i) / (1 - drop_p) for i < n (n % 4 == 0): the factor the forward multiplies element i by. */
 RRT_API int rrt_dropout_mask(float* out, int64_t n, float drop_p, uint64_t seed, uint32_t mask_stream,
                              void* stream);
+/* RRT_OK when rrt_encoder_backward covers this configuration AND this bag length, else RRT_E_INVALID with the
+ * reason in rrt_last_error().  The limits depend on the bag, not only on the configuration: the R-MSA backward
+ * keeps a region resident (regions of at most 256 tokens: N <= 16384 at region_num = 8), R-MSA / CR-MSA head_dim
+ * must be 32 or 64 (crmsa_heads = 1 at dim 512 is not covered), crmsa_k <= 8, no crmsa_mlp / PEG / PPEG / FFN.
+ * Callers check it BEFORE the taped forward, so that a training loop fails at the first call and not inside
+ * loss.backward(). */
+RRT_API int rrt_backward_supported(const rrt_config* cfg, int64_t L);
 RRT_API int rrt_backward_workspace_bytes(const rrt_config* cfg, int64_t L, size_t* bytes);
 /* x: the forward input; dout: d(loss)/d(out) [L, D]; dx: d(loss)/dx [L, D] (may not alias dout). */
 RRT_API int rrt_encoder_backward(const rrt_config* cfg, const rrt_weights* w, const float* x,

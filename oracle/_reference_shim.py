@@ -1,14 +1,15 @@
 """Read-only import of the upstream reference (``/root/reference``) for pinning the oracle.
 
-TEST INFRASTRUCTURE ONLY.  Used in the build container by ``oracle/make_golden.py`` and by
-the ``not gpu`` oracle tests when ``/root/reference`` exists.  It never travels: the GPU box
-has no ``/root/reference`` and nothing in the ``-m gpu`` tests, ``smoke()`` or ``bench.py``
-calls this module.
+TEST / BASELINE INFRASTRUCTURE ONLY.  Used in the build container by ``oracle/make_golden.py`` and by
+the ``not gpu`` oracle tests when ``/root/reference`` exists.  ``/root/reference`` itself never travels;
+``oracle/build_ref.py`` stages byte-for-byte copies of the hot path's modules under the git-ignored
+``oracle/_ref/``, which does travel to the GPU box, where ``bench.py --impl reference`` and
+``tests/test_gpu_dropin.py`` import them through this module.  The product never does.
 
 The reference imports ``timm.models.layers.DropPath`` (modules/rrt.py:7) and
 ``trunc_normal_`` (modules/emb_position.py:4); ``timm`` is not installed, so two stand-in
 symbols are registered in ``sys.modules`` before the import.  Nothing under
-``/root/reference`` is modified or copied.
+``/root/reference`` is modified.
 """
 from __future__ import annotations
 
@@ -19,7 +20,11 @@ import types
 import torch
 from torch import nn
 
-REFERENCE_ROOT = os.environ.get("RRT_REFERENCE_ROOT", "/root/reference")
+# /root/reference in the build container; on the GPU box the tree staged by oracle/build_ref.py (oracle/_ref/,
+# git-ignored, travels with the gpurun snapshot)
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get("RRT_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/modules/rrt.py") else _STAGED)
 
 
 def available() -> bool:

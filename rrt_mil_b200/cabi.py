@@ -12,7 +12,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librrt_b200.so")
 
-RRT_ABI_VERSION = 5
+RRT_ABI_VERSION = 6
 RRT_DROP_STREAM_CRMSA = 64
 RRT_DROP_STREAM_PATCH = 65
 RRT_POS_NONE, RRT_POS_PEG, RRT_POS_PPEG = 0, 1, 2
@@ -114,6 +114,7 @@ SIGNATURES = {
     "rrt_adam_step": (C.c_int, [C.POINTER(RrtAdamTensor), C.c_int32, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_int32, C.c_int64, C.c_float, _P]),
     "rrt_dropout_mask": (C.c_int, [_P, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, _P]),
+    "rrt_backward_supported": (C.c_int, [C.POINTER(RrtConfig), C.c_int64]),
     "rrt_backward_workspace_bytes": (C.c_int, [C.POINTER(RrtConfig), C.c_int64, C.POINTER(C.c_size_t)]),
     "rrt_encoder_backward": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P, C.c_int64,
                                        _P, C.c_size_t, C.POINTER(RrtGrads), _P, _P, C.c_size_t,
@@ -172,9 +173,9 @@ def lib() -> C.CDLL:
                 fn.restype, fn.argtypes = res, args
             if handle.rrt_abi_version() != RRT_ABI_VERSION:
                 raise RuntimeError("librrt_b200.so ABI version mismatch: rebuild it")
-            if os.environ.get("RRT_ATTN"):  # tuning knob: tc05 | mma
-                handle.rrt_debug_set_attention_kernel(int(os.environ["RRT_ATTN"] == "tc05"))
-            if os.environ.get("RRT_GEMM_CLUSTER"):  # tuning knob: 11 (default), 2, 21, 22, 128, 256, 3 (experimental fused LN+QKV)
+            if os.environ.get("RRT_ATTN"):  # tuning knob: auto (default) | tc05 (wherever supported) | mma
+                handle.rrt_debug_set_attention_kernel({"mma": 0, "auto": 1, "tc05": 2}[os.environ["RRT_ATTN"]])
+            if os.environ.get("RRT_GEMM_CLUSTER"):  # tuning knob: 11 (default), 2, 21, 22, 128, 256
                 handle.rrt_debug_set_gemm_cluster(int(os.environ["RRT_GEMM_CLUSTER"]))
             _lib = handle
     return _lib

@@ -339,7 +339,8 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
   { StageScope s_(kStRmsaAttn, st);
     const float* taps = c->epeg ? a->pe_w : nullptr;
     if (s_.skip()) {
-    } else if (rrt::g_attn_tc05 && rrt::rmsa_attention_tc05_supported(g, D, c->n_heads))
+    } else if ((rrt::g_attn_tc05 == 2 || (rrt::g_attn_tc05 == 1 && g.P > 128)) &&
+               rrt::rmsa_attention_tc05_supported(g, D, c->n_heads, taps ? c->epeg_k : 0))
       RRT_CUDA(rrt::launch_rmsa_attention_tc05(ws_qkv, taps, ws_o, g, D, c->n_heads, c->epeg_k, st),
                "rmsa attention (tcgen05)");
     else if (rrt::rmsa_attention_f16_supported(g, D, c->n_heads))
@@ -429,7 +430,10 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
     if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lm, wq, ws.lqkv, tc_attn, T, 3 * D, D, e1, st), "landmark qkv"); }
   { StageScope s_(kStLmAttn, st);
     if (s_.skip()) {
-    } else if (tc_attn)
+    } else if (tc_attn && rrt::g_attn_tc05 == 2 && rrt::rmsa_attention_tc05_supported(lg, D, c->crmsa_heads, 0))
+      RRT_CUDA(rrt::launch_rmsa_attention_tc05(reinterpret_cast<const __half*>(ws.lqkv), nullptr, ws.lo,
+                                               lg, D, c->crmsa_heads, 1, st), "landmark attention (tcgen05)");
+    else if (tc_attn)
       RRT_CUDA(rrt::launch_rmsa_attention_f16(reinterpret_cast<const __half*>(ws.lqkv), nullptr, ws.lo,
                                               lg, D, c->crmsa_heads, 1, st), "landmark attention");
     else
@@ -581,25 +585,33 @@ RRT_API int rrt_encoder_forward(const rrt_config* cfg, const rrt_weights* w, con
 }
 
 namespace {
-// Internal fork/join lanes of the batch entry point (one process drives one GPU).
+// Internal fork/join lanes of the batch entry point: one set of streams + events per (host thread, device), so
+// that concurrent callers (different host threads, different caller streams, different GPUs of one process)
+// never share a fork / join event.  Created on first use on the device that is current for the call; they live
+// until the process exits (a host thread that ends leaves its lanes to the driver's teardown).
 struct Lanes {
   cudaStream_t stream[RRT_MAX_LANES] = {};
   cudaEvent_t done[RRT_MAX_LANES] = {};
   cudaEvent_t fork = nullptr;
   bool ready = false;
 };
-Lanes g_lanes;
-std::mutex g_lanes_mu;
+constexpr int kMaxDevices = 64;
+thread_local Lanes g_lanes_tl[kMaxDevices];
 
-cudaError_t ensure_lanes() {
-  std::lock_guard<std::mutex> l(g_lanes_mu);
-  if (g_lanes.ready) return cudaSuccess;
-  cudaError_t e = cudaEventCreateWithFlags(&g_lanes.fork, cudaEventDisableTiming);
+cudaError_t ensure_lanes(Lanes** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  Lanes& L = g_lanes_tl[dev];
+  *out = &L;
+  if (L.ready) return cudaSuccess;
+  e = cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming);
   for (int i = 1; i < RRT_MAX_LANES && e == cudaSuccess; ++i) {
-    e = cudaStreamCreateWithFlags(&g_lanes.stream[i], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_lanes.done[i], cudaEventDisableTiming);
+    e = cudaStreamCreateWithFlags(&L.stream[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&L.done[i], cudaEventDisableTiming);
   }
-  g_lanes.ready = (e == cudaSuccess);
+  L.ready = (e == cudaSuccess);
   return e;
 }
 }  // namespace
@@ -627,13 +639,15 @@ RRT_API int rrt_encoder_forward_batch(const rrt_config* cfg, const rrt_weights* 
   if (lanes > RRT_MAX_LANES) lanes = RRT_MAX_LANES;
   if (lanes > n_bags) lanes = n_bags;
   cudaStream_t user = (cudaStream_t)stream;
-  cudaStream_t lane_stream[RRT_MAX_LANES] = {user, user, user, user};
+  cudaStream_t lane_stream[RRT_MAX_LANES];
+  for (auto& ls : lane_stream) ls = user;
+  Lanes* lanes_p = nullptr;
   if (lanes > 1) {
-    RRT_CUDA(ensure_lanes(), "lane streams");
-    RRT_CUDA(cudaEventRecord(g_lanes.fork, user), "fork");
+    RRT_CUDA(ensure_lanes(&lanes_p), "lane streams");
+    RRT_CUDA(cudaEventRecord(lanes_p->fork, user), "fork");
     for (int l = 1; l < lanes; ++l) {
-      lane_stream[l] = g_lanes.stream[l];
-      RRT_CUDA(cudaStreamWaitEvent(lane_stream[l], g_lanes.fork, 0), "fork wait");
+      lane_stream[l] = lanes_p->stream[l];
+      RRT_CUDA(cudaStreamWaitEvent(lane_stream[l], lanes_p->fork, 0), "fork wait");
     }
   }
   // >= 4 bags in flight: the bag-sized GEMMs keep to 64 SMs (csrc/gemm_tcgen05.cu, "SM cap")
@@ -651,8 +665,8 @@ RRT_API int rrt_encoder_forward_batch(const rrt_config* cfg, const rrt_weights* 
   }
   rrt::set_gemm_sm_cap(0);
   for (int l = 1; l < lanes; ++l) {  // always join, also on error, so `stream` stays ordered
-    cudaEventRecord(g_lanes.done[l], lane_stream[l]);
-    cudaStreamWaitEvent(user, g_lanes.done[l], 0);
+    cudaEventRecord(lanes_p->done[l], lane_stream[l]);
+    cudaStreamWaitEvent(user, lanes_p->done[l], 0);
   }
   return rc;
 }
@@ -959,8 +973,9 @@ RRT_API int rrt_debug_set_attn_trace(void* device_buffer) {
   return RRT_OK;
 }
 
-RRT_API int rrt_debug_set_attention_kernel(int32_t use_tcgen05) {
-  rrt::g_attn_tc05 = use_tcgen05 ? 1 : 0;
+RRT_API int rrt_debug_set_attention_kernel(int32_t mode) {
+  if (mode < 0 || mode > 2) return fail(RRT_E_INVALID, "mode must be 0 (mma.sync), 1 (auto) or 2 (tcgen05 wherever supported)");
+  rrt::g_attn_tc05 = mode;
   return RRT_OK;
 }
 
@@ -1296,6 +1311,12 @@ RRT_API int rrt_encoder_forward_train(const rrt_config* cfg, const rrt_weights* 
   tr.tape = true;  // the backward re-reads z, q/k/v, o: no kernel variant may skip an intermediate
   PdlScope pdl(!g_timing.load(std::memory_order_relaxed));
   return encoder_forward(cfg, w, x, out, L, ws, (cudaStream_t)stream, tr);
+}
+
+RRT_API int rrt_backward_supported(const rrt_config* cfg, int64_t L) {
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  return check_backward_support(cfg, L);
 }
 
 RRT_API int rrt_backward_workspace_bytes(const rrt_config* cfg, int64_t L, size_t* bytes) {

@@ -77,8 +77,8 @@ cudaError_t launch_rmsa_attention_f16(const __half* qkv, const float* taps, __ha
 cudaError_t launch_rmsa_attention(const __half* qkv, const float* taps, __half* o, const Grid& grid,
                                   int D, int heads, int epeg_k, cudaStream_t stream);
 // ---- rmsa_attn_tc05.cu: same contract, S and O products on tcgen05 (head_dim 64, P <= 256) ----
-extern int g_attn_tc05;  // 1: use it when supported (rrt_debug_set_attention_kernel / RRT_ATTN=tc05)
-bool rmsa_attention_tc05_supported(const Grid& grid, int D, int heads);
+extern int g_attn_tc05;  // 1 (default): auto (regions > 128 tokens), 2: wherever supported, 0: never
+bool rmsa_attention_tc05_supported(const Grid& grid, int D, int heads, int epeg_k /* 0 = no EPEG */);
 cudaError_t launch_rmsa_attention_tc05(const __half* qkv, const float* taps, __half* o,
                                        const Grid& grid, int D, int heads, int epeg_k,
                                        cudaStream_t stream);

@@ -294,6 +294,33 @@ class RRTEncoder(nn.Module):
         self._shadow.clear()
         self.__dict__.pop("_w_cache", None)
 
+    # The caches hold ctypes structs full of device pointers, fp16 shadow tensors keyed by id() and a closure:
+    # none of it may travel with a copy or a pickle (copy.deepcopy for EMA / teacher models, torch.save(model)).
+    _TRANSIENT = ("_w_cache", "_np_cache")
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in self._TRANSIENT:
+            state.pop(k, None)
+        state["_shadow"] = {}
+        state["_cfg"] = bytes(self._cfg)          # ctypes.Structure -> plain bytes
+        return state
+
+    def __setstate__(self, state):
+        cfg = state.pop("_cfg")
+        self.__dict__.update(state)
+        self._cfg = cabi.RrtConfig.from_buffer_copy(cfg) if isinstance(cfg, (bytes, bytearray)) else cfg
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        state = self.__getstate__()
+        cfg = state.pop("_cfg")
+        new.__dict__.update(copy.deepcopy(state, memo))
+        new._cfg = cabi.RrtConfig.from_buffer_copy(cfg)
+        return new
+
     def _attn_weights(self, inner: InnerAttention, dst: cabi.RrtAttnWeights, device, shadows=False):
         p = self._ptr
         dst.qkv_w, dst.qkv_b = p(inner.qkv.weight, device), p(inner.qkv.bias, device)
@@ -416,6 +443,21 @@ class RRTEncoder(nn.Module):
                 raise NotImplementedError("backward through the PEG / PPEG ablation is not built")
             if self._cfg.ffn:
                 raise NotImplementedError("backward through the FFN ablation is not built")
+            # limits that depend on the BAG, not only on the configuration (region size, head_dim): checked here,
+            # before the taped forward, so that a training loop fails at the call and not inside loss.backward()
+            N = x.shape[-2] if x.dim() >= 2 else 0
+            lib = cabi.lib()
+            if N >= 1 and lib.rrt_backward_supported(C.byref(self._cfg), N) != cabi.RRT_OK:
+                why = lib.rrt_last_error().decode("utf-8", "replace")
+                raise NotImplementedError(
+                    f"training is not covered for this bag / configuration (N={N}, region_num={self._cfg.region_num}, "
+                    f"R-MSA head_dim={self._cfg.dim // max(self._cfg.n_heads, 1)}, CR-MSA head_dim="
+                    f"{self._cfg.dim // max(self._cfg.crmsa_heads, 1)}): {why}")
+        if self.training and self._cfg.ffn and self.drop_out > 0:
+            # the reference's Mlp applies nn.Dropout(drop_out) twice in training mode (modules/rrt.py:25-41);
+            # the FFN kernels have no dropout, so computing on would silently differ from the reference
+            raise NotImplementedError("training-mode dropout inside the FFN ablation is not built: "
+                                      "use .eval() or drop_out=0")
         if self.training and self.drop_path_rate > 0:
             raise NotImplementedError("training-mode drop_path (default 0) is not built")
         if self.training and self.drop_out > 0 and not allow_grad:

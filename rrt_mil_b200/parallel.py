@@ -19,8 +19,17 @@ def shard_indices(n_bags: int, world_size: int, rank: int) -> List[int]:
     return list(range(rank, n_bags, world_size))
 
 
+def _default_device(group=None) -> torch.device:
+    """Device of the collectives' buffers for a rank that holds no tensor to take it from: the current CUDA
+    device under NCCL (every rank must hand CUDA tensors to the same collective), the CPU otherwise."""
+    if dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
 def gather_ragged(local: Sequence[torch.Tensor], n_bags: int, group=None,
-                  dst: Optional[int] = None) -> Optional[List[torch.Tensor]]:
+                  dst: Optional[int] = None, device: Optional[torch.device] = None,
+                  dtype: torch.dtype = torch.float32) -> Optional[List[torch.Tensor]]:
     """All ranks hold the outputs of their ``shard_indices`` bags (``[N_i, D]`` each, ragged N_i).
     Returns the ``n_bags`` outputs in bag order on every rank (``dst=None``) or on ``dst`` only.
 
@@ -32,8 +41,12 @@ def gather_ragged(local: Sequence[torch.Tensor], n_bags: int, group=None,
     mine = shard_indices(n_bags, world, rank)
     if len(mine) != len(local):
         raise ValueError(f"rank {rank} holds {len(local)} bags, expected {len(mine)}")
-    device = local[0].device if local else torch.device("cpu")
-    dtype = local[0].dtype if local else torch.float32
+    # a rank without bags (world_size > n_bags) must still join the collectives with tensors on the same
+    # kind of device as everybody else: `device` from the caller, else the backend's default
+    if local:
+        device, dtype = local[0].device, local[0].dtype
+    elif device is None:
+        device = _default_device(group)
     width = local[0].shape[1] if local else 0
     per_rank = (n_bags + world - 1) // world
     # sizes: [world, per_rank + 1] (last column = feature width, so empty ranks learn it too)
@@ -80,7 +93,7 @@ def encode_bags_parallel(encoder, bags: Sequence[torch.Tensor], group=None, gath
     local_out = encoder.forward_bags(local_in) if local_in else []
     if not gather:
         return local_out
-    return gather_ragged(local_out, len(bags), group=group, dst=dst)
+    return gather_ragged(local_out, len(bags), group=group, dst=dst, device=dev)
 
 
 @torch.no_grad()
@@ -151,3 +164,82 @@ def allreduce_gradients(params, group=None, bucket_bytes: int = 32 << 20, averag
             p.grad.copy_(flat[off:off + n].view_as(p.grad))
             off += n
     return len(buckets)
+
+
+class GradReducer:
+    """Data-parallel gradient averaging OVERLAPPED with the backward pass (BASELINE configs[4]; the reference has
+    no distributed training at all, main.py:103).
+
+    ``groups`` is a list of parameter lists in the order their gradients become available during backward (for
+    ``RRTMIL``: pooling head + predictor, encoder, ``patch_to_emb``).  A post-accumulate hook on every parameter
+    counts the group down; when the last gradient of a group has been written, the group is packed into one flat
+    bucket and its all-reduce is launched asynchronously -- the collective of the head runs under the encoder's
+    backward kernels, the encoder's under ``patch_to_emb``'s.  ``finish()`` (call it after ``loss.backward()``,
+    before the optimizer step) waits for the collectives, averages and scatters the buckets back into ``.grad``.
+    Parameters that received no gradient in a step contribute zeros, so every rank reduces the same layout.
+    """
+
+    def __init__(self, groups, group=None, average: bool = True):
+        self.pg = group
+        self.average = average
+        self.world = dist.get_world_size(group)
+        self.groups = [[p for p in g if p.requires_grad] for g in groups]
+        self.groups = [g for g in self.groups if g]
+        self._pending = [len(g) for g in self.groups]
+        self._work = []          # (group index, flat, handle)
+        self._launched = [False] * len(self.groups)
+        self._hooks = []
+        if self.world > 1:
+            for gi, g in enumerate(self.groups):
+                for p in g:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(gi)))
+
+    def _make_hook(self, gi):
+        def hook(_param):
+            self._pending[gi] -= 1
+            if self._pending[gi] == 0:
+                self._launch(gi)
+        return hook
+
+    def _launch(self, gi):
+        g = self.groups[gi]
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in g])
+        self._work.append((gi, flat, dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)))
+        self._launched[gi] = True
+
+    def finish(self) -> int:
+        """Waits for the launched collectives (launching those of groups whose hooks did not all fire), writes
+        the averaged gradients back; returns the number of collectives of this step and re-arms the hooks."""
+        if self.world == 1:
+            return 0
+        for gi in range(len(self.groups)):
+            if not self._launched[gi]:
+                self._launch(gi)
+        n = len(self._work)
+        for gi, flat, handle in self._work:
+            handle.wait()
+            if self.average:
+                flat.div_(self.world)
+            off = 0
+            for p in self.groups[gi]:
+                k = p.numel()
+                if p.grad is None:
+                    p.grad = flat[off:off + k].view_as(p).clone()
+                else:
+                    p.grad.copy_(flat[off:off + k].view_as(p.grad))
+                off += k
+        self._work = []
+        self._pending = [len(g) for g in self.groups]
+        self._launched = [False] * len(self.groups)
+        return n
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def rrtmil_grad_groups(model):
+    """The three groups of an ``RRTMIL`` in backward order: head (pooling + predictor), encoder, patch_to_emb."""
+    head = list(model.pool_fn.parameters()) + list(model.predictor.parameters())
+    return [head, list(model.online_encoder.parameters()), list(model.patch_to_emb.parameters())]

@@ -16,18 +16,24 @@ def hazards_and_survival(logits: torch.Tensor):
 
 
 def nll_surv_loss(hazards, S, Y, c, alpha: float = 0.0, eps: float = 1e-7):
-    """Negative log-likelihood survival loss (Survival/utils/loss.py:25-43).  ``Y``: ground-truth bin
-    ``[B]`` (long), ``c``: censorship status ``[B]`` (0 = event observed)."""
-    B = len(Y)
-    Y = Y.view(B, 1)
-    c = c.view(B, 1).float()
+    """Discrete-time survival negative log-likelihood, same value as the reference's ``nll_loss``
+    (Survival/utils/loss.py:25-43), stated per sample instead of through a padded survival table:
+
+        event observed in bin y (c = 0):   -( log S(y - 1) + log h(y) ),   S(-1) = 1
+        censored in bin y       (c = 1):   -  log S(y)
+
+    and ``loss = mean(event + (1 - alpha) * censored)``.  ``hazards``, ``S``: ``[B, n_bins]``; ``Y``: bin index
+    ``[B]``; ``c``: censorship flag ``[B]``.  Logs are taken of values clamped at ``eps``."""
+    y = Y.reshape(-1).long()
+    cens = c.reshape(-1).to(hazards.dtype)
     if S is None:
-        S = torch.cumprod(1 - hazards, dim=1)
-    S_padded = torch.cat([torch.ones_like(c), S], 1)
-    uncensored = -(1 - c) * (torch.log(torch.gather(S_padded, 1, Y).clamp(min=eps)) +
-                             torch.log(torch.gather(hazards, 1, Y).clamp(min=eps)))
-    censored = -c * torch.log(torch.gather(S_padded, 1, Y + 1).clamp(min=eps))
-    return ((1 - alpha) * (censored + uncensored) + alpha * uncensored).mean()
+        S = (1 - hazards).cumprod(dim=1)
+    rows = torch.arange(y.numel(), device=y.device)
+    log_s_here = S[rows, y].clamp_min(eps).log()
+    s_before = torch.where(y > 0, S[rows, (y - 1).clamp_min(0)], torch.ones_like(log_s_here))
+    log_event = s_before.clamp_min(eps).log() + hazards[rows, y].clamp_min(eps).log()
+    per_sample = -(1 - cens) * log_event - (1 - alpha) * cens * log_s_here
+    return per_sample.mean()
 
 
 class SurvivalRRTMIL(RRTMIL):

@@ -206,7 +206,8 @@ def test_concurrent_lanes_equal_serial_per_bag_forward():
 
 
 @pytest.mark.parametrize("knob,value,restore", [
-    ("rrt_debug_set_attention_kernel", 1, 0),   # tcgen05 attention core (S, O on tcgen05.mma, TMEM softmax)
+    ("rrt_debug_set_attention_kernel", 2, 1),   # tcgen05 attention core wherever supported (auto: regions > 128)
+    ("rrt_debug_set_attention_kernel", 0, 1),   # mma.sync attention core everywhere
     ("rrt_debug_set_gemm_cluster", 2, 11),      # cta_group::2 GEMM (CTA pairs, M=256 tiles)
     ("rrt_debug_set_gemm_cluster", 21, 11),     # 2x1 cluster, TMA multicast of the W tile
     ("rrt_debug_set_gemm_cluster", 22, 11),     # 2x2 cluster, multicast of both operand tiles
@@ -218,7 +219,7 @@ def test_alternative_kernel_variants_keep_parity(knob, value, restore):
     lib = cabi.lib()
     getattr(lib, knob)(value)
     try:
-        for name in ("c2_n9000_d512", "plip_k9_shortcut", "c4_n50000_g16"):
+        for name in ("c2_n9000_d512", "plip_k9_shortcut", "c4_n50000_g16", "c1_n512_d512", "n65", "d256_g4"):
             cfg, w, x, gold = load_case(name)
             m = G.make_encoder(cfg, w)
             with torch.no_grad():

@@ -137,3 +137,26 @@ def test_drops_into_the_reference_mil_hosts(host):
     assert float((enc.norm.weight.detach() - 1).abs().sum()) == 0.0
     assert sum(p.numel() for p in enc.parameters()) == sum(
         p.numel() for p in [m for m in theirs.modules() if isinstance(m, ref_rrt.RRTEncoder)][0].parameters())
+
+
+def test_encoder_survives_deepcopy_and_pickle_with_populated_caches():
+    """EMA / teacher copies (copy.deepcopy) and torch.save(model) must work after a forward has populated the
+    pointer caches (ctypes structs, fp16 shadows, the parameter-walk closure): none of them may travel."""
+    import copy
+    import io
+    m = RRTEncoder(mlp_dim=128, n_heads=4, crmsa_heads=4, need_init=True)
+    m._named_param_cache()
+    m.__dict__["_w_cache"] = (("cpu", False, ()), object.__new__(type("Opaque", (), {"__reduce__": None})))
+    m._shadow[1] = ((0, 0), torch.zeros(1))
+    c = copy.deepcopy(m)
+    assert "_w_cache" not in c.__dict__ and "_np_cache" not in c.__dict__ and c._shadow == {}
+    assert bytes(c._cfg) == bytes(m._cfg) and c._cfg is not m._cfg
+    for (n1, p1), (n2, p2) in zip(m.named_parameters(), c.named_parameters()):
+        assert n1 == n2 and p1 is not p2 and torch.equal(p1, p2)
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    r = torch.load(buf, weights_only=False)
+    assert bytes(r._cfg) == bytes(m._cfg) and r.state_dict().keys() == m.state_dict().keys()
+    # the copy is a working module: it rebuilds its caches on demand
+    assert [n for n in r._named_param_cache()[0]] == [n for n, _ in m.named_parameters()]

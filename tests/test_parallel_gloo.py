@@ -134,3 +134,71 @@ def test_logits_gather_world2(lens):
     results = mgr.dict()
     mp.spawn(_logit_worker, args=(world, port, lens, results), nprocs=world, join=True)
     assert dict(results) == {0: True, 1: True}
+
+
+def _reducer_worker(rank, world, port, results):
+    """GradReducer: hooks launch one asynchronous all-reduce per group while backward is still running; the
+    result must equal the serial average, step after step (hooks re-arm), also when a group gets no gradient."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        front, back = torch.nn.Linear(16, 32), torch.nn.Linear(32, 4)
+        unused = torch.nn.Linear(4, 4)                         # a group that never takes part in the loss
+        groups = [list(back.parameters()), list(front.parameters()), list(unused.parameters())]
+        red = parallel.GradReducer(groups)
+        g = torch.Generator().manual_seed(1)
+        ok = True
+        for step in range(3):
+            bags = [torch.randn(10 + 3 * i + step, 16, generator=g) for i in range(world)]
+            for q in [p for grp in groups for p in grp]:
+                q.grad = None
+            back(torch.tanh(front(bags[rank]))).square().mean().backward()
+            n = red.finish()
+            ok = ok and n == 3
+            ok = ok and all(q.grad is not None and float(q.grad.abs().sum()) == 0.0 for q in unused.parameters())
+            mine = [q.grad.clone() for q in list(back.parameters()) + list(front.parameters())]
+            ref = [torch.zeros_like(q) for q in mine]
+            for b in bags:
+                for q in [p for grp in groups for p in grp]:
+                    q.grad = None
+                back(torch.tanh(front(b))).square().mean().backward()
+                for r, q in zip(ref, list(back.parameters()) + list(front.parameters())):
+                    r += q.grad / world
+            red._pending = [len(grp) for grp in red.groups]     # the oracle passes fired the hooks too: re-arm
+            for _, _, h in red._work:
+                h.wait()
+            red._work, red._launched = [], [False] * len(red.groups)
+            ok = ok and all(torch.allclose(a, b, atol=1e-6) for a, b in zip(mine, ref))
+        red.remove()
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_reducer_overlapped_allreduce_equals_serial_average_world2():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_reducer_worker, args=(world, port, results), nprocs=world, join=True)
+    assert dict(results) == {0: True, 1: True}
+
+
+def _empty_rank_worker(rank, world, port, results):
+    """world_size > n_bags: the rank without a bag must still join both collectives."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        bags = [torch.arange(12.0).view(3, 4)]
+        outs = parallel.encode_bags_parallel(_StandIn(), bags)
+        results[rank] = len(outs) == 1 and torch.equal(outs[0], 2.0 * bags[0] + 1.0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_with_a_rank_that_holds_no_bag_world2():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_empty_rank_worker, args=(world, port, results), nprocs=world, join=True)
+    assert dict(results) == {0: True, 1: True}
