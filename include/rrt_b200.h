@@ -223,6 +223,11 @@ RRT_API int rrt_debug_skip_stages(uint32_t mask);
 /* dst[i] = fp16(src[i]), round to nearest, saturating at +-65504.  dst is n fp16 values; n % 4 == 0. */
 RRT_API int rrt_convert_f16(const float* src, void* dst, int64_t n, void* stream);
 
+/* dst[i] = fp32(src[i]) for n fp16 (src_is_bf16 = 0) or bf16 values, n % 4 == 0.  The encoder's I/O contract is
+ * fp32; a host running under fp16 / bf16 autocast (the reference's --amp, main.py:101-102,439) hands it half rows,
+ * which are widened here (exact) before the path runs. */
+RRT_API int rrt_widen_f32(const void* src, int32_t src_is_bf16, float* dst, int64_t n, void* stream);
+
 /* The tcgen05/TMA/TMEM GEMM every linear layer of the path runs on, exposed for parity tests:
  * c[M,N] (fp32) = a[M,K] (fp16) @ w[N,K]^T (fp16) + bias[N] (fp32, may be NULL).
  * 16-byte aligned pointers; K % 64 == 0, N % 4 == 0. */

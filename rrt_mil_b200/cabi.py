@@ -143,6 +143,7 @@ SIGNATURES = {
     "rrt_debug_set_gemm_cluster": (C.c_int, [C.c_int32]),
     "rrt_debug_skip_stages": (C.c_int, [C.c_uint32]),
     "rrt_convert_f16": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "rrt_widen_f32": (C.c_int, [_P, C.c_int32, _P, C.c_int64, _P]),
     "rrt_linear_f16_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "rrt_linear_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "rrt_layernorm_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, _P]),

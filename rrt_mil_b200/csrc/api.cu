@@ -999,6 +999,13 @@ RRT_API int rrt_convert_f16(const float* src, void* dst, int64_t n, void* stream
   return RRT_OK;
 }
 
+RRT_API int rrt_widen_f32(const void* src, int32_t src_is_bf16, float* dst, int64_t n, void* stream) {
+  if (!src || !dst || n < 0 || n % 4) return fail(RRT_E_INVALID, "bad argument");
+  StageScope s_(kStOther, (cudaStream_t)stream);
+  RRT_CUDA(rrt::launch_widen_f32(src, src_is_bf16 != 0, dst, (size_t)n, (cudaStream_t)stream), "widen to fp32");
+  return RRT_OK;
+}
+
 RRT_API int rrt_linear_f16_forward(const void* a_f16, const void* w_f16, const float* bias, float* c,
                                    int64_t M, int32_t N, int32_t K, void* stream) {
   if (!a_f16 || !w_f16 || !c || M < 1 || M > (1 << 30)) return fail(RRT_E_INVALID, "bad argument");

@@ -601,6 +601,24 @@ __global__ void convert_f16_kernel(const float* __restrict__ src, __half* __rest
     reinterpret_cast<uint2*>(dst)[i] = pack_h4(__ldg(reinterpret_cast<const float4*>(src) + i));
 }
 
+// 16-bit floating point rows (fp16 or bf16: an autocast host feeds the encoder half tensors, main.py:439) -> fp32
+template <bool BF16>
+__global__ void widen_f32_kernel(const uint2* __restrict__ src, float4* __restrict__ dst, size_t n4) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const uint2 u = __ldg(src + i);
+    float4 v;
+    if (BF16) {
+      v = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                      __uint_as_float(u.y & 0xffff0000u));
+    } else {
+      v = unpack_h4(u);
+    }
+    dst[i] = v;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -719,6 +737,18 @@ cudaError_t launch_convert_f16(const float* src, __half* dst, size_t n, cudaStre
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   convert_f16_kernel<<<blocks, 256, 0, stream>>>(src, dst, n4);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_widen_f32(const void* src, bool bf16, float* dst, size_t n, cudaStream_t stream) {
+  if (n % 4 || ((reinterpret_cast<uintptr_t>(src) & 7) | (reinterpret_cast<uintptr_t>(dst) & 15)))
+    return cudaErrorInvalidValue;
+  const size_t n4 = n / 4;
+  if (n4 == 0) return cudaSuccess;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (bf16) widen_f32_kernel<true><<<blocks, 256, 0, stream>>>(static_cast<const uint2*>(src), reinterpret_cast<float4*>(dst), n4);
+  else widen_f32_kernel<false><<<blocks, 256, 0, stream>>>(static_cast<const uint2*>(src), reinterpret_cast<float4*>(dst), n4);
   return cudaGetLastError();
 }
 

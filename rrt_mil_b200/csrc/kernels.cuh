@@ -57,6 +57,9 @@ extern long long* g_gemm_trace;  // debug: device buffer [8 CTAs][16] of clock64
 // dst[i] = fp16(src[i]) round-to-nearest, saturating; n % 4 == 0
 cudaError_t launch_convert_f16(const float* src, __half* dst, size_t n, cudaStream_t stream);
 
+// dst[i] = fp32(src[i]) for fp16 (bf16 = false) or bf16 rows; n % 4 == 0, src 8-byte / dst 16-byte aligned
+cudaError_t launch_widen_f32(const void* src, bool bf16, float* dst, size_t n, cudaStream_t stream);
+
 // ---- gemm_mma.cu ----------------------------------------------------------------------
 // fp32-in / fp32-out c = a @ w^T (+epilogue) on mma.sync tf32: the general-purpose linear of the
 // C ABI (rrt_linear_forward) for callers whose operands are not fp16.  K % 32 == 0.

@@ -431,8 +431,12 @@ class RRTEncoder(nn.Module):
     def _check_mode(self, x, allow_grad=False):
         if not x.is_cuda:
             raise RuntimeError("RRTEncoder (rrt_mil_b200) runs on CUDA only; there is no CPU fallback")
-        if x.dtype != torch.float32:
-            raise NotImplementedError(f"input dtype {x.dtype}: only float32 bags are supported")
+        if x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            raise NotImplementedError(f"input dtype {x.dtype}: float32 bags (or float16 / bfloat16 rows from an "
+                                      "autocast host, widened to float32) are supported")
+        if x.dtype != torch.float32 and self._needs_grad(x):
+            raise NotImplementedError("half-precision inputs are an inference convenience (autocast hosts); "
+                                      "train with float32 bags")
         if self._needs_grad(x):
             if not allow_grad:
                 raise NotImplementedError("forward_bags is inference-only: call it under "
@@ -463,6 +467,20 @@ class RRTEncoder(nn.Module):
         if self.training and self.drop_out > 0 and not allow_grad:
             raise NotImplementedError("forward_bags is inference-only (no dropout): call .eval() first")
 
+    @staticmethod
+    def _as_f32(x: torch.Tensor) -> torch.Tensor:
+        """float16 / bfloat16 rows (a host under autocast: the reference's ``--amp``, main.py:101-102,439) are
+        widened to float32 by the library; like the reference under autocast (its LayerNorms run in float32),
+        the result is float32."""
+        if x.dtype == torch.float32:
+            return x
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = cabi.lib().rrt_widen_f32(x.data_ptr(), int(x.dtype == torch.bfloat16), out.data_ptr(), x.numel(),
+                                          torch.cuda.current_stream(x.device).cuda_stream)
+        cabi.check(rc, "rrt_widen_f32")
+        return out
+
     def forward_bag(self, x: torch.Tensor) -> torch.Tensor:
         """One bag ``[N, D]`` float32 CUDA -> ``[N, D]``; enqueues on the current stream."""
         self._check_mode(x, allow_grad=True)
@@ -471,7 +489,7 @@ class RRTEncoder(nn.Module):
         N = x.shape[0]
         if N < 1:
             raise ValueError("empty bag")
-        x = x.contiguous()
+        x = self._as_f32(x.contiguous())
         if self._needs_grad(x) or (self.training and self.drop_out > 0):
             # autograd / training path: forward with a tape (+ proj dropout), backward kernels
             return _EncoderFunction.apply(self, x, *self._named_param_cache()[1])
@@ -501,6 +519,7 @@ class RRTEncoder(nn.Module):
             if x.device != bags[0].device:
                 raise ValueError("all bags of one call must live on the same device")
         device = bags[0].device
+        bags = [self._as_f32(x) for x in bags]
         if outs is None:
             outs = [torch.empty_like(x) for x in bags]
         n = len(bags)
