@@ -288,7 +288,8 @@ RRT_API int rrt_attn_pool_forward(const float* h, int64_t L, int32_t dim, int32_
  * zero-initialised by the caller (bias / LayerNorm / tap / phi gradients are accumulated with
  * atomics; weight gradients are overwritten).  Tensor-core operands of the backward GEMMs are fp16
  * with automatic per-stage power-of-two scaling (csrc/backward.cuh), accumulators fp32.
- * Not covered (RRT_E_INVALID): crmsa_mlp, crmsa_k > 8, head_dim 128, regions > 256 tokens. */
+ * crmsa_mlp (logits = phi.2 tanh(phi.0 z)): gradients of both weights; needs dim 512 or 1024.
+ * Not covered (RRT_E_INVALID): crmsa_k > 8, head_dim other than 32 / 64, regions > 256 tokens, PEG / PPEG, FFN. */
 typedef struct rrt_attn_grads {
   float* qkv_w;  /* [3D, D] */
   float* qkv_b;  /* [3D] or NULL */
@@ -307,6 +308,8 @@ typedef struct rrt_grads {
   float* cr_norm_b;
   float* cr_phi; /* [D, k] */
   rrt_attn_grads cr_attn;
+  float* cr_phi_w1; /* crmsa_mlp: phi.0.weight [D/4, D] */
+  float* cr_phi_w2; /* crmsa_mlp: phi.2.weight [k, D/4] */
 } rrt_grads;
 
 RRT_API int rrt_train_tape_bytes(const rrt_config* cfg, int64_t L, size_t* bytes);

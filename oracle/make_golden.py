@@ -92,6 +92,8 @@ TRAIN_CASES = [
     ("train_d256_shortcut_p25", 500, dict(mlp_dim=256, region_num=4, epeg_k=5, crmsa_k=4, crmsa_heads=4,
                                           all_shortcut=True, n_layers=3), 0.25, 77),
     ("train_n700_p0", 700, dict(), 0.0, 0),   # eval-arithmetic backward pinned against reference autograd
+    # crmsa_mlp (phi = Linear -> tanh -> Linear, modules/rmsa.py:248-252; README.md:119 trains with it)
+    ("train_mlp_k5_p10", 600, dict(crmsa_mlp=True, crmsa_k=5, epeg_k=9), 0.1, 31337),
 ]
 GRAD_SEED = 43
 # Full RRTMIL train step: name, L, input_dim, n_classes, da_act, da_bias, label, encoder
@@ -205,7 +207,11 @@ def crmsa_tie_gap(x, w, cfg, drop):
     if rs == 1:
         return float("inf")
     z = O._to_regions(O.layer_norm(h, w["cr_msa.norm.weight"], w["cr_msa.norm.bias"]), L, H, rs)
-    srt = (z @ w["cr_msa.attn.phi"]).sort(1).values  # [R,P,k]
+    if cfg.crmsa_mlp:
+        lg = torch.tanh(z @ w["cr_msa.attn.phi.0.weight"].T) @ w["cr_msa.attn.phi.2.weight"].T
+    else:
+        lg = z @ w["cr_msa.attn.phi"]
+    srt = lg.sort(1).values  # [R,P,k]
     rng = (srt[:, -1] - srt[:, 0]).clamp_min(1e-300)
     gaps = torch.cat([(srt[:, 1] - srt[:, 0]) / rng, (srt[:, -1] - srt[:, -2]) / rng])
     real = (O.region_slot_map(H, rs) < L).view(-1, rs * rs).any(1).repeat(2)

@@ -83,6 +83,7 @@ class RrtGrads(C.Structure):
         ("layer_attn", RrtAttnGrads * RRT_MAX_RMSA_LAYERS),
         ("cr_norm_w", c_float_p), ("cr_norm_b", c_float_p), ("cr_phi", c_float_p),
         ("cr_attn", RrtAttnGrads),
+        ("cr_phi_w1", c_float_p), ("cr_phi_w2", c_float_p),
     ]
 
 

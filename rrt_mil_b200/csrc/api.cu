@@ -1068,6 +1068,11 @@ struct BwdWorkspace {
   float* dh;       // [L, D] gradient wrt the final norm's input
   float* ga;       // [L, D] residual-stream gradient ping
   float* gb;       // [L, D] pong
+  // crmsa_mlp only
+  float* dlogits;  // [Np_c, k]   (zeroed per call: pad slots keep 0)
+  float* dpre;     // [Np_c, D/4] gradient wrt the tanh pre-activation
+  __half* dpre16;  // [Np_c, D/4] scaled
+  __half* dzc16;   // [Np_c, D]   gradient wrt LN_cr(x1) through the MLP, scaled
   size_t bytes;
 };
 
@@ -1109,14 +1114,25 @@ bool carve_bwd(const rrt_config* c, int64_t L, void* base, BwdWorkspace* b) {
   b->dh = (float*)take((size_t)L * D * 4);
   b->ga = (float*)take((size_t)L * D * 4);
   b->gb = (float*)take((size_t)L * D * 4);
+  const bool mlp = c->cr_msa && c->crmsa_mlp;
+  b->dlogits = (float*)take(mlp ? np_c * k * 4 : 0);
+  b->dpre = (float*)take(mlp ? np_c * (D / 4) * 4 : 0);
+  b->dpre16 = (__half*)take(mlp ? np_c * (D / 4) * 2 : 0);
+  b->dzc16 = (__half*)take(mlp ? np_c * D * 2 : 0);
   b->bytes = off + 256;
   return true;
+}
+
+bool wgrad_mn() {
+  static const bool on = [] { const char* e = getenv("RRT_WGRAD"); return !(e && !strcmp(e, "transpose")); }();
+  return on;
 }
 
 int check_backward_support(const rrt_config* c, int64_t L) {
   if (c->pos != RRT_POS_NONE) return fail(RRT_E_INVALID, "backward: PEG / PPEG (ablation) is not covered");
   if (c->ffn) return fail(RRT_E_INVALID, "backward: the FFN ablation is not covered");
-  if (c->cr_msa && c->crmsa_mlp) return fail(RRT_E_INVALID, "backward: crmsa_mlp is not covered");
+  if (c->cr_msa && c->crmsa_mlp && ((c->dim / 4) % 128 != 0 || !wgrad_mn()))
+    return fail(RRT_E_INVALID, "backward: crmsa_mlp needs dim in {512, 1024} (and the default MN-major weight-gradient path)");
   if (c->n_rmsa_layers == 0 && !c->cr_msa) return fail(RRT_E_INVALID, "backward: encoder has no block");
   if (c->n_rmsa_layers > 0) {
     rrt::Grid g{};
@@ -1140,10 +1156,6 @@ int check_backward_support(const rrt_config* c, int64_t L) {
 // act: the forward's fp16 input rows [M, C_in].
 // 1 (default): weight gradients read dy / act MN-major straight from their row-major buffers
 // (launch_gemm_tcgen05_wgrad); 0 (RRT_WGRAD=transpose): transposed fp16 copies + the K-major GEMM.
-bool wgrad_mn() {
-  static const bool on = [] { const char* e = getenv("RRT_WGRAD"); return !(e && !strcmp(e, "transpose")); }();
-  return on;
-}
 
 int linear_backward(const __half* dy, const __half* dyT, const __half* act, const float* w, int M,
                     int C_out, int C_in, const uint32_t* amax, __half* d_in, float* dW,
@@ -1210,7 +1222,9 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
     rrt::Grid gc{};
     if (!crmsa_grid(L, &gc)) return fail(RRT_E_INVALID, "bad geometry");
     const int k = c->crmsa_k, T = k * gc.R;
-    if (!gr->norm_w || !gr->norm_b || !gr->cr_norm_w || !gr->cr_norm_b || !gr->cr_phi ||
+    const bool mlp = c->crmsa_mlp != 0;
+    if (!gr->norm_w || !gr->norm_b || !gr->cr_norm_w || !gr->cr_norm_b || (!mlp && !gr->cr_phi) ||
+        (mlp && (!gr->cr_phi_w1 || !gr->cr_phi_w2 || !w->cr_phi_w1 || !w->cr_phi_w2)) ||
         !gr->cr_attn.qkv_w || !gr->cr_attn.proj_w || !gr->cr_attn.proj_b ||
         (c->qkv_bias && !gr->cr_attn.qkv_b))
       return fail(RRT_E_INVALID, "NULL gradient buffer");
@@ -1232,11 +1246,40 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
     if (rc) return rc;
     float* out = nl > 0 ? b.ga : dx;
     const float dh_weight = (nl == 0 && c->all_shortcut) ? 2.f : 1.f;
-    { StageScope s_(kStBwdCr, st);
+    if (!mlp) {
+      StageScope s_(kStBwdCr, st);
       RRT_CUDA(rrt::launch_crmsa_combine_bwd(x_last, w->cr_norm_w, w->cr_norm_b, w->cr_phi, tp.logits,
                                              tp.rstat, tp.lm, b.dz, &b.amax[0], b.dw, b.rgrad, b.dh,
                                              dh_weight, out, gr->cr_phi, gr->cr_norm_w, gr->cr_norm_b,
-                                             &b.amax[1], gc, D, k, st), "crmsa combine backward"); }
+                                             &b.amax[1], gc, D, k, st), "crmsa combine backward");
+    } else {
+      // logits = phi.2 tanh(phi.0 z): pass 1 emits dlogits, the MLP backward turns them into dW2, dW1 and the
+      // gradient wrt z (fp16, scaled by amax[30]), pass 2 adds it to the combine path and finishes LN_cr
+      const int H4 = D / 4;
+      { StageScope s_(kStBwdCr, st, 3);
+        RRT_CUDA(cudaMemsetAsync(b.dlogits, 0, (size_t)gc.Np * k * sizeof(float), st), "zero dlogits");
+        RRT_CUDA(cudaMemsetAsync(gr->cr_phi_w2, 0, (size_t)k * H4 * sizeof(float), st), "zero dW2");
+        RRT_CUDA(rrt::launch_crmsa_combine_bwd(x_last, w->cr_norm_w, w->cr_norm_b, nullptr, tp.logits, tp.rstat,
+                                               tp.lm, b.dz, &b.amax[0], b.dw, b.rgrad, b.dh, dh_weight, out,
+                                               nullptr, gr->cr_norm_w, gr->cr_norm_b, nullptr, gc, D, k, st, 1,
+                                               b.dlogits), "crmsa combine backward (logit gradients)");
+        RRT_CUDA(rrt::launch_crmsa_mlp_hidden_bwd(b.dlogits, tp.hidden, w->cr_phi_w2, b.dpre, gr->cr_phi_w2, gc.Np,
+                                                  H4, k, st), "crmsa_mlp hidden backward"); }
+      rrt::Grid idn{};
+      idn.L = gc.Np; idn.Np = gc.Np;
+      { StageScope s_(kStBwdPrep, st, 2);
+        RRT_CUDA(rrt::launch_amax(b.dpre, (size_t)gc.Np * H4, &b.amax[30], st), "amax");
+        RRT_CUDA(rrt::launch_grad_partition(b.dpre, idn, gc.Np, H4, &b.amax[30], b.dpre16, nullptr, nullptr, st),
+                 "crmsa_mlp grad rows"); }
+      int rc2 = linear_backward(b.dpre16, nullptr, tp.zc, w->cr_phi_w1, gc.Np, H4, D, &b.amax[30], b.dzc16,
+                                gr->cr_phi_w1, b, st);
+      if (rc2) return rc2;
+      StageScope s_(kStBwdCr, st);
+      RRT_CUDA(rrt::launch_crmsa_combine_bwd(x_last, w->cr_norm_w, w->cr_norm_b, nullptr, tp.logits, tp.rstat,
+                                             tp.lm, b.dz, &b.amax[0], b.dw, b.rgrad, b.dh, dh_weight, out, nullptr,
+                                             gr->cr_norm_w, gr->cr_norm_b, &b.amax[1], gc, D, k, st, 2, nullptr,
+                                             b.dzc16, &b.amax[30]), "crmsa combine backward (crmsa_mlp)");
+    }
     g = out;
     am = 1;
   } else {

@@ -183,7 +183,11 @@ __global__ void __launch_bounds__(256) crmsa_dispatch_bwd_kernel(
 }
 
 // grid (R, chunks), 256 threads; smem: dLs[KMAX][D] | Ph[KMAX][D] | red[8][D] | rs[4][KMAX]
-template <int V, int KMAX>
+// MODE 0: logits = z phi (linear landmark directions).
+// crmsa_mlp (logits = W2 tanh(W1 z), modules/rmsa.py:248-252,305) takes two passes around the MLP backward:
+// MODE 1 only emits the logit gradient dl[slot, n] (-> dlogits), MODE 2 replaces the dl . phi term of dz by the
+// MLP's input gradient (dzx16: fp16 rows in slot order, scaled by amax_x) and finishes the LayerNorm backward.
+template <int V, int KMAX, int MODE>
 __global__ void __launch_bounds__(256) crmsa_combine_bwd_kernel(
     const float* __restrict__ x1, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ phi, const float* __restrict__ logits, const float2* __restrict__ rstat,
@@ -191,7 +195,8 @@ __global__ void __launch_bounds__(256) crmsa_combine_bwd_kernel(
     const uint32_t* __restrict__ amax_l, const float* __restrict__ dw, const float2* __restrict__ rgrad,
     const float* __restrict__ dh, float dh_weight, float* __restrict__ dx1, float* __restrict__ dphi,
     float* __restrict__ dgamma, float* __restrict__ dbeta, uint32_t* __restrict__ amax_out, Grid grid,
-    int k, int tpc) {
+    int k, int tpc, float* __restrict__ dlogits, const __half* __restrict__ dzx16,
+    const uint32_t* __restrict__ amax_x) {
   constexpr int D = 128 * V;
   extern __shared__ __align__(16) float smem[];
   float* dLs = smem;              // unscaled dL rows of this region
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(256) crmsa_combine_bwd_kernel(
   for (int i = tid; i < k * D; i += 256) {
     int n = i / D, c = i - n * D;
     dLs[i] = __half2float(dlm16[((size_t)n * grid.R + rho) * D + c]) * inv_s;
-    Ph[i] = __ldg(phi + (size_t)c * k + n);
+    if (MODE == 0) Ph[i] = __ldg(phi + (size_t)c * k + n);
   }
   __syncthreads();
   for (int n = warp; n < k; n += 8) {
@@ -290,9 +295,21 @@ __global__ void __launch_bounds__(256) crmsa_combine_bwd_kernel(
       if (lg == mm.x) dl += rg.x;
       if (lg == mm.y) dl += rg.y;
     }
+    if (MODE == 1) {  // the MLP backward runs between the passes: only the logit gradient leaves this one
+      if (lane < k) dlogits[(size_t)slot * k + lane] = dl;
+      continue;
+    }
     float4 dz[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) dz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == 2) {  // d z through the MLP (dgrad GEMM of phi.0), unscaled
+      const float inv_x = grad_inv_scale(__ldg(amax_x));
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float4 e = unpack_h4(__ldg(reinterpret_cast<const uint2*>(dzx16 + (size_t)slot * D) + lane + 32 * i));
+        dz[i] = make_float4(e.x * inv_x, e.y * inv_x, e.z * inv_x, e.w * inv_x);
+      }
+    }
 #pragma unroll
     for (int n = 0; n < KMAX; ++n) {
       if (n < k) {
@@ -300,8 +317,10 @@ __global__ void __launch_bounds__(256) crmsa_combine_bwd_kernel(
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           axpy4(dz[i], cwn, *reinterpret_cast<const float4*>(dLs + n * D + 4 * (lane + 32 * i)));
-          axpy4(dz[i], dln, *reinterpret_cast<const float4*>(Ph + n * D + 4 * (lane + 32 * i)));
-          axpy4(aphi[n][i], dln, z[i]);
+          if (MODE == 0) {
+            axpy4(dz[i], dln, *reinterpret_cast<const float4*>(Ph + n * D + 4 * (lane + 32 * i)));
+            axpy4(aphi[n][i], dln, z[i]);
+          }
         }
       }
     }
@@ -329,15 +348,56 @@ __global__ void __launch_bounds__(256) crmsa_combine_bwd_kernel(
       reinterpret_cast<float4*>(dx1 + (size_t)tok * D)[lane + 32 * i] = o;
     }
   }
+  if (MODE == 1) return;
   if (amax_out) {
     amax = warp_max(amax);
     if (lane == 0 && amax > 0.f) atomic_amax(amax_out, amax);
   }
+  if (MODE == 0) {
 #pragma unroll
-  for (int n = 0; n < KMAX; ++n)
-    if (n < k) cta_colsum_atomic<V>(aphi[n], red, dphi + n, k, warp, lane);
+    for (int n = 0; n < KMAX; ++n)
+      if (n < k) cta_colsum_atomic<V>(aphi[n], red, dphi + n, k, warp, lane);
+  }
   cta_colsum_atomic<V>(dg, red, dgamma, 1, warp, lane);
   cta_colsum_atomic<V>(db, red, dbeta, 1, warp, lane);
+}
+
+// Backward of logits = W2 tanh(pre) for one slot per warp: dpre[slot, j] = (sum_n dl[slot, n] W2[n, j]) (1 - h^2),
+// dW2[n, j] += dl[slot, n] h[slot, j].  h = tanh(pre) is the forward's hidden activation (fp32).  H4 = D / 4.
+template <int KMAX>
+__global__ void __launch_bounds__(256) crmsa_mlp_hidden_bwd_kernel(const float* __restrict__ dlogits,
+                                                                   const float* __restrict__ hidden,
+                                                                   const float* __restrict__ w2,
+                                                                   float* __restrict__ dpre, float* __restrict__ dw2,
+                                                                   int rows, int H4, int k) {
+  extern __shared__ __align__(16) float smem[];
+  float* W = smem;             // [k][H4]
+  float* acc = W + KMAX * H4;  // [k][H4] CTA partial of dW2
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < k * H4; i += 256) { W[i] = __ldg(w2 + i); acc[i] = 0.f; }
+  __syncthreads();
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+    const float dl = lane < k ? __ldg(dlogits + (size_t)r * k + lane) : 0.f;
+    if (__all_sync(0xffffffffu, dl == 0.f)) {   // pad slots and tokens whose logits carry no gradient
+      for (int j = lane; j < H4; j += 32) dpre[(size_t)r * H4 + j] = 0.f;
+      continue;
+    }
+    for (int j = lane; j < H4; j += 32) {
+      const float h = __ldg(hidden + (size_t)r * H4 + j);
+      float g = 0.f;
+#pragma unroll
+      for (int n = 0; n < KMAX; ++n)
+        if (n < k) {
+          const float d = __shfl_sync(0xffffffffu, dl, n);
+          g = fmaf(d, W[n * H4 + j], g);
+          atomicAdd(&acc[n * H4 + j], d * h);
+        }
+      dpre[(size_t)r * H4 + j] = g * (1.f - h * h);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < k * H4; i += 256)
+    if (acc[i] != 0.f) atomicAdd(dw2 + i, acc[i]);
 }
 
 int token_chunks(const Grid& g) {
@@ -393,18 +453,41 @@ cudaError_t launch_crmsa_combine_bwd(const float* x1, const float* gamma, const 
                                      const float* dw, const float2* rgrad, const float* dh,
                                      float dh_weight, float* dx1, float* dphi, float* dgamma,
                                      float* dbeta, uint32_t* amax_out, const Grid& grid, int D, int k,
-                                     cudaStream_t stream) {
-  if (!crmsa_backward_supported(D, k)) return cudaErrorInvalidValue;
+                                     cudaStream_t stream, int mode, float* dlogits, const __half* dzx16,
+                                     const uint32_t* amax_x) {
+  if (!crmsa_backward_supported(D, k) || mode < 0 || mode > 2) return cudaErrorInvalidValue;
+  if ((mode == 0 && !phi) || (mode == 1 && !dlogits) || (mode == 2 && (!dzx16 || !amax_x))) return cudaErrorInvalidValue;
   const int chunks = token_chunks(grid), tpc = (grid.P + chunks - 1) / chunks;
   dim3 gr(grid.R, chunks);
+#define RRT_CRB_LAUNCH(MODE_)                                                                                   \
+  {                                                                                                             \
+    auto kern = crmsa_combine_bwd_kernel<V, KM, MODE_>;                                                         \
+    cudaError_t e = set_smem(kern, smem);                                                                       \
+    if (e != cudaSuccess) return e;                                                                             \
+    kern<<<gr, 256, smem, stream>>>(x1, gamma, beta, phi, logits, rstat, lm16, dlm16, amax_l, dw, rgrad, dh,    \
+                                    dh_weight, dx1, dphi, dgamma, dbeta, amax_out, grid, k, tpc, dlogits,       \
+                                    dzx16, amax_x);                                                             \
+  }
   RRT_CRB_DISPATCH(D, k, {
     size_t smem = ((size_t)(2 * KM + 8) * D + 4 * KM) * sizeof(float);
-    auto kern = crmsa_combine_bwd_kernel<V, KM>;
-    cudaError_t e = set_smem(kern, smem);
-    if (e != cudaSuccess) return e;
-    kern<<<gr, 256, smem, stream>>>(x1, gamma, beta, phi, logits, rstat, lm16, dlm16, amax_l, dw, rgrad,
-                                    dh, dh_weight, dx1, dphi, dgamma, dbeta, amax_out, grid, k, tpc);
+    if (mode == 0) RRT_CRB_LAUNCH(0) else if (mode == 1) RRT_CRB_LAUNCH(1) else RRT_CRB_LAUNCH(2)
   });
+#undef RRT_CRB_LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t launch_crmsa_mlp_hidden_bwd(const float* dlogits, const float* hidden, const float* w2, float* dpre,
+                                        float* dw2, int rows, int H4, int k, cudaStream_t stream) {
+  if (k < 1 || k > 8 || H4 < 1 || rows < 1) return cudaErrorInvalidValue;
+  int blocks = (rows + 7) / 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (k <= 4) {
+    size_t smem = (size_t)2 * 4 * H4 * sizeof(float);
+    crmsa_mlp_hidden_bwd_kernel<4><<<blocks, 256, smem, stream>>>(dlogits, hidden, w2, dpre, dw2, rows, H4, k);
+  } else {
+    size_t smem = (size_t)2 * 8 * H4 * sizeof(float);
+    crmsa_mlp_hidden_bwd_kernel<8><<<blocks, 256, smem, stream>>>(dlogits, hidden, w2, dpre, dw2, rows, H4, k);
+  }
   return cudaGetLastError();
 }
 

@@ -201,6 +201,11 @@ cudaError_t launch_crmsa_combine_bwd(const float* x1, const float* gamma, const 
                                      const float* dw, const float2* rgrad, const float* dh,
                                      float dh_weight, float* dx1, float* dphi, float* dgamma,
                                      float* dbeta, uint32_t* amax_out, const Grid& grid, int D, int k,
-                                     cudaStream_t stream);
+                                     cudaStream_t stream, int mode = 0, float* dlogits = nullptr,
+                                     const __half* dzx16 = nullptr, const uint32_t* amax_x = nullptr);
+// crmsa_mlp: backward of logits = W2 tanh(pre) (dpre fp32 [rows, H4], dW2 [k, H4] accumulated); mode 1 / 2 of
+// launch_crmsa_combine_bwd run before / after it (csrc/crmsa_bwd.cu)
+cudaError_t launch_crmsa_mlp_hidden_bwd(const float* dlogits, const float* hidden, const float* w2, float* dpre,
+                                        float* dw2, int rows, int H4, int k, cudaStream_t stream);
 
 }  // namespace rrt

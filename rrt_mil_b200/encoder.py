@@ -395,6 +395,7 @@ class RRTEncoder(nn.Module):
         if self._cfg.cr_msa:
             g.cr_norm_w, g.cr_norm_b = ptr("cr_msa.norm.weight"), ptr("cr_msa.norm.bias")
             g.cr_phi = ptr("cr_msa.attn.phi")
+            g.cr_phi_w1, g.cr_phi_w2 = ptr("cr_msa.attn.phi.0.weight"), ptr("cr_msa.attn.phi.2.weight")
             attn("cr_msa.attn.attn.", g.cr_attn)
         return g
 
@@ -441,8 +442,6 @@ class RRTEncoder(nn.Module):
             if not allow_grad:
                 raise NotImplementedError("forward_bags is inference-only: call it under "
                                           "torch.no_grad(), or use forward() for autograd")
-            if self._crmsa_mlp:
-                raise NotImplementedError("backward through crmsa_mlp=True is not built")
             if self._cfg.pos != cabi.RRT_POS_NONE:
                 raise NotImplementedError("backward through the PEG / PPEG ablation is not built")
             if self._cfg.ffn:

@@ -136,6 +136,8 @@ ENC_CASES = [
     ("shortcut_d256", 300, dict(mlp_dim=256, region_num=4, epeg_k=5, crmsa_k=4, crmsa_heads=4, all_shortcut=True)),
     ("three_layers", 2500, dict(region_num=16, n_layers=3, epeg_k=21, crmsa_k=5)),
     ("tiny", 50, dict()),
+    ("crmsa_mlp_k5", 600, dict(crmsa_mlp=True, crmsa_k=5)),           # README NSCLC-PLIP recipe's phi (README.md:119)
+    ("crmsa_mlp_shortcut", 400, dict(crmsa_mlp=True, all_shortcut=True, region_num=4, epeg_k=7)),
     ("n9000", 9000, dict()),
     ("n50000_g16", 50000, dict(region_num=16)),     # BASELINE configs[3] shape: P = 196 (R-MSA), 784 (CR-MSA)
 ]
@@ -249,3 +251,17 @@ def test_backward_rejects_unsupported():
     m2 = G.make_encoder(O.EncoderConfig(), O.make_weights(O.EncoderConfig(), 3)).train()
     with pytest.raises(NotImplementedError):     # the batch entry point is inference-only
         m2.forward_bags([x.detach()])
+
+
+def test_backward_limits_are_reported_before_the_forward():
+    """Limits that depend on the bag or on derived sizes raise at the call, not inside loss.backward()."""
+    cases = [(dict(mlp_dim=256, n_heads=4, crmsa_heads=4, crmsa_mlp=True), 300),   # crmsa_mlp hidden width 64
+             (dict(crmsa_heads=1), 300),                                           # CR-MSA head_dim 512
+             (dict(), 20000)]                                                      # R-MSA regions of 324 tokens
+    for over, L in cases:
+        m = RRTEncoder(**over).cuda().train()
+        x = torch.randn(1, L, m.final_dim, device="cuda")
+        with pytest.raises(NotImplementedError, match="not covered"):
+            m(x)
+        with torch.no_grad():
+            m.eval()(x)     # inference is unaffected
