@@ -289,7 +289,8 @@ RRT_API int rrt_attn_pool_forward(const float* h, int64_t L, int32_t dim, int32_
  * atomics; weight gradients are overwritten).  Tensor-core operands of the backward GEMMs are fp16
  * with automatic per-stage power-of-two scaling (csrc/backward.cuh), accumulators fp32.
  * crmsa_mlp (logits = phi.2 tanh(phi.0 z)): gradients of both weights; needs dim 512 or 1024.
- * Not covered (RRT_E_INVALID): crmsa_k > 8, head_dim other than 32 / 64, regions > 256 tokens, PEG / PPEG, FFN. */
+ * Not covered (RRT_E_INVALID): crmsa_k > 8, R-MSA head_dim other than 32 / 64, CR-MSA head_dim 128, regions > 256
+ * tokens, PEG / PPEG, FFN. */
 typedef struct rrt_attn_grads {
   float* qkv_w;  /* [3D, D] */
   float* qkv_b;  /* [3D] or NULL */
@@ -328,8 +329,9 @@ RRT_API int rrt_dropout_mask(float* out, int64_t n, float drop_p, uint64_t seed,
                              void* stream);
 /* RRT_OK when rrt_encoder_backward covers this configuration AND this bag length, else RRT_E_INVALID with the
  * reason in rrt_last_error().  The limits depend on the bag, not only on the configuration: the R-MSA backward
- * keeps a region resident (regions of at most 256 tokens: N <= 16384 at region_num = 8), R-MSA / CR-MSA head_dim
- * must be 32 or 64 (crmsa_heads = 1 at dim 512 is not covered), crmsa_k <= 8, no crmsa_mlp / PEG / PPEG / FFN.
+ * keeps a region resident (regions of at most 256 tokens: N <= 16384 at region_num = 8), R-MSA head_dim must be
+ * 32 or 64, CR-MSA head_dim anything but 128 (crmsa_heads = 1 runs an fp32 landmark backward), crmsa_k <= 8,
+ * crmsa_mlp needs dim 512 / 1024, no PEG / PPEG / FFN.
  * Callers check it BEFORE the taped forward, so that a training loop fails at the first call and not inside
  * loss.backward(). */
 RRT_API int rrt_backward_supported(const rrt_config* cfg, int64_t L);

@@ -1145,8 +1145,9 @@ int check_backward_support(const rrt_config* c, int64_t L) {
   if (c->cr_msa) {
     if (!rrt::crmsa_backward_supported(c->dim, c->crmsa_k))
       return fail(RRT_E_INVALID, "backward: CR-MSA needs dim in {128,256,512,1024} and crmsa_k <= 8");
-    if (!rrt::rmsa_attention_bwd_supported(64, c->dim, c->crmsa_heads, 1))
-      return fail(RRT_E_INVALID, "backward: CR-MSA head_dim must be 32 or 64");
+    const int cr_hd = c->dim / c->crmsa_heads;
+    if (cr_hd == 128 || (cr_hd != 32 && cr_hd != 64 && cr_hd % 32 != 0))
+      return fail(RRT_E_INVALID, "backward: CR-MSA head_dim 128 is not covered (32, 64 and any other multiple of 32 are)");
   }
   return RRT_OK;
 }
@@ -1189,17 +1190,23 @@ int linear_backward(const __half* dy, const __half* dyT, const __half* act, cons
 
 // Backward of one attention module on rows in slot order: dy (scaled fp16 [M, D], + transpose) is the
 // gradient wrt the projection output.  Leaves the gradient wrt the module input (z / landmarks) in b.dz.
+// qkv_f32 != null: the landmark MHA with a head_dim outside the tensor-core attention kernels (crmsa_heads = 1);
+// its forward kept q / k / v in fp32 and the backward of the core is the fp32 kernel (64 tokens per sequence).
 int attention_module_backward(const rrt_config* c, const rrt_attn_weights* a, const rrt_attn_grads* ga,
                               const __half* z, const __half* qkv, const __half* o, int R, int P,
                               int heads, bool epeg, const uint32_t* amax, BwdWorkspace& b,
-                              cudaStream_t st) {
+                              cudaStream_t st, const float* qkv_f32 = nullptr) {
   const int D = c->dim, M = R * P;
   int rc = linear_backward(b.dy, b.dyT, o, a->proj_w, M, D, D, amax, b.dO, ga->proj_w, b, st);
   if (rc) return rc;
   { StageScope s_(kStBwdAttn, st);
-    RRT_CUDA(rrt::launch_rmsa_attention_bwd(qkv, o, b.dO, epeg ? a->pe_w : nullptr, b.dqkv,
-                                            epeg ? ga->pe_w : nullptr, amax, R, P, D, heads,
-                                            epeg ? c->epeg_k : 1, st), "attention backward"); }
+    if (qkv_f32)
+      RRT_CUDA(rrt::launch_landmark_attention_bwd(qkv_f32, b.dO, b.dqkv, R, P, D, heads, st),
+               "landmark attention backward (fp32)");
+    else
+      RRT_CUDA(rrt::launch_rmsa_attention_bwd(qkv, o, b.dO, epeg ? a->pe_w : nullptr, b.dqkv,
+                                              epeg ? ga->pe_w : nullptr, amax, R, P, D, heads,
+                                              epeg ? c->epeg_k : 1, st), "attention backward"); }
   { StageScope s_(kStBwdPrep, st);
     float* colsum = c->qkv_bias ? ga->qkv_b : nullptr;   // qkv.bias gradient = column sums of dqkv
     __half* dqkvT = wgrad_mn() ? nullptr : b.dqkvT;
@@ -1240,9 +1247,11 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
                                           gr->cr_attn.proj_b, st,
                                           rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream)),
                "landmark grad rows"); }
+    const int cr_hd = D / c->crmsa_heads;
+    const bool lm_f32 = cr_hd != 32 && cr_hd != 64 && cr_hd != 128;   // the forward's fp32 landmark path
     int rc = attention_module_backward(c, &w->cr_attn, &gr->cr_attn, tp.lm,
                                        reinterpret_cast<const __half*>(tp.lqkv), tp.lo, k, gc.R,
-                                       c->crmsa_heads, false, &b.amax[0], b, st);
+                                       c->crmsa_heads, false, &b.amax[0], b, st, lm_f32 ? tp.lqkv : nullptr);
     if (rc) return rc;
     float* out = nl > 0 ? b.ga : dx;
     const float dh_weight = (nl == 0 && c->all_shortcut) ? 2.f : 1.f;

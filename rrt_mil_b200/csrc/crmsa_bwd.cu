@@ -400,6 +400,145 @@ __global__ void __launch_bounds__(256) crmsa_mlp_hidden_bwd_kernel(const float* 
     if (acc[i] != 0.f) atomicAdd(dw2 + i, acc[i]);
 }
 
+// Backward of the landmark MHA core for head dims the tensor-core attention backward does not cover
+// (crmsa_heads = 1: head_dim = D, the reference's BRCA-R50 / LUAD-PLIP recipes): fp32, 64 landmarks per sequence.
+//   P = softmax(scale Q K^T),  dV = P^T dO,  dP = dO V^T,  dS = P (dP - rowsum(dP P)),  dQ = scale dS K,  dK = scale dS^T Q
+// grid (heads, k), 256 threads = a 16 x 16 grid of 4 x 4 register tiles; head_dim walked in chunks of 32.
+// lqkv: fp32 [k*64, 3D] (the forward's tape); dO16 / dqkv16: fp16 rows in the scaled gradient domain (the kernel
+// is linear in dO, so the scale passes through).
+__global__ void __launch_bounds__(256) landmark_attn_bwd_kernel(const float* __restrict__ lqkv,
+                                                                const __half* __restrict__ dO16,
+                                                                __half* __restrict__ dqkv16, int D, int heads,
+                                                                float scale) {
+  constexpr int R = 64, CH = 32;
+  extern __shared__ __align__(16) float lab_smem[];   // 49 KB: dynamic (above the 48 KB static limit)
+  float (*a_s)[CH + 1] = reinterpret_cast<float (*)[CH + 1]>(lab_smem);
+  float (*b_s)[CH + 1] = reinterpret_cast<float (*)[CH + 1]>(lab_smem + R * (CH + 1));
+  float (*ps)[R + 1] = reinterpret_cast<float (*)[R + 1]>(lab_smem + 2 * R * (CH + 1));               // P
+  float (*ds)[R + 1] = reinterpret_cast<float (*)[R + 1]>(lab_smem + 2 * R * (CH + 1) + R * (R + 1));  // dP, then dS
+  const int h = blockIdx.x, n = blockIdx.y, dh = D / heads;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const size_t ld = 3 * (size_t)D;
+  const float* base = lqkv + (size_t)n * R * ld + h * dh;
+  const __half* dob = dO16 + (size_t)n * R * D + h * dh;
+  __half* dqb = dqkv16 + (size_t)n * R * ld + h * dh;
+
+  float s[4][4], g[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[i][j] = g[i][j] = 0.f;
+  // S = Q K^T and dP = dO V^T, accumulated over the head dim
+  for (int c0 = 0; c0 < dh; c0 += CH) {
+    __syncthreads();
+    for (int i = tid; i < R * CH; i += 256) {
+      int r = i / CH, c = i - r * CH;
+      a_s[r][c] = __ldg(base + (size_t)r * ld + c0 + c);
+      b_s[r][c] = __ldg(base + (size_t)r * ld + D + c0 + c);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < CH; ++c) {
+      float qv[4], kv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { qv[i] = a_s[ty * 4 + i][c]; kv[i] = b_s[tx * 4 + i][c]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = fmaf(qv[i], kv[j], s[i][j]);
+    }
+    __syncthreads();
+    for (int i = tid; i < R * CH; i += 256) {
+      int r = i / CH, c = i - r * CH;
+      a_s[r][c] = __half2float(dob[(size_t)r * D + c0 + c]);
+      b_s[r][c] = __ldg(base + (size_t)r * ld + 2 * D + c0 + c);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < CH; ++c) {
+      float ov[4], vv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { ov[i] = a_s[ty * 4 + i][c]; vv[i] = b_s[tx * 4 + i][c]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[i][j] = fmaf(ov[i], vv[j], g[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ps[ty * 4 + i][tx * 4 + j] = s[i][j] * scale;
+      ds[ty * 4 + i][tx * 4 + j] = g[i][j];
+    }
+  __syncthreads();
+  {  // rows: P = softmax(S), dS = P (dP - sum_j dP_j P_j); warp w owns rows 8w..8w+7
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+      float a = ps[r][lane], b = ps[r][lane + 32];
+      const float mx = warp_max(fmaxf(a, b));
+      a = __expf(a - mx);
+      b = __expf(b - mx);
+      const float inv = 1.f / warp_sum(a + b);
+      a *= inv;
+      b *= inv;
+      const float da = ds[r][lane], db = ds[r][lane + 32];
+      const float dot = warp_sum(da * a + db * b);
+      ps[r][lane] = a;
+      ps[r][lane + 32] = b;
+      ds[r][lane] = a * (da - dot);
+      ds[r][lane + 32] = b * (db - dot);
+    }
+  }
+  // per head-dim chunk: dQ = scale dS K, dK = scale dS^T Q, dV = P^T dO   (thread: 4 rows x 2 columns)
+  for (int c0 = 0; c0 < dh; c0 += CH) {
+    float dq[4][2], dk[4][2], dv[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dq[i][0] = dq[i][1] = dk[i][0] = dk[i][1] = dv[i][0] = dv[i][1] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < R * CH; i += 256) {   // a_s = K chunk, b_s = Q chunk
+      int r = i / CH, c = i - r * CH;
+      a_s[r][c] = __ldg(base + (size_t)r * ld + D + c0 + c);
+      b_s[r][c] = __ldg(base + (size_t)r * ld + c0 + c);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < R; ++j) {
+      const float k0 = a_s[j][tx * 2], k1 = a_s[j][tx * 2 + 1], q0 = b_s[j][tx * 2], q1 = b_s[j][tx * 2 + 1];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dsr = ds[ty * 4 + i][j];   // dS[row][j]
+        const float dst = ds[j][ty * 4 + i];   // dS[j][row]  (dS^T)
+        dq[i][0] = fmaf(dsr, k0, dq[i][0]); dq[i][1] = fmaf(dsr, k1, dq[i][1]);
+        dk[i][0] = fmaf(dst, q0, dk[i][0]); dk[i][1] = fmaf(dst, q1, dk[i][1]);
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < R * CH; i += 256) {   // a_s = dO chunk
+      int r = i / CH, c = i - r * CH;
+      a_s[r][c] = __half2float(dob[(size_t)r * D + c0 + c]);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < R; ++j) {
+      const float o0 = a_s[j][tx * 2], o1 = a_s[j][tx * 2 + 1];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float pt = ps[j][ty * 4 + i];    // P[j][row]  (P^T)
+        dv[i][0] = fmaf(pt, o0, dv[i][0]); dv[i][1] = fmaf(pt, o1, dv[i][1]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half* row = dqb + (size_t)(ty * 4 + i) * ld + c0 + tx * 2;
+      *reinterpret_cast<uint32_t*>(row) = pack_h2(dq[i][0] * scale, dq[i][1] * scale);
+      *reinterpret_cast<uint32_t*>(row + D) = pack_h2(dk[i][0] * scale, dk[i][1] * scale);
+      *reinterpret_cast<uint32_t*>(row + 2 * D) = pack_h2(dv[i][0], dv[i][1]);
+    }
+  }
+}
+
 int token_chunks(const Grid& g) {
   int chunks = (2 * 148 + g.R - 1) / g.R;
   if (chunks > (g.P + 7) / 8) chunks = (g.P + 7) / 8;
@@ -473,6 +612,17 @@ cudaError_t launch_crmsa_combine_bwd(const float* x1, const float* gamma, const 
     if (mode == 0) RRT_CRB_LAUNCH(0) else if (mode == 1) RRT_CRB_LAUNCH(1) else RRT_CRB_LAUNCH(2)
   });
 #undef RRT_CRB_LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t launch_landmark_attention_bwd(const float* lqkv, const __half* dO16, __half* dqkv16, int k, int R, int D,
+                                          int heads, cudaStream_t stream) {
+  if (R != 64 || heads <= 0 || D % heads || (D / heads) % 32) return cudaErrorInvalidValue;
+  const float scale = 1.f / sqrtf((float)(D / heads));
+  const size_t smem = (size_t)(2 * 64 * 33 + 2 * 64 * 65) * sizeof(float);
+  cudaError_t e = set_smem(landmark_attn_bwd_kernel, smem);
+  if (e != cudaSuccess) return e;
+  landmark_attn_bwd_kernel<<<dim3(heads, k), 256, smem, stream>>>(lqkv, dO16, dqkv16, D, heads, scale);
   return cudaGetLastError();
 }
 

@@ -203,6 +203,10 @@ cudaError_t launch_crmsa_combine_bwd(const float* x1, const float* gamma, const 
                                      float* dbeta, uint32_t* amax_out, const Grid& grid, int D, int k,
                                      cudaStream_t stream, int mode = 0, float* dlogits = nullptr,
                                      const __half* dzx16 = nullptr, const uint32_t* amax_x = nullptr);
+// backward of launch_landmark_attention (fp32 tape, any head_dim % 32 == 0): dqkv16 [k*64, 3D] fp16 in the scaled
+// gradient domain of dO16
+cudaError_t launch_landmark_attention_bwd(const float* lqkv, const __half* dO16, __half* dqkv16, int k, int R, int D,
+                                          int heads, cudaStream_t stream);
 // crmsa_mlp: backward of logits = W2 tanh(pre) (dpre fp32 [rows, H4], dW2 [k, H4] accumulated); mode 1 / 2 of
 // launch_crmsa_combine_bwd run before / after it (csrc/crmsa_bwd.cu)
 cudaError_t launch_crmsa_mlp_hidden_bwd(const float* dlogits, const float* hidden, const float* w2, float* dpre,

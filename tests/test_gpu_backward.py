@@ -138,6 +138,9 @@ ENC_CASES = [
     ("tiny", 50, dict()),
     ("crmsa_mlp_k5", 600, dict(crmsa_mlp=True, crmsa_k=5)),           # README NSCLC-PLIP recipe's phi (README.md:119)
     ("crmsa_mlp_shortcut", 400, dict(crmsa_mlp=True, all_shortcut=True, region_num=4, epeg_k=7)),
+    ("crmsa_heads1", 700, dict(crmsa_heads=1)),                        # BRCA-R50 / LUAD-PLIP recipes: head_dim 512
+    ("nsclc_plip_mlp_h1", 500, dict(crmsa_mlp=True, crmsa_heads=1, crmsa_k=5)),   # README.md:119
+    ("crmsa_heads1_d256", 300, dict(mlp_dim=256, n_heads=4, crmsa_heads=1, crmsa_k=4)),
     ("n9000", 9000, dict()),
     ("n50000_g16", 50000, dict(region_num=16)),     # BASELINE configs[3] shape: P = 196 (R-MSA), 784 (CR-MSA)
 ]
@@ -256,7 +259,7 @@ def test_backward_rejects_unsupported():
 def test_backward_limits_are_reported_before_the_forward():
     """Limits that depend on the bag or on derived sizes raise at the call, not inside loss.backward()."""
     cases = [(dict(mlp_dim=256, n_heads=4, crmsa_heads=4, crmsa_mlp=True), 300),   # crmsa_mlp hidden width 64
-             (dict(crmsa_heads=1), 300),                                           # CR-MSA head_dim 512
+             (dict(crmsa_heads=4), 300),                                           # CR-MSA head_dim 128
              (dict(), 20000)]                                                      # R-MSA regions of 324 tokens
     for over, L in cases:
         m = RRTEncoder(**over).cuda().train()
