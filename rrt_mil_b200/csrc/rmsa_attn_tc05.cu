@@ -166,6 +166,8 @@ struct AttnTcParams {
   int P, P16, heads, D, epeg_k, pad, nkc, q_rows, ntail, n_items;
   int kv_stages, q_stages;                 // ring depths (3 / 2 when shared memory allows)
   int tail_helpers, epeg_helpers;          // 2 + 5 dedicated warps (<= 2 tail tiles per item), else all 7 do both
+  int sep_o;                               // 1: O | l in columns of their own (P16 <= 160): S of item n + 2 is issued
+                                           // right behind O of item n instead of after its epilogue
   uint32_t slot_stride, o_off;             // TMEM columns of one warpgroup's slot: S, P at 0; O | l at o_off
   uint32_t tmem_cols, q_bytes, kv_bytes, qp_bytes;
   float qscale;
@@ -402,6 +404,7 @@ rmsa_attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           stamp2(p, 16, n, 0);
           const int slot = n & 1, u = n >> 1;
           mbar_wait_c(&bars[kPReady + slot], u & 1);
+          if (p.sep_o && u > 0) mbar_wait_c(&bars[kODone + slot], (u - 1) & 1);  // epilogue of item n - 2 has read O
           tc_fence_after();
           stamp2(p, 16, n, 1);
           const uint32_t tP = tmem_base + (uint32_t)slot * p.slot_stride;
@@ -440,7 +443,10 @@ rmsa_attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           ++nlk;
         }
         if (j < total) {
-          if (n >= 0) mbar_wait_c(&bars[kODone + (n & 1)], (n >> 1) & 1);  // epilogue of item n has read O: slot free
+          // the slot's S / P columns are free: aliased layout -> once the epilogue of item n has read O (which
+          // lives over S); separate layout -> already (the tensor pipe runs O of item n, which reads P, before this
+          // S: same issuing thread, in order; every softmax thread has read S: p_ready)
+          if (n >= 0 && !p.sep_o) mbar_wait_c(&bars[kODone + (n & 1)], (n >> 1) & 1);
           if (n >= 0) stamp2(p, 16, n, 3);
           mbar_wait_c(&bars[kQpFull + (j & 1)], (j >> 1) & 1);
           mbar_wait_c(&bars[kKvFull + j % KS], (j / KS) & 1);
@@ -707,7 +713,7 @@ bool cached_map3(CUtensorMap* tm, const __half* base, int ld, int P, int R, int 
 uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 struct Geometry {
-  int P16, pad, nkc, q_rows, ntail, kv_stages, q_stages;
+  int P16, pad, nkc, q_rows, ntail, kv_stages, q_stages, sep_o;
   uint32_t o_off, slot_stride, tmem_cols, qp_bytes;
   size_t smem;
 };
@@ -720,11 +726,19 @@ bool geometry(const Grid& grid, bool epeg, int epeg_k, Geometry* g) {
   g->q_rows = 16 * (W - 1) + 16 * g->nkc;
   if (g->q_rows < 16 * W + 2 * g->pad) g->q_rows = (16 * W + 2 * g->pad + 7) / 8 * 8;
   g->ntail = P > 128 ? (P - 128 + 15) / 16 : 0;
-  // TMEM slot of one warpgroup: [ S: P16 | P over S[0, P16/2) | O (64) and l (16) over the tail of S ]
+  // TMEM slot of one warpgroup: [ S: P16 | P over S[0, P16/2) | O (64) and l (16) ]; O | l behind S when two such
+  // slots fit the 512 columns (P16 <= 160), else over the tail of S
   const uint32_t p16 = (uint32_t)g->P16;
-  const uint32_t o_min = p16 / 2 > (p16 > 80 ? p16 - 80 : 0) ? p16 / 2 : p16 - 80;
-  g->o_off = round_up(o_min, 32);
-  g->slot_stride = round_up(g->o_off + 80 > p16 ? g->o_off + 80 : p16, 32);
+  const uint32_t sep_stride = round_up(round_up(p16, 32) + 80, 32);
+  g->sep_o = 2 * sep_stride <= 512 ? 1 : 0;
+  if (g->sep_o) {
+    g->o_off = round_up(p16, 32);
+    g->slot_stride = sep_stride;
+  } else {
+    const uint32_t o_min = p16 / 2 > (p16 > 80 ? p16 - 80 : 0) ? p16 / 2 : p16 - 80;
+    g->o_off = round_up(o_min, 32);
+    g->slot_stride = round_up(g->o_off + 80 > p16 ? g->o_off + 80 : p16, 32);
+  }
   uint32_t cols = 32;
   while (cols < 2 * g->slot_stride) cols *= 2;
   g->tmem_cols = cols;
@@ -768,6 +782,7 @@ cudaError_t launch_rmsa_attention_tc05(const __half* qkv, const float* taps, __h
   p.epeg_k = epeg ? epeg_k : 0; p.pad = g.pad; p.nkc = g.nkc; p.q_rows = g.q_rows; p.ntail = g.ntail;
   p.n_items = grid.R * heads;
   p.kv_stages = g.kv_stages; p.q_stages = g.q_stages;
+  p.sep_o = g.sep_o;
   p.tail_helpers = g.ntail <= 2 ? 2 : kHelpers;
   p.epeg_helpers = g.ntail <= 2 ? kHelpers - 2 : kHelpers;
   p.slot_stride = g.slot_stride; p.o_off = g.o_off; p.tmem_cols = g.tmem_cols;
