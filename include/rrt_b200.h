@@ -42,7 +42,7 @@ extern "C" {
 #define RRT_API __attribute__((visibility("default")))
 #endif
 
-#define RRT_ABI_VERSION 6
+#define RRT_ABI_VERSION 7
 #define RRT_MAX_RMSA_LAYERS 8 /* n_layers-1 R-MSA TransLayers (modules/rrt.py:143) */
 #define RRT_MAX_CRMSA_K 16    /* crmsa_k landmarks per region                         */
 #define RRT_MAX_EPEG_K 63     /* odd EPEG kernel length                               */
@@ -241,8 +241,13 @@ RRT_API int rrt_linear_forward(const float* a, const float* w, const float* bias
 /* ---- SURVEY.md 8(f) "next" rows f1 / f2: the layers RRTMIL wraps around the encoder ------------ */
 /* activation codes of the two entries below */
 enum { RRT_ACT_NONE = 0, RRT_ACT_RELU = 1, RRT_ACT_GELU = 2, RRT_ACT_TANH = 3 };
+/* flag OR-ed into `act` of rrt_attn_pool_forward / _backward: the gated head (AttentionGated,
+ * modules/datten.py:40-83).  w1 is then [2*hid, dim] = [attention_a.0.weight; attention_b.0.weight], b1
+ * [2*hid] likewise, w2 = attention_c.weight [hid]:  A = (act(h Wa^T + ba) * sigmoid(h Wb^T + bb)) w2 + b2.
+ * Workspace sizes are asked for with 2*hid in the `hid` argument. */
+#define RRT_ACT_GATED 0x100
 
-/* Device workspace (bytes) of rrt_patch_embed_forward / rrt_attn_pool_forward. */
+/* Device workspace (bytes) of rrt_patch_embed_forward / rrt_attn_pool_forward (hid = rows of w1). */
 RRT_API int rrt_mil_head_workspace_bytes(int64_t L, int32_t in_dim, int32_t dim, int32_t hid,
                                          size_t* bytes);
 
@@ -250,18 +255,21 @@ RRT_API int rrt_mil_head_workspace_bytes(int64_t L, int32_t in_dim, int32_t dim,
  * 228).  w_f16 = optional fp16 shadow of w (rrt_convert_f16) or NULL.  in_dim % 64 == 0.
  * drop_p / seed: RRTMIL.dp (nn.Dropout(0.25), modules/rrt.py:215,229) in training mode, counter-based mask
  * stream RRT_DROP_STREAM_PATCH over [L, out_dim]; 0 = eval.  After the call the workspace starts with the
- * fp16 copy of x, which rrt_patch_embed_backward reads as its tape. */
+ * fp16 copy of x, which rrt_patch_embed_backward reads as its tape.
+ * pre (nullable, [L, out_dim] fp32): with act = RRT_ACT_GELU it receives the pre-activations x w^T + b, which
+ * the backward needs (gelu' is not a function of the output); ignored for the other activations. */
 #define RRT_DROP_STREAM_PATCH 65
 RRT_API int rrt_patch_embed_forward(const float* x, int64_t L, int32_t in_dim, int32_t out_dim,
                                     const float* w, const float* b, const void* w_f16, int32_t act,
                                     float* out, void* workspace, size_t workspace_bytes, float drop_p,
-                                    uint64_t seed, void* stream);
+                                    uint64_t seed, float* pre, void* stream);
 /* Backward of patch_to_emb (+ dp): dout [L, out_dim] = gradient wrt the forward's `out`; dw [out_dim, in_dim],
- * db [out_dim] (nullable) are overwritten.  act = RRT_ACT_RELU (mask read off `out`) or RRT_ACT_NONE (dropout
- * mask regenerated from drop_p / seed).  tape = the forward's workspace, untouched since.  No gradient wrt x
- * (the bag's features are data).  workspace >= 512 + L * out_dim * 2 bytes (256-aligned). */
-RRT_API int rrt_patch_embed_backward(const float* dout, const float* out, int64_t L, int32_t in_dim,
-                                     int32_t out_dim, int32_t act, float drop_p, uint64_t seed,
+ * db [out_dim] (nullable) are overwritten.  act = RRT_ACT_RELU (mask read off `out`), RRT_ACT_GELU (needs
+ * `pre` of the forward; dropout mask regenerated) or RRT_ACT_NONE (dropout mask regenerated from drop_p /
+ * seed).  tape = the forward's workspace, untouched since.  No gradient wrt x (the bag's features are data).
+ * workspace >= 512 + L * out_dim * 2 bytes (256-aligned). */
+RRT_API int rrt_patch_embed_backward(const float* dout, const float* out, const float* pre, int64_t L,
+                                     int32_t in_dim, int32_t out_dim, int32_t act, float drop_p, uint64_t seed,
                                      const void* tape, size_t tape_bytes, float* dw, float* db,
                                      void* workspace, size_t workspace_bytes, void* stream);
 
@@ -269,13 +277,18 @@ RRT_API int rrt_patch_embed_backward(const float* dout, const float* out, int64_
  *   A = act(h @ w1^T + b1) @ w2^T + b2  [L];  a = softmax_L(A);  pooled[dim] = a @ h;
  *   logits[n_classes] = pooled @ pred_w^T + pred_b   (pred_w may be NULL: pooling only).
  * attn (optional, [L]) receives a, or the raw scores A when attn_raw != 0 (the reference's no_norm).
- * b1 / b2 / pred_b / w1_f16 may be NULL. */
+ * b1 / b2 / pred_b / w1_f16 may be NULL.  act may carry RRT_ACT_GATED (above).
+ * drop_p / seed: the nn.Dropout(0.25) inside the score MLP (da_dropout=True, modules/datten.py:20-21,58-60)
+ * in training mode: counter-based mask, stream RRT_DROP_STREAM_POOL over the hidden buffer [L, rows of w1]
+ * (gated: independent masks for the two branches, as in the reference); 0 = eval.
+ * pre (nullable, [L, hid]): with act = RRT_ACT_GELU it receives the pre-activations of the act branch. */
+#define RRT_DROP_STREAM_POOL 66
 RRT_API int rrt_attn_pool_forward(const float* h, int64_t L, int32_t dim, int32_t hid,
                                   const float* w1, const float* b1, const void* w1_f16, int32_t act,
                                   const float* w2, const float* b2, const float* pred_w,
                                   const float* pred_b, int32_t n_classes, float* pooled,
-                                  float* logits, float* attn, int32_t attn_raw, void* workspace,
-                                  size_t workspace_bytes, void* stream);
+                                  float* logits, float* attn, int32_t attn_raw, float drop_p, uint64_t seed,
+                                  float* pre, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- training: forward with a tape + backward (autograd of modules/rrt.py:165-202) ---------------
  * Dropout is not applied (drop_out = 0 or eval mode); the Python module raises for active dropout.
@@ -359,14 +372,16 @@ RRT_API int rrt_layernorm_backward(const float* x, const float* gamma, const flo
 /* Backward of rrt_attn_pool_forward (autograd of modules/datten.py:28-38 + the predictor): dlogits
  * [n_classes] -> dh [L, dim] (overwritten) and the gradients of w1 [hid, dim], b1 [hid] (nullable), w2 [hid],
  * b2 [1] (nullable), pred_w [n_classes, dim], pred_b [n_classes] (nullable), all overwritten.  pooled = the
- * forward's output; tape = the forward's workspace, untouched since.  act = relu | tanh | none. */
+ * forward's output; tape = the forward's workspace, untouched since.  act = relu | tanh | gelu (needs `pre`) |
+ * none, optionally | RRT_ACT_GATED (hid = 128; w1 / dw1 [256, dim], b1 / db1 [256]).  drop_p / seed as in the
+ * forward.  Workspace: rrt_mil_head_backward_workspace_bytes with hid = rows of w1. */
 RRT_API int rrt_mil_head_backward_workspace_bytes(int64_t L, int32_t dim, int32_t hid, size_t* bytes);
 RRT_API int rrt_attn_pool_backward(const float* h, int64_t L, int32_t dim, int32_t hid, const float* w1,
                                    int32_t act, const float* w2, const float* pred_w, int32_t n_classes,
-                                   const float* pooled, const float* dlogits, const void* tape,
-                                   size_t tape_bytes, float* dh, float* dw1, float* db1, float* dw2,
-                                   float* db2, float* dpred_w, float* dpred_b, void* workspace,
-                                   size_t workspace_bytes, void* stream);
+                                   const float* pooled, const float* dlogits, float drop_p, uint64_t seed,
+                                   const float* pre, const void* tape, size_t tape_bytes, float* dh, float* dw1,
+                                   float* db1, float* dw2, float* db2, float* dpred_w, float* dpred_b,
+                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- optimizer step of the training harness (main.py:224-233: torch.optim.Adam, lr 2e-4, wd 1e-5) ----
  * One launch updates every tensor of the list with torch.optim.Adam (decoupled = 0: L2 weight decay

@@ -75,6 +75,10 @@ MIL_CASES = [
     ("mil_r50_n3000", 3000, 1024, 2, "relu", "relu", False, dict()),
     ("mil_plip_n1200_gelu_bias", 1200, 512, 4, "gelu", "tanh", True, dict(epeg_k=9, all_shortcut=True)),
     ("mil_n9000_k21", 9000, 1024, 2, "relu", "relu", False, dict(epeg_k=21, crmsa_k=5)),
+    # AttentionGated head (modules/datten.py:40-83, da_gated=True); the trailing dict = RRTMIL keywords
+    ("mil_gated_n1500", 1500, 1024, 2, "relu", "relu", False, dict(), dict(da_gated=True)),
+    ("mil_gated_gelu_bias_dropout_n700", 700, 512, 3, "gelu", "gelu", True, dict(epeg_k=9),
+     dict(da_gated=True, da_dropout=True)),
 ]
 
 # Training mode (proj_drop active) + backward: name, L, config overrides, drop_out, dropout seed.
@@ -102,6 +106,13 @@ GRAD_SEED = 43
 MIL_TRAIN_CASES = [
     ("miltrain_r50_n800", 800, 1024, 2, "relu", False, 1, dict(), 0.25, 0.1, 500),
     ("miltrain_tanh_bias_n600", 600, 512, 3, "tanh", True, 2, dict(epeg_k=9, all_shortcut=True), 0.25, 0.1, 900),
+    # trailing dict = RRTMIL keywords: gated head, GELU in patch_to_emb and in the head, nn.Dropout(0.25) inside
+    # the head's score MLP (da_dropout; its masks installed like the others, stream DROP_STREAM_POOL)
+    ("miltrain_gated_n700", 700, 1024, 2, "relu", False, 0, dict(), 0.25, 0.1, 1300, dict(da_gated=True)),
+    ("miltrain_gelu_dadrop_n600", 600, 512, 2, "gelu", True, 1, dict(epeg_k=9), 0.25, 0.1, 1700,
+     dict(act="gelu", da_dropout=True)),
+    ("miltrain_gated_tanh_dadrop_bias_n500", 500, 512, 3, "tanh", True, 2, dict(), 0.25, 0.0, 2100,
+     dict(da_gated=True, da_dropout=True)),
 ]
 
 MAX_ROWS = 96
@@ -257,13 +268,28 @@ def generate_train(name, L, overrides, p, seed):
                 bag_seed=bag_seed, bag_kind="relu", grad_seed=GRAD_SEED, min_crmsa_tie_gap=gap)
 
 
-def generate_mil_train(name, L, input_dim, n_classes, da_act, da_bias, label, overrides, p_dp, p_enc, seed):
+def install_pool_dropout_masks(m, L, p, seed):
+    """Replace the nn.Dropout modules inside the pooling head's score MLP by the library's masks."""
+    att = m.pool_fn.attention
+    if hasattr(att, "attention_c"):
+        mask = O.dropout_mask(L, 256, p, seed, O.DROP_STREAM_POOL)
+        att.attention_a[-1], att.attention_b[-1] = _MaskMul(mask[:, :128]), _MaskMul(mask[:, 128:])
+    else:
+        idx = [i for i, l in enumerate(att.attention) if isinstance(l, torch.nn.Dropout)][0]
+        att.attention[idx] = _MaskMul(O.dropout_mask(L, 128, p, seed, O.DROP_STREAM_POOL))
+
+
+def generate_mil_train(name, L, input_dim, n_classes, da_act, da_bias, label, overrides, p_dp, p_enc, seed,
+                       extra=None):
+    extra = dict(extra or {})
+    act = extra.get("act", "relu")
     cfg = O.EncoderConfig(**overrides)
-    w = O.make_mil_weights(cfg, input_dim, n_classes, WEIGHT_SEED, da_bias=da_bias)
+    w = O.make_mil_weights(cfg, input_dim, n_classes, WEIGHT_SEED, da_bias=da_bias,
+                           da_gated=extra.get("da_gated", False), da_dropout=extra.get("da_dropout", False))
     x = O.make_bag(L, input_dim, 7, kind="randn")
     enc_w = {k[len("online_encoder."):]: v for k, v in w.items() if k.startswith("online_encoder.")}
     for _ in range(400):   # first seed whose bag stays off the CR-MSA argmin / argmax ties (crmsa_tie_gap)
-        h0 = torch.relu(torch.nn.functional.linear(x, w["patch_to_emb.0.weight"], w["patch_to_emb.0.bias"]))
+        h0 = O._act(act)(torch.nn.functional.linear(x, w["patch_to_emb.0.weight"], w["patch_to_emb.0.bias"]))
         h0 = h0 * O.dropout_mask(L, 512, p_dp, seed, O.DROP_STREAM_PATCH)
         gap = crmsa_tie_gap(h0, enc_w, cfg, (p_enc, seed + 1))
         if gap >= MIN_TIE_GAP:
@@ -272,13 +298,16 @@ def generate_mil_train(name, L, input_dim, n_classes, da_act, da_bias, label, ov
     else:
         raise SystemExit(f"{name}: no seed with a CR-MSA tie gap >= {MIN_TIE_GAP}")
     ref = shim.import_reference_rrt()
-    m = ref.RRTMIL(input_dim=input_dim, n_classes=n_classes, act="relu", da_act=da_act, da_bias=da_bias,
+    m = ref.RRTMIL(input_dim=input_dim, n_classes=n_classes, act=act, da_act=da_act, da_bias=da_bias,
                    dropout=p_dp, trans_dropout=p_enc, region_num=cfg.region_num, n_layers=cfg.n_layers,
                    epeg_k=cfg.epeg_k, crmsa_k=cfg.crmsa_k, all_shortcut=cfg.all_shortcut,
-                   crmsa_heads=cfg.crmsa_heads).double().train()
+                   crmsa_heads=cfg.crmsa_heads, da_gated=extra.get("da_gated", False),
+                   da_dropout=extra.get("da_dropout", False)).double().train()
     m.load_state_dict(w, strict=True)
     m.dp = _MaskMul(O.dropout_mask(L, 512, p_dp, seed, O.DROP_STREAM_PATCH))
     install_dropout_masks(m.online_encoder, cfg, L, p_enc, seed + 1)
+    if extra.get("da_dropout"):
+        install_pool_dropout_masks(m, L, 0.25, seed)
     with torch.enable_grad():
         logits = m(x.unsqueeze(0))
         loss = torch.nn.functional.cross_entropy(logits, torch.tensor([label]))
@@ -291,25 +320,27 @@ def generate_mil_train(name, L, input_dim, n_classes, da_act, da_bias, label, ov
     np.savez(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
     return dict(name=name, L=L, input_dim=input_dim, n_classes=n_classes, da_act=da_act, da_bias=da_bias,
                 label=label, config=cfg.to_dict(), dropout=p_dp, trans_dropout=p_enc, seed=seed,
-                weight_seed=WEIGHT_SEED, bag_seed=7, min_crmsa_tie_gap=gap)
+                weight_seed=WEIGHT_SEED, bag_seed=7, min_crmsa_tie_gap=gap, extra=extra)
 
 
-def generate_mil(name, L, input_dim, n_classes, act, da_act, da_bias, overrides):
+def generate_mil(name, L, input_dim, n_classes, act, da_act, da_bias, overrides, extra=None):
+    extra = dict(extra or {})
     cfg = O.EncoderConfig(**overrides)
-    w = O.make_mil_weights(cfg, input_dim, n_classes, WEIGHT_SEED, da_bias=da_bias)
+    w = O.make_mil_weights(cfg, input_dim, n_classes, WEIGHT_SEED, da_bias=da_bias,
+                           da_gated=extra.get("da_gated", False), da_dropout=extra.get("da_dropout", False))
     x = O.make_bag(L, input_dim, 7, kind="randn")
     ref = shim.import_reference_rrt()
     m = ref.RRTMIL(input_dim=input_dim, n_classes=n_classes, act=act, da_act=da_act, da_bias=da_bias,
                    region_num=cfg.region_num, n_layers=cfg.n_layers, epeg_k=cfg.epeg_k,
                    crmsa_k=cfg.crmsa_k, all_shortcut=cfg.all_shortcut, crmsa_heads=cfg.crmsa_heads,
-                   crmsa_mlp=cfg.crmsa_mlp).double().eval()
+                   crmsa_mlp=cfg.crmsa_mlp, **extra).double().eval()
     m.load_state_dict(w, strict=True)
     with torch.no_grad():
         logits, attn = m(x.unsqueeze(0), return_attn=True)
     np.savez(os.path.join(GOLDEN_DIR, name + ".npz"), logits=logits[0].numpy(),
              attn=attn[0].numpy().astype(np.float32))
     return dict(name=name, L=L, input_dim=input_dim, n_classes=n_classes, act=act, da_act=da_act,
-                da_bias=da_bias, config=cfg.to_dict(), weight_seed=WEIGHT_SEED, bag_seed=7)
+                da_bias=da_bias, config=cfg.to_dict(), weight_seed=WEIGHT_SEED, bag_seed=7, extra=extra)
 
 
 def main():

@@ -125,6 +125,7 @@ def region_slot_map(H: int, rs: int) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------
 DROP_STREAM_CRMSA = 64  # == RRT_DROP_STREAM_CRMSA (include/rrt_b200.h); R-MSA layer i uses stream i
 DROP_STREAM_PATCH = 65  # == RRT_DROP_STREAM_PATCH: RRTMIL.dp behind patch_to_emb
+DROP_STREAM_POOL = 66   # == RRT_DROP_STREAM_POOL: nn.Dropout inside the pooling head's score MLP (da_dropout)
 _M64 = (1 << 64) - 1
 
 
@@ -325,7 +326,7 @@ def _act(name):
 
 
 def mil_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfig, act: str = "relu",
-                da_act: str = "relu", order: str = "reference", drop=None):
+                da_act: str = "relu", order: str = "reference", drop=None, pool_drop=None):
     """``RRTMIL.forward`` (eval) for one bag ``x`` [L, input_dim] -> (logits [C], attention [L])
     (modules/rrt.py:227-246, modules/datten.py:28-38,94-101).  Encoder weights carry the reference's
     ``online_encoder.`` prefix."""
@@ -336,10 +337,23 @@ def mil_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfig,
         enc_drop = (drop[2], drop[3]) if drop[2] > 0 else None
     enc = {k[len("online_encoder."):]: v for k, v in w.items() if k.startswith("online_encoder.")}
     h = encoder_forward(h, enc, cfg, order, drop=enc_drop)
-    keys = sorted(k for k in w if k.startswith("pool_fn.attention.attention.") and k.endswith("weight"))
-    k0, k1 = keys[0], keys[-1]
-    a = _act(da_act)(F.linear(h, w[k0], w.get(k0[:-6] + "bias")))
-    a = F.linear(a, w[k1], w.get(k1[:-6] + "bias")).squeeze(-1)  # [L]
+    # pool_drop = (p, seed): the nn.Dropout(0.25) inside the score MLP (da_dropout=True) in training mode, the
+    # library's counter-based mask over the hidden buffer [L, 128] (gated: [L, 256] = act branch | gate branch)
+    pa = "pool_fn.attention."
+    if pa + "attention_c.weight" in w:                       # AttentionGated (modules/datten.py:66-83)
+        ga = _act(da_act)(F.linear(h, w[pa + "attention_a.0.weight"], w.get(pa + "attention_a.0.bias")))
+        gb = torch.sigmoid(F.linear(h, w[pa + "attention_b.0.weight"], w.get(pa + "attention_b.0.bias")))
+        if pool_drop is not None and pool_drop[0] > 0:
+            m = dropout_mask(h.shape[0], 2 * ga.shape[1], pool_drop[0], pool_drop[1], DROP_STREAM_POOL, h.dtype)
+            ga, gb = ga * m[:, :ga.shape[1]], gb * m[:, ga.shape[1]:]
+        a = F.linear(ga * gb, w[pa + "attention_c.weight"], w.get(pa + "attention_c.bias")).squeeze(-1)
+    else:                                                    # Attention (modules/datten.py:28-38)
+        keys = sorted(k for k in w if k.startswith(pa + "attention.") and k.endswith("weight"))
+        k0, k1 = keys[0], keys[-1]
+        a = _act(da_act)(F.linear(h, w[k0], w.get(k0[:-6] + "bias")))
+        if pool_drop is not None and pool_drop[0] > 0:
+            a = a * dropout_mask(h.shape[0], a.shape[1], pool_drop[0], pool_drop[1], DROP_STREAM_POOL, h.dtype)
+        a = F.linear(a, w[k1], w.get(k1[:-6] + "bias")).squeeze(-1)  # [L]
     attn = torch.softmax(a, 0)
     pooled = attn @ h
     logits = F.linear(pooled, w["predictor.weight"], w["predictor.bias"])
@@ -347,7 +361,7 @@ def mil_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfig,
 
 
 def make_mil_weights(cfg: EncoderConfig, input_dim: int, n_classes: int, seed: int, da_bias: bool = False,
-                     dtype=torch.float64) -> Dict[str, torch.Tensor]:
+                     dtype=torch.float64, da_gated: bool = False, da_dropout: bool = False) -> Dict[str, torch.Tensor]:
     enc = make_weights(cfg, seed, dtype)
     rs = np.random.RandomState(seed + 1)
 
@@ -359,10 +373,19 @@ def make_mil_weights(cfg: EncoderConfig, input_dim: int, n_classes: int, seed: i
 
     w = {"online_encoder." + k: v for k, v in enc.items()}
     w["patch_to_emb.0.weight"], w["patch_to_emb.0.bias"] = lin(512, input_dim), vec(512)
-    w["pool_fn.attention.attention.0.weight"] = lin(128, cfg.mlp_dim)
-    w["pool_fn.attention.attention.2.weight"] = lin(1, 128)
-    if da_bias:
-        w["pool_fn.attention.attention.0.bias"], w["pool_fn.attention.attention.2.bias"] = vec(128), vec(1)
+    if da_gated:      # key names of modules/datten.py:47-65
+        pa = "pool_fn.attention."
+        w[pa + "attention_a.0.weight"], w[pa + "attention_b.0.weight"] = lin(128, cfg.mlp_dim), lin(128, cfg.mlp_dim)
+        w[pa + "attention_c.weight"] = lin(1, 128)
+        if da_bias:
+            w[pa + "attention_a.0.bias"], w[pa + "attention_b.0.bias"], w[pa + "attention_c.bias"] = \
+                vec(128), vec(128), vec(1)
+    else:
+        last = 3 if da_dropout else 2     # the nn.Dropout shifts the index of the score Linear in the Sequential
+        w["pool_fn.attention.attention.0.weight"] = lin(128, cfg.mlp_dim)
+        w[f"pool_fn.attention.attention.{last}.weight"] = lin(1, 128)
+        if da_bias:
+            w["pool_fn.attention.attention.0.bias"], w[f"pool_fn.attention.attention.{last}.bias"] = vec(128), vec(1)
     w["predictor.weight"], w["predictor.bias"] = lin(n_classes, cfg.mlp_dim), vec(n_classes)
     return w
 

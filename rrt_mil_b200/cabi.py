@@ -12,9 +12,10 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librrt_b200.so")
 
-RRT_ABI_VERSION = 6
+RRT_ABI_VERSION = 7
 RRT_DROP_STREAM_CRMSA = 64
 RRT_DROP_STREAM_PATCH = 65
+RRT_DROP_STREAM_POOL = 66
 RRT_POS_NONE, RRT_POS_PEG, RRT_POS_PPEG = 0, 1, 2
 RRT_MAX_RMSA_LAYERS = 8
 RRT_MAX_CRMSA_K = 16
@@ -23,6 +24,7 @@ RRT_MAX_LANES = 8
 RRT_OK, RRT_E_INVALID, RRT_E_WORKSPACE, RRT_E_CUDA = 0, -1, -2, -3
 RRT_MATH_F16 = 0
 RRT_ACT_NONE, RRT_ACT_RELU, RRT_ACT_GELU, RRT_ACT_TANH = 0, 1, 2, 3
+RRT_ACT_GATED = 0x100
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 
@@ -125,14 +127,16 @@ SIGNATURES = {
     "rrt_layernorm_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "rrt_mil_head_workspace_bytes": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "rrt_patch_embed_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P,
-                                          C.c_size_t, C.c_float, C.c_uint64, _P]),
-    "rrt_patch_embed_backward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                          C.c_size_t, C.c_float, C.c_uint64, _P, _P]),
+    "rrt_patch_embed_backward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                            C.c_uint64, _P, C.c_size_t, _P, _P, _P, C.c_size_t, _P]),
     "rrt_mil_head_backward_workspace_bytes": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "rrt_attn_pool_backward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32,
-                                         _P, _P, _P, C.c_size_t, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+                                         _P, _P, C.c_float, C.c_uint64, _P, _P, C.c_size_t, _P, _P, _P, _P, _P, _P,
+                                         _P, _P, C.c_size_t, _P]),
     "rrt_attn_pool_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P,
-                                        C.c_int32, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),
+                                        C.c_int32, _P, _P, _P, C.c_int32, C.c_float, C.c_uint64, _P, _P, C.c_size_t,
+                                        _P]),
     "rrt_launch_count": (C.c_int64, []),
     "rrt_stage_timing_enable": (C.c_int, [C.c_int32]),
     "rrt_stage_count": (C.c_int32, []),

@@ -749,9 +749,10 @@ RRT_API int rrt_mil_head_workspace_bytes(int64_t L, int32_t in_dim, int32_t dim,
 RRT_API int rrt_patch_embed_forward(const float* x, int64_t L, int32_t in_dim, int32_t out_dim,
                                     const float* w, const float* b, const void* w_f16, int32_t act,
                                     float* out, void* workspace, size_t workspace_bytes, float drop_p,
-                                    uint64_t seed, void* stream) {
+                                    uint64_t seed, float* pre, void* stream) {
   if (!(drop_p >= 0.f) || drop_p >= 1.f) return fail(RRT_E_INVALID, "drop_p must be in [0, 1)");
   if (!x || !w || !out || L < 1 || L > (1 << 28)) return fail(RRT_E_INVALID, "bad argument");
+  if (pre && (((uintptr_t)pre) & 15)) return fail(RRT_E_INVALID, "pre must be 16-byte aligned");
   if (in_dim % 64 || out_dim % 4 || !rrt::gemm_tcgen05_supported((int)L, out_dim, in_dim))
     return fail(RRT_E_INVALID, "patch_embed: in_dim must be a multiple of 64, out_dim of 4");
   int a;
@@ -762,7 +763,8 @@ RRT_API int rrt_patch_embed_forward(const float* x, int64_t L, int32_t in_dim, i
   cudaStream_t st = (cudaStream_t)stream;
   __half* x16 = (__half*)workspace;
   __half* w16s = (__half*)((char*)workspace + align_up((size_t)L * (in_dim > out_dim ? in_dim : out_dim) * 2));
-  StageScope s_(kStOther, st, 2 + (w_f16 ? 0 : 1));
+  const bool keep_pre = pre && a == rrt::kActGelu;   // training through nn.GELU: the backward needs z
+  StageScope s_(kStOther, st, 2 + (w_f16 ? 0 : 1) + (keep_pre ? 1 : 0));
   RRT_CUDA(rrt::launch_convert_f16(x, x16, (size_t)L * in_dim, st), "patch_embed: convert input");
   const __half* w16 = (const __half*)w_f16;
   if (!w16) {
@@ -771,8 +773,9 @@ RRT_API int rrt_patch_embed_forward(const float* x, int64_t L, int32_t in_dim, i
   }
   rrt::GemmEpilogue e;
   e.bias = b;
-  e.act = a;
+  e.act = keep_pre ? (int)rrt::kActNone : a;
   RRT_CUDA(rrt::launch_gemm_tcgen05(x16, w16, out, false, (int)L, out_dim, in_dim, e, st), "patch_embed gemm");
+  if (keep_pre) RRT_CUDA(rrt::launch_gelu_keep_pre(out, pre, (size_t)L, out_dim, out_dim, st), "patch_embed gelu");
   if (drop_p > 0.f) {  // RRTMIL.dp (modules/rrt.py:215,229), training mode
     g_launches.fetch_add(1, std::memory_order_relaxed);
     RRT_CUDA(rrt::launch_dropout_inplace(out, (size_t)L * out_dim,
@@ -786,38 +789,48 @@ RRT_API int rrt_attn_pool_forward(const float* h, int64_t L, int32_t dim, int32_
                                   const float* w1, const float* b1, const void* w1_f16, int32_t act,
                                   const float* w2, const float* b2, const float* pred_w,
                                   const float* pred_b, int32_t n_classes, float* pooled,
-                                  float* logits, float* attn, int32_t attn_raw, void* workspace,
-                                  size_t workspace_bytes, void* stream) {
+                                  float* logits, float* attn, int32_t attn_raw, float drop_p, uint64_t seed,
+                                  float* pre, void* workspace, size_t workspace_bytes, void* stream) {
   if (!h || !w1 || !w2 || !pooled || L < 1 || L > (1 << 28)) return fail(RRT_E_INVALID, "bad argument");
   if (pred_w && (!logits || n_classes < 1)) return fail(RRT_E_INVALID, "logits buffer missing");
-  if (dim % 64 || hid % 4 || !rrt::gemm_tcgen05_supported((int)L, hid, dim))
-    return fail(RRT_E_INVALID, "attn_pool: dim must be a multiple of 64, hid of 4");
+  if (!(drop_p >= 0.f) || drop_p >= 1.f) return fail(RRT_E_INVALID, "drop_p must be in [0, 1)");
+  const bool gated = (act & RRT_ACT_GATED) != 0;
+  const int N = gated ? 2 * hid : hid;   // rows of w1 = columns of the hidden buffer
+  if (dim % 64 || hid % 4 || (gated && hid % 32) || !rrt::gemm_tcgen05_supported((int)L, N, dim))
+    return fail(RRT_E_INVALID, "attn_pool: dim must be a multiple of 64, hid of 4 (of 32 when gated)");
+  if (pre && (((uintptr_t)pre) & 15)) return fail(RRT_E_INVALID, "pre must be 16-byte aligned");
   int a;
-  int rc = act_code(act, &a);
+  int rc = act_code(act & ~RRT_ACT_GATED, &a);
   if (rc) return rc;
-  if (!workspace || (((uintptr_t)workspace) & 255) || workspace_bytes < head_ws_bytes(L, dim, dim, hid))
+  if (!workspace || (((uintptr_t)workspace) & 255) || workspace_bytes < head_ws_bytes(L, dim, dim, N))
     return fail(RRT_E_WORKSPACE, "workspace too small or misaligned");
   cudaStream_t st = (cudaStream_t)stream;
   char* p = (char*)workspace;
   __half* h16 = (__half*)p;
   p += align_up((size_t)L * dim * 2);
   __half* w16s = (__half*)p;
-  p += align_up((size_t)dim * (dim > hid ? dim : hid) * 2);
+  p += align_up((size_t)dim * (dim > N ? dim : N) * 2);
   float* hidden = (float*)p;
-  float* scratch = hidden + (size_t)L * hid;
-  StageScope s_(kStOther, st, 5 + (w1_f16 ? 0 : 1) + (attn ? 1 : 0));
+  float* scratch = hidden + (size_t)L * N;
+  const bool keep_pre = pre && a == rrt::kActGelu;
+  StageScope s_(kStOther, st, 5 + (w1_f16 ? 0 : 1) + (attn ? 1 : 0) + (keep_pre ? 1 : 0) + (drop_p > 0.f ? 1 : 0));
   RRT_CUDA(rrt::launch_convert_f16(h, h16, (size_t)L * dim, st), "attn_pool: convert input");
   const __half* w16 = (const __half*)w1_f16;
   if (!w16) {
-    RRT_CUDA(rrt::launch_convert_f16(w1, w16s, (size_t)hid * dim, st), "attn_pool: convert weight");
+    RRT_CUDA(rrt::launch_convert_f16(w1, w16s, (size_t)N * dim, st), "attn_pool: convert weight");
     w16 = w16s;
   }
   rrt::GemmEpilogue e;
   e.bias = b1;
-  e.act = a;
-  RRT_CUDA(rrt::launch_gemm_tcgen05(h16, w16, hidden, false, (int)L, hid, dim, e, st), "attn_pool gemm");
+  e.act = keep_pre ? (int)rrt::kActNone : a;
+  if (gated) { e.act2 = rrt::kActSigmoid; e.act_split = hid; }
+  RRT_CUDA(rrt::launch_gemm_tcgen05(h16, w16, hidden, false, (int)L, N, dim, e, st), "attn_pool gemm");
+  if (keep_pre) RRT_CUDA(rrt::launch_gelu_keep_pre(hidden, pre, (size_t)L, hid, N, st), "attn_pool gelu");
+  if (drop_p > 0.f)   // nn.Dropout(0.25) inside the score MLP (da_dropout, modules/datten.py:20-21,58-60), training
+    RRT_CUDA(rrt::launch_dropout_inplace(hidden, (size_t)L * N, rrt::dropout_make(drop_p, seed, RRT_DROP_STREAM_POOL),
+                                         st), "attn_pool dropout");
   RRT_CUDA(rrt::launch_attn_pool(h, hidden, w2, b2, pred_w, pred_b, pred_w ? n_classes : 0, scratch, pooled,
-                                 logits, attn, attn_raw, (int)L, dim, hid, st), "attn_pool");
+                                 logits, attn, attn_raw, (int)L, dim, hid, gated, st), "attn_pool");
   return RRT_OK;
 }
 
@@ -835,14 +848,16 @@ RRT_API int rrt_mil_head_backward_workspace_bytes(int64_t L, int32_t dim, int32_
   return RRT_OK;
 }
 
-RRT_API int rrt_patch_embed_backward(const float* dout, const float* out, int64_t L, int32_t in_dim,
-                                     int32_t out_dim, int32_t act, float drop_p, uint64_t seed,
+RRT_API int rrt_patch_embed_backward(const float* dout, const float* out, const float* pre, int64_t L,
+                                     int32_t in_dim, int32_t out_dim, int32_t act, float drop_p, uint64_t seed,
                                      const void* tape, size_t tape_bytes, float* dw, float* db,
                                      void* workspace, size_t workspace_bytes, void* stream) {
   if (!dout || !out || !tape || !dw || L < 1 || L > (1 << 28)) return fail(RRT_E_INVALID, "bad argument");
   if (in_dim % 64 || out_dim % 128) return fail(RRT_E_INVALID, "patch_embed backward: in_dim % 64, out_dim % 128");
-  if (act != RRT_ACT_RELU && act != RRT_ACT_NONE)
-    return fail(RRT_E_INVALID, "patch_embed backward covers act = relu | none (gelu needs the pre-activation)");
+  if (act != RRT_ACT_RELU && act != RRT_ACT_NONE && act != RRT_ACT_GELU)
+    return fail(RRT_E_INVALID, "patch_embed backward covers act = relu | gelu | none");
+  if (act == RRT_ACT_GELU && !pre)
+    return fail(RRT_E_INVALID, "patch_embed backward through gelu needs the forward's pre-activations (pre)");
   if (!(drop_p >= 0.f) || drop_p >= 1.f) return fail(RRT_E_INVALID, "drop_p must be in [0, 1)");
   if (tape_bytes < head_ws_bytes(L, in_dim, out_dim, 1)) return fail(RRT_E_WORKSPACE, "tape too small");
   const size_t need = 256 + align_up((size_t)L * out_dim * 2) + 256;
@@ -859,10 +874,12 @@ RRT_API int rrt_patch_embed_backward(const float* dout, const float* out, int64_
   rrt::Grid ident{};
   ident.L = (int)L; ident.Np = (int)L;
   // dz = dout * [out != 0] / (1 - p) for ReLU (+ dropout); act = none: the dropout mask is regenerated
-  const bool relu = act == RRT_ACT_RELU;
+  // gelu: dz = dout * mask * gelu'(pre)
+  const bool relu = act == RRT_ACT_RELU, gelu = act == RRT_ACT_GELU;
   RRT_CUDA(rrt::launch_grad_partition(dout, ident, (int)L, out_dim, amax, dz16, nullptr, db, st,
                                       relu ? rrt::Dropout{} : rrt::dropout_make(drop_p, seed, RRT_DROP_STREAM_PATCH),
-                                      relu ? out : nullptr, relu && drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f),
+                                      relu ? out : (gelu ? pre : nullptr),
+                                      relu && drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f, gelu ? 1 : 0),
            "patch_embed grad rows");
   RRT_CUDA(cudaMemsetAsync(dw, 0, (size_t)out_dim * in_dim * 4, st), "zero dw");
   RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad(dz16, x16, dw, (int)L, out_dim, in_dim, st), "patch_embed wgrad");
@@ -872,60 +889,64 @@ RRT_API int rrt_patch_embed_backward(const float* dout, const float* out, int64_
 
 RRT_API int rrt_attn_pool_backward(const float* h, int64_t L, int32_t dim, int32_t hid, const float* w1,
                                    int32_t act, const float* w2, const float* pred_w, int32_t n_classes,
-                                   const float* pooled, const float* dlogits, const void* tape,
-                                   size_t tape_bytes, float* dh, float* dw1, float* db1, float* dw2,
-                                   float* db2, float* dpred_w, float* dpred_b, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   const float* pooled, const float* dlogits, float drop_p, uint64_t seed,
+                                   const float* pre, const void* tape, size_t tape_bytes, float* dh, float* dw1,
+                                   float* db1, float* dw2, float* db2, float* dpred_w, float* dpred_b,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
   if (!h || !w1 || !w2 || !pred_w || !pooled || !dlogits || !tape || !dh || !dw1 || !dw2 || !dpred_w ||
       L < 1 || L > (1 << 28) || n_classes < 1)
     return fail(RRT_E_INVALID, "bad argument");
-  if (dim % 128 || dim > 1024 || hid % 128 || hid > 256)
-    return fail(RRT_E_INVALID, "attn_pool backward: dim % 128 (<= 1024), hid in {128, 256}");
-  if (act != RRT_ACT_RELU && act != RRT_ACT_TANH && act != RRT_ACT_NONE)
-    return fail(RRT_E_INVALID, "attn_pool backward covers act = relu | tanh | none (gelu needs the pre-activation)");
-  if (tape_bytes < head_ws_bytes(L, dim, dim, hid)) return fail(RRT_E_WORKSPACE, "tape too small");
-  if (!workspace || (((uintptr_t)workspace | (uintptr_t)tape) & 255) || workspace_bytes < head_bwd_ws_bytes(L, dim, hid))
+  if (!(drop_p >= 0.f) || drop_p >= 1.f) return fail(RRT_E_INVALID, "drop_p must be in [0, 1)");
+  const bool gated = (act & RRT_ACT_GATED) != 0;
+  const int N = gated ? 2 * hid : hid;
+  if (dim % 128 || dim > 1024 || N % 128 || N > 256 || (gated && hid != 128))
+    return fail(RRT_E_INVALID, "attn_pool backward: dim % 128 (<= 1024), hid in {128, 256} (128 when gated)");
+  int a;
+  int rc = act_code(act & ~RRT_ACT_GATED, &a);
+  if (rc) return rc;
+  if (a == rrt::kActGelu && !pre)
+    return fail(RRT_E_INVALID, "attn_pool backward through gelu needs the forward's pre-activations (pre)");
+  if (tape_bytes < head_ws_bytes(L, dim, dim, N)) return fail(RRT_E_WORKSPACE, "tape too small");
+  if (!workspace || (((uintptr_t)workspace | (uintptr_t)tape) & 255) || workspace_bytes < head_bwd_ws_bytes(L, dim, N))
     return fail(RRT_E_WORKSPACE, "workspace too small or misaligned");
   cudaStream_t st = (cudaStream_t)stream;
   // the forward's workspace (rrt_attn_pool_forward): h16 | weight scratch | hidden | scores | partials | (M, Z)
   const char* tp = static_cast<const char*>(tape);
   const __half* h16 = reinterpret_cast<const __half*>(tp);
   tp += align_up((size_t)L * dim * 2);
-  tp += align_up((size_t)dim * (dim > hid ? dim : hid) * 2);
+  tp += align_up((size_t)dim * (dim > N ? dim : N) * 2);
   const float* hidden = reinterpret_cast<const float*>(tp);
-  const float* scores = hidden + (size_t)L * hid;
+  const float* scores = hidden + (size_t)L * N;
   const int nblocks = (int)((L + 63) / 64);
   const float* mz = scores + (((size_t)L + 3) & ~(size_t)3) + (size_t)nblocks * (4 + dim);
   char* p = static_cast<char*>(workspace);
   uint32_t* amax = reinterpret_cast<uint32_t*>(p);                 p += 256;
   float* dp_cdot = reinterpret_cast<float*>(p);                    p += align_up((size_t)(dim + 4) * 4);
-  float* dhid = reinterpret_cast<float*>(p);                       p += align_up((size_t)L * hid * 4);
-  __half* dhid16 = reinterpret_cast<__half*>(p);                   p += align_up((size_t)L * hid * 2);
-  __half* wT = reinterpret_cast<__half*>(p);                       p += align_up((size_t)hid * dim * 2);
+  float* dhid = reinterpret_cast<float*>(p);                       p += align_up((size_t)L * N * 4);
+  __half* dhid16 = reinterpret_cast<__half*>(p);                   p += align_up((size_t)L * N * 2);
+  __half* wT = reinterpret_cast<__half*>(p);                       p += align_up((size_t)N * dim * 2);
   __half* dz16 = reinterpret_cast<__half*>(p);
   StageScope s_(kStOther, st, 10);
   RRT_CUDA(cudaMemsetAsync(amax, 0, 256, st), "zero amax");
   RRT_CUDA(cudaMemsetAsync(dw2, 0, (size_t)hid * 4, st), "zero dw2");
   if (db2) RRT_CUDA(cudaMemsetAsync(db2, 0, 4, st), "zero db2");
-  if (db1) RRT_CUDA(cudaMemsetAsync(db1, 0, (size_t)hid * 4, st), "zero db1");
+  if (db1) RRT_CUDA(cudaMemsetAsync(db1, 0, (size_t)N * 4, st), "zero db1");
   RRT_CUDA(rrt::launch_pool_bwd_head(dlogits, pred_w, pooled, n_classes, dim, dp_cdot, dpred_w, dpred_b, st),
            "pool backward (head)");
-  int a;
-  int rc = act_code(act, &a);
-  if (rc) return rc;
-  RRT_CUDA(rrt::launch_pool_bwd_rows(h, hidden, scores, mz, dp_cdot, w2, a, dh, dhid, dw2, db2, amax, (int)L, dim,
-                                     hid, st), "pool backward (rows)");
+  RRT_CUDA(rrt::launch_pool_bwd_rows(h, hidden, scores, mz, dp_cdot, w2, a, pre,
+                                     rrt::dropout_make(drop_p, seed, RRT_DROP_STREAM_POOL), gated, dh, dhid, dw2,
+                                     db2, amax, (int)L, dim, hid, st), "pool backward (rows)");
   rrt::Grid ident{};
   ident.L = (int)L; ident.Np = (int)L;
-  RRT_CUDA(rrt::launch_grad_partition(dhid, ident, (int)L, hid, amax, dhid16, nullptr, db1, st), "dhid rows");
-  // score-MLP first layer: dh += dhid W1 (dgrad), dW1 = dhid^T h (wgrad, both operands MN-major)
+  RRT_CUDA(rrt::launch_grad_partition(dhid, ident, (int)L, N, amax, dhid16, nullptr, db1, st), "dhid rows");
+  // score-MLP first layer(s): dh += dhid W1 (dgrad), dW1 = dhid^T h (wgrad, both operands MN-major)
   rrt::GemmEpilogue e;
-  RRT_CUDA(rrt::launch_wt_convert(w1, wT, hid, dim, st), "w1 transpose");
-  RRT_CUDA(rrt::launch_gemm_tcgen05(dhid16, wT, dz16, true, (int)L, dim, hid, e, st), "pool dgrad");
+  RRT_CUDA(rrt::launch_wt_convert(w1, wT, N, dim, st), "w1 transpose");
+  RRT_CUDA(rrt::launch_gemm_tcgen05(dhid16, wT, dz16, true, (int)L, dim, N, e, st), "pool dgrad");
   RRT_CUDA(rrt::launch_add_scaled_f16(dh, dz16, (size_t)L * dim, amax, st), "pool dh accumulate");
-  RRT_CUDA(cudaMemsetAsync(dw1, 0, (size_t)hid * dim * 4, st), "zero dw1");
-  RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad(dhid16, h16, dw1, (int)L, hid, dim, st), "pool wgrad");
-  RRT_CUDA(rrt::launch_scale_by_inv(dw1, (size_t)hid * dim, amax, st), "pool wgrad unscale");
+  RRT_CUDA(cudaMemsetAsync(dw1, 0, (size_t)N * dim * 4, st), "zero dw1");
+  RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad(dhid16, h16, dw1, (int)L, N, dim, st), "pool wgrad");
+  RRT_CUDA(rrt::launch_scale_by_inv(dw1, (size_t)N * dim, amax, st), "pool wgrad unscale");
   return RRT_OK;
 }
 

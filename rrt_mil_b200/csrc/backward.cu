@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, 
 // S(amax); the scaled fp16 rows go to `rows` [M, C] (nullable).  !IN_F32: `in` is fp16 [M, C].
 // Both: transpose to outT [C, M64] (nullable), columns >= M zero; colsum[c] += sum over rows of the
 // UNSCALED value (fp16 input: value * 1/S(amax) when amax != null).
+// mask_src (IN_F32): mode 0 = keep (x mask_scale) where mask_src != 0 (ReLU read off its output); mode 1 =
+// multiply by gelu'(mask_src), mask_src = the layer's pre-activations.
 constexpr int kTileR = 64, kTileC = 128, kLdt = 130;
 template <bool IN_F32>
 __global__ void __launch_bounds__(256) grad_tile_kernel(const void* __restrict__ in_,
@@ -36,7 +38,8 @@ __global__ void __launch_bounds__(256) grad_tile_kernel(const void* __restrict__
                                                         float* __restrict__ colsum,
                                                         const uint32_t* __restrict__ amax, Grid grid,
                                                         int M, int M64, int C, Dropout drop,
-                                                        const float* __restrict__ mask_src, float mask_scale) {
+                                                        const float* __restrict__ mask_src, float mask_scale,
+                                                        int mask_mode) {
   __shared__ __align__(16) __half tile[kTileR * kLdt];
   __shared__ float red[8][kTileC];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -59,8 +62,12 @@ __global__ void __launch_bounds__(256) grad_tile_kernel(const void* __restrict__
           }
           if (IN_F32 && mask_src) {
             const float4 m = __ldg(reinterpret_cast<const float4*>(mask_src + (size_t)t * C + c0) + lane);
+            if (mask_mode == 1) {  // mask_src = pre-activations of an nn.GELU
+              v.x *= gelu_grad(m.x); v.y *= gelu_grad(m.y); v.z *= gelu_grad(m.z); v.w *= gelu_grad(m.w);
+            } else {
             v.x = m.x != 0.f ? v.x * mask_scale : 0.f; v.y = m.y != 0.f ? v.y * mask_scale : 0.f;
             v.z = m.z != 0.f ? v.z * mask_scale : 0.f; v.w = m.w != 0.f ? v.w * mask_scale : 0.f;
+            }
           }
         }
       } else {
@@ -238,12 +245,12 @@ cudaError_t launch_amax(const float* x, size_t n, uint32_t* amax, cudaStream_t s
 
 cudaError_t launch_grad_partition(const float* g, const Grid& grid, int M, int C, const uint32_t* amax,
                                   __half* rows, __half* rowsT, float* colsum, cudaStream_t stream,
-                                  const Dropout& drop, const float* mask_src, float mask_scale) {
+                                  const Dropout& drop, const float* mask_src, float mask_scale, int mask_mode) {
   if (C % kTileC || M <= 0) return cudaErrorInvalidValue;
   const int M64 = (M + 63) / 64 * 64;
   dim3 gr(M64 / kTileR, C / kTileC);
   grad_tile_kernel<true><<<gr, 256, 0, stream>>>(g, rows, rowsT, colsum, amax, grid, M, M64, C, drop, mask_src,
-                                                 mask_scale);
+                                                 mask_scale, mask_mode);
   return cudaGetLastError();
 }
 
@@ -285,7 +292,7 @@ cudaError_t launch_transpose_f16(const __half* in, int M, int C, __half* outT, f
   dim3 gr(M64 / kTileR, C / kTileC);
   Grid none{};
   grad_tile_kernel<false><<<gr, 256, 0, stream>>>(in, nullptr, outT, colsum, amax, none, M, M64, C, Dropout{},
-                                                  nullptr, 1.f);
+                                                  nullptr, 1.f, 0);
   return cudaGetLastError();
 }
 

@@ -199,6 +199,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// nn.GELU() (erf form) and its derivative  Phi(z) + z phi(z)
+__device__ __forceinline__ float gelu_fwd(float z) { return 0.5f * z * (1.f + erff(z * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float z) {
+  return 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
+}
+
 // D(16x8,f32) += A(16x8,tf32,row) * B(8x8,tf32,col)
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4],
                                                 const uint32_t (&b)[2]) {

@@ -54,6 +54,7 @@ struct Tc05Params {
   const float* resid;
   Grid grid;
   int act;           // GemmActivation, store mode only
+  int act2, act_split;  // columns >= act_split (multiple of 32, 0 = none) use act2
   Dropout drop;      // kEpiResidualUnpartDrop only
   int ksplit;        // >= 1: the K loop of every tile is cut into ksplit work items (kEpiAtomicAdd)
   long long* trace;  // debug: per-CTA clock64 stamps (tools/gemm_trace.py), null in production
@@ -203,6 +204,7 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
           __syncwarp();
         }
         uint8_t* rowp = stage + lane * ROWB;
+        const int act_j = (p.act_split > 0 && n0 + (c_begin + j) * 32 >= p.act_split) ? p.act2 : p.act;
         // swizzle: 16-B chunk index ^= bits of the row (128B pattern: row%8; 64B pattern: (row/2)%4)
         const int sw = ROWB == 128 ? (lane & 7) : ((lane >> 1) & 3);
 #pragma unroll
@@ -212,7 +214,7 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
 #pragma unroll
           for (int e = 0; e < EPC; ++e) {
             f[e] = __uint_as_float(rr[q * EPC + e]) + __shfl_sync(0xffffffffu, bias_l[j], q * EPC + e);
-            if (MODE == kEpiStoreAct) f[e] = apply_act(f[e], p.act);
+            if (MODE == kEpiStoreAct) f[e] = apply_act(f[e], act_j);
           }
           uint4 pk;
           if (sizeof(OutT) == 2) {
@@ -899,6 +901,8 @@ cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float
   p.M = C_out; p.N = C_in; p.K = rows;
   p.C = dw;
   p.act = kActNone;
+  p.act2 = kActNone;
+  p.act_split = 0;
   p.trace = nullptr;
   const int tiles = ((C_out + BM - 1) / BM) * ((C_in + BN - 1) / BN), KB = (rows + BK - 1) / BK;
   int ksplit = sm_count() / tiles;
@@ -938,6 +942,9 @@ cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool 
   p.M = M; p.N = N; p.K = K;
   p.bias = epi.bias; p.C = c; p.resid = epi.resid; p.grid = epi.grid;
   p.act = epi.mode == kEpiTanh ? (int)kActTanh : epi.act;
+  p.act2 = epi.act2;
+  p.act_split = epi.act_split;
+  if (p.act_split % 32 || p.act_split < 0) return cudaErrorInvalidValue;
   p.trace = g_gemm_trace ? g_gemm_trace + (size_t)(g_trace_launch++ % 8) * 128 : nullptr;
   p.drop = epi.drop;
   p.ksplit = 1;
@@ -956,7 +963,7 @@ cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool 
     return out_f16 ? cudaErrorInvalidValue : launch_mode<kEpiResidualUnpartDrop, float>(a, w, p, stream);
   if (is_resid_mode(epi.mode))
     return out_f16 ? cudaErrorInvalidValue : launch_mode<kEpiResidualUnpart, float>(a, w, p, stream);
-  if (p.act != kActNone)
+  if (p.act != kActNone || (p.act_split > 0 && p.act2 != kActNone))
     return out_f16 ? launch_mode<kEpiStoreAct, __half>(a, w, p, stream)
                    : launch_mode<kEpiStoreAct, float>(a, w, p, stream);
   return out_f16 ? launch_mode<kEpiStore, __half>(a, w, p, stream)

@@ -35,6 +35,8 @@ enum GemmActivation { kActNone = 0, kActRelu = 1, kActGelu = 2, kActTanh = 3, kA
 struct GemmEpilogue {
   int mode = kEpiStore;
   int act = kActNone;            // applied to acc + bias (tcgen05 kernel, store mode)
+  int act2 = kActNone;           // columns >= act_split (a multiple of 32; 0 = no split) use act2 instead:
+  int act_split = 0;             //   the gated pooling head runs [W_a; W_b] as one GEMM (act | sigmoid)
   const float* bias = nullptr;   // [N] or null
   const float* resid = nullptr;  // [L, N] (mode 2)
   Grid grid{};                   // (mode 2)
@@ -143,15 +145,17 @@ size_t attn_pool_scratch_floats(int L, int D, int hid);
 cudaError_t launch_attn_pool(const float* h, const float* hidden, const float* w2, const float* b2,
                              const float* pred_w, const float* pred_b, int n_classes, float* scratch,
                              float* pooled, float* logits, float* attn, int attn_raw, int L, int D,
-                             int hid, cudaStream_t stream);
+                             int hid, bool gated, cudaStream_t stream);
+// buf[r, 0:n] (row pitch ld) holds pre-activations: copy them to pre [rows, n] and apply nn.GELU in place
+cudaError_t launch_gelu_keep_pre(float* buf, float* pre, size_t rows, int n, int ld, cudaStream_t stream);
 
 // backward of the pooling head (mil_head.cu): dp_cdot = dpooled[D] | pooled . dpooled
 cudaError_t launch_pool_bwd_head(const float* dlogits, const float* pred_w, const float* pooled, int n_classes,
                                  int D, float* dp_cdot, float* dpred_w, float* dpred_b, cudaStream_t stream);
 cudaError_t launch_pool_bwd_rows(const float* h, const float* hidden, const float* scores, const float* mz,
-                                 const float* dp_cdot, const float* w2, int act, float* dh, float* dhid,
-                                 float* dw2, float* db2, uint32_t* amax, int L, int D, int hid,
-                                 cudaStream_t stream);
+                                 const float* dp_cdot, const float* w2, int act, const float* pre,
+                                 const Dropout& drop, bool gated, float* dh, float* dhid, float* dw2, float* db2,
+                                 uint32_t* amax, int L, int D, int hid, cudaStream_t stream);
 cudaError_t launch_add_scaled_f16(float* dh, const __half* dz, size_t n, const uint32_t* amax,
                                   cudaStream_t stream);
 
@@ -167,7 +171,7 @@ cudaError_t launch_amax(const float* x, size_t n, uint32_t* amax, cudaStream_t s
 cudaError_t launch_grad_partition(const float* g, const Grid& grid, int M, int C, const uint32_t* amax,
                                   __half* rows, __half* rowsT, float* colsum, cudaStream_t stream,
                                   const Dropout& drop = Dropout{}, const float* mask_src = nullptr,
-                                  float mask_scale = 1.f);
+                                  float mask_scale = 1.f, int mask_mode = 0);
 // x[i] *= mask(i) / (1-p) in place, x fp32 [rows, C] (the landmark projection output in training mode)
 cudaError_t launch_dropout_inplace(float* x, size_t n, const Dropout& drop, cudaStream_t stream);
 // mask(i)/(1-p) of n elements as fp32 (parity tests: the oracle consumes the same mask)

@@ -12,16 +12,37 @@
 namespace rrt {
 namespace {
 
+// hidden: [L, ld]; gated (AttentionGated, modules/datten.py:66-70): columns [hid, 2 hid) hold the sigmoid
+// branch and multiply the first hid columns before the dot product with w2 (= attention_c.weight)
 __global__ void __launch_bounds__(256) pool_scores_kernel(const float* __restrict__ hidden,
                                                           const float* __restrict__ w2,
                                                           const float* __restrict__ b2,
-                                                          float* __restrict__ scores, int L, int hid) {
+                                                          float* __restrict__ scores, int L, int hid, int ld,
+                                                          int gated) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= L) return;
   float d = 0.f;
-  for (int c = lane; c < hid; c += 32) d = fmaf(__ldg(hidden + (size_t)row * hid + c), __ldg(w2 + c), d);
+  for (int c = lane; c < hid; c += 32) {
+    float v = __ldg(hidden + (size_t)row * ld + c);
+    if (gated) v *= __ldg(hidden + (size_t)row * ld + hid + c);
+    d = fmaf(v, __ldg(w2 + c), d);
+  }
   d = warp_sum(d);
   if (lane == 0) scores[row] = d + (b2 ? __ldg(b2) : 0.f);
+}
+
+// training forward through nn.GELU: the GEMM stored the PRE-activation; keep it (the backward needs it, the
+// output alone does not determine gelu') and activate.  buf: [L, ld], columns [0, n) are touched; pre: [L, n]
+__global__ void __launch_bounds__(256) gelu_keep_pre_kernel(float* __restrict__ buf, float* __restrict__ pre,
+                                                            size_t rows, int n4, int ld4) {
+  const size_t total = rows * (size_t)n4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / n4;
+    const int c = (int)(i - r * n4);
+    float4 z = reinterpret_cast<float4*>(buf)[r * ld4 + c];
+    if (pre != buf) reinterpret_cast<float4*>(pre)[i] = z;
+    reinterpret_cast<float4*>(buf)[r * ld4 + c] = make_float4(gelu_fwd(z.x), gelu_fwd(z.y), gelu_fwd(z.z), gelu_fwd(z.w));
+  }
 }
 
 constexpr int kPoolRows = 64;
@@ -126,23 +147,35 @@ __global__ void pool_weights_kernel(const float* __restrict__ scores, const floa
 }
 }  // namespace
 
+// hid = row length of the hidden buffer (2 x the attention width for the gated head)
 size_t attn_pool_scratch_floats(int L, int D, int hid) {
   size_t nblocks = (L + kPoolRows - 1) / kPoolRows;
   return (size_t)L * hid + (size_t)L + nblocks * (4 + D) + 4;
 }
 
-// hidden: [L, hid] fp32 (already activated); h: [L, D] fp32.  scratch: attn_pool_scratch_floats minus
-// the hidden buffer, laid out as scores[L] | part[nblocks][4+D] | mz[4]
+cudaError_t launch_gelu_keep_pre(float* buf, float* pre, size_t rows, int n, int ld, cudaStream_t stream) {
+  if (n % 4 || ld % 4 || !pre) return cudaErrorInvalidValue;
+  if (rows == 0) return cudaSuccess;
+  size_t items = rows * (size_t)(n / 4);
+  int blocks = (int)((items + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  gelu_keep_pre_kernel<<<blocks, 256, 0, stream>>>(buf, pre, rows, n / 4, ld / 4);
+  return cudaGetLastError();
+}
+
+// hidden: [L, ld] fp32 (already activated; ld = hid, or 2 hid when gated); h: [L, D] fp32.  scratch:
+// attn_pool_scratch_floats minus the hidden buffer, laid out as scores[L] | part[nblocks][4+D] | mz[4]
 cudaError_t launch_attn_pool(const float* h, const float* hidden, const float* w2, const float* b2,
                              const float* pred_w, const float* pred_b, int n_classes, float* scratch,
                              float* pooled, float* logits, float* attn, int attn_raw, int L, int D,
-                             int hid, cudaStream_t stream) {
+                             int hid, bool gated, cudaStream_t stream) {
   if (L < 1 || D % 4 || n_classes < 0) return cudaErrorInvalidValue;
   const int nblocks = (L + kPoolRows - 1) / kPoolRows;
   float* scores = scratch;
   float* part = scores + (((size_t)L + 3) & ~(size_t)3);
   float* mz = part + (size_t)nblocks * (4 + D);
-  pool_scores_kernel<<<(L + 7) / 8, 256, 0, stream>>>(hidden, w2, b2, scores, L, hid);
+  pool_scores_kernel<<<(L + 7) / 8, 256, 0, stream>>>(hidden, w2, b2, scores, L, hid, gated ? 2 * hid : hid,
+                                                      gated ? 1 : 0);
   pool_partial_kernel<<<nblocks, 256, 0, stream>>>(h, scores, part, L, D);
   size_t smem = ((size_t)nblocks + D) * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
@@ -206,13 +239,17 @@ __global__ void __launch_bounds__(512) pool_bwd_head_kernel(const float* __restr
   }
 }
 
-// warp per token (grid-stride).  V = D / 128; hid <= 128 * HV.  act: kActRelu | kActTanh | kActNone
-template <int V, int HV>
+// warp per token (grid-stride).  V = D / 128; hid <= 128 * HV.  act: kActRelu | kActTanh | kActGelu | kActNone.
+// hidden holds the values the score layer consumed (after the activation and, when drop.on(), after the MLP's
+// nn.Dropout, whose mask is regenerated here: index = l * ld + column, stream RRT_DROP_STREAM_POOL).
+// pre: [L, hid] pre-activations, GELU only.  GATED (hid == 128, ld == 256): columns 128.. are the sigmoid branch:
+//   s = sum_c a_c b_c w2_c  ->  da_c = ds w2_c b_c,  db_c = ds w2_c a_c,  dz_b = db m_b sig(1 - sig)
+template <int V, int HV, bool GATED>
 __global__ void __launch_bounds__(256) pool_bwd_rows_kernel(
     const float* __restrict__ h, const float* __restrict__ hidden, const float* __restrict__ scores,
     const float* __restrict__ mz, const float* __restrict__ dp_cdot, const float* __restrict__ w2, int act,
-    float* __restrict__ dh, float* __restrict__ dhid, float* __restrict__ dw2, float* __restrict__ db2,
-    uint32_t* __restrict__ amax, int L, int hid) {
+    const float* __restrict__ pre, Dropout drop, float* __restrict__ dh, float* __restrict__ dhid,
+    float* __restrict__ dw2, float* __restrict__ db2, uint32_t* __restrict__ amax, int L, int hid, int ld) {
   constexpr int D = 128 * V;
   __shared__ float s_dw2[128 * HV];
   __shared__ float s_db2;
@@ -231,6 +268,15 @@ __global__ void __launch_bounds__(256) pool_bwd_rows_kernel(
     w2r[j] = c < hid ? __ldg(w2 + c) : 0.f;
     acc_dw2[j] = 0.f;
   }
+  // derivative of (dropout o act) wrt the pre-activation, from the stored value hv, its mask factor m
+  // (0 or 1/(1-p); 1 without dropout) and, for GELU, the pre-activation z
+  auto dact = [&](float hv, float m, float z) -> float {
+    if (act == kActRelu) return hv != 0.f ? m : 0.f;
+    if (act == kActTanh) { const float t = m != 0.f ? hv / m : 0.f; return m * (1.f - t * t); }
+    if (act == kActGelu) return m * gelu_grad(z);
+    return m;
+  };
+  const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
   float acc_db2 = 0.f, amx = 0.f;
   for (int l = blockIdx.x * wpb + warp; l < L; l += gridDim.x * wpb) {
     const float4* hrow = reinterpret_cast<const float4*>(h + (size_t)l * D);
@@ -249,22 +295,49 @@ __global__ void __launch_bounds__(256) pool_bwd_rows_kernel(
     for (int i = 0; i < V; ++i)
       drow[lane + 32 * i] = make_float4(a * dp[i].x, a * dp[i].y, a * dp[i].z, a * dp[i].w);
     acc_db2 += da;   // identical on every lane
+    if (GATED) {
+      const int c = 4 * lane;
+      const size_t ia = (size_t)l * ld + c, ib = ia + hid;
+      const float4 ha4 = __ldg(reinterpret_cast<const float4*>(hidden + ia));
+      const float4 hb4 = __ldg(reinterpret_cast<const float4*>(hidden + ib));
+      const float4 ma4 = drop.on() ? dropout_scale4(drop, ia) : one4;
+      const float4 mb4 = drop.on() ? dropout_scale4(drop, ib) : one4;
+      const float4 pz4 = act == kActGelu ? __ldg(reinterpret_cast<const float4*>(pre + (size_t)l * hid + c)) : one4;
+      const float ha[4] = {ha4.x, ha4.y, ha4.z, ha4.w}, hb[4] = {hb4.x, hb4.y, hb4.z, hb4.w};
+      const float ma[4] = {ma4.x, ma4.y, ma4.z, ma4.w}, mb[4] = {mb4.x, mb4.y, mb4.z, mb4.w};
+      const float pz[4] = {pz4.x, pz4.y, pz4.z, pz4.w};
+      float oa[4], ob[4];
 #pragma unroll
-    for (int q = 0; q < HV; ++q) {
-      const int c = 4 * lane + 128 * q;
-      if (c < hid) {
-        const float4 hd = __ldg(reinterpret_cast<const float4*>(hidden + (size_t)l * hid + c));
-        const float hv4[4] = {hd.x, hd.y, hd.z, hd.w};
-        float o[4];
+      for (int e = 0; e < 4; ++e) {
+        acc_dw2[e] = fmaf(da, ha[e] * hb[e], acc_dw2[e]);
+        const float dg = da * w2r[e];
+        oa[e] = dg * hb[e] * dact(ha[e], ma[e], pz[e]);
+        const float sg = mb[e] != 0.f ? hb[e] / mb[e] : 0.f;
+        ob[e] = dg * ha[e] * mb[e] * sg * (1.f - sg);
+        amx = fmaxf(amx, fmaxf(fabsf(oa[e]), fabsf(ob[e])));
+      }
+      *reinterpret_cast<float4*>(dhid + ia) = make_float4(oa[0], oa[1], oa[2], oa[3]);
+      *reinterpret_cast<float4*>(dhid + ib) = make_float4(ob[0], ob[1], ob[2], ob[3]);
+    } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          acc_dw2[4 * q + e] = fmaf(da, hv4[e], acc_dw2[4 * q + e]);
-          const float d = act == kActRelu ? (hv4[e] > 0.f ? 1.f : 0.f)
-                                          : (act == kActTanh ? 1.f - hv4[e] * hv4[e] : 1.f);
-          o[e] = da * w2r[4 * q + e] * d;
-          amx = fmaxf(amx, fabsf(o[e]));
+      for (int q = 0; q < HV; ++q) {
+        const int c = 4 * lane + 128 * q;
+        if (c < hid) {
+          const size_t idx = (size_t)l * ld + c;
+          const float4 hd = __ldg(reinterpret_cast<const float4*>(hidden + idx));
+          const float4 m4 = drop.on() ? dropout_scale4(drop, idx) : one4;
+          const float4 pz4 = act == kActGelu ? __ldg(reinterpret_cast<const float4*>(pre + (size_t)l * hid + c)) : one4;
+          const float hv4[4] = {hd.x, hd.y, hd.z, hd.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
+          const float pz[4] = {pz4.x, pz4.y, pz4.z, pz4.w};
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc_dw2[4 * q + e] = fmaf(da, hv4[e], acc_dw2[4 * q + e]);
+            o[e] = da * w2r[4 * q + e] * dact(hv4[e], mm[e], pz[e]);
+            amx = fmaxf(amx, fabsf(o[e]));
+          }
+          *reinterpret_cast<float4*>(dhid + idx) = make_float4(o[0], o[1], o[2], o[3]);
         }
-        *reinterpret_cast<float4*>(dhid + (size_t)l * hid + c) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
   }
@@ -305,20 +378,21 @@ cudaError_t launch_pool_bwd_head(const float* dlogits, const float* pred_w, cons
 }
 
 cudaError_t launch_pool_bwd_rows(const float* h, const float* hidden, const float* scores, const float* mz,
-                                 const float* dp_cdot, const float* w2, int act, float* dh, float* dhid,
-                                 float* dw2, float* db2, uint32_t* amax, int L, int D, int hid,
-                                 cudaStream_t stream) {
+                                 const float* dp_cdot, const float* w2, int act, const float* pre,
+                                 const Dropout& drop, bool gated, float* dh, float* dhid, float* dw2, float* db2,
+                                 uint32_t* amax, int L, int D, int hid, cudaStream_t stream) {
   if (D % 128 || D > 1024 || hid % 4 || hid > 256) return cudaErrorInvalidValue;
+  if (gated && hid != 128) return cudaErrorInvalidValue;
+  if (act == kActGelu && !pre) return cudaErrorInvalidValue;
+  const int ld = gated ? 2 * hid : hid;
   int blocks = (L + 7) / 8;
   if (blocks > 148 * 4) blocks = 148 * 4;
-#define RRT_PB(VV)                                                                                          \
-  {                                                                                                         \
-    if (hid <= 128)                                                                                         \
-      pool_bwd_rows_kernel<VV, 1><<<blocks, 256, 0, stream>>>(h, hidden, scores, mz, dp_cdot, w2, act, dh,  \
-                                                              dhid, dw2, db2, amax, L, hid);                \
-    else                                                                                                    \
-      pool_bwd_rows_kernel<VV, 2><<<blocks, 256, 0, stream>>>(h, hidden, scores, mz, dp_cdot, w2, act, dh,  \
-                                                              dhid, dw2, db2, amax, L, hid);                \
+#define RRT_PB_ARGS h, hidden, scores, mz, dp_cdot, w2, act, pre, drop, dh, dhid, dw2, db2, amax, L, hid, ld
+#define RRT_PB(VV)                                                                        \
+  {                                                                                       \
+    if (gated) pool_bwd_rows_kernel<VV, 1, true><<<blocks, 256, 0, stream>>>(RRT_PB_ARGS); \
+    else if (hid <= 128) pool_bwd_rows_kernel<VV, 1, false><<<blocks, 256, 0, stream>>>(RRT_PB_ARGS); \
+    else pool_bwd_rows_kernel<VV, 2, false><<<blocks, 256, 0, stream>>>(RRT_PB_ARGS);     \
   }
   switch (D / 128) {
     case 1: RRT_PB(1) break;
@@ -328,6 +402,7 @@ cudaError_t launch_pool_bwd_rows(const float* h, const float* hidden, const floa
     default: return cudaErrorInvalidValue;
   }
 #undef RRT_PB
+#undef RRT_PB_ARGS
   return cudaGetLastError();
 }
 

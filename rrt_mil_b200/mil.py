@@ -34,10 +34,40 @@ class Attention(nn.Module):
         if act in _ACT:
             layers.append(_ACT[act][0]())
             self.act_code = _ACT[act][1]
+        self.drop_p = 0.25 if dropout else 0.0
         if dropout:
             layers.append(nn.Dropout(0.25))
         layers.append(nn.Linear(self.D, self.K, bias=bias))
         self.attention = nn.Sequential(*layers)
+
+    def head_params(self):
+        """(first-layer Linear modules, score Linear, act code for the C entry)."""
+        return [self.attention[0]], self.attention[-1], self.act_code
+
+
+class AttentionGated(nn.Module):
+    """Parameters of modules/datten.py:40-65: ``attention_a`` = Linear-act-[Dropout], ``attention_b`` =
+    Linear-Sigmoid-[Dropout], ``attention_c`` = Linear(128,1); scores = attention_c(a * b)."""
+
+    def __init__(self, input_dim=512, act='relu', bias=False, dropout=False):
+        super().__init__()
+        self.L, self.D, self.K = input_dim, 128, 1
+        a = [nn.Linear(self.L, self.D, bias=bias)]
+        self.act_code = cabi.RRT_ACT_NONE
+        if act in _ACT:
+            a.append(_ACT[act][0]())
+            self.act_code = _ACT[act][1]
+        b = [nn.Linear(self.L, self.D, bias=bias), nn.Sigmoid()]
+        self.drop_p = 0.25 if dropout else 0.0
+        if dropout:
+            a.append(nn.Dropout(0.25))
+            b.append(nn.Dropout(0.25))
+        self.attention_a = nn.Sequential(*a)
+        self.attention_b = nn.Sequential(*b)
+        self.attention_c = nn.Linear(self.D, self.K, bias=bias)
+
+    def head_params(self):
+        return [self.attention_a[0], self.attention_b[0]], self.attention_c, self.act_code | cabi.RRT_ACT_GATED
 
 
 class DAttention(nn.Module):
@@ -45,10 +75,8 @@ class DAttention(nn.Module):
 
     def __init__(self, input_dim=512, act='relu', gated=False, bias=False, dropout=False):
         super().__init__()
-        if gated:
-            raise NotImplementedError("da_gated=True (AttentionGated) is not built")
         self.gated = gated
-        self.attention = Attention(input_dim, act, bias, dropout)
+        self.attention = (AttentionGated if gated else Attention)(input_dim, act, bias, dropout)
 
 
 def _stream(dev):
@@ -69,17 +97,20 @@ class _PatchEmbedFunction(torch.autograd.Function):
             cabi.check(lib.rrt_mil_head_workspace_bytes(L, max(in_dim, dim), dim, 128, C.byref(n)), "workspace")
             tape = torch.empty(n.value, dtype=torch.uint8, device=dev)
             out = torch.empty(L, dim, device=dev)
+            # nn.GELU: the backward needs the pre-activations (gelu' is not a function of the output)
+            pre = torch.empty(L, dim, device=dev) if mil._fc_act == cabi.RRT_ACT_GELU else None
             cabi.check(lib.rrt_patch_embed_forward(bag.data_ptr(), L, in_dim, dim, weight.data_ptr(),
                                                    RRTMIL._p(bias), None, mil._fc_act, out.data_ptr(),
-                                                   tape.data_ptr(), n.value, drop_p, seed, _stream(dev)),
+                                                   tape.data_ptr(), n.value, drop_p, seed, RRTMIL._p(pre),
+                                                   _stream(dev)),
                        "rrt_patch_embed_forward")
         ctx.mil, ctx.drop, ctx.shape = mil, (drop_p, seed), (L, in_dim, dim)
-        ctx.save_for_backward(out, tape, weight, bias)
+        ctx.save_for_backward(out, tape, weight, bias, pre)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        out, tape, weight, bias = ctx.saved_tensors
+        out, tape, weight, bias, pre = ctx.saved_tensors
         lib, dev = cabi.lib(), out.device
         L, in_dim, dim = ctx.shape
         dout = dout.contiguous().float()
@@ -88,7 +119,7 @@ class _PatchEmbedFunction(torch.autograd.Function):
             db = torch.empty_like(bias) if bias is not None else None
             nws = 512 + L * dim * 2 + 256
             ws = torch.empty(nws, dtype=torch.uint8, device=dev)
-            cabi.check(lib.rrt_patch_embed_backward(dout.data_ptr(), out.data_ptr(), L, in_dim, dim,
+            cabi.check(lib.rrt_patch_embed_backward(dout.data_ptr(), out.data_ptr(), RRTMIL._p(pre), L, in_dim, dim,
                                                     ctx.mil._fc_act, ctx.drop[0], ctx.drop[1], tape.data_ptr(),
                                                     tape.numel(), dw.data_ptr(), RRTMIL._p(db), ws.data_ptr(),
                                                     nws, _stream(dev)), "rrt_patch_embed_backward")
@@ -96,50 +127,64 @@ class _PatchEmbedFunction(torch.autograd.Function):
 
 
 class _AttnPoolFunction(torch.autograd.Function):
-    """logits = predictor(DAttention(h)) (modules/datten.py:28-38, modules/rrt.py:241)."""
+    """logits = predictor(DAttention(h)) (modules/datten.py:28-38,66-83, modules/rrt.py:241).  ``wb`` / ``bb`` are
+    the gate branch of AttentionGated (None for the plain head): the C entry takes [W_a; W_b] as one matrix."""
 
     @staticmethod
-    def forward(ctx, mil, h, w1, b1, w2, b2, pw, pb):
+    def forward(ctx, mil, h, wa, ba, wb, bb, w2, b2, pw, pb):
         lib, dev = cabi.lib(), h.device
         L, dim = h.shape
-        hid, ncls = w1.shape[0], pw.shape[0]
+        gated = wb is not None
+        w1 = torch.cat([wa, wb]) if gated else wa
+        b1 = (torch.cat([ba, bb]) if gated else ba) if ba is not None else None
+        hid, n1, ncls = wa.shape[0], w1.shape[0], pw.shape[0]
+        act = mil.pool_fn.attention.head_params()[2]
+        drop_p, seed = mil._pool_dropout()
         with torch.cuda.device(dev):
             n = C.c_size_t()
-            cabi.check(lib.rrt_mil_head_workspace_bytes(L, dim, dim, hid, C.byref(n)), "workspace")
+            cabi.check(lib.rrt_mil_head_workspace_bytes(L, dim, dim, n1, C.byref(n)), "workspace")
             tape = torch.empty(n.value, dtype=torch.uint8, device=dev)
             pooled, logits = torch.empty(dim, device=dev), torch.empty(ncls, device=dev)
+            pre = torch.empty(L, hid, device=dev) if (act & 0xff) == cabi.RRT_ACT_GELU else None
             cabi.check(lib.rrt_attn_pool_forward(h.data_ptr(), L, dim, hid, w1.data_ptr(), RRTMIL._p(b1), None,
-                                                 mil.pool_fn.attention.act_code, w2.data_ptr(), RRTMIL._p(b2),
+                                                 act, w2.data_ptr(), RRTMIL._p(b2),
                                                  pw.data_ptr(), RRTMIL._p(pb), ncls, pooled.data_ptr(),
-                                                 logits.data_ptr(), None, 0, tape.data_ptr(), n.value,
-                                                 _stream(dev)), "rrt_attn_pool_forward")
-        ctx.mil = mil
-        ctx.save_for_backward(h, tape, pooled, w1, b1, w2, b2, pw, pb)
+                                                 logits.data_ptr(), None, 0, drop_p, seed, RRTMIL._p(pre),
+                                                 tape.data_ptr(), n.value, _stream(dev)), "rrt_attn_pool_forward")
+        ctx.mil, ctx.act, ctx.drop, ctx.gated, ctx.has_b1 = mil, act, (drop_p, seed), gated, b1 is not None
+        ctx.save_for_backward(h, tape, pooled, w1, w2, b2, pw, pb, pre)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        h, tape, pooled, w1, b1, w2, b2, pw, pb = ctx.saved_tensors
+        h, tape, pooled, w1, w2, b2, pw, pb, pre = ctx.saved_tensors
         lib, dev = cabi.lib(), h.device
         L, dim = h.shape
-        hid, ncls = w1.shape[0], pw.shape[0]
+        n1, ncls = w1.shape[0], pw.shape[0]
+        hid = n1 // 2 if ctx.gated else n1
         dlogits = dlogits.contiguous().float()
         with torch.cuda.device(dev):
             n = C.c_size_t()
-            cabi.check(lib.rrt_mil_head_backward_workspace_bytes(L, dim, hid, C.byref(n)), "workspace")
+            cabi.check(lib.rrt_mil_head_backward_workspace_bytes(L, dim, n1, C.byref(n)), "workspace")
             ws = torch.empty(n.value, dtype=torch.uint8, device=dev)
             dh = torch.empty_like(h)
             dw1, dw2, dpw = torch.empty_like(w1), torch.empty_like(w2), torch.empty_like(pw)
-            db1 = torch.empty_like(b1) if b1 is not None else None
+            db1 = torch.empty(n1, device=dev) if ctx.has_b1 else None
             db2 = torch.empty_like(b2) if b2 is not None else None
             dpb = torch.empty_like(pb) if pb is not None else None
-            cabi.check(lib.rrt_attn_pool_backward(h.data_ptr(), L, dim, hid, w1.data_ptr(),
-                                                  ctx.mil.pool_fn.attention.act_code, w2.data_ptr(), pw.data_ptr(),
-                                                  ncls, pooled.data_ptr(), dlogits.data_ptr(), tape.data_ptr(),
-                                                  tape.numel(), dh.data_ptr(), dw1.data_ptr(), RRTMIL._p(db1),
-                                                  dw2.data_ptr(), RRTMIL._p(db2), dpw.data_ptr(), RRTMIL._p(dpb),
-                                                  ws.data_ptr(), n.value, _stream(dev)), "rrt_attn_pool_backward")
-        return None, dh, dw1, db1, dw2, db2, dpw, dpb
+            cabi.check(lib.rrt_attn_pool_backward(h.data_ptr(), L, dim, hid, w1.data_ptr(), ctx.act,
+                                                  w2.data_ptr(), pw.data_ptr(), ncls, pooled.data_ptr(),
+                                                  dlogits.data_ptr(), ctx.drop[0], ctx.drop[1], RRTMIL._p(pre),
+                                                  tape.data_ptr(), tape.numel(), dh.data_ptr(), dw1.data_ptr(),
+                                                  RRTMIL._p(db1), dw2.data_ptr(), RRTMIL._p(db2), dpw.data_ptr(),
+                                                  RRTMIL._p(dpb), ws.data_ptr(), n.value, _stream(dev)),
+                       "rrt_attn_pool_backward")
+        if ctx.gated:
+            dwa, dwb = dw1[:hid], dw1[hid:]
+            dba, dbb = (db1[:hid], db1[hid:]) if db1 is not None else (None, None)
+        else:
+            dwa, dwb, dba, dbb = dw1, None, db1, None
+        return None, dh, dwa, dba, dwb, dbb, dw2, db2, dpw, dpb
 
 
 class RRTMIL(nn.Module):
@@ -200,21 +245,51 @@ class RRTMIL(nn.Module):
             seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
         return self.dropout_p, seed
 
+    def _pool_dropout(self):
+        """(p, seed) of the nn.Dropout(0.25) inside the pooling head's score MLP (da_dropout=True); training only.
+        Same step seed as ``dp``: the two masks come from different counter streams."""
+        p = self.pool_fn.attention.drop_p
+        if not self.training or p <= 0.0:
+            return 0.0, 0
+        if self._dropout_seed is not None:
+            return p, self._dropout_seed
+        return p, int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+    def _head_weights(self):
+        """Inference operands of the pooling head: (w1 fp32, b1, w1 fp16 shadow, score Linear, act code, hid).
+        The gated head's two first layers are concatenated once per parameter version."""
+        firsts, score, act = self.pool_fn.attention.head_params()
+        if len(firsts) == 1:
+            a0 = firsts[0]
+            return a0.weight, a0.bias, self._f16(a0.weight), score, act, a0.out_features
+        ps = [q for l in firsts for q in (l.weight, l.bias) if q is not None]
+        key = tuple((q.data_ptr(), q._version) for q in ps)
+        ent = self._shadow.get("gated")
+        if ent is None or ent[0] != key:
+            with torch.no_grad():
+                w1 = torch.cat([l.weight for l in firsts]).contiguous()
+                b1 = torch.cat([l.bias for l in firsts]).contiguous() if firsts[0].bias is not None else None
+                w16 = torch.empty(w1.shape, dtype=torch.float16, device=w1.device)
+                cabi.check(cabi.lib().rrt_convert_f16(w1.data_ptr(), w16.data_ptr(), w1.numel(), _stream(w1.device)),
+                           "rrt_convert_f16")
+            ent = (key, w1, b1, w16)
+            self._shadow["gated"] = ent
+        return ent[1], ent[2], ent[3].data_ptr(), score, act, firsts[0].out_features
+
     def _forward_train(self, bag):
         """Autograd / training path: three CUDA-backed autograd Functions in a row."""
-        fc, att, pred = self.patch_to_emb[0], self.pool_fn.attention, self.predictor
-        a0, a2 = att.attention[0], att.attention[-1]
-        if self._fc_act == cabi.RRT_ACT_GELU or att.act_code == cabi.RRT_ACT_GELU:
-            raise NotImplementedError("training through act='gelu' / da_act='gelu' is not built "
-                                      "(the backward would need the pre-activations)")
-        if self.training and any(isinstance(m, nn.Dropout) for m in att.attention):
-            raise NotImplementedError("da_dropout=True is not built for training")
-        if fc.out_features % 128 or a0.out_features % 128:
-            raise NotImplementedError("training needs 128-aligned layer widths")
+        fc, pred = self.patch_to_emb[0], self.predictor
+        firsts, score, _ = self.pool_fn.attention.head_params()
+        if fc.out_features % 128 or firsts[0].out_features != 128:
+            raise NotImplementedError("training needs a 128-aligned patch_to_emb width and the reference's "
+                                      "128-wide pooling MLP")
         h0 = _PatchEmbedFunction.apply(self, bag, fc.weight, fc.bias)
         h1 = self.online_encoder.forward_bag(h0)
-        logits = _AttnPoolFunction.apply(self, h1, a0.weight, a0.bias, a2.weight.view(-1), a2.bias, pred.weight,
-                                         pred.bias)
+        gate = firsts[1] if len(firsts) == 2 else None
+        logits = _AttnPoolFunction.apply(self, h1, firsts[0].weight, firsts[0].bias,
+                                         None if gate is None else gate.weight,
+                                         None if gate is None else gate.bias,
+                                         score.weight.view(-1), score.bias, pred.weight, pred.bias)
         return logits.unsqueeze(0)
 
     def forward(self, x, return_attn=False, no_norm=False):
@@ -235,29 +310,30 @@ class RRTMIL(nn.Module):
         L, in_dim = bag.shape
         dev = bag.device
         lib = cabi.lib()
-        fc, att, pred = self.patch_to_emb[0], self.pool_fn.attention, self.predictor
-        a0, a2 = att.attention[0], att.attention[-1]
-        hid, dim, ncls = a0.out_features, self.online_encoder.final_dim, pred.out_features
+        fc, pred = self.patch_to_emb[0], self.predictor
+        w1, b1, w1_f16, score, act, hid = self._head_weights()
+        dim, ncls = self.online_encoder.final_dim, pred.out_features
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
             n = C.c_size_t()
-            cabi.check(lib.rrt_mil_head_workspace_bytes(L, max(in_dim, dim), dim, hid, C.byref(n)), "workspace")
+            cabi.check(lib.rrt_mil_head_workspace_bytes(L, max(in_dim, dim), dim, w1.shape[0], C.byref(n)),
+                       "workspace")
             ws = torch.empty(n.value, dtype=torch.uint8, device=dev)
             h0 = torch.empty(L, dim, device=dev)
             cabi.check(lib.rrt_patch_embed_forward(bag.data_ptr(), L, in_dim, dim, fc.weight.data_ptr(),
                                                    self._p(fc.bias), self._f16(fc.weight), self._fc_act,
-                                                   h0.data_ptr(), ws.data_ptr(), n.value, 0.0, 0, st),
+                                                   h0.data_ptr(), ws.data_ptr(), n.value, 0.0, 0, None, st),
                        "rrt_patch_embed_forward")
             h1 = self.online_encoder.forward_bag(h0)
             pooled = torch.empty(dim, device=dev)
             logits = torch.empty(ncls, device=dev)
             attn = torch.empty(L, device=dev) if return_attn else None
-            cabi.check(lib.rrt_attn_pool_forward(h1.data_ptr(), L, dim, hid, a0.weight.data_ptr(),
-                                                 self._p(a0.bias), self._f16(a0.weight), att.act_code,
-                                                 a2.weight.data_ptr(), self._p(a2.bias),
+            cabi.check(lib.rrt_attn_pool_forward(h1.data_ptr(), L, dim, hid, w1.data_ptr(),
+                                                 self._p(b1), w1_f16, act,
+                                                 score.weight.data_ptr(), self._p(score.bias),
                                                  pred.weight.data_ptr(), self._p(pred.bias), ncls,
                                                  pooled.data_ptr(), logits.data_ptr(), self._p(attn),
-                                                 int(bool(no_norm)), ws.data_ptr(), n.value, st),
+                                                 int(bool(no_norm)), 0.0, 0, None, ws.data_ptr(), n.value, st),
                        "rrt_attn_pool_forward")
         if return_attn:
             return logits.unsqueeze(0), attn.unsqueeze(0)

@@ -16,10 +16,16 @@ MIL = {c["name"]: c for c in MANIFEST.get("mil_cases", [])}
 MIL_TRAIN = {c["name"]: c for c in MANIFEST.get("mil_train_cases", [])}
 
 
+def _head_kw(c):
+    """RRTMIL keywords beyond the fixed columns of a fixture (da_gated, da_dropout, act)."""
+    return dict(c.get("extra") or {})
+
+
 def load_mil(name, dtype=torch.float64):
     c = MIL[name]
     cfg = O.EncoderConfig(**c["config"])
-    w = O.make_mil_weights(cfg, c["input_dim"], c["n_classes"], c["weight_seed"], da_bias=c["da_bias"], dtype=dtype)
+    w = O.make_mil_weights(cfg, c["input_dim"], c["n_classes"], c["weight_seed"], da_bias=c["da_bias"], dtype=dtype,
+                           **{k: v for k, v in _head_kw(c).items() if k in ("da_gated", "da_dropout")})
     x = O.make_bag(c["L"], c["input_dim"], c["bag_seed"], dtype=dtype)
     gold = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
     return c, cfg, w, x, gold
@@ -36,7 +42,8 @@ def test_oracle_mil_matches_golden(name, order):
 
 @pytest.mark.skipif(not shim.available(), reason="/root/reference only exists in the build container")
 @pytest.mark.parametrize("kw", [dict(), dict(input_dim=512, n_classes=4, act='gelu', da_act='tanh', da_bias=True),
-                                dict(epeg_k=21, crmsa_k=5, da_dropout=True)])
+                                dict(epeg_k=21, crmsa_k=5, da_dropout=True),
+                                dict(da_gated=True), dict(da_gated=True, da_bias=True, da_dropout=True, da_act='gelu')])
 def test_rrtmil_state_dict_interchangeable_with_reference(kw):
     from rrt_mil_b200 import RRTMIL
     ref = shim.import_reference_rrt().RRTMIL(**kw)
@@ -49,8 +56,6 @@ def test_rrtmil_state_dict_interchangeable_with_reference(kw):
 def test_rrtmil_unsupported_options_raise():
     from rrt_mil_b200 import RRTMIL
     with pytest.raises(NotImplementedError):
-        RRTMIL(da_gated=True)
-    with pytest.raises(NotImplementedError):
         RRTMIL(pool='avg')
     m = RRTMIL().eval()
     with torch.no_grad(), pytest.raises(RuntimeError):
@@ -60,7 +65,8 @@ def test_rrtmil_unsupported_options_raise():
 def load_mil_train(name, dtype=torch.float64):
     c = MIL_TRAIN[name]
     cfg = O.EncoderConfig(**c["config"])
-    w = O.make_mil_weights(cfg, c["input_dim"], c["n_classes"], c["weight_seed"], da_bias=c["da_bias"], dtype=dtype)
+    w = O.make_mil_weights(cfg, c["input_dim"], c["n_classes"], c["weight_seed"], da_bias=c["da_bias"], dtype=dtype,
+                           **{k: v for k, v in _head_kw(c).items() if k in ("da_gated", "da_dropout")})
     x = O.make_bag(c["L"], c["input_dim"], c["bag_seed"], dtype=dtype)
     gold = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
     return c, cfg, w, x, gold
@@ -90,8 +96,10 @@ def test_oracle_mil_train_step_matches_reference_autograd(name):
     the reference produced with the same masks installed."""
     c, cfg, w, x, gold = load_mil_train(name)
     w = {k: v.clone().requires_grad_() for k, v in w.items()}
-    logits, _ = O.mil_forward(x, w, cfg, "relu", c["da_act"], "spec",
-                              drop=(c["dropout"], c["seed"], c["trans_dropout"], c["seed"] + 1))
+    kw = _head_kw(c)
+    logits, _ = O.mil_forward(x, w, cfg, kw.get("act", "relu"), c["da_act"], "spec",
+                              drop=(c["dropout"], c["seed"], c["trans_dropout"], c["seed"] + 1),
+                              pool_drop=(0.25, c["seed"]) if kw.get("da_dropout") else None)
     loss = torch.nn.functional.cross_entropy(logits[None], torch.tensor([c["label"]]))
     loss.backward()
     assert np.abs(logits.detach().numpy() - gold["logits"]).max() < 1e-9 and abs(float(loss) - float(gold["loss"])) < 1e-9
@@ -112,8 +120,9 @@ def test_cuda_rrtmil_train_step_matches_reference_fixture(name):
     c, cfg, w, x, gold = load_mil_train(name)
     kw = {k: v for k, v in c["config"].items() if k in ("region_num", "n_layers", "epeg_k", "crmsa_k",
                                                           "all_shortcut", "crmsa_heads")}
+    hk = _head_kw(c)
     m = RRTMIL(input_dim=c["input_dim"], n_classes=c["n_classes"], da_act=c["da_act"], da_bias=c["da_bias"],
-               dropout=c["dropout"], trans_dropout=c["trans_dropout"], **kw).cuda().train()
+               dropout=c["dropout"], trans_dropout=c["trans_dropout"], **kw, **hk).cuda().train()
     m.load_state_dict({k: v.float() for k, v in w.items()}, strict=True)
     m._dropout_seed, m.online_encoder._dropout_seed = c["seed"], c["seed"] + 1
     logits = m(x.float().cuda().unsqueeze(0))
@@ -136,7 +145,8 @@ def test_cuda_rrtmil_train_step_matches_reference_fixture(name):
     # eval mode still runs the inference kernels and ignores both dropouts
     with torch.no_grad():
         le = m.eval()(x.float().cuda().unsqueeze(0))
-    ref_eval, _ = O.mil_forward(x, {k: v for k, v in load_mil_train(name)[2].items()}, cfg, "relu", c["da_act"], "spec")
+    ref_eval, _ = O.mil_forward(x, {k: v for k, v in load_mil_train(name)[2].items()}, cfg, hk.get("act", "relu"),
+                                c["da_act"], "spec")
     assert np.abs(le[0].cpu().numpy() - ref_eval.numpy()).max() <= TOL * max(1.0, float(ref_eval.abs().max()))
 
 
@@ -148,7 +158,7 @@ def test_cuda_rrtmil_matches_golden(name):
     kw = {k: v for k, v in c["config"].items() if k in ("region_num", "n_layers", "epeg_k", "crmsa_k",
                                                           "all_shortcut", "crmsa_heads", "crmsa_mlp")}
     m = RRTMIL(input_dim=c["input_dim"], n_classes=c["n_classes"], act=c["act"], da_act=c["da_act"],
-               da_bias=c["da_bias"], **kw).cuda().eval()
+               da_bias=c["da_bias"], **kw, **_head_kw(c)).cuda().eval()
     m.load_state_dict({k: v.float() for k, v in w.items()}, strict=True)
     with torch.no_grad():
         logits, attn = m(x.float().cuda().unsqueeze(0), return_attn=True)
@@ -185,19 +195,23 @@ def test_cuda_patch_embed_matches_fp64(L, din, act):
     xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
     code = {"none": 0, "relu": 1, "gelu": 2}[act]
     cabi.check(lib.rrt_patch_embed_forward(xd.data_ptr(), L, din, 512, wd.data_ptr(), bd.data_ptr(), None, code,
-                                           out.data_ptr(), ws.data_ptr(), n.value, 0.0, 0,
+                                           out.data_ptr(), ws.data_ptr(), n.value, 0.0, 0, None,
                                            torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert O.rel_err(out.cpu(), ref) < TOL
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("L,da_act,bias,ncls", [(800, "relu", False, 2), (600, "tanh", True, 3), (65, "relu", True, 4),
-                                                (9000, "relu", False, 2)])
-def test_cuda_attn_pool_backward_matches_fp64_autograd(L, da_act, bias, ncls):
-    """The pooling head + predictor backward alone vs torch autograd in fp64.
+@pytest.mark.parametrize("L,da_act,bias,ncls,gated,dadrop", [
+    (800, "relu", False, 2, False, False), (600, "tanh", True, 3, False, False), (65, "relu", True, 4, False, False),
+    (9000, "relu", False, 2, False, False),
+    (700, "gelu", True, 2, False, False), (500, "relu", False, 2, False, True), (640, "tanh", True, 3, False, True),
+    (900, "relu", False, 2, True, False), (450, "gelu", True, 3, True, True), (300, "tanh", True, 2, True, True)])
+def test_cuda_attn_pool_backward_matches_fp64_autograd(L, da_act, bias, ncls, gated, dadrop):
+    """The pooling head + predictor backward alone vs torch autograd in fp64: plain and gated head
+    (modules/datten.py:5-83), every activation, with and without the nn.Dropout inside the score MLP.
 
-    The reference evaluates the ReLU of the score MLP at the pre-activations the fp16-operand forward
+    The reference evaluates the activation of the score MLP at the pre-activations the fp16-operand forward
     actually produced (straight-through: value of the fp16-rounded product, gradient of the exact one):
     d/dz ReLU is a step function, and ~0.04 % of the pre-activations sit within the forward's rounding
     error of the kink; evaluated at the fp64 values instead, those flips alone are 0.5-2 % of the gradient
@@ -208,48 +222,65 @@ def test_cuda_attn_pool_backward_matches_fp64_autograd(L, da_act, bias, ncls):
     from rrt_mil_b200.mil import _AttnPoolFunction
     g = torch.Generator().manual_seed(L)
     h = torch.randn(L, 512, generator=g, dtype=torch.float64)
-    m = RRTMIL(input_dim=512, n_classes=ncls, da_act=da_act, da_bias=bias).cuda()
-    att = m.pool_fn.attention
-    a0, a2, pred = att.attention[0], att.attention[-1], m.predictor
+    m = RRTMIL(input_dim=512, n_classes=ncls, da_act=da_act, da_bias=bias, da_gated=gated, da_dropout=dadrop).cuda()
+    m.train(dadrop)
+    seed = 4242
+    m._dropout_seed = seed
+    firsts, score, _ = m.pool_fn.attention.head_params()
+    pred = m.predictor
+    lins = firsts + [score, pred]
     with torch.no_grad():
-        for p in (a0.weight, a2.weight, pred.weight):
-            p.copy_(torch.randn(p.shape, generator=g) * (2.0 / sum(p.shape)) ** 0.5)
-        for p in (a0.bias, a2.bias, pred.bias):
-            if p is not None:
-                p.copy_(0.1 * torch.randn(p.shape, generator=g))
-    ps = [a0.weight, a0.bias, a2.weight, a2.bias, pred.weight, pred.bias]
-    r = [None if p is None else p.detach().double().cpu().requires_grad_() for p in ps]
+        for l in lins:
+            l.weight.copy_(torch.randn(l.weight.shape, generator=g) * (2.0 / sum(l.weight.shape)) ** 0.5)
+            if l.bias is not None:
+                l.bias.copy_(0.1 * torch.randn(l.bias.shape, generator=g))
+    dbl = lambda t: None if t is None else t.detach().double().cpu().requires_grad_()
+    rw, rb = [dbl(l.weight) for l in lins], [dbl(l.bias) for l in lins]
     hr = h.clone().requires_grad_()
-    act = torch.relu if da_act == "relu" else torch.tanh
-    pre = F.linear(hr, r[0])
-    pre = pre + (F.linear(h.half().double(), r[0].detach().half().double()) - pre).detach()
-    if r[1] is not None:
-        pre = pre + r[1]
-    sc = F.linear(act(pre), r[2], r[3]).squeeze(-1)
-    logits_ref = F.linear(torch.softmax(sc, 0) @ hr, r[4], r[5])
+
+    def first_layer(i):   # value of the fp16-operand product, gradient of the exact one
+        pre = F.linear(hr, rw[i])
+        pre = pre + (F.linear(h.half().double(), rw[i].detach().half().double()) - pre).detach()
+        return pre if rb[i] is None else pre + rb[i]
+
+    hid = O._act(da_act)(first_layer(0))
+    N = 256 if gated else 128
+    mask = O.dropout_mask(L, N, 0.25, seed, O.DROP_STREAM_POOL) if dadrop else torch.ones(L, N, dtype=torch.float64)
+    hid = hid * mask[:, :128]
+    if gated:
+        hid = hid * (torch.sigmoid(first_layer(1)) * mask[:, 128:])
+    ns = len(firsts)
+    sc = F.linear(hid, rw[ns], rb[ns]).squeeze(-1)
+    logits_ref = F.linear(torch.softmax(sc, 0) @ hr, rw[ns + 1], rb[ns + 1])
     label = torch.tensor([ncls - 1])
     F.cross_entropy(logits_ref[None], label).backward()
     hd = h.float().cuda().requires_grad_()
-    logits = _AttnPoolFunction.apply(m, hd, a0.weight, a0.bias, a2.weight.view(-1), a2.bias, pred.weight, pred.bias)
+    gate = firsts[1] if gated else None
+    logits = _AttnPoolFunction.apply(m, hd, firsts[0].weight, firsts[0].bias, None if gate is None else gate.weight,
+                                     None if gate is None else gate.bias, score.weight.view(-1), score.bias,
+                                     pred.weight, pred.bias)
     F.cross_entropy(logits[None], label.cuda()).backward()
     torch.cuda.synchronize()
     assert float((logits.detach().cpu().double() - logits_ref.detach()).abs().max()) < \
         2e-3 * max(1.0, float(logits_ref.abs().max()))
     errs = {"dh": O.rel_err(hd.grad.cpu(), hr.grad)}
-    for n, p, q in zip(["w1", "b1", "w2", "b2", "pw", "pb"], ps, r):
-        if p is None:
+    names = (["wa", "wb"] if gated else ["w1"]) + ["w2", "pw"]
+    for n, l, qw, qb in zip(names, lins, rw, rb):
+        errs[n] = O.rel_err(l.weight.grad.cpu(), qw.grad)
+        if l.bias is None:
             continue
-        if n == "b2":   # softmax is shift invariant: d loss / d b2 == 0 exactly; only rounding noise may remain
-            assert float(p.grad.abs().max()) <= 1e-4 * float(a2.weight.grad.abs().max())
+        if n == "w2":   # softmax is shift invariant: d loss / d b2 == 0 exactly; only rounding noise may remain
+            assert float(l.bias.grad.abs().max()) <= 1e-4 * float(l.weight.grad.abs().max())
             continue
-        errs[n] = O.rel_err(p.grad.cpu(), q.grad)
-    print(L, da_act, errs)
+        errs[n + ".b"] = O.rel_err(l.bias.grad.cpu(), qb.grad)
+    print(L, da_act, gated, dadrop, errs)
     for n, e in errs.items():
         assert e < 2e-3, (n, e, errs)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("L,din,act,p", [(800, 1024, "relu", 0.25), (333, 512, "relu", 0.0), (500, 512, "none", 0.25)])
+@pytest.mark.parametrize("L,din,act,p", [(800, 1024, "relu", 0.25), (333, 512, "relu", 0.0), (500, 512, "none", 0.25),
+                                         (700, 512, "gelu", 0.25), (260, 1024, "gelu", 0.0)])
 def test_cuda_patch_embed_backward_matches_fp64(L, din, act, p):
     """patch_to_emb + dp backward alone: dW, db vs fp64 (the mask of the forward regenerated / read off
     the output), and the training forward itself (dropout applied) vs the oracle with the same mask."""
@@ -263,20 +294,26 @@ def test_cuda_patch_embed_backward_matches_fp64(L, din, act, p):
     seed = 1234
     mask = O.dropout_mask(L, 512, p, seed, O.DROP_STREAM_PATCH)
     z = x.double() @ w.double().T + b.double()
-    out_ref = (torch.relu(z) if act == "relu" else z) * mask
+    out_ref = O._act(act)(z) * mask
     lib, st = cabi.lib(), torch.cuda.current_stream().cuda_stream
     n = C.c_size_t()
     cabi.check(lib.rrt_mil_head_workspace_bytes(L, din, 512, 128, C.byref(n)))
     tape = torch.empty(n.value, dtype=torch.uint8, device="cuda")
     out = torch.empty(L, 512, device="cuda")
     xd, wd, bd, dd = x.cuda(), w.cuda(), b.cuda(), dout.cuda()
-    code = {"none": 0, "relu": 1}[act]
+    code = {"none": 0, "relu": 1, "gelu": 2}[act]
+    pre = torch.empty(L, 512, device="cuda") if act == "gelu" else None
+    pre_p = None if pre is None else pre.data_ptr()
     cabi.check(lib.rrt_patch_embed_forward(xd.data_ptr(), L, din, 512, wd.data_ptr(), bd.data_ptr(), None, code,
-                                           out.data_ptr(), tape.data_ptr(), n.value, p, seed, st))
+                                           out.data_ptr(), tape.data_ptr(), n.value, p, seed, pre_p, st))
     dw, db = torch.empty_like(wd), torch.empty_like(bd)
     nws = 512 + L * 512 * 2 + 256
     ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
-    cabi.check(lib.rrt_patch_embed_backward(dd.data_ptr(), out.data_ptr(), L, din, 512, code, p, seed, tape.data_ptr(),
+    if act == "gelu":   # without the forward's pre-activations the backward refuses
+        assert lib.rrt_patch_embed_backward(dd.data_ptr(), out.data_ptr(), None, L, din, 512, code, p, seed,
+                                            tape.data_ptr(), n.value, dw.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                            nws, st) == cabi.RRT_E_INVALID
+    cabi.check(lib.rrt_patch_embed_backward(dd.data_ptr(), out.data_ptr(), pre_p, L, din, 512, code, p, seed, tape.data_ptr(),
                                             n.value, dw.data_ptr(), db.data_ptr(), ws.data_ptr(), nws, st))
     torch.cuda.synchronize()
     assert O.rel_err(out.cpu(), out_ref) < TOL
@@ -284,5 +321,10 @@ def test_cuda_patch_embed_backward_matches_fp64(L, din, act, p):
     # fp16-operand forward puts ~0.04 % of the pre-activations on the other side of it than fp64 does (9e-3 of
     # the gradient norm), so the reference takes the kept / dropped pattern from the GPU's own output
     keep = (out.cpu().double() != 0).double() / (1.0 - p) if act == "relu" else mask
+    if act == "gelu":   # smooth: the derivative at the fp64 pre-activations is the reference
+        assert O.rel_err(pre.cpu(), z) < TOL
+        zr = z.clone().requires_grad_()
+        torch.nn.functional.gelu(zr).sum().backward()
+        keep = mask * zr.grad
     dz = dout.double() * keep
     assert O.rel_err(dw.cpu(), dz.T @ x.double()) < 2e-3 and O.rel_err(db.cpu(), dz.sum(0)) < 2e-3
