@@ -199,6 +199,7 @@ struct Workspace {
   float* xs[RRT_MAX_RMSA_LAYERS];    // [L, D] output of layer i (residual stream)
   __half* zc;      // [Np_c, D] CR-MSA LN output (crmsa_mlp only)
   float2* stats;   // [Np_c]
+  float* rs_part;  // [L, D/128, 8] row partials the last projection GEMM leaves for CR-MSA (row_stats_fused)
   float* logits;   // [Np_c, k]
   float2* rstat;   // [R_c, k]
   __half* lm;      // [k*R_c, D]
@@ -265,6 +266,7 @@ bool carve(const rrt_config* c, int64_t L, void* base, Workspace* ws, bool train
     ws->zc = z;
   }
   ws->stats = (float2*)take(np_c * 8);
+  ws->rs_part = (float*)take(c->cr_msa ? (size_t)L * (D / 128 + 1) * 32 : 0);
   ws->logits = (float*)take(np_c * k * 4);
   ws->rstat = (float2*)take(64 * k * 8);
   ws->lm = (__half*)take(T * D * 2);
@@ -315,9 +317,28 @@ int f16_weight(const float* w32, const void* shadow, __half* scratch, size_t n, 
 struct TrainOpts { float drop_p = 0.f; unsigned long long seed = 0; bool tape = false; };
 constexpr unsigned kCrDropStream = 64;
 
+// CR-MSA reads the rows the LAST R-MSA projection GEMM writes: when nothing sits in between (no FFN, no
+// positional encoding after that layer), the GEMM's epilogue leaves per-row partial sums (LayerNorm statistics
+// and the k <= 4 logit dot products) and the CR-MSA front starts from them instead of re-reading x1
+// (crmsa_rowstats_kernel disappears: one launch and one 4*L*D-byte pass less).  Returns the number of
+// 128-column parts per row, 0 = not fused.  RRT_CRMSA_ROWSTATS=kernel forces the separate kernel.
+int row_stats_fused(const rrt_config* c, const rrt_weights* w, int64_t L) {
+  static const bool off = [] { const char* e = getenv("RRT_CRMSA_ROWSTATS"); return e && !strcmp(e, "kernel"); }();
+  static const bool front_split = [] { const char* e = getenv("RRT_CRMSA_FRONT"); return !e || !strcmp(e, "split"); }();
+  if (off || !front_split || !c->cr_msa || c->crmsa_mlp || c->ffn || c->n_rmsa_layers < 1 || c->crmsa_k > 4 ||
+      !w->cr_phi || c->dim % 128)
+    return 0;
+  const int V = c->dim / 128;
+  if (V != 1 && V != 2 && V != 4 && V != 8) return 0;
+  rrt::Grid g{};
+  if (!make_grid(L, c->region_num, c->region_size, c->min_region_num, c->min_region_ratio, &g)) return 0;
+  return rrt::gemm_tcgen05_rowstat_parts(g.Np, c->dim);
+}
+
 int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
                const rrt_attn_weights* a, const float* x, float* x1, int64_t L, Workspace& ws,
-               cudaStream_t st, int layer = 0, const TrainOpts& tr = TrainOpts{}) {
+               cudaStream_t st, int layer = 0, const TrainOpts& tr = TrainOpts{},
+               const rrt_weights* rs_w = nullptr) {
   __half* const ws_z = ws.z[layer];
   __half* const ws_qkv = ws.qkv[layer];
   __half* const ws_o = ws.o[layer];
@@ -355,6 +376,12 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
   e2.bias = a->proj_b;
   e2.resid = x;
   e2.grid = g;
+  if (rs_w) {  // row partials for the CR-MSA block that follows (row_stats_fused)
+    e2.rs_part = ws.rs_part;
+    e2.rs_gamma = rs_w->cr_norm_w;
+    e2.rs_phi = rs_w->cr_phi;
+    e2.rs_k = c->crmsa_k;
+  }
   { StageScope s_(kStProjGemm, st);
     if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws_o, wp, x1, false, g.Np, D, D, e2, st), "proj gemm"); }
   return RRT_OK;
@@ -362,7 +389,7 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
 
 int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, const float* x0,
                 float* out, int64_t L, bool final_norm, Workspace& ws, cudaStream_t st,
-                const TrainOpts& tr = TrainOpts{}) {
+                const TrainOpts& tr = TrainOpts{}, int rs_parts = 0) {
   rrt::Grid g{};
   if (!crmsa_grid(L, &g)) return fail(RRT_E_INVALID, "bad geometry");
   const int D = c->dim, k = c->crmsa_k, T = k * g.R;
@@ -398,10 +425,11 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   }();
   bool front_done = false;
   if (front_mode == 0) {
-    StageScope s_(kStCrCombine, st, 2);
+    StageScope s_(kStCrCombine, st, rs_parts ? 1 : 2);
     cudaError_t e = s_.skip() ? cudaSuccess
                               : rrt::launch_crmsa_front_split(x1, w->cr_norm_w, w->cr_norm_b, phi, ws.stats,
-                                                              ws.logits, ws.lm, ws.rstat, g, D, k, st);
+                                                              ws.logits, ws.lm, ws.rstat, g, D, k, st,
+                                                              rs_parts ? ws.rs_part : nullptr, rs_parts);
     if (e == cudaSuccess) front_done = true;
     else if (e != cudaErrorNotSupported) return fail_cuda(e, "crmsa front (split)");
   }
@@ -507,6 +535,7 @@ int encoder_forward(const rrt_config* cfg, const rrt_weights* w, const float* x,
     int rc = pos_embed();
     if (rc) return rc;
   }
+  const int rs_parts = row_stats_fused(cfg, w, L);
   for (int i = 0; i < cfg->n_rmsa_layers; ++i) {
     if (i == 1 && cfg->pos != RRT_POS_NONE && cfg->pos_pos == 0) {
       int rc = pos_embed();
@@ -514,7 +543,7 @@ int encoder_forward(const rrt_config* cfg, const rrt_weights* w, const float* x,
     }
     float* nxt = ws.xs[i];
     int rc = rmsa_block(cfg, w->layer_norm_w[i], w->layer_norm_b[i], &w->layer_attn[i], cur, nxt, L,
-                        ws, st, i, tr);
+                        ws, st, i, tr, (rs_parts && i == cfg->n_rmsa_layers - 1) ? w : nullptr);
     if (rc) return rc;
     cur = nxt;
     if (cfg->ffn) {
@@ -535,7 +564,7 @@ int encoder_forward(const rrt_config* cfg, const rrt_weights* w, const float* x,
     RRT_CUDA(rrt::launch_add_layernorm(ws.ffn_out2, x0, w->norm_w, w->norm_b, out, (int)L, D, st), "final norm");
     return RRT_OK;
   }
-  if (cfg->cr_msa) return crmsa_block(cfg, w, cur, x0, out, L, true, ws, st, tr);
+  if (cfg->cr_msa) return crmsa_block(cfg, w, cur, x0, out, L, true, ws, st, tr, rs_parts);
   { StageScope s_(kStFinalLn, st); RRT_CUDA(rrt::launch_add_layernorm(cur, x0, w->norm_w, w->norm_b, out, (int)L, D, st), "final norm"); }
   return RRT_OK;
 }

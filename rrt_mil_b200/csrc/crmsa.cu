@@ -318,27 +318,81 @@ __global__ void __launch_bounds__(256) crmsa_rowstats_kernel(
 }
 
 // grid (D/128, R), 256 threads.  smem: wq[P][KMAX] | tok[P] | part[8][KMAX][128] | s01[2][KMAX]
-template <int KMAX>
+// FROM_PARTS: the statistics and logits do not exist yet; the projection GEMM that wrote x1 left, per token and
+// 128-column part, [sum x, sum x^2, sum_c x_c gamma_c phi[c,n]] (GemmEpilogue::rs_part).  Every CTA of a region
+// finishes mean / rstd / logits of its rows from those records (chunk 0 also publishes them in stats_out /
+// logits_out for the dispatch kernel), so x1 is read once by the CR-MSA front instead of twice.
+template <int KMAX, bool FROM_PARTS>
 __global__ void __launch_bounds__(256) crmsa_combine2_kernel(
     const float* __restrict__ x1, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float2* __restrict__ stats, const float* __restrict__ logits, __half* __restrict__ landmarks,
-    float2* __restrict__ rstat, Grid grid, int D, int k) {
+    float2* __restrict__ rstat, Grid grid, int D, int k, const float* __restrict__ rs_part, int rs_parts,
+    const float* __restrict__ phi, float2* __restrict__ stats_out, float* __restrict__ logits_out) {
   extern __shared__ __align__(16) float smem[];
   const int P = grid.P, rho = blockIdx.y, chunk = blockIdx.x;
   float* wq = smem;                                          // [P][KMAX]: logits -> cw*rstd
   int* tok = reinterpret_cast<int*>(wq + (size_t)P * KMAX);  // [P]
   float* part = reinterpret_cast<float*>(tok + ((P + 3) & ~3));  // [8][KMAX][128]
   float* s01 = part + 8 * KMAX * 128;                        // [2][KMAX]: S0, S1
+  float2* sst = reinterpret_cast<float2*>(s01 + 2 * KMAX);   // [P] (mean, rstd); rstd = 0 marks a pad slot
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();
+  if (FROM_PARTS) {
+    // weights only (runs ahead of the predecessor): A[n] = sum_c gamma_c phi[c,n], B[n] = sum_c beta_c phi[c,n],
+    // parked in s01 until the softmax below overwrites it
+    for (int n = warp; n < k; n += 8) {
+      float a = 0.f, b = 0.f;
+      for (int c = lane; c < D; c += 32) {
+        const float ph = __ldg(phi + (size_t)c * k + n);
+        a = fmaf(__ldg(gamma + c), ph, a);
+        b = fmaf(__ldg(beta + c), ph, b);
+      }
+      a = warp_sum(a);
+      b = warp_sum(b);
+      if (lane == 0) { s01[n] = a; s01[KMAX + n] = b; }
+    }
+    __syncthreads();
+  }
   pdl_wait();
 
   for (int p = tid; p < P; p += 256) {
     int slot = rho * P + p;
-    float2 st = __ldg(stats + slot);
-    tok[p] = st.y != 0.f ? grid.slot_to_token(slot) : -1;
+    if (FROM_PARTS) {
+      const int t = grid.slot_to_token(slot);
+      float2 st = make_float2(0.f, 0.f);
+      float lg[KMAX];
 #pragma unroll
-    for (int n = 0; n < KMAX; ++n) wq[p * KMAX + n] = n < k ? __ldg(logits + (size_t)slot * k + n) : 0.f;
+      for (int n = 0; n < KMAX; ++n) lg[n] = 0.f;
+      if (t < grid.L) {
+        float sum = 0.f, sq = 0.f, dot[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int q = 0; q < rs_parts; ++q) {
+          const float4* rec = reinterpret_cast<const float4*>(rs_part + ((size_t)t * rs_parts + q) * 8);
+          const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+          sum += r0.x; sq += r0.y;
+          dot[0] += r0.z; dot[1] += r0.w; dot[2] += r1.x; dot[3] += r1.y;
+        }
+        const float mean = sum / D;
+        const float var = fmaxf(sq / D - mean * mean, 0.f);
+        st = make_float2(mean, rsqrtf(var + kLnEps));
+#pragma unroll
+        for (int n = 0; n < KMAX; ++n)
+          if (n < k && n < 4) lg[n] = st.y * (dot[n] - mean * s01[n]) + s01[KMAX + n];
+      }
+      sst[p] = st;
+      tok[p] = t < grid.L ? t : -1;
+#pragma unroll
+      for (int n = 0; n < KMAX; ++n) wq[p * KMAX + n] = lg[n];
+      if (chunk == 0) {
+        stats_out[slot] = st;
+        for (int n = 0; n < k; ++n) logits_out[(size_t)slot * k + n] = lg[n];
+      }
+    } else {
+      float2 st = __ldg(stats + slot);
+      sst[p] = st;
+      tok[p] = st.y != 0.f ? grid.slot_to_token(slot) : -1;
+#pragma unroll
+      for (int n = 0; n < KMAX; ++n) wq[p * KMAX + n] = n < k ? __ldg(logits + (size_t)slot * k + n) : 0.f;
+    }
   }
   __syncthreads();
   // per landmark: softmax over the region, min, max; then w' = cw * rstd, S0, S1
@@ -357,7 +411,7 @@ __global__ void __launch_bounds__(256) crmsa_combine2_kernel(
     float s0 = 0.f, s1 = 0.f;
     for (int p = lane; p < P; p += 32) {
       float cw = __expf(wq[p * KMAX + n] - mx) * inv;
-      float2 st = __ldg(stats + rho * P + p);
+      float2 st = sst[p];
       float w = cw * st.y;  // rstd = 0 for pad rows: they contribute nothing
       wq[p * KMAX + n] = w;
       if (st.y != 0.f) s0 += cw;
@@ -941,12 +995,13 @@ cudaError_t launch_crmsa_landmarks(const float* x1, const float* gamma, const fl
 cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const float* beta,
                                      const float* phi, float2* stats, float* logits,
                                      __half* landmarks, float2* rstat, const Grid& grid, int D, int k,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, const float* rs_part, int rs_parts) {
   if (D % 128 || k < 1 || k > RRT_MAX_K_DEV) return cudaErrorInvalidValue;
   const int V = D / 128;
   if (V != 1 && V != 2 && V != 4 && V != 8) return cudaErrorNotSupported;
   const int KM = k <= 4 ? 4 : (k <= 8 ? 8 : 16);
-  {
+  if (rs_part && (k > 4 || !phi || rs_parts < 1)) return cudaErrorInvalidValue;
+  if (!rs_part) {
     size_t smem = ((size_t)KM * D + 2 * KM) * sizeof(float);
     int blocks = (grid.Np + 15) / 16;
     if (blocks > 148 * 4) blocks = 148 * 4;
@@ -976,23 +1031,26 @@ cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const 
     if (e != cudaSuccess) return e;
   }
   {
-    size_t smem = ((size_t)grid.P * KM + ((grid.P + 3) & ~3) + (size_t)8 * KM * 128 + 2 * KM) * sizeof(float);
+    size_t smem = ((size_t)grid.P * KM + ((grid.P + 3) & ~3) + (size_t)8 * KM * 128 + 2 * KM + 2 * (size_t)grid.P) *
+                  sizeof(float);
     if (smem > 227 * 1024) return cudaErrorNotSupported;
     dim3 g(D / 128, grid.R);
-#define RRT_C2(KK)                                                                                 \
+#define RRT_C2(KK, FP)                                                                             \
   {                                                                                                \
     static DeviceOnce configured;                                                                \
     if (configured.needed()) {                                                                             \
-      cudaError_t e = cudaFuncSetAttribute(crmsa_combine2_kernel<KK>,                              \
+      cudaError_t e = cudaFuncSetAttribute(crmsa_combine2_kernel<KK, FP>,                          \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
       if (e != cudaSuccess) return e;                                                              \
     }                                                                                              \
-    prefer_max_shared(crmsa_combine2_kernel<KK>);                                                  \
-    cudaError_t le = launch_chain_kernel(crmsa_combine2_kernel<KK>, g, dim3(256), smem, stream, x1, gamma, beta, \
-                                         stats, logits, landmarks, rstat, grid, D, k);             \
+    prefer_max_shared(crmsa_combine2_kernel<KK, FP>);                                              \
+    cudaError_t le = launch_chain_kernel(crmsa_combine2_kernel<KK, FP>, g, dim3(256), smem, stream, x1, gamma, beta, \
+                                         (const float2*)stats, (const float*)logits, landmarks, rstat, grid, D, k, \
+                                         rs_part, rs_parts, phi, stats, logits);                   \
     if (le != cudaSuccess) return le;                                                              \
   }
-    if (KM == 4) RRT_C2(4) else if (KM == 8) RRT_C2(8) else RRT_C2(16)
+    if (rs_part) RRT_C2(4, true)
+    else if (KM == 4) RRT_C2(4, false) else if (KM == 8) RRT_C2(8, false) else RRT_C2(16, false)
 #undef RRT_C2
   }
   return cudaGetLastError();

@@ -55,6 +55,12 @@ struct Tc05Params {
   Grid grid;
   int act;           // GemmActivation, store mode only
   int act2, act_split;  // columns >= act_split (multiple of 32, 0 = none) use act2
+  // residual modes, optional: per-row partial LayerNorm / CR-MSA logit sums of the rows this GEMM writes
+  // (GemmEpilogue::rs_part); rs_gamma [N], rs_phi [N, rs_k]
+  float* rs_part;
+  const float* rs_gamma;
+  const float* rs_phi;
+  int rs_k;
   Dropout drop;      // kEpiResidualUnpartDrop only
   int ksplit;        // >= 1: the K loop of every tile is cut into ksplit work items (kEpiAtomicAdd)
   long long* trace;  // debug: per-CTA clock64 stamps (tools/gemm_trace.py), null in production
@@ -178,6 +184,10 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
     const uint32_t t_addr = tmem_acc + ((uint32_t)(quad * 32) << 16) + c_begin * 32;
     uint32_t r[2][32];
     tmem_ld_32x32(t_addr, r[0]);
+    // row statistics of the rows being written (thread = row `lane` of this warp's 32): sum, sum of squares
+    // and up to four dot products with gamma (.) phi[:, n] over this warp's NC * 32 columns
+    float rs_sum = 0.f, rs_sq = 0.f, rs_dot[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool row_stats = is_resid_mode(MODE) && p.rs_part != nullptr;
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
       tmem_ld_wait();  // chunk j is in registers
@@ -269,13 +279,61 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
           else store_out4(out, (size_t)orow[i] * p.N + gc, v[i]);
         }
       if (first && threadIdx.x == 128 && j < 2) stamp(p, 12 + 3 * j);
+      if (is_resid_mode(MODE) && row_stats) {
+        // hand the finished values back through the scratch tile (same swizzled slots they were read from)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + sub_r;
+          *reinterpret_cast<float4*>(scratch + rl * EPI_LD + 4 * ((lane & 7) ^ (rl & 7))) = v[i];
+        }
+        __syncwarp();
+      }
       if (is_resid_mode(MODE) && j + 1 < NC) load_resid(j + 1);  // next chunk's residual rows
+      if (is_resid_mode(MODE) && row_stats) {
+        // lane c keeps gamma_c * phi[c, 0..3] of column c of this chunk; the row pass broadcasts them by shuffle
+        const int gcl = n0 + (c_begin + j) * 32 + lane;
+        const float gm = __ldg(p.rs_gamma + gcl);
+        float gq[4];
+        if (p.rs_k == 4) {
+          const float4 ph = __ldg(reinterpret_cast<const float4*>(p.rs_phi) + gcl);
+          gq[0] = gm * ph.x; gq[1] = gm * ph.y; gq[2] = gm * ph.z; gq[3] = gm * ph.w;
+        } else {
+#pragma unroll
+          for (int n = 0; n < 4; ++n) gq[n] = n < p.rs_k ? gm * __ldg(p.rs_phi + (size_t)gcl * p.rs_k + n) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 xv = *reinterpret_cast<const float4*>(scratch + lane * EPI_LD + 4 * (q ^ (lane & 7)));
+          rs_sum += (xv.x + xv.y) + (xv.z + xv.w);
+          rs_sq = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, fmaf(xv.z, xv.z, fmaf(xv.w, xv.w, rs_sq))));
+          const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+              rs_dot[n] = fmaf(xe[e], __shfl_sync(0xffffffffu, gq[n], 4 * q + e), rs_dot[n]);
+        }
+      }
       __syncwarp();
       }  // !kTmaStore
     }
     if (kTmaStore) {  // both staging buffers are free again before the next tile reuses them
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();
+    }
+    if (is_resid_mode(MODE) && row_stats) {
+      // one 32-byte record per (token, 128-column part): [sum, sum sq, dot_0..3, -, -]
+      const int gr = m0 + quad * 32 + lane;
+      if (gr < p.M) {
+        const int tok = p.grid.slot_to_token(gr);
+        if (tok < p.grid.L) {
+          constexpr int PW = NC * 32;  // columns per part
+          const int parts = p.N / PW, part = (n0 + c_begin * 32) / PW;
+          float4* rec = reinterpret_cast<float4*>(p.rs_part + ((size_t)tok * parts + part) * 8);
+          rec[0] = make_float4(rs_sum, rs_sq, rs_dot[0], rs_dot[1]);
+          rec[1] = make_float4(rs_dot[2], rs_dot[3], 0.f, 0.f);
+        }
+      }
     }
 }
 
@@ -870,6 +928,18 @@ cudaError_t launch_pair(const __half* a, const __half* w, const Tc05Params& p, c
   return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p);
 }
 
+}  // namespace
+// Row-statistics side output of the residual epilogue: number of 128-column parts per row, or 0 when the
+// launch below would not pick a 256-column tile for this problem (the part width is half a tile).
+// Must mirror launch_mode().
+int gemm_tcgen05_rowstat_parts(int M, int N) {
+  const int tiles_m = (M + BM - 1) / BM, tiles_n256 = (N + 255) / 256;
+  if (tiles_m * tiles_n256 < sm_count() / 2) return 0;                               // BN = 64
+  if (g_gemm_narrow && tiles_m * tiles_n256 <= sm_count() && N % 128 == 0) return 0;  // BN = 128
+  if (N % 128) return 0;
+  return N / 128;
+}
+namespace {
 template <int MODE, typename OutT>
 cudaError_t launch_mode(const __half* a, const __half* w, const Tc05Params& p, cudaStream_t stream) {
   // small problems: narrower tiles so that more SMs share the (latency-bound) work
@@ -903,6 +973,7 @@ cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float
   p.act = kActNone;
   p.act2 = kActNone;
   p.act_split = 0;
+  p.rs_part = nullptr; p.rs_gamma = nullptr; p.rs_phi = nullptr; p.rs_k = 0;
   p.trace = nullptr;
   const int tiles = ((C_out + BM - 1) / BM) * ((C_in + BN - 1) / BN), KB = (rows + BK - 1) / BK;
   int ksplit = sm_count() / tiles;
@@ -945,6 +1016,13 @@ cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool 
   p.act2 = epi.act2;
   p.act_split = epi.act_split;
   if (p.act_split % 32 || p.act_split < 0) return cudaErrorInvalidValue;
+  p.rs_part = nullptr; p.rs_gamma = nullptr; p.rs_phi = nullptr; p.rs_k = 0;
+  if (epi.rs_part) {
+    if (!is_resid_mode(epi.mode) || !epi.rs_gamma || !epi.rs_phi || epi.rs_k < 1 || epi.rs_k > 4 ||
+        gemm_tcgen05_rowstat_parts(M, N) == 0)
+      return cudaErrorInvalidValue;
+    p.rs_part = epi.rs_part; p.rs_gamma = epi.rs_gamma; p.rs_phi = epi.rs_phi; p.rs_k = epi.rs_k;
+  }
   p.trace = g_gemm_trace ? g_gemm_trace + (size_t)(g_trace_launch++ % 8) * 128 : nullptr;
   p.drop = epi.drop;
   p.ksplit = 1;

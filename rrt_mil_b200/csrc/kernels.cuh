@@ -41,7 +41,16 @@ struct GemmEpilogue {
   const float* resid = nullptr;  // [L, N] (mode 2)
   Grid grid{};                   // (mode 2)
   Dropout drop{};                // (mode 4) mask index = token * N + n
+  // residual modes, optional side output for the CR-MSA block that consumes the rows this GEMM writes:
+  // rs_part [L][N/128][8] receives, per token and 128-column part, sum x, sum x^2 and sum_c x_c gamma_c phi[c,n]
+  // (n < rs_k <= 4); crmsa finishes LayerNorm statistics and logits from them instead of re-reading the rows.
+  // Only when gemm_tcgen05_rowstat_parts(M, N) != 0.
+  float* rs_part = nullptr;
+  const float* rs_gamma = nullptr;  // [N]  cr_msa.norm.weight
+  const float* rs_phi = nullptr;    // [N, rs_k]
+  int rs_k = 0;
 };
+int gemm_tcgen05_rowstat_parts(int M, int N);
 
 // ---- gemm_tcgen05.cu ------------------------------------------------------------------
 // c[M,N] = a[M,K] @ w[N,K]^T (+epilogue) on tcgen05 + TMA + TMEM; fp16 operands, fp32 accumulate.
@@ -116,7 +125,7 @@ cudaError_t launch_crmsa_landmarks(const float* x1, const float* gamma, const fl
 cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const float* beta,
                                      const float* phi, float2* stats, float* logits,
                                      __half* landmarks, float2* rstat, const Grid& grid, int D, int k,
-                                     cudaStream_t stream);
+                                     cudaStream_t stream, const float* rs_part = nullptr, int rs_parts = 0);
 // MHA core over the landmarks: batch = k, sequence = R (64), heads, head_dim = D/heads, plain
 // softmax(q k^T * scale) v, fp32 math.  lqkv: [k*R, 3D] fp32 rows (n, rho); lo: [k*R, D] f16.
 cudaError_t launch_landmark_attention(const float* lqkv, __half* lo, int k, int R, int D, int heads,

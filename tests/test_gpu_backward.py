@@ -244,7 +244,7 @@ def test_training_dropout_is_reproducible_under_manual_seed():
 
 
 def test_backward_rejects_unsupported():
-    cfg = O.EncoderConfig(crmsa_mlp=True, crmsa_heads=1, crmsa_k=5)
+    cfg = O.EncoderConfig(pos="ppeg", pos_pos=-1)       # PEG / PPEG have no backward
     m = G.make_encoder(cfg, O.make_weights(cfg, 3))
     x = O.make_bag(200, 512, 4).float().cuda().requires_grad_()
     with pytest.raises(NotImplementedError):
