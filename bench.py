@@ -98,18 +98,29 @@ def stage_algorithmic(stage, L):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks/throttle reasons sampled every 50 ms.  The process is started BEFORE the warm-up steps
+    (its NVML start-up takes driver locks for ~100 ms and stalled the launches of the first timed steps when every
+    rank started one at the top of the timed region) and keeps sampling through the timed region; `mark()` sets
+    the window whose samples are summarised (falls back to every sample under load when the window is shorter
+    than a sampling period)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
+
+    def mark(self, start):
+        if start:
+            self.t0 = time.monotonic()
+        else:
+            self.t1 = time.monotonic()
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -119,11 +130,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.25)
+            time.sleep(0.06)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -133,7 +144,11 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1 + 0.05]
+        window = "timed region"
+        if not inside:      # region shorter than a sampling period: every sample since the warm-up started
+            inside, window = [r for _, r in self.rows], "warm-up + timed region"
+        for r in inside:
             if len(r) < 7:
                 continue
             try:
@@ -146,7 +161,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -334,20 +349,23 @@ def run_b200_arm(args):
             for _ in range(reps):
                 enc.forward_bags(bags, outs, lanes=args.lanes)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-
-    # ---- timed region: device-resident inputs -------------------------------------------------
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0 = cabi.launch_count()
-    barrier(); torch.cuda.synchronize()
     with ClockSampler(local) as clk:
+        time.sleep(0.3)                      # nvidia-smi is up and sampling before anything is timed
+        for _ in range(max(args.warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+
+        # ---- timed region: device-resident inputs -------------------------------------------------
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = cabi.launch_count()
+        barrier(); torch.cuda.synchronize()
+        clk.mark(True)
         e0.record()
         for _ in range(args.steps):
             step()
         e1.record()
         torch.cuda.synchronize()
+        clk.mark(False)
     barrier()
     launches = cabi.launch_count() - n0
     my_ms = e0.elapsed_time(e1)
@@ -582,6 +600,7 @@ def run_b200_arm(args):
         q1.record()
         torch.cuda.synchronize()
         t_ms = max_over_ranks(q0.elapsed_time(q1))
+        t_launches = (cabi.launch_count() - l0) // t_steps
         host = []
         for _ in range(5):   # host cost of ONE step enqueued into an empty queue (all ranks in step: collectives)
             torch.cuda.synchronize(); barrier()
@@ -593,7 +612,8 @@ def run_b200_arm(args):
         workloads["train_configs4"] = {
             "value": world * N_TOKENS * t_steps / (t_ms * 1e-3), "unit": UNIT, "us_per_step": t_ms / t_steps * 1e3,
             "bags_per_step": world, "host_enqueue_us_per_step": host_us,
-            "launches_per_step": (cabi.launch_count() - l0) // t_steps, "collectives_per_step": n_coll,
+            "launches_per_step": t_launches, "collectives_per_step": n_coll,
+            "collectives_in_place": (red.last_in_place if red is not None else 0),
             "gradient_bytes": sum(q.numel() for q in tm.parameters()) * 4, "final_loss": float(loss.detach()),
             "what": "RRTMIL(input_dim=1024, epeg_k=21, crmsa_k=5): forward + cross entropy + backward + gradient "
                     "all-reduce (3 buckets launched from autograd hooks, overlapping backward) + fused Adam; one "

@@ -83,6 +83,18 @@ def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+def _flat_views(shapes, device):
+    """Gradient tensors of one backward Function as views of ONE buffer (256-byte aligned pieces; ``None`` stays
+    ``None``): a data-parallel reducer can then all-reduce the whole group in place (parallel.GradReducer)."""
+    offs, total = [], 0
+    for shp in shapes:
+        offs.append(total)
+        if shp is not None:
+            total += (int(torch.Size(shp).numel()) + 63) // 64 * 64
+    flat = torch.empty(max(total, 1), dtype=torch.float32, device=device)
+    return [None if shp is None else flat[o:o + torch.Size(shp).numel()].view(shp) for o, shp in zip(offs, shapes)]
+
+
 class _PatchEmbedFunction(torch.autograd.Function):
     """h0 = dp(act(x W^T + b)) (modules/rrt.py:228-229); no gradient for the bag's features."""
 
@@ -115,8 +127,7 @@ class _PatchEmbedFunction(torch.autograd.Function):
         L, in_dim, dim = ctx.shape
         dout = dout.contiguous().float()
         with torch.cuda.device(dev):
-            dw = torch.empty_like(weight)
-            db = torch.empty_like(bias) if bias is not None else None
+            dw, db = _flat_views([weight.shape, None if bias is None else bias.shape], dev)
             nws = 512 + L * dim * 2 + 256
             ws = torch.empty(nws, dtype=torch.uint8, device=dev)
             cabi.check(lib.rrt_patch_embed_backward(dout.data_ptr(), out.data_ptr(), RRTMIL._p(pre), L, in_dim, dim,
@@ -168,10 +179,9 @@ class _AttnPoolFunction(torch.autograd.Function):
             cabi.check(lib.rrt_mil_head_backward_workspace_bytes(L, dim, n1, C.byref(n)), "workspace")
             ws = torch.empty(n.value, dtype=torch.uint8, device=dev)
             dh = torch.empty_like(h)
-            dw1, dw2, dpw = torch.empty_like(w1), torch.empty_like(w2), torch.empty_like(pw)
-            db1 = torch.empty(n1, device=dev) if ctx.has_b1 else None
-            db2 = torch.empty_like(b2) if b2 is not None else None
-            dpb = torch.empty_like(pb) if pb is not None else None
+            dw1, db1, dw2, db2, dpw, dpb = _flat_views(
+                [w1.shape, (n1,) if ctx.has_b1 else None, w2.shape, None if b2 is None else b2.shape, pw.shape,
+                 None if pb is None else pb.shape], dev)
             cabi.check(lib.rrt_attn_pool_backward(h.data_ptr(), L, dim, hid, w1.data_ptr(), ctx.act,
                                                   w2.data_ptr(), pw.data_ptr(), ncls, pooled.data_ptr(),
                                                   dlogits.data_ptr(), ctx.drop[0], ctx.drop[1], RRTMIL._p(pre),

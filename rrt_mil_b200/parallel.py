@@ -172,9 +172,10 @@ class GradReducer:
 
     ``groups`` is a list of parameter lists in the order their gradients become available during backward (for
     ``RRTMIL``: pooling head + predictor, encoder, ``patch_to_emb``).  A post-accumulate hook on every parameter
-    counts the group down; when the last gradient of a group has been written, the group is packed into one flat
-    bucket and its all-reduce is launched asynchronously -- the collective of the head runs under the encoder's
-    backward kernels, the encoder's under ``patch_to_emb``'s.  ``finish()`` (call it after ``loss.backward()``,
+    counts the group down; when the last gradient of a group has been written its all-reduce is launched
+    asynchronously -- IN PLACE on the buffer the group's gradients are views of (the library's backward Functions
+    allocate the gradients of one Function from one buffer), or on a packed copy when they are not -- so the
+    collective of the head runs under the encoder's backward kernels, the encoder's under ``patch_to_emb``'s.  ``finish()`` (call it after ``loss.backward()``,
     before the optimizer step) waits for the collectives, averages and scatters the buckets back into ``.grad``.
     Parameters that received no gradient in a step contribute zeros, so every rank reduces the same layout.
     """
@@ -186,7 +187,8 @@ class GradReducer:
         self.groups = [[p for p in g if p.requires_grad] for g in groups]
         self.groups = [g for g in self.groups if g]
         self._pending = [len(g) for g in self.groups]
-        self._work = []          # (group index, flat, handle)
+        self._work = []          # (group index, flat, handle, in_place, divide_after)
+        self.last_in_place = 0
         self._launched = [False] * len(self.groups)
         self._hooks = []
         if self.world > 1:
@@ -201,25 +203,55 @@ class GradReducer:
                 self._launch(gi)
         return hook
 
+    @staticmethod
+    def _shared_span(grads):
+        """One flat tensor over the storage range the gradients of a group occupy, when they are contiguous
+        views of ONE buffer (the library's backward Functions allocate theirs that way); else None."""
+        st = grads[0].untyped_storage()
+        base = st.data_ptr()
+        lo, hi = None, 0
+        for g in grads:
+            if g.dtype != torch.float32 or not g.is_contiguous() or g.untyped_storage().data_ptr() != base:
+                return None
+            a = g.storage_offset()
+            lo = a if lo is None else min(lo, a)
+            hi = max(hi, a + g.numel())
+        if (hi - lo) > 2 * sum(g.numel() for g in grads) + 4096:   # mostly foreign data in between: do not touch it
+            return None
+        return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, lo, (hi - lo,))
+
     def _launch(self, gi):
         g = self.groups[gi]
-        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in g])
-        self._work.append((gi, flat, dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)))
+        grads = [p.grad for p in g]
+        flat = self._shared_span(grads) if all(x is not None for x in grads) else None
+        in_place = flat is not None
+        if not in_place:
+            flat = torch.cat([(x if x is not None else torch.zeros_like(p)).reshape(-1) for x, p in zip(grads, g)])
+        # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then divide in finish()
+        avg_op = self.average and dist.get_backend(self.pg) == "nccl"
+        op = dist.ReduceOp.AVG if avg_op else dist.ReduceOp.SUM
+        self._work.append((gi, flat, dist.all_reduce(flat, op=op, group=self.pg, async_op=True), in_place,
+                           self.average and not avg_op))
         self._launched[gi] = True
 
     def finish(self) -> int:
-        """Waits for the launched collectives (launching those of groups whose hooks did not all fire), writes
-        the averaged gradients back; returns the number of collectives of this step and re-arms the hooks."""
+        """Waits for the launched collectives (launching those of groups whose hooks did not all fire) and, for
+        groups that had to be packed, writes the averaged gradients back; returns the number of collectives of
+        this step and re-arms the hooks.  Groups whose gradients are views of one buffer were reduced in place:
+        nothing is copied."""
         if self.world == 1:
             return 0
         for gi in range(len(self.groups)):
             if not self._launched[gi]:
                 self._launch(gi)
         n = len(self._work)
-        for gi, flat, handle in self._work:
+        self.last_in_place = sum(1 for w in self._work if w[3])   # buckets reduced without packing (introspection)
+        for gi, flat, handle, in_place, divide in self._work:
             handle.wait()
-            if self.average:
+            if divide:
                 flat.div_(self.world)
+            if in_place:
+                continue
             off = 0
             for p in self.groups[gi]:
                 k = p.numel()

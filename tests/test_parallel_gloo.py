@@ -166,11 +166,22 @@ def _reducer_worker(rank, world, port, results):
                 for r, q in zip(ref, list(back.parameters()) + list(front.parameters())):
                     r += q.grad / world
             red._pending = [len(grp) for grp in red.groups]     # the oracle passes fired the hooks too: re-arm
-            for _, _, h in red._work:
-                h.wait()
+            for w in red._work:
+                w[2].wait()
             red._work, red._launched = [], [False] * len(red.groups)
             ok = ok and all(torch.allclose(a, b, atol=1e-6) for a, b in zip(mine, ref))
         red.remove()
+        # gradients that are views of ONE buffer (what the library's backward Functions hand out) are reduced in
+        # place: same storage afterwards, padding between the views untouched by anything but the average
+        ps = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7))]
+        flat = torch.full((64 + 7,), float(rank + 1))
+        ps[0].grad, ps[1].grad = flat[:15].view(5, 3), flat[64:71]
+        red2 = parallel.GradReducer([ps])
+        ok = ok and red2._shared_span([q.grad for q in ps]) is not None
+        ok = ok and red2.finish() == 1
+        ok = ok and ps[0].grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
+        ok = ok and bool(torch.allclose(flat, torch.full_like(flat, (1 + world) / 2.0)))
+        red2.remove()
         results[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
