@@ -452,31 +452,44 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   rrt::Grid lg{};
   lg.L = T; lg.H = 0; lg.rs = 0; lg.g = 0; lg.P = g.R; lg.R = k; lg.Np = T;
   const bool tc_attn = rrt::rmsa_attention_f16_supported(lg, D, c->crmsa_heads);
+  // One cluster kernel for the whole landmark MHA (landmark_chain.cu) in the inference forward; the training
+  // forward keeps the three-kernel chain (its tape wants lqkv, and the projection output takes the dropout).
+  static const bool chain_split = [] { const char* e = getenv("RRT_LANDMARK_CHAIN"); return e && !strcmp(e, "split"); }();
+  const bool fuse_chain = !chain_split && !tr.tape && tr.drop_p == 0.f && g.R == 64 &&
+                          rrt::landmark_chain_supported(k, D, c->crmsa_heads);
+  if (fuse_chain) {
+    StageScope s_(kStLmAttn, st);
+    if (!s_.skip())
+      RRT_CUDA(rrt::launch_landmark_chain(ws.lm, wq, wp, c->qkv_bias ? w->cr_attn.qkv_b : nullptr,
+                                          w->cr_attn.proj_b, ws.lo, ws.lout, k, D, c->crmsa_heads, st),
+               "landmark chain");
+  } else {
   rrt::GemmEpilogue e1;
-  e1.bias = c->qkv_bias ? w->cr_attn.qkv_b : nullptr;
-  { StageScope s_(kStLmQkv, st);
-    if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lm, wq, ws.lqkv, tc_attn, T, 3 * D, D, e1, st), "landmark qkv"); }
-  { StageScope s_(kStLmAttn, st);
-    if (s_.skip()) {
-    } else if (tc_attn && rrt::g_attn_tc05 == 2 && rrt::rmsa_attention_tc05_supported(lg, D, c->crmsa_heads, 0))
-      RRT_CUDA(rrt::launch_rmsa_attention_tc05(reinterpret_cast<const __half*>(ws.lqkv), nullptr, ws.lo,
-                                               lg, D, c->crmsa_heads, 1, st), "landmark attention (tcgen05)");
-    else if (tc_attn)
-      RRT_CUDA(rrt::launch_rmsa_attention_f16(reinterpret_cast<const __half*>(ws.lqkv), nullptr, ws.lo,
-                                              lg, D, c->crmsa_heads, 1, st), "landmark attention");
-    else
-      RRT_CUDA(rrt::launch_landmark_attention(ws.lqkv, ws.lo, k, g.R, D, c->crmsa_heads, st),
-               "landmark attention (fp32)"); }
-  rrt::GemmEpilogue e2;
-  e2.bias = w->cr_attn.proj_b;
-  { StageScope s_(kStLmProj, st);
-    if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lo, wp, ws.lout, false, T, D, D, e2, st), "landmark proj");
-    if (tr.drop_p > 0.f) {  // L' = dropout(proj(...)): the tape keeps the masked landmarks
-      g_launches.fetch_add(1, std::memory_order_relaxed);
-      RRT_CUDA(rrt::launch_dropout_inplace(ws.lout, (size_t)T * D,
-                                           rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream), st),
-               "landmark proj dropout");
-    } }
+    e1.bias = c->qkv_bias ? w->cr_attn.qkv_b : nullptr;
+    { StageScope s_(kStLmQkv, st);
+      if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lm, wq, ws.lqkv, tc_attn, T, 3 * D, D, e1, st), "landmark qkv"); }
+    { StageScope s_(kStLmAttn, st);
+      if (s_.skip()) {
+      } else if (tc_attn && rrt::g_attn_tc05 == 2 && rrt::rmsa_attention_tc05_supported(lg, D, c->crmsa_heads, 0))
+        RRT_CUDA(rrt::launch_rmsa_attention_tc05(reinterpret_cast<const __half*>(ws.lqkv), nullptr, ws.lo,
+                                                 lg, D, c->crmsa_heads, 1, st), "landmark attention (tcgen05)");
+      else if (tc_attn)
+        RRT_CUDA(rrt::launch_rmsa_attention_f16(reinterpret_cast<const __half*>(ws.lqkv), nullptr, ws.lo,
+                                                lg, D, c->crmsa_heads, 1, st), "landmark attention");
+      else
+        RRT_CUDA(rrt::launch_landmark_attention(ws.lqkv, ws.lo, k, g.R, D, c->crmsa_heads, st),
+                 "landmark attention (fp32)"); }
+    rrt::GemmEpilogue e2;
+    e2.bias = w->cr_attn.proj_b;
+    { StageScope s_(kStLmProj, st);
+      if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lo, wp, ws.lout, false, T, D, D, e2, st), "landmark proj");
+      if (tr.drop_p > 0.f) {  // L' = dropout(proj(...)): the tape keeps the masked landmarks
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        RRT_CUDA(rrt::launch_dropout_inplace(ws.lout, (size_t)T * D,
+                                             rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream), st),
+                 "landmark proj dropout");
+      } }
+  }
   { StageScope s_(kStCrDispatch, st);
     if (!s_.skip()) RRT_CUDA(rrt::launch_crmsa_dispatch(x1, x0, ws.logits, ws.rstat, ws.lout,
                                         final_norm ? w->norm_w : nullptr,

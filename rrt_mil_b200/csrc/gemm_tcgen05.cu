@@ -929,6 +929,10 @@ cudaError_t launch_pair(const __half* a, const __half* w, const Tc05Params& p, c
 }
 
 }  // namespace
+// landmark_chain.cu builds its operand maps with the same encoder / cache
+bool tc05_make_kmajor_map(CUtensorMap* m, const __half* base, int rows, int K, int box_rows) {
+  return make_map(m, base, rows, K, box_rows);
+}
 // Row-statistics side output of the residual epilogue: number of 128-column parts per row, or 0 when the
 // launch below would not pick a 256-column tile for this problem (the part width is half a tile).
 // Must mirror launch_mode().
