@@ -49,25 +49,67 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ xrow, const flo
   }
 }
 
+// Two adjacent slots per warp, both rows' loads issued before either is reduced (2 x D x 4 bytes in flight per
+// warp), so that the whole bag is ONE resident wave (N=9000, D=512: 576 CTAs at 4 per SM; one slot per warp was
+// 1152 CTAs = 1.56 waves at 5 per SM, the second one 56 % full: 9.7 us for 27.8 MB).
 template <int V>
-__global__ void __launch_bounds__(256) ln_partition_kernel(const float* __restrict__ x,
-                                                           const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta,
-                                                           __half* __restrict__ z, Grid grid) {
-  const int D = 128 * V;
+__global__ void __launch_bounds__(256, 4) ln_partition_kernel(const float* __restrict__ x,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              __half* __restrict__ z, Grid grid) {
+  constexpr int D = 128 * V, U = V <= 4 ? 2 : 1;   // wide rows: one per warp (registers)
   pdl_launch_dependents();
   pdl_wait();
-  int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  int lane = threadIdx.x & 31;
-  if (slot >= grid.Np) return;
-  int t = grid.slot_to_token(slot);
-  __half* zrow = z + (size_t)slot * D;
-  if (t >= grid.L) {  // pad token: exact zeros AFTER the norm (modules/rmsa.py:200)
+  const int lane = threadIdx.x & 31;
+  const int slot0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * U;
+  if (slot0 >= grid.Np) return;
+  float4 v[U][V];
+  bool real[U];
 #pragma unroll
-    for (int i = 0; i < V; ++i) reinterpret_cast<uint2*>(zrow)[lane + 32 * i] = make_uint2(0u, 0u);
-    return;
+  for (int u = 0; u < U; ++u) {
+    const int slot = slot0 + u;
+    const int t = slot < grid.Np ? grid.slot_to_token(slot) : grid.L;
+    real[u] = t < grid.L;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      v[u][i] = real[u] ? __ldg(reinterpret_cast<const float4*>(x + (size_t)t * D) + lane + 32 * i)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  ln_row<V>(x + (size_t)t * D, nullptr, gamma, beta, zrow, lane);
+  const float inv_d = 1.f / D;
+  float mean[U], rstd[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+    mean[u] = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float a = v[u][i].x - mean[u], b = v[u][i].y - mean[u], c = v[u][i].z - mean[u], d = v[u][i].w - mean[u];
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    rstd[u] = rsqrtf(warp_sum(q) * inv_d + kLnEps);
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (slot0 + u >= grid.Np) continue;
+      uint2* zrow = reinterpret_cast<uint2*>(z + (size_t)(slot0 + u) * D);
+      // pad token: exact zeros AFTER the norm (modules/rmsa.py:200)
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (real[u]) {
+        o.x = (v[u][i].x - mean[u]) * rstd[u] * gm.x + bt.x;
+        o.y = (v[u][i].y - mean[u]) * rstd[u] * gm.y + bt.y;
+        o.z = (v[u][i].z - mean[u]) * rstd[u] * gm.z + bt.z;
+        o.w = (v[u][i].w - mean[u]) * rstd[u] * gm.w + bt.w;
+      }
+      zrow[lane + 32 * i] = real[u] ? pack_h4(o) : make_uint2(0u, 0u);
+    }
+  }
 }
 
 template <int V>
@@ -97,8 +139,8 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
 cudaError_t launch_ln_partition(const float* x, const float* gamma, const float* beta, __half* z,
                                 const Grid& grid, int D, cudaStream_t stream) {
   if (D % 128) return cudaErrorInvalidValue;
-  const int wpb = 8;
-  int blocks = (grid.Np + wpb - 1) / wpb;
+  const int wpb = 8, rows_per_cta = (D <= 512 ? 2 : 1) * wpb;   // U of the kernel
+  int blocks = (grid.Np + rows_per_cta - 1) / rows_per_cta;
   RRT_DISPATCH_V(D, prefer_max_shared(ln_partition_kernel<V>);
                  return launch_chain_kernel(ln_partition_kernel<V>, dim3(blocks), dim3(wpb * 32), 0, stream, x,
                                             gamma, beta, z, grid));
