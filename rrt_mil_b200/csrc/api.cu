@@ -452,17 +452,21 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   rrt::Grid lg{};
   lg.L = T; lg.H = 0; lg.rs = 0; lg.g = 0; lg.P = g.R; lg.R = k; lg.Np = T;
   const bool tc_attn = rrt::rmsa_attention_f16_supported(lg, D, c->crmsa_heads);
-  // One cluster kernel for the whole landmark MHA (landmark_chain.cu) in the inference forward; the training
-  // forward keeps the three-kernel chain (its tape wants lqkv, and the projection output takes the dropout).
+  // One cluster kernel for the whole landmark MHA (landmark_chain.cu) when head_dim is 64; with a tape it also
+  // writes the f16 q|k|v rows the backward re-reads, so training and inference forwards stay bit-identical.
   static const bool chain_split = [] { const char* e = getenv("RRT_LANDMARK_CHAIN"); return e && !strcmp(e, "split"); }();
-  const bool fuse_chain = !chain_split && !tr.tape && tr.drop_p == 0.f && g.R == 64 &&
-                          rrt::landmark_chain_supported(k, D, c->crmsa_heads);
+  const bool fuse_chain = !chain_split && tc_attn && g.R == 64 && rrt::landmark_chain_supported(k, D, c->crmsa_heads);
   if (fuse_chain) {
-    StageScope s_(kStLmAttn, st);
+    StageScope s_(kStLmAttn, st, tr.drop_p > 0.f ? 2 : 1);
     if (!s_.skip())
       RRT_CUDA(rrt::launch_landmark_chain(ws.lm, wq, wp, c->qkv_bias ? w->cr_attn.qkv_b : nullptr,
-                                          w->cr_attn.proj_b, ws.lo, ws.lout, k, D, c->crmsa_heads, st),
+                                          w->cr_attn.proj_b, tr.tape ? reinterpret_cast<__half*>(ws.lqkv) : nullptr,
+                                          ws.lo, ws.lout, k, D, c->crmsa_heads, st),
                "landmark chain");
+    if (tr.drop_p > 0.f)   // L' = dropout(proj(...)): the tape keeps the masked landmarks
+      RRT_CUDA(rrt::launch_dropout_inplace(ws.lout, (size_t)T * D,
+                                           rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream), st),
+               "landmark proj dropout");
   } else {
   rrt::GemmEpilogue e1;
     e1.bias = c->qkv_bias ? w->cr_attn.qkv_b : nullptr;

@@ -127,11 +127,12 @@ cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const 
                                      __half* landmarks, float2* rstat, const Grid& grid, int D, int k,
                                      cudaStream_t stream, const float* rs_part = nullptr, int rs_parts = 0);
 // landmark_chain.cu: the whole landmark MHA (QKV projection, attention, output projection) as ONE cluster
-// kernel, CTA = head; head_dim 64, heads <= 8, inference.  lm / lo f16 [k*64, D], lout fp32 [k*64, D].
+// kernel, CTA = head; head_dim 64, heads <= 8.  lm / lo f16 [k*64, D], lout fp32 [k*64, D]; lqkv (nullable):
+// f16 [k*64, 3D] copy of the projected q|k|v rows for the training tape.
 bool landmark_chain_supported(int k, int D, int heads);
 cudaError_t launch_landmark_chain(const __half* lm, const __half* wq, const __half* wp, const float* qkv_b,
-                                  const float* proj_b, __half* lo, float* lout, int k, int D, int heads,
-                                  cudaStream_t stream);
+                                  const float* proj_b, __half* lqkv, __half* lo, float* lout, int k, int D,
+                                  int heads, cudaStream_t stream);
 // MHA core over the landmarks: batch = k, sequence = R (64), heads, head_dim = D/heads, plain
 // softmax(q k^T * scale) v, fp32 math.  lqkv: [k*R, 3D] fp32 rows (n, rho); lo: [k*R, D] f16.
 cudaError_t launch_landmark_attention(const float* lqkv, __half* lo, int k, int R, int D, int heads,

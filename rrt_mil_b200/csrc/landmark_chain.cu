@@ -15,7 +15,7 @@
 //            (M128 N64; the ring re-cut into 6 stages of 24 KB), +bias -> lout fp32
 // The kernel is latency-bound (8 k-blocks of 40 KB, then 8 of 24 KB per CTA): the ring depth, not the tensor
 // core, sets its time.
-// Inference forward only (the training forward keeps the three-kernel chain: its tape wants lqkv).
+// The training forward uses it too: it then also stores the f16 q|k|v rows the backward re-reads (lqkv).
 #include <cuda.h>
 #include "kernels.cuh"
 #include "mma_f16.cuh"
@@ -47,6 +47,7 @@ struct LmParams {
   int T, D, heads;
   const float* qkv_b;   // [3 D] or null
   const float* proj_b;  // [D] or null
+  __half* lqkv;         // [T, 3 D] or null: copy of q|k|v for the training tape
   __half* lo;           // [T, D]
   float* lout;          // [T, D]
   float scale_log2;     // head_dim^-0.5 * log2(e)
@@ -141,6 +142,11 @@ landmark_chain_kernel(const __grid_constant__ CUtensorMap tmLm, const __grid_con
       tmem_ld_32x32(t_addr + c * 32, r);
       tmem_ld_wait();
       uint4* dst = reinterpret_cast<uint4*>(tile + (size_t)row * LDQ + c * 32);
+      // tape copy: chunk c = section c / 2 (q, k, v) of this head, columns (c & 1) * 32 .. + 31
+      const int grow = mt * 128 + row;
+      uint4* gdst = (p.lqkv && grow < T)
+                        ? reinterpret_cast<uint4*>(p.lqkv + (size_t)grow * 3 * D + (c >> 1) * D + h * HD + (c & 1) * 32)
+                        : nullptr;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint32_t w[4];
@@ -149,6 +155,7 @@ landmark_chain_kernel(const __grid_constant__ CUtensorMap tmLm, const __grid_con
           w[e] = pack_h2(__uint_as_float(r[8 * q + 2 * e]) + sbias[c * 32 + 8 * q + 2 * e],
                          __uint_as_float(r[8 * q + 2 * e + 1]) + sbias[c * 32 + 8 * q + 2 * e + 1]);
         dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
+        if (gdst) gdst[q] = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
     tc_fence_before();
@@ -309,8 +316,8 @@ bool landmark_chain_supported(int k, int D, int heads) {
 
 // lm [k*64, D] f16 (landmarks, batch-major), wq [3D, D] / wp [D, D] f16; lo [k*64, D] f16 and lout [k*64, D] fp32 out
 cudaError_t launch_landmark_chain(const __half* lm, const __half* wq, const __half* wp, const float* qkv_b,
-                                  const float* proj_b, __half* lo, float* lout, int k, int D, int heads,
-                                  cudaStream_t stream) {
+                                  const float* proj_b, __half* lqkv, __half* lo, float* lout, int k, int D,
+                                  int heads, cudaStream_t stream) {
   if (!landmark_chain_supported(k, D, heads)) return cudaErrorInvalidValue;
   const int T = k * 64;
   CUtensorMap tmLm, tmWq, tmLo, tmWp;
@@ -324,7 +331,7 @@ cudaError_t launch_landmark_chain(const __half* lm, const __half* wq, const __ha
   }
   LmParams p;
   p.T = T; p.D = D; p.heads = heads;
-  p.qkv_b = qkv_b; p.proj_b = proj_b; p.lo = lo; p.lout = lout;
+  p.qkv_b = qkv_b; p.proj_b = proj_b; p.lqkv = lqkv; p.lo = lo; p.lout = lout;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(heads * ((T + 127) / 128));   // one cluster of `heads` CTAs per 128-row tile
