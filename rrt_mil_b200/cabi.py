@@ -137,6 +137,7 @@ SIGNATURES = {
     "rrt_attn_pool_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P,
                                         C.c_int32, _P, _P, _P, C.c_int32, C.c_float, C.c_uint64, _P, _P, C.c_size_t,
                                         _P]),
+    "rrt_set_step_state": (C.c_int, [_P]),
     "rrt_launch_count": (C.c_int64, []),
     "rrt_stage_timing_enable": (C.c_int, [C.c_int32]),
     "rrt_stage_count": (C.c_int32, []),

@@ -16,6 +16,7 @@
 namespace rrt {
 thread_local bool g_pdl = false;  // common.cuh: programmatic dependent launch of the serial kernel chain
 thread_local bool g_pdl_light = false;
+thread_local const unsigned long long* g_step_seed_dev = nullptr;  // common.cuh: device-resident dropout seed
 }
 
 namespace {
@@ -1524,11 +1525,19 @@ RRT_API int rrt_adam_step(const rrt_adam_tensor* tensors, int32_t n_tensors, flo
     p[i] = t.param; g[i] = t.grad; m[i] = t.exp_avg; v[i] = t.exp_avg_sq; n[i] = t.n;
   }
   int launches = 0;
+  // step state in device memory (rrt_set_step_state): {u64 seed, f32 bc1, f32 bc2_rsqrt}
+  const float* bc_dev = rrt::g_step_seed_dev ? reinterpret_cast<const float*>(rrt::g_step_seed_dev + 1) : nullptr;
   cudaError_t e = rrt::launch_adam(p.data(), g.data(), m.data(), v.data(), n.data(), n_tensors, lr, beta1,
                                    beta2, eps, weight_decay, decoupled != 0, step, grad_scale, &launches,
-                                   (cudaStream_t)stream);
+                                   (cudaStream_t)stream, bc_dev);
   g_launches.fetch_add(launches, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail_cuda(e, "adam step");
+  return RRT_OK;
+}
+
+RRT_API int rrt_set_step_state(const void* device_state) {
+  if (((uintptr_t)device_state) & 15) return fail(RRT_E_INVALID, "step state must be 16-byte aligned");
+  rrt::g_step_seed_dev = static_cast<const unsigned long long*>(device_state);
   return RRT_OK;
 }
 

@@ -115,8 +115,12 @@ struct Dropout {
   unsigned long long key = 0;  // seed + stream * golden ratio (host side: dropout_make)
   uint32_t thresh = 0;         // round(p * 65536); 0 = off
   float scale = 1.f;           // 1 / (1 - p)
+  // optional: a per-step seed that lives in DEVICE memory and is ADDED to `key` when the mask is evaluated, so
+  // that a captured CUDA graph of a training step draws a new mask on every replay (rrt_set_step_state)
+  const unsigned long long* seed_dev = nullptr;
   __host__ __device__ bool on() const { return thresh != 0; }
 };
+extern thread_local const unsigned long long* g_step_seed_dev;  // api.cu (rrt_set_step_state); null = off
 inline Dropout dropout_make(float p, unsigned long long seed, unsigned stream_id) {
   Dropout d;
   if (p > 0.f) {
@@ -124,6 +128,7 @@ inline Dropout dropout_make(float p, unsigned long long seed, unsigned stream_id
     d.thresh = t >= 65535.0 ? 65535u : (uint32_t)t;
     d.scale = 1.f / (1.f - p);
     d.key = seed + (unsigned long long)(stream_id + 1) * 0x9E3779B97F4A7C15ull;
+    d.seed_dev = g_step_seed_dev;
   }
   return d;
 }
@@ -134,7 +139,8 @@ __host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long 
 }
 // keep-and-scale factors of the 4 elements at flat indices idx .. idx+3 (idx % 4 == 0)
 __device__ __forceinline__ float4 dropout_scale4(const Dropout& d, unsigned long long idx) {
-  const unsigned long long h = splitmix64((idx >> 2) + d.key);
+  const unsigned long long key = d.seed_dev ? d.key + __ldg(d.seed_dev) : d.key;
+  const unsigned long long h = splitmix64((idx >> 2) + key);
   float4 m;
   m.x = (uint32_t)(h & 0xffffu) >= d.thresh ? d.scale : 0.f;
   m.y = (uint32_t)((h >> 16) & 0xffffu) >= d.thresh ? d.scale : 0.f;

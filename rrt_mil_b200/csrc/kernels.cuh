@@ -154,7 +154,7 @@ cudaError_t launch_peg(const float* x, float* out, int L, int D, int peg_k, bool
 cudaError_t launch_adam(float* const* p, const float* const* g, float* const* m, float* const* v,
                         const long long* n, int count, float lr, float beta1, float beta2, float eps,
                         float wd, bool decoupled, long long step, float grad_scale, int* launches,
-                        cudaStream_t stream);
+                        cudaStream_t stream, const float* bc_dev = nullptr);
 
 // ---- mil_head.cu: DAttention pooling + predictor behind the encoder ---------
 size_t attn_pool_scratch_floats(int L, int D, int hid);

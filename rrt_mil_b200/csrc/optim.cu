@@ -24,6 +24,7 @@ struct AdamHyper {
   float lr, beta1, beta2, eps, wd, grad_scale;
   float bc1, bc2_rsqrt;  // 1 - beta1^t,  1 / sqrt(1 - beta2^t)
   int decoupled;         // AdamW: p *= 1 - lr*wd instead of g += wd*p
+  const float* bc_dev;   // optional {bc1, bc2_rsqrt} in device memory (a replayed CUDA graph: the step number changes)
 };
 
 __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamHyper& h) {
@@ -37,6 +38,7 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, con
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable tb, AdamHyper h) {
+  if (h.bc_dev) { h.bc1 = __ldg(h.bc_dev); h.bc2_rsqrt = __ldg(h.bc_dev + 1); }
   int t = 0;
   while (t + 1 < tb.count && (int)blockIdx.x >= tb.chunk_begin[t + 1]) ++t;
   const long long n = tb.n[t];
@@ -74,12 +76,13 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamT
 cudaError_t launch_adam(float* const* p, const float* const* g, float* const* m, float* const* v,
                         const long long* n, int count, float lr, float beta1, float beta2, float eps,
                         float wd, bool decoupled, long long step, float grad_scale, int* launches,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const float* bc_dev) {
   AdamHyper h;
   h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.wd = wd; h.grad_scale = grad_scale;
   h.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   h.bc2_rsqrt = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)step)));
   h.decoupled = decoupled ? 1 : 0;
+  h.bc_dev = bc_dev;
   *launches = 0;
   for (int first = 0; first < count; first += kMaxTensors) {
     AdamTable tb;

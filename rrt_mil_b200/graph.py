@@ -86,3 +86,112 @@ class GraphedForward:
             if x.data_ptr() != buf.data_ptr():
                 buf.copy_(x, non_blocking=True)
         return self.replay()
+
+
+class GraphedTrainStep:
+    """One training step of a fixed-geometry bag -- ``zero_grad``, forward, loss, ``backward``, optimizer step --
+    recorded once into a ``torch.cuda.CUDAGraph`` and replayed with a single launch (the eager
+    step is host-bound, ~70 kernel launches + autograd + Python per step against ~0.9 ms of GPU work).
+
+    What changes from step to step and would otherwise be frozen into the graph lives in a 16-byte DEVICE buffer
+    (``rrt_set_step_state``): the dropout seed (added to every mask's seed when the mask is evaluated, forward and
+    backward alike) and Adam's bias corrections.  ``__call__(bag, label)`` copies the inputs into the static
+    buffers, uploads the step state and replays; it returns the static loss tensor (overwritten by the next call).
+
+    Requirements: ``model(bag) -> logits [1, C]`` built from this package's modules (their C calls are capture
+    safe: no host synchronisation, caller-owned workspaces), ``optimizer`` = ``rrt_mil_b200.optim.Adam`` with one
+    parameter group, one CUDA device, no gradient all-reduce inside the step (single rank).  The optimizer's
+    Python-side ``state[p]["step"]`` is brought up to date by ``sync_optimizer_state()``."""
+
+    _RING = 64
+
+    def __init__(self, model, optimizer, n_patches: int, in_dim: int, loss_fn=None, seed: int = 0, device=None):
+        from .optim import Adam
+        if not isinstance(optimizer, Adam) or len(optimizer.param_groups) != 1:
+            raise TypeError("GraphedTrainStep needs rrt_mil_b200.optim.Adam with a single parameter group")
+        self.model, self.opt = model, optimizer
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("GraphedTrainStep needs the model on a CUDA device; there is no CPU fallback")
+        self.loss_fn = loss_fn if loss_fn is not None else torch.nn.functional.cross_entropy
+        self.bag = torch.zeros(1, int(n_patches), int(in_dim), device=self.device)
+        self.label = torch.zeros(1, dtype=torch.long, device=self.device)
+        self.loss = None
+        self._state = torch.zeros(2, dtype=torch.int64, device=self.device)        # {u64 seed | f32 bc1, f32 bc2}
+        self._host = torch.zeros(self._RING, 2, dtype=torch.int64).pin_memory()
+        self._host_f32 = self._host.view(torch.float32)                            # [RING, 4]: floats 2, 3 of a row
+        self._events = [None] * self._RING
+        self._seed = int(seed)
+        self._graph = None
+        st = [optimizer.state[p].get("step", 0) for p in optimizer.param_groups[0]["params"] if p in optimizer.state]
+        self.t = int(max(st)) if st else 0     # optimizer steps taken so far
+        self.replays = 0
+
+    # -- per-step device state ------------------------------------------------------------------------------
+    def _upload_state(self, t: int) -> None:
+        k = t % self._RING
+        if self._events[k] is not None:
+            self._events[k].synchronize()       # the copy that last read this pinned slot (64 steps ago)
+        b1, b2 = self.opt.param_groups[0]["betas"]
+        self._host[k, 0] = (self._seed + t * 0x9E3779B97F4A7C15) % (1 << 63)
+        self._host_f32[k, 2] = 1.0 - b1 ** t
+        self._host_f32[k, 3] = 1.0 / (1.0 - b2 ** t) ** 0.5
+        self._state.copy_(self._host[k], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._events[k] = ev
+
+    def _step_eager(self):
+        self.opt.zero_grad(set_to_none=True)
+        loss = self.loss_fn(self.model(self.bag), self.label)
+        loss.backward()
+        self.opt.step()
+        return loss
+
+    def _capture(self) -> None:
+        lib = cabi.lib()
+        if not self.model.training:
+            raise RuntimeError("GraphedTrainStep captures a TRAINING step: call .train() first")
+        cabi.check(lib.rrt_set_step_state(self._state.data_ptr()), "rrt_set_step_state")
+        try:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(3):      # optimizer state, function attributes, TMA descriptor cache, allocator warm-up
+                    self.t += 1
+                    self._upload_state(self.t)
+                    self._step_eager()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                self.loss = self._step_eager()
+            self._graph = graph
+        finally:
+            cabi.check(lib.rrt_set_step_state(None), "rrt_set_step_state")
+        # the capture itself did not run the kernels; Adam.step counted one step on the Python side
+        self.sync_optimizer_state()
+
+    def sync_optimizer_state(self) -> None:
+        for p in self.opt.param_groups[0]["params"]:
+            if p in self.opt.state and self.opt.state[p]:
+                self.opt.state[p]["step"] = self.t
+
+    def __call__(self, bag: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+        if bag.dim() == 2:
+            bag = bag.unsqueeze(0)
+        if bag.shape != self.bag.shape:
+            raise ValueError(f"expected a bag of shape {tuple(self.bag.shape)}, got {tuple(bag.shape)}")
+        if self._graph is None:
+            self._capture()
+        if bag.data_ptr() != self.bag.data_ptr():
+            self.bag.copy_(bag, non_blocking=True)
+        self.label.copy_(label.reshape(1), non_blocking=True)
+        self.t += 1
+        self._upload_state(self.t)
+        self._graph.replay()
+        self.replays += 1
+        # the graph wrote the parameters through raw pointers: caches keyed on version counters must see it
+        for p in self.opt.param_groups[0]["params"]:
+            torch.autograd.graph.increment_version(p)
+        return self.loss

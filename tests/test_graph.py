@@ -46,3 +46,71 @@ def test_graph_replay_equals_eager_forward():
             assert torch.equal(a, b)
         with pytest.raises(ValueError):
             g(bags[:-1] + [bags[-1][:-1]] if bags[-1].shape[0] > 1 else bags + bags)
+
+
+def _mil(seed, **kw):
+    from rrt_mil_b200 import RRTMIL
+    torch.manual_seed(seed)
+    return RRTMIL(input_dim=512, n_classes=2, epeg_k=9, crmsa_k=3, **kw).cuda().train()
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_follows_the_eager_training_trajectory():
+    """Captured step == eager step: same bags, dropout off (no masks), 8 steps of Adam.  The backward sums with fp32
+    atomics, so trajectories agree to rounding, not bit for bit: losses within 2e-3 relative, parameters within a
+    small fraction of what the optimizer moved them."""
+    from rrt_mil_b200.graph import GraphedTrainStep
+    from rrt_mil_b200.optim import Adam
+    g = torch.Generator(device="cuda").manual_seed(5)
+    bags = [torch.randn(1, 700, 512, device="cuda", generator=g) for _ in range(8)]
+    labels = [torch.tensor([i % 2], device="cuda") for i in range(8)]
+    ma, mb = _mil(3, dropout=0.0, trans_dropout=0.0), _mil(3, dropout=0.0, trans_dropout=0.0)
+    start = [p.detach().clone() for p in ma.parameters()]
+    oa, ob = Adam(ma.parameters(), lr=2e-4, weight_decay=1e-5), Adam(mb.parameters(), lr=2e-4, weight_decay=1e-5)
+    step = GraphedTrainStep(mb, ob, 700, 512)
+    la, lb = [], []
+    # the capture runs three warm-up steps on its static (zero) bag: give the eager model the same three
+    for _ in range(3):
+        oa.zero_grad(set_to_none=True)
+        torch.nn.functional.cross_entropy(ma(torch.zeros(1, 700, 512, device="cuda")),
+                                          torch.zeros(1, dtype=torch.long, device="cuda")).backward()
+        oa.step()
+    for x, y in zip(bags, labels):
+        oa.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.cross_entropy(ma(x), y)
+        loss.backward()
+        oa.step()
+        la.append(float(loss))
+        lb.append(float(step(x, y)))
+    torch.cuda.synchronize()
+    assert step.replays == 8 and step.t == 11
+    assert all(abs(a - b) <= 2e-3 * max(1.0, abs(a)) for a, b in zip(la, lb)), (la, lb)
+    moved = sum(float((p - s).abs().sum()) for p, s in zip(ma.parameters(), start))
+    apart = sum(float((p - q).abs().sum()) for p, q in zip(ma.parameters(), mb.parameters()))
+    assert apart <= 0.05 * moved, (apart, moved)
+    step.sync_optimizer_state()
+    assert all(ob.state[p]["step"] == 11 for p in mb.parameters())
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_draws_a_new_dropout_mask_per_replay_and_learns():
+    from rrt_mil_b200.graph import GraphedTrainStep
+    from rrt_mil_b200.optim import Adam
+    m = _mil(4, dropout=0.25, trans_dropout=0.1)
+    opt = Adam(m.parameters(), lr=0.0)                         # lr 0: only the masks differ between replays
+    step = GraphedTrainStep(m, opt, 600, 512, seed=123)
+    x = torch.randn(1, 600, 512, device="cuda")
+    y = torch.tensor([1], device="cuda")
+    losses = [float(step(x, y)) for _ in range(4)]
+    assert len({round(v, 6) for v in losses}) == 4, losses     # four replays, four masks
+    m2 = _mil(4, dropout=0.25, trans_dropout=0.1)
+    step2 = GraphedTrainStep(m2, Adam(m2.parameters(), lr=2e-4), 600, 512, seed=7)
+    first = sum(float(step2(x, y)) for _ in range(5)) / 5
+    for _ in range(40):
+        step2(x, y)
+    last = sum(float(step2(x, y)) for _ in range(5)) / 5
+    assert last < 0.5 * first, (first, last)
+    # eval after graphed training sees the updated weights (version counters were bumped)
+    with torch.no_grad():
+        logits = m2.eval()(x)
+    assert int(logits.argmax()) == 1
