@@ -604,6 +604,7 @@ def run_b200_arm(args):
         graph_us = None
         if world == 1:      # the same step captured in a CUDA graph (rrt_mil_b200.graph.GraphedTrainStep)
             from rrt_mil_b200.graph import GraphedTrainStep
+            loss = float(loss.detach())   # the eager steps' autograd graph must be gone before the capture
             gstep = GraphedTrainStep(tm, opt, N_TOKENS, 1024)
             for _ in range(3):
                 gstep(tb, label)
@@ -637,7 +638,8 @@ def run_b200_arm(args):
             "bags_per_step": world, "host_enqueue_us_per_step": host_us,
             "launches_per_step": t_launches, "collectives_per_step": n_coll,
             "collectives_in_place": (red.last_in_place if red is not None else 0),
-            "gradient_bytes": sum(q.numel() for q in tm.parameters()) * 4, "final_loss": float(loss.detach()),
+            "gradient_bytes": sum(q.numel() for q in tm.parameters()) * 4,
+            "final_loss": (loss if isinstance(loss, float) else float(loss.detach())),
             "cuda_graph": (None if graph_us is None else {
                 "us_per_step": graph_us, "value": N_TOKENS / (graph_us * 1e-6), "host_enqueue_us_per_step": graph_host_us,
                 "final_loss": graph_loss,

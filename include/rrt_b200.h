@@ -391,7 +391,7 @@ RRT_API int rrt_attn_pool_backward(const float* h, int64_t L, int32_t dim, int32
  * All pointers are device fp32 arrays of n elements; the struct array itself is host memory. */
 /* Per-step state in DEVICE memory, for training steps captured in a CUDA graph (values passed by value would be
  * frozen into the graph):  struct { uint64_t seed; float bc1; float bc2_rsqrt; }  (16 bytes, 16-byte aligned).
- * While set (per host thread; NULL switches it off), every dropout mask of the training entry points adds
+ * While set (process-wide -- torch runs the backward on its autograd thread; NULL switches it off), every dropout mask of the training entry points adds
  * `seed` to the seed argument of the call when the mask is evaluated, and rrt_adam_step takes its bias
  * corrections bc1 = 1 - beta1^t, bc2_rsqrt = 1 / sqrt(1 - beta2^t) from the buffer instead of from `step`.
  * The caller updates the buffer (one 16-byte copy on the stream) before every replay. */

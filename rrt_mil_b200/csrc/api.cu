@@ -16,7 +16,7 @@
 namespace rrt {
 thread_local bool g_pdl = false;  // common.cuh: programmatic dependent launch of the serial kernel chain
 thread_local bool g_pdl_light = false;
-thread_local const unsigned long long* g_step_seed_dev = nullptr;  // common.cuh: device-resident dropout seed
+const unsigned long long* volatile g_step_seed_dev = nullptr;  // common.cuh: device-resident dropout seed
 }
 
 namespace {

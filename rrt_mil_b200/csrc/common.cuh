@@ -120,7 +120,9 @@ struct Dropout {
   const unsigned long long* seed_dev = nullptr;
   __host__ __device__ bool on() const { return thresh != 0; }
 };
-extern thread_local const unsigned long long* g_step_seed_dev;  // api.cu (rrt_set_step_state); null = off
+// api.cu (rrt_set_step_state); null = off.  PROCESS-wide, not per thread: torch runs the backward of a step on its
+// autograd thread, and forward and backward must evaluate the same masks
+extern const unsigned long long* volatile g_step_seed_dev;
 inline Dropout dropout_make(float p, unsigned long long seed, unsigned stream_id) {
   Dropout d;
   if (p > 0.f) {

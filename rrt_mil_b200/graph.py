@@ -101,7 +101,12 @@ class GraphedTrainStep:
     Requirements: ``model(bag) -> logits [1, C]`` built from this package's modules (their C calls are capture
     safe: no host synchronisation, caller-owned workspaces), ``optimizer`` = ``rrt_mil_b200.optim.Adam`` with one
     parameter group, one CUDA device, no gradient all-reduce inside the step (single rank).  The optimizer's
-    Python-side ``state[p]["step"]`` is brought up to date by ``sync_optimizer_state()``."""
+    Python-side ``state[p]["step"]`` is brought up to date by ``sync_optimizer_state()``.
+
+    Drop every tensor that still hangs on to an EARLIER eager step's autograd graph (e.g. its loss) before the
+    first call: such a graph keeps the parameters' AccumulateGrad nodes alive on the stream that step ran on
+    (usually the legacy default stream), and torch then has to synchronise that stream with the capturing one,
+    which CUDA forbids ("would make the legacy stream depend on a capturing blocking stream")."""
 
     _RING = 64
 
@@ -123,6 +128,7 @@ class GraphedTrainStep:
         self._events = [None] * self._RING
         self._seed = int(seed)
         self._graph = None
+        self.capture_error_mode = "thread_local"
         st = [optimizer.state[p].get("step", 0) for p in optimizer.param_groups[0]["params"] if p in optimizer.state]
         self.t = int(max(st)) if st else 0     # optimizer steps taken so far
         self.replays = 0
@@ -163,8 +169,12 @@ class GraphedTrainStep:
                     self._step_eager()
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
+            import gc
+            gc.collect()            # dead autograd graphs of earlier eager steps release their AccumulateGrad nodes
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
+            # thread_local: torch runs the backward on its autograd thread and other host threads of the process
+            # (pinned-memory bookkeeping, NCCL watchdogs, monitoring) may call CUDA while the step is being recorded
+            with torch.cuda.graph(graph, stream=side, capture_error_mode=self.capture_error_mode):
                 self.loss = self._step_eager()
             self._graph = graph
         finally:

@@ -104,6 +104,12 @@ def test_graphed_train_step_draws_a_new_dropout_mask_per_replay_and_learns():
     losses = [float(step(x, y)) for _ in range(4)]
     assert len({round(v, 6) for v in losses}) == 4, losses     # four replays, four masks
     m2 = _mil(4, dropout=0.25, trans_dropout=0.1)
+    # an eager step on the default stream first (a loop that switches to the graph after a few steps): its
+    # autograd graph must be released before the capture, see the class docstring
+    eager_loss = torch.nn.functional.cross_entropy(m2(x), y)
+    eager_loss.backward()
+    m2.zero_grad(set_to_none=True)
+    del eager_loss
     step2 = GraphedTrainStep(m2, Adam(m2.parameters(), lr=2e-4), 600, 512, seed=7)
     first = sum(float(step2(x, y)) for _ in range(5)) / 5
     for _ in range(40):
