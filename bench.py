@@ -601,30 +601,37 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
         t_ms = max_over_ranks(q0.elapsed_time(q1))
         t_launches = (cabi.launch_count() - l0) // t_steps
-        graph_us = None
-        if world == 1:      # the same step captured in a CUDA graph (rrt_mil_b200.graph.GraphedTrainStep)
+        graph_us, graph_err = None, None
+        # the same step captured in a CUDA graph (rrt_mil_b200.graph.GraphedTrainStep); with W > 1 the gradient
+        # all-reduces launched by the reducer's hooks are part of the graph
+        try:
             from rrt_mil_b200.graph import GraphedTrainStep
             loss = float(loss.detach())   # the eager steps' autograd graph must be gone before the capture
-            gstep = GraphedTrainStep(tm, opt, N_TOKENS, 1024)
+            gstep = GraphedTrainStep(tm, opt, N_TOKENS, 1024, reducer=red)
             for _ in range(3):
                 gstep(tb, label)
-            torch.cuda.synchronize()
+            torch.cuda.synchronize(); barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
             for _ in range(t_steps):
                 gloss = gstep(tb, label)
             g1.record()
             torch.cuda.synchronize()
-            graph_us = g0.elapsed_time(g1) / t_steps * 1e3
+            graph_us = max_over_ranks(g0.elapsed_time(g1)) / t_steps * 1e3
             gh = []
             for _ in range(5):
-                torch.cuda.synchronize()
+                torch.cuda.synchronize(); barrier()
                 h0 = time.perf_counter()
                 gstep(tb, label)
                 gh.append((time.perf_counter() - h0) * 1e6)
             torch.cuda.synchronize()
             graph_host_us = statistics.median(gh)
             graph_loss = float(gloss.detach())
+            del gloss
+            gstep.close()     # a graph holding NCCL collectives must not outlive the process group
+            del gstep
+        except Exception as exc:   # optional leg: never take the bench line down with it
+            graph_us, graph_err = None, f"{type(exc).__name__}: {str(exc).splitlines()[0][:200]}"
         host = []
         for _ in range(5):   # host cost of ONE step enqueued into an empty queue (all ranks in step: collectives)
             torch.cuda.synchronize(); barrier()
@@ -640,8 +647,9 @@ def run_b200_arm(args):
             "collectives_in_place": (red.last_in_place if red is not None else 0),
             "gradient_bytes": sum(q.numel() for q in tm.parameters()) * 4,
             "final_loss": (loss if isinstance(loss, float) else float(loss.detach())),
-            "cuda_graph": (None if graph_us is None else {
-                "us_per_step": graph_us, "value": N_TOKENS / (graph_us * 1e-6), "host_enqueue_us_per_step": graph_host_us,
+            "cuda_graph": ({"error": graph_err} if graph_us is None else {
+                "us_per_step": graph_us, "value": world * N_TOKENS / (graph_us * 1e-6),
+                "host_enqueue_us_per_step": graph_host_us,
                 "final_loss": graph_loss,
                 "what": "the same step (zero_grad, forward, CE, backward, Adam) captured once in a CUDA graph and "
                         "replayed; dropout seed and Adam bias corrections come from a 16-byte device buffer "
@@ -697,8 +705,17 @@ def run_b200_arm(args):
             line["cpu_baseline"] = time_cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
+        import gc
+        # the line is out; a communicator teardown that hangs must not hold the job (seen once with a CUDA graph that
+        # still referenced NCCL work): leave after 45 s at the latest
+        sys.stdout.flush()
+        threading.Timer(45.0, lambda: os._exit(0)).start()
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
     return line
 
 

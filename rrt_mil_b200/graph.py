@@ -100,8 +100,9 @@ class GraphedTrainStep:
 
     Requirements: ``model(bag) -> logits [1, C]`` built from this package's modules (their C calls are capture
     safe: no host synchronisation, caller-owned workspaces), ``optimizer`` = ``rrt_mil_b200.optim.Adam`` with one
-    parameter group, one CUDA device, no gradient all-reduce inside the step (single rank).  The optimizer's
-    Python-side ``state[p]["step"]`` is brought up to date by ``sync_optimizer_state()``.
+    parameter group, one CUDA device per process; ``reducer`` = an optional ``parallel.GradReducer`` (data-parallel
+    step: its NCCL all-reduces become part of the graph).  The optimizer's Python-side ``state[p]["step"]`` is
+    brought up to date by ``sync_optimizer_state()``.
 
     Drop every tensor that still hangs on to an EARLIER eager step's autograd graph (e.g. its loss) before the
     first call: such a graph keeps the parameters' AccumulateGrad nodes alive on the stream that step ran on
@@ -110,11 +111,16 @@ class GraphedTrainStep:
 
     _RING = 64
 
-    def __init__(self, model, optimizer, n_patches: int, in_dim: int, loss_fn=None, seed: int = 0, device=None):
+    def __init__(self, model, optimizer, n_patches: int, in_dim: int, loss_fn=None, seed: int = 0, device=None,
+                 reducer=None):
         from .optim import Adam
         if not isinstance(optimizer, Adam) or len(optimizer.param_groups) != 1:
             raise TypeError("GraphedTrainStep needs rrt_mil_b200.optim.Adam with a single parameter group")
         self.model, self.opt = model, optimizer
+        # data-parallel: a parallel.GradReducer whose hooks launch the gradient all-reduces during backward;
+        # finish() is part of the recorded step (NCCL collectives are capturable), so a replay is the whole
+        # batch-W step of this rank
+        self.reducer = reducer
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs the model on a CUDA device; there is no CPU fallback")
@@ -151,6 +157,8 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         loss = self.loss_fn(self.model(self.bag), self.label)
         loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
         self.opt.step()
         return loss
 
@@ -180,6 +188,15 @@ class GraphedTrainStep:
         finally:
             cabi.check(lib.rrt_set_step_state(None), "rrt_set_step_state")
         # the capture itself did not run the kernels; Adam.step counted one step on the Python side
+        self.sync_optimizer_state()
+
+    def close(self) -> None:
+        """Drops the recorded graph (and its private memory pool).  A graph that contains NCCL collectives must be
+        gone before ``torch.distributed.destroy_process_group()``, or the teardown of the communicator hangs."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.device)
+            self._graph = None
+            self.loss = None
         self.sync_optimizer_state()
 
     def sync_optimizer_state(self) -> None:
