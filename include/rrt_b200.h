@@ -42,7 +42,7 @@ extern "C" {
 #define RRT_API __attribute__((visibility("default")))
 #endif
 
-#define RRT_ABI_VERSION 7
+#define RRT_ABI_VERSION 8
 #define RRT_MAX_RMSA_LAYERS 8 /* n_layers-1 R-MSA TransLayers (modules/rrt.py:143) */
 #define RRT_MAX_CRMSA_K 16    /* crmsa_k landmarks per region                         */
 #define RRT_MAX_EPEG_K 63     /* odd EPEG kernel length                               */
@@ -89,12 +89,18 @@ typedef struct rrt_config {
   int32_t ffn;              /* on/off                                                   */
   int32_t ffn_act;          /* RRT_ACT_GELU (ffn_act='gelu', default) or RRT_ACT_RELU    */
   int32_t ffn_hidden;       /* int(dim * mlp_ratio); multiple of 64                     */
+  /* EPEG ablation variants (modules/rmsa.py:72-87,104-129); inference only */
+  int32_t epeg_type;        /* RRT_EPEG_ATTN (default) / RRT_EPEG_VALUE_BF / RRT_EPEG_VALUE_AF */
+  int32_t epeg_2d;          /* k x k kernel instead of (k, 1)                           */
 } rrt_config;
+enum { RRT_EPEG_ATTN = 0, RRT_EPEG_VALUE_BF = 1, RRT_EPEG_VALUE_AF = 2 };
 enum { RRT_POS_NONE = 0, RRT_POS_PEG = 1, RRT_POS_PPEG = 2 };
 
 /* One InnerAttention (modules/rmsa.py:56-89).  qkv_b may be NULL (qkv_bias=False);
- * pe_w is the depthwise EPEG taps [heads, epeg_k] (= pe.weight[h,0,:,0]) or NULL.
- * pe.bias is not needed: it is constant along the softmax axis. */
+ * pe_w is the depthwise EPEG kernel (= pe.weight, contiguous) or NULL: [heads, epeg_k] for the default
+ * epeg_type 'attn' ([heads, k, k] with epeg_2d), [D, epeg_k] resp. [D, k, k] for the value variants.
+ * pe.bias is not needed for 'attn' (constant along the softmax axis); the value variants
+ * read it from pe_b ([D] or NULL). */
 typedef struct rrt_attn_weights {
   const float* qkv_w;  /* [3D, D] */
   const float* qkv_b;  /* [3D] or NULL */
@@ -106,6 +112,7 @@ typedef struct rrt_attn_weights {
    * slower).  The Python binding keeps shadows and refreshes them when a parameter changes. */
   const void* qkv_w_f16;  /* [3D, D] fp16 */
   const void* proj_w_f16; /* [D, D] fp16 */
+  const float* pe_b;      /* [D] or NULL: pe.bias of the value variants of EPEG */
 } rrt_attn_weights;
 
 /* One Mlp + its pre-norm (TransLayer.norm2 / TransLayer.mlp, modules/rrt.py:47,106); all NULL when ffn = 0. */

@@ -76,7 +76,7 @@ def build_reference_encoder(cfg, weights, dtype=torch.float64):
                        crmsa_mlp=cfg.crmsa_mlp, crmsa_heads=cfg.crmsa_heads,
                        epeg_bias=cfg.epeg_bias, pos=cfg.pos, pos_pos=cfg.pos_pos, peg_k=cfg.peg_k,
                        peg_bias=cfg.peg_bias, peg_1d=cfg.peg_1d, ffn=cfg.ffn, ffn_act=cfg.ffn_act,
-                       mlp_ratio=cfg.mlp_ratio)
+                       mlp_ratio=cfg.mlp_ratio, epeg_2d=cfg.epeg_2d, epeg_type=cfg.epeg_type)
     m = m.to(dtype).eval()
     m.load_state_dict({k: v.to(dtype) for k, v in weights.items()}, strict=True)
     return m

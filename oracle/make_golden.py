@@ -68,6 +68,14 @@ CASES = [
     ("ffn_relu_d256_3layers", 700, dict(mlp_dim=256, ffn=True, ffn_act="relu", mlp_ratio=2.0, n_layers=3,
                                         all_shortcut=True), 7, "randn"),
     ("ffn_nocr", 500, dict(mlp_dim=256, ffn=True, cr_msa=False), 7, "randn"),
+    # EPEG ablation variants (modules/rmsa.py:72-87,104-129)
+    ("epeg2d_k5_n1500", 1500, dict(epeg_2d=True, epeg_k=5), 7, "relu"),
+    ("epeg2d_k15_n9000", 9000, dict(epeg_2d=True), 7, "relu"),
+    ("epeg_value_bf_k7_n2000", 2000, dict(epeg_type="value_bf", epeg_k=7), 7, "relu"),
+    ("epeg_value_af_k9_3layers", 1200, dict(epeg_type="value_af", epeg_k=9, n_layers=3, epeg_bias=False), 7, "randn"),
+    ("epeg_value_bf_2d_k3_n9000", 9000, dict(epeg_type="value_bf", epeg_2d=True, epeg_k=3), 7, "relu"),
+    ("epeg_value_af_2d_k5_d256", 900, dict(epeg_type="value_af", epeg_2d=True, epeg_k=5, mlp_dim=256, n_heads=4,
+                                           crmsa_heads=4), 7, "randn"),
 ]
 
 # RRTMIL end-to-end: name, L, input_dim, n_classes, act, da_act, da_bias, encoder overrides

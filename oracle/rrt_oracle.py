@@ -53,6 +53,8 @@ class EncoderConfig:
     n_heads: int = 8
     epeg: bool = True
     epeg_k: int = 15
+    epeg_2d: bool = False        # ablation: k x k kernel instead of (k, 1)  (modules/rmsa.py:76-87)
+    epeg_type: str = "attn"      # ablation: 'attn' | 'value_bf' | 'value_af'  (modules/rmsa.py:104-129)
     region_size: int = 0
     min_region_num: int = 0
     min_region_ratio: float = 0.0
@@ -175,11 +177,15 @@ def _from_regions(y: torch.Tensor, L: int, H: int, rs: int) -> torch.Tensor:
 
 
 def inner_attention(xr: torch.Tensor, w: Dict[str, torch.Tensor], prefix: str, heads: int,
-                    order: str) -> torch.Tensor:
+                    order: str, epeg_type: str = "attn") -> torch.Tensor:
     """Multi-head attention over each row-block of ``xr`` [B_,S,D] (modules/rmsa.py:91-134).
 
     ``prefix`` points at the InnerAttention (``...attn.attn.``).  EPEG is applied when
-    ``prefix + 'pe.weight'`` exists.  Eval mode: both dropouts are identities.
+    ``prefix + 'pe.weight'`` exists; its kernel is (k, 1) or k x k (``epeg_2d``), read off the weight's shape.
+    ``epeg_type``: 'attn' = conv on the logit map; 'value_bf' / 'value_af' = depthwise conv on V folded into the
+    region's sqrt(S) x sqrt(S) grid, added to V before resp. to the output after the attention
+    (modules/rmsa.py:114-129, including the reference's channel reinterpretation: the conv sees channel
+    d*heads + h, its result is read back as channel h'*d_head + d').  Eval mode: both dropouts are identities.
     """
     B_, S, D = xr.shape
     d = D // heads
@@ -187,14 +193,24 @@ def inner_attention(xr: torch.Tensor, w: Dict[str, torch.Tensor], prefix: str, h
     qkv = qkv.view(B_, S, 3, heads, d).permute(2, 0, 3, 1, 4)  # [3,B_,h,S,d]
     q, k, v = qkv[0] * d ** -0.5, qkv[1], qkv[2]
     pe_w = w.get(prefix + "pe.weight")
-    if order == "reference":
+    pe_b = w.get(prefix + "pe.bias")
+    on_logits = pe_w is not None and epeg_type == "attn"
+    two_d = pe_w is not None and pe_w.shape[3] > 1
+
+    def value_pe():
+        side = _ceil_sqrt(S)
+        kk = pe_w.shape[2]
+        img = v.permute(0, 3, 1, 2).reshape(B_, D, side, side)
+        return F.conv2d(img, pe_w, pe_b, padding=(kk // 2, kk // 2 if two_d else 0), groups=D)
+
+    if order == "reference" or (on_logits and two_d):
         logits = q @ k.transpose(-1, -2)  # [B_,h,S,S]
-        if pe_w is not None:
+        if on_logits:
             kk = pe_w.shape[2]
-            logits = logits + F.conv2d(logits, pe_w, w.get(prefix + "pe.bias"),
-                                       padding=(kk // 2, 0), groups=heads)
+            logits = logits + F.conv2d(logits, pe_w, pe_b, padding=(kk // 2, kk // 2 if two_d else 0),
+                                       groups=heads)
     else:
-        if pe_w is not None:
+        if on_logits:
             kk = pe_w.shape[2]
             # depthwise conv along the token axis of q, one tap vector per head; the conv
             # bias is constant along the key axis and vanishes in the softmax.
@@ -203,8 +219,12 @@ def inner_attention(xr: torch.Tensor, w: Dict[str, torch.Tensor], prefix: str, h
             qc = F.conv1d(qc, taps, padding=kk // 2, groups=heads * d)
             q = q + qc.view(B_, heads, d, S).permute(0, 1, 3, 2)
         logits = q @ k.transpose(-1, -2)
-    o = torch.softmax(logits, -1) @ v  # [B_,h,S,d]
-    o = o.transpose(1, 2).reshape(B_, S, D)
+    attn = torch.softmax(logits, -1)
+    if pe_w is not None and epeg_type == "value_bf":
+        v = v + value_pe().reshape(B_, heads, d, S).permute(0, 1, 3, 2)
+    o = (attn @ v).transpose(1, 2).reshape(B_, S, D)  # [B_,S,D]
+    if pe_w is not None and epeg_type == "value_af":
+        o = o + value_pe().reshape(B_, D, S).transpose(-1, -2)
     return F.linear(o, w[prefix + "proj.weight"], w[prefix + "proj.bias"])
 
 
@@ -215,7 +235,7 @@ def rmsa_block(z, w, prefix, cfg: EncoderConfig, order, mask=None):
     L = z.shape[0]
     H, rs, _ = grid_geometry(L, cfg.region_num, cfg.region_size, cfg.min_region_num,
                              cfg.min_region_ratio)
-    y = inner_attention(_to_regions(z, L, H, rs), w, prefix + "attn.", cfg.n_heads, order)
+    y = inner_attention(_to_regions(z, L, H, rs), w, prefix + "attn.", cfg.n_heads, order, cfg.epeg_type)
     y = _from_regions(y, L, H, rs)
     return y if mask is None else y * mask
 
@@ -404,9 +424,10 @@ def weight_shapes(cfg: EncoderConfig) -> Dict[str, Tuple[int, ...]]:
         shp[prefix + "proj.weight"] = (D, D)
         shp[prefix + "proj.bias"] = (D,)
         if epeg:
-            shp[prefix + "pe.weight"] = (cfg.n_heads, 1, cfg.epeg_k, 1)
+            ch = cfg.n_heads if cfg.epeg_type == "attn" else D     # modules/rmsa.py:76-87
+            shp[prefix + "pe.weight"] = (ch, 1, cfg.epeg_k, cfg.epeg_k if cfg.epeg_2d else 1)
             if cfg.epeg_bias:
-                shp[prefix + "pe.bias"] = (cfg.n_heads,)
+                shp[prefix + "pe.bias"] = (ch,)
 
     for i in range(cfg.n_layers - 1):
         shp[f"layers.{i}.norm.weight"] = (D,)
@@ -451,7 +472,7 @@ def make_weights(cfg: EncoderConfig, seed: int, dtype=torch.float64,
         elif name.startswith("pos_embedding.") and name.endswith("weight"):
             a = rs.standard_normal(shape) * (0.5 / math.sqrt(shape[2] * shape[3]))
         elif name.endswith("pe.weight"):
-            fan = shape[2]  # Conv2d(h,h,(k,1),groups=h): fan_in = fan_out = k per group
+            fan = shape[2] * shape[3]  # Conv2d(h,h,(k,1) | (k,k),groups=h): fan_in = fan_out = taps per group
             a = rs.standard_normal(shape) * math.sqrt(2.0 / (fan + fan))
         elif name.endswith("phi"):
             bound = 1.0 / math.sqrt(shape[1])  # kaiming_uniform(a=sqrt5) on [D,k]: fan_in=k

@@ -12,11 +12,12 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librrt_b200.so")
 
-RRT_ABI_VERSION = 7
+RRT_ABI_VERSION = 8
 RRT_DROP_STREAM_CRMSA = 64
 RRT_DROP_STREAM_PATCH = 65
 RRT_DROP_STREAM_POOL = 66
 RRT_POS_NONE, RRT_POS_PEG, RRT_POS_PPEG = 0, 1, 2
+RRT_EPEG_ATTN, RRT_EPEG_VALUE_BF, RRT_EPEG_VALUE_AF = 0, 1, 2
 RRT_MAX_RMSA_LAYERS = 8
 RRT_MAX_CRMSA_K = 16
 RRT_MAX_EPEG_K = 63
@@ -39,13 +40,14 @@ class RrtConfig(C.Structure):
         ("math_mode", C.c_int32),
         ("pos", C.c_int32), ("pos_pos", C.c_int32), ("peg_k", C.c_int32), ("peg_1d", C.c_int32),
         ("ffn", C.c_int32), ("ffn_act", C.c_int32), ("ffn_hidden", C.c_int32),
+        ("epeg_type", C.c_int32), ("epeg_2d", C.c_int32),
     ]
 
 
 class RrtAttnWeights(C.Structure):
     _fields_ = [("qkv_w", c_float_p), ("qkv_b", c_float_p), ("proj_w", c_float_p),
                 ("proj_b", c_float_p), ("pe_w", c_float_p), ("qkv_w_f16", c_float_p),
-                ("proj_w_f16", c_float_p)]
+                ("proj_w_f16", c_float_p), ("pe_b", c_float_p)]
 
 
 class RrtFfnWeights(C.Structure):

@@ -166,6 +166,9 @@ int check_config(const rrt_config* c) {
     if (c->epeg && (c->epeg_k < 1 || c->epeg_k > RRT_MAX_EPEG_K || c->epeg_k % 2 == 0))
       return fail(RRT_E_INVALID, "epeg_k must be odd and <= 63 (the reference fails on even k)");
     if (c->region_size <= 0 && c->region_num < 1) return fail(RRT_E_INVALID, "region_num < 1");
+    if (c->epeg_type != RRT_EPEG_ATTN && c->epeg_type != RRT_EPEG_VALUE_BF && c->epeg_type != RRT_EPEG_VALUE_AF)
+      return fail(RRT_E_INVALID, "unknown epeg_type");
+    if (c->epeg_2d != 0 && c->epeg_2d != 1) return fail(RRT_E_INVALID, "epeg_2d must be 0 or 1");
   }
   if (c->cr_msa) {
     if (c->crmsa_k < 1 || c->crmsa_k > RRT_MAX_CRMSA_K)
@@ -358,9 +361,29 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
     if (!s_.skip()) RRT_CUDA(rrt::launch_ln_partition(x, norm_w, norm_b, ws_z, g, D, st), "ln_partition"); }
   { StageScope s_(kStQkvGemm, st);
     if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws_z, wq, ws_qkv, true, g.Np, 3 * D, D, e1, st), "qkv gemm"); }
+  // EPEG ablation variants (epeg_variants.cu): the depthwise conv on V replaces the conv on the logit map
+  const bool value_pe = c->epeg && c->epeg_type != RRT_EPEG_ATTN;
+  const bool epeg2d_attn = c->epeg && c->epeg_type == RRT_EPEG_ATTN && c->epeg_2d;
+  if (value_pe || epeg2d_attn) {
+    if (!a->pe_w) return fail(RRT_E_INVALID, "epeg: pe_w missing");
+    if (tr.tape) return fail(RRT_E_INVALID, "the EPEG ablation variants (epeg_2d / epeg_type != attn) are inference only");
+    if (g.rs * g.rs != g.P) return fail(RRT_E_INVALID, "epeg variants need square regions");
+  }
+  if (value_pe) {   // pe from the ORIGINAL v into the (now free) z buffer; value_bf adds it to v before the attention
+    StageScope s_(kStOther, st, c->epeg_type == RRT_EPEG_VALUE_BF ? 2 : 1);
+    RRT_CUDA(rrt::launch_epeg_value_pe(ws_qkv, a->pe_w, a->pe_b, ws_z, g, D, c->n_heads, c->epeg_k,
+                                       c->epeg_2d ? c->epeg_k : 1, st), "epeg value conv");
+    if (c->epeg_type == RRT_EPEG_VALUE_BF)
+      RRT_CUDA(rrt::launch_epeg_value_add(ws_qkv, 3 * D, 2 * D, ws_z, g.Np, D, st), "epeg value_bf add");
+  }
   { StageScope s_(kStRmsaAttn, st);
-    const float* taps = c->epeg ? a->pe_w : nullptr;
+    const float* taps = (c->epeg && !value_pe && !epeg2d_attn) ? a->pe_w : nullptr;
     if (s_.skip()) {
+    } else if (epeg2d_attn) {
+      if (!rrt::rmsa_attention_epeg2d_supported(g, D, c->n_heads, c->epeg_k))
+        return fail(RRT_E_INVALID, "epeg_2d on the logit map covers regions of at most 160 tokens");
+      RRT_CUDA(rrt::launch_rmsa_attention_epeg2d(ws_qkv, a->pe_w, ws_o, g, D, c->n_heads, c->epeg_k, st),
+               "rmsa attention (epeg_2d)");
     } else if ((rrt::g_attn_tc05 == 2 || (rrt::g_attn_tc05 == 1 && g.P > 128)) &&
                rrt::rmsa_attention_tc05_supported(g, D, c->n_heads, taps ? c->epeg_k : 0))
       RRT_CUDA(rrt::launch_rmsa_attention_tc05(ws_qkv, taps, ws_o, g, D, c->n_heads, c->epeg_k, st),
@@ -371,6 +394,10 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
     else
       RRT_CUDA(rrt::launch_rmsa_attention(ws_qkv, taps, ws_o, g, D, c->n_heads, c->epeg_k, st),
                "rmsa attention (flash)"); }
+  if (value_pe && c->epeg_type == RRT_EPEG_VALUE_AF) {
+    StageScope s_(kStOther, st);
+    RRT_CUDA(rrt::launch_epeg_value_add(ws_o, D, 0, ws_z, g.Np, D, st), "epeg value_af add");
+  }
   rrt::GemmEpilogue e2;
   e2.mode = tr.drop_p > 0.f ? rrt::kEpiResidualUnpartDrop : rrt::kEpiResidualUnpart;
   e2.drop = rrt::dropout_make(tr.drop_p, tr.seed, (unsigned)layer);
@@ -1199,6 +1226,8 @@ bool wgrad_mn() {
 int check_backward_support(const rrt_config* c, int64_t L) {
   if (c->pos != RRT_POS_NONE) return fail(RRT_E_INVALID, "backward: PEG / PPEG (ablation) is not covered");
   if (c->ffn) return fail(RRT_E_INVALID, "backward: the FFN ablation is not covered");
+  if (c->epeg && c->n_rmsa_layers > 0 && (c->epeg_2d || c->epeg_type != RRT_EPEG_ATTN))
+    return fail(RRT_E_INVALID, "backward: the EPEG ablation variants (epeg_2d / epeg_type != attn) are not covered");
   if (c->cr_msa && c->crmsa_mlp && ((c->dim / 4) % 128 != 0 || !wgrad_mn()))
     return fail(RRT_E_INVALID, "backward: crmsa_mlp needs dim in {512, 1024} (and the default MN-major weight-gradient path)");
   if (c->n_rmsa_layers == 0 && !c->cr_msa) return fail(RRT_E_INVALID, "backward: encoder has no block");

@@ -126,6 +126,14 @@ cudaError_t launch_crmsa_front_split(const float* x1, const float* gamma, const 
                                      const float* phi, float2* stats, float* logits,
                                      __half* landmarks, float2* rstat, const Grid& grid, int D, int k,
                                      cudaStream_t stream, const float* rs_part = nullptr, int rs_parts = 0);
+// epeg_variants.cu: EPEG ablations (modules/rmsa.py:72-87,104-129), inference only
+cudaError_t launch_epeg_value_pe(const __half* qkv, const float* w, const float* bias, __half* pe, const Grid& grid,
+                                 int D, int heads, int k, int kw, cudaStream_t stream);
+cudaError_t launch_epeg_value_add(__half* dst, int ld, int col0, const __half* pe, int rows, int D,
+                                  cudaStream_t stream);
+bool rmsa_attention_epeg2d_supported(const Grid& grid, int D, int heads, int k);
+cudaError_t launch_rmsa_attention_epeg2d(const __half* qkv, const float* taps, __half* o, const Grid& grid, int D,
+                                         int heads, int k, cudaStream_t stream);
 // landmark_chain.cu: the whole landmark MHA (QKV projection, attention, output projection) as ONE cluster
 // kernel, CTA = head; head_dim 64, heads <= 8.  lm / lo f16 [k*64, D], lout fp32 [k*64, D]; lqkv (nullable):
 // f16 [k*64, 3D] copy of the projected q|k|v rows for the training tape.

@@ -41,13 +41,15 @@ class _ParamHolder(nn.Module):
 class InnerAttention(_ParamHolder):
     """Parameters of modules/rmsa.py:56-89: ``qkv``, ``proj`` and the EPEG conv ``pe``."""
 
-    def __init__(self, dim, num_heads, qkv_bias, epeg, epeg_k, epeg_bias):
+    def __init__(self, dim, num_heads, qkv_bias, epeg, epeg_k, epeg_bias, epeg_2d=False, epeg_type='attn'):
         super().__init__()
         self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
         self.proj = nn.Linear(dim, dim)
         if epeg:
-            self.pe = nn.Conv2d(num_heads, num_heads, (epeg_k, 1), padding=(epeg_k // 2, 0),
-                                groups=num_heads, bias=epeg_bias)
+            # modules/rmsa.py:76-87: per-head conv on the logit map, or per-channel conv on V (value_bf / value_af)
+            ch = num_heads if epeg_type == 'attn' else dim
+            ks, pad = (epeg_k, epeg_k // 2) if epeg_2d else ((epeg_k, 1), (epeg_k // 2, 0))
+            self.pe = nn.Conv2d(ch, ch, ks, padding=pad, groups=ch, bias=epeg_bias)
         else:
             self.pe = None
 
@@ -55,9 +57,9 @@ class InnerAttention(_ParamHolder):
 class RegionAttention(_ParamHolder):
     """modules/rmsa.py:152-173 (``RegionAttntion``)."""
 
-    def __init__(self, dim, num_heads, qkv_bias, epeg, epeg_k, epeg_bias):
+    def __init__(self, dim, num_heads, qkv_bias, epeg, epeg_k, epeg_bias, epeg_2d=False, epeg_type='attn'):
         super().__init__()
-        self.attn = InnerAttention(dim, num_heads, qkv_bias, epeg, epeg_k, epeg_bias)
+        self.attn = InnerAttention(dim, num_heads, qkv_bias, epeg, epeg_k, epeg_bias, epeg_2d, epeg_type)
 
 
 class CrossRegionAttention(_ParamHolder):
@@ -200,8 +202,8 @@ class RRTEncoder(nn.Module):
         epeg_type = kwargs.pop('epeg_type', 'attn')
         epeg_bias = kwargs.pop('epeg_bias', True)
         region_attn = kwargs.pop('region_attn', 'native')
-        if epeg and (epeg_2d or epeg_type != 'attn'):
-            raise NotImplementedError("epeg_2d / epeg_type != 'attn' (ablations) are not built")
+        if epeg_type not in ('attn', 'value_bf', 'value_af'):
+            raise NotImplementedError(f"epeg_type={epeg_type!r}: 'attn', 'value_bf' and 'value_af' are built")
         if region_attn != 'native':
             raise NotImplementedError("region_attn != 'native' (ablation) is not built")
         if kwargs:
@@ -219,7 +221,8 @@ class RRTEncoder(nn.Module):
         self.pos_pos = pos_pos
         self.norm = nn.LayerNorm(mlp_dim)
         self.layers = nn.Sequential(*[
-            TransLayer(mlp_dim, RegionAttention(mlp_dim, n_heads, qkv_bias, epeg, epeg_k, epeg_bias),
+            TransLayer(mlp_dim, RegionAttention(mlp_dim, n_heads, qkv_bias, epeg, epeg_k, epeg_bias,
+                                                bool(epeg_2d), epeg_type),
                        ffn, ffn_act, mlp_ratio, drop_out)
             for _ in range(n_layers - 1)])
         self.cr_msa = (TransLayer(mlp_dim, CrossRegionAttention(mlp_dim, crmsa_heads, qkv_bias,
@@ -245,6 +248,9 @@ class RRTEncoder(nn.Module):
         cfg.pos_pos, cfg.peg_k, cfg.peg_1d = int(pos_pos), int(peg_k), int(bool(peg_1d))
         cfg.ffn, cfg.ffn_hidden = int(bool(ffn)), int(mlp_dim * mlp_ratio) if ffn else 0
         cfg.ffn_act = cabi.RRT_ACT_GELU if ffn_act == 'gelu' else cabi.RRT_ACT_RELU
+        cfg.epeg_2d = int(bool(epeg_2d))
+        cfg.epeg_type = {'attn': cabi.RRT_EPEG_ATTN, 'value_bf': cabi.RRT_EPEG_VALUE_BF,
+                         'value_af': cabi.RRT_EPEG_VALUE_AF}[epeg_type]
         self._cfg = cfg
         self._crmsa_mlp = bool(crmsa_mlp)
         self._shadow = {}
@@ -326,6 +332,7 @@ class RRTEncoder(nn.Module):
         dst.qkv_w, dst.qkv_b = p(inner.qkv.weight, device), p(inner.qkv.bias, device)
         dst.proj_w, dst.proj_b = p(inner.proj.weight, device), p(inner.proj.bias, device)
         dst.pe_w = p(inner.pe.weight, device) if inner.pe is not None else None
+        dst.pe_b = p(inner.pe.bias, device) if inner.pe is not None and inner.pe.bias is not None else None
         if shadows:
             dst.qkv_w_f16 = self._f16_shadow(inner.qkv.weight)
             dst.proj_w_f16 = self._f16_shadow(inner.proj.weight)

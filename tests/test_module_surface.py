@@ -20,6 +20,9 @@ VARIANTS = [
     dict(pos='peg', peg_k=5, peg_1d=True, peg_bias=False, n_layers=3),
     dict(ffn=True),
     dict(ffn=True, ffn_act='relu', mlp_ratio=2.0, mlp_dim=256, n_layers=3, cr_msa=False),
+    dict(epeg_2d=True, epeg_k=5),
+    dict(epeg_type='value_bf', epeg_k=7),
+    dict(epeg_type='value_af', epeg_2d=True, epeg_k=3, epeg_bias=False),
 ]
 
 
@@ -72,9 +75,7 @@ def test_unsupported_options_raise_loudly():
     with pytest.raises(ValueError):
         RRTEncoder(ffn=True, mlp_ratio=0.3)
     with pytest.raises(NotImplementedError):
-        RRTEncoder(epeg_2d=True)
-    with pytest.raises(NotImplementedError):
-        RRTEncoder(epeg_type='value_bf')
+        RRTEncoder(epeg_type='value_xx')
     with pytest.raises(ValueError):
         RRTEncoder(epeg_k=4)
     with pytest.raises(TypeError):
