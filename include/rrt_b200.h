@@ -309,8 +309,9 @@ RRT_API int rrt_attn_pool_forward(const float* h, int64_t L, int32_t dim, int32_
  * atomics; weight gradients are overwritten).  Tensor-core operands of the backward GEMMs are fp16
  * with automatic per-stage power-of-two scaling (csrc/backward.cuh), accumulators fp32.
  * crmsa_mlp (logits = phi.2 tanh(phi.0 z)): gradients of both weights; needs dim 512 or 1024.
+ * PEG / PPEG (pos != none): gradients of the conv kernels and biases; PPEG needs bags of >= 37 tokens.
  * Not covered (RRT_E_INVALID): crmsa_k > 8, R-MSA head_dim other than 32 / 64, CR-MSA head_dim 128, regions > 256
- * tokens, PEG / PPEG, FFN. */
+ * tokens, FFN, the EPEG ablation variants. */
 typedef struct rrt_attn_grads {
   float* qkv_w;  /* [3D, D] */
   float* qkv_b;  /* [3D] or NULL */
@@ -331,6 +332,8 @@ typedef struct rrt_grads {
   rrt_attn_grads cr_attn;
   float* cr_phi_w1; /* crmsa_mlp: phi.0.weight [D/4, D] */
   float* cr_phi_w2; /* crmsa_mlp: phi.2.weight [k, D/4] */
+  float* pos_w[3];  /* PEG: proj.weight; PPEG: proj / proj1 / proj2 .weight ([D,1,k,k] or [D,1,k,1]); overwritten */
+  float* pos_b[3];  /* the matching biases [D] or NULL */
 } rrt_grads;
 
 RRT_API int rrt_train_tape_bytes(const rrt_config* cfg, int64_t L, size_t* bytes);

@@ -106,6 +106,10 @@ TRAIN_CASES = [
     ("train_n700_p0", 700, dict(), 0.0, 0),   # eval-arithmetic backward pinned against reference autograd
     # crmsa_mlp (phi = Linear -> tanh -> Linear, modules/rmsa.py:248-252; README.md:119 trains with it)
     ("train_mlp_k5_p10", 600, dict(crmsa_mlp=True, crmsa_k=5, epeg_k=9), 0.1, 31337),
+    # PEG / PPEG backward (modules/emb_position.py:24-82): in front of the first layer / between layers 0 and 1
+    ("train_ppeg_front_p10", 600, dict(pos="ppeg", pos_pos=-1, epeg_k=9), 0.1, 4242),
+    ("train_peg_k5_between_d256", 500, dict(pos="peg", pos_pos=0, peg_k=5, n_layers=3, mlp_dim=256, n_heads=4,
+                                            crmsa_heads=4, peg_bias=False, all_shortcut=True, epeg_k=5), 0.1, 99),
 ]
 GRAD_SEED = 43
 # Full RRTMIL train step: name, L, input_dim, n_classes, da_act, da_bias, label, encoder

@@ -88,6 +88,7 @@ class RrtGrads(C.Structure):
         ("cr_norm_w", c_float_p), ("cr_norm_b", c_float_p), ("cr_phi", c_float_p),
         ("cr_attn", RrtAttnGrads),
         ("cr_phi_w1", c_float_p), ("cr_phi_w2", c_float_p),
+        ("pos_w", c_float_p * 3), ("pos_b", c_float_p * 3),
     ]
 
 

@@ -1168,6 +1168,9 @@ struct BwdWorkspace {
   float* dpre;     // [Np_c, D/4] gradient wrt the tanh pre-activation
   __half* dpre16;  // [Np_c, D/4] scaled
   __half* dzc16;   // [Np_c, D]   gradient wrt LN_cr(x1) through the MLP, scaled
+  // PEG / PPEG only
+  float* gp;       // [L, D] gradient wrt the positional encoding's output
+  float* peg_dw;   // folded weight gradient (peg_scratch_floats)
   size_t bytes;
 };
 
@@ -1214,6 +1217,9 @@ bool carve_bwd(const rrt_config* c, int64_t L, void* base, BwdWorkspace* b) {
   b->dpre = (float*)take(mlp ? np_c * (D / 4) * 4 : 0);
   b->dpre16 = (__half*)take(mlp ? np_c * (D / 4) * 2 : 0);
   b->dzc16 = (__half*)take(mlp ? np_c * D * 2 : 0);
+  const bool pos = c->pos != RRT_POS_NONE;
+  b->gp = (float*)take(pos ? (size_t)L * D * 4 : 0);
+  b->peg_dw = (float*)take(pos ? rrt::peg_scratch_floats((int)D, c->peg_k, c->pos == RRT_POS_PPEG, c->peg_1d != 0) * 4 : 0);
   b->bytes = off + 256;
   return true;
 }
@@ -1224,7 +1230,11 @@ bool wgrad_mn() {
 }
 
 int check_backward_support(const rrt_config* c, int64_t L) {
-  if (c->pos != RRT_POS_NONE) return fail(RRT_E_INVALID, "backward: PEG / PPEG (ablation) is not covered");
+  if (c->pos != RRT_POS_NONE) {
+    if (c->n_rmsa_layers == 0) return fail(RRT_E_INVALID, "backward: PEG / PPEG without an R-MSA layer is not covered");
+    if (c->pos == RRT_POS_PPEG && ceil_sqrt(L) < 7)
+      return fail(RRT_E_INVALID, "backward: PPEG on bags below 37 tokens (zero-extended 7x7 grid) is not covered");
+  }
   if (c->ffn) return fail(RRT_E_INVALID, "backward: the FFN ablation is not covered");
   if (c->epeg && c->n_rmsa_layers > 0 && (c->epeg_2d || c->epeg_type != RRT_EPEG_ATTN))
     return fail(RRT_E_INVALID, "backward: the EPEG ablation variants (epeg_2d / epeg_type != attn) are not covered");
@@ -1402,12 +1412,18 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
   rrt::Grid gg{};
   if (!make_grid(L, c->region_num, c->region_size, c->min_region_num, c->min_region_ratio, &gg))
     return fail(RRT_E_INVALID, "bad geometry");
+  // positional encoding (ablation): applied in front of R-MSA layer `pos_at` (modules/rrt.py:181-188)
+  const int pos_at = c->pos == RRT_POS_NONE ? -1 : (c->pos_pos == -1 ? 0 : (nl >= 2 ? 1 : -1));
+  if (pos_at >= 0 && (!gr->pos_w[0] || (c->pos == RRT_POS_PPEG && (!gr->pos_w[1] || !gr->pos_w[2]))))
+    return fail(RRT_E_INVALID, "NULL gradient buffer (pos_embedding)");
   for (int i = nl - 1; i >= 0; --i) {
     const rrt_attn_grads* ga = &gr->layer_attn[i];
     if (!gr->layer_norm_w[i] || !gr->layer_norm_b[i] || !ga->qkv_w || !ga->proj_w || !ga->proj_b ||
         (c->qkv_bias && !ga->qkv_b) || (c->epeg && !ga->pe_w))
       return fail(RRT_E_INVALID, "NULL gradient buffer");
-    const float* x_in = i > 0 ? tp.xs[i - 1] : x;
+    const bool peg_here = i == pos_at;
+    const float* x_prev = i > 0 ? tp.xs[i - 1] : x;          // what the layer (or the encoding in front of it) read
+    const float* x_in = peg_here ? tp.pe_out : x_prev;
     { StageScope s_(kStBwdPrep, st);
       RRT_CUDA(rrt::launch_grad_partition(g, gg, gg.Np, D, &b.amax[am], b.dy, wgrad_mn() ? nullptr : b.dyT,
                                           ga->proj_b, st,
@@ -1417,13 +1433,26 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
                                        c->n_heads, c->epeg != 0, &b.amax[am], b, st);
     if (rc) return rc;
     float* out = i == 0 ? dx : (g == b.ga ? b.gb : b.ga);
+    const float* shortcut = (i == 0 && c->all_shortcut) ? b.dh : nullptr;   // d/dx of "+ x" (modules/rrt.py:195)
     { StageScope s_(kStBwdLn, st);
       RRT_CUDA(rrt::launch_ln_backward(x_in, nullptr, w->layer_norm_w[i], b.dz, true, &b.amax[am], g,
-                                       (i == 0 && c->all_shortcut) ? b.dh : nullptr, out,
+                                       peg_here ? nullptr : shortcut, peg_here ? b.gp : out,
                                        gr->layer_norm_w[i], gr->layer_norm_b[i], &b.amax[am + 1], gg, D,
                                        st), "layer norm backward"); }
-    g = out;
     ++am;
+    if (peg_here) {   // gradient wrt the encoding's output -> its input (+ the shortcut) and its conv parameters
+      StageScope s_(kStOther, st, 5);
+      cudaError_t e = rrt::launch_peg_backward(x_prev, b.gp, shortcut, out, (int)L, D, c->peg_k,
+                                               c->pos == RRT_POS_PPEG, c->peg_1d != 0, tp.pe_w, b.peg_dw,
+                                               gr->pos_w, gr->pos_b, st);
+      if (e == cudaErrorNotSupported) return fail(RRT_E_INVALID, "backward: PPEG on a zero-extended grid is not covered");
+      if (e != cudaSuccess) return fail_cuda(e, "pos_embedding backward");
+      if (i > 0) {     // the next layer down scales its gradient rows by the amax of `out`
+        ++am;
+        RRT_CUDA(rrt::launch_amax(out, (size_t)L * D, &b.amax[am], st), "amax");
+      }
+    }
+    g = out;
   }
   return RRT_OK;
 }

@@ -157,6 +157,11 @@ cudaError_t launch_crmsa_dispatch(const float* x1, const float* x0, const float*
 size_t peg_scratch_floats(int D, int peg_k, bool ppeg, bool conv_1d);
 cudaError_t launch_peg(const float* x, float* out, int L, int D, int peg_k, bool ppeg, bool conv_1d,
                        const float* const* w, const float* const* b, float* scratch, cudaStream_t stream);
+// backward of launch_peg: dx (+ dres), dw[j] / db[j] in the reference's parameter layout; weff = the forward's
+// folded kernel (its scratch), scratch = another peg_scratch_floats floats
+cudaError_t launch_peg_backward(const float* x, const float* dy, const float* dres, float* dx, int L, int D,
+                                int peg_k, bool ppeg, bool conv_1d, const float* weff, float* scratch,
+                                float* const* dw, float* const* db, cudaStream_t stream);
 
 // ---- optim.cu: multi-tensor Adam / AdamW step, torch.optim semantics ----------
 cudaError_t launch_adam(float* const* p, const float* const* g, float* const* m, float* const* v,

@@ -247,4 +247,139 @@ cudaError_t launch_peg(const float* x, float* out, int L, int D, int peg_k, bool
   return cudaGetLastError();
 }
 
+// ---- backward (autograd of modules/emb_position.py:36-58,66-82) ------------------------------------------------
+// forward:  out[o] = b_eff + sum_tap w_eff[tap] * in(o + off(tap)),  o < L,  in(cell) = x[cell] (cell < L),
+//           x[cell - L] (wrap cells L <= cell < Hn^2), 0 otherwise
+//   d in(s)      = sum_tap w_eff[tap] * dy[s - off(tap)]            (dy = 0 for cells >= L: the fill is cropped)
+//   dx[t]        = d in(t) + d in(L + t) [t < Hn^2 - L]  (+ dres[t])
+//   dw_eff[tap]  = sum_{o < L} dy[o] * in(o + off(tap)),   db_eff = sum_o dy[o]
+// and every conv of the fold (k; PPEG also 5 and 3) reads ITS taps out of dw_eff; all of them get db_eff.
+namespace {
+__global__ void __launch_bounds__(256) peg_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ weff,
+                                                         const float* __restrict__ dres, float* __restrict__ dx,
+                                                         PegGeom g) {
+  const int q4 = g.D / 4;
+  const long long items = (long long)g.L * q4;
+  const int wrap = g.Hn * g.Hn - g.L;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(it / q4), q = (int)(it - (long long)t * q4);
+    float4 acc = dres ? __ldg(reinterpret_cast<const float4*>(dres + (size_t)t * g.D) + q)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int rep = 0; rep < 2; ++rep) {
+      if (rep == 1 && t >= wrap) break;
+      const int s = rep == 0 ? t : g.L + t;
+      const int r = s / g.Hg, c = s - r * g.Hg;
+      for (int ky = 0; ky < g.K; ++ky) {
+        const int ro = r - (ky - g.K / 2);
+        if (ro < 0 || ro >= g.Hg) continue;
+        for (int kx = 0; kx < g.KW; ++kx) {
+          const int co = g.KW == 1 ? c : c - (kx - g.K / 2);
+          if (co < 0 || co >= g.Hg) continue;
+          const int o = ro * g.Hg + co;
+          if (o >= g.L) continue;
+          const float4 v = __ldg(reinterpret_cast<const float4*>(dy + (size_t)o * g.D) + q);
+          const float4 w = __ldg(reinterpret_cast<const float4*>(weff + (size_t)(ky * g.KW + kx) * g.D) + q);
+          acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y);
+          acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w);
+        }
+      }
+    }
+    reinterpret_cast<float4*>(dx + (size_t)t * g.D)[q] = acc;
+  }
+}
+
+// grid (K*KW + 1 taps [the last = bias], D / 128 slabs, cell chunks); 256 threads = 8 warps x 32 channel quads
+__global__ void __launch_bounds__(256) peg_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                         float* __restrict__ dweff, PegGeom g) {
+  __shared__ float4 red[8][32];
+  const int tap = blockIdx.x, slab = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = slab * 32 + lane;       // channel quad
+  const bool is_bias = tap == g.K * g.KW;
+  const int ky = is_bias ? 0 : tap / g.KW, kx = is_bias ? 0 : tap - ky * g.KW;
+  const int oy = is_bias ? 0 : ky - g.K / 2, ox = (is_bias || g.KW == 1) ? 0 : kx - g.K / 2;
+  const int wrap_end = g.Hn * g.Hn;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q * 4 < g.D) {
+    for (int o = blockIdx.z * 8 + warp; o < g.L; o += gridDim.z * 8) {
+      const float4 d = __ldg(reinterpret_cast<const float4*>(dy + (size_t)o * g.D) + q);
+      float4 v = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (!is_bias) {
+        const int r = o / g.Hg + oy, c = o % g.Hg + ox;
+        if (r < 0 || r >= g.Hg || c < 0 || c >= g.Hg) continue;
+        const int cell = r * g.Hg + c;
+        const int src = cell < g.L ? cell : (cell < wrap_end ? cell - g.L : -1);
+        if (src < 0) continue;
+        v = __ldg(reinterpret_cast<const float4*>(x + (size_t)src * g.D) + q);
+      }
+      acc.x = fmaf(d.x, v.x, acc.x); acc.y = fmaf(d.y, v.y, acc.y);
+      acc.z = fmaf(d.z, v.z, acc.z); acc.w = fmaf(d.w, v.w, acc.w);
+    }
+  }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && q * 4 < g.D) {
+    float4 s = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { s.x += red[w][lane].x; s.y += red[w][lane].y; s.z += red[w][lane].z; s.w += red[w][lane].w; }
+    float* dst = dweff + (size_t)tap * g.D + q * 4;
+    atomicAdd(dst, s.x); atomicAdd(dst + 1, s.y); atomicAdd(dst + 2, s.z); atomicAdd(dst + 3, s.w);
+  }
+}
+
+// dw_j [D, 1, k_j, kw_j] (reference layout) and db_j [D] from dw_eff [K*KW + 1][D]
+__global__ void __launch_bounds__(256) peg_bwd_unfold_kernel(const float* __restrict__ dweff, float* __restrict__ dw,
+                                                             float* __restrict__ db, int k, int conv_1d, int D, int K,
+                                                             int KW) {
+  const int kw = conv_1d ? 1 : k, n = D * k * kw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + (db ? D : 0); i += gridDim.x * blockDim.x) {
+    if (i >= n) { db[i - n] = dweff[(size_t)K * KW * D + (i - n)]; continue; }
+    const int c = i / (k * kw), y = (i / kw) % k, x = i % kw;
+    const int ky = y - k / 2 + K / 2, kx = conv_1d ? 0 : x - k / 2 + K / 2;
+    dw[i] = dweff[(size_t)(ky * KW + kx) * D + c];
+  }
+}
+}  // namespace
+
+// x: the forward's input [L, D]; dy: gradient wrt the forward's output; dres (nullable): added to dx (the
+// all_shortcut gradient); weff: the forward's folded kernel (the scratch of launch_peg, untouched since);
+// scratch: peg_scratch_floats floats.  dw[j] / db[j]: gradients in the reference's parameter layout (db nullable).
+cudaError_t launch_peg_backward(const float* x, const float* dy, const float* dres, float* dx, int L, int D,
+                                int peg_k, bool ppeg, bool conv_1d, const float* weff, float* scratch,
+                                float* const* dw, float* const* db, cudaStream_t stream) {
+  if (D % 4 || L < 1 || peg_k < 1 || peg_k % 2 == 0 || !dw[0] || !weff || !scratch) return cudaErrorInvalidValue;
+  if (ppeg && (!dw[1] || !dw[2])) return cudaErrorInvalidValue;
+  PegGeom g;
+  g.L = L; g.D = D;
+  g.Hn = ceil_sqrt_i(L);
+  g.Hg = (ppeg && g.Hn < 7) ? 7 : g.Hn;
+  if (g.Hg != g.Hn) return cudaErrorNotSupported;   // PPEG's zero extension of grids below 7 x 7 (L < 37)
+  g.K = ppeg && peg_k < 5 ? 5 : peg_k;
+  g.KW = conv_1d ? 1 : g.K;
+  long long items = (long long)L * (D / 4);
+  long long blocks = (items + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  peg_bwd_dx_kernel<<<(int)blocks, 256, 0, stream>>>(dy, weff, dres, dx, g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int taps = g.K * g.KW + 1;
+  e = cudaMemsetAsync(scratch, 0, (size_t)taps * D * sizeof(float), stream);
+  if (e != cudaSuccess) return e;
+  int zc = (L + 8 * 32 - 1) / (8 * 32);
+  if (zc > 64) zc = 64;
+  if (zc < 1) zc = 1;
+  peg_bwd_dw_kernel<<<dim3(taps, (D + 127) / 128, zc), 256, 0, stream>>>(x, dy, scratch, g);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int ks[3] = {peg_k, 5, 3};
+  for (int j = 0; j < (ppeg ? 3 : 1); ++j) {
+    const int n = D * ks[j] * (conv_1d ? 1 : ks[j]) + D;
+    peg_bwd_unfold_kernel<<<(n + 255) / 256, 256, 0, stream>>>(scratch, dw[j], db ? db[j] : nullptr, ks[j],
+                                                               conv_1d ? 1 : 0, D, g.K, g.KW);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 }  // namespace rrt

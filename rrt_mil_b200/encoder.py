@@ -404,6 +404,10 @@ class RRTEncoder(nn.Module):
             g.cr_phi = ptr("cr_msa.attn.phi")
             g.cr_phi_w1, g.cr_phi_w2 = ptr("cr_msa.attn.phi.0.weight"), ptr("cr_msa.attn.phi.2.weight")
             attn("cr_msa.attn.attn.", g.cr_attn)
+        if self._cfg.pos != cabi.RRT_POS_NONE:
+            for j, conv in enumerate(("proj", "proj1", "proj2")):
+                g.pos_w[j] = ptr(f"pos_embedding.{conv}.weight")
+                g.pos_b[j] = ptr(f"pos_embedding.{conv}.bias")
         return g
 
     def _named_param_cache(self):
@@ -449,8 +453,6 @@ class RRTEncoder(nn.Module):
             if not allow_grad:
                 raise NotImplementedError("forward_bags is inference-only: call it under "
                                           "torch.no_grad(), or use forward() for autograd")
-            if self._cfg.pos != cabi.RRT_POS_NONE:
-                raise NotImplementedError("backward through the PEG / PPEG ablation is not built")
             if self._cfg.ffn:
                 raise NotImplementedError("backward through the FFN ablation is not built")
             # limits that depend on the BAG, not only on the configuration (region size, head_dim): checked here,

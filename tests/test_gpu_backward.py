@@ -141,6 +141,10 @@ ENC_CASES = [
     ("crmsa_heads1", 700, dict(crmsa_heads=1)),                        # BRCA-R50 / LUAD-PLIP recipes: head_dim 512
     ("nsclc_plip_mlp_h1", 500, dict(crmsa_mlp=True, crmsa_heads=1, crmsa_k=5)),   # README.md:119
     ("crmsa_heads1_d256", 300, dict(mlp_dim=256, n_heads=4, crmsa_heads=1, crmsa_k=4)),
+    ("ppeg_front", 700, dict(pos="ppeg", pos_pos=-1)),                 # PEG / PPEG backward (f3)
+    ("peg_between_3layers_d256", 900, dict(pos="peg", pos_pos=0, n_layers=3, peg_k=5, mlp_dim=256, n_heads=4,
+                                           crmsa_heads=4)),
+    ("ppeg_1d_shortcut", 400, dict(pos="ppeg", pos_pos=-1, peg_1d=True, all_shortcut=True)),
     ("n9000", 9000, dict()),
     ("n50000_g16", 50000, dict(region_num=16)),     # BASELINE configs[3] shape: P = 196 (R-MSA), 784 (CR-MSA)
 ]
@@ -244,7 +248,7 @@ def test_training_dropout_is_reproducible_under_manual_seed():
 
 
 def test_backward_rejects_unsupported():
-    cfg = O.EncoderConfig(pos="ppeg", pos_pos=-1)       # PEG / PPEG have no backward
+    cfg = O.EncoderConfig(ffn=True)                     # the FFN ablation has no backward
     m = G.make_encoder(cfg, O.make_weights(cfg, 3))
     x = O.make_bag(200, 512, 4).float().cuda().requires_grad_()
     with pytest.raises(NotImplementedError):
