@@ -344,9 +344,13 @@ RRT_API int rrt_train_tape_bytes(const rrt_config* cfg, int64_t L, size_t* bytes
  * order), landmark MHA of CR-MSA -> RRT_DROP_STREAM_CRMSA (mask over [k*64, D]).  It is the reference's
  * dropout in distribution, not torch's Philox stream; rrt_dropout_mask exposes it for parity tests. */
 #define RRT_DROP_STREAM_CRMSA 64
+/* branch_scale (HOST array of n_rmsa_layers + 1 floats: the R-MSA layers, then CR-MSA; NULL = all ones):
+ * stochastic depth of this step (drop_path, modules/rrt.py:102,125: x + drop_path(attn(norm(x))) with a batch
+ * of one bag): 0 = the block's branch is dropped (x passes through), otherwise the factor 1 / keep_prob on the
+ * branch.  The caller draws the Bernoulli variables and passes the same array to rrt_encoder_backward. */
 RRT_API int rrt_encoder_forward_train(const rrt_config* cfg, const rrt_weights* w, const float* x,
                                       float* out, int64_t L, void* tape, size_t tape_bytes,
-                                      float drop_p, uint64_t seed, void* stream);
+                                      float drop_p, uint64_t seed, const float* branch_scale, void* stream);
 /* out[i] = keep(i) / (1 - drop_p) for i < n (n % 4 == 0): the factor the forward multiplies element i by. */
 RRT_API int rrt_dropout_mask(float* out, int64_t n, float drop_p, uint64_t seed, uint32_t mask_stream,
                              void* stream);
@@ -363,7 +367,8 @@ RRT_API int rrt_backward_workspace_bytes(const rrt_config* cfg, int64_t L, size_
 RRT_API int rrt_encoder_backward(const rrt_config* cfg, const rrt_weights* w, const float* x,
                                  const float* dout, int64_t L, const void* tape, size_t tape_bytes,
                                  const rrt_grads* grads, float* dx, void* workspace,
-                                 size_t workspace_bytes, float drop_p, uint64_t seed, void* stream);
+                                 size_t workspace_bytes, float drop_p, uint64_t seed, const float* branch_scale,
+                                 void* stream);
 
 /* Building blocks of the backward pass, exposed for the parity tests.
  * rrt_attention_backward: qkv [R*P, 3D] fp16 and o [R*P, D] fp16 as the forward wrote them,

@@ -110,6 +110,12 @@ TRAIN_CASES = [
     ("train_ppeg_front_p10", 600, dict(pos="ppeg", pos_pos=-1, epeg_k=9), 0.1, 4242),
     ("train_peg_k5_between_d256", 500, dict(pos="peg", pos_pos=0, peg_k=5, n_layers=3, mlp_dim=256, n_heads=4,
                                             crmsa_heads=4, peg_bias=False, all_shortcut=True, epeg_k=5), 0.1, 99),
+    # stochastic depth (drop_path, modules/rrt.py:102,125): trailing (rate, keep per block).  The reference's
+    # DropPath modules are replaced by the fixed outcome of the Bernoulli draw (0 or 1 / keep on the branch)
+    ("train_droppath_skip_layer1", 600, dict(n_layers=3, epeg_k=9, all_shortcut=True), 0.1, 5150, (0.2, [1, 0, 1])),
+    ("train_droppath_skip_crmsa_p0", 500, dict(epeg_k=9), 0.0, 0, (0.25, [1, 0])),
+    ("train_droppath_skip_layer0", 550, dict(n_layers=3, epeg_k=9, mlp_dim=256, n_heads=4, crmsa_heads=4), 0.1, 808,
+     (0.1, [0, 1, 1])),
 ]
 GRAD_SEED = 43
 # Full RRTMIL train step: name, L, input_dim, n_classes, da_act, da_bias, label, encoder
@@ -214,7 +220,7 @@ def sample_rows(a, max_rows=MAX_ROWS):
     return a2[::stride].astype(np.float32), stride
 
 
-def crmsa_tie_gap(x, w, cfg, drop):
+def crmsa_tie_gap(x, w, cfg, drop, scales=None):
     """Smallest gap between the two lowest / two highest CR-MSA logits of a region, relative to the
     region's logit range (exact ties between zero pad slots do not count: pads carry no gradient)."""
     if not cfg.cr_msa:
@@ -224,8 +230,10 @@ def crmsa_tie_gap(x, w, cfg, drop):
     for i in range(cfg.n_layers - 1):
         p = f"layers.{i}."
         m = O.dropout_mask(L, D, drop[0], drop[1], i) if drop[0] > 0 else None
-        h = h + O.rmsa_block(O.layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w, p + "attn.", cfg,
-                             "spec", m)
+        sc = 1.0 if scales is None else scales[i]
+        if sc != 0.0:
+            h = h + sc * O.rmsa_block(O.layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w, p + "attn.",
+                                      cfg, "spec", m)
     H, rs, _ = O.grid_geometry(L, 8)
     if rs == 1:
         return float("inf")
@@ -242,13 +250,25 @@ def crmsa_tie_gap(x, w, cfg, drop):
     return float(gaps[gaps > 0].min())
 
 
-def generate_train(name, L, overrides, p, seed):
+class _Scale(torch.nn.Module):
+    def __init__(self, s):
+        super().__init__()
+        self.s = float(s)
+
+    def forward(self, t):
+        return t * self.s
+
+
+def generate_train(name, L, overrides, p, seed, droppath=None):
     cfg = O.EncoderConfig(**overrides)
     w = O.make_weights(cfg, WEIGHT_SEED)
     bag_seed = 7
+    pre_scales = None
+    if droppath is not None:
+        pre_scales = [(1.0 / (1.0 - droppath[0])) if k else 0.0 for k in droppath[1]]
     for _ in range(400):
         x = O.make_bag(L, cfg.mlp_dim, bag_seed, kind="relu")
-        gap = crmsa_tie_gap(x, w, cfg, (p, seed))
+        gap = crmsa_tie_gap(x, w, cfg, (p, seed), pre_scales)
         if gap >= MIN_TIE_GAP:
             break
         if p > 0:
@@ -260,6 +280,14 @@ def generate_train(name, L, overrides, p, seed):
     gout = torch.randn(L, cfg.mlp_dim, generator=torch.Generator().manual_seed(GRAD_SEED), dtype=torch.float64)
     model = shim.build_reference_encoder(cfg, w).train()
     install_dropout_masks(model, cfg, L, p, seed)
+    scales = None
+    if droppath is not None:     # the outcome of every block's DropPath draw, as a fixed factor on its branch
+        rate, keep = droppath
+        scales = [(1.0 / (1.0 - rate)) if k else 0.0 for k in keep]
+        blocks = list(model.layers.children()) + ([model.cr_msa] if cfg.cr_msa else [])
+        assert len(blocks) == len(scales)
+        for blk, sc in zip(blocks, scales):
+            blk.drop_path = _Scale(sc)
     with torch.enable_grad():
         xr = x.clone().requires_grad_()
         y = model(xr.unsqueeze(0))[0]
@@ -276,8 +304,11 @@ def generate_train(name, L, overrides, p, seed):
         out["g:" + n_], _ = sample_rows(g)
         out["gfro:" + n_] = np.array(np.linalg.norm(g))
     np.savez(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
-    return dict(name=name, L=L, config=cfg.to_dict(), drop_out=p, dropout_seed=seed, weight_seed=WEIGHT_SEED,
-                bag_seed=bag_seed, bag_kind="relu", grad_seed=GRAD_SEED, min_crmsa_tie_gap=gap)
+    rec = dict(name=name, L=L, config=cfg.to_dict(), drop_out=p, dropout_seed=seed, weight_seed=WEIGHT_SEED,
+               bag_seed=bag_seed, bag_kind="relu", grad_seed=GRAD_SEED, min_crmsa_tie_gap=gap)
+    if droppath is not None:
+        rec["drop_path"], rec["drop_path_keep"] = droppath[0], [int(k) for k in droppath[1]]
+    return rec
 
 
 def install_pool_dropout_masks(m, L, p, seed):

@@ -305,9 +305,11 @@ def ffn_block(h: torch.Tensor, w: Dict[str, torch.Tensor], prefix: str, cfg: Enc
 
 
 def encoder_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderConfig,
-                    order: str = "reference", drop=None) -> torch.Tensor:
+                    order: str = "reference", drop=None, branch_scale=None) -> torch.Tensor:
     """``RRTEncoder.forward`` for one bag ``x`` [L,D] -> [L,D] (modules/rrt.py:165-202).
-    ``drop=(p, seed)``: training mode with ``drop_out=p`` (proj_drop masks from ``dropout_mask``)."""
+    ``drop=(p, seed)``: training mode with ``drop_out=p`` (proj_drop masks from ``dropout_mask``).
+    ``branch_scale``: one factor per block (R-MSA layers, then CR-MSA) on its residual branch -- stochastic depth
+    (``drop_path``, modules/rrt.py:102,125) for a batch of one: 0 = dropped, 1 / keep otherwise."""
     assert order in ("reference", "spec")
     assert x.dim() == 2 and x.shape[1] == cfg.mlp_dim
     L, D = x.shape
@@ -323,14 +325,18 @@ def encoder_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], cfg: EncoderCon
         if i == 1 and has_pos and cfg.pos_pos == 0:        # modules/rrt.py:186-187
             h = pos_embedding(h, w, cfg)
         p = f"layers.{i}."
-        h = h + rmsa_block(layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w,
-                           p + "attn.", cfg, order, mask(L, i))
+        bs = 1.0 if branch_scale is None else float(branch_scale[i])
+        if bs != 0.0:
+            h = h + bs * rmsa_block(layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w,
+                                    p + "attn.", cfg, order, mask(L, i))
         if cfg.ffn:
             h = ffn_block(h, w, p, cfg)
     if cfg.cr_msa:
         p = "cr_msa."
-        h = h + crmsa_block(layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w,
-                            p + "attn.", cfg, order, mask(cfg.crmsa_k * 64, DROP_STREAM_CRMSA))
+        bs = 1.0 if branch_scale is None else float(branch_scale[cfg.n_layers - 1])
+        if bs != 0.0:
+            h = h + bs * crmsa_block(layer_norm(h, w[p + "norm.weight"], w[p + "norm.bias"]), w,
+                                     p + "attn.", cfg, order, mask(cfg.crmsa_k * 64, DROP_STREAM_CRMSA))
         if cfg.ffn:
             h = ffn_block(h, w, p, cfg)
     if cfg.all_shortcut:

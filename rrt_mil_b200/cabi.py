@@ -113,7 +113,8 @@ SIGNATURES = {
                                           C.c_int64, C.c_int32, _P, C.c_size_t, _P]),
     "rrt_train_tape_bytes": (C.c_int, [C.POINTER(RrtConfig), C.c_int64, C.POINTER(C.c_size_t)]),
     "rrt_encoder_forward_train": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P,
-                                            C.c_int64, _P, C.c_size_t, C.c_float, C.c_uint64, _P]),
+                                            C.c_int64, _P, C.c_size_t, C.c_float, C.c_uint64,
+                                            C.POINTER(C.c_float), _P]),
     "rrt_peg_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.POINTER(c_float_p), C.POINTER(c_float_p), _P]),
     "rrt_linear_wgrad_f16": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
@@ -124,7 +125,7 @@ SIGNATURES = {
     "rrt_backward_workspace_bytes": (C.c_int, [C.POINTER(RrtConfig), C.c_int64, C.POINTER(C.c_size_t)]),
     "rrt_encoder_backward": (C.c_int, [C.POINTER(RrtConfig), C.POINTER(RrtWeights), _P, _P, C.c_int64,
                                        _P, C.c_size_t, C.POINTER(RrtGrads), _P, _P, C.c_size_t,
-                                       C.c_float, C.c_uint64, _P]),
+                                       C.c_float, C.c_uint64, C.POINTER(C.c_float), _P]),
     "rrt_attention_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_int32, _P]),
     "rrt_layernorm_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),

@@ -318,7 +318,12 @@ int f16_weight(const float* w32, const void* shadow, __half* scratch, size_t n, 
 
 // training-mode proj_drop (modules/rmsa.py:70,132): probability and the seed of this step; the mask
 // stream of R-MSA layer i is i, the landmark MHA of CR-MSA uses kCrDropStream
-struct TrainOpts { float drop_p = 0.f; unsigned long long seed = 0; bool tape = false; };
+// branch_scale (host array, one per block: R-MSA layers, then CR-MSA; NULL = all 1): stochastic depth of the step
+// (modules/rrt.py:102,125: x + drop_path(attn(norm(x))), batch of one) -- 0 = the block is skipped, else 1 / keep
+struct TrainOpts {
+  float drop_p = 0.f; unsigned long long seed = 0; bool tape = false; const float* branch_scale = nullptr;
+  float scale_of(int block) const { return branch_scale ? branch_scale[block] : 1.f; }
+};
 constexpr unsigned kCrDropStream = 64;
 
 // CR-MSA reads the rows the LAST R-MSA projection GEMM writes: when nothing sits in between (no FFN, no
@@ -346,6 +351,12 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
   __half* const ws_z = ws.z[layer];
   __half* const ws_qkv = ws.qkv[layer];
   __half* const ws_o = ws.o[layer];
+  const float bscale = tr.scale_of(layer);
+  if (bscale == 0.f) {   // stochastic depth dropped this block: x1 = x
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    RRT_CUDA(cudaMemcpyAsync(x1, x, (size_t)L * c->dim * sizeof(float), cudaMemcpyDeviceToDevice, st), "skip block");
+    return RRT_OK;
+  }
   rrt::Grid g{};
   if (!make_grid(L, c->region_num, c->region_size, c->min_region_num, c->min_region_ratio, &g))
     return fail(RRT_E_INVALID, "bad geometry");
@@ -399,8 +410,9 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
     RRT_CUDA(rrt::launch_epeg_value_add(ws_o, D, 0, ws_z, g.Np, D, st), "epeg value_af add");
   }
   rrt::GemmEpilogue e2;
-  e2.mode = tr.drop_p > 0.f ? rrt::kEpiResidualUnpartDrop : rrt::kEpiResidualUnpart;
   e2.drop = rrt::dropout_make(tr.drop_p, tr.seed, (unsigned)layer);
+  e2.drop.scale *= bscale;   // stochastic depth: 1 / keep on the branch
+  e2.mode = e2.drop.on() ? rrt::kEpiResidualUnpartDrop : rrt::kEpiResidualUnpart;
   e2.bias = a->proj_b;
   e2.resid = x;
   e2.grid = g;
@@ -421,6 +433,13 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   rrt::Grid g{};
   if (!crmsa_grid(L, &g)) return fail(RRT_E_INVALID, "bad geometry");
   const int D = c->dim, k = c->crmsa_k, T = k * g.R;
+  const float bscale = tr.scale_of(c->n_rmsa_layers);
+  if (bscale == 0.f) {   // stochastic depth dropped the CR-MSA branch: out = LN(x1 (+ x0))
+    if (!final_norm) return fail(RRT_E_INVALID, "drop_path with the FFN ablation is not covered");
+    StageScope s_(kStFinalLn, st);
+    RRT_CUDA(rrt::launch_add_layernorm(x1, x0, w->norm_w, w->norm_b, out, (int)L, D, st), "final norm");
+    return RRT_OK;
+  }
   const bool fused_front = rrt::crmsa_landmarks_supported(g, D, k);
   const float* phi = nullptr;
   if (c->crmsa_mlp) {
@@ -485,16 +504,16 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
   static const bool chain_split = [] { const char* e = getenv("RRT_LANDMARK_CHAIN"); return e && !strcmp(e, "split"); }();
   const bool fuse_chain = !chain_split && tc_attn && g.R == 64 && rrt::landmark_chain_supported(k, D, c->crmsa_heads);
   if (fuse_chain) {
-    StageScope s_(kStLmAttn, st, tr.drop_p > 0.f ? 2 : 1);
+    rrt::Dropout ldrop = rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream);
+    ldrop.scale *= bscale;
+    StageScope s_(kStLmAttn, st, ldrop.on() ? 2 : 1);
     if (!s_.skip())
       RRT_CUDA(rrt::launch_landmark_chain(ws.lm, wq, wp, c->qkv_bias ? w->cr_attn.qkv_b : nullptr,
                                           w->cr_attn.proj_b, tr.tape ? reinterpret_cast<__half*>(ws.lqkv) : nullptr,
                                           ws.lo, ws.lout, k, D, c->crmsa_heads, st),
                "landmark chain");
-    if (tr.drop_p > 0.f)   // L' = dropout(proj(...)): the tape keeps the masked landmarks
-      RRT_CUDA(rrt::launch_dropout_inplace(ws.lout, (size_t)T * D,
-                                           rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream), st),
-               "landmark proj dropout");
+    if (ldrop.on())   // L' = dropout(proj(...)) (x 1 / keep of the branch): the tape keeps the masked landmarks
+      RRT_CUDA(rrt::launch_dropout_inplace(ws.lout, (size_t)T * D, ldrop, st), "landmark proj dropout");
   } else {
   rrt::GemmEpilogue e1;
     e1.bias = c->qkv_bias ? w->cr_attn.qkv_b : nullptr;
@@ -515,11 +534,11 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
     e2.bias = w->cr_attn.proj_b;
     { StageScope s_(kStLmProj, st);
       if (!s_.skip()) RRT_CUDA(rrt::launch_gemm_tcgen05(ws.lo, wp, ws.lout, false, T, D, D, e2, st), "landmark proj");
-      if (tr.drop_p > 0.f) {  // L' = dropout(proj(...)): the tape keeps the masked landmarks
+      rrt::Dropout ldrop = rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream);
+      ldrop.scale *= bscale;
+      if (ldrop.on()) {  // L' = dropout(proj(...)) (x 1 / keep of the branch): the tape keeps the masked landmarks
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        RRT_CUDA(rrt::launch_dropout_inplace(ws.lout, (size_t)T * D,
-                                             rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream), st),
-                 "landmark proj dropout");
+        RRT_CUDA(rrt::launch_dropout_inplace(ws.lout, (size_t)T * D, ldrop, st), "landmark proj dropout");
       } }
   }
   { StageScope s_(kStCrDispatch, st);
@@ -580,7 +599,8 @@ int encoder_forward(const rrt_config* cfg, const rrt_weights* w, const float* x,
     int rc = pos_embed();
     if (rc) return rc;
   }
-  const int rs_parts = row_stats_fused(cfg, w, L);
+  // (stochastic depth may skip the GEMM that would leave the row partials: separate kernel then)
+  const int rs_parts = tr.branch_scale ? 0 : row_stats_fused(cfg, w, L);
   for (int i = 0; i < cfg->n_rmsa_layers; ++i) {
     if (i == 1 && cfg->pos != RRT_POS_NONE && cfg->pos_pos == 0) {
       int rc = pos_embed();
@@ -1224,6 +1244,14 @@ bool carve_bwd(const rrt_config* c, int64_t L, void* base, BwdWorkspace* b) {
   return true;
 }
 
+int check_branch_scale(const rrt_config* c, const float* bs) {
+  if (!bs) return RRT_OK;
+  for (int i = 0; i <= c->n_rmsa_layers; ++i)
+    if (!(bs[i] >= 0.f) || !(bs[i] < 1e6f)) return fail(RRT_E_INVALID, "branch_scale entries must be 0 or 1 / keep");
+  if (c->ffn) return fail(RRT_E_INVALID, "drop_path with the FFN ablation is not covered");
+  return RRT_OK;
+}
+
 bool wgrad_mn() {
   static const bool on = [] { const char* e = getenv("RRT_WGRAD"); return !(e && !strcmp(e, "transpose")); }();
   return on;
@@ -1332,7 +1360,8 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
   rrt::Grid ident{};
   const float* g = nullptr;  // gradient wrt x_last
   int am = 0;                // index of g's amax word
-  if (c->cr_msa) {
+  const float cr_scale = tr.scale_of(nl);
+  if (c->cr_msa && cr_scale != 0.f) {
     rrt::Grid gc{};
     if (!crmsa_grid(L, &gc)) return fail(RRT_E_INVALID, "bad geometry");
     const int k = c->crmsa_k, T = k * gc.R;
@@ -1349,10 +1378,11 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
     // landmark MHA backward on T = k*64 rows (batch k, sequence 64, no EPEG)
     ident.L = T; ident.Np = T;
     { StageScope s_(kStBwdPrep, st, 2);
+      rrt::Dropout ldrop = rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream);
+      ldrop.scale *= cr_scale;
       RRT_CUDA(rrt::launch_amax(b.dLp, (size_t)T * D, &b.amax[0], st), "amax");
       RRT_CUDA(rrt::launch_grad_partition(b.dLp, ident, T, D, &b.amax[0], b.dy, wgrad_mn() ? nullptr : b.dyT,
-                                          gr->cr_attn.proj_b, st,
-                                          rrt::dropout_make(tr.drop_p, tr.seed, kCrDropStream)),
+                                          gr->cr_attn.proj_b, st, ldrop),
                "landmark grad rows"); }
     const int cr_hd = D / c->crmsa_heads;
     const bool lm_f32 = cr_hd != 32 && cr_hd != 64 && cr_hd != 128;   // the forward's fp32 landmark path
@@ -1424,10 +1454,32 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
     const bool peg_here = i == pos_at;
     const float* x_prev = i > 0 ? tp.xs[i - 1] : x;          // what the layer (or the encoding in front of it) read
     const float* x_in = peg_here ? tp.pe_out : x_prev;
+    const float lscale = tr.scale_of(i);
+    if (lscale == 0.f) {   // stochastic depth dropped this block in the forward: the gradient passes through
+      float* out = i == 0 ? dx : (g == b.ga ? b.gb : b.ga);
+      const float* shortcut = (i == 0 && c->all_shortcut) ? b.dh : nullptr;
+      StageScope s_(kStOther, st, peg_here ? 5 : 1);
+      if (peg_here) {
+        cudaError_t e = rrt::launch_peg_backward(x_prev, g, shortcut, out, (int)L, D, c->peg_k,
+                                                 c->pos == RRT_POS_PPEG, c->peg_1d != 0, tp.pe_w, b.peg_dw,
+                                                 gr->pos_w, gr->pos_b, st);
+        if (e != cudaSuccess) return fail_cuda(e, "pos_embedding backward");
+        if (i > 0) {
+          ++am;
+          RRT_CUDA(rrt::launch_amax(out, (size_t)L * D, &b.amax[am], st), "amax");
+        }
+        g = out;
+      } else if (i == 0) {   // dx = g (+ the shortcut); deeper layers just keep reading g and its amax word
+        RRT_CUDA(rrt::launch_add2(dx, g, shortcut, (size_t)L * D, st), "gradient pass-through");
+        g = dx;
+      }
+      continue;
+    }
     { StageScope s_(kStBwdPrep, st);
+      rrt::Dropout ldrop = rrt::dropout_make(tr.drop_p, tr.seed, (unsigned)i);
+      ldrop.scale *= lscale;
       RRT_CUDA(rrt::launch_grad_partition(g, gg, gg.Np, D, &b.amax[am], b.dy, wgrad_mn() ? nullptr : b.dyT,
-                                          ga->proj_b, st,
-                                          rrt::dropout_make(tr.drop_p, tr.seed, (unsigned)i)),
+                                          ga->proj_b, st, ldrop),
                "gradient partition"); }
     int rc = attention_module_backward(c, &w->layer_attn[i], ga, tp.z[i], tp.qkv[i], tp.o[i], gg.R, gg.P,
                                        c->n_heads, c->epeg != 0, &b.amax[am], b, st);
@@ -1480,7 +1532,7 @@ int check_drop(float p) {
 
 RRT_API int rrt_encoder_forward_train(const rrt_config* cfg, const rrt_weights* w, const float* x,
                                       float* out, int64_t L, void* tape, size_t tape_bytes,
-                                      float drop_p, uint64_t seed, void* stream) {
+                                      float drop_p, uint64_t seed, const float* branch_scale, void* stream) {
   int rc = check_config(cfg);
   if (rc) return rc;
   if (!w || !x || !out || x == out) return fail(RRT_E_INVALID, "bad pointer");
@@ -1494,6 +1546,9 @@ RRT_API int rrt_encoder_forward_train(const rrt_config* cfg, const rrt_weights* 
   tr.drop_p = drop_p;
   tr.seed = seed;
   tr.tape = true;  // the backward re-reads z, q/k/v, o: no kernel variant may skip an intermediate
+  rc = check_branch_scale(cfg, branch_scale);
+  if (rc) return rc;
+  tr.branch_scale = branch_scale;
   PdlScope pdl(!g_timing.load(std::memory_order_relaxed));
   return encoder_forward(cfg, w, x, out, L, ws, (cudaStream_t)stream, tr);
 }
@@ -1517,7 +1572,8 @@ RRT_API int rrt_backward_workspace_bytes(const rrt_config* cfg, int64_t L, size_
 RRT_API int rrt_encoder_backward(const rrt_config* cfg, const rrt_weights* w, const float* x,
                                  const float* dout, int64_t L, const void* tape, size_t tape_bytes,
                                  const rrt_grads* grads, float* dx, void* workspace,
-                                 size_t workspace_bytes, float drop_p, uint64_t seed, void* stream) {
+                                 size_t workspace_bytes, float drop_p, uint64_t seed, const float* branch_scale,
+                                 void* stream) {
   int rc = check_config(cfg);
   if (rc) return rc;
   if (!w || !x || !dout || !grads || !dx || dx == dout) return fail(RRT_E_INVALID, "bad pointer");
@@ -1526,6 +1582,9 @@ RRT_API int rrt_encoder_backward(const rrt_config* cfg, const rrt_weights* w, co
   TrainOpts tr;
   tr.drop_p = drop_p;
   tr.seed = seed;
+  rc = check_branch_scale(cfg, branch_scale);
+  if (rc) return rc;
+  tr.branch_scale = branch_scale;
   rc = check_backward_support(cfg, L);
   if (rc) return rc;
   Workspace tp{};

@@ -265,6 +265,30 @@ __global__ void __launch_bounds__(256) dropout_kernel(float* __restrict__ x, siz
 }
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) add2_kernel(float* __restrict__ out, const float* __restrict__ a,
+                                                   const float* __restrict__ b, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(a) + i);
+    if (b) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(b) + i);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+}  // namespace
+
+// out = a (+ b); n % 4 == 0
+cudaError_t launch_add2(float* out, const float* a, const float* b, size_t n, cudaStream_t stream) {
+  if (n % 4) return cudaErrorInvalidValue;
+  if (n == 0) return cudaSuccess;
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  add2_kernel<<<blocks, 256, 0, stream>>>(out, a, b, n / 4);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_dropout_inplace(float* x, size_t n, const Dropout& drop, cudaStream_t stream) {
   if (n % 4) return cudaErrorInvalidValue;
   if (n == 0 || !drop.on()) return cudaSuccess;

@@ -118,7 +118,8 @@ struct Dropout {
   // optional: a per-step seed that lives in DEVICE memory and is ADDED to `key` when the mask is evaluated, so
   // that a captured CUDA graph of a training step draws a new mask on every replay (rrt_set_step_state)
   const unsigned long long* seed_dev = nullptr;
-  __host__ __device__ bool on() const { return thresh != 0; }
+  // thresh == 0 with scale != 1: nothing is dropped, everything is scaled (stochastic depth's 1/keep on a branch)
+  __host__ __device__ bool on() const { return thresh != 0 || scale != 1.f; }
 };
 // api.cu (rrt_set_step_state); null = off.  PROCESS-wide, not per thread: torch runs the backward of a step on its
 // autograd thread, and forward and backward must evaluate the same masks

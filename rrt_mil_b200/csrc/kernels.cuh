@@ -201,6 +201,8 @@ cudaError_t launch_grad_partition(const float* g, const Grid& grid, int M, int C
                                   __half* rows, __half* rowsT, float* colsum, cudaStream_t stream,
                                   const Dropout& drop = Dropout{}, const float* mask_src = nullptr,
                                   float mask_scale = 1.f, int mask_mode = 0);
+// out = a (+ b), fp32, n % 4 == 0
+cudaError_t launch_add2(float* out, const float* a, const float* b, size_t n, cudaStream_t stream);
 // x[i] *= mask(i) / (1-p) in place, x fp32 [rows, C] (the landmark projection output in training mode)
 cudaError_t launch_dropout_inplace(float* x, size_t n, const Dropout& drop, cudaStream_t stream);
 // mask(i)/(1-p) of n elements as fp32 (parity tests: the oracle consumes the same mask)

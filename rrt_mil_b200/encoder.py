@@ -132,6 +132,7 @@ class _EncoderFunction(torch.autograd.Function):
     def forward(ctx, enc, x, *params):
         lib, cfg, N = cabi.lib(), enc._cfg, x.shape[0]
         drop_p, seed = enc._train_dropout()
+        scales = enc._branch_scales()       # stochastic depth of this step (drop_path), or None
         with torch.cuda.device(x.device):
             n = C.c_size_t()
             cabi.check(lib.rrt_train_tape_bytes(C.byref(cfg), N, C.byref(n)), "rrt_train_tape_bytes")
@@ -139,11 +140,12 @@ class _EncoderFunction(torch.autograd.Function):
             out = torch.empty_like(x)
             w = enc._weights(x.device)
             rc = lib.rrt_encoder_forward_train(C.byref(cfg), C.byref(w), x.data_ptr(), out.data_ptr(), N,
-                                               tape.data_ptr(), n.value, drop_p, seed,
+                                               tape.data_ptr(), n.value, drop_p, seed, scales,
                                                torch.cuda.current_stream(x.device).cuda_stream)
         cabi.check(rc, "rrt_encoder_forward_train")
         ctx.enc = enc
         ctx.drop = (drop_p, seed)
+        ctx.scales = scales
         ctx.save_for_backward(x, tape, *params)
         return out
 
@@ -171,7 +173,7 @@ class _EncoderFunction(torch.autograd.Function):
             w = enc._weights(x.device)
             rc = lib.rrt_encoder_backward(C.byref(cfg), C.byref(w), x.data_ptr(), dout.data_ptr(), N,
                                           tape.data_ptr(), tape.numel(), C.byref(g), dx.data_ptr(),
-                                          ws.data_ptr(), n.value, ctx.drop[0], ctx.drop[1],
+                                          ws.data_ptr(), n.value, ctx.drop[0], ctx.drop[1], ctx.scales,
                                           torch.cuda.current_stream(x.device).cuda_stream)
         cabi.check(rc, "rrt_encoder_backward")
         grads = [v if p_.requires_grad else None for v, p_ in zip(views, params)]
@@ -436,6 +438,24 @@ class RRTEncoder(nn.Module):
         self.last_dropout_seed = seed
         return float(self.drop_out), seed
 
+    def _branch_scales(self):
+        """Stochastic depth (``drop_path``, modules/rrt.py:102,125) of this training forward: one Bernoulli(keep)
+        per block (R-MSA layers, then CR-MSA) from torch's CPU generator -- the bag is the whole batch, so a dropped
+        block is skipped outright and a kept one has its branch scaled by 1 / keep (timm's DropPath).  Returns a
+        ctypes float array for the C entries, or None.  ``_drop_path_keep`` (list of bools) pins the draw (tests)."""
+        p = self.drop_path_rate
+        if not self.training or p <= 0.0:
+            return None
+        nb = self._cfg.n_rmsa_layers + (1 if self._cfg.cr_msa else 0)
+        keep = self.__dict__.get("_drop_path_keep")
+        if keep is None:
+            keep = (torch.rand(nb) >= p).tolist()
+        self.last_drop_path_keep = [bool(k) for k in keep]
+        vals = [(1.0 / (1.0 - p)) if k else 0.0 for k in keep[:nb]]
+        while len(vals) < self._cfg.n_rmsa_layers + 1:      # the C array always has n_rmsa_layers + 1 entries
+            vals.append(1.0)
+        return (C.c_float * len(vals))(*vals)
+
     def _needs_grad(self, x) -> bool:
         return torch.is_grad_enabled() and (
             x.requires_grad or any(p.requires_grad for p in self._named_param_cache()[1]))
@@ -470,10 +490,10 @@ class RRTEncoder(nn.Module):
             # the FFN kernels have no dropout, so computing on would silently differ from the reference
             raise NotImplementedError("training-mode dropout inside the FFN ablation is not built: "
                                       "use .eval() or drop_out=0")
-        if self.training and self.drop_path_rate > 0:
-            raise NotImplementedError("training-mode drop_path (default 0) is not built")
-        if self.training and self.drop_out > 0 and not allow_grad:
-            raise NotImplementedError("forward_bags is inference-only (no dropout): call .eval() first")
+        if self.training and self.drop_path_rate > 0 and self._cfg.ffn:
+            raise NotImplementedError("training-mode drop_path with the FFN ablation is not built")
+        if self.training and (self.drop_out > 0 or self.drop_path_rate > 0) and not allow_grad:
+            raise NotImplementedError("forward_bags is inference-only (no dropout / drop_path): call .eval() first")
 
     @staticmethod
     def _as_f32(x: torch.Tensor) -> torch.Tensor:
@@ -498,7 +518,7 @@ class RRTEncoder(nn.Module):
         if N < 1:
             raise ValueError("empty bag")
         x = self._as_f32(x.contiguous())
-        if self._needs_grad(x) or (self.training and self.drop_out > 0):
+        if self._needs_grad(x) or (self.training and (self.drop_out > 0 or self.drop_path_rate > 0)):
             # autograd / training path: forward with a tape (+ proj dropout), backward kernels
             return _EncoderFunction.apply(self, x, *self._named_param_cache()[1])
         lib, cfg = cabi.lib(), self._cfg

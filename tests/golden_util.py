@@ -64,7 +64,15 @@ def load_train_case(name, dtype=torch.float64):
     gout = torch.randn(c["L"], cfg.mlp_dim, generator=torch.Generator().manual_seed(c["grad_seed"]),
                        dtype=torch.float64).to(dtype)
     gold = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
-    return cfg, w, x, gout, (c["drop_out"], c["dropout_seed"]), gold
+    # (drop_out p, seed, drop_path rate, keep per block) -- the last two None without stochastic depth
+    return cfg, w, x, gout, (c["drop_out"], c["dropout_seed"], c.get("drop_path"), c.get("drop_path_keep")), gold
+
+
+def branch_scales(drop):
+    """Per-block branch factors of a train fixture with stochastic depth (None otherwise)."""
+    if len(drop) < 4 or drop[2] is None:
+        return None
+    return [(1.0 / (1.0 - drop[2])) if k else 0.0 for k in drop[3]]
 
 
 def _rows(a, stride):

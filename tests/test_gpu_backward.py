@@ -209,10 +209,12 @@ def test_dropout_mask_matches_oracle(rows, D, p, seed, stream):
 def test_training_mode_matches_reference_fixture(name):
     """.train() forward (proj_drop active) + backward through the CUDA kernels against the fixture the
     REFERENCE produced in .train() with the same masks installed (oracle/make_golden.py)."""
-    cfg, w, x, gout, (p, seed), gold = load_train_case(name)
-    m = RRTEncoder(**cfg.to_dict(), drop_out=p).cuda().train()
+    cfg, w, x, gout, (p, seed, dp_rate, dp_keep), gold = load_train_case(name)
+    m = RRTEncoder(**cfg.to_dict(), drop_out=p, drop_path=dp_rate or 0.0).cuda().train()
     m.load_state_dict({k: v.float() for k, v in w.items()}, strict=True)
     m._dropout_seed = seed
+    if dp_keep is not None:     # stochastic depth: pin the outcome of the Bernoulli draws the fixture was made with
+        m._drop_path_keep = [bool(k) for k in dp_keep]
     xd = x.float().cuda().requires_grad_()
     y = m(xd)
     (y * gout.float().cuda()).sum().backward()
@@ -222,6 +224,8 @@ def test_training_mode_matches_reference_fixture(name):
     for k, v in e.items():
         tol = 1e-3 if k.startswith("out") else TOL_GRAD
         assert v < tol, (k, v, e)
+    if dp_keep is not None:
+        assert m.last_drop_path_keep == [bool(k) for k in dp_keep]
     if p > 0:   # a different seed gives a different (but equally valid) result; eval ignores drop_out
         m._dropout_seed = seed + 1
         with torch.no_grad():
@@ -253,8 +257,20 @@ def test_backward_rejects_unsupported():
     x = O.make_bag(200, 512, 4).float().cuda().requires_grad_()
     with pytest.raises(NotImplementedError):
         m(x)
-    with pytest.raises(NotImplementedError):     # drop_path (stochastic depth, default 0) is not built
-        RRTEncoder(drop_path=0.1).cuda().train()(x.detach())
+    # drop_path (stochastic depth): the Bernoulli draws come from torch's CPU generator (reproducible), every block
+    # is dropped now and then, and eval ignores it
+    md = RRTEncoder(drop_path=0.5, n_layers=3, need_init=True).cuda().train()
+    torch.manual_seed(11)
+    keeps = []
+    for _ in range(12):
+        md(x.detach())
+        keeps.append(tuple(md.last_drop_path_keep))
+    assert len(set(keeps)) > 1 and all(len(k) == 3 for k in keeps)
+    torch.manual_seed(11)
+    md(x.detach())
+    assert tuple(md.last_drop_path_keep) == keeps[0]
+    with torch.no_grad():
+        assert torch.equal(md.eval()(x.detach()), md(x.detach()))
     m2 = G.make_encoder(O.EncoderConfig(), O.make_weights(O.EncoderConfig(), 3)).train()
     with pytest.raises(NotImplementedError):     # the batch entry point is inference-only
         m2.forward_bags([x.detach()])

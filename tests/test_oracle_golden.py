@@ -6,7 +6,8 @@ import torch
 
 from oracle import rrt_oracle as O
 from oracle import _reference_shim as shim
-from golden_util import CASES, TRAIN_CASES, load_case, load_train_case, train_errors, assert_matches_golden
+from golden_util import (CASES, TRAIN_CASES, load_case, load_train_case, train_errors, assert_matches_golden,
+                         branch_scales)
 
 # the 50k-token case needs ~2 GB in float64 reference order; keep it but only in "spec" order
 BIG = {"c4_n50000_g16"}
@@ -75,7 +76,8 @@ def test_oracle_training_mode_matches_reference_autograd(name, order):
     cfg, w, x, gout, drop, gold = load_train_case(name)
     w = {k: v.clone().requires_grad_() for k, v in w.items()}
     xr = x.clone().requires_grad_()
-    y = O.encoder_forward(xr, w, cfg, order, drop=drop if drop[0] > 0 else None)
+    y = O.encoder_forward(xr, w, cfg, order, drop=drop[:2] if drop[0] > 0 else None,
+                          branch_scale=branch_scales(drop))
     (y * gout).sum().backward()
     e = train_errors(y, xr.grad, {k: v.grad for k, v in w.items()}, gold)
     bad = {k: v for k, v in e.items() if not v <= 2e-6}
