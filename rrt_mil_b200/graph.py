@@ -116,6 +116,9 @@ class GraphedTrainStep:
         from .optim import Adam
         if not isinstance(optimizer, Adam) or len(optimizer.param_groups) != 1:
             raise TypeError("GraphedTrainStep needs rrt_mil_b200.optim.Adam with a single parameter group")
+        if any(getattr(mod, "drop_path_rate", 0.0) > 0.0 for mod in model.modules()):
+            raise NotImplementedError("GraphedTrainStep: drop_path > 0 changes the kernel sequence from step to step "
+                                      "(a dropped block is skipped); train those models eagerly")
         self.model, self.opt = model, optimizer
         # data-parallel: a parallel.GradReducer whose hooks launch the gradient all-reduces during backward;
         # finish() is part of the recorded step (NCCL collectives are capturable), so a replay is the whole
