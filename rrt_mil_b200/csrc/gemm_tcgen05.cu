@@ -214,18 +214,33 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
           __syncwarp();
         }
         uint8_t* rowp = stage + lane * ROWB;
-        const int act_j = (p.act_split > 0 && n0 + (c_begin + j) * 32 >= p.act_split) ? p.act2 : p.act;
         // swizzle: 16-B chunk index ^= bits of the row (128B pattern: row%8; 64B pattern: (row/2)%4)
         const int sw = ROWB == 128 ? (lane & 7) : ((lane >> 1) & 3);
+        float fv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) fv[i] = __uint_as_float(rr[i]) + __shfl_sync(0xffffffffu, bias_l[j], i);
+        if (MODE == kEpiStoreAct) {
+          // ONE branch per 32-column chunk (a per-element switch kept erff / tanhf on every element's path:
+          // 70 us for the 9000 x 1024 x 512 patch_to_emb GEMM with a ReLU)
+          const int act_j = (p.act_split > 0 && n0 + (c_begin + j) * 32 >= p.act_split) ? p.act2 : p.act;
+          if (act_j == kActRelu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) fv[i] = fmaxf(fv[i], 0.f);
+          } else if (act_j == kActGelu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) fv[i] = gelu_fwd(fv[i]);
+          } else if (act_j == kActTanh) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) fv[i] = tanhf(fv[i]);
+          } else if (act_j == kActSigmoid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) fv[i] = 1.f / (1.f + __expf(-fv[i]));
+          }
+        }
 #pragma unroll
         for (int q = 0; q < NCH; ++q) {
           constexpr int EPC = 16 / (int)sizeof(OutT);      // elements per 16-byte chunk
-          float f[EPC];
-#pragma unroll
-          for (int e = 0; e < EPC; ++e) {
-            f[e] = __uint_as_float(rr[q * EPC + e]) + __shfl_sync(0xffffffffu, bias_l[j], q * EPC + e);
-            if (MODE == kEpiStoreAct) f[e] = apply_act(f[e], act_j);
-          }
+          const float* f = fv + q * EPC;
           uint4 pk;
           if (sizeof(OutT) == 2) {
             pk = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4 % EPC], f[5 % EPC]),
