@@ -205,6 +205,25 @@ def test_dropout_mask_matches_oracle(rows, D, p, seed, stream):
     assert torch.equal(out.cpu(), ref)
 
 
+def test_device_step_state_shifts_the_dropout_seed():
+    """rrt_set_step_state: the mask a kernel evaluates is the one of (seed argument + the u64 in the device buffer),
+    so a CUDA-graph replay draws a new mask by updating 8 bytes; switching the state off restores the plain seed."""
+    lib = cabi.lib()
+    state = torch.zeros(2, dtype=torch.int64, device="cuda")
+    out = torch.empty(300, 512, device="cuda")
+    try:
+        for dev_seed in (0, 7, 2 ** 40 + 3):
+            state[0] = dev_seed
+            cabi.check(lib.rrt_set_step_state(state.data_ptr()), "rrt_set_step_state")
+            cabi.check(lib.rrt_dropout_mask(out.data_ptr(), out.numel(), 0.25, 1000, 3, G.stream_ptr()), "mask")
+            assert torch.equal(out.cpu(), O.dropout_mask(300, 512, 0.25, 1000 + dev_seed, 3, dtype=torch.float32))
+    finally:
+        cabi.check(lib.rrt_set_step_state(None), "rrt_set_step_state")
+    cabi.check(lib.rrt_dropout_mask(out.data_ptr(), out.numel(), 0.25, 1000, 3, G.stream_ptr()), "mask")
+    assert torch.equal(out.cpu(), O.dropout_mask(300, 512, 0.25, 1000, 3, dtype=torch.float32))
+    assert lib.rrt_set_step_state(state.data_ptr() + 8) == cabi.RRT_E_INVALID      # 16-byte alignment
+
+
 @pytest.mark.parametrize("name", sorted(TRAIN_CASES))
 def test_training_mode_matches_reference_fixture(name):
     """.train() forward (proj_drop active) + backward through the CUDA kernels against the fixture the
