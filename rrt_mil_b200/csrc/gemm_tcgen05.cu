@@ -37,12 +37,19 @@ constexpr int NTHREADS = 32 * (4 + kEpiWarps);
 //             ONE tile and run prologue, main loop and epilogue back to back; two 128-column tiles
 //             per CTA let the second main loop hide the first (HBM-bound, residual) epilogue
 //   BN =  64: landmark GEMMs (M = k*64 rows): 4x more CTAs, 4x shorter MMA chain per tile
-template <int BN_>
+//   RESID (the residual-scatter epilogues): the epilogue, not the main loop, bounds those GEMMs -- 256 KB of fp32
+//             residual in / x1 out per 128 x 256 tile against 5.7 k cycles of MMAs -- so part of the operand ring
+//             is given to a per-warp ring of kResidRing residual chunks filled by cp.async up to a tile ahead
+constexpr int kResidRing = 3;                  // 32 x 32 fp32 chunks in flight per epilogue warp
+constexpr int kResidChunkBytes = 32 * 32 * 4;
+template <int BN_, bool RESID_ = false>
 struct TileCfg {
-  static constexpr int STAGES = BN_ == 256 ? 4 : (BN_ == 128 ? 6 : 8);
+  static constexpr int STAGES =
+      RESID_ ? (BN_ == 256 ? 2 : (BN_ == 128 ? 3 : 4)) : (BN_ == 256 ? 4 : (BN_ == 128 ? 6 : 8));
   static constexpr int B_BYTES = BN_ * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static constexpr int RESID_BYTES = RESID_ ? kResidRing * kEpiWarps * kResidChunkBytes : 0;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + RESID_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 227 * 1024, "dynamic shared memory budget exceeded");
   static constexpr int TMEM_COLS = 2 * BN_ < 32 ? 32 : 2 * BN_;
 };
@@ -105,6 +112,195 @@ __device__ __forceinline__ void red_add4(float* base, size_t off, float4 v) {
                : "memory");
 }
 __device__ __forceinline__ void red_add4(__half*, size_t, float4) {}
+
+// ---- residual-scatter epilogue (kEpiResidualUnpart / kEpiResidualUnpartDrop) of the single-CTA kernel ------------
+// Residual prefetch cursor of one epilogue warp: walks the (tile, chunk) sequence the warp will consume,
+// kResidRing chunks ahead of the consumer, and cp.asyncs each 32 x 32 fp32 residual chunk into the next slot of the
+// warp's ring.  Every 16-byte piece is written and later read by the SAME thread (row group i -> row 4i + lane / 8,
+// columns 4 * (lane % 8)): no cross-thread synchronisation, only cp.async.wait_group.  One commit group per call
+// (empty past the last chunk), so that wait_group<kResidRing - 1> always means "the chunk being consumed has landed".
+// (one copy of the three integer divisions: inlined at its four call sites they were 3.4 k of the kernel's SASS)
+// (scalars by value: a reference to the Grid inside the kernel parameters would put a copy of them on the stack)
+__device__ __noinline__ int resid_token_of_slot_(int slot, int M, int P, int g, int rs, int H, int L) {
+  if (slot >= M) return -1;
+  Grid gr;
+  gr.P = P; gr.g = g; gr.rs = rs; gr.H = H; gr.L = L;
+  const int t = gr.slot_to_token(slot);
+  return t < L ? t : -1;
+}
+__device__ __forceinline__ int resid_token_of_slot(const Grid& g, int slot, int M) {
+  return resid_token_of_slot_(slot, M, g.P, g.g, g.rs, g.H, g.L);
+}
+
+template <int BN>
+struct ResidCursor {
+  static constexpr int NC = (BN / 32) / 2;
+  uint8_t* ring;     // this warp's kResidRing chunks
+  int wt, step, num_work, tiles_nc, ci, cj, CM, CN;
+  int j, slot;       // chunk within the cursor's tile; ring slot of the next chunk
+  int tok[8];        // token rows of the cursor's tile for this lane's 8 row groups (-1: pad / outside)
+  int n0;
+  __device__ __forceinline__ void load_tile(const Tc05Params& p, int quad, int lane) {
+    if (wt >= num_work) return;
+    const int m0 = ((wt / tiles_nc) * CM + ci) * BM;
+    n0 = ((wt % tiles_nc) * CN + cj) * BN;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      tok[i] = resid_token_of_slot(p.grid, m0 + quad * 32 + 4 * i + (lane >> 3), p.M);
+    }
+  }
+  __device__ __forceinline__ void issue(const Tc05Params& p, int ew, int lane) {
+    if (wt < num_work) {
+      const int gc = n0 + ((ew >> 2) * NC + j) * 32 + (lane & 7) * 4;
+      uint8_t* dst = ring + slot * kResidChunkBytes + lane * 16;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = tok[i] >= 0 && gc < p.N;
+        cp_async16(dst + i * 512, ok ? p.resid + (size_t)tok[i] * p.N + gc : p.resid, ok);
+      }
+      if (++slot == kResidRing) slot = 0;
+      if (++j == NC) {
+        j = 0;
+        wt += step;
+        load_tile(p, ew & 3, lane);
+      }
+    }
+    cp_async_commit();
+  }
+};
+
+// One 128 x BN accumulator for one of the 8 epilogue warps.  The chunk loop is ROLLED and the row-statistics pass
+// reads gamma (.) phi from shared memory: the unrolled form of this epilogue was 10 k SASS instructions (157 KB; with
+// dropout 188 KB) and ran out of the instruction cache -- ncu's warp-state samples of the 8 epilogue warps were
+// dominated by no_inst (profiles/r02f_*): 28 k cycles per tile against 5.7 k for the main loop.
+template <int MODE, int BN, typename ReleaseFn>
+__device__ __forceinline__ void epilogue_tile_resid(const Tc05Params& p, uint32_t tmem_acc, uint64_t* tfull_bar,
+                                                    uint32_t tfull_parity, int m0, int n0, int ew, int lane,
+                                                    float* scratch, bool first, ReleaseFn release,
+                                                    ResidCursor<BN>& cur, int& cons_slot) {
+  constexpr int NC = (BN / 32) / 2;  // chunks per epilogue warp
+  const int quad = ew & 3;           // TMEM lanes [32*quad, 32*quad+32) are readable by this warp
+  const int c_begin = (ew >> 2) * NC;
+  float* const out = reinterpret_cast<float*>(p.C);
+  const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+  // output row of each of the 8 row groups this lane stores (region slot -> token; -1: pad row)
+  int orow[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) orow[i] = resid_token_of_slot(p.grid, m0 + quad * 32 + 4 * i + sub_r, p.M);
+  // row statistics of the rows being written (thread = row `lane` of this warp's 32): sum, sum of squares and up
+  // to four dot products with gamma (.) phi[:, n] over this warp's NC * 32 columns
+  float rs_sum = 0.f, rs_sq = 0.f, rs_dot[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool row_stats = p.rs_part != nullptr;
+  mbar_wait(tfull_bar, tfull_parity);
+  tc_fence_after();
+  if (first && threadIdx.x == 128) stamp(p, 6);
+  const uint32_t t_addr = tmem_acc + ((uint32_t)(quad * 32) << 16) + c_begin * 32;
+  uint32_t r[32];
+  tmem_ld_32x32(t_addr, r);
+#pragma unroll 1
+  for (int j = 0; j < NC; ++j) {
+    const int gc = n0 + (c_begin + j) * 32 + sub_c;
+    const bool col_ok = gc < p.N;
+    // bias of this lane's 4 columns and gamma_c * phi[c, 0..3] of column c = `lane` of this chunk: fetched here, used
+    // after the transpose resp. at the end of the chunk
+    const float4 bv = (p.bias && col_ok) ? __ldg(reinterpret_cast<const float4*>(p.bias + gc))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row_stats) {
+      const int gcl = n0 + (c_begin + j) * 32 + lane;
+      const float gm = __ldg(p.rs_gamma + gcl);
+      if (p.rs_k == 4) {
+        const float4 ph = __ldg(reinterpret_cast<const float4*>(p.rs_phi) + gcl);
+        gq = make_float4(gm * ph.x, gm * ph.y, gm * ph.z, gm * ph.w);
+      } else {
+        const float* ph = p.rs_phi + (size_t)gcl * p.rs_k;
+        gq.x = gm * __ldg(ph);
+        if (p.rs_k > 1) gq.y = gm * __ldg(ph + 1);
+        if (p.rs_k > 2) gq.z = gm * __ldg(ph + 2);
+      }
+    }
+    tmem_ld_wait();  // chunk j is in registers
+    if (first && threadIdx.x == 128 && j < 2) stamp(p, 10 + 3 * j);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)  // row = lane; 16-byte slot q lands at slot q ^ (row & 7)
+      *reinterpret_cast<float4*>(scratch + lane * EPI_LD + 4 * (q ^ (lane & 7))) =
+          make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                      __uint_as_float(r[4 * q + 3]));
+    if (j + 1 < NC) {
+      tmem_ld_32x32(t_addr + (j + 1) * 32, r);  // overlaps the rest of chunk j
+    } else {
+      // the whole accumulator slice of this warp has left TMEM: release it to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      release();
+    }
+    __syncwarp();
+    if (first && threadIdx.x == 128 && j < 2) stamp(p, 11 + 3 * j);
+    // this thread's 8 pieces of the residual chunk have landed in the ring
+    cp_async_wait<kResidRing - 1>();
+    uint8_t* slot = cur.ring + cons_slot * kResidChunkBytes;
+    if (++cons_slot == kResidRing) cons_slot = 0;
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(slot + i * 512 + lane * 16);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = 4 * i + sub_r;
+      const float4 a = *reinterpret_cast<const float4*>(scratch + rl * EPI_LD + 4 * ((lane & 7) ^ (rl & 7)));
+      if (MODE == kEpiResidualUnpartDrop) {  // x1 = x + dropout(o Wp^T + b)   (modules/rmsa.py:131-132)
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (orow[i] >= 0) m = dropout_scale4(p.drop, (unsigned long long)orow[i] * p.N + gc);
+        v[i].x = fmaf(a.x + bv.x, m.x, v[i].x); v[i].y = fmaf(a.y + bv.y, m.y, v[i].y);
+        v[i].z = fmaf(a.z + bv.z, m.z, v[i].z); v[i].w = fmaf(a.w + bv.w, m.w, v[i].w);
+      } else {
+        v[i].x += a.x + bv.x; v[i].y += a.y + bv.y; v[i].z += a.z + bv.z; v[i].w += a.w + bv.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (orow[i] >= 0 && col_ok) store_out4(out, (size_t)orow[i] * p.N + gc, v[i]);
+    if (first && threadIdx.x == 128 && j < 2) stamp(p, 12 + 3 * j);
+    if (row_stats) {
+      // hand the finished values back through the scratch tile (same swizzled slots they were read from); the
+      // 32 x 4 table of gamma (.) phi goes into the ring slot just consumed (each lane overwrites one of ITS pieces)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = 4 * i + sub_r;
+        *reinterpret_cast<float4*>(scratch + rl * EPI_LD + 4 * ((lane & 7) ^ (rl & 7))) = v[i];
+      }
+      *reinterpret_cast<float4*>(slot + lane * 16) = gq;
+      __syncwarp();
+#pragma unroll 2
+      for (int q = 0; q < 8; ++q) {
+        const float4 xv = *reinterpret_cast<const float4*>(scratch + lane * EPI_LD + 4 * (q ^ (lane & 7)));
+        rs_sum += (xv.x + xv.y) + (xv.z + xv.w);
+        rs_sq = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, fmaf(xv.z, xv.z, fmaf(xv.w, xv.w, rs_sq))));
+        const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 g = *reinterpret_cast<const float4*>(slot + (4 * q + e) * 16);  // broadcast read
+          rs_dot[0] = fmaf(xe[e], g.x, rs_dot[0]);
+          rs_dot[1] = fmaf(xe[e], g.y, rs_dot[1]);
+          rs_dot[2] = fmaf(xe[e], g.z, rs_dot[2]);
+          rs_dot[3] = fmaf(xe[e], g.w, rs_dot[3]);
+        }
+      }
+    }
+    __syncwarp();  // every lane is done with the scratch tile and the borrowed ring slot
+    cur.issue(p, ew, lane);  // the slot just consumed takes the chunk kResidRing ahead
+  }
+  if (row_stats) {
+    // one 32-byte record per (token, 128-column part): [sum, sum sq, dot_0..3, -, -]
+    const int tok = resid_token_of_slot(p.grid, m0 + quad * 32 + lane, p.M);
+    if (tok >= 0) {
+      constexpr int PW = NC * 32;  // columns per part
+      const int parts = p.N / PW, part = (n0 + c_begin * 32) / PW;
+      float4* rec = reinterpret_cast<float4*>(p.rs_part + ((size_t)tok * parts + part) * 8);
+      rec[0] = make_float4(rs_sum, rs_sq, rs_dot[0], rs_dot[1]);
+      rec[1] = make_float4(rs_dot[2], rs_dot[3], 0.f, 0.f);
+    }
+  }
+}
 
 // Epilogue of one 128 x BN accumulator for one of the 8 epilogue warps (two per TMEM lane quadrant):
 // software-pipelined tcgen05.ld, accumulator released (release()) as soon as this warp's slice is in
@@ -366,7 +562,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                         const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmC, Tc05Params p) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, is_resid_mode(MODE)>;
   constexpr int CSIZE = CM * CN;
   // plain stores (kEpiStore): the epilogue hands each 32x32 chunk to the TMA engine; the scatter /
   // tanh epilogues keep st.global (rows are permuted resp. the layer is tiny)
@@ -379,7 +575,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   float* sEpi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  uint8_t* sResid = smem + STAGES * STAGE_BYTES + EPI_BYTES;  // residual modes: kEpiWarps x kResidRing chunks
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES + Cfg::RESID_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -505,15 +702,31 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int ew = warp - 4;
     float* scratch = sEpi + ew * 32 * EPI_LD;
     int acc = 0, aph = 0;
+    ResidCursor<BN> cur;
+    int cons_slot = 0;
+    if (is_resid_mode(MODE)) {  // the first kResidRing residual chunks are in flight while the first main loop runs
+      cur.ring = sResid + (size_t)ew * kResidRing * kResidChunkBytes;
+      cur.wt = cluster_id; cur.step = num_clusters; cur.num_work = num_work; cur.tiles_nc = tiles_nc;
+      cur.ci = ci; cur.cj = cj; cur.CM = CM; cur.CN = CN;
+      cur.j = 0; cur.slot = 0;
+      cur.load_tile(p, ew & 3, lane);
+#pragma unroll 1
+      for (int r = 0; r < kResidRing; ++r) cur.issue(p, ew, lane);
+    }
     for (int wt = cluster_id; wt < num_work; wt += num_clusters) {
       const int ct = wt % num_ctiles;
       const int m0 = ((ct / tiles_nc) * CM + ci) * BM, n0 = ((ct % tiles_nc) * CN + cj) * BN;
       uint64_t* te = &tempty[acc];
-      epilogue_tile<MODE, BN, OutT>(p, &tmC, tmem_base + acc * BN, &tfull[acc], aph, m0, n0, ew, lane,
-                                    scratch, wt == cluster_id, [&] { if (lane == 0) mbar_arrive(te); });
+      if constexpr (is_resid_mode(MODE))
+        epilogue_tile_resid<MODE, BN>(p, tmem_base + acc * BN, &tfull[acc], aph, m0, n0, ew, lane, scratch,
+                                      wt == cluster_id, [&] { if (lane == 0) mbar_arrive(te); }, cur, cons_slot);
+      else
+        epilogue_tile<MODE, BN, OutT>(p, &tmC, tmem_base + acc * BN, &tfull[acc], aph, m0, n0, ew, lane,
+                                      scratch, wt == cluster_id, [&] { if (lane == 0) mbar_arrive(te); });
       if (++acc == 2) { acc = 0; aph ^= 1; }
       if (threadIdx.x == 128) stamp(p, wt == cluster_id ? 7 : 8);
     }
+    if (is_resid_mode(MODE)) cp_async_wait<0>();
   }
 
   if (kTmaStore && warp >= 4 && lane == 0) tma_store_wait_all<0>();  // smem must outlive the stores
@@ -839,7 +1052,7 @@ bool gemm_tcgen05_supported(int M, int N, int K) {
 namespace {
 template <int MODE, int BN, typename OutT, int CM, int CN>
 cudaError_t launch_cfg(const __half* a, const __half* w, const Tc05Params& p, cudaStream_t stream) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, is_resid_mode(MODE)>;
   constexpr int CSIZE = CM * CN;
   CUtensorMap tmA, tmB, tmC;
   if (!make_map(&tmA, a, p.M, p.K, BM / CN) || !make_map(&tmB, w, p.N, p.K, BN / CM))
