@@ -205,18 +205,18 @@ __device__ __forceinline__ void epilogue_tile_resid(const Tc05Params& p, uint32_
     // after the transpose resp. at the end of the chunk
     const float4 bv = (p.bias && col_ok) ? __ldg(reinterpret_cast<const float4*>(p.bias + gc))
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+    float gm = 0.f;   // (raw loads here, the product where the table is written: no scoreboard wait at the top)
+    float4 ph = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row_stats) {
       const int gcl = n0 + (c_begin + j) * 32 + lane;
-      const float gm = __ldg(p.rs_gamma + gcl);
+      gm = __ldg(p.rs_gamma + gcl);
       if (p.rs_k == 4) {
-        const float4 ph = __ldg(reinterpret_cast<const float4*>(p.rs_phi) + gcl);
-        gq = make_float4(gm * ph.x, gm * ph.y, gm * ph.z, gm * ph.w);
+        ph = __ldg(reinterpret_cast<const float4*>(p.rs_phi) + gcl);
       } else {
-        const float* ph = p.rs_phi + (size_t)gcl * p.rs_k;
-        gq.x = gm * __ldg(ph);
-        if (p.rs_k > 1) gq.y = gm * __ldg(ph + 1);
-        if (p.rs_k > 2) gq.z = gm * __ldg(ph + 2);
+        const float* pp = p.rs_phi + (size_t)gcl * p.rs_k;
+        ph.x = __ldg(pp);
+        if (p.rs_k > 1) ph.y = __ldg(pp + 1);
+        if (p.rs_k > 2) ph.z = __ldg(pp + 2);
       }
     }
     tmem_ld_wait();  // chunk j is in registers
@@ -268,7 +268,7 @@ __device__ __forceinline__ void epilogue_tile_resid(const Tc05Params& p, uint32_
         const int rl = 4 * i + sub_r;
         *reinterpret_cast<float4*>(scratch + rl * EPI_LD + 4 * ((lane & 7) ^ (rl & 7))) = v[i];
       }
-      *reinterpret_cast<float4*>(slot + lane * 16) = gq;
+      *reinterpret_cast<float4*>(slot + lane * 16) = make_float4(gm * ph.x, gm * ph.y, gm * ph.z, gm * ph.w);
       __syncwarp();
 #pragma unroll 2
       for (int q = 0; q < 8; ++q) {
@@ -300,6 +300,86 @@ __device__ __forceinline__ void epilogue_tile_resid(const Tc05Params& p, uint32_
       rec[1] = make_float4(rs_dot[2], rs_dot[3], 0.f, 0.f);
     }
   }
+}
+
+// ---- TMA-store epilogue with a run-time activation (kEpiStoreAct: patch_to_emb, the pooling head's score layers) -----
+// Same data path as the kEpiStore branch of epilogue_tile (thread = row, +bias, activation, swizzled staging tile,
+// TMA store), but with the chunk loop ROLLED: unrolled, the four activation bodies x 32 elements x NC chunks made this
+// kernel 146 KB of SASS, and its epilogue warps starved on instruction fetch like the residual epilogue's did.
+template <int BN, typename OutT, typename ReleaseFn>
+__device__ __forceinline__ void epilogue_tile_store_act(const Tc05Params& p, const CUtensorMap* tmC, uint32_t tmem_acc,
+                                                        uint64_t* tfull_bar, uint32_t tfull_parity, int m0, int n0,
+                                                        int ew, int lane, float* scratch, ReleaseFn release) {
+  constexpr int NC = (BN / 32) / 2;
+  constexpr int ROWB = 32 * (int)sizeof(OutT);      // 64 B (f16) or 128 B (fp32) per row
+  constexpr int NCH = ROWB / 16;                     // 16-byte chunks per row
+  constexpr int NBUF = (2 * 32 * ROWB <= 32 * EPI_LD * 4) ? 2 : 1;  // staging tiles in this warp's 4 KB scratch
+  constexpr int EPC = 16 / (int)sizeof(OutT);       // elements per 16-byte chunk
+  const int quad = ew & 3, c_begin = (ew >> 2) * NC;
+  mbar_wait(tfull_bar, tfull_parity);
+  tc_fence_after();
+  const uint32_t t_addr = tmem_acc + ((uint32_t)(quad * 32) << 16) + c_begin * 32;
+  uint32_t r[32];
+  tmem_ld_32x32(t_addr, r);
+  int buf = 0;
+#pragma unroll 1
+  for (int j = 0; j < NC; ++j) {
+    const int gcl = n0 + (c_begin + j) * 32 + lane;   // lane l keeps the bias of column l, broadcast by shuffle
+    const float bias_l = (p.bias && gcl < p.N) ? __ldg(p.bias + gcl) : 0.f;
+    tmem_ld_wait();
+    float fv[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) fv[i] = __uint_as_float(r[i]) + __shfl_sync(0xffffffffu, bias_l, i);
+    if (j + 1 < NC) {
+      tmem_ld_32x32(t_addr + (j + 1) * 32, r);  // overlaps the activation and the store of chunk j
+    } else {
+      tc_fence_before();
+      __syncwarp();
+      release();
+    }
+    const int act_j = (p.act_split > 0 && n0 + (c_begin + j) * 32 >= p.act_split) ? p.act2 : p.act;
+    if (act_j == kActRelu) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) fv[i] = fmaxf(fv[i], 0.f);
+    } else if (act_j == kActGelu) {  // (full unrolls: fv stays in registers; only the taken branch is fetched)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) fv[i] = gelu_fwd(fv[i]);
+    } else if (act_j == kActTanh) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) fv[i] = tanhf(fv[i]);
+    } else if (act_j == kActSigmoid) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) fv[i] = 1.f / (1.f + __expf(-fv[i]));
+    }
+    uint8_t* stage = reinterpret_cast<uint8_t*>(scratch) + buf * (32 * ROWB);
+    if (j >= NBUF) {  // the store that last read this buffer must have drained it
+      if (lane == 0) tma_store_wait_read<NBUF - 1>();
+      __syncwarp();
+    }
+    uint8_t* rowp = stage + lane * ROWB;
+    const int sw = ROWB == 128 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) {
+      const float* f = fv + q * EPC;
+      uint4 pk;
+      if (sizeof(OutT) == 2) {
+        pk = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4 % EPC], f[5 % EPC]),
+                        pack_h2(f[6 % EPC], f[7 % EPC]));
+      } else {
+        pk = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+      }
+      *reinterpret_cast<uint4*>(rowp + 16 * (q ^ sw)) = pk;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmC, stage, n0 + (c_begin + j) * 32, m0 + quad * 32);
+      tma_store_commit();
+    }
+    if (++buf == NBUF) buf = 0;
+  }
+  if (lane == 0) tma_store_wait_read<0>();  // both staging buffers are free again before the next tile reuses them
+  __syncwarp();
 }
 
 // Epilogue of one 128 x BN accumulator for one of the 8 epilogue warps (two per TMEM lane quadrant):
@@ -570,8 +650,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int TMEM_COLS = Cfg::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   float* sEpi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
@@ -720,6 +799,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       if constexpr (is_resid_mode(MODE))
         epilogue_tile_resid<MODE, BN>(p, tmem_base + acc * BN, &tfull[acc], aph, m0, n0, ew, lane, scratch,
                                       wt == cluster_id, [&] { if (lane == 0) mbar_arrive(te); }, cur, cons_slot);
+      else if constexpr (MODE == kEpiStoreAct)
+        epilogue_tile_store_act<BN, OutT>(p, &tmC, tmem_base + acc * BN, &tfull[acc], aph, m0, n0, ew, lane, scratch,
+                                          [&] { if (lane == 0) mbar_arrive(te); });
       else
         epilogue_tile<MODE, BN, OutT>(p, &tmC, tmem_base + acc * BN, &tfull[acc], aph, m0, n0, ew, lane,
                                       scratch, wt == cluster_id, [&] { if (lane == 0) mbar_arrive(te); });
@@ -763,8 +845,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
   constexpr int BN = P2_BN, STAGES = P2_STAGES;
   constexpr bool kTmaStore = is_store_mode(MODE);
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sA = smem;                               // [STAGES][128 x 64] my rows of A
   uint8_t* sB = smem + STAGES * A_BYTES;            // [STAGES][128 x 64] my half of the W tile
   float* sEpi = reinterpret_cast<float*>(smem + STAGES * P2_STAGE_BYTES);
@@ -934,14 +1015,21 @@ struct MapKey {
   }
 };
 struct MapSlot { MapKey key; CUtensorMap map; bool valid; };
-constexpr int kMapSlots = 128;
+// 128 sets x 4 ways: a direct-mapped table of 128 slots ping-ponged between colliding keys once 8 lanes x ~10 maps
+// were live (two encodes per call on the hot path, and cuTensorMapEncodeTiled inside ncu range replays)
+constexpr int kMapSets = 128, kMapWays = 4;
 bool cached_map(const MapKey& k, CUtensorMap* out, bool (*encode)(const MapKey&, CUtensorMap*)) {
-  static thread_local MapSlot slots[kMapSlots] = {};
+  static thread_local MapSlot slots[kMapSets * kMapWays] = {};
+  static thread_local unsigned char next_way[kMapSets] = {};
   size_t h = (reinterpret_cast<uintptr_t>(k.base) >> 8) * 0x9E3779B97F4A7C15ull;
   h ^= (size_t)k.a * 0x85EBCA6Bull ^ (size_t)k.b * 0xC2B2AE35ull ^ (size_t)k.c * 0x27D4EB2Full ^ (size_t)k.kind;
-  MapSlot& s = slots[(h >> 20) % kMapSlots];
-  if (s.valid && s.key == k) { *out = s.map; return true; }
+  const int set = (int)((h >> 20) % kMapSets);
+  MapSlot* ways = slots + set * kMapWays;
+  for (int w = 0; w < kMapWays; ++w)
+    if (ways[w].valid && ways[w].key == k) { *out = ways[w].map; return true; }
   if (!encode(k, out)) return false;
+  MapSlot& s = ways[next_way[set]];
+  next_way[set] = (unsigned char)((next_way[set] + 1) % kMapWays);
   s.key = k; s.map = *out; s.valid = true;
   return true;
 }
@@ -1140,6 +1228,9 @@ cudaError_t launch_pair(const __half* a, const __half* w, const Tc05Params& p, c
   }
   const int ptiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + P2_BN - 1) / P2_BN);
   int pairs = sm_count() / 2;
+  static const int env_cap = [] { const char* e = getenv("RRT_GEMM_SMS"); return e ? atoi(e) : -1; }();
+  const int sm_cap = env_cap >= 0 ? env_cap : g_gemm_sm_cap;   // see launch_cfg
+  if (sm_cap > 0 && pairs > sm_cap / 2) pairs = sm_cap / 2 > 0 ? sm_cap / 2 : 1;
   if (ptiles < pairs) pairs = ptiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(pairs * 2);
@@ -1181,7 +1272,9 @@ cudaError_t launch_mode(const __half* a, const __half* w, const Tc05Params& p, c
   if (g_gemm_narrow && tiles_m * tiles_n256 <= sm_count() && p.N % 128 == 0)
     return launch_cfg<MODE, 128, OutT, 1, 1>(a, w, p, stream);
   if (MODE == kEpiStoreAct) return launch_cfg<MODE, 256, OutT, 1, 1>(a, w, p, stream);  // no tuning variants
-  if (g_gemm_pair && tiles_m >= 2) return launch_pair<MODE, OutT>(a, w, p, stream);
+  // (the residual epilogues exist for the single-CTA kernel only: their cp.async ring follows its tile schedule)
+  if constexpr (!is_resid_mode(MODE) && MODE != kEpiStoreAct)
+    if (g_gemm_pair && tiles_m >= 2) return launch_pair<MODE, OutT>(a, w, p, stream);
   // bag-sized problems: clusters with multicast operand tiles when the tile grid allows it
   if (g_gemm_cluster == 22 && tiles_m >= 2 && tiles_n256 >= 2 && tiles_n256 % 2 == 0)
     return launch_cfg<MODE, 256, OutT, 2, 2>(a, w, p, stream);

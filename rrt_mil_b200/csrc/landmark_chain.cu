@@ -58,7 +58,7 @@ landmark_chain_kernel(const __grid_constant__ CUtensorMap tmLm, const __grid_con
                       const __grid_constant__ CUtensorMap tmLo, const __grid_constant__ CUtensorMap tmWp,
                       LmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* ring = smem;
   __half* tile = reinterpret_cast<__half*>(smem + STAGES * STAGE_BYTES);
   float* sbias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + TILE_BYTES);   // [192] qkv | [64] proj

@@ -340,8 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 rmsa_attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                       const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sQp = smem;                                             // 2 x [max(P16,128)][128 B] swizzled
   uint8_t* sQraw = sQp + 2 * (size_t)p.qp_bytes;                   // q_stages x [q_rows][128 B] swizzled (TMA)
   uint8_t* sK = sQraw + (size_t)p.q_stages * p.q_bytes;            // kv_stages x [P16][128 B]
@@ -694,7 +693,7 @@ bool make_map3(CUtensorMap* tm, const __half* base, int ld, int P, int R, int ro
 struct MapKey3 { const void* base; int ld, P, R, rows; };
 struct MapSlot3 { MapKey3 k; CUtensorMap m; bool valid; };
 bool cached_map3(CUtensorMap* tm, const __half* base, int ld, int P, int R, int rows) {
-  static thread_local MapSlot3 slots[48];
+  static thread_local MapSlot3 slots[96];
   static thread_local int next = 0;
   for (auto& s : slots)
     if (s.valid && s.k.base == base && s.k.ld == ld && s.k.P == P && s.k.R == R && s.k.rows == rows) {
@@ -703,7 +702,7 @@ bool cached_map3(CUtensorMap* tm, const __half* base, int ld, int P, int R, int 
     }
   if (!make_map3(tm, base, ld, P, R, rows)) return false;
   MapSlot3& s = slots[next];
-  next = (next + 1) % 48;
+  next = (next + 1) % 96;
   s.k = MapKey3{base, ld, P, R, rows};
   s.m = *tm;
   s.valid = true;

@@ -13,6 +13,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// First 1024-byte boundary (SWIZZLE_128B atoms) at or behind the start of the dynamic shared memory.  Pointer
+// arithmetic on the __shared__ symbol, not an integer round trip: through (uintptr_t + 1023) & ~1023 the compiler
+// loses the address space and every ordinary access to the buffers behind it becomes a GENERIC LD.E / ST.E.
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* smem_raw) {
+  return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -35,13 +35,13 @@ def timed(lanes, steps=20):
 
 quick = "--quick" in sys.argv
 print("RRT_GEMM_CLUSTER =", os.environ.get("RRT_GEMM_CLUSTER"), " RRT_ATTN =", os.environ.get("RRT_ATTN"))
-for lanes in ((1, 4) if quick else (1, 2, 3, 4, 6, 8)):
+for lanes in ((1, 4) if quick else ((8,) if "--l8" in sys.argv else (1, 2, 3, 4, 6, 8))):
     us, host = timed(lanes)
     print(f"lanes={lanes}: {us:7.2f} us/bag   host enqueue {host:6.2f} us/bag", flush=True)
 
 fwd = ["ln_partition", "qkv_gemm", "rmsa_attention", "proj_gemm_residual", "crmsa_landmarks",
        "landmark_qkv_gemm", "landmark_attention", "landmark_proj_gemm", "crmsa_dispatch_final_ln"]
-for lanes in (() if quick else (1, 4)):
+for lanes in (() if quick else ((8,) if "--l8" in sys.argv else (1, 4))):
     base, _ = timed(lanes)
     print(f"--- lanes={lanes}: all stages {base:.2f} us/bag")
     for n in fwd:
