@@ -420,44 +420,55 @@ rmsa_attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           umma_commit(&bars[kKvEmpty + n % KS]);  // K and V of this stage are consumed (by the tensor core)
           stamp2(p, 16, n, 2);
         }
-        // loads: those of item j must go out now (S of item j is next: wait for the ring slot if need be);
-        // further ahead only into ring slots that are free already, so that a slow tail never blocks the MMAs
-        while (nlq < total && nlq <= j + QS) {
-          const int st = nlq % QS, u = nlq / QS;
-          if (nlq <= j) mbar_wait_c(&bars[kQEmpty + st], (u & 1) ^ 1);
-          else if (!mbar_test(&bars[kQEmpty + st], (u & 1) ^ 1)) break;
-          const int item = first + nlq * step, rho = item / p.heads, h = item - rho * p.heads;
-          mbar_arrive_expect_tx(&bars[kQFull + st], p.q_bytes);
-          tma_load_3d(sQraw + (size_t)st * p.q_bytes, &tmQ, &bars[kQFull + st], h * HD, -p.pad, rho);
-          ++nlq;
-        }
-        while (nlk < total && nlk <= j + KS) {
-          const int st = nlk % KS, u = nlk / KS;
-          if (nlk <= j) mbar_wait_c(&bars[kKvEmpty + st], (u & 1) ^ 1);
-          else if (!mbar_test(&bars[kKvEmpty + st], (u & 1) ^ 1)) break;
-          const int item = first + nlk * step, rho = item / p.heads, h = item - rho * p.heads;
-          mbar_arrive_expect_tx(&bars[kKvFull + st], 2 * p.kv_bytes);
-          tma_load_3d(sK + (size_t)st * p.kv_bytes, &tmKV, &bars[kKvFull + st], p.D + h * HD, 0, rho);
-          tma_load_3d(sV + (size_t)st * p.kv_bytes, &tmKV, &bars[kKvFull + st], 2 * p.D + h * HD, 0, rho);
-          ++nlk;
-        }
-        if (j < total) {
-          // the slot's S / P columns are free: aliased layout -> once the epilogue of item n has read O (which
-          // lives over S); separate layout -> already (the tensor pipe runs O of item n, which reads P, before this
-          // S: same issuing thread, in order; every softmax thread has read S: p_ready)
-          if (n >= 0 && !p.sep_o) mbar_wait_c(&bars[kODone + (n & 1)], (n >> 1) & 1);
-          if (n >= 0) stamp2(p, 16, n, 3);
-          mbar_wait_c(&bars[kQpFull + (j & 1)], (j >> 1) & 1);
-          mbar_wait_c(&bars[kKvFull + j % KS], (j / KS) & 1);
-          tc_fence_after();
-          const uint64_t ad = umma_desc_k_sw128(smem_u32(sQp + (size_t)(j & 1) * p.qp_bytes));
-          const uint64_t kd = umma_desc_k_sw128(smem_u32(sK + (size_t)(j % KS) * p.kv_bytes));
-          const uint32_t tS = tmem_base + (uint32_t)(j & 1) * p.slot_stride;
+        // S of item j goes out right behind O of item j - 2 when its operands were requested in an earlier step
+        // (the usual case from j = 2 on); otherwise the loads first.  (One code copy of each: the flag only
+        // orders the two sections.)
+        const bool s_first = j < total && nlq > j && nlk > j;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          if ((pass == 0) == s_first) {
+            if (j < total) {
+              // the slot's S / P columns are free: aliased layout -> once the epilogue of item n has read O (which
+              // lives over S); separate layout -> already (the tensor pipe runs O of item n, which reads P, before
+              // this S: same issuing thread, in order; every softmax thread has read S: p_ready)
+              if (n >= 0 && !p.sep_o) mbar_wait_c(&bars[kODone + (n & 1)], (n >> 1) & 1);
+              if (n >= 0) stamp2(p, 16, n, 3);
+              mbar_wait_c(&bars[kQpFull + (j & 1)], (j >> 1) & 1);
+              mbar_wait_c(&bars[kKvFull + j % KS], (j / KS) & 1);
+              tc_fence_after();
+              const uint64_t ad = umma_desc_k_sw128(smem_u32(sQp + (size_t)(j & 1) * p.qp_bytes));
+              const uint64_t kd = umma_desc_k_sw128(smem_u32(sK + (size_t)(j % KS) * p.kv_bytes));
+              const uint32_t tS = tmem_base + (uint32_t)(j & 1) * p.slot_stride;
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_f16(tS, ad + 2 * k, kd + 2 * k, idesc_s, k != 0);
-          umma_commit(&bars[kSFull + (j & 1)]);
-          umma_commit(&bars[kQpEmpty + (j & 1)]);  // the S product has read rows 0..127 of Q'
-          if (n >= 0) stamp2(p, 16, n, 4);
+              for (int k = 0; k < HD / 16; ++k) umma_f16(tS, ad + 2 * k, kd + 2 * k, idesc_s, k != 0);
+              umma_commit(&bars[kSFull + (j & 1)]);
+              umma_commit(&bars[kQpEmpty + (j & 1)]);  // the S product has read rows 0..127 of Q'
+              if (n >= 0) stamp2(p, 16, n, 4);
+            }
+          } else {
+            // loads: those of item j must go out now (S of item j is next: wait for the ring slot if need be);
+            // further ahead only into ring slots that are free already, so that a slow tail never blocks the MMAs
+            while (nlq < total && nlq <= j + QS) {
+              const int st = nlq % QS, u = nlq / QS;
+              if (nlq <= j) mbar_wait_c(&bars[kQEmpty + st], (u & 1) ^ 1);
+              else if (!mbar_test(&bars[kQEmpty + st], (u & 1) ^ 1)) break;
+              const int item = first + nlq * step, rho = item / p.heads, h = item - rho * p.heads;
+              mbar_arrive_expect_tx(&bars[kQFull + st], p.q_bytes);
+              tma_load_3d(sQraw + (size_t)st * p.q_bytes, &tmQ, &bars[kQFull + st], h * HD, -p.pad, rho);
+              ++nlq;
+            }
+            while (nlk < total && nlk <= j + KS) {
+              const int st = nlk % KS, u = nlk / KS;
+              if (nlk <= j) mbar_wait_c(&bars[kKvEmpty + st], (u & 1) ^ 1);
+              else if (!mbar_test(&bars[kKvEmpty + st], (u & 1) ^ 1)) break;
+              const int item = first + nlk * step, rho = item / p.heads, h = item - rho * p.heads;
+              mbar_arrive_expect_tx(&bars[kKvFull + st], 2 * p.kv_bytes);
+              tma_load_3d(sK + (size_t)st * p.kv_bytes, &tmKV, &bars[kKvFull + st], p.D + h * HD, 0, rho);
+              tma_load_3d(sV + (size_t)st * p.kv_bytes, &tmKV, &bars[kKvFull + st], 2 * p.D + h * HD, 0, rho);
+              ++nlk;
+            }
+            if (n >= 0) stamp2(p, 16, n, 5);
+          }
         }
       }
     }

@@ -91,7 +91,7 @@ with torch.no_grad():
         for n in range(4):
             r = full[16 + n].tolist()
             print(f"  issuer item {n}: " + " ".join(f"{nm}={r[i] - t0 if r[i] else -1}" for i, nm in
-                  enumerate(["top", "p_ready", "o_issued", "o_done", "s_issued"])))
+                  enumerate(["top", "p_ready", "o_issued", "s_go", "s_issued", "loads_done"])))
 lib.rrt_debug_set_attention_kernel(1)
 print("FAILED" if bad else "all OK")
 sys.exit(1 if bad else 0)
