@@ -212,6 +212,10 @@ struct Workspace {
   float* lout;     // [k*R_c, D]
   float* hidden;   // [Np_c, D/4] (crmsa_mlp)
   __half* wconv;   // [3D*D + D*D] fp16 weights when the caller passes no shadow
+  // the same, per attention module (R-MSA layer i; [RRT_MAX_RMSA_LAYERS] = the landmark MHA).  Inference: all alias
+  // wconv.  Training tape: one buffer each, so that the backward's input-gradient GEMMs read the forward's fp16
+  // weights (MN-major) instead of converting + transposing them again
+  __half* wconv_m[RRT_MAX_RMSA_LAYERS + 1];
   __half* ffn_z;   // [Hi*Hi, D] LayerNorm(norm2) rows of the FFN (ffn = 1; Hi = ceil(sqrt(L)))
   __half* ffn_h;   // [L, ffn_hidden] fp16 hidden activations
   float* ffn_out;  // [L, D] x + mlp(norm2(x))
@@ -279,6 +283,11 @@ bool carve(const rrt_config* c, int64_t L, void* base, Workspace* ws, bool train
   ws->lout = (float*)take(T * D * 4);
   ws->hidden = (float*)take(mlp ? np_c * (D / 4) * 4 : 0);
   ws->wconv = (__half*)take(4 * D * D * 2);
+  for (int i = 0; i <= RRT_MAX_RMSA_LAYERS; ++i) ws->wconv_m[i] = ws->wconv;
+  if (train) {
+    for (int i = 0; i < c->n_rmsa_layers; ++i) ws->wconv_m[i] = (__half*)take(4 * D * D * 2);
+    if (c->cr_msa) ws->wconv_m[RRT_MAX_RMSA_LAYERS] = (__half*)take(4 * D * D * 2);
+  }
   const size_t Hi = (size_t)ceil_sqrt(L), FH = c->ffn ? (size_t)c->ffn_hidden : 0;
   ws->ffn_z = (__half*)take(c->ffn ? Hi * Hi * D * 2 : 0);
   ws->ffn_h = (__half*)take((size_t)L * FH * 2);
@@ -362,9 +371,9 @@ int rmsa_block(const rrt_config* c, const float* norm_w, const float* norm_b,
     return fail(RRT_E_INVALID, "bad geometry");
   const int D = c->dim;
   const __half *wq, *wp;
-  int rc = f16_weight(a->qkv_w, a->qkv_w_f16, ws.wconv, (size_t)3 * D * D, st, &wq);
+  int rc = f16_weight(a->qkv_w, a->qkv_w_f16, ws.wconv_m[layer], (size_t)3 * D * D, st, &wq);
   if (rc) return rc;
-  rc = f16_weight(a->proj_w, a->proj_w_f16, ws.wconv + (size_t)3 * D * D, (size_t)D * D, st, &wp);
+  rc = f16_weight(a->proj_w, a->proj_w_f16, ws.wconv_m[layer] + (size_t)3 * D * D, (size_t)D * D, st, &wp);
   if (rc) return rc;
   rrt::GemmEpilogue e1;
   e1.bias = c->qkv_bias ? a->qkv_b : nullptr;
@@ -461,10 +470,10 @@ int crmsa_block(const rrt_config* c, const rrt_weights* w, const float* x1, cons
     phi = w->cr_phi;
   }
   const __half *wq, *wp;
-  int rc = f16_weight(w->cr_attn.qkv_w, w->cr_attn.qkv_w_f16, ws.wconv, (size_t)3 * D * D, st, &wq);
+  __half* const wcr = ws.wconv_m[RRT_MAX_RMSA_LAYERS];
+  int rc = f16_weight(w->cr_attn.qkv_w, w->cr_attn.qkv_w_f16, wcr, (size_t)3 * D * D, st, &wq);
   if (rc) return rc;
-  rc = f16_weight(w->cr_attn.proj_w, w->cr_attn.proj_w_f16, ws.wconv + (size_t)3 * D * D,
-                  (size_t)D * D, st, &wp);
+  rc = f16_weight(w->cr_attn.proj_w, w->cr_attn.proj_w_f16, wcr + (size_t)3 * D * D, (size_t)D * D, st, &wp);
   if (rc) return rc;
   static const int front_mode = [] {  // tuning knob: RRT_CRMSA_FRONT=split (default) | fused | legacy
     const char* e = getenv("RRT_CRMSA_FRONT");
@@ -976,8 +985,7 @@ RRT_API int rrt_patch_embed_backward(const float* dout, const float* out, const 
                                       relu && drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f, gelu ? 1 : 0),
            "patch_embed grad rows");
   RRT_CUDA(cudaMemsetAsync(dw, 0, (size_t)out_dim * in_dim * 4, st), "zero dw");
-  RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad(dz16, x16, dw, (int)L, out_dim, in_dim, st), "patch_embed wgrad");
-  RRT_CUDA(rrt::launch_scale_by_inv(dw, (size_t)out_dim * in_dim, amax, st), "patch_embed unscale");
+  RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad(dz16, x16, dw, (int)L, out_dim, in_dim, st, amax), "patch_embed wgrad");
   return RRT_OK;
 }
 
@@ -1039,8 +1047,7 @@ RRT_API int rrt_attn_pool_backward(const float* h, int64_t L, int32_t dim, int32
   RRT_CUDA(rrt::launch_gemm_tcgen05(dhid16, wT, dz16, true, (int)L, dim, N, e, st), "pool dgrad");
   RRT_CUDA(rrt::launch_add_scaled_f16(dh, dz16, (size_t)L * dim, amax, st), "pool dh accumulate");
   RRT_CUDA(cudaMemsetAsync(dw1, 0, (size_t)N * dim * 4, st), "zero dw1");
-  RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad(dhid16, h16, dw1, (int)L, N, dim, st), "pool wgrad");
-  RRT_CUDA(rrt::launch_scale_by_inv(dw1, (size_t)N * dim, amax, st), "pool wgrad unscale");
+  RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad(dhid16, h16, dw1, (int)L, N, dim, st, amax), "pool wgrad");
   return RRT_OK;
 }
 
@@ -1257,6 +1264,12 @@ bool wgrad_mn() {
   return on;
 }
 
+// 1 (default): the input-gradient GEMMs read the forward's fp16 weight MN-major; 0 (RRT_DGRAD=transpose): transposed copy
+bool dgrad_mn() {
+  static const bool on = [] { const char* e = getenv("RRT_DGRAD"); return !(e && !strcmp(e, "transpose")); }();
+  return on;
+}
+
 int check_backward_support(const rrt_config* c, int64_t L) {
   if (c->pos != RRT_POS_NONE) {
     if (c->n_rmsa_layers == 0) return fail(RRT_E_INVALID, "backward: PEG / PPEG without an R-MSA layer is not covered");
@@ -1293,33 +1306,39 @@ int check_backward_support(const rrt_config* c, int64_t L) {
 // 1 (default): weight gradients read dy / act MN-major straight from their row-major buffers
 // (launch_gemm_tcgen05_wgrad); 0 (RRT_WGRAD=transpose): transposed fp16 copies + the K-major GEMM.
 
+// w16: the forward's fp16 copy of w (rrt_attn_weights::*_f16) or null.  With it the input-gradient GEMM reads the
+// weight MN-major as it is (launch_gemm_tcgen05_dgrad); without, a transposed fp16 copy is made first.
 int linear_backward(const __half* dy, const __half* dyT, const __half* act, const float* w, int M,
                     int C_out, int C_in, const uint32_t* amax, __half* d_in, float* dW,
-                    BwdWorkspace& b, cudaStream_t st) {
+                    BwdWorkspace& b, cudaStream_t st, const void* w16 = nullptr) {
   const int M64 = (M + 63) / 64 * 64;
   rrt::GemmEpilogue e;
-  if (d_in) {
+  if (d_in && w16 && dgrad_mn()) {
+    StageScope s_(kStBwdDgrad, st);
+    RRT_CUDA(rrt::launch_gemm_tcgen05_dgrad(dy, static_cast<const __half*>(w16), d_in, M, C_out, C_in, st),
+             "dgrad gemm (MN-major weight)");
+  } else if (d_in) {
     { StageScope s_(kStBwdPrep, st);
       RRT_CUDA(rrt::launch_wt_convert(w, b.wT, C_out, C_in, st), "weight transpose"); }
     StageScope s_(kStBwdDgrad, st);
     RRT_CUDA(rrt::launch_gemm_tcgen05(dy, b.wT, d_in, true, M, C_in, C_out, e, st), "dgrad gemm");
   }
   if (wgrad_mn()) {
-    StageScope s_(kStBwdWgrad, st, 3);
+    // (the split-K partial sums are unscaled in the GEMM epilogue: the factor is a power of two)
+    StageScope s_(kStBwdWgrad, st, 2);
     RRT_CUDA(cudaMemsetAsync(dW, 0, (size_t)C_out * C_in * sizeof(float), st), "zero weight gradient");
-    RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad(dy, act, dW, M, C_out, C_in, st), "wgrad gemm (MN-major)");
-    RRT_CUDA(rrt::launch_scale_by_inv(dW, (size_t)C_out * C_in, amax, st), "wgrad unscale");
+    RRT_CUDA(rrt::launch_gemm_tcgen05_wgrad(dy, act, dW, M, C_out, C_in, st, amax), "wgrad gemm (MN-major)");
     return RRT_OK;
   }
   { StageScope s_(kStBwdPrep, st);
     RRT_CUDA(rrt::launch_transpose_f16(act, M, C_in, b.actT, nullptr, nullptr, st), "activation transpose"); }
-  { StageScope s_(kStBwdWgrad, st, 3);
+  { StageScope s_(kStBwdWgrad, st, 2);
     // few output tiles, K = every token of the bag: split-K over all SMs into the zeroed gradient
     rrt::GemmEpilogue ew;
     ew.mode = rrt::kEpiAtomicAdd;
+    ew.unscale_amax = amax;
     RRT_CUDA(cudaMemsetAsync(dW, 0, (size_t)C_out * C_in * sizeof(float), st), "zero weight gradient");
-    RRT_CUDA(rrt::launch_gemm_tcgen05(dyT, b.actT, dW, false, C_out, C_in, M64, ew, st), "wgrad gemm");
-    RRT_CUDA(rrt::launch_scale_by_inv(dW, (size_t)C_out * C_in, amax, st), "wgrad unscale"); }
+    RRT_CUDA(rrt::launch_gemm_tcgen05(dyT, b.actT, dW, false, C_out, C_in, M64, ew, st), "wgrad gemm"); }
   return RRT_OK;
 }
 
@@ -1330,9 +1349,12 @@ int linear_backward(const __half* dy, const __half* dyT, const __half* act, cons
 int attention_module_backward(const rrt_config* c, const rrt_attn_weights* a, const rrt_attn_grads* ga,
                               const __half* z, const __half* qkv, const __half* o, int R, int P,
                               int heads, bool epeg, const uint32_t* amax, BwdWorkspace& b,
-                              cudaStream_t st, const float* qkv_f32 = nullptr) {
+                              cudaStream_t st, const float* qkv_f32 = nullptr, const __half* w16_tape = nullptr) {
   const int D = c->dim, M = R * P;
-  int rc = linear_backward(b.dy, b.dyT, o, a->proj_w, M, D, D, amax, b.dO, ga->proj_w, b, st);
+  // fp16 weights of the forward: the caller's shadows, else the copies the training forward left in its tape
+  const void* wq16 = a->qkv_w_f16 ? a->qkv_w_f16 : (const void*)w16_tape;
+  const void* wp16 = a->proj_w_f16 ? a->proj_w_f16 : (w16_tape ? (const void*)(w16_tape + (size_t)3 * D * D) : nullptr);
+  int rc = linear_backward(b.dy, b.dyT, o, a->proj_w, M, D, D, amax, b.dO, ga->proj_w, b, st, wp16);
   if (rc) return rc;
   { StageScope s_(kStBwdAttn, st);
     if (qkv_f32)
@@ -1347,7 +1369,7 @@ int attention_module_backward(const rrt_config* c, const rrt_attn_weights* a, co
     __half* dqkvT = wgrad_mn() ? nullptr : b.dqkvT;
     if (colsum || dqkvT)
       RRT_CUDA(rrt::launch_transpose_f16(b.dqkv, M, 3 * D, dqkvT, colsum, amax, st), "dqkv transpose"); }
-  return linear_backward(b.dqkv, b.dqkvT, z, a->qkv_w, M, 3 * D, D, amax, b.dz, ga->qkv_w, b, st);
+  return linear_backward(b.dqkv, b.dqkvT, z, a->qkv_w, M, 3 * D, D, amax, b.dz, ga->qkv_w, b, st, wq16);
 }
 
 int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, const float* dout,
@@ -1388,7 +1410,8 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
     const bool lm_f32 = cr_hd != 32 && cr_hd != 64 && cr_hd != 128;   // the forward's fp32 landmark path
     int rc = attention_module_backward(c, &w->cr_attn, &gr->cr_attn, tp.lm,
                                        reinterpret_cast<const __half*>(tp.lqkv), tp.lo, k, gc.R,
-                                       c->crmsa_heads, false, &b.amax[0], b, st, lm_f32 ? tp.lqkv : nullptr);
+                                       c->crmsa_heads, false, &b.amax[0], b, st, lm_f32 ? tp.lqkv : nullptr,
+                                       tp.wconv_m[RRT_MAX_RMSA_LAYERS] != tp.wconv ? tp.wconv_m[RRT_MAX_RMSA_LAYERS] : nullptr);
     if (rc) return rc;
     float* out = nl > 0 ? b.ga : dx;
     const float dh_weight = (nl == 0 && c->all_shortcut) ? 2.f : 1.f;
@@ -1482,7 +1505,8 @@ int encoder_backward(const rrt_config* c, const rrt_weights* w, const float* x, 
                                           ga->proj_b, st, ldrop),
                "gradient partition"); }
     int rc = attention_module_backward(c, &w->layer_attn[i], ga, tp.z[i], tp.qkv[i], tp.o[i], gg.R, gg.P,
-                                       c->n_heads, c->epeg != 0, &b.amax[am], b, st);
+                                       c->n_heads, c->epeg != 0, &b.amax[am], b, st, nullptr,
+                                       tp.wconv_m[i] != tp.wconv ? tp.wconv_m[i] : nullptr);
     if (rc) return rc;
     float* out = i == 0 ? dx : (g == b.ga ? b.gb : b.ga);
     const float* shortcut = (i == 0 && c->all_shortcut) ? b.dh : nullptr;   // d/dx of "+ x" (modules/rrt.py:195)

@@ -224,13 +224,6 @@ __global__ void __launch_bounds__(256) wt_convert_kernel(const float* __restrict
     if (k0 + r < K && n0 + tx < N) wT[(size_t)(k0 + r) * N + n0 + tx] = __float2half_rn(t[tx][r]);
 }
 
-__global__ void __launch_bounds__(256) scale_by_inv_kernel(float* __restrict__ x, size_t n,
-                                                           const uint32_t* __restrict__ amax) {
-  const float inv = grad_inv_scale(__ldg(amax));
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    x[i] *= inv;
-}
-
 }  // namespace
 
 cudaError_t launch_amax(const float* x, size_t n, uint32_t* amax, cudaStream_t stream) {
@@ -352,14 +345,6 @@ cudaError_t launch_ln_backward(const float* x, const float* x_add, const float* 
 cudaError_t launch_wt_convert(const float* w, __half* wT, int N, int K, cudaStream_t stream) {
   dim3 gr((K + 31) / 32, (N + 31) / 32);
   wt_convert_kernel<<<gr, 256, 0, stream>>>(w, wT, N, K);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_scale_by_inv(float* x, size_t n, const uint32_t* amax, cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  scale_by_inv_kernel<<<blocks, 256, 0, stream>>>(x, n, amax);
   return cudaGetLastError();
 }
 

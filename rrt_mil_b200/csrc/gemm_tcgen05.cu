@@ -16,6 +16,7 @@
 // and half the operand traffic; with fp32 (tf32) tiles this kernel was bound by L2->SMEM operand
 // bytes (profiles/r01_ncu_full_v2_tf32_summary.csv).
 #include <cstdlib>
+#include "backward.cuh"
 #include "kernels.cuh"
 #include "sm100.cuh"
 
@@ -70,6 +71,9 @@ struct Tc05Params {
   int rs_k;
   Dropout drop;      // kEpiResidualUnpartDrop only
   int ksplit;        // >= 1: the K loop of every tile is cut into ksplit work items (kEpiAtomicAdd)
+  // kEpiAtomicAdd, optional: amax word of the scaled fp16 gradient operand; every partial sum is multiplied by
+  // grad_inv_scale (a power of two: exact) before it is added, so the result needs no separate unscale pass
+  const uint32_t* unscale_amax;
   long long* trace;  // debug: per-CTA clock64 stamps (tools/gemm_trace.py), null in production
 };
 
@@ -566,7 +570,13 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (orow[i] >= 0 && col_ok) {
-          if (MODE == kEpiAtomicAdd) red_add4(out, (size_t)orow[i] * p.N + gc, v[i]);
+          if (MODE == kEpiAtomicAdd) {
+            if (p.unscale_amax) {
+              const float us = grad_inv_scale(__ldg(p.unscale_amax));
+              v[i].x *= us; v[i].y *= us; v[i].z *= us; v[i].w *= us;
+            }
+            red_add4(out, (size_t)orow[i] * p.N + gc, v[i]);
+          }
           else store_out4(out, (size_t)orow[i] * p.N + gc, v[i]);
         }
       if (first && threadIdx.x == 128 && j < 2) stamp(p, 12 + 3 * j);
@@ -636,8 +646,9 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
 // MNMAJOR: both operands arrive MN-major -- A = a[K, M], W = w[K, N] row-major, i.e. C = a^T @ w with the
 // contraction over ROWS (the weight-gradient GEMM: dW[C_out, C_in] = dY[tokens, C_out]^T act[tokens, C_in],
 // straight from the row-major activations, no transposed copies).  Tiles are staged as 64 x 64 TMA boxes
-// (sm100.cuh::umma_desc_mn_sw128).
-template <int MODE, int BN, typename OutT, int CM, int CN, bool MNMAJOR = false>
+// (sm100.cuh::umma_desc_mn_sw128).  MNMAJOR = 2: only W is MN-major -- C = a @ w with w[K, N] row-major (the
+// input-gradient GEMM d_in = dY W straight from the forward's fp16 weight, no transposed copy).
+template <int MODE, int BN, typename OutT, int CM, int CN, int MNMAJOR = 0>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                         const __grid_constant__ CUtensorMap tmB,
@@ -720,7 +731,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           if (is_a) {
             mbar_arrive_expect_tx(&full[s], A_BYTES);  // my slice + the peers' slices of MY tile
             uint8_t* dst = sA + s * A_BYTES + cj * (A_BYTES / CN);
-            if (MNMAJOR) {
+            if (MNMAJOR == 1) {
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j)  // 64 (M) x 64 (K rows) boxes, 8 KB each
                 tma_load_2d(dst + j * 8192, &tmA, &full[s], m0 + 64 * j, kb * BK);
@@ -745,7 +756,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc(kFmtF16, BM, BN) | (MNMAJOR ? kIdescMnMajorAB : 0u);
+      constexpr uint32_t idesc = umma_idesc(kFmtF16, BM, BN) |
+                                 (MNMAJOR == 1 ? kIdescMnMajorAB : (MNMAJOR == 2 ? kIdescMnMajorB : 0u));
       int s = 0, ph = 0, acc = 0, aph = 0;
       for (int wt = cluster_id; wt < num_work; wt += num_clusters) {
         const int ks = wt / num_ctiles;
@@ -757,15 +769,15 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           mbar_wait(&full[s], ph);
           tc_fence_after();
           if (wt == cluster_id && kb == kb0) stamp(p, 4);
-          const uint64_t ad = MNMAJOR ? umma_desc_mn_sw128(smem_u32(sA + s * A_BYTES))
+          const uint64_t ad = MNMAJOR == 1 ? umma_desc_mn_sw128(smem_u32(sA + s * A_BYTES))
                                       : umma_desc_k_sw128(smem_u32(sA + s * A_BYTES));
           const uint64_t bd = MNMAJOR ? umma_desc_mn_sw128(smem_u32(sB + s * B_BYTES))
                                       : umma_desc_k_sw128(smem_u32(sB + s * B_BYTES));
           // K-major: 16 fp16 = 32 bytes per MMA along K (+2 in 16-B units); MN-major: 16 rows of 128 B (+128)
-          constexpr int kstep = MNMAJOR ? 128 : 2;
+          constexpr int kstep_a = MNMAJOR == 1 ? 128 : 2, kstep_b = MNMAJOR ? 128 : 2;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_f16(d_tmem, ad + kstep * k, bd + kstep * k, idesc, ((kb - kb0) | k) != 0);
+            umma_f16(d_tmem, ad + kstep_a * k, bd + kstep_b * k, idesc, ((kb - kb0) | k) != 0);
           // smem stage reusable once these MMAs have read it: tell every CTA that writes into it
           if (CSIZE > 1) umma_commit_mcast(&empty[s], (uint16_t)(mask_a | mask_b));
           else umma_commit(&empty[s]);
@@ -1286,7 +1298,7 @@ cudaError_t launch_mode(const __half* a, const __half* w, const Tc05Params& p, c
 // dw[C_out, C_in] (fp32, zeroed by the caller) += dy[rows, C_out]^T @ act[rows, C_in]: both operands
 // MN-major straight from the row-major activations, split-K over the rows so that every SM has work.
 cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float* dw, int rows, int C_out,
-                                      int C_in, cudaStream_t stream) {
+                                      int C_in, cudaStream_t stream, const uint32_t* unscale_amax) {
   if (rows < 1 || C_out < 8 || C_in < 8 || (C_out % 8) || (C_in % 8)) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(act) | reinterpret_cast<uintptr_t>(dw)) & 15)
     return cudaErrorInvalidValue;
@@ -1300,6 +1312,7 @@ cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float
   p.act_split = 0;
   p.rs_part = nullptr; p.rs_gamma = nullptr; p.rs_phi = nullptr; p.rs_k = 0;
   p.trace = nullptr;
+  p.unscale_amax = unscale_amax;
   const int tiles = ((C_out + BM - 1) / BM) * ((C_in + BN - 1) / BN), KB = (rows + BK - 1) / BK;
   int ksplit = sm_count() / tiles;
   if (ksplit > KB) ksplit = KB;
@@ -1307,7 +1320,7 @@ cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float
   p.ksplit = ksplit;
   CUtensorMap tmA, tmB;
   if (!make_map_mn(&tmA, dy, rows, C_out) || !make_map_mn(&tmB, act, rows, C_in)) return cudaErrorUnknown;
-  auto kern = gemm_f16_tcgen05_kernel<kEpiAtomicAdd, BN, float, 1, 1, true>;
+  auto kern = gemm_f16_tcgen05_kernel<kEpiAtomicAdd, BN, float, 1, 1, 1>;
   static DeviceOnce configured;
   if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -1316,6 +1329,38 @@ cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float
   int ctas = tiles * ksplit;
   if (ctas > sm_count()) ctas = sm_count();
   kern<<<ctas, NTHREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA, p);
+  return cudaGetLastError();
+}
+
+// input gradient: d_in[rows, C_in] (fp16) = dy[rows, C_out] (fp16, K-major) @ w16[C_out, C_in] (fp16, row-major =
+// MN-major B operand): the forward's fp16 weight as it is, no transposed copy
+cudaError_t launch_gemm_tcgen05_dgrad(const __half* dy, const __half* w16, __half* d_in, int rows, int C_out,
+                                      int C_in, cudaStream_t stream) {
+  constexpr int BN = 256;
+  using Cfg = TileCfg<BN>;
+  if (rows < 1 || C_out < BK || (C_out % BK) || C_in < 8 || (C_in % 8)) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(w16) | reinterpret_cast<uintptr_t>(d_in)) & 15)
+    return cudaErrorInvalidValue;
+  Tc05Params p{};
+  p.M = rows; p.N = C_in; p.K = C_out;
+  p.C = d_in;
+  p.act = kActNone; p.act2 = kActNone; p.act_split = 0;
+  p.ksplit = 1;
+  CUtensorMap tmA, tmB, tmC;
+  if (!make_map(&tmA, dy, rows, C_out, BM) || !make_map_mn(&tmB, w16, C_out, C_in) ||
+      !make_store_map(&tmC, d_in, rows, C_in, 2))
+    return cudaErrorUnknown;
+  auto kern = gemm_f16_tcgen05_kernel<kEpiStore, BN, __half, 1, 1, 2>;
+  static DeviceOnce configured;
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+  }
+  const int tiles = ((rows + BM - 1) / BM) * ((C_in + BN - 1) / BN);
+  int ctas = sm_count();
+  if (g_gemm_sm_cap > 0 && ctas > g_gemm_sm_cap) ctas = g_gemm_sm_cap;
+  if (tiles < ctas) ctas = tiles;
+  kern<<<ctas, NTHREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   return cudaGetLastError();
 }
 
@@ -1342,6 +1387,7 @@ cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool 
   p.act_split = epi.act_split;
   if (p.act_split % 32 || p.act_split < 0) return cudaErrorInvalidValue;
   p.rs_part = nullptr; p.rs_gamma = nullptr; p.rs_phi = nullptr; p.rs_k = 0;
+  p.unscale_amax = epi.mode == kEpiAtomicAdd ? epi.unscale_amax : nullptr;
   if (epi.rs_part) {
     if (!is_resid_mode(epi.mode) || !epi.rs_gamma || !epi.rs_phi || epi.rs_k < 1 || epi.rs_k > 4 ||
         gemm_tcgen05_rowstat_parts(M, N) == 0)

@@ -49,6 +49,9 @@ struct GemmEpilogue {
   const float* rs_gamma = nullptr;  // [N]  cr_msa.norm.weight
   const float* rs_phi = nullptr;    // [N, rs_k]
   int rs_k = 0;
+  // kEpiAtomicAdd, optional: amax word of a scaled fp16 gradient operand (backward.cuh); partial sums are multiplied
+  // by its (power-of-two) inverse scale before they are added
+  const uint32_t* unscale_amax = nullptr;
 };
 int gemm_tcgen05_rowstat_parts(int M, int N);
 
@@ -59,8 +62,12 @@ bool gemm_tcgen05_supported(int M, int N, int K);
 cudaError_t launch_gemm_tcgen05(const __half* a, const __half* w, void* c, bool out_f16, int M,
                                 int N, int K, const GemmEpilogue& epi, cudaStream_t stream);
 // weight gradient: dw[C_out, C_in] (fp32, zeroed) += dy[rows, C_out]^T @ act[rows, C_in] (fp16, row-major)
-cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float* dw, int rows, int C_out,
+// input gradient: d_in[rows, C_in] (fp16) = dy[rows, C_out] (fp16) @ w16[C_out, C_in] (fp16 row-major: MN-major B)
+cudaError_t launch_gemm_tcgen05_dgrad(const __half* dy, const __half* w16, __half* d_in, int rows, int C_out,
                                       int C_in, cudaStream_t stream);
+// unscale_amax != null: dy is a scaled gradient (backward.cuh); dw receives the unscaled sums
+cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float* dw, int rows, int C_out,
+                                      int C_in, cudaStream_t stream, const uint32_t* unscale_amax = nullptr);
 void set_gemm_cluster_mode(int mode);
 // at most n SMs for the bag-sized GEMMs launched by THIS host thread from now on (0 = all)
 void set_gemm_sm_cap(int n);  // debug/tuning: 22 = 2x2 clusters, 21 = 2x1, 11 = none
@@ -216,7 +223,6 @@ cudaError_t launch_ln_backward(const float* x, const float* x_add, const float* 
                                const float* dres2, float* dx, float* dgamma, float* dbeta,
                                uint32_t* amax_out, const Grid& grid, int D, cudaStream_t stream);
 cudaError_t launch_wt_convert(const float* w, __half* wT, int N, int K, cudaStream_t stream);
-cudaError_t launch_scale_by_inv(float* x, size_t n, const uint32_t* amax, cudaStream_t stream);
 // attention core backward: qkv/o as written by the forward, dO fp16 [R*P, D] (scaled) ->
 // dqkv fp16 [R*P, 3D] (scaled), dtaps[heads, epeg_k] += unscaled tap gradients (taps may be null)
 bool rmsa_attention_bwd_supported(int P, int D, int heads, int epeg_k);

@@ -209,6 +209,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
   return d;
 }
 constexpr uint32_t kIdescMnMajorAB = (1u << 15) | (1u << 16);  // a_major = b_major = MN
+constexpr uint32_t kIdescMnMajorB = 1u << 16;                  // b_major = MN, A stays K-major
 
 // kind::tf32 / kind::f16 instruction descriptor: fp32 accumulate, both operands K-major
 enum UmmaFmt { kFmtF16 = 0, kFmtBF16 = 1, kFmtTF32 = 2 };

@@ -6,7 +6,7 @@ import torch
 from rrt_mil_b200 import cabi, RRTEncoder
 import gpu_util as G
 m = RRTEncoder(need_init=True).cuda().eval()
-x = torch.randn(9000, 512, device="cuda")
+x = torch.randn(int(sys.argv[1]) if len(sys.argv) > 1 else 9000, 512, device="cuda")
 def probe(tag, fn, n=10):
     with torch.no_grad():
         for _ in range(3): fn()
