@@ -2,20 +2,12 @@
 # scratch driver for one gpurun call (edited per call)
 cd "$(dirname "$0")/.."
 O=gpurun_out
-T=${TAG:-r02f}
-timeout 900 python -m pytest tests -x -q -m gpu > $O/${T}_tests.log 2>&1; echo "tests rc=$?"; tail -2 $O/${T}_tests.log
-timeout 600 python bench.py > $O/${T}_bench_default.json 2> $O/${T}_bench_default.err; echo "bench rc=$?"
-timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > $O/${T}_bench_reference_arm.json 2> $O/${T}_bench_reference_arm.err; echo "ref rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file $O/${T}_launches_default.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train --no-workloads > $O/${T}_ncu_b.log 2>&1
-timeout 600 ncu --set full --clock-control none -s 14 -c 7 -o $O/${T}_fwd_full -f python tools/one_bag.py 3 > $O/${T}_ncu_full.log 2>&1; tail -1 $O/${T}_ncu_full.log
-python tools/ncu_summary.py $O/${T}_fwd_full.ncu-rep $O/${T}_ncu_full_summary.csv > /dev/null 2>&1
-ls -la $O/${T}_*
-python - <<'PY'
+for occ in 1 2; do
+RRT_CRB_OCC=$occ timeout 600 python bench.py --no-cpu-baseline --no-workloads --steps 3 > $O/c15_occ$occ.json 2>/dev/null
+python - <<PY
 import json
-d=json.loads(open('gpurun_out/r02f_bench_default.json').read().strip().splitlines()[-1])
-print(d['value'], d['us_per_bag'], d['e2e']['value'], d['roofline']['kernel'], d['roofline']['frac'], d['roofline']['encoder']['frac'], d['clocks'])
-print(d['stages_us_per_launch'])
-print(json.dumps(d.get('train_step'))[:700])
-r=json.loads(open('gpurun_out/r02f_bench_reference_arm.json').read().strip().splitlines()[-1])
-print({k:r[k] for k in ('value','ms_per_step','cpu_baseline') if k in r})
+d=json.loads(open('gpurun_out/c15_occ$occ.json').read().strip().splitlines()[-1])
+print('occ', $occ, d['train_step']['stages_us_per_step']['bwd_crmsa'], d['train_step']['us_per_bag_fwd_bwd'])
 PY
+done
+RRT_CRB_OCC=2 timeout 600 python -m pytest tests/test_gpu_backward.py -x -q -m gpu 2>&1 | tail -2
