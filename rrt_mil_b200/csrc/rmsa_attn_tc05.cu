@@ -166,6 +166,7 @@ struct AttnTcParams {
   int P, P16, heads, D, epeg_k, pad, nkc, q_rows, ntail, n_items;
   int kv_stages, q_stages;                 // ring depths (3 / 2 when shared memory allows)
   int tail_helpers, epeg_helpers;          // 2 + 5 dedicated warps (<= 2 tail tiles per item), else all 7 do both
+  int tail_part;                           // min(ntail, tail_helpers): tail helpers that work on any one item
   int sep_o;                               // 1: O | l in columns of their own (P16 <= 160): S of item n + 2 is issued
                                            // right behind O of item n instead of after its epilogue
   uint32_t slot_stride, o_off;             // TMEM columns of one warpgroup's slot: S, P at 0; O | l at o_off
@@ -360,13 +361,13 @@ rmsa_attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     prefetch_tensormap(&tmO);
     for (int i = 0; i < 3; ++i) {
       mbar_init(&bars[kKvFull + i], 1);
-      mbar_init(&bars[kKvEmpty + i], 1 + p.tail_helpers);   // O of the item committed + every tail helper past its tiles
+      mbar_init(&bars[kKvEmpty + i], 1 + p.tail_part);   // O of the item committed + the tail helpers that have a tile of it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[kQFull + i], 1);
       mbar_init(&bars[kQEmpty + i], p.epeg_helpers);
       mbar_init(&bars[kQpFull + i], p.epeg_helpers);
-      mbar_init(&bars[kQpEmpty + i], 1 + p.tail_helpers);   // S of the item committed + tail helpers have their A fragments
+      mbar_init(&bars[kQpEmpty + i], 1 + p.tail_part);   // S of the item committed + those tail helpers have their A fragments
       mbar_init(&bars[kSFull + i], 1);
       mbar_init(&bars[kPReady + i], 4);
       mbar_init(&bars[kOFull + i], 1);
@@ -396,7 +397,32 @@ rmsa_attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const uint32_t idesc_o = idesc_f16(128, HD + 16, 1);
       const uint32_t ones_a = smem_u32(sOnes);
       const int ksteps = P16 / 16;
-      int nlq = 0, nlk = 0;
+      // Start-up: this thread requests item 0 only; the first fill of the other ring slots (items 1 .. stages - 1)
+      // is issued by the first tail helper, which has nothing to do until the first S operands exist.  The single
+      // issuing thread needs ~800 cycles per TMA request with cold code: eight of them in front of the first S held
+      // it 2.6 k cycles behind its operands (tools/attn_probe.py --trace).
+      int nlq = total < QS ? total : QS, nlk = total < KS ? total : KS;
+      // (region, head) of the next Q / K|V request, advanced by one grid stride per item: no divisions in the loop
+      const int d_rho = step / p.heads, d_h = step - d_rho * p.heads;
+      int rho_q, h_q, rho_k, h_k;
+      {
+        const int iq = first + nlq * step, ik = first + nlk * step;
+        rho_q = iq / p.heads; h_q = iq - rho_q * p.heads;
+        rho_k = ik / p.heads; h_k = ik - rho_k * p.heads;
+      }
+      // ring stage / phase of the next request (sq, uq | sk, uk), of the item whose O is next (so) and of the item
+      // whose S is next (ss, us): counters instead of runtime % and / by the ring depths
+      int sq = nlq == QS ? 0 : nlq, uq = nlq == QS ? 1 : 0;
+      int sk = nlk == KS ? 0 : nlk, uk = nlk == KS ? 1 : 0;
+      int so = 0, ss = 0, us = 0;
+      if (total > 0) {
+        const int rho = first / p.heads, h = first - rho * p.heads;
+        mbar_arrive_expect_tx(&bars[kQFull], p.q_bytes);
+        tma_load_3d(sQraw, &tmQ, &bars[kQFull], h * HD, -p.pad, rho);
+        mbar_arrive_expect_tx(&bars[kKvFull], 2 * p.kv_bytes);
+        tma_load_3d(sK, &tmKV, &bars[kKvFull], p.D + h * HD, 0, rho);
+        tma_load_3d(sV, &tmKV, &bars[kKvFull], 2 * p.D + h * HD, 0, rho);
+      }
       for (int j = 0; j < total + 2; ++j) {   // step j: O of item j - 2, loads, S of item j
         const int n = j - 2;
         if (n >= 0) {
@@ -410,20 +436,23 @@ rmsa_attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const uint32_t tO = tP + p.o_off;
           // O | l = P [V | 1]: the second 64-column chunk of every K step is the same 2 KB tile of ones (LBO is
           // per descriptor), operands advance by constants
-          uint32_t va = smem_u32(sV + (size_t)(n % KS) * p.kv_bytes), ta = tP;
+          uint32_t va = smem_u32(sV + (size_t)so * p.kv_bytes), ta = tP;
           for (int ks = 0; ks < ksteps; ++ks) {
             umma_f16_ts(tO, ta, umma_desc_v_sw128(va, ones_a - va), idesc_o, ks != 0);
             va += 2048;
             ta += 8;
           }
           umma_commit(&bars[kOFull + slot]);
-          umma_commit(&bars[kKvEmpty + n % KS]);  // K and V of this stage are consumed (by the tensor core)
+          umma_commit(&bars[kKvEmpty + so]);  // K and V of this stage are consumed (by the tensor core)
+          if (++so == KS) so = 0;
           stamp2(p, 16, n, 2);
         }
         // S of item j goes out right behind O of item j - 2 when its operands were requested in an earlier step
         // (the usual case from j = 2 on); otherwise the loads first.  (One code copy of each: the flag only
         // orders the two sections.)
-        const bool s_first = j < total && nlq > j && nlk > j;
+        // (step 0 keeps the loads first: nothing can be requested yet, but the section's first, instruction-cache-cold
+        // pass costs ~2 k cycles, and there it runs while the first EPEG is still in progress)
+        const bool s_first = j > 0 && j < total && nlq > j && nlk > j;
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
           if ((pass == 0) == s_first) {
@@ -433,39 +462,64 @@ rmsa_attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
               // this S: same issuing thread, in order; every softmax thread has read S: p_ready)
               if (n >= 0 && !p.sep_o) mbar_wait_c(&bars[kODone + (n & 1)], (n >> 1) & 1);
               if (n >= 0) stamp2(p, 16, n, 3);
+              if (j < 2) stamp2(p, 24, j, 0);
               mbar_wait_c(&bars[kQpFull + (j & 1)], (j >> 1) & 1);
-              mbar_wait_c(&bars[kKvFull + j % KS], (j / KS) & 1);
+              if (j < 2) stamp2(p, 24, j, 1);
+              mbar_wait_c(&bars[kKvFull + ss], us);
+              if (j < 2) stamp2(p, 24, j, 2);
               tc_fence_after();
               const uint64_t ad = umma_desc_k_sw128(smem_u32(sQp + (size_t)(j & 1) * p.qp_bytes));
-              const uint64_t kd = umma_desc_k_sw128(smem_u32(sK + (size_t)(j % KS) * p.kv_bytes));
+              const uint64_t kd = umma_desc_k_sw128(smem_u32(sK + (size_t)ss * p.kv_bytes));
+              if (++ss == KS) { ss = 0; us ^= 1; }
               const uint32_t tS = tmem_base + (uint32_t)(j & 1) * p.slot_stride;
 #pragma unroll
               for (int k = 0; k < HD / 16; ++k) umma_f16(tS, ad + 2 * k, kd + 2 * k, idesc_s, k != 0);
               umma_commit(&bars[kSFull + (j & 1)]);
               umma_commit(&bars[kQpEmpty + (j & 1)]);  // the S product has read rows 0..127 of Q'
+              if (j < 2) stamp2(p, 24, j, 3);
               if (n >= 0) stamp2(p, 16, n, 4);
             }
           } else {
             // loads: those of item j must go out now (S of item j is next: wait for the ring slot if need be);
-            // further ahead only into ring slots that are free already, so that a slow tail never blocks the MMAs
-            while (nlq < total && nlq <= j + QS) {
-              const int st = nlq % QS, u = nlq / QS;
-              if (nlq <= j) mbar_wait_c(&bars[kQEmpty + st], (u & 1) ^ 1);
-              else if (!mbar_test(&bars[kQEmpty + st], (u & 1) ^ 1)) break;
-              const int item = first + nlq * step, rho = item / p.heads, h = item - rho * p.heads;
-              mbar_arrive_expect_tx(&bars[kQFull + st], p.q_bytes);
-              tma_load_3d(sQraw + (size_t)st * p.q_bytes, &tmQ, &bars[kQFull + st], h * HD, -p.pad, rho);
-              ++nlq;
-            }
-            while (nlk < total && nlk <= j + KS) {
-              const int st = nlk % KS, u = nlk / KS;
-              if (nlk <= j) mbar_wait_c(&bars[kKvEmpty + st], (u & 1) ^ 1);
-              else if (!mbar_test(&bars[kKvEmpty + st], (u & 1) ^ 1)) break;
-              const int item = first + nlk * step, rho = item / p.heads, h = item - rho * p.heads;
-              mbar_arrive_expect_tx(&bars[kKvFull + st], 2 * p.kv_bytes);
-              tma_load_3d(sK + (size_t)st * p.kv_bytes, &tmKV, &bars[kKvFull + st], p.D + h * HD, 0, rho);
-              tma_load_3d(sV + (size_t)st * p.kv_bytes, &tmKV, &bars[kKvFull + st], 2 * p.D + h * HD, 0, rho);
-              ++nlk;
+            // further ahead only into ring slots that are free already, so that a slow tail never blocks the MMAs.
+            // Item by item (Q, then K | V of the same item): at kernel start every CTA requests up to three items
+            // at once (21 MB over the chip), and the first S waits for whatever was queued ahead of its K tile
+            for (;;) {
+              const bool q_ok = nlq < total && nlq <= j + QS, k_ok = nlk < total && nlk <= j + KS;
+              const bool q_turn = q_ok && (nlq <= nlk || !k_ok);
+              bool did = false;
+              if (q_turn) {
+                const int st = sq;
+                bool go = true;
+                if (nlq <= j) mbar_wait_c(&bars[kQEmpty + st], uq ^ 1);
+                else go = mbar_test(&bars[kQEmpty + st], uq ^ 1);
+                if (go) {
+                  mbar_arrive_expect_tx(&bars[kQFull + st], p.q_bytes);
+                  tma_load_3d(sQraw + (size_t)st * p.q_bytes, &tmQ, &bars[kQFull + st], h_q * HD, -p.pad, rho_q);
+                  ++nlq;
+                  if (++sq == QS) { sq = 0; uq ^= 1; }
+                  rho_q += d_rho; h_q += d_h;
+                  if (h_q >= p.heads) { h_q -= p.heads; ++rho_q; }
+                  did = true;
+                }
+              }
+              if (!did && k_ok) {
+                const int st = sk;
+                bool go = true;
+                if (nlk <= j) mbar_wait_c(&bars[kKvEmpty + st], uk ^ 1);
+                else go = mbar_test(&bars[kKvEmpty + st], uk ^ 1);
+                if (go) {
+                  mbar_arrive_expect_tx(&bars[kKvFull + st], 2 * p.kv_bytes);
+                  tma_load_3d(sK + (size_t)st * p.kv_bytes, &tmKV, &bars[kKvFull + st], p.D + h_k * HD, 0, rho_k);
+                  tma_load_3d(sV + (size_t)st * p.kv_bytes, &tmKV, &bars[kKvFull + st], 2 * p.D + h_k * HD, 0, rho_k);
+                  ++nlk;
+                  if (++sk == KS) { sk = 0; uk ^= 1; }
+                  rho_k += d_rho; h_k += d_h;
+                  if (h_k >= p.heads) { h_k -= p.heads; ++rho_k; }
+                  did = true;
+                }
+              }
+              if (!did) break;
             }
             if (n >= 0) stamp2(p, 16, n, 5);
           }
@@ -486,9 +540,26 @@ rmsa_attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int ntiles = P16 / 16;
     int cur_h = -1;
     uint32_t ca01[2][4];
+    if (w == 0 && lane == 0) {   // first fill of ring slots 1 .. (see the issuer's start-up)
+      for (int i = 1; i < total && (i < QS || i < KS); ++i) {
+        const int item = first + i * step, rho = item / p.heads, h = item - rho * p.heads;
+        if (i < QS) {
+          mbar_arrive_expect_tx(&bars[kQFull + i], p.q_bytes);
+          tma_load_3d(sQraw + (size_t)i * p.q_bytes, &tmQ, &bars[kQFull + i], h * HD, -p.pad, rho);
+        }
+        if (i < KS) {
+          mbar_arrive_expect_tx(&bars[kKvFull + i], 2 * p.kv_bytes);
+          tma_load_3d(sK + (size_t)i * p.kv_bytes, &tmKV, &bars[kKvFull + i], p.D + h * HD, 0, rho);
+          tma_load_3d(sV + (size_t)i * p.kv_bytes, &tmKV, &bars[kKvFull + i], 2 * p.D + h * HD, 0, rho);
+        }
+      }
+    }
     for (int stp = 0; stp < total + 2; ++stp) {   // step: tail rows of item stp - 2, then EPEG of item stp
       const int n = stp - 2;
-      if (n >= 0 && does_tail) {
+      // Only the helpers that own a tail tile of item n take part in its hand-offs (min(ntail, tail_helpers) of them:
+      // the barrier counts).  When every tail helper had to arrive for every item, the one busy with the 7 k-cycle tail
+      // of item n - 1 held the Q' buffer and the K | V stage of item n (and with them EPEG and S of item n + 2).
+      if (n >= 0 && does_tail && (wt + n) % p.tail_helpers < p.ntail) {
         // both waits also order this helper's arrivals on the "empty" barriers behind the previous use of the stage
         mbar_wait_c(&bars[kQpFull + (n & 1)], (n >> 1) & 1);
         mbar_wait_c(&bars[kKvFull + n % KS], (n / KS) & 1);
@@ -795,6 +866,7 @@ cudaError_t launch_rmsa_attention_tc05(const __half* qkv, const float* taps, __h
   p.sep_o = g.sep_o;
   p.tail_helpers = g.ntail <= 2 ? 2 : kHelpers;
   p.epeg_helpers = g.ntail <= 2 ? kHelpers - 2 : kHelpers;
+  p.tail_part = g.ntail < p.tail_helpers ? g.ntail : p.tail_helpers;
   p.slot_stride = g.slot_stride; p.o_off = g.o_off; p.tmem_cols = g.tmem_cols;
   p.q_bytes = (uint32_t)g.q_rows * 128u; p.kv_bytes = (uint32_t)g.P16 * 128u; p.qp_bytes = g.qp_bytes;
   p.qscale = 1.4426950408889634f / sqrtf((float)HD);

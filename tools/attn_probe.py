@@ -92,6 +92,10 @@ with torch.no_grad():
             r = full[16 + n].tolist()
             print(f"  issuer item {n}: " + " ".join(f"{nm}={r[i] - t0 if r[i] else -1}" for i, nm in
                   enumerate(["top", "p_ready", "o_issued", "s_go", "s_issued", "loads_done"])))
+        for n in range(2):
+            r = full[24 + n].tolist()
+            print(f"  issuer first steps j={n}: " + " ".join(f"{nm}={r[i] - t0 if r[i] else -1}" for i, nm in
+                  enumerate(["s_section", "qp_full", "kv_full", "s_issued"])))
 lib.rrt_debug_set_attention_kernel(1)
 print("FAILED" if bad else "all OK")
 sys.exit(1 if bad else 0)
