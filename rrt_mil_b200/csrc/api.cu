@@ -756,6 +756,9 @@ RRT_API int rrt_encoder_forward_batch(const rrt_config* cfg, const rrt_weights* 
   // >= 4 bags in flight: the bag-sized GEMMs keep to 64 SMs (csrc/gemm_tcgen05.cu, "SM cap")
   // (measured, us per bag: 4 lanes x 64 SMs 67.9, 8 lanes x 64 67.8, 8 lanes x 48 67.6, 8 lanes x 37 66.4)
   rrt::set_gemm_sm_cap(lanes >= 8 ? 37 : (lanes >= 4 ? 64 : 0));
+  // ... and the tcgen05 attention kernel to 64 (rmsa_attn_tc05.cu, g_attn_sm_cap: 8 lanes 61.9 -> 59.9 us per bag,
+  // 4 lanes 64.0 -> 63.0)
+  rrt::set_attn_sm_cap(lanes >= 4 ? 64 : 0);
   // programmatic dependent launch pays up to 3 bags in flight (measured, us/bag without -> with: 1 lane
   // 117.0 -> 96.9, 2 lanes 77.9 -> 72.1, 3 lanes 76.2 -> 72.9) and costs a little from 4 on (68.0 -> 69.2)
   PdlScope pdl(lanes <= 3 && !g_timing.load(std::memory_order_relaxed));
@@ -767,6 +770,7 @@ RRT_API int rrt_encoder_forward_batch(const rrt_config* cfg, const rrt_weights* 
     if (rc) break;
   }
   rrt::set_gemm_sm_cap(0);
+  rrt::set_attn_sm_cap(0);
   for (int l = 1; l < lanes; ++l) {  // always join, also on error, so `stream` stays ordered
     cudaEventRecord(lanes_p->done[l], lane_stream[l]);
     cudaStreamWaitEvent(user, lanes_p->done[l], 0);

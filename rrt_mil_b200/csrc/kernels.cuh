@@ -70,6 +70,7 @@ cudaError_t launch_gemm_tcgen05_wgrad(const __half* dy, const __half* act, float
                                       int C_in, cudaStream_t stream, const uint32_t* unscale_amax = nullptr);
 void set_gemm_cluster_mode(int mode);
 // at most n SMs for the bag-sized GEMMs launched by THIS host thread from now on (0 = all)
+void set_attn_sm_cap(int n);  // persistent-grid cap of the tcgen05 attention kernel (0 = none), per host thread
 void set_gemm_sm_cap(int n);  // debug/tuning: 22 = 2x2 clusters, 21 = 2x1, 11 = none
 extern long long* g_gemm_trace;  // debug: device buffer [8 CTAs][16] of clock64 stamps, or null
 // dst[i] = fp16(src[i]) round-to-nearest, saturating; n % 4 == 0

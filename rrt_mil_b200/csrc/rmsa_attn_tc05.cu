@@ -842,6 +842,12 @@ bool geometry(const Grid& grid, bool epeg, int epeg_k, Geometry* g) {
 // (N = 512: 8.6 vs 14.8 us -- per-item pipeline overhead with little tensor work to hide it); 2 = this kernel
 // wherever it is supported; 0 = mma.sync only
 int g_attn_tc05 = 1;
+// Persistent-grid cap of this kernel while several bags are in flight (api.cu sets it per call, per host thread).
+// With 8 bags in flight 64 CTAs x 8 items beat 128 x 4: the start-up of a CTA (first loads + first EPEG, ~6 k cycles
+// before the first S) is paid once per CTA, and the SMs left over run the other bags' kernels meanwhile.
+// Measured, us per bag, 8 lanes: no cap 61.9, 103 SMs 61.6, 86 60.7, 74 60.7, 64 59.9, 52 59.9.
+static thread_local int g_attn_sm_cap = 0;
+void set_attn_sm_cap(int n) { g_attn_sm_cap = n; }
 
 bool rmsa_attention_tc05_supported(const Grid& grid, int D, int heads, int epeg_k) {
   if (!(heads > 0 && D % heads == 0 && D / heads == HD && grid.P >= 1 && grid.P <= 256 && D % 8 == 0)) return false;
@@ -889,7 +895,9 @@ cudaError_t launch_rmsa_attention_tc05(const __half* qkv, const float* taps, __h
   // persistent grid: every CTA walks the same number of items (+-1); the smallest grid that keeps the
   // number of rounds of a full-chip grid leaves the remaining SMs to whatever else is in flight
   int nsm = sms[dev & 31] > 0 ? sms[dev & 31] : 148;
-  static const int cap = [] { const char* e = getenv("RRT_ATTN_SMS"); return e ? atoi(e) : 0; }();
+  // SM cap: RRT_ATTN_SMS, else what the batch entry point set for the number of bags in flight (set_attn_sm_cap)
+  static const int env_cap = [] { const char* e = getenv("RRT_ATTN_SMS"); return e ? atoi(e) : -1; }();
+  const int cap = env_cap >= 0 ? env_cap : g_attn_sm_cap;
   if (cap > 0 && cap < nsm) nsm = cap;
   const int rounds = (p.n_items + nsm - 1) / nsm;
   const int ctas = (p.n_items + rounds - 1) / rounds;

@@ -1,4 +1,9 @@
 #!/usr/bin/env bash
 cd "$(dirname "$0")/.."
-./tools/micro/mbar_racecheck
-timeout 120 compute-sanitizer --tool racecheck ./tools/micro/mbar_racecheck > gpurun_out/c22_mbar_racecheck.log 2>&1; tail -12 gpurun_out/c22_mbar_racecheck.log
+run() { echo -n "$* : "; env "$@" timeout 120 python tools/lanes_sweep.py 4 2>&1 | tail -1; }
+echo -n "default: "; timeout 120 python tools/lanes_sweep.py 1 8 2>&1 | tail -1
+run RRT_ATTN_SMS_4=0
+run RRT_ATTN_SMS_4=64
+run RRT_ATTN_SMS_4=86
+run RRT_ATTN_SMS_4=103
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_graph.py -x -q -m gpu 2>&1 | tail -2
