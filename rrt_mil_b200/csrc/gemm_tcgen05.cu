@@ -1285,8 +1285,13 @@ cudaError_t launch_mode(const __half* a, const __half* w, const Tc05Params& p, c
     return launch_cfg<MODE, 128, OutT, 1, 1>(a, w, p, stream);
   if (MODE == kEpiStoreAct) return launch_cfg<MODE, 256, OutT, 1, 1>(a, w, p, stream);  // no tuning variants
   // (the residual epilogues exist for the single-CTA kernel only: their cp.async ring follows its tile schedule)
-  if constexpr (!is_resid_mode(MODE) && MODE != kEpiStoreAct)
-    if (g_gemm_pair && tiles_m >= 2) return launch_pair<MODE, OutT>(a, w, p, stream);
+  // CTA pairs also whenever the SM cap is on (several bags in flight: SM time is what counts there, and a pair moves
+  // 512 KB instead of 768 KB per tile through each SM's shared memory): 8 lanes 59.9 -> 59.2 us per bag.  A single bag
+  // keeps the single-CTA kernel (20.9 vs 23.0 us: cluster set-up and the longer tail at 3 tiles per CTA).
+  if constexpr (!is_resid_mode(MODE) && MODE != kEpiStoreAct) {
+    static const bool pair_capped = [] { const char* e = getenv("RRT_GEMM_PAIR_CAPPED"); return !(e && atoi(e) == 0); }();
+    if ((g_gemm_pair || (pair_capped && g_gemm_sm_cap > 0)) && tiles_m >= 2) return launch_pair<MODE, OutT>(a, w, p, stream);
+  }
   // bag-sized problems: clusters with multicast operand tiles when the tile grid allows it
   if (g_gemm_cluster == 22 && tiles_m >= 2 && tiles_n256 >= 2 && tiles_n256 % 2 == 0)
     return launch_cfg<MODE, 256, OutT, 2, 2>(a, w, p, stream);
