@@ -123,17 +123,39 @@ __device__ __forceinline__ void red_add4(__half*, size_t, float4) {}
 // warp's ring.  Every 16-byte piece is written and later read by the SAME thread (row group i -> row 4i + lane / 8,
 // columns 4 * (lane % 8)): no cross-thread synchronisation, only cp.async.wait_group.  One commit group per call
 // (empty past the last chunk), so that wait_group<kResidRing - 1> always means "the chunk being consumed has landed".
-// (one copy of the three integer divisions: inlined at its four call sites they were 3.4 k of the kernel's SASS)
-// (scalars by value: a reference to the Grid inside the kernel parameters would put a copy of them on the stack)
-__device__ __noinline__ int resid_token_of_slot_(int slot, int M, int P, int g, int rs, int H, int L) {
-  if (slot >= M) return -1;
-  Grid gr;
-  gr.P = P; gr.g = g; gr.rs = rs; gr.H = H; gr.L = L;
-  const int t = gr.slot_to_token(slot);
-  return t < L ? t : -1;
+// Region slot -> token row for the 8 row groups of a lane (slots first, first + 4, ..., first + 28; -1 = pad slot or
+// outside the bag).  The three integer divisions of Grid::slot_to_token are paid ONCE (out of line: inlined at every
+// call site they were 3.4 k of the kernel's SASS); the other seven rows follow by stepping (region, row, column)
+// with carries.  With eight full conversions per tile in the cursor and eight more at the top of the epilogue a tile
+// cost ~8 k cycles of divisions on the epilogue warps' critical path (tools/gemm_trace.py under the SM cap).
+struct SlotPos { int rr, rc, pr, pc; };
+__device__ __noinline__ SlotPos resid_slot_pos(int slot, int P, int g, int rs) {
+  SlotPos s;
+  const int rho = slot / P, p = slot - rho * P;
+  s.rr = rho / g; s.rc = rho - s.rr * g;
+  s.pr = p / rs;  s.pc = p - s.pr * rs;
+  return s;
 }
+__device__ __forceinline__ void resid_tokens8(const Grid& g, int first, int M, int (&tok)[8]) {
+  SlotPos s = resid_slot_pos(first, g.P, g.g, g.rs);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int t = (s.rr * g.rs + s.pr) * g.H + s.rc * g.rs + s.pc;
+    tok[i] = (first + 4 * i < M && t < g.L) ? t : -1;
+    s.pc += 4;
+    while (s.pc >= g.rs) { s.pc -= g.rs; ++s.pr; }
+    while (s.pr >= g.rs) {
+      s.pr -= g.rs;
+      if (++s.rc == g.g) { s.rc = 0; ++s.rr; }
+    }
+  }
+}
+// single slot (the row-statistics record of a thread's row)
 __device__ __forceinline__ int resid_token_of_slot(const Grid& g, int slot, int M) {
-  return resid_token_of_slot_(slot, M, g.P, g.g, g.rs, g.H, g.L);
+  if (slot >= M) return -1;
+  const SlotPos s = resid_slot_pos(slot, g.P, g.g, g.rs);
+  const int t = (s.rr * g.rs + s.pr) * g.H + s.rc * g.rs + s.pc;
+  return t < g.L ? t : -1;
 }
 
 template <int BN>
@@ -148,10 +170,7 @@ struct ResidCursor {
     if (wt >= num_work) return;
     const int m0 = ((wt / tiles_nc) * CM + ci) * BM;
     n0 = ((wt % tiles_nc) * CN + cj) * BN;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      tok[i] = resid_token_of_slot(p.grid, m0 + quad * 32 + 4 * i + (lane >> 3), p.M);
-    }
+    resid_tokens8(p.grid, m0 + quad * 32 + (lane >> 3), p.M, tok);
   }
   __device__ __forceinline__ void issue(const Tc05Params& p, int ew, int lane) {
     if (wt < num_work) {
@@ -189,8 +208,7 @@ __device__ __forceinline__ void epilogue_tile_resid(const Tc05Params& p, uint32_
   const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
   // output row of each of the 8 row groups this lane stores (region slot -> token; -1: pad row)
   int orow[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) orow[i] = resid_token_of_slot(p.grid, m0 + quad * 32 + 4 * i + sub_r, p.M);
+  resid_tokens8(p.grid, m0 + quad * 32 + sub_r, p.M, orow);
   // row statistics of the rows being written (thread = row `lane` of this warp's 32): sum, sum of squares and up
   // to four dot products with gamma (.) phi[:, n] over this warp's NC * 32 columns
   float rs_sum = 0.f, rs_sq = 0.f, rs_dot[4] = {0.f, 0.f, 0.f, 0.f};
