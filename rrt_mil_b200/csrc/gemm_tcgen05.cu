@@ -406,33 +406,26 @@ __device__ __forceinline__ void epilogue_tile_store_act(const Tc05Params& p, con
 
 // Epilogue of one 128 x BN accumulator for one of the 8 epilogue warps (two per TMEM lane quadrant):
 // software-pipelined tcgen05.ld, accumulator released (release()) as soon as this warp's slice is in
-// registers, then either TMA tile stores (kEpiStore) or transpose + st.global (tanh / residual scatter).
+// registers, then either TMA tile stores (kEpiStore) or transpose + st.global (tanh, split-K reduction).  The
+// residual-scatter modes have their own epilogue (epilogue_tile_resid) and the activation-store mode too.
 template <int MODE, int BN, typename OutT, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtensorMap* tmC,
                                               uint32_t tmem_acc, uint64_t* tfull_bar,
                                               uint32_t tfull_parity, int m0, int n0, int ew, int lane,
                                               float* scratch, bool first, ReleaseFn release) {
+  static_assert(!is_resid_mode(MODE), "residual modes: epilogue_tile_resid");
   constexpr bool kTmaStore = is_store_mode(MODE);
   constexpr int NC = (BN / 32) / 2;  // chunks per epilogue warp
   const int quad = ew & 3;           // TMEM lanes [32*quad, 32*quad+32) are readable by this warp
   const int c_begin = (ew >> 2) * NC;
   OutT* const out = reinterpret_cast<OutT*>(p.C);
   const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
-    // output row of each of the 8 row groups this lane stores (mode 2: region slot -> token)
-    long long orow[8];
+    // output row of each of the 8 row groups this lane stores (-1: outside the matrix)
+    int orow[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      int gr = m0 + quad * 32 + 4 * i + sub_r;
-      long long o = -1;
-      if (gr < p.M) {
-        if (is_resid_mode(MODE)) {
-          int tok = p.grid.slot_to_token(gr);
-          if (tok < p.grid.L) o = tok;
-        } else {
-          o = gr;
-        }
-      }
-      orow[i] = o;
+      const int gr = m0 + quad * 32 + 4 * i + sub_r;
+      orow[i] = gr < p.M ? gr : -1;
     }
     // TMA-store mode: thread = row needs the bias of all 32 columns of a chunk; lane l keeps
     // column l of every chunk and the value is broadcast with a shuffle when used
@@ -453,39 +446,12 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float4 v[8];
-    auto load_resid = [&](int j) {  // residual rows of chunk j: eight independent 16-byte loads
-      const int gc = n0 + (c_begin + j) * 32 + sub_c;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (orow[i] >= 0 && gc < p.N)
-          v[i] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)orow[i] * p.N + gc));
-      }
-    };
-    if (is_resid_mode(MODE)) {
-      load_resid(0);
-      // the residual rows of the later chunks: pull them into L2 while the MMA warp is still busy, so
-      // that the per-chunk loads below are L2 hits instead of NC serial HBM round trips
-      if ((lane & 7) == 0) {
-#pragma unroll
-        for (int j = 1; j < NC; ++j) {
-          const int gc = n0 + (c_begin + j) * 32;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (orow[i] >= 0 && gc < p.N) prefetch_l2(p.resid + (size_t)orow[i] * p.N + gc);
-        }
-      }
-    }
     mbar_wait(tfull_bar, tfull_parity);
     tc_fence_after();
     if (first && threadIdx.x == 128) stamp(p, 6);
     const uint32_t t_addr = tmem_acc + ((uint32_t)(quad * 32) << 16) + c_begin * 32;
     uint32_t r[2][32];
     tmem_ld_32x32(t_addr, r[0]);
-    // row statistics of the rows being written (thread = row `lane` of this warp's 32): sum, sum of squares
-    // and up to four dot products with gamma (.) phi[:, n] over this warp's NC * 32 columns
-    float rs_sum = 0.f, rs_sq = 0.f, rs_dot[4] = {0.f, 0.f, 0.f, 0.f};
-    const bool row_stats = is_resid_mode(MODE) && p.rs_part != nullptr;
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
       tmem_ld_wait();  // chunk j is in registers
@@ -572,18 +538,9 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
         const int rl = 4 * i + sub_r;
         float4 a = *reinterpret_cast<const float4*>(scratch + rl * EPI_LD +
                                                     4 * ((lane & 7) ^ (rl & 7)));
-        if (MODE == kEpiResidualUnpartDrop) {  // x1 = x + dropout(o Wp^T + b)   (modules/rmsa.py:131-132)
-          float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (orow[i] >= 0) m = dropout_scale4(p.drop, (unsigned long long)orow[i] * p.N + gc);
-          v[i].x = fmaf(a.x + bv.x, m.x, v[i].x); v[i].y = fmaf(a.y + bv.y, m.y, v[i].y);
-          v[i].z = fmaf(a.z + bv.z, m.z, v[i].z); v[i].w = fmaf(a.w + bv.w, m.w, v[i].w);
-        } else if (is_resid_mode(MODE)) {
-          v[i].x += a.x + bv.x; v[i].y += a.y + bv.y; v[i].z += a.z + bv.z; v[i].w += a.w + bv.w;
-        } else {
-          v[i] = make_float4(a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w);
-          if (MODE == kEpiTanh)
-            v[i] = make_float4(tanhf(v[i].x), tanhf(v[i].y), tanhf(v[i].z), tanhf(v[i].w));
-        }
+        v[i] = make_float4(a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w);
+        if (MODE == kEpiTanh)
+          v[i] = make_float4(tanhf(v[i].x), tanhf(v[i].y), tanhf(v[i].z), tanhf(v[i].w));
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -598,61 +555,12 @@ __device__ __forceinline__ void epilogue_tile(const Tc05Params& p, const CUtenso
           else store_out4(out, (size_t)orow[i] * p.N + gc, v[i]);
         }
       if (first && threadIdx.x == 128 && j < 2) stamp(p, 12 + 3 * j);
-      if (is_resid_mode(MODE) && row_stats) {
-        // hand the finished values back through the scratch tile (same swizzled slots they were read from)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = 4 * i + sub_r;
-          *reinterpret_cast<float4*>(scratch + rl * EPI_LD + 4 * ((lane & 7) ^ (rl & 7))) = v[i];
-        }
-        __syncwarp();
-      }
-      if (is_resid_mode(MODE) && j + 1 < NC) load_resid(j + 1);  // next chunk's residual rows
-      if (is_resid_mode(MODE) && row_stats) {
-        // lane c keeps gamma_c * phi[c, 0..3] of column c of this chunk; the row pass broadcasts them by shuffle
-        const int gcl = n0 + (c_begin + j) * 32 + lane;
-        const float gm = __ldg(p.rs_gamma + gcl);
-        float gq[4];
-        if (p.rs_k == 4) {
-          const float4 ph = __ldg(reinterpret_cast<const float4*>(p.rs_phi) + gcl);
-          gq[0] = gm * ph.x; gq[1] = gm * ph.y; gq[2] = gm * ph.z; gq[3] = gm * ph.w;
-        } else {
-#pragma unroll
-          for (int n = 0; n < 4; ++n) gq[n] = n < p.rs_k ? gm * __ldg(p.rs_phi + (size_t)gcl * p.rs_k + n) : 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 xv = *reinterpret_cast<const float4*>(scratch + lane * EPI_LD + 4 * (q ^ (lane & 7)));
-          rs_sum += (xv.x + xv.y) + (xv.z + xv.w);
-          rs_sq = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, fmaf(xv.z, xv.z, fmaf(xv.w, xv.w, rs_sq))));
-          const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-#pragma unroll
-            for (int n = 0; n < 4; ++n)
-              rs_dot[n] = fmaf(xe[e], __shfl_sync(0xffffffffu, gq[n], 4 * q + e), rs_dot[n]);
-        }
-      }
       __syncwarp();
       }  // !kTmaStore
     }
     if (kTmaStore) {  // both staging buffers are free again before the next tile reuses them
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();
-    }
-    if (is_resid_mode(MODE) && row_stats) {
-      // one 32-byte record per (token, 128-column part): [sum, sum sq, dot_0..3, -, -]
-      const int gr = m0 + quad * 32 + lane;
-      if (gr < p.M) {
-        const int tok = p.grid.slot_to_token(gr);
-        if (tok < p.grid.L) {
-          constexpr int PW = NC * 32;  // columns per part
-          const int parts = p.N / PW, part = (n0 + c_begin * 32) / PW;
-          float4* rec = reinterpret_cast<float4*>(p.rs_part + ((size_t)tok * parts + part) * 8);
-          rec[0] = make_float4(rs_sum, rs_sq, rs_dot[0], rs_dot[1]);
-          rec[1] = make_float4(rs_dot[2], rs_dot[3], 0.f, 0.f);
-        }
-      }
     }
 }
 
