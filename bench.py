@@ -444,7 +444,8 @@ def run_b200_arm(args):
             "time_share": stage_share[dom], "peak_source": peaks["source"],
             "how": "CUDA events recorded by the library around the kernel on its launching stream, bags back to "
                    "back (lanes=1, every GEMM on all SMs); the interval includes the launch gap.  In the timed "
-                   "region the bag-sized GEMMs run under an SM cap (37 SMs with 8 bags in flight), so the "
+                   "region the bag-sized GEMMs run under an SM cap (37 SMs with 8 bags in flight; the QKV GEMM as CTA pairs) "
+                   "and the attention kernel on a 64-SM persistent grid, so the "
                    "honest whole-step figure is roofline.encoder"}
     tr_file = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes/launch from ncu --set full
     if os.path.isfile(tr_file):
