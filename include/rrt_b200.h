@@ -302,8 +302,9 @@ RRT_API int rrt_attn_pool_forward(const float* h, int64_t L, int32_t dim, int32_
  * rrt_encoder_forward_train computes exactly what rrt_encoder_forward computes and keeps, in the
  * caller-owned `tape` (rrt_train_tape_bytes), what the backward pass re-reads: per R-MSA layer the
  * LayerNorm output, q/k/v, the attention output (fp16) and the layer output (fp32); for CR-MSA the
- * logits, min/max, landmarks and the landmark MHA's q/k/v, o and output.  The attention
- * probabilities are recomputed.  rrt_encoder_backward takes d(loss)/d(out) and writes d(loss)/dx and
+ * logits, min/max, landmarks and the landmark MHA's q/k/v, o and output; and, when the caller passes
+ * no fp16 weight shadows, the fp16 copies of the GEMM weights the forward made (the backward's
+ * input-gradient GEMMs read them as they are).  The attention probabilities are recomputed.  rrt_encoder_backward takes d(loss)/d(out) and writes d(loss)/dx and
  * every parameter gradient.  Gradient buffers follow rrt_weights (same shapes, fp32) and MUST be
  * zero-initialised by the caller (bias / LayerNorm / tap / phi gradients are accumulated with
  * atomics; weight gradients are overwritten).  Tensor-core operands of the backward GEMMs are fp16
